@@ -1,0 +1,169 @@
+/*
+ * smoqyelph_b200.h -- C ABI of libsmoqyelph_b200.so
+ *
+ * B200 (sm_100a) implementation of the linear-scaling electron-phonon hot path of SmoQyElPhQMC.jl.
+ * The reference has no FFI layer: its seam is Julia multiple dispatch.  Each entry
+ * point below names the reference method (file:line under /root/reference) whose body it replaces;
+ * julia/SmoQyElPhB200.jl and INTEGRATION.md show the `ccall` binding a maintainer would add.
+ *
+ * Conventions
+ *  - Every function returns 0 on success, non-zero on failure; sq_last_error() gives the message.
+ *    The Julia shim raises on non-zero so the reference's try/catch "numerical instability =>
+ *    reject the update" semantics are preserved (src/EFAPFFHMCUpdater.jl:168-187).  CG
+ *    non-convergence is NOT an error: iters == maxiter is returned (ConjugateGradient.jl:248).
+ *  - All array arguments are dense, column-major HOST arrays owned by the caller, exactly as Julia
+ *    holds them: space-time vectors are (Ltau x N) Complex{Float64} with tau fastest; V is
+ *    (N x Ltau), t is (Nh x Ltau), x / p / dSdx are (Nph x Ltau) Float64.  Index tables are Int64
+ *    and 1-BASED (Julia's), converted inside the library.  sq_complex = interleaved (re, im).
+ *  - Entry points with the suffix _dev take DEVICE pointers in the library's internal layout
+ *    (site fastest: element (l, i) at i + l*N) and never synchronise the host; they exist for
+ *    pipelines that keep their vectors resident in HBM (bench.py `value`, multi-GPU drivers).
+ *  - Calls are blocking (stream-synchronised on return) unless suffixed _dev.  One handle is used
+ *    from one host thread at a time.  The library owns all device memory behind its handles.
+ *  - There is no CPU fallback: every entry point fails with an error if no CUDA device is usable.
+ */
+#ifndef SMOQYELPH_B200_H
+#define SMOQYELPH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } sq_complex;
+typedef struct sq_fdm sq_fdm;       /* FermionDetMatrix{T,E}      src/FermionDetMatrix.jl:19-55,137-148 */
+typedef struct sq_kpm sq_kpm;       /* KPMPreconditioner          src/KPMPreconditioner.jl:28-190        */
+typedef struct sq_elph sq_elph;     /* ElectronPhononParameters + FermionPathIntegral fields the path reads */
+typedef struct sq_pff sq_pff;       /* PFFCalculator              src/PFFCalculator.jl:9-53              */
+typedef struct sq_hmc sq_hmc;       /* EFAPFFHMCUpdater           src/EFAPFFHMCUpdater.jl:9-99           */
+typedef struct sq_greens sq_greens; /* GreensEstimator (solves + scalar measurements) src/Measurements/GreensEstimator.jl:10-175 */
+
+enum { SQ_OP_M = 0, SQ_OP_MT = 1, SQ_OP_MTM = 2, SQ_OP_MMT = 3 };
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char *sq_last_error(void);
+int sq_version(void);
+int sq_device_count(int *count);
+
+/* ---- FermionDetMatrix ------------------------------------------------------------------------ */
+/* SymFermionDetMatrix(fpi; maxiter, tol) / AsymFermionDetMatrix(...): src/FermionDetMatrix.jl:66-111,159-204.
+ * nt (2 x Nh) is the PERMUTED neighbour table, perm (Nh) maps checkerboard index -> original hopping
+ * index, color_lo/hi (ncolors) the inclusive 1-based bond ranges of each colour -- the outputs of
+ * Checkerboard.checkerboard_decomposition! (:95-97); the library never recomputes the colouring. */
+int sq_fdm_create(sq_fdm **out, int sym, int64_t Ltau, int64_t N, int64_t Nh, const int64_t *nt,
+                  const int64_t *perm, int64_t ncolors, const int64_t *color_lo, const int64_t *color_hi,
+                  double tol, int64_t maxiter, int device);
+int sq_fdm_destroy(sq_fdm *f);
+/* update!(fdm, fpi): src/FermionDetMatrix.jl:208-236.  V (N x Ltau), t (Nh x Ltau, original order). */
+int sq_fdm_update(sq_fdm *f, const double *V, const double *t, double dtau);
+/* mul_M! :385/:430, mul_Mt! :484/:528, mul_MtM! :329, mul_MMt! :357 (in == out allowed). */
+int sq_fdm_mul(sq_fdm *f, int op, sq_complex *out, const sq_complex *in);
+/* ldiv!(x, fdm, b; preconditioner, maxiter, tol): src/FermionDetMatrix.jl:248-267 + cg_solve!
+ * src/IterativeSolvers/ConjugateGradient.jl:93-249.  zero_start != 0 <=> `x === b` (x is output only).
+ * kpm may be NULL (preconditioner = I).  If kpm != NULL and lanczos_start != NULL the preconditioner is
+ * refreshed first (update_preconditioner!, KPMPreconditioner.jl:554) with that N-vector as the randn!
+ * start; lanczos_start == NULL draws it from the library's Philox stream. */
+int sq_fdm_cg(sq_fdm *f, sq_complex *x, const sq_complex *b, int zero_start, sq_kpm *kpm, int refresh_kpm,
+              const double *lanczos_start, double tol, int64_t maxiter, int64_t *iters, double *eps);
+/* read back expnΔτV (Ltau x N), coshΔτt, sinhΔτt (Ltau x Nh) in the reference's layout (tests) */
+int sq_fdm_get_coefficients(sq_fdm *f, double *expV, double *cosh_t, double *sinh_t);
+/* device-resident variants (internal layout, no host sync) */
+int sq_fdm_mul_dev(sq_fdm *f, int op, void *d_out, const void *d_in);
+int sq_fdm_cg_dev(sq_fdm *f, void *d_x, const void *d_b, int zero_start, sq_kpm *kpm, double tol,
+                  int64_t maxiter, int64_t *iters, double *eps);
+/* kernel configuration of the fused matvec (slices per CTA, threads per CTA; 0 = autotune) */
+int sq_fdm_set_tuning(sq_fdm *f, int slab, int threads);
+int sq_fdm_get_tuning(sq_fdm *f, int *slab, int *threads, int *path);
+int sq_fdm_stream(sq_fdm *f, void **cuda_stream);
+int64_t sq_fdm_launch_count(sq_fdm *f);
+
+/* ---- KPMPreconditioner ----------------------------------------------------------------------- */
+/* KPMPreconditioner(fdm; rng, rbuf, n, a1, a2): src/KPMPreconditioner.jl:198-284 (does NOT run the
+ * first update; call sq_kpm_update). */
+int sq_kpm_create(sq_kpm **out, sq_fdm *f, double rbuf, int64_t n, double a1, double a2);
+int sq_kpm_destroy(sq_kpm *k);
+/* update_preconditioner!(P, fdm, rng): :554-597.  lanczos_start: N normals (NULL = library RNG). */
+int sq_kpm_update(sq_kpm *k, const double *lanczos_start, int *active, double *bounds);
+/* test hook: refresh B-bar and force the eigenvalue bounds (identical coefficients on both sides) */
+int sq_kpm_set_bounds(sq_kpm *k, double emin, double emax);
+int sq_kpm_get_orders(sq_kpm *k, int64_t *ncoef, int64_t *orders /* may be NULL to query ncoef */);
+int sq_kpm_get_coefs(sq_kpm *k, int64_t l /* 0-based */, sq_complex *coefs);
+/* ldiv!(u', P, u) for complex vectors: Sym :355-414, Asym :488-550 */
+int sq_kpm_ldiv(sq_kpm *k, sq_complex *out, const sq_complex *in);
+int sq_kpm_ldiv_dev(sq_kpm *k, void *d_out, const void *d_in);
+/* U v / U^-1 v of FourierTransformer: src/FourierTransformer.jl:39-64 */
+int sq_kpm_fourier(sq_kpm *k, sq_complex *v, int forward);
+
+/* ---- electron-phonon model ------------------------------------------------------------------- */
+/* The arrays the path reads from SmoQyDQMC's ElectronPhononParameters / TightBindingParameters:
+ * PhononParameters Omega, Omega4, M (Nph); HolsteinParameters coupling_to_phonon, coupling_to_site,
+ * alpha..alpha4 (Nhol) and ph_sym_form expanded per coupling; SSHParameters coupling_to_phonon
+ * (2 x Nssh), the hopping each coupling modulates (inverse of hopping_to_couplings), alpha..alpha4;
+ * bare on-site energy minus mu (N) and bare hopping (Nh, original order). */
+int sq_elph_create(sq_elph **out, sq_fdm *f, double dtau, int64_t Nph, const double *Omega, const double *Omega4,
+                   const double *M, int64_t Nhol, const int64_t *hol_phonon, const int64_t *hol_site,
+                   const double *hol_a, const double *hol_a2, const double *hol_a3, const double *hol_a4,
+                   const int32_t *hol_phsym, int64_t Nssh, const int64_t *ssh_phonon, const int64_t *ssh_hopping,
+                   const double *ssh_a, const double *ssh_a2, const double *ssh_a3, const double *ssh_a4,
+                   const double *V0, const double *t0);
+int sq_elph_destroy(sq_elph *e);
+int sq_elph_set_x(sq_elph *e, const double *x);          /* (Nph x Ltau) */
+int sq_elph_get_x(sq_elph *e, double *x);
+int sq_elph_shift_mu(sq_elph *e, double dmu);             /* V += -mu' + mu: update_chemical_potential.jl:66-67 */
+/* SmoQyDQMC.update!(fpi, elph, x, +1) followed by update!(fdm, fpi) (EFAPFFHMCUpdater.jl:152-153), on device */
+int sq_elph_refresh_fdm(sq_elph *e);
+int sq_elph_get_Vt(sq_elph *e, double *V, double *t);
+int sq_elph_bosonic_action(sq_elph *e, double *Sb);
+
+/* ---- PFFCalculator --------------------------------------------------------------------------- */
+int sq_pff_create(sq_pff **out, sq_elph *e);                                   /* src/PFFCalculator.jl:30-53 */
+int sq_pff_destroy(sq_pff *p);
+int sq_pff_set_exact_holstein(sq_pff *p, int flag);    /* 0 = reference behaviour, 1 = exact derivative */
+/* sample_pseudofermion_fields!: :56-76.  R = the randn!(rng, Phi) draw (Ltau x N), NULL = library RNG. */
+int sq_pff_sample(sq_pff *p, const sq_complex *R, double *Sf);
+/* calculate_fermionic_action!: :79-116 */
+int sq_pff_action(sq_pff *p, sq_kpm *kpm, const double *lanczos_start, double tol, int64_t maxiter,
+                  double *Sf, int64_t *iters, double *eps);
+/* calculate_derivative_fermionic_action!: :119-158.  dSdx (Nph x Ltau) is accumulated into (+=). */
+int sq_pff_force(sq_pff *p, double *dSdx, sq_kpm *kpm, const double *lanczos_start, double tol, int64_t maxiter,
+                 double *Sf, int64_t *iters, double *eps);
+int sq_pff_get_fields(sq_pff *p, sq_complex *Phi, sq_complex *Psi, double *Lambda);   /* any may be NULL */
+int sq_pff_set_Phi(sq_pff *p, const sq_complex *Phi);
+/* holstein_shift_matrix.jl:47-153 on caller vectors; which: 0 mul_Λ!, 1 ldiv_Λ!, 2 mul_Λᵀ!, 3 ldiv_Λᵀ! */
+int sq_pff_lambda_op(sq_pff *p, int which, sq_complex *out, const sq_complex *in);
+/* mul_νRe∂M∂x! (fermion_det_matrix_dervative.jl:2/117) and mul_νRe∂Λ∂x! (holstein_shift_matrix.jl:156) */
+int sq_pff_dM_dx(sq_pff *p, double *F, double nu, const sq_complex *u, const sq_complex *v);
+int sq_pff_dLambda_dx(sq_pff *p, double *F, double nu, const sq_complex *up, const sq_complex *u);
+
+/* ---- EFAPFFHMCUpdater ------------------------------------------------------------------------ */
+/* EFAPFFHMCUpdater(; electron_phonon_parameters, Nt, dt, eta, delta): src/EFAPFFHMCUpdater.jl:40-72 */
+int sq_hmc_create(sq_hmc **out, sq_pff *p, int64_t Nt, double dt, double eta, double delta, uint64_t seed);
+int sq_hmc_destroy(sq_hmc *h);
+/* hmc_update!: :102-279.  randoms == NULL draws from the library's Philox stream; otherwise the
+ * stream documented in DESIGN.md (same order as oracle/ref_c.c ref_hmc_update) is consumed.
+ * info[8] = iters_avg, dH, Sf0, Sf1, Sb0, Sb1, K0, K1. */
+int sq_hmc_update(sq_hmc *h, sq_kpm *kpm, double tol_action, double tol_force, int64_t maxiter,
+                  const double *randoms, int64_t nrandoms, int *accepted, double *info);
+/* EFA pieces for parity tests: SmoQyDQMC initialize_momentum!, kinetic_energy, evolve_eom! */
+int sq_hmc_init_momentum(sq_hmc *h, const double *R, double *p, double *K);
+int sq_hmc_kinetic(sq_hmc *h, const double *p, double *K);
+int sq_hmc_evolve(sq_hmc *h, double *x, double *p, double dt);
+
+/* ---- GreensEstimator ------------------------------------------------------------------------- */
+int sq_greens_create(sq_greens **out, sq_fdm *f, int64_t Nrv, uint64_t seed);   /* GreensEstimator.jl:63-118 */
+int sq_greens_destroy(sq_greens *g);
+/* update_greens_estimator!: :125-175.  R (V x Nrv) unit-modulus vectors or NULL (library RNG);
+ * warm start from the previous GR as in the reference. */
+int sq_greens_update(sq_greens *g, sq_kpm *kpm, const sq_complex *R, double tol, int64_t maxiter, double *avg_iters);
+int sq_greens_get(sq_greens *g, sq_complex *R, sq_complex *GR);
+int sq_greens_set_GR(sq_greens *g, const sq_complex *GR);
+/* measure_n :15, measure_double_occ :112, measure_Nsqrd :31 of src/Measurements/scalar_measurements.jl */
+int sq_greens_measure(sq_greens *g, sq_complex *n, sq_complex *double_occ, sq_complex *Nsqrd);
+/* update_chemical_potential! minus the MuTuner scalar logic (stays in Julia): returns n, N^2 then
+ * applies the new mu via sq_elph_shift_mu + sq_elph_refresh_fdm.  src/update_chemical_potential.jl:21-73 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

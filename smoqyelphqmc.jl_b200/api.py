@@ -1,0 +1,417 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+Same names, argument meaning and error behaviour as the Julia package (docs/src/api.md of the
+reference), so the parity tests read like the reference's own code:
+
+    fdm  = SymFermionDetMatrix(model, maxiter=..., tol=...)      src/FermionDetMatrix.jl:66
+    elph = ElectronPhononParameters(model, fdm); elph.x = x; elph.update_fdm()
+    P    = KPMPreconditioner(fdm, rbuf=0.1, n=20, a1=1.0, a2=1.0)  src/KPMPreconditioner.jl:198
+    pff  = PFFCalculator(elph, fdm)                               src/PFFCalculator.jl:30
+    hmc  = EFAPFFHMCUpdater(elph, pff, Nt=..., dt=...)            src/EFAPFFHMCUpdater.jl:40
+    accepted, iters = hmc.hmc_update(preconditioner=P, tol_action=..., tol_force=..., maxiter=...)
+
+Every method is a thin call into the C ABI (lib.py); vectors are numpy arrays in the reference's
+layout, (Ltau, N) complex128 Fortran order.  A failed library call raises `SqError`, which callers
+treat like the reference's "numerical instability" exceptions (reject the update).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _l
+from .lib import SqError, check, ptr  # noqa: F401
+
+OP_M, OP_MT, OP_MTM, OP_MMT = 0, 1, 2, 3
+
+
+def _cvec(model, a=None):
+    out = np.zeros((model.Ltau, model.N), np.complex128, order="F")
+    if a is not None:
+        out[...] = np.asarray(a).reshape(out.shape, order="F")
+    return out
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def _i64(a, one_based=True):
+    return np.ascontiguousarray(np.asarray(a, np.int64) + (1 if one_based else 0))
+
+
+class FermionDetMatrix:
+    """FermionDetMatrix{T,E}: matrix-free M with its CG workspace (src/FermionDetMatrix.jl:19-55)."""
+
+    def __init__(self, model, sym=True, maxiter=None, tol=1e-6, device=0):
+        self.L = _l.load()
+        self.model, self.sym = model, bool(sym)
+        self.tol = tol
+        self.maxiter = int(maxiter if maxiter is not None else model.N * model.Ltau)
+        nt = _i64(model.nt_chk.T)                       # (Nh, 2) C-order == (2, Nh) column-major
+        perm = _i64(model.perm)
+        clo = _i64([c[0] for c in model.colors])         # 1-based inclusive lower bound
+        chi = _i64([c[1] - 1 for c in model.colors])     # 1-based inclusive upper bound
+        h = C.c_void_p()
+        check(self.L.sq_fdm_create(C.byref(h), int(sym), model.Ltau, model.N, model.Nh, ptr(nt), ptr(perm), len(model.colors),
+                                   ptr(clo), ptr(chi), tol, self.maxiter, device))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sq_fdm_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # update!(fdm, fpi): V (N, Ltau), t (Nh, Ltau) Fortran
+    def update(self, V, t, dtau=None):
+        V = np.asfortranarray(V, np.float64)
+        t = np.asfortranarray(t, np.float64)
+        check(self.L.sq_fdm_update(self.h, ptr(V), ptr(t), self.model.dtau if dtau is None else dtau))
+
+    def _mul(self, op, v):
+        v = _cvec(self.model, v)
+        out = _cvec(self.model)
+        check(self.L.sq_fdm_mul(self.h, op, ptr(out), ptr(v)))
+        return out
+
+    def mul_M(self, v): return self._mul(OP_M, v)
+    def mul_Mt(self, v): return self._mul(OP_MT, v)
+    def mul_MtM(self, v): return self._mul(OP_MTM, v)
+    def mul_MMt(self, v): return self._mul(OP_MMT, v)
+    mul = mul_MtM                                        # mul!(v', fdm, v) = M^T M v  (:304-315)
+
+    def ldiv(self, b, x0=None, preconditioner=None, tol=None, maxiter=None, lanczos_start=None, refresh=True):
+        """ldiv!(x, fdm, b; preconditioner, tol, maxiter) -> (x, iters, eps).  x0=None <=> x === b."""
+        b = _cvec(self.model, b)
+        zero = x0 is None
+        x = _cvec(self.model, None if zero else x0)
+        it, eps = C.c_int64(0), C.c_double(0)
+        ls = None if lanczos_start is None else _f64(lanczos_start)
+        check(self.L.sq_fdm_cg(self.h, ptr(x), ptr(b), int(zero), preconditioner.h if preconditioner is not None else None,
+                               int(refresh and preconditioner is not None), ptr(ls), self.tol if tol is None else tol,
+                               self.maxiter if maxiter is None else int(maxiter), C.byref(it), C.byref(eps)))
+        return x, it.value, eps.value
+
+    def coefficients(self):
+        m = self.model
+        e = np.zeros((m.Ltau, m.N), order="F")
+        c = np.zeros((m.Ltau, m.Nh), order="F")
+        s = np.zeros((m.Ltau, m.Nh), order="F")
+        check(self.L.sq_fdm_get_coefficients(self.h, ptr(e), ptr(c), ptr(s)))
+        return e, c, s
+
+    # device-resident entry points (internal [l][i] layout; raw device addresses, e.g. torch data_ptr())
+    def mul_dev(self, op, d_out, d_in): check(self.L.sq_fdm_mul_dev(self.h, op, ptr(d_out), ptr(d_in)))
+
+    def cg_dev(self, d_x, d_b, zero_start=True, preconditioner=None, tol=None, maxiter=None):
+        it, eps = C.c_int64(0), C.c_double(0)
+        check(self.L.sq_fdm_cg_dev(self.h, ptr(d_x), ptr(d_b), int(zero_start), preconditioner.h if preconditioner is not None else None,
+                                   self.tol if tol is None else tol, self.maxiter if maxiter is None else int(maxiter),
+                                   C.byref(it), C.byref(eps)))
+        return it.value, eps.value
+
+    @property
+    def tuning(self):
+        s, t, p = C.c_int(0), C.c_int(0), C.c_int(0)
+        check(self.L.sq_fdm_get_tuning(self.h, C.byref(s), C.byref(t), C.byref(p)))
+        return {"slab": s.value, "threads": t.value, "path": p.value}
+
+    def set_tuning(self, slab, threads): check(self.L.sq_fdm_set_tuning(self.h, slab, threads))
+
+    @property
+    def stream(self):
+        s = C.c_void_p()
+        check(self.L.sq_fdm_stream(self.h, C.byref(s)))
+        return s.value
+
+    @property
+    def launch_count(self): return int(self.L.sq_fdm_launch_count(self.h))
+
+
+def SymFermionDetMatrix(model, **kw): return FermionDetMatrix(model, sym=True, **kw)
+def AsymFermionDetMatrix(model, **kw): return FermionDetMatrix(model, sym=False, **kw)
+
+
+class KPMPreconditioner:
+    """KPMPreconditioner(fdm; rng, rbuf, n, a1, a2) (src/KPMPreconditioner.jl:198-284)."""
+
+    def __init__(self, fdm, rbuf=0.10, n=20, a1=1.0, a2=1.0, lanczos_start=None, update=True):
+        self.L, self.fdm = fdm.L, fdm
+        h = C.c_void_p()
+        check(self.L.sq_kpm_create(C.byref(h), fdm.h, rbuf, n, a1, a2))
+        self.h = h
+        if update:
+            self.update(lanczos_start)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sq_kpm_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def update(self, lanczos_start=None):
+        """update_preconditioner!(P, fdm, rng) (:554-597) -> (active, bounds)."""
+        act, b = C.c_int(0), np.zeros(2)
+        ls = None if lanczos_start is None else _f64(lanczos_start)
+        check(self.L.sq_kpm_update(self.h, ptr(ls), C.byref(act), ptr(b)))
+        return bool(act.value), b
+
+    def set_bounds(self, emin, emax): check(self.L.sq_kpm_set_bounds(self.h, emin, emax))
+
+    @property
+    def orders(self):
+        n = C.c_int64(0)
+        check(self.L.sq_kpm_get_orders(self.h, C.byref(n), None))
+        o = np.zeros(n.value, np.int64)
+        check(self.L.sq_kpm_get_orders(self.h, C.byref(n), ptr(o)))
+        return o
+
+    def coefs(self, l):
+        c = np.zeros(int(self.orders[l]), np.complex128)
+        check(self.L.sq_kpm_get_coefs(self.h, l, ptr(c)))
+        return c
+
+    def ldiv(self, v):
+        v = _cvec(self.fdm.model, v)
+        out = _cvec(self.fdm.model)
+        check(self.L.sq_kpm_ldiv(self.h, ptr(out), ptr(v)))
+        return out
+
+    def ldiv_dev(self, d_out, d_in): check(self.L.sq_kpm_ldiv_dev(self.h, ptr(d_out), ptr(d_in)))
+
+    def fourier(self, v, forward=True):
+        v = _cvec(self.fdm.model, v)
+        check(self.L.sq_kpm_fourier(self.h, ptr(v), int(forward)))
+        return v
+
+
+class ElectronPhononParameters:
+    """Device twin of the SmoQyDQMC ElectronPhononParameters / FermionPathIntegral fields the path reads."""
+
+    def __init__(self, model, fdm):
+        self.L, self.model, self.fdm = fdm.L, model, fdm
+        m = model
+        k = [_f64(m.Omega), _f64(m.Omega4), _f64(m.Mass), _i64(m.hol_phonon), _i64(m.hol_site),
+             _f64(m.hol_alpha[0]), _f64(m.hol_alpha[1]), _f64(m.hol_alpha[2]), _f64(m.hol_alpha[3]),
+             np.ascontiguousarray(m.hol_phsym, np.int32), _i64(m.ssh_phonon.T), _i64(m.ssh_hopping),
+             _f64(m.ssh_alpha[0]), _f64(m.ssh_alpha[1]), _f64(m.ssh_alpha[2]), _f64(m.ssh_alpha[3]), _f64(m.V0), _f64(m.t0)]
+        h = C.c_void_p()
+        check(self.L.sq_elph_create(C.byref(h), fdm.h, m.dtau, m.Nph, ptr(k[0]), ptr(k[1]), ptr(k[2]),
+                                    m.Nhol, ptr(k[3]), ptr(k[4]), ptr(k[5]), ptr(k[6]), ptr(k[7]), ptr(k[8]), ptr(k[9]),
+                                    m.Nssh, ptr(k[10]), ptr(k[11]), ptr(k[12]), ptr(k[13]), ptr(k[14]), ptr(k[15]),
+                                    ptr(k[16]), ptr(k[17])))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sq_elph_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def x(self):
+        out = np.zeros((self.model.Nph, self.model.Ltau), order="F")
+        check(self.L.sq_elph_get_x(self.h, ptr(out)))
+        return out
+
+    @x.setter
+    def x(self, val):
+        val = np.asfortranarray(val, np.float64)
+        assert val.shape == (self.model.Nph, self.model.Ltau)
+        check(self.L.sq_elph_set_x(self.h, ptr(val)))
+
+    def update_fdm(self):
+        """update!(fpi, elph, x, +1); update!(fdm, fpi) (src/EFAPFFHMCUpdater.jl:152-153)."""
+        check(self.L.sq_elph_refresh_fdm(self.h))
+
+    def shift_mu(self, dmu): check(self.L.sq_elph_shift_mu(self.h, dmu))
+
+    def Vt(self):
+        m = self.model
+        V = np.zeros((m.N, m.Ltau), order="F")
+        t = np.zeros((m.Nh, m.Ltau), order="F")
+        check(self.L.sq_elph_get_Vt(self.h, ptr(V), ptr(t)))
+        return V, t
+
+    def bosonic_action(self):
+        s = C.c_double(0)
+        check(self.L.sq_elph_bosonic_action(self.h, C.byref(s)))
+        return s.value
+
+
+class PFFCalculator:
+    """PFFCalculator(elph, fdm) (src/PFFCalculator.jl:30-53)."""
+
+    def __init__(self, elph, fdm=None, exact_holstein=False):
+        self.L, self.elph, self.fdm = elph.L, elph, elph.fdm
+        h = C.c_void_p()
+        check(self.L.sq_pff_create(C.byref(h), elph.h))
+        self.h = h
+        check(self.L.sq_pff_set_exact_holstein(self.h, int(exact_holstein)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sq_pff_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def sample_pseudofermion_fields(self, R=None):
+        Sf = C.c_double(0)
+        Rv = None if R is None else _cvec(self.fdm.model, R)
+        check(self.L.sq_pff_sample(self.h, ptr(Rv), C.byref(Sf)))
+        return Sf.value
+
+    def calculate_fermionic_action(self, preconditioner=None, lanczos_start=None, tol=1e-10, maxiter=10000):
+        Sf, it, eps = C.c_double(0), C.c_int64(0), C.c_double(0)
+        ls = None if lanczos_start is None else _f64(lanczos_start)
+        check(self.L.sq_pff_action(self.h, preconditioner.h if preconditioner is not None else None, ptr(ls), tol, int(maxiter),
+                                   C.byref(Sf), C.byref(it), C.byref(eps)))
+        return Sf.value, it.value, eps.value
+
+    def calculate_derivative_fermionic_action(self, dSdx=None, preconditioner=None, lanczos_start=None, tol=1e-5, maxiter=10000):
+        m = self.fdm.model
+        F = np.zeros((m.Nph, m.Ltau), order="F") if dSdx is None else dSdx
+        assert F.flags.f_contiguous and F.dtype == np.float64
+        Sf, it, eps = C.c_double(0), C.c_int64(0), C.c_double(0)
+        ls = None if lanczos_start is None else _f64(lanczos_start)
+        check(self.L.sq_pff_force(self.h, ptr(F), preconditioner.h if preconditioner is not None else None, ptr(ls), tol, int(maxiter),
+                                  C.byref(Sf), C.byref(it), C.byref(eps)))
+        return F, Sf.value, it.value, eps.value
+
+    def fields(self):
+        m = self.fdm.model
+        Phi, Psi = _cvec(m), _cvec(m)
+        Lam = np.zeros((m.Ltau, m.N), order="F")
+        check(self.L.sq_pff_get_fields(self.h, ptr(Phi), ptr(Psi), ptr(Lam)))
+        return Phi, Psi, Lam
+
+    def set_Phi(self, Phi):
+        Phi = _cvec(self.fdm.model, Phi)
+        check(self.L.sq_pff_set_Phi(self.h, ptr(Phi)))
+
+    def lambda_op(self, which, v):
+        code = {"mul": 0, "ldiv": 1, "mulT": 2, "ldivT": 3}[which]
+        v = _cvec(self.fdm.model, v)
+        out = _cvec(self.fdm.model)
+        check(self.L.sq_pff_lambda_op(self.h, code, ptr(out), ptr(v)))
+        return out
+
+    def dM_dx(self, nu, u, v):
+        m = self.fdm.model
+        F = np.zeros((m.Nph, m.Ltau), order="F")
+        check(self.L.sq_pff_dM_dx(self.h, ptr(F), nu, ptr(_cvec(m, u)), ptr(_cvec(m, v))))
+        return F
+
+    def dLambda_dx(self, nu, up, u):
+        m = self.fdm.model
+        F = np.zeros((m.Nph, m.Ltau), order="F")
+        check(self.L.sq_pff_dLambda_dx(self.h, ptr(F), nu, ptr(_cvec(m, up)), ptr(_cvec(m, u))))
+        return F
+
+
+class EFAPFFHMCUpdater:
+    """EFAPFFHMCUpdater(; electron_phonon_parameters, Nt, dt, eta, delta) (src/EFAPFFHMCUpdater.jl:40-72)."""
+
+    def __init__(self, elph, pff, Nt, dt=None, eta=0.0, delta=0.05, seed=0):
+        self.L, self.elph, self.pff = elph.L, elph, pff
+        self.Nt = int(Nt)
+        self.dt = float(np.pi / (2 * Nt) if dt is None else dt)
+        h = C.c_void_p()
+        check(self.L.sq_hmc_create(C.byref(h), pff.h, self.Nt, self.dt, eta, delta, seed))
+        self.h = h
+        self.info = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sq_hmc_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def hmc_update(self, preconditioner=None, tol_action=1e-10, tol_force=1e-5, maxiter=10000, randoms=None):
+        """hmc_update! (:102-279) -> (accepted, iters_avg).  A library failure == numerical instability => rejected."""
+        acc = C.c_int(0)
+        info = np.zeros(8)
+        rnd = None if randoms is None else _f64(randoms)
+        check(self.L.sq_hmc_update(self.h, preconditioner.h if preconditioner is not None else None, tol_action, tol_force, int(maxiter),
+                                   ptr(rnd), 0 if rnd is None else rnd.size, C.byref(acc), ptr(info)))
+        self.info = info
+        return bool(acc.value), info[0]
+
+    def init_momentum(self, R):
+        m = self.elph.model
+        p = np.zeros((m.Nph, m.Ltau), order="F")
+        K = C.c_double(0)
+        check(self.L.sq_hmc_init_momentum(self.h, ptr(np.asfortranarray(R, np.float64)), ptr(p), C.byref(K)))
+        return p, K.value
+
+    def kinetic(self, p):
+        K = C.c_double(0)
+        check(self.L.sq_hmc_kinetic(self.h, ptr(np.asfortranarray(p, np.float64)), C.byref(K)))
+        return K.value
+
+    def evolve(self, x, p, dt):
+        x = np.array(x, np.float64, order="F", copy=True)
+        p = np.array(p, np.float64, order="F", copy=True)
+        check(self.L.sq_hmc_evolve(self.h, ptr(x), ptr(p), dt))
+        return x, p
+
+
+class GreensEstimator:
+    """GreensEstimator(fdm, model_geometry; Nrv, ...) solves + scalar measurements
+    (src/Measurements/GreensEstimator.jl:63-175, scalar_measurements.jl)."""
+
+    def __init__(self, fdm, Nrv=10, seed=0):
+        self.L, self.fdm, self.Nrv = fdm.L, fdm, int(Nrv)
+        h = C.c_void_p()
+        check(self.L.sq_greens_create(C.byref(h), fdm.h, self.Nrv, seed))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sq_greens_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def update_greens_estimator(self, preconditioner=None, R=None, tol=1e-10, maxiter=10000):
+        avg = C.c_double(0)
+        Rv = None if R is None else np.asfortranarray(R, np.complex128)
+        check(self.L.sq_greens_update(self.h, preconditioner.h if preconditioner is not None else None, ptr(Rv), tol, int(maxiter), C.byref(avg)))
+        return avg.value
+
+    def get(self):
+        V = self.fdm.model.N * self.fdm.model.Ltau
+        R = np.zeros((V, self.Nrv), np.complex128, order="F")
+        GR = np.zeros((V, self.Nrv), np.complex128, order="F")
+        check(self.L.sq_greens_get(self.h, ptr(R), ptr(GR)))
+        return R, GR
+
+    def set_GR(self, GR): check(self.L.sq_greens_set_GR(self.h, ptr(np.asfortranarray(GR, np.complex128))))
+
+    def measure(self):
+        out = np.zeros((3, 2))
+        check(self.L.sq_greens_measure(self.h, ptr(out[0]), ptr(out[1]), ptr(out[2])))
+        return {"n": complex(*out[0]), "double_occ": complex(*out[1]), "Nsqrd": complex(*out[2])}
+
+
+def update_chemical_potential(fdm, greens, elph, mu, mu_new_fn, preconditioner=None, update_greens_estimator=True, tol=1e-10, maxiter=10000):
+    """update_chemical_potential! (src/update_chemical_potential.jl:21-73).  The MuTuner scalar logic stays on
+    the host: `mu_new_fn(n, Nsqrd) -> mu'` stands in for MuTuner.update!.  Returns (mu', iters)."""
+    iters = 0
+    if update_greens_estimator:
+        iters = greens.update_greens_estimator(preconditioner=preconditioner, tol=tol, maxiter=maxiter)
+    meas = greens.measure()
+    n = (2 * meas["n"]).real
+    Nsqrd = meas["Nsqrd"].real
+    mu_new = mu_new_fn(n, Nsqrd)
+    elph.shift_mu(mu_new - mu)
+    elph.update_fdm()
+    return mu_new, iters

@@ -1,0 +1,243 @@
+// cg.cu -- conjugate gradient on M^T M, device resident.
+//
+// Replaces /root/reference/src/IterativeSolvers/ConjugateGradient.jl:93-167 (P = I) and :169-249
+// (left preconditioner) plus ldiv!(x, fdm, b) at src/FermionDetMatrix.jl:248-267.
+//
+// The recurrence, stopping rule (|r|/|b| < tol checked before the loop and after every r update),
+// complex alpha/beta and the returned (iters, eps) are the reference's.  All scalars live in a
+// ping-ponged device struct; kernels of iterations launched after convergence exit immediately on the
+// `done` flag, so the host only synchronises once per batch of iterations.  BLAS-1 work is fused:
+//   K_A  z = M^T M p and per-CTA partials of p.A p = |M p|^2            (fdm.cu, fused matvec)
+//   K_B  alpha, x += alpha p, r -= alpha z, partials of |r|^2             (one pass over x, r, p, z)
+//   K_C  eps / convergence, beta, p = r + beta p  (P = I)                 (one pass over r, p)
+// With a preconditioner K_C splits into the convergence check, P^-1 r, the r.z partials and the
+// p update.  Reductions are deterministic (fixed-order partial sums, no floating-point atomics).
+#include "sq_internal.h"
+
+// reduce partial sums of up to 3 quantities laid out as part[q*SQ_MAXPART + k]; result in all threads of warp 0,
+// broadcast through shared memory to the block.
+__device__ __forceinline__ void reduce_partials(const double *part, int n, int nq, double *sh /*[3]*/) {
+    if (threadIdx.x < 32) {
+        for (int q = 0; q < nq; q++) {
+            double s = warp_sum_partials(part + (size_t)q * SQ_MAXPART, n);
+            if (threadIdx.x == 0) sh[q] = s;
+        }
+    }
+    __syncthreads();
+}
+
+// partials of conj(a).b (re, im) and |a|^2
+__global__ void k_dot_partials(const double2 *__restrict__ a, const double2 *__restrict__ b, size_t n, double *__restrict__ part,
+                               const CgState *__restrict__ skip) {
+    __shared__ double red[3 * 32];
+    if (skip && skip->done) return;
+    double v[3] = {0, 0, 0};
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        double2 x = a[k], y = b[k];
+        v[0] += x.x * y.x + x.y * y.y;
+        v[1] += x.x * y.y - x.y * y.x;
+        v[2] += x.x * x.x + x.y * x.y;
+    }
+    block_sum<3>(v, red);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = v[0];
+        part[SQ_MAXPART + blockIdx.x] = v[1];
+        part[2 * SQ_MAXPART + blockIdx.x] = v[2];
+    }
+}
+
+// r = b - r   (axpby!(1, b, -1, r), ConjugateGradient.jl:196)
+__global__ void k_residual(double2 *__restrict__ r, const double2 *__restrict__ b, size_t n) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        double2 x = b[k], y = r[k];
+        r[k] = make_double2(x.x - y.x, x.y - y.y);
+    }
+}
+
+// initial state: normb from part_b (|b|^2 in slot 2), r.z / |r|^2 from part_rz; eps0 test (:206-214)
+__global__ void k_cg_init(CgState *st, const double *part_b, int nb, const double *part_rz, int nrz, double tol) {
+    __shared__ double sh[3], shb[3];
+    reduce_partials(part_b, nb, 3, shb);
+    reduce_partials(part_rz, nrz, 3, sh);
+    if (threadIdx.x == 0) {
+        CgState s;
+        s.normb = sqrt(shb[2]);
+        s.rz_re = sh[0];
+        s.rz_im = sh[1];
+        s.eps = sqrt(sh[2]) / s.normb;
+        s.tol = tol;
+        s.iters = 0;
+        s.done = (s.eps < tol) ? 1 : 0;
+        if (!(s.eps == s.eps)) s.done = 2;            // NaN: stop, reported as an error by the host
+        st[0] = s;
+        st[1] = s;
+    }
+}
+
+// K_B: alpha = rz / pAp ; x += alpha p ; r -= alpha z ; partial |r|^2      (:219-226)
+// pAp_complex != 0: p.Ap is taken from the complex partials (re, im) instead of the real |Mp|^2.
+__global__ void k_cg_update_xr(const CgState *__restrict__ st, double2 *__restrict__ x, double2 *__restrict__ r,
+                               const double2 *__restrict__ p, const double2 *__restrict__ z, size_t n,
+                               const double *__restrict__ pAp_part, int npart, int pAp_complex, double *__restrict__ rr_part) {
+    __shared__ double sh[3];
+    __shared__ double red[32];
+    if (st->done) return;
+    reduce_partials(pAp_part, npart, pAp_complex ? 2 : 1, sh);
+    double2 pAp = make_double2(sh[0], pAp_complex ? sh[1] : 0.0);
+    double2 alpha = cdiv(make_double2(st->rz_re, st->rz_im), pAp);
+    double acc = 0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        double2 pk = p[k], zk = z[k], xk = x[k], rk = r[k];
+        double2 ap = cmul(alpha, pk), az = cmul(alpha, zk);
+        xk = cadd(xk, ap);
+        rk = csub(rk, az);
+        x[k] = xk;
+        r[k] = rk;
+        acc += rk.x * rk.x + rk.y * rk.y;
+    }
+    double v[1] = {acc};
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) rr_part[blockIdx.x] = v[0];
+}
+
+// K_C (P = I): eps = |r|/|b|; stop or beta = rr_new/rr_old, p = r + beta p     (:229-245)
+__global__ void k_cg_update_p(const CgState *__restrict__ cur, CgState *__restrict__ nxt, double2 *__restrict__ p,
+                              const double2 *__restrict__ r, size_t n, const double *__restrict__ rr_part, int npart, int iter) {
+    __shared__ double sh[3];
+    if (cur->done) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *nxt = *cur;
+        return;
+    }
+    reduce_partials(rr_part, npart, 1, sh);
+    double rr = sh[0];
+    double eps = sqrt(rr) / cur->normb;
+    bool stop = (eps < cur->tol) || !(eps == eps);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        CgState s = *cur;
+        s.eps = eps;
+        s.iters = iter;
+        s.done = stop ? ((eps == eps) ? 1 : 2) : 0;
+        s.rz_re = rr;
+        s.rz_im = 0.0;
+        *nxt = s;
+    }
+    if (stop) return;
+    double2 beta = cdiv(make_double2(rr, 0.0), make_double2(cur->rz_re, cur->rz_im));
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        double2 pk = p[k], rk = r[k];
+        p[k] = cadd(rk, cmul(beta, pk));
+    }
+}
+
+// preconditioned: convergence check only (writes nxt without touching rz)
+__global__ void k_cg_check(const CgState *__restrict__ cur, CgState *__restrict__ nxt, const double *__restrict__ rr_part,
+                           int npart, int iter) {
+    __shared__ double sh[3];
+    if (cur->done) {
+        if (threadIdx.x == 0) *nxt = *cur;
+        return;
+    }
+    reduce_partials(rr_part, npart, 1, sh);
+    if (threadIdx.x == 0) {
+        CgState s = *cur;
+        s.eps = sqrt(sh[0]) / cur->normb;
+        s.iters = iter;
+        s.done = (s.eps < cur->tol) ? 1 : 0;
+        if (!(s.eps == s.eps)) s.done = 2;
+        *nxt = s;
+    }
+}
+// preconditioned: beta = (r.z)_new / (r.z)_old ; p = z + beta p ; state->rz updated by block 0 AFTER all reads.
+// `st` is the state written by k_cg_check; the old r.z is read from `old` (the other ping-pong slot).
+__global__ void k_cg_update_p_prec(CgState *__restrict__ st, const CgState *__restrict__ old, double2 *__restrict__ p,
+                                   const double2 *__restrict__ z, size_t n, const double *__restrict__ rz_part, int npart) {
+    __shared__ double sh[3];
+    if (st->done) return;
+    reduce_partials(rz_part, npart, 2, sh);
+    double2 rz = make_double2(sh[0], sh[1]);
+    double2 beta = cdiv(rz, make_double2(old->rz_re, old->rz_im));
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        double2 pk = p[k], zk = z[k];
+        p[k] = cadd(zk, cmul(beta, pk));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->rz_re = rz.x; st->rz_im = rz.y; }
+}
+
+static int vec_grid(const sq_fdm *f, size_t n, int threads) {
+    size_t want = (n + threads - 1) / threads;
+    size_t cap = (size_t)f->num_sms * 4;
+    size_t g = std::min(want, cap);
+    g = std::min<size_t>(g, SQ_MAXPART);
+    return (int)std::max<size_t>(g, 1);
+}
+
+// Solve M^T M x = b.  x, b device vectors in the [l][i] layout.  Follows cg_solve! step by step.
+void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter,
+                i64 *iters, double *eps) {
+    const size_t n = (size_t)f->L * f->N;
+    const int TB = 256, G = vec_grid(f, n, TB);
+    cudaStream_t s = f->stream;
+    double *part = f->part.p;
+    double *part_b = part, *part_rz = part + 3 * SQ_MAXPART, *part_pAp = part + 6 * SQ_MAXPART, *part_rr = part + 7 * SQ_MAXPART;
+    double2 *r = f->r.p, *p = f->p.p, *z = f->z.p;
+    CgState *st = f->cg.p;
+    const bool prec = (kpm != nullptr) && kpm->active;
+
+    k_dot_partials<<<G, TB, 0, s>>>(b, b, n, part_b, nullptr);                      // |b|
+    if (zero_start) {
+        if (x != b) {
+            SQ_CUDA(cudaMemcpyAsync(r, b, n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+        } else {
+            SQ_CUDA(cudaMemcpyAsync(r, b, n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+        }
+        SQ_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double2), s));
+    } else {
+        fdm_mul_dev(f, SQ_OP_MTM, r, x);
+        k_residual<<<G, TB, 0, s>>>(r, b, n);
+    }
+    if (prec) {
+        kpm_ldiv_dev(kpm, z, r);
+        SQ_CUDA(cudaMemcpyAsync(p, z, n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+        k_dot_partials<<<G, TB, 0, s>>>(r, z, n, part_rz, nullptr);
+    } else {
+        SQ_CUDA(cudaMemcpyAsync(p, r, n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+        k_dot_partials<<<G, TB, 0, s>>>(r, r, n, part_rz, nullptr);
+    }
+    k_cg_init<<<1, 64, 0, s>>>(st, part_b, G, part_rz, G, tol);
+    SQ_LAUNCH_CHECK();
+    f->launches += 4;
+
+    const int batch = prec ? 4 : 16;
+    i64 it = 0;
+    int cur = 0;
+    bool finished = false;
+    // is the system already solved?  (cheap check folded into the first batch read-back)
+    while (!finished) {
+        i64 upto = std::min<i64>(maxiter, it + batch);
+        for (; it < upto; ) {
+            it++;
+            const CgState *sc = st + cur;
+            CgState *sn = st + (cur ^ 1);
+            int npart = 0;
+            fdm_mul_dev(f, SQ_OP_MTM, z, p, part_pAp, &npart, sc);
+            k_cg_update_xr<<<G, TB, 0, s>>>(sc, x, r, p, z, n, part_pAp, npart, 0, part_rr);
+            if (!prec) {
+                k_cg_update_p<<<G, TB, 0, s>>>(sc, sn, p, r, n, part_rr, G, (int)it);
+                f->launches += 2;
+            } else {
+                k_cg_check<<<1, 64, 0, s>>>(sc, sn, part_rr, G, (int)it);
+                int g = kpm_ldiv_dev_dot(kpm, z, r, sn, r, part_rz);      // z = P^-1 r with the r.z partials fused in
+                k_cg_update_p_prec<<<G, TB, 0, s>>>(sn, sc, p, z, n, part_rz, g);
+                f->launches += 3;
+            }
+            cur ^= 1;
+        }
+        SQ_LAUNCH_CHECK();
+        SQ_CUDA(cudaMemcpyAsync(f->h_cg, st + cur, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+        SQ_CUDA(cudaStreamSynchronize(s));
+        if (f->h_cg->done || it >= maxiter) finished = true;
+    }
+    if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+    *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
+    *eps = f->h_cg->eps;
+}

@@ -1,0 +1,123 @@
+// common.cuh -- error handling, device buffers and small device helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+typedef int64_t i64;
+
+struct SqError : public std::runtime_error {
+    explicit SqError(const std::string &m) : std::runtime_error(m) {}
+};
+
+void sq_set_last_error(const std::string &m);
+
+#define SQ_CUDA(expr)                                                                                  \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            throw SqError(std::string("CUDA error '") + cudaGetErrorString(_e) + "' at " + __FILE__ + \
+                          ":" + std::to_string(__LINE__) + " in " #expr);                              \
+    } while (0)
+
+#define SQ_REQUIRE(cond, msg)                                                       \
+    do {                                                                            \
+        if (!(cond)) throw SqError(std::string("invalid argument: ") + (msg));     \
+    } while (0)
+
+#define SQ_LAUNCH_CHECK() SQ_CUDA(cudaGetLastError())
+
+// RAII device buffer
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count, bool zero = true) {
+        release();
+        n = count;
+        size_t bytes = (count ? count : 1) * sizeof(T);
+        SQ_CUDA(cudaMalloc((void **)&p, bytes));
+        if (zero) {
+            // cudaMemset runs on the legacy default stream, which the library's non-blocking streams do not
+            // order against: finish it before anyone can enqueue work on the new buffer.
+            SQ_CUDA(cudaMemset(p, 0, bytes));
+            SQ_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+        }
+    }
+    void upload(const T *h, size_t count, cudaStream_t s) {
+        if (count > n) throw SqError("DevBuf::upload overflow");
+        if (count) SQ_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T *h, size_t count, cudaStream_t s) const {
+        if (count > n) throw SqError("DevBuf::download overflow");
+        if (count) SQ_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+    void from_vector(const std::vector<T> &v, cudaStream_t s) {
+        alloc(v.size(), false);
+        upload(v.data(), v.size(), s);
+        SQ_CUDA(cudaStreamSynchronize(s));   // the vector may be a temporary
+    }
+};
+
+// ---- device helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {   // conj(a) * b
+    return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cscale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+__device__ __forceinline__ double2 cdiv(double2 a, double2 b) {
+    double d = b.x * b.x + b.y * b.y;
+    return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block reduction of up to 4 doubles per thread.  `red` needs 4*32 doubles of shared
+// memory.  The result is valid in thread 0.
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double *red) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) red[k * 32 + warp] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double t = lane < nw ? red[k * 32 + lane] : 0.0;
+            v[k] = warp_sum(t);
+        }
+    }
+}
+
+// Sum `n` per-block partials (stride-1 array) in a fixed order with one warp; all lanes get the result.
+__device__ __forceinline__ double warp_sum_partials(const double *part, int n) {
+    double t = 0.0;
+    for (int k = threadIdx.x & 31; k < n; k += 32) t += part[k];
+    return warp_sum(t);
+}

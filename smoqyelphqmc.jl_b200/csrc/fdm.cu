@@ -1,0 +1,637 @@
+// fdm.cu -- the space-time fermion matrix M as a matrix-free operator on B200.
+//
+// Replaces (reference, /root/reference/src): FermionDetMatrix.jl:208-236 (update!), :329-368
+// (mul_MtM!/mul_MMt!), :385-466 (mul_M!), :484-563 (mul_Mt!) and checkerboard_matrix_multiply.jl:26-72.
+//
+// K1 (fused M^T M v): one CTA owns a slab of S consecutive time slices.  It stages the S+2 input
+// slices v[l0-1 .. l0+S] in shared memory once, applies the S+1 propagators B_l needed for
+// w = M v on [l0, l0+S] (halo recompute of one slice), then the S transposed propagators for
+// out = M^T w, and writes S output slices: one pass over HBM per matvec (v, v', exp(-dtau V), cosh,
+// sinh each touched once, plus the 2-slice halo).  All checkerboard colour steps of all slices in
+// flight share one __syncthreads per step.  |w|^2 = p.A p for CG falls out of the first phase.
+#include "sq_internal.h"
+
+// ---------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rot(double2 &a, double2 &b, double c, double s) {
+    double2 na = make_double2(fma(s, b.x, c * a.x), fma(s, b.y, c * a.y));
+    double2 nb = make_double2(fma(s, a.x, c * b.x), fma(s, a.y, c * b.y));
+    a = na;
+    b = nb;
+}
+
+struct TIdx { int tx, ty, TY; };
+
+__device__ __forceinline__ TIdx tidx(const KParams &P) {
+    TIdx t;
+    t.tx = threadIdx.x & (P.TX - 1);
+    t.ty = threadIdx.x >> P.TXshift;
+    t.TY = blockDim.x >> P.TXshift;
+    return t;
+}
+
+// one colour of 2x2 rotations on nsl shared-memory slices; slice k uses the coefficients of time
+// slice (lfirst + k) mod L.  (checkerboard_lmul! with interval = one colour.)
+__device__ __forceinline__ void sweep_color(double2 *buf, int nsl, int lfirst, int c, const KParams &P, TIdx t) {
+    const int lo = P.clo[c], nb = P.chi[c] - lo;
+    for (int k = t.ty; k < nsl; k += t.TY) {
+        int l = (lfirst + k) % P.L;
+        double2 *u = buf + (size_t)k * P.N;
+        const double2 *csl = P.cs + (size_t)l * P.Nh + lo;
+        for (int b = t.tx; b < nb; b += P.TX) {
+            int2 ij = __ldg(P.nt + lo + b);
+            double2 cs = __ldg(csl + b);
+            double2 a = u[ij.x], bb = u[ij.y];
+            rot(a, bb, cs.x, cs.y);
+            u[ij.x] = a;
+            u[ij.y] = bb;
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void scale_D(double2 *buf, int nsl, int lfirst, const KParams &P, TIdx t) {
+    for (int k = t.ty; k < nsl; k += t.TY) {
+        int l = (lfirst + k) % P.L;
+        double2 *u = buf + (size_t)k * P.N;
+        const double *d = P.expV + (size_t)l * P.N;
+        for (int i = t.tx; i < P.N; i += P.TX) {
+            double dd = __ldg(d + i);
+            double2 a = u[i];
+            u[i] = make_double2(dd * a.x, dd * a.y);
+        }
+    }
+    __syncthreads();
+}
+
+// colour 0 of Gamma^T, the diagonal, and colour 0 of Gamma in one shared-memory round trip
+__device__ __forceinline__ void sweep_mid(double2 *buf, int nsl, int lfirst, const KParams &P, TIdx t) {
+    const int lo = P.clo[0], nb = P.chi[0] - lo;
+    for (int k = t.ty; k < nsl; k += t.TY) {
+        int l = (lfirst + k) % P.L;
+        double2 *u = buf + (size_t)k * P.N;
+        const double2 *csl = P.cs + (size_t)l * P.Nh + lo;
+        const double *d = P.expV + (size_t)l * P.N;
+        for (int b = t.tx; b < nb; b += P.TX) {
+            int2 ij = __ldg(P.nt + lo + b);
+            double2 cs = __ldg(csl + b);
+            double di = __ldg(d + ij.x), dj = __ldg(d + ij.y);
+            double2 a = u[ij.x], bb = u[ij.y];
+            rot(a, bb, cs.x, cs.y);
+            a = make_double2(di * a.x, di * a.y);
+            bb = make_double2(dj * bb.x, dj * bb.y);
+            rot(a, bb, cs.x, cs.y);
+            u[ij.x] = a;
+            u[ij.y] = bb;
+        }
+        for (int q = t.tx; q < P.nunc0; q += P.TX) {
+            int i = __ldg(P.unc0 + q);
+            double dd = __ldg(d + i);
+            double2 a = u[i];
+            u[i] = make_double2(dd * a.x, dd * a.y);
+        }
+    }
+    __syncthreads();
+}
+
+// buf[k] <- B_{lfirst+k} buf[k]  (transposed: B^T).  Sym: B = Gamma D Gamma^T (= B^T for real hoppings);
+// Asym: B = D Gamma, B^T = Gamma^T D.   (FermionDetMatrix.jl:401-410, :445-451, :497-506, :541-544)
+__device__ __forceinline__ void apply_B(double2 *buf, int nsl, int lfirst, bool transposed, const KParams &P, TIdx t) {
+    if (P.sym) {
+        if (P.C == 0) { scale_D(buf, nsl, lfirst, P, t); return; }
+        for (int c = P.C - 1; c >= 1; c--) sweep_color(buf, nsl, lfirst, c, P, t);
+        sweep_mid(buf, nsl, lfirst, P, t);
+        for (int c = 1; c < P.C; c++) sweep_color(buf, nsl, lfirst, c, P, t);
+    } else if (!transposed) {
+        for (int c = 0; c < P.C; c++) sweep_color(buf, nsl, lfirst, c, P, t);
+        scale_D(buf, nsl, lfirst, P, t);
+    } else {
+        scale_D(buf, nsl, lfirst, P, t);
+        for (int c = P.C - 1; c >= 0; c--) sweep_color(buf, nsl, lfirst, c, P, t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: fused kernels.  MODE 0: out = M in; 1: out = M^T in; 2: out = M^T M in (+ partial |M in|^2)
+// ---------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1)
+k_fdm_fused(const __grid_constant__ KParams P, double2 *__restrict__ out, const double2 *__restrict__ in,
+            double *__restrict__ pAp_part, const CgState *__restrict__ skip) {
+    extern __shared__ double2 smem[];
+    __shared__ double red[32];
+    if (skip && skip->done) return;
+    const TIdx t = tidx(P);
+    const int L = P.L, N = P.N;
+    const int l0 = blockIdx.x * P.S;
+    const int ns = min(P.S, L - l0);
+    const int T = blockDim.x;
+
+    if (MODE == 2) {
+        // A[k] = v[l0-1+k], k = 0..ns+1 ; W[k] = copy of A[k], k = 0..ns
+        double2 *A = smem, *W = smem + (size_t)(P.S + 2) * N;
+        for (int k = 0; k <= ns + 1; k++) {
+            int l = (l0 - 1 + k + L) % L;
+            const double2 *src = in + (size_t)l * N;
+            for (int i = threadIdx.x; i < N; i += T) {
+                double2 v = src[i];
+                A[(size_t)k * N + i] = v;
+                if (k <= ns) W[(size_t)k * N + i] = v;
+            }
+        }
+        __syncthreads();
+        apply_B(W, ns + 1, l0 % L, false, P, t);            // W[k] = B_{l0+k} v[l0+k-1]
+        // w[l0+k] = v[l0+k] -/+ W[k]  (+ on the antiperiodic slice l = 0); T[k] := A[k+1] for k >= 1
+        double acc = 0.0;
+        for (int k = 0; k <= ns; k++) {
+            int l = (l0 + k) % L;
+            double sg = (l == 0) ? 1.0 : -1.0;
+            for (int i = threadIdx.x; i < N; i += T) {
+                double2 a = A[(size_t)(k + 1) * N + i], b = W[(size_t)k * N + i];
+                double2 w = make_double2(fma(sg, b.x, a.x), fma(sg, b.y, a.y));
+                W[(size_t)k * N + i] = w;
+                if (k >= 1) A[(size_t)(k + 1) * N + i] = w;
+                if (k < ns) acc += w.x * w.x + w.y * w.y;
+            }
+        }
+        __syncthreads();
+        if (ns > 0) apply_B(A + (size_t)2 * N, ns, (l0 + 1) % L, true, P, t);   // T[k] = B^T_{l0+k} w[l0+k], k = 1..ns
+        for (int k = 1; k <= ns; k++) {
+            int lb = (l0 + k) % L;
+            double sg = (lb == 0) ? 1.0 : -1.0;
+            double2 *dst = out + (size_t)(l0 + k - 1) * N;
+            for (int i = threadIdx.x; i < N; i += T) {
+                double2 a = W[(size_t)(k - 1) * N + i], b = A[(size_t)(k + 1) * N + i];
+                dst[i] = make_double2(fma(sg, b.x, a.x), fma(sg, b.y, a.y));
+            }
+        }
+        if (pAp_part) {
+            double v[1] = {acc};
+            block_sum<1>(v, red);
+            if (threadIdx.x == 0) pAp_part[blockIdx.x] = v[0];
+        }
+    } else if (MODE == 0) {
+        // A[k] = v[l0-1+k], k = 0..ns ; W[k] = A[k], k = 0..ns-1
+        double2 *A = smem, *W = smem + (size_t)(P.S + 1) * N;
+        for (int k = 0; k <= ns; k++) {
+            int l = (l0 - 1 + k + L) % L;
+            const double2 *src = in + (size_t)l * N;
+            for (int i = threadIdx.x; i < N; i += T) {
+                double2 v = src[i];
+                A[(size_t)k * N + i] = v;
+                if (k < ns) W[(size_t)k * N + i] = v;
+            }
+        }
+        __syncthreads();
+        apply_B(W, ns, l0 % L, false, P, t);
+        for (int k = 0; k < ns; k++) {
+            double sg = (l0 + k == 0) ? 1.0 : -1.0;
+            double2 *dst = out + (size_t)(l0 + k) * N;
+            for (int i = threadIdx.x; i < N; i += T) {
+                double2 a = A[(size_t)(k + 1) * N + i], b = W[(size_t)k * N + i];
+                dst[i] = make_double2(fma(sg, b.x, a.x), fma(sg, b.y, a.y));
+            }
+        }
+    } else {
+        // A[k] = v[l0+k], k = 0..ns ; W[k] = A[k+1] copies, k = 0..ns-1  (W[k] -> B^T_{l0+k+1} v[l0+k+1])
+        double2 *A = smem, *W = smem + (size_t)(P.S + 1) * N;
+        for (int k = 0; k <= ns; k++) {
+            int l = (l0 + k) % L;
+            const double2 *src = in + (size_t)l * N;
+            for (int i = threadIdx.x; i < N; i += T) {
+                double2 v = src[i];
+                A[(size_t)k * N + i] = v;
+                if (k >= 1) W[(size_t)(k - 1) * N + i] = v;
+            }
+        }
+        __syncthreads();
+        apply_B(W, ns, (l0 + 1) % L, true, P, t);
+        for (int k = 0; k < ns; k++) {
+            double sg = ((l0 + k + 1) % L == 0) ? 1.0 : -1.0;
+            double2 *dst = out + (size_t)(l0 + k) * N;
+            for (int i = threadIdx.x; i < N; i += T) {
+                double2 a = A[(size_t)k * N + i], b = W[(size_t)k * N + i];
+                dst[i] = make_double2(fma(sg, b.x, a.x), fma(sg, b.y, a.y));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Global-memory passes: fallback when a slice does not fit in shared memory, and building blocks of
+// the force evaluation (single-colour lmul / ldiv on full space-time vectors).
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_sweep_global(const __grid_constant__ KParams P, double2 *__restrict__ u, int lo, int nb, double sgn) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t tot = (size_t)P.L * nb;
+    if (idx >= tot) return;
+    int l = (int)(idx / nb), b = (int)(idx - (size_t)l * nb);
+    int2 ij = __ldg(P.nt + lo + b);
+    double2 cs = __ldg(P.cs + (size_t)l * P.Nh + lo + b);
+    double2 *ul = u + (size_t)l * P.N;
+    double2 a = ul[ij.x], bb = ul[ij.y];
+    rot(a, bb, cs.x, sgn * cs.y);
+    ul[ij.x] = a;
+    ul[ij.y] = bb;
+}
+__global__ void k_scale_global(const __grid_constant__ KParams P, double2 *__restrict__ u, int inverse) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)P.L * P.N) return;
+    double d = P.expV[idx];
+    double2 a = u[idx];
+    u[idx] = inverse ? make_double2(a.x / d, a.y / d) : make_double2(d * a.x, d * a.y);
+}
+// dst[l] = src[l - shift] (cyclic)
+__global__ void k_shift_copy(double2 *__restrict__ dst, const double2 *__restrict__ src, int L, int N, int shift) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)L * N) return;
+    int l = (int)(idx / N), i = (int)(idx - (size_t)l * N);
+    int ls = ((l - shift) % L + L) % L;
+    dst[idx] = src[(size_t)ls * N + i];
+}
+// M: out[l] = in[l] -/+ w[l] (+ at l = 0).  Mt: out[l] = in[l] -/+ w[l+1] (+ at l = L-1)
+__global__ void k_combine_global(double2 *__restrict__ out, const double2 *__restrict__ in, const double2 *__restrict__ w,
+                                 int L, int N, int transposed) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)L * N) return;
+    int l = (int)(idx / N), i = (int)(idx - (size_t)l * N);
+    double2 a = in[idx], b;
+    double sg;
+    if (!transposed) { b = w[idx]; sg = (l == 0) ? 1.0 : -1.0; }
+    else { int lp = (l + 1 == L) ? 0 : l + 1; b = w[(size_t)lp * N + i]; sg = (lp == 0) ? 1.0 : -1.0; }
+    out[idx] = make_double2(fma(sg, b.x, a.x), fma(sg, b.y, a.y));
+}
+__global__ void k_norm2_partials(const double2 *__restrict__ a, size_t n, double *__restrict__ part) {
+    __shared__ double red[32];
+    double acc = 0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        double2 v = a[k];
+        acc += v.x * v.x + v.y * v.y;
+    }
+    double v[1] = {acc};
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = v[0];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5: operator refresh.  expV[l][i] = exp(-dtau V[i,l]); (cosh, sinh)(dtau' |t|) in checkerboard order.
+// V (N x L) and t (Nh x L) arrive site-fastest, i.e. already in the device layout.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_fdm_update(double *__restrict__ expV, double2 *__restrict__ cs, const double *__restrict__ V,
+                             const double *__restrict__ t, const int *__restrict__ perm, int L, int N, int Nh,
+                             double dtau, double dtaup) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t nV = (size_t)L * N, nT = (size_t)L * Nh;
+    if (idx < nV) expV[idx] = exp(-dtau * V[idx]);
+    if (idx < nT) {
+        int l = (int)(idx / Nh), h = (int)(idx - (size_t)l * Nh);
+        double tp = t[(size_t)l * Nh + perm[h]];
+        double a = dtaup * fabs(tp);
+        double sg = (tp > 0.0) ? 1.0 : ((tp < 0.0) ? -1.0 : 0.0);
+        cs[idx] = make_double2(cosh(a), sg * sinh(a));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// layout conversion at the host boundary: (rows x cols) with rows fastest  <->  cols fastest
+// ---------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void k_transpose(T *__restrict__ dst, const T *__restrict__ src, int rows, int cols) {
+    // src[r + c*rows] -> dst[c + r*cols]
+    __shared__ T tile[32][33];
+    int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int r = r0 + threadIdx.x, c = c0 + j;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = src[(size_t)c * rows + r];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int c = c0 + threadIdx.x, r = r0 + j;
+        if (r < rows && c < cols) dst[(size_t)r * cols + c] = tile[threadIdx.x][j];
+    }
+}
+
+template <class T>
+static void transpose_launch(T *dst, const T *src, int rows, int cols, cudaStream_t s) {
+    dim3 grid((rows + 31) / 32, (cols + 31) / 32), block(32, 8);
+    k_transpose<T><<<grid, block, 0, s>>>(dst, src, rows, cols);
+    SQ_LAUNCH_CHECK();
+}
+
+void fdm_host_to_dev(sq_fdm *f, double2 *d_dst, const void *h_src) {
+    SQ_CUDA(cudaMemcpyAsync(f->io1.p, h_src, f->vec_bytes(), cudaMemcpyHostToDevice, f->stream));
+    transpose_launch<double2>(d_dst, f->io1.p, (int)f->L, (int)f->N, f->stream);     // (L x N) tau-fastest -> [l][i]
+    f->launches++;
+}
+void fdm_dev_to_host(sq_fdm *f, void *h_dst, const double2 *d_src) {
+    transpose_launch<double2>(f->io1.p, d_src, (int)f->N, (int)f->L, f->stream);     // [l][i] = (N x L) i-fastest -> tau-fastest
+    f->launches++;
+    SQ_CUDA(cudaMemcpyAsync(h_dst, f->io1.p, f->vec_bytes(), cudaMemcpyDeviceToHost, f->stream));
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
+}
+void fdm_transpose_real(sq_fdm *f, double *dst, const double *src, int rows, int cols, bool) {
+    transpose_launch<double>(dst, src, rows, cols, f->stream);
+    f->launches++;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+KParams sq_fdm::kparams(int S, int T) const {
+    KParams P;
+    P.L = (int)L; P.N = (int)N; P.Nh = (int)Nh; P.C = (int)C; P.sym = sym; P.S = S;
+    int nbmax = 1;
+    for (int c = 0; c < C; c++) { P.clo[c] = clo[c]; P.chi[c] = chi[c]; nbmax = std::max(nbmax, chi[c] - clo[c]); }
+    for (int c = (int)C; c < SQ_MAXC; c++) { P.clo[c] = 0; P.chi[c] = 0; }
+    int TX = 32, sh = 5;
+    while (TX < nbmax && TX < T) { TX <<= 1; sh++; }
+    if (TX > T) { TX = T; sh = 0; while ((1 << sh) < T) sh++; }
+    P.TX = TX; P.TXshift = sh;
+    P.nunc0 = nunc0;
+    P.nt = nt.p; P.cs = cs.p; P.expV = expV.p; P.unc0 = unc0.p;
+    return P;
+}
+
+static size_t fused_smem_bytes(const sq_fdm *f, int mode, int S) {
+    size_t slices = (mode == 2) ? (size_t)(2 * S + 3) : (size_t)(2 * S + 1);
+    return slices * f->N * sizeof(double2);
+}
+
+template <int MODE>
+static void launch_fused(sq_fdm *f, int S, int T, double2 *out, const double2 *in, double *part, const CgState *skip) {
+    KParams P = f->kparams(S, T);
+    size_t smem = fused_smem_bytes(f, MODE, S);
+    int grid = (int)((f->L + S - 1) / S);
+    k_fdm_fused<MODE><<<grid, T, smem, f->stream>>>(P, out, in, part, skip);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+}
+
+void fdm_sweep_global(sq_fdm *f, double2 *u, int lo, int hi, bool inverse) {
+    int nb = hi - lo;
+    if (nb <= 0) return;
+    KParams P = f->kparams(1, 256);
+    size_t tot = (size_t)f->L * nb;
+    k_sweep_global<<<(unsigned)((tot + 255) / 256), 256, 0, f->stream>>>(P, u, lo, nb, inverse ? -1.0 : 1.0);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+}
+void fdm_scale_global(sq_fdm *f, double2 *u, bool inverse) {
+    KParams P = f->kparams(1, 256);
+    size_t tot = (size_t)f->L * f->N;
+    k_scale_global<<<(unsigned)((tot + 255) / 256), 256, 0, f->stream>>>(P, u, inverse ? 1 : 0);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+}
+
+// un-fused M / M^T through global memory (path 1)
+static void mul_global(sq_fdm *f, bool transposed, double2 *out, const double2 *in, double2 *w) {
+    size_t tot = (size_t)f->L * f->N;
+    unsigned g = (unsigned)((tot + 255) / 256);
+    int C = (int)f->C;
+    if (!transposed) {
+        k_shift_copy<<<g, 256, 0, f->stream>>>(w, in, (int)f->L, (int)f->N, 1);
+        // the coefficient slice used on w[l] is l: B_l v[l-1]
+        if (f->sym) {
+            for (int c = C - 1; c >= 0; c--) fdm_sweep_global(f, w, f->clo[c], f->chi[c], false);
+            fdm_scale_global(f, w, false);
+            for (int c = 0; c < C; c++) fdm_sweep_global(f, w, f->clo[c], f->chi[c], false);
+        } else {
+            for (int c = 0; c < C; c++) fdm_sweep_global(f, w, f->clo[c], f->chi[c], false);
+            fdm_scale_global(f, w, false);
+        }
+    } else {
+        SQ_CUDA(cudaMemcpyAsync(w, in, f->vec_bytes(), cudaMemcpyDeviceToDevice, f->stream));
+        if (f->sym) {
+            for (int c = C - 1; c >= 0; c--) fdm_sweep_global(f, w, f->clo[c], f->chi[c], false);
+            fdm_scale_global(f, w, false);
+            for (int c = 0; c < C; c++) fdm_sweep_global(f, w, f->clo[c], f->chi[c], false);
+        } else {
+            fdm_scale_global(f, w, false);
+            for (int c = C - 1; c >= 0; c--) fdm_sweep_global(f, w, f->clo[c], f->chi[c], false);
+        }
+    }
+    k_combine_global<<<g, 256, 0, f->stream>>>(out, in, w, (int)f->L, (int)f->N, transposed ? 1 : 0);
+    SQ_LAUNCH_CHECK();
+    f->launches += 2;
+}
+
+// out = op(in) on device vectors.  out may alias in (a copy through tmp2 is made).
+// For SQ_OP_MTM with pAp_partials != nullptr the per-CTA partial sums of |M in|^2 are written there.
+void fdm_mul_dev(sq_fdm *f, int op, double2 *out, const double2 *in, double *pAp_partials, int *npart,
+                 const CgState *skip) {
+    SQ_REQUIRE(op >= 0 && op <= 3, "unknown operator id");
+    const double2 *src = in;
+    if (out == in) {
+        SQ_CUDA(cudaMemcpyAsync(f->tmp2.p, in, f->vec_bytes(), cudaMemcpyDeviceToDevice, f->stream));
+        src = f->tmp2.p;
+    }
+    if (f->path == 0) {
+        int S = f->slab, T = f->threads;
+        if (op == 2) {
+            launch_fused<2>(f, S, T, out, src, pAp_partials, skip);
+            if (npart) *npart = (int)((f->L + S - 1) / S);
+        } else if (op == 0) launch_fused<0>(f, S, T, out, src, nullptr, skip);
+        else if (op == 1) launch_fused<1>(f, S, T, out, src, nullptr, skip);
+        else {
+            launch_fused<1>(f, S, T, f->tmp1.p, src, nullptr, skip);
+            launch_fused<0>(f, S, T, out, f->tmp1.p, nullptr, skip);
+        }
+    } else {
+        double2 *w = f->io2.p;                           // scratch (never a caller-visible vector)
+        if (op == 0) mul_global(f, false, out, src, w);
+        else if (op == 1) mul_global(f, true, out, src, w);
+        else if (op == 2) {
+            mul_global(f, false, f->tmp1.p, src, w);
+            if (pAp_partials) {
+                int nb = std::min<int>(SQ_MAXPART, f->num_sms * 4);
+                k_norm2_partials<<<nb, 256, 0, f->stream>>>(f->tmp1.p, (size_t)f->L * f->N, pAp_partials);
+                SQ_LAUNCH_CHECK();
+                f->launches++;
+                if (npart) *npart = nb;
+            }
+            mul_global(f, true, out, f->tmp1.p, w);
+        } else {
+            mul_global(f, true, f->tmp1.p, src, w);
+            mul_global(f, false, out, f->tmp1.p, w);
+        }
+    }
+}
+
+// choose (slab, threads) by timing the fused kernel on the device (done once per handle)
+static void fdm_autotune(sq_fdm *f) {
+    size_t lim = f->smem_optin;
+    int Smax = 0;
+    for (int S = 1; S <= f->L; S++) {
+        if (fused_smem_bytes(f, 2, S) <= lim) Smax = S; else break;
+    }
+    if (Smax == 0) { f->path = 1; f->slab = 0; f->threads = 256; return; }
+    f->path = 0;
+    const char *envS = getenv("SQ_SLAB"), *envT = getenv("SQ_THREADS");
+    if (envS && envT) { f->slab = std::min(Smax, std::max(1, atoi(envS))); f->threads = atoi(envT); return; }
+    std::vector<int> Ss;
+    for (int S = 1; S <= Smax; S++) {
+        int nsl = (int)((f->L + S - 1) / S);
+        // keep candidates that change the CTA count
+        if (S == 1 || (int)((f->L + S - 2) / (S - 1)) != nsl) Ss.push_back(S);
+    }
+    if (Ss.size() > 12) {   // thin out: prefer CTA counts near multiples of the SM count
+        std::vector<int> keep;
+        for (int S : Ss) {
+            int nsl = (int)((f->L + S - 1) / S);
+            if (S <= 4 || nsl <= 2 * f->num_sms) keep.push_back(S);
+        }
+        Ss = keep;
+        while (Ss.size() > 12) Ss.erase(Ss.begin() + Ss.size() / 2);
+    }
+    cudaEvent_t e0, e1;
+    SQ_CUDA(cudaEventCreate(&e0));
+    SQ_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    int bS = Ss[0], bT = 256;
+    for (int S : Ss) {
+        for (int T : {256, 512, 1024}) {
+            for (int rep = 0; rep < 2; rep++) launch_fused<2>(f, S, T, f->z.p, f->p.p, nullptr, nullptr);
+            SQ_CUDA(cudaEventRecord(e0, f->stream));
+            for (int rep = 0; rep < 5; rep++) launch_fused<2>(f, S, T, f->z.p, f->p.p, nullptr, nullptr);
+            SQ_CUDA(cudaEventRecord(e1, f->stream));
+            SQ_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            SQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (ms < best) { best = ms; bS = S; bT = T; }
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    f->slab = bS;
+    f->threads = bT;
+    f->launches = 0;
+}
+
+void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt, const i64 *perm, i64 C,
+                     const i64 *clo, const i64 *chi, double tol, i64 maxiter, int device) {
+    SQ_REQUIRE(out != nullptr, "out handle pointer is NULL");
+    SQ_REQUIRE(L >= 1 && N >= 1 && Nh >= 0 && C >= 0, "bad dimensions");
+    SQ_REQUIRE(C <= SQ_MAXC, "too many checkerboard colours (max 32)");
+    SQ_REQUIRE((size_t)L * (size_t)std::max(N, Nh) < (size_t)1 << 31, "space-time volume too large for 32-bit indexing");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        throw SqError("no CUDA device available: libsmoqyelph_b200 has no CPU fallback");
+    SQ_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+    SQ_CUDA(cudaSetDevice(device));
+    sq_fdm *f = new sq_fdm();
+    try {
+        f->device = device; f->sym = sym ? 1 : 0; f->L = L; f->N = N; f->Nh = Nh; f->C = C;
+        f->tol = tol; f->maxiter = maxiter;
+        cudaDeviceProp prop;
+        SQ_CUDA(cudaGetDeviceProperties(&prop, device));
+        f->num_sms = prop.multiProcessorCount;
+        f->smem_optin = prop.sharedMemPerBlockOptin - 1024;   // leave room for the kernels' static shared memory
+        SQ_CUDA(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+        SQ_CUDA(cudaFuncSetAttribute(k_fdm_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        SQ_CUDA(cudaFuncSetAttribute(k_fdm_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        SQ_CUDA(cudaFuncSetAttribute(k_fdm_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        std::vector<char> covered(N, 0);
+        f->h_nt.resize(Nh);
+        f->h_perm.resize(Nh);
+        for (i64 h = 0; h < Nh; h++) {
+            i64 i = nt[2 * h] - 1, j = nt[2 * h + 1] - 1, p = perm[h] - 1;
+            SQ_REQUIRE(i >= 0 && i < N && j >= 0 && j < N && i != j, "neighbour table entry out of range");
+            SQ_REQUIRE(p >= 0 && p < Nh, "checkerboard permutation entry out of range");
+            f->h_nt[h] = make_int2((int)i, (int)j);
+            f->h_perm[h] = (int)p;
+        }
+        i64 expect = 0;
+        for (i64 c = 0; c < C; c++) {
+            i64 lo = clo[c] - 1, hi = chi[c];        // 1-based inclusive -> 0-based half-open
+            SQ_REQUIRE(lo == expect && hi >= lo && hi <= Nh, "colour ranges must tile 1..Nh in order");
+            expect = hi;
+            f->clo.push_back((int)lo);
+            f->chi.push_back((int)hi);
+            std::vector<char> seen(N, 0);
+            for (i64 h = lo; h < hi; h++) {
+                int2 ij = f->h_nt[h];
+                SQ_REQUIRE(!seen[ij.x] && !seen[ij.y], "two bonds of one colour share a site");
+                seen[ij.x] = seen[ij.y] = 1;
+                if (c == 0) covered[ij.x] = covered[ij.y] = 1;
+            }
+        }
+        SQ_REQUIRE(expect == Nh, "colour ranges do not cover all bonds");
+        std::vector<int> unc;
+        for (i64 i = 0; i < N; i++) if (!covered[i]) unc.push_back((int)i);
+        f->nunc0 = (int)unc.size();
+        f->nt.alloc(Nh + 1); f->nt.upload(f->h_nt.data(), Nh, f->stream);
+        f->perm.alloc(Nh + 1); f->perm.upload(f->h_perm.data(), Nh, f->stream);
+        f->unc0.alloc(unc.size() + 1); f->unc0.upload(unc.data(), unc.size(), f->stream);
+        size_t V = (size_t)L * N;
+        f->expV.alloc(V); f->cs.alloc((size_t)L * Nh + 1);
+        f->tmp1.alloc(V); f->tmp2.alloc(V); f->r.alloc(V); f->p.alloc(V); f->z.alloc(V);
+        f->io1.alloc(V); f->io2.alloc(V);
+        size_t nreal = (size_t)L * std::max(N, Nh) + 1;
+        f->iod1.alloc(nreal); f->iod2.alloc(nreal);
+        f->part.alloc(8 * SQ_MAXPART);
+        f->cg.alloc(2);
+        SQ_CUDA(cudaMallocHost((void **)&f->h_cg, 2 * sizeof(CgState)));
+        // neutral operator (V = 0, t = 0) so that the autotuner runs on finite numbers
+        std::vector<double> ones(V, 1.0);
+        f->expV.upload(ones.data(), V, f->stream);
+        std::vector<double2> cs1((size_t)L * Nh + 1, make_double2(1.0, 0.0));
+        f->cs.upload(cs1.data(), (size_t)L * Nh, f->stream);
+        SQ_CUDA(cudaStreamSynchronize(f->stream));
+        fdm_autotune(f);
+        SQ_CUDA(cudaStreamSynchronize(f->stream));
+    } catch (...) {
+        delete f;
+        throw;
+    }
+    *out = f;
+}
+
+void fdm_destroy_impl(sq_fdm *f) {
+    if (!f) return;
+    cudaSetDevice(f->device);
+    if (f->stream) { cudaStreamSynchronize(f->stream); cudaStreamDestroy(f->stream); }
+    if (f->h_cg) cudaFreeHost(f->h_cg);
+    delete f;
+}
+
+// device V ([l][i]) and t ([l][h], original order) -> operator coefficients
+void fdm_update_dev(sq_fdm *f, const double *dV, const double *dt_, double dtau) {
+    size_t tot = (size_t)f->L * std::max(f->N, f->Nh);
+    k_fdm_update<<<(unsigned)((tot + 255) / 256), 256, 0, f->stream>>>(f->expV.p, f->cs.p, dV, dt_, f->perm.p, (int)f->L,
+                                                                        (int)f->N, (int)f->Nh, dtau, f->sym ? dtau / 2 : dtau);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+    f->coef_version++;
+}
+
+void fdm_update_impl(sq_fdm *f, const double *V, const double *t, double dtau) {
+    SQ_CUDA(cudaSetDevice(f->device));
+    f->iod1.upload(V, (size_t)f->L * f->N, f->stream);
+    f->iod2.upload(t, (size_t)f->L * f->Nh, f->stream);
+    fdm_update_dev(f, f->iod1.p, f->iod2.p, dtau);
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
+}
+
+void fdm_get_coefficients_impl(sq_fdm *f, double *expV, double *ch, double *sh) {
+    SQ_CUDA(cudaSetDevice(f->device));
+    size_t nV = (size_t)f->L * f->N, nT = (size_t)f->L * f->Nh;
+    std::vector<double> hV(nV);
+    std::vector<double2> hcs(nT + 1);
+    f->expV.download(hV.data(), nV, f->stream);
+    f->cs.download(hcs.data(), nT, f->stream);
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
+    for (i64 l = 0; l < f->L; l++) {
+        for (i64 i = 0; i < f->N; i++) expV[l + i * f->L] = hV[i + l * f->N];
+        for (i64 h = 0; h < f->Nh; h++) { ch[l + h * f->L] = hcs[h + l * f->Nh].x; sh[l + h * f->L] = hcs[h + l * f->Nh].y; }
+    }
+}
+
+void fdm_mul_impl(sq_fdm *f, int op, void *out, const void *in) {
+    SQ_CUDA(cudaSetDevice(f->device));
+    fdm_host_to_dev(f, f->r.p, in);
+    fdm_mul_dev(f, op, f->z.p, f->r.p);
+    fdm_dev_to_host(f, out, f->z.p);
+}

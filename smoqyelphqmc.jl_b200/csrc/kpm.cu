@@ -1,0 +1,468 @@
+// kpm.cu -- K4: the KPM / tau-Fourier preconditioner  P^-1 = [Mbar^T Mbar]^-1.
+//
+// Replaces src/KPMPreconditioner.jl: ldiv! (Sym complex :355-414, Asym complex :488-550),
+// update_preconditioner! (:554-597), update_B̄! (:604-621), calculate_bounds! (:625-658),
+// update_kpm_expansion_order!/coefs! (:696-795), and the un-vendored SmoQyKPMCore kernels kpm_lmul!,
+// kpm_coefs!, lanczos! plus JDQMCFramework's Sym/AsymChkbrdPropagator mul! that they call.
+//
+// Apply = forward tau-FFT (fft.cu; also applies the order-1 "scalar" frequencies) -> one CTA per
+// frequency with expansion order > 1 runs the whole Chebyshev recurrence of B-bar on its N-vector in
+// shared memory -> inverse tau-FFT (optionally fused with the CG r.z reduction).  The frequency-major
+// layout falls out of the [l][i] device layout, so the reference's two transposes do not exist here.
+// Frequencies are scheduled longest-recurrence-first.  Bounds, orders and coefficients are tiny scalar
+// work and are computed on the host in double precision exactly as the reference does.
+#include "sq_internal.h"
+
+#include <algorithm>
+#include <cmath>
+
+int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, int N, double2 *out, const double2 *in, bool inverse,
+                   bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
+                   double *dot_part, const CgState *skip, size_t smem_limit);
+
+struct BbarParams {
+    int N, Nh, C, sym;
+    int clo[SQ_MAXC], chi[SQ_MAXC];
+    const int2 *nt;
+    const double2 *csbar;
+    const double *Dbar;
+};
+
+__device__ __forceinline__ void rotb(double2 &a, double2 &b, double c, double s) {
+    double2 na = make_double2(fma(s, b.x, c * a.x), fma(s, b.y, c * a.y));
+    double2 nb = make_double2(fma(s, a.x, c * b.x), fma(s, a.y, c * b.y));
+    a = na;
+    b = nb;
+}
+
+__device__ __forceinline__ void bbar_color(double2 *y, int c, const BbarParams &P) {
+    const int lo = P.clo[c], nb = P.chi[c] - lo;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        int2 ij = __ldg(P.nt + lo + b);
+        double2 cs = __ldg(P.csbar + lo + b);
+        double2 a = y[ij.x], bb = y[ij.y];
+        rotb(a, bb, cs.x, cs.y);
+        y[ij.x] = a;
+        y[ij.y] = bb;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void bbar_diag(double2 *y, const BbarParams &P, bool squared) {
+    for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
+        double d = __ldg(P.Dbar + i);
+        if (squared) d *= d;
+        double2 a = y[i];
+        y[i] = make_double2(d * a.x, d * a.y);
+    }
+    __syncthreads();
+}
+// y <- B-bar y in shared memory.  Sym: Gamma D Gamma^T; Asym: D Gamma.  (KPMPreconditioner.jl:260,274)
+__device__ __forceinline__ void bbar_apply(double2 *y, const BbarParams &P) {
+    if (P.sym) {
+        for (int c = P.C - 1; c >= 0; c--) bbar_color(y, c, P);
+        bbar_diag(y, P, false);
+        for (int c = 0; c < P.C; c++) bbar_color(y, c, P);
+    } else {
+        for (int c = 0; c < P.C; c++) bbar_color(y, c, P);
+        bbar_diag(y, P, false);
+    }
+}
+// y <- B-bar^T B-bar y (Asym Lanczos operator, :661-679)
+__device__ __forceinline__ void bbar_apply_BtB(double2 *y, const BbarParams &P) {
+    for (int c = 0; c < P.C; c++) bbar_color(y, c, P);
+    bbar_diag(y, P, true);
+    for (int c = P.C - 1; c >= 0; c--) bbar_color(y, c, P);
+}
+
+// v <- sum_q c_q T_q(B') v with B' = (B-bar - avg)/mag   [kpm_lmul!]
+__device__ __forceinline__ void cheb_apply(double2 *T0, double2 *T1, double2 *Y, double2 *ACC, const double2 *__restrict__ c, int ord,
+                                           double avg, double imag_, const BbarParams &P) {
+    const int N = P.N;
+    // entry: T0 = v.  T1 = B' v
+    for (int i = threadIdx.x; i < N; i += blockDim.x) Y[i] = T0[i];
+    __syncthreads();
+    bbar_apply(Y, P);
+    double2 c0 = c[0], c1 = c[1];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        double2 t0 = T0[i], y = Y[i];
+        double2 t1 = make_double2((y.x - avg * t0.x) * imag_, (y.y - avg * t0.y) * imag_);
+        T1[i] = t1;
+        Y[i] = t1;
+        ACC[i] = cadd(cmul(c0, t0), cmul(c1, t1));
+    }
+    __syncthreads();
+    for (int q = 2; q < ord; q++) {
+        bbar_apply(Y, P);                              // Y = B-bar T1 (Y held a copy of T1)
+        double2 cq = c[q];
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            double2 t0 = T0[i], t1 = T1[i], y = Y[i];
+            double2 t2 = make_double2(2.0 * (y.x - avg * t1.x) * imag_ - t0.x, 2.0 * (y.y - avg * t1.y) * imag_ - t0.y);
+            T0[i] = t1;                                // shift the window: (T0, T1) <- (T1, T2)
+            T1[i] = t2;
+            Y[i] = t2;
+            ACC[i] = cadd(ACC[i], cmul(cq, t2));
+        }
+        __syncthreads();
+    }
+}
+
+// one CTA per scheduled frequency.  z is [n][i].  For the Asym preconditioner two expansions are applied
+// back to back (coefficients of the mirrored frequency, then of this one).
+__global__ void __launch_bounds__(1024, 1)
+k_kpm_cheb(const __grid_constant__ BbarParams P, double2 *__restrict__ z, const int *__restrict__ sched, const int *__restrict__ order,
+           const int *__restrict__ coef_off, const double2 *__restrict__ coefs, int L, double avg, double imag_,
+           const CgState *__restrict__ skip) {
+    extern __shared__ double2 sm[];
+    if (skip && skip->done) return;
+    const int N = P.N;
+    double2 *T0 = sm, *T1 = sm + N, *Y = sm + 2 * (size_t)N, *ACC = sm + 3 * (size_t)N;
+    const int n = sched[blockIdx.x];
+    double2 *zn = z + (size_t)n * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) T0[i] = zn[i];
+    __syncthreads();
+    if (P.sym) {
+        int np = (n + 1 > (L + 1) / 2) ? L - 1 - n : n;                       // :387
+        cheb_apply(T0, T1, Y, ACC, coefs + coef_off[np], order[np], avg, imag_, P);
+    } else {
+        int nm = L - 1 - n;
+        cheb_apply(T0, T1, Y, ACC, coefs + coef_off[nm], order[nm], avg, imag_, P);   // :527
+        for (int i = threadIdx.x; i < N; i += blockDim.x) T0[i] = ACC[i];
+        __syncthreads();
+        cheb_apply(T0, T1, Y, ACC, coefs + coef_off[n], order[n], avg, imag_, P);     // :530
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) zn[i] = ACC[i];
+}
+
+// tau-means of the operator coefficients (update_B̄!, :604-621): grid over sites/bonds, 32 x 8 threads
+__global__ void k_tau_means(double *__restrict__ Dbar, double2 *__restrict__ csbar, const double *__restrict__ expV,
+                            const double2 *__restrict__ cs, int L, int N, int Nh) {
+    __shared__ double sx[8][33], sy[8][33];
+    int idx = blockIdx.x * 32 + threadIdx.x;
+    double ax = 0, ay = 0;
+    if (idx < N) {
+        for (int l = threadIdx.y; l < L; l += 8) ax += expV[(size_t)l * N + idx];
+    } else if (idx - N < Nh && idx >= N) {
+        int h = idx - N;
+        for (int l = threadIdx.y; l < L; l += 8) { double2 v = cs[(size_t)l * Nh + h]; ax += v.x; ay += v.y; }
+    }
+    sx[threadIdx.y][threadIdx.x] = ax;
+    sy[threadIdx.y][threadIdx.x] = ay;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        double tx = 0, ty = 0;
+        for (int k = 0; k < 8; k++) { tx += sx[k][threadIdx.x]; ty += sy[k][threadIdx.x]; }
+        if (idx < N) Dbar[idx] = tx / L;
+        else if (idx - N < Nh) csbar[idx - N] = make_double2(tx / L, ty / L);
+    }
+}
+
+// Lanczos on B-bar (Sym) or B-bar^T B-bar (Asym) in one CTA  [lanczos!], plain three-term recurrence.
+// out[0..n) = alpha, out[n..2n-1) = beta.
+__global__ void __launch_bounds__(1024, 1)
+k_lanczos(const __grid_constant__ BbarParams P, const double *__restrict__ start, int n, double *__restrict__ out) {
+    extern __shared__ double2 sm[];
+    __shared__ double red[32];
+    __shared__ double bc;
+    const int N = P.N;
+    double2 *vp = sm, *v = sm + N, *w = sm + 2 * (size_t)N;
+    double acc = 0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { double s = start[i]; acc += s * s; }
+    double t1[1] = {acc};
+    block_sum<1>(t1, red);
+    if (threadIdx.x == 0) bc = sqrt(t1[0]);
+    __syncthreads();
+    double nrm = bc;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { v[i] = make_double2(start[i] / nrm, 0.0); vp[i] = make_double2(0, 0); }
+    __syncthreads();
+    double bprev = 0;
+    for (int j = 0; j < n; j++) {
+        for (int i = threadIdx.x; i < N; i += blockDim.x) w[i] = v[i];
+        __syncthreads();
+        if (P.sym) bbar_apply(w, P); else bbar_apply_BtB(w, P);
+        acc = 0;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) acc += v[i].x * w[i].x;
+        t1[0] = acc;
+        block_sum<1>(t1, red);
+        if (threadIdx.x == 0) bc = t1[0];
+        __syncthreads();
+        double a = bc;
+        acc = 0;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            double x = w[i].x - a * v[i].x - bprev * vp[i].x;
+            w[i].x = x;
+            acc += x * x;
+        }
+        t1[0] = acc;
+        block_sum<1>(t1, red);
+        if (threadIdx.x == 0) { bc = sqrt(t1[0]); out[j] = a; if (j < n - 1) out[n + j] = bc; }
+        __syncthreads();
+        double b = bc;
+        if (j < n - 1) {
+            // breakdown (b == 0) leaves zeros in the remaining entries; the host truncates there
+            if (b < 1e-300) { for (int q = j + 1 + threadIdx.x; q < n; q += blockDim.x) { out[q] = 0; if (q < n - 1) out[n + q] = 0; } return; }
+            for (int i = threadIdx.x; i < N; i += blockDim.x) { vp[i] = v[i]; v[i] = make_double2(w[i].x / b, 0.0); }
+            bprev = b;
+            __syncthreads();
+        }
+    }
+}
+
+// global-memory fallback of B-bar v is not provided: the preconditioner requires 4 N-vectors in shared memory.
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static BbarParams bbar_params(const sq_kpm *k) {
+    const sq_fdm *f = k->f;
+    BbarParams P;
+    P.N = (int)f->N; P.Nh = (int)f->Nh; P.C = (int)f->C; P.sym = f->sym;
+    for (int c = 0; c < SQ_MAXC; c++) { P.clo[c] = c < f->C ? f->clo[c] : 0; P.chi[c] = c < f->C ? f->chi[c] : 0; }
+    P.nt = f->nt.p; P.csbar = k->csbar.p; P.Dbar = k->Dbar.p;
+    return P;
+}
+
+static int kpm_threads(const sq_kpm *k) {
+    int nbmax = 32;
+    for (int c = 0; c < k->f->C; c++) nbmax = std::max(nbmax, k->f->chi[c] - k->f->clo[c]);
+    int t = 32;
+    while (t < nbmax && t < 1024) t <<= 1;
+    return t;
+}
+
+static void sturm_extremes(const std::vector<double> &a, const std::vector<double> &b, int n, double *emin, double *emax) {
+    auto count = [&](double x) {
+        int cnt = 0;
+        double d = 1.0;
+        for (int i = 0; i < n; i++) {
+            double bb = (i == 0) ? 0.0 : b[i - 1] * b[i - 1];
+            d = a[i] - x - (d != 0.0 ? bb / d : bb / 1e-300);
+            if (d < 0) cnt++;
+        }
+        return cnt;
+    };
+    double lo = a[0], hi = a[0];
+    for (int i = 0; i < n; i++) {
+        double r = (i > 0 ? fabs(b[i - 1]) : 0) + (i < n - 1 ? fabs(b[i]) : 0);
+        lo = std::min(lo, a[i] - r);
+        hi = std::max(hi, a[i] + r);
+    }
+    double l = lo, h = hi;
+    for (int it = 0; it < 200; it++) { double m = 0.5 * (l + h); if (count(m) >= 1) h = m; else l = m; }
+    *emin = 0.5 * (l + h);
+    l = lo; h = hi;
+    for (int it = 0; it < 200; it++) { double m = 0.5 * (l + h); if (count(m) >= n) h = m; else l = m; }
+    *emax = 0.5 * (l + h);
+}
+
+static void kpm_refresh_bbar(sq_kpm *k) {
+    sq_fdm *f = k->f;
+    if (k->bbar_version == f->coef_version) return;      // operator unchanged since the last refresh
+    int tot = (int)(f->N + f->Nh);
+    k_tau_means<<<(tot + 31) / 32, dim3(32, 8), 0, f->stream>>>(k->Dbar.p, k->csbar.p, f->expV.p, f->cs.p, (int)f->L, (int)f->N, (int)f->Nh);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+    k->bbar_version = f->coef_version;
+}
+
+// Chebyshev-Gauss coefficients [kpm_coefs!]: c_q = (2 - delta_q0)/Nq sum_j f(x_j) cos(q pi (j + 1/2)/Nq), Nq = 2 order
+static void cheb_coefs(std::vector<double2> &c, int order, bool sym, double phi, const double bounds[2]) {
+    const double PI = 3.14159265358979323846;
+    int Nq = 2 * order;
+    double avg = 0.5 * (bounds[1] + bounds[0]), mag = 0.5 * (bounds[1] - bounds[0]);
+    std::vector<double2> fx(Nq);
+    for (int j = 0; j < Nq; j++) {
+        double x = mag * cos(PI * (j + 0.5) / Nq) + avg;
+        if (sym) fx[j] = make_double2(1.0 / (x * x - 2 * x * cos(phi) + 1), 0.0);            // f_B̄_sym :800
+        else {                                                                                // f_B̄_asym :804
+            double re = 1.0 - cos(phi) * x, im = sin(phi) * x, d = re * re + im * im;
+            fx[j] = make_double2(re / d, -im / d);
+        }
+    }
+    c.assign(order, make_double2(0, 0));
+    for (int q = 0; q < order; q++) {
+        double sr = 0, si = 0;
+        for (int j = 0; j < Nq; j++) {
+            double cs = cos(PI * q * (j + 0.5) / Nq);
+            sr += fx[j].x * cs;
+            si += fx[j].y * cs;
+        }
+        double w = (q == 0 ? 1.0 : 2.0) / Nq;
+        c[q] = make_double2(w * sr, w * si);
+    }
+}
+
+// update_kpm_expansion_order! + update_kpm_expansion_coefs! (:696-795) and upload
+static void kpm_update_expansions(sq_kpm *k) {
+    const double PI = 3.14159265358979323846;
+    sq_fdm *f = k->f;
+    int L = (int)f->L;
+    double emin = k->bounds[0], emax = k->bounds[1];
+    for (i64 l = 0; l < k->ncoef; l++) {
+        double phi = 2 * PI / L * (l + 0.5);
+        double ph = phi > PI ? 2 * PI - phi : phi;
+        i64 n = (i64)floor((emax - emin) * (k->a1 / ph + k->a2));
+        k->order[l] = std::max<i64>(1, n);
+    }
+    if (f->sym) {
+        for (i64 l = 0; l < k->ncoef; l++) cheb_coefs(k->coefs[l], (int)k->order[l], true, 2 * PI / L * (l + 0.5), k->bounds);
+    } else {
+        for (i64 l = 0; l < (L + 1) / 2; l++) {
+            cheb_coefs(k->coefs[l], (int)k->order[l], false, 2 * PI / L * (l + 0.5), k->bounds);
+            i64 m = L - 1 - l;
+            k->coefs[m] = k->coefs[l];
+            for (auto &c : k->coefs[m]) c.y = -c.y;
+        }
+    }
+    // flatten and upload; build the launch schedule (frequencies with order > 1, longest first) and the
+    // per-frequency scalar for order-1 frequencies
+    std::vector<int> h_order(k->ncoef), h_off(k->ncoef);
+    std::vector<double2> flat;
+    int maxo = 0;
+    for (i64 l = 0; l < k->ncoef; l++) {
+        h_order[l] = (int)k->order[l];
+        h_off[l] = (int)flat.size();
+        flat.insert(flat.end(), k->coefs[l].begin(), k->coefs[l].end());
+        if (k->coefs[l].size() < 2) flat.push_back(make_double2(0, 0));   // c[1] is always readable
+        maxo = std::max(maxo, h_order[l]);
+    }
+    k->max_order = maxo;
+    std::vector<std::pair<int, int>> sched;
+    std::vector<double> scale1(L, 1.0);
+    for (int n = 0; n < L; n++) {
+        int np = f->sym ? ((n + 1 > (L + 1) / 2) ? L - 1 - n : n) : n;
+        if (h_order[np] > 1) sched.push_back({-h_order[np], n});
+        else {
+            double2 c = k->coefs[np][0];
+            scale1[n] = f->sym ? c.x : (c.x * c.x + c.y * c.y);              // :398 / :534
+        }
+    }
+    std::sort(sched.begin(), sched.end());
+    std::vector<int> h_sched;
+    for (auto &p : sched) h_sched.push_back(p.second);
+    k->nsched = (int)h_sched.size();
+    k->d_order.alloc(h_order.size() + 1, false); k->d_order.upload(h_order.data(), h_order.size(), f->stream);
+    k->d_coef_off.alloc(h_off.size() + 1, false); k->d_coef_off.upload(h_off.data(), h_off.size(), f->stream);
+    k->d_coefs.alloc(flat.size() + 1, false); k->d_coefs.upload(flat.data(), flat.size(), f->stream);
+    k->d_freq_sched.alloc(h_sched.size() + 1, false); k->d_freq_sched.upload(h_sched.data(), h_sched.size(), f->stream);
+    k->d_scale1.alloc(L, false); k->d_scale1.upload(scale1.data(), L, f->stream);
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
+}
+
+void kpm_create_impl(sq_kpm **out, sq_fdm *f, double rbuf, i64 n, double a1, double a2) {
+    SQ_REQUIRE(out && f, "NULL argument");
+    SQ_REQUIRE(n >= 2 && n <= 512, "number of Lanczos iterations out of range");
+    SQ_REQUIRE((size_t)4 * f->N * sizeof(double2) <= f->smem_optin, "lattice too large for the shared-memory KPM kernel");
+    SQ_CUDA(cudaSetDevice(f->device));
+    sq_kpm *k = new sq_kpm();
+    try {
+        k->f = f; k->rbuf = rbuf; k->nlanczos = n; k->a2 = a2;
+        k->a1 = f->sym ? 2 * a1 : a1;                                   // :263
+        k->ncoef = f->sym ? (f->L + 1) / 2 : f->L;
+        k->order.assign(k->ncoef, 0);
+        k->coefs.resize(k->ncoef);
+        k->Dbar.alloc(f->N); k->csbar.alloc(f->Nh + 1);
+        std::vector<double2> tw, th(f->L);
+        fft_make_twiddles(f->L, tw);
+        const long double PI = 3.141592653589793238462643383279502884L;
+        for (i64 l = 0; l < f->L; l++) {
+            long double a = -PI * (long double)l / (long double)f->L;   // FourierTransformer.jl:15
+            th[l] = make_double2((double)cosl(a), (double)sinl(a));
+        }
+        k->tw.alloc(f->L, false); k->tw.upload(tw.data(), f->L, f->stream);
+        k->theta.alloc(f->L, false); k->theta.upload(th.data(), f->L, f->stream);
+        SQ_CUDA(cudaStreamSynchronize(f->stream));
+        fft_radices(f->L, k->radices);
+        k->ztmp.alloc((size_t)f->L * f->N);
+        k->lan.alloc(2 * n);
+        k->lan_start.alloc(f->N);
+        SQ_CUDA(cudaFuncSetAttribute(k_kpm_cheb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        SQ_CUDA(cudaFuncSetAttribute(k_lanczos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+    } catch (...) {
+        delete k;
+        throw;
+    }
+    *out = k;
+}
+
+void kpm_set_bounds(sq_kpm *k, double emin, double emax) {
+    kpm_refresh_bbar(k);
+    k->bounds[0] = emin; k->bounds[1] = emax; k->active = 1;
+    kpm_update_expansions(k);
+}
+
+// calculate_bounds! on the device; returns the raw Lanczos extremes
+void kpm_lanczos(sq_kpm *k, const double *h_start, const double *d_start, double *emin, double *emax) {
+    sq_fdm *f = k->f;
+    kpm_refresh_bbar(k);
+    const double *start = d_start;
+    if (!start) {
+        if (h_start) k->lan_start.upload(h_start, f->N, f->stream);
+        else rng_fill_normal(k->lan_start.p, f->N, 0x5eedULL, k->rng_counter++, f->stream);
+        start = k->lan_start.p;
+    }
+    int n = (int)k->nlanczos;
+    BbarParams P = bbar_params(k);
+    k_lanczos<<<1, kpm_threads(k), 3 * f->N * sizeof(double2), f->stream>>>(P, start, n, k->lan.p);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+    std::vector<double> h(2 * n);
+    k->lan.download(h.data(), 2 * n, f->stream);
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
+    std::vector<double> a(h.begin(), h.begin() + n), b(h.begin() + n, h.begin() + 2 * n - 1);
+    int used = n;
+    for (int j = 0; j < n - 1; j++) if (!(b[j] >= 1e-300)) { used = j + 1; break; }
+    for (int j = 0; j < used; j++) if (!(a[j] == a[j])) throw SqError("KPM preconditioner: NaN in the Lanczos recurrence");
+    sturm_extremes(a, b, used, emin, emax);
+    if (!f->sym) { *emin = sqrt(*emin); *emax = sqrt(*emax); }          // :655
+}
+
+// update_preconditioner! (:554-597)
+void kpm_update(sq_kpm *k, const double *h_start, const double *d_start) {
+    double emin, emax;
+    kpm_lanczos(k, h_start, d_start, &emin, &emax);
+    emin *= (1 - k->rbuf);
+    emax *= (1 + k->rbuf);
+    if (0.0 < emin && emin < 1.0 && 1.0 < emax && emax < 2.0) {
+        k->active = 1;
+        double e0 = k->bounds[0], e1 = k->bounds[1];
+        if (e0 == 0.0 || fabs((emin - e0) / e0) > k->rbuf / 2 || fabs((emax - e1) / e1) > k->rbuf / 2) {
+            k->bounds[0] = emin; k->bounds[1] = emax;
+            kpm_update_expansions(k);
+        }
+    } else k->active = 0;
+}
+
+// out = P^-1 in  on device [l][i] vectors (out may alias in).  dot partial fusion is requested by cg.cu.
+int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *skip, const double2 *dot_with, double *dot_part) {
+    sq_fdm *f = k->f;
+    size_t n = (size_t)f->L * f->N;
+    if (!k->active) {                                                    // :407-411
+        if (out != in) SQ_CUDA(cudaMemcpyAsync(out, in, n * sizeof(double2), cudaMemcpyDeviceToDevice, f->stream));
+        return 0;
+    }
+    double2 *zt = k->ztmp.p;
+    tau_fft_launch(f->stream, k->radices, (int)f->L, (int)f->N, zt, in, false, true, k->tw.p, k->theta.p, k->d_scale1.p, nullptr, nullptr,
+                   skip, f->smem_optin);
+    if (k->nsched > 0) {
+        BbarParams P = bbar_params(k);
+        double avg = 0.5 * (k->bounds[1] + k->bounds[0]), mag = 0.5 * (k->bounds[1] - k->bounds[0]);
+        k_kpm_cheb<<<k->nsched, kpm_threads(k), 4 * f->N * sizeof(double2), f->stream>>>(P, zt, k->d_freq_sched.p, k->d_order.p,
+                                                                                        k->d_coef_off.p, k->d_coefs.p, (int)f->L, avg,
+                                                                                        1.0 / mag, skip);
+        SQ_LAUNCH_CHECK();
+        f->launches++;
+    }
+    int g = tau_fft_launch(f->stream, k->radices, (int)f->L, (int)f->N, out, zt, true, true, k->tw.p, k->theta.p, nullptr, dot_with,
+                           dot_part, skip, f->smem_optin);
+    f->launches += 2;
+    return g;
+}
+void kpm_ldiv_dev(sq_kpm *k, double2 *out, const double2 *in, const CgState *skip) { kpm_ldiv_dev_dot(k, out, in, skip, nullptr, nullptr); }
+
+void kpm_fourier_dev(sq_kpm *k, double2 *v, bool forward) {
+    sq_fdm *f = k->f;
+    tau_fft_launch(f->stream, k->radices, (int)f->L, (int)f->N, k->ztmp.p, v, !forward, true, k->tw.p, k->theta.p, nullptr, nullptr, nullptr,
+                   nullptr, f->smem_optin);
+    SQ_CUDA(cudaMemcpyAsync(v, k->ztmp.p, f->vec_bytes(), cudaMemcpyDeviceToDevice, f->stream));
+    f->launches++;
+}

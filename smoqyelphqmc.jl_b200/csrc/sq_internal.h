@@ -1,0 +1,178 @@
+// sq_internal.h -- handle definitions behind the opaque types of include/smoqyelph_b200.h
+#pragma once
+#include "common.cuh"
+#include "smoqyelph_b200.h"
+
+#define SQ_MAXC 32          // maximum number of checkerboard colours
+#define SQ_MAXPART 4096     // maximum number of per-CTA partial sums of one reduction
+
+// Device layout everywhere: site fastest, element (l, i) at i + l*N  ("[l][i]").
+// A time slice is a contiguous N-vector, tau-slabs are contiguous ranges.
+
+struct KParams {            // by-value kernel parameter block of the operator kernels
+    int L, N, Nh, C, sym;
+    int S;                  // slices owned by one CTA (fused kernels)
+    int TX, TXshift;        // threads along the bond / site index (power of two)
+    int clo[SQ_MAXC], chi[SQ_MAXC];
+    int nunc0;              // sites not touched by colour 0 (fused middle step)
+    const int2 *nt;         // Nh bonds (i, j), checkerboard order, 0-based
+    const double2 *cs;      // [l][h] (cosh, sinh)
+    const double *expV;     // [l][i]
+    const int *unc0;
+};
+
+struct CgState {            // device-resident CG scalars, ping-ponged between iterations
+    double rz_re, rz_im;    // r.z (or r.r)
+    double normb;           // |b|
+    double eps;             // |r|/|b| after the last completed iteration
+    double tol;
+    int iters, done;
+};
+
+struct sq_fdm {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sym = 1;
+    i64 L = 0, N = 0, Nh = 0, C = 0;
+    std::vector<int> clo, chi;
+    std::vector<int> h_perm;                 // checkerboard index -> original hopping (0-based)
+    std::vector<int2> h_nt;
+    DevBuf<int2> nt;
+    DevBuf<int> perm, unc0;
+    int nunc0 = 0;
+    DevBuf<double> expV;                     // [l][i]
+    DevBuf<double2> cs;                      // [l][h]
+    DevBuf<double2> tmp1, tmp2, r, p, z;     // [l][i]
+    DevBuf<double2> io1, io2;                // staging in the host (tau-fastest) layout
+    DevBuf<double> iod1, iod2;               // real staging
+    DevBuf<double> part;                     // 8 * SQ_MAXPART partial sums
+    DevBuf<CgState> cg;                      // 2 states
+    CgState *h_cg = nullptr;                 // pinned
+    double tol = 1e-6;
+    i64 maxiter = 0;
+    // fused-kernel configuration
+    int path = 0;                            // 0 = slices staged in shared memory, 1 = global-memory passes
+    int slab = 0, threads = 0;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+    i64 launches = 0;
+    i64 coef_version = 0;                    // bumped by every operator refresh (KPM B-bar cache)
+
+    KParams kparams(int S, int T) const;
+    size_t vec_bytes() const { return (size_t)L * N * sizeof(double2); }
+};
+
+struct sq_kpm {
+    sq_fdm *f = nullptr;
+    int active = 0;
+    double rbuf = 0.1, a1 = 1, a2 = 1;
+    i64 nlanczos = 20;
+    double bounds[2] = {0, 0};
+    i64 ncoef = 0;
+    std::vector<i64> order;
+    std::vector<std::vector<double2>> coefs;
+    // device
+    DevBuf<double> Dbar;                     // N
+    DevBuf<double2> csbar;                   // Nh
+    DevBuf<double2> tw;                      // Ltau forward twiddles exp(-2 pi i k / L)
+    DevBuf<double2> theta;                   // Ltau twist
+    DevBuf<int> d_order, d_coef_off, d_freq_sched;   // per frequency (Ltau): order, offset into d_coefs; schedule
+    DevBuf<double2> d_coefs;
+    DevBuf<double> d_scale1;                 // per frequency: scalar applied by the FFT store when order == 1
+    int nsched = 0;                          // frequencies with order > 1
+    DevBuf<double2> ztmp;                    // [n][i] frequency-space scratch
+    DevBuf<double> lan;                      // Lanczos alpha/beta read-back
+    DevBuf<double> lan_start;                // N
+    DevBuf<double2> cheb_ws;                 // workspace for the global-memory Chebyshev fallback
+    std::vector<int> radices;
+    i64 bbar_version = -1;
+    int max_order = 0;
+    uint64_t rng_counter = 0;
+};
+
+struct sq_elph {
+    sq_fdm *f = nullptr;
+    double dtau = 0;
+    i64 Nph = 0, Nhol = 0, Nssh = 0;
+    std::vector<double> h_M;
+    DevBuf<double> x;                        // [l][p]
+    DevBuf<double> Om, Om4, M;
+    DevBuf<int> fin;                         // isfinite(M[p])
+    // Holstein couplings
+    DevBuf<int> hol_ph, hol_site, hol_sym;
+    DevBuf<double> ha;                       // a[c], a2[Nhol+c], a3[2Nhol+c], a4[3Nhol+c]
+    DevBuf<int> site_ptr, site_cpl;          // CSR: site -> Holstein couplings (ascending coupling index)
+    // SSH couplings
+    DevBuf<int> ssh_p, ssh_pp;               // the phonon pair (p, p') of each coupling
+    DevBuf<int> ssh_bond;                    // checkerboard bond index the coupling modulates
+    DevBuf<double> sa;                       // 4 * Nssh
+    DevBuf<int> bond_ptr, bond_cpl;          // CSR: checkerboard bond -> SSH couplings
+    // force gather lists: phonon -> Holstein couplings, phonon -> signed SSH couplings (+-(c+1))
+    DevBuf<int> ph_hol_ptr, ph_hol_cpl, ph_ssh_ptr, ph_ssh_cpl;
+    DevBuf<double> V0, t0;                   // bare on-site energy (N), bare hopping (Nh, ORIGINAL order)
+    DevBuf<double> V, t;                     // materialised only by sq_elph_get_Vt: [l][i], [l][h] original order
+    bool any_phsym = false;
+};
+
+struct sq_pff {
+    sq_elph *e = nullptr;
+    DevBuf<double2> Phi, u, up, upp, w1, w2; // [l][i]
+    DevBuf<double> Lam;                      // [l][i]
+    DevBuf<double> F;                        // [l][p] force accumulator on the device
+    DevBuf<double> HV, HL, SV;               // per-coupling force contributions [l][c]
+    DevBuf<double> part;                     // reduction partials
+    int exact_holstein = 0;
+    uint64_t seed = 0x0ff1ce, rng_counter = 0;
+};
+
+struct sq_hmc {
+    sq_pff *p = nullptr;
+    i64 Nt = 0;
+    double dt = 0, eta = 0, delta = 0;
+    uint64_t seed = 0, counter = 0;
+    DevBuf<double> x0, pm, dS;               // [l][p]
+    DevBuf<double> Mt, wd;                   // [w][p]
+    DevBuf<double2> fz, fw;                  // Fourier work arrays [w][p]
+    DevBuf<double2> tw;                      // twiddles
+    DevBuf<double> rnd;                      // random stream of one trajectory
+    DevBuf<double> part;
+    std::vector<int> radices;
+};
+
+struct sq_greens {
+    sq_fdm *f = nullptr;
+    i64 Nrv = 0;
+    uint64_t seed = 0, counter = 0;
+    DevBuf<double2> R, GR, MtR;              // Nrv vectors, [l][i] each
+    DevBuf<double> part;
+};
+
+// ---- functions shared between translation units (all enqueue on f->stream) ------------------------
+void fdm_mul_dev(sq_fdm *f, int op, double2 *out, const double2 *in, double *pAp_partials = nullptr,
+                 int *npart = nullptr, const CgState *skip_if_done = nullptr);
+void fdm_host_to_dev(sq_fdm *f, double2 *d_dst, const void *h_src);      // (Ltau x N) tau-fastest -> [l][i]
+void fdm_dev_to_host(sq_fdm *f, void *h_dst, const double2 *d_src);
+void fdm_transpose_real(sq_fdm *f, double *dst, const double *src, int rows_fast_src, int cols, bool to_host_layout);
+void fdm_sweep_global(sq_fdm *f, double2 *u, int lo, int hi, bool inverse);
+void fdm_scale_global(sq_fdm *f, double2 *u, bool inverse);
+void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter,
+                i64 *iters, double *eps);
+void kpm_ldiv_dev(sq_kpm *k, double2 *out, const double2 *in, const CgState *skip_if_done = nullptr);
+int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *skip, const double2 *dot_with, double *dot_part);
+void kpm_fourier_dev(sq_kpm *k, double2 *v, bool forward);
+void kpm_lanczos(sq_kpm *k, const double *h_start, const double *d_start, double *emin, double *emax);
+void kpm_update(sq_kpm *k, const double *h_lanczos_start, const double *d_lanczos_start);
+void kpm_set_bounds(sq_kpm *k, double emin, double emax);
+void elph_refresh_fdm(sq_elph *e);
+double elph_bosonic_action(sq_elph *e);
+void elph_update_lambda(sq_elph *e, double *Lam);
+void elph_lambda_op(sq_elph *e, int which, double2 *out, const double2 *in, const double *Lam);
+void fdm_update_dev(sq_fdm *f, const double *dV, const double *dt_, double dtau);
+double reduce_partials_host(sq_fdm *f, const double *d_part, int n);
+int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, int N, double2 *out, const double2 *in, bool inverse,
+                   bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
+                   double *dot_part, const CgState *skip, size_t smem_limit);
+void rng_fill_normal(double *d_out, size_t n, uint64_t seed, uint64_t stream, cudaStream_t s);
+void rng_fill_uniform(double *d_out, size_t n, uint64_t seed, uint64_t stream, cudaStream_t s);
+void fft_radices(i64 n, std::vector<int> &rad);
+void fft_make_twiddles(i64 n, std::vector<double2> &tw);

@@ -1,0 +1,116 @@
+"""GPU parity: FermionDetMatrix products and CG through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from smoqyelph_b200 import model as mdl
+from oracle import oracle as orc
+import dense_ref as dr
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12   # north_star: M^T M v within 1e-12 relative error in Float64
+
+
+def rand_cvec(rng, m):
+    return np.asfortranarray((rng.standard_normal((m.Ltau, m.N)) + 1j * rng.standard_normal((m.Ltau, m.N))) / np.sqrt(2))
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+MODELS = {
+    "cfg1t": lambda: mdl.config("cfg1t"),
+    "cfg1": lambda: mdl.config("cfg1"),
+    "cfg2": lambda: mdl.config("cfg2"),
+    "cfg3": lambda: mdl.config("cfg3"),
+    "cfg4": lambda: mdl.config("cfg4"),
+    "mixed_odd": lambda: mdl.holstein_ssh_chain(7, 0.65),     # odd ring: 3 colours, last colour 1 bond, uncovered sites
+    "tiny_L1": lambda: mdl.ossh_chain(4, 0.05),               # Ltau = 1
+    "tiny_L2": lambda: mdl.ossh_chain(6, 0.10),               # Ltau = 2
+}
+
+
+def setup(name, sym, seed=0):
+    from smoqyelph_b200 import api
+    m = MODELS[name]()
+    rng = np.random.default_rng(seed)
+    x = m.random_fields(rng)
+    V, t = dr.build_Vt(m, x)
+    ref = orc.RefFDM(m, sym=sym)
+    ref.update(V, t)
+    fdm = api.FermionDetMatrix(m, sym=sym)
+    fdm.update(V, t)
+    return m, rng, ref, fdm
+
+
+@pytest.mark.parametrize("sym", [True, False])
+@pytest.mark.parametrize("name", list(MODELS))
+def test_products_match_oracle(name, sym):
+    m, rng, ref, fdm = setup(name, sym)
+    e, c, s = fdm.coefficients()
+    assert np.abs(e - ref.expV).max() <= 4e-16 * np.abs(ref.expV).max()
+    if m.Nh:
+        assert np.abs(c - ref.cosh).max() <= 4e-16 * np.abs(ref.cosh).max()
+        assert np.abs(s - ref.sinh).max() <= 1e-15
+    v = rand_cvec(rng, m)
+    for op in ("mul_M", "mul_Mt", "mul_MtM", "mul_MMt"):
+        got = getattr(fdm, op)(v)
+        want = getattr(ref, op)(v)
+        assert relerr(got, want) < RTOL, (name, sym, op, relerr(got, want))
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4"])
+def test_all_tunings_agree(name):
+    m, rng, ref, fdm = setup(name, True)
+    v = rand_cvec(rng, m)
+    want = ref.mul_MtM(v)
+    assert fdm.tuning["path"] == 0
+    for slab in (1, 2, 3, 5):
+        for threads in (128, 256, 1024):
+            try:
+                fdm.set_tuning(slab, threads)
+            except Exception:
+                continue
+            assert relerr(fdm.mul_MtM(v), want) < RTOL, (slab, threads)
+            assert relerr(fdm.mul_M(v), ref.mul_M(v)) < RTOL
+            assert relerr(fdm.mul_Mt(v), ref.mul_Mt(v)) < RTOL
+
+
+def test_linearity_and_adjointness_full_size():
+    """Size-independent properties at BASELINE's full size (cfg4)."""
+    m, rng, ref, fdm = setup("cfg4", True)
+    a, b = rand_cvec(rng, m), rand_cvec(rng, m)
+    al = 0.3 - 1.1j
+    lhs = fdm.mul_MtM(a + al * b)
+    rhs = fdm.mul_MtM(a) + al * fdm.mul_MtM(b)
+    assert relerr(lhs, rhs) < 1e-13
+    # <a, M b> == <M^T a, b> for real M
+    l = np.vdot(a, fdm.mul_M(b))
+    r = np.vdot(fdm.mul_Mt(a), b)
+    assert abs(l - r) < 1e-12 * abs(l)
+    # M^T M is positive: <a, M^T M a> = |M a|^2
+    assert abs(np.vdot(a, fdm.mul_MtM(a)) - np.linalg.norm(fdm.mul_M(a)) ** 2) < 1e-11 * np.linalg.norm(a) ** 2
+
+
+@pytest.mark.parametrize("sym", [True, False])
+@pytest.mark.parametrize("name", ["cfg1t", "cfg2", "mixed_odd"])
+def test_cg_matches_oracle(name, sym):
+    m, rng, ref, fdm = setup(name, sym)
+    b = rand_cvec(rng, m)
+    # solutions compared with both solvers converged far below the comparison tolerance (hard part 3)
+    xr, itr, epsr = ref.cg(b, tol=1e-14, maxiter=20000)
+    xg, itg, epsg = fdm.ldiv(b, tol=1e-14, maxiter=20000)
+    assert epsg < 1e-14 and epsr < 1e-14
+    assert relerr(xg, xr) < 1e-11
+    # iteration counts at production tolerances
+    for tol in (1e-5, 1e-10):
+        _, itr, _ = ref.cg(b, tol=tol, maxiter=20000)
+        _, itg, epsg = fdm.ldiv(b, tol=tol, maxiter=20000)
+        assert abs(itg - itr) <= 1, (tol, itg, itr)
+        assert epsg < tol
+    # warm start: x0 = solution => 0 iterations ; maxiter cut-off returns maxiter
+    _, it0, _ = fdm.ldiv(b, x0=xg, tol=1e-10)
+    assert it0 == 0
+    _, itc, epsc = fdm.ldiv(b, tol=1e-14, maxiter=3)
+    assert itc == 3 and epsc > 1e-14

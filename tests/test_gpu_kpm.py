@@ -1,0 +1,125 @@
+"""GPU parity: tau-FFT, KPM preconditioner and preconditioned CG through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from smoqyelph_b200 import model as mdl
+from oracle import oracle as orc
+import dense_ref as dr
+
+pytestmark = pytest.mark.gpu
+
+
+def rand_cvec(rng, m):
+    return np.asfortranarray((rng.standard_normal((m.Ltau, m.N)) + 1j * rng.standard_normal((m.Ltau, m.N))) / np.sqrt(2))
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def setup(m, sym, seed=0, smooth=True):
+    from smoqyelph_b200 import api
+    rng = np.random.default_rng(seed)
+    x = m.random_fields(rng, smooth=smooth)
+    V, t = dr.build_Vt(m, x)
+    ref = orc.RefFDM(m, sym=sym)
+    ref.update(V, t)
+    fdm = api.FermionDetMatrix(m, sym=sym)
+    fdm.update(V, t)
+    return rng, ref, fdm
+
+
+@pytest.mark.parametrize("Lt", [1, 2, 3, 4, 5, 7, 12, 20, 35, 44, 80, 128, 200, 243, 320, 400])
+def test_tau_fft_matches_numpy(Lt):
+    """FourierTransformer: every radix path (2, 3, 4, 5, 7, generic 11) and the twist / normalisation."""
+    from smoqyelph_b200 import api
+    m = mdl.ossh_chain(10, Lt * 0.05)
+    assert m.Ltau == Lt
+    rng = np.random.default_rng(Lt)
+    fdm = api.FermionDetMatrix(m)
+    P = api.KPMPreconditioner(fdm, update=False)
+    v = rand_cvec(rng, m)
+    theta = np.exp(-1j * np.pi * np.arange(Lt) / Lt)[:, None]
+    want = np.fft.fft(theta / np.sqrt(Lt) * v, axis=0)
+    got = P.fourier(v, True)
+    assert np.abs(got - want).max() < 1e-13 * max(1.0, np.abs(want).max())
+    back = P.fourier(got, False)
+    assert np.abs(back - v).max() < 1e-13 * np.abs(v).max()
+
+
+@pytest.mark.parametrize("sym", [True, False])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "mixed"])
+def test_preconditioner_matches_oracle(name, sym):
+    from smoqyelph_b200 import api
+    m = mdl.holstein_ssh_chain(7, 1.0) if name == "mixed" else mdl.config(name)
+    rng, ref, fdm = setup(m, sym)
+    Pr = orc.RefKPM(ref)
+    Pg = api.KPMPreconditioner(fdm, update=False)
+    start = rng.standard_normal(m.N)
+    # Lanczos bounds (same start vector) and the activation decision
+    Pr.update(start)
+    act, bounds = Pg.update(start)
+    assert act == Pr.active
+    np.testing.assert_allclose(bounds, Pr.bounds, rtol=1e-9)
+    # identical bounds injected => identical orders and (to rounding) coefficients
+    Pg.set_bounds(*Pr.bounds)
+    np.testing.assert_array_equal(Pg.orders, Pr.orders)
+    for l in (0, 1, len(Pr.orders) // 2, len(Pr.orders) - 1):
+        np.testing.assert_allclose(Pg.coefs(l), Pr.coefs(l), rtol=1e-10, atol=1e-13)
+    v = rand_cvec(rng, m)
+    assert relerr(Pg.ldiv(v), Pr.ldiv(v)) < 1e-11
+
+
+@pytest.mark.parametrize("sym", [True, False])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "mixed"])
+def test_preconditioned_cg_matches_oracle(name, sym):
+    from smoqyelph_b200 import api
+    m = mdl.holstein_ssh_chain(7, 1.0) if name == "mixed" else mdl.config(name)
+    rng, ref, fdm = setup(m, sym)
+    Pr = orc.RefKPM(ref)
+    Pg = api.KPMPreconditioner(fdm, update=False)
+    Pr.update(rng.standard_normal(m.N))
+    assert Pr.active
+    Pg.set_bounds(*Pr.bounds)
+    b = rand_cvec(rng, m)
+    xr, itr, _ = ref.cg(b, P=Pr, tol=1e-14, maxiter=5000)
+    xg, itg, epsg = fdm.ldiv(b, preconditioner=Pg, tol=1e-14, maxiter=5000, refresh=False)
+    assert epsg < 1e-14
+    assert relerr(xg, xr) < 1e-11
+    for tol in (1e-5, 1e-10):
+        _, itr, _ = ref.cg(b, P=Pr, tol=tol, maxiter=5000)
+        _, itg, epsg = fdm.ldiv(b, preconditioner=Pg, tol=tol, maxiter=5000, refresh=False)
+        assert abs(itg - itr) <= 1, (tol, itg, itr)
+        _, it0, _ = fdm.ldiv(b, tol=tol, maxiter=5000)
+        assert itg < it0                      # the preconditioner pays for itself on tau-smooth fields
+    # warm start + preconditioner
+    _, itw, _ = fdm.ldiv(b, x0=xg, preconditioner=Pg, tol=1e-10, refresh=False)
+    assert itw == 0
+
+
+def test_tau_independent_fields_exact_inverse_full_size():
+    """Size-independent property at cfg4: tau-independent fields => P^-1 M^T M = I at high order."""
+    from smoqyelph_b200 import api
+    m = mdl.config("cfg4")
+    rng = np.random.default_rng(3)
+    x = np.repeat(0.3 * rng.standard_normal((m.Nph, 1)), m.Ltau, axis=1)
+    V, t = dr.build_Vt(m, x)
+    fdm = api.FermionDetMatrix(m)
+    fdm.update(V, t)
+    P = api.KPMPreconditioner(fdm, a1=30.0, a2=30.0)
+    v = rand_cvec(rng, m)
+    w = P.ldiv(fdm.mul_MtM(v))
+    assert np.abs(w - v).max() / np.abs(v).max() < 1e-7
+    _, it, eps = fdm.ldiv(v, preconditioner=P, tol=1e-10, refresh=False)
+    assert it <= 3
+
+
+def test_inactive_preconditioner_is_identity():
+    from smoqyelph_b200 import api
+    m = mdl.ossh_chain(8, 0.5, t=40.0)           # huge hopping => eps_max >> 2 => deactivated (KPMPreconditioner.jl:570)
+    rng, ref, fdm = setup(m, True)
+    Pg = api.KPMPreconditioner(fdm, update=False)
+    act, _ = Pg.update(rng.standard_normal(m.N))
+    assert not act
+    v = rand_cvec(rng, m)
+    assert np.array_equal(Pg.ldiv(v), v)

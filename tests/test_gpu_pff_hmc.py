@@ -1,0 +1,220 @@
+"""GPU parity: Lambda, pseudofermion action, force, EFA, hmc_update! and the measurement solves vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from smoqyelph_b200 import model as mdl
+from oracle import oracle as orc
+import dense_ref as dr
+
+pytestmark = pytest.mark.gpu
+
+FORCE_RTOL = 1e-12     # north_star: forces within 1e-12 relative error (solves converged below it, see tol)
+
+
+def rand_cvec(rng, m):
+    return np.asfortranarray((rng.standard_normal((m.Ltau, m.N)) + 1j * rng.standard_normal((m.Ltau, m.N))) / np.sqrt(2))
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+MODELS = {
+    "cfg1t": lambda: mdl.config("cfg1t"),
+    "cfg1": lambda: mdl.config("cfg1"),
+    "cfg2s": lambda: mdl.ossh_chain(64, 2.0),
+    "cfg3s": lambda: mdl.bssh_square(8, 8, 1.0),
+    "mixed": lambda: mdl.holstein_ssh_chain(7, 0.65),
+    "nosym": lambda: mdl.holstein_square(4, 4, 0.5, ph_sym=False),
+}
+
+
+def both(name, sym, seed=0, exact=False):
+    from smoqyelph_b200 import api
+    m = MODELS[name]()
+    rng = np.random.default_rng(seed)
+    x = m.random_fields(rng)
+    rf = orc.RefFDM(m, sym=sym, tol=1e-14, maxiter=20000)
+    re = orc.RefElPh(m)
+    re.set_x(x)
+    re.refresh(rf)
+    rp = orc.RefPFF(re, rf, exact_holstein=exact)
+    gf = api.FermionDetMatrix(m, sym=sym)
+    ge = api.ElectronPhononParameters(m, gf)
+    ge.x = x
+    ge.update_fdm()
+    gp = api.PFFCalculator(ge, exact_holstein=exact)
+    return m, rng, x, (rf, re, rp), (gf, ge, gp)
+
+
+@pytest.mark.parametrize("sym", [True, False])
+@pytest.mark.parametrize("name", list(MODELS))
+def test_refresh_and_lambda(name, sym):
+    m, rng, x, (rf, re, rp), (gf, ge, gp) = both(name, sym)
+    V, t = ge.Vt()
+    np.testing.assert_allclose(V, re.V, rtol=1e-14, atol=1e-14)
+    np.testing.assert_allclose(t, re.t, rtol=1e-14, atol=1e-14)
+    e, c, s = gf.coefficients()
+    np.testing.assert_allclose(e, rf.expV, rtol=1e-14)
+    np.testing.assert_allclose(c, rf.cosh, rtol=1e-14)
+    np.testing.assert_allclose(s, rf.sinh, rtol=1e-13, atol=1e-15)
+    assert np.array_equal(ge.x, x)
+    assert abs(ge.bosonic_action() - re.bosonic_action()) < 1e-12 * abs(re.bosonic_action())
+    Lam = re.Lambda()
+    v = rand_cvec(rng, m)
+    for which in ("mul", "ldiv", "mulT", "ldivT"):
+        assert relerr(gp.lambda_op(which, v), re.lam_op(which, Lam, v)) < 1e-14, which
+    # derivative pieces on arbitrary vectors
+    u = rand_cvec(rng, m)
+    for nu in (-2.0, 0.7):
+        Fr = re.dM_dx(nu, u, v, rf)
+        Fg = gp.dM_dx(nu, u, v)
+        assert relerr(Fg, Fr) < 1e-12 or np.abs(Fr).max() == 0
+        Fr = re.dLambda_dx(nu, u, v, Lam)
+        Fg = gp.dLambda_dx(nu, u, v)
+        assert relerr(Fg, Fr) < 1e-13 or np.abs(Fr).max() == 0
+    assert np.all(Fg[~np.isfinite(m.Mass)] == 0)
+
+
+@pytest.mark.parametrize("exact", [False, True])
+@pytest.mark.parametrize("sym", [True, False])
+@pytest.mark.parametrize("name", list(MODELS))
+def test_action_and_force(name, sym, exact):
+    m, rng, x, (rf, re, rp), (gf, ge, gp) = both(name, sym, exact=exact)
+    R = rand_cvec(rng, m)
+    Sr = rp.sample(R)
+    Sg = gp.sample_pseudofermion_fields(R)
+    assert abs(Sg - Sr) < 1e-13 * abs(Sr)
+    Phi, _, Lam = gp.fields()
+    assert relerr(Phi, rp.Phi) < 1e-13
+    assert relerr(Lam, re.Lambda()) < 1e-15
+    # move the field, as the trajectory does, then action + force
+    x2 = x + 0.05 * rng.standard_normal(x.shape)
+    x2[~np.isfinite(m.Mass)] = 0
+    re.set_x(x2)
+    re.refresh(rf)
+    ge.x = x2
+    ge.update_fdm()
+    Sr, itr, _ = rp.action(tol=1e-14, maxiter=20000)
+    Sg, itg, epsg = gp.calculate_fermionic_action(tol=1e-14, maxiter=20000)
+    assert abs(Sg - Sr) < 1e-11 * abs(Sr)
+    Fr, Sr, _, _ = rp.force(tol=1e-14, maxiter=20000)
+    F0 = np.asfortranarray(0.25 * np.ones((m.Nph, m.Ltau)))          # dSdx is accumulated into (+=)
+    Fg, Sg, _, _ = gp.calculate_derivative_fermionic_action(dSdx=F0.copy(order="F"), tol=1e-14, maxiter=20000)
+    assert relerr(Fg - 0.25, Fr) < 1e-10      # CG solutions converged to 1e-14 on both sides; force is linear in Psi (x2)
+    _, Psi, _ = gp.fields()
+    assert relerr(Psi, rp.Psi) < 1e-10
+    # production tolerances: iteration counts within +-1
+    for tol in (1e-5, 1e-10):
+        _, itr, _ = rp.action(tol=tol, maxiter=20000)
+        _, itg, _ = gp.calculate_fermionic_action(tol=tol, maxiter=20000)
+        assert abs(itg - itr) <= 1
+
+
+def test_force_parity_at_fixed_psi_is_1e12():
+    """With identical Psi on both sides (no solver noise) the force kernels agree to 1e-12."""
+    m, rng, x, (rf, re, rp), (gf, ge, gp) = both("cfg1", True)
+    u, v = rand_cvec(rng, m), rand_cvec(rng, m)
+    Fr = re.dM_dx(-2.0, u, v, rf)
+    Fg = gp.dM_dx(-2.0, u, v)
+    assert relerr(Fg, Fr) < FORCE_RTOL
+
+
+@pytest.mark.parametrize("name", ["cfg3s", "mixed", "cfg1t"])
+def test_efa_pieces(name):
+    from smoqyelph_b200 import api
+    m, rng, x, (rf, re, rp), (gf, ge, gp) = both(name, True)
+    ra = orc.RefEFA(re)
+    hmc = api.EFAPFFHMCUpdater(ge, gp, Nt=4)
+    R = rng.standard_normal((m.Nph, m.Ltau))
+    pr, Kr = ra.init_momentum(R)
+    pg, Kg = hmc.init_momentum(R)
+    assert abs(Kg - Kr) < 1e-13 * Kr and relerr(pg, pr) < 1e-13
+    assert abs(hmc.kinetic(pr) - ra.kinetic(pr)) < 1e-13 * Kr
+    xr, pr2 = ra.evolve(x, pr, 0.31)
+    xg, pg2 = hmc.evolve(x, pr, 0.31)
+    assert relerr(xg, xr) < 1e-13 and relerr(pg2, pr2) < 1e-13
+
+
+@pytest.mark.parametrize("precond", [False, True])
+@pytest.mark.parametrize("name,sym", [("cfg1t", True), ("mixed", True), ("mixed", False), ("cfg3s", True)])
+def test_hmc_update_matches_oracle(name, sym, precond):
+    """One full hmc_update! with the same random stream on both sides: same trajectory, energies, decision."""
+    from smoqyelph_b200 import api
+    m, rng, x, (rf, re, rp), (gf, ge, gp) = both(name, sym, seed=5)
+    Nt = 6
+    ra = orc.RefEFA(re)
+    hmc = api.EFAPFFHMCUpdater(ge, gp, Nt=Nt, delta=0.05)
+    Pr = Pg = None
+    if precond:
+        Pr = orc.RefKPM(rf)
+        Pg = api.KPMPreconditioner(gf, update=False)
+    nr = orc.hmc_random_count(m, Nt, precond)
+    rnd = rng.standard_normal(nr)
+    rnd[0] = 0.3
+    rnd[-1] = 0.0         # always below the acceptance probability: accepted unless dH = +inf
+    acc_r, info_r = orc.hmc_update(re, rf, rp, ra, Pr, Nt, np.pi / (2 * Nt), 0.05, 1e-13, 1e-13, 20000, rnd)
+    acc_g, it_g = hmc.hmc_update(preconditioner=Pg, tol_action=1e-13, tol_force=1e-13, maxiter=20000, randoms=rnd)
+    info_g = hmc.info
+    assert acc_g == acc_r
+    assert relerr(ge.x, re.x) < 1e-9
+    for k in (2, 3, 4, 5, 6, 7):          # Sf0, Sf1, Sb0, Sb1, K0, K1
+        assert abs(info_g[k] - info_r[k]) < 1e-9 * max(1.0, abs(info_r[k])), k
+    assert abs(info_g[1] - info_r[1]) < 1e-7 * max(1.0, abs(info_r[1]))
+    assert abs(info_g[0] - info_r[0]) <= 1.0
+    # rejected trajectory restores x and the operator
+    x_before = ge.x
+    rnd[-1] = 2.0
+    acc_g, _ = hmc.hmc_update(preconditioner=Pg, tol_action=1e-10, tol_force=1e-5, maxiter=20000, randoms=rnd)
+    assert not acc_g
+    assert np.array_equal(ge.x, x_before)
+    e1, _, _ = gf.coefficients()
+    ge.update_fdm()
+    e2, _, _ = gf.coefficients()
+    assert np.array_equal(e1, e2)
+
+
+def test_hmc_library_rng_runs_and_conserves_energy():
+    from smoqyelph_b200 import api
+    m, rng, x, _, (gf, ge, gp) = both("cfg1", True, exact=True)
+    dHs = []
+    for Nt in (4, 16):
+        ge.x = x
+        ge.update_fdm()
+        hmc = api.EFAPFFHMCUpdater(ge, gp, Nt=Nt, delta=0.0, seed=11)
+        hmc.hmc_update(tol_action=1e-12, tol_force=1e-12)
+        dHs.append(abs(hmc.info[1]))
+    assert dHs[1] < dHs[0] / 4
+
+
+@pytest.mark.parametrize("name", ["cfg1t", "mixed"])
+def test_greens_estimator_and_scalar_measurements(name):
+    from smoqyelph_b200 import api
+    m, rng, x, (rf, re, rp), (gf, ge, gp) = both(name, True)
+    Nrv, V = 6, m.N * m.Ltau
+    R = rng.standard_normal((V, Nrv)) + 1j * rng.standard_normal((V, Nrv))
+    R = np.asfortranarray(R / np.abs(R))
+    GRr = np.zeros((V, Nrv), np.complex128, order="F")
+    avg_r = orc.greens_update(rf, None, R, GRr, 1e-13, 20000)
+    g = api.GreensEstimator(gf, Nrv=Nrv)
+    avg_g = g.update_greens_estimator(R=R, tol=1e-13, maxiter=20000)
+    Rg, GRg = g.get()
+    assert np.array_equal(Rg, R)
+    assert relerr(GRg, GRr) < 1e-10
+    assert abs(avg_g - avg_r) <= 1.0
+    meas = g.measure()
+    for key in ("n", "double_occ"):
+        want = orc.measure(key, R, GRg)
+        assert abs(meas[key] - want) < 1e-12 * max(1.0, abs(want)), key
+    want = orc.measure("Nsqrd", R, GRg, Ltau=m.Ltau)
+    assert abs(meas["Nsqrd"] - want) < 1e-11 * max(1.0, abs(want))
+    # warm start: a second update with the same R converges immediately
+    assert g.update_greens_estimator(R=R, tol=1e-10, maxiter=20000) == 0
+    # library RNG path + update_chemical_potential wiring
+    g2 = api.GreensEstimator(gf, Nrv=4, seed=3)
+    g2.update_greens_estimator(tol=1e-10)
+    R2, _ = g2.get()
+    assert np.allclose(np.abs(R2), 1.0)
+    mu_new, it = api.update_chemical_potential(gf, g2, ge, 0.0, lambda n, N2: 0.1, tol=1e-10)
+    V2, _ = ge.Vt()
+    np.testing.assert_allclose(V2, re.V - 0.1, atol=1e-13)
