@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- EFA-HMC trajectories/s on the synthetic 32x32 Holstein square lattice (beta=20, dtau=0.05),
+plus the fused M^T M v kernel against the HBM roofline and the CPU path timed beside it.
+
+    python bench.py --gpus N --steps K --warmup W            (native arm; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the oracle port on host cores)
+
+A "step" is one hmc_update! trajectory (Nt = 24 leapfrog steps = 24 force solves + 1 action solve,
+src/EFAPFFHMCUpdater.jl:102-279) of one Markov chain.  `value` keeps the phonon field resident in HBM;
+`e2e` pushes x host->device before and reads it back after every trajectory through the C ABI, as the Julia
+drop-in does.  N > 1 runs one independent chain per GPU (the MPI tutorial's mode, weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NT = 24
+TOL_ACTION, TOL_FORCE, MAXITER = 1e-10, 1e-5, 10000        # tutorials/holstein_honeycomb.jl:64-68,591
+ITERS_FILE = os.path.join(ROOT, "profiles", "bench_state.json")
+
+
+def cdw_start(m, seed):
+    """Synthetic but physical start: the staggered (charge-density-wave) phonon order of the half-filled
+    Holstein model at beta = 20, plus free-phonon thermal fluctuations.  Warm-up trajectories relax it."""
+    from smoqyelph_b200 import model as mdl
+    rng = np.random.default_rng(seed)
+    Lx = m.lattice_dims[0]
+    s = np.arange(m.N)
+    stag = np.where(((s % Lx) + (s // Lx)) % 2 == 0, 1.0, -1.0)
+    return np.asfortranarray(1.5 * stag[:, None] + 0.3 * mdl.thermal_fields(m, rng))
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [q.strip() for q in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(m):
+    """One fused M^T M v: read v, write v', read exp(-dtau V), cosh, sinh once each."""
+    return (40 * m.N + 16 * m.Nh) * m.Ltau
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm / cpu_baseline: the oracle port, bounded sample, extrapolated with the trajectory's CG iteration count
+# ------------------------------------------------------------------------------------------------------
+def cpu_sample(m, x, precond, omp, budget_s, iters_per_traj):
+    from oracle import oracle as orc
+    rng = np.random.default_rng(7)
+    f = orc.RefFDM(m, sym=True, tol=TOL_FORCE, maxiter=MAXITER, omp=omp)
+    e = orc.RefElPh(m, omp=omp)
+    e.set_x(x)
+    t0 = time.perf_counter()
+    e.refresh(f)
+    t_refresh = time.perf_counter() - t0
+    pff = orc.RefPFF(e, f)
+    R = (rng.standard_normal((m.Ltau, m.N)) + 1j * rng.standard_normal((m.Ltau, m.N))) / np.sqrt(2)
+    pff.sample(R)
+    P = None
+    if precond:
+        P = orc.RefKPM(f)
+        P.update(rng.standard_normal(m.N))
+    # calibrate: 3 CG iterations, then size the sample to the budget
+    b = np.asfortranarray(R)
+    t0 = time.perf_counter()
+    f.cg(b, P=P, tol=1e-300, maxiter=3)
+    t3 = (time.perf_counter() - t0) / 3
+    n_it = int(max(5, min(400, budget_s * 0.7 / t3)))
+    t0 = time.perf_counter()
+    f.cg(b, P=P, tol=1e-300, maxiter=n_it)
+    t_iter = (time.perf_counter() - t0) / n_it
+    # force evaluation with the solve capped at 2 iterations: the non-CG tail (Lambda ops, M, M^T, dM/dx, dLambda/dx)
+    t0 = time.perf_counter()
+    pff.force(P=P, lanczos_start=rng.standard_normal(m.N) if P is not None else None, tol=1e-300, maxiter=2)
+    t_tail = max(0.0, time.perf_counter() - t0 - 2 * t_iter)
+    t_traj = iters_per_traj * t_iter + NT * t_tail + (NT + 2) * t_refresh
+    threads = f.L.ref_num_threads()
+    sample = (f"{n_it} CG iterations of M^T M (precond={'KPM' if precond else 'I'}) + 1 force tail + 1 operator refresh of the C oracle "
+              f"port on the bench phonon state; t_iter={t_iter * 1e3:.2f} ms, t_tail={t_tail * 1e3:.1f} ms, t_refresh={t_refresh * 1e3:.1f} ms; "
+              f"extrapolated to one trajectory = {iters_per_traj:.0f} CG iterations (count from the GPU arm, parity-tested +-1) "
+              f"+ {NT} tails + {NT + 2} refreshes")
+    return 1.0 / t_traj, threads, sample, {"t_iter_ms": t_iter * 1e3, "t_tail_ms": t_tail * 1e3, "t_refresh_ms": t_refresh * 1e3, "n_it": n_it}
+
+
+def stored_iters(precond):
+    try:
+        d = json.load(open(ITERS_FILE))
+        return float(d["precond_on" if precond else "precond_off"]["cg_iters_per_trajectory"])
+    except Exception:
+        return 20000.0 if not precond else 4000.0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from smoqyelph_b200 import model as mdl
+    m = mdl.config(args.config)
+    precond = args.precond == "on"
+    x = cdw_start(m, 1000)
+    iters = stored_iters(precond)
+    vals, info, threads, sample = [], None, 1, ""
+    budget = max(5.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    for step in range(args.warmup + args.steps):
+        v, threads, sample, info = cpu_sample(m, x, precond, True, budget, iters)
+        if step >= args.warmup:
+            vals.append(v)
+    val = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "efa_hmc_trajectories_per_s", "value": val, "unit": "trajectories/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(m, precond, "cpu"),
+            "cpu_baseline": {"value": val, "unit": "trajectories/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "detail": info}
+    print(json.dumps(line))
+
+
+def workload_config(m, precond, where):
+    return {"workload": f"{m.name}: Holstein square {m.lattice_dims[0]}x{m.lattice_dims[1]}, beta={m.beta:g}, dtau={m.dtau:g} "
+                        f"(N={m.N}, Ltau={m.Ltau}, N*Ltau={m.N * m.Ltau}), Omega=1, alpha=1.5, mu=0, ph_sym_form; "
+                        f"EFA-PFF-HMC Nt={NT}, tol_action={TOL_ACTION:g}, tol_force={TOL_FORCE:g}, SymFermionDetMatrix",
+            "preconditioner": "KPM (defaults)" if precond else "I",
+            "phonon_state": "staggered CDW order 1.5 + 0.3 x free-phonon thermal noise, relaxed by the warm-up trajectories",
+            "parallelism": "independent chains, one per GPU" if where == "gpu" else "OpenMP over tau inside each sweep",
+            "l2": "trajectory working set is L2-resident by nature (vector 6.5 MB); roofline kernel timed with an L2 flush "
+                  "(256 MB write) between launches"}
+
+
+# ------------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import ctypes as C
+    from smoqyelph_b200 import api, lib, model as mdl
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    m = mdl.config(args.config)
+    precond = args.precond == "on"
+    fdm = api.SymFermionDetMatrix(m, tol=TOL_ACTION, maxiter=MAXITER, device=local)
+    elph = api.ElectronPhononParameters(m, fdm)
+    pff = api.PFFCalculator(elph)
+    P = api.KPMPreconditioner(fdm, update=False) if precond else None
+    elph.x = cdw_start(m, 1000 + rank)
+    elph.update_fdm()
+    stream = torch.cuda.ExternalStream(fdm.stream, device=dev)
+    L = lib.load()
+
+    def trajectory(h):
+        acc = C.c_int(0)
+        info = np.zeros(8)
+        lib.check(L.sq_hmc_update(h.h, P.h if P is not None else None, TOL_ACTION, TOL_FORCE, MAXITER, None, 0, C.byref(acc), lib.ptr(info)))
+        return bool(acc.value), info
+
+    # ---- warm-up (untimed): relaxes the synthetic start, warms the caches and the clocks
+    hmc = api.EFAPFFHMCUpdater(elph, pff, Nt=NT, seed=77 + rank)
+    for _ in range(args.warmup):
+        trajectory(hmc)
+    x_w = elph.x                                             # state every timed leg starts from
+
+    def fresh_updater():
+        elph.x = x_w
+        elph.update_fdm()
+        return api.EFAPFFHMCUpdater(elph, pff, Nt=NT, seed=4242 + rank)
+
+    # ---- value: K trajectories, x resident in HBM, timed with CUDA events on the library stream
+    h = fresh_updater()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = fdm.launch_count
+    e0.record(stream)
+    iters_total, accepted = 0.0, 0
+    for _ in range(args.steps):
+        acc, info = trajectory(h)
+        iters_total += info[0] * (NT + 1)
+        accepted += int(acc)
+    e1.record(stream)
+    e1.synchronize()
+    launches = fdm.launch_count - l0
+    ms_dev = e0.elapsed_time(e1)
+    t = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_value = float(t.item())
+    value = world * args.steps / (ms_value * 1e-3)
+
+    # ---- e2e: same trajectories, x crosses PCIe both ways every step (pinned host buffer), wall clock
+    h = fresh_updater()
+    nx = m.Nph * m.Ltau
+    pin = torch.empty(nx, dtype=torch.float64).pin_memory()
+    pin.copy_(torch.from_numpy(np.ascontiguousarray(x_w.ravel(order="F"))))
+    pptr = C.c_void_p(pin.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lib.check(L.sq_elph_set_x(elph.h, pptr))             # H2D
+        lib.check(L.sq_elph_refresh_fdm(elph.h))
+        trajectory(h)
+        lib.check(L.sq_elph_get_x(elph.h, pptr))             # D2H (blocking)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    barrier()
+    e2e_value = world * args.steps / float(t.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_fdm_fused<2>), rank 0: CUDA events around single launches
+    n = m.N * m.Ltau
+    d_in = torch.randn(n, 2, dtype=torch.float64, device=dev)
+    d_out = torch.zeros_like(d_in)
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)          # 256 MB > 126 MB L2
+    B = algorithmic_bytes(m)
+
+    def time_matvec(cold, reps=40):
+        ts = []
+        with torch.cuda.stream(stream):
+            for _ in range(5):
+                fdm.mul_dev(api.OP_MTM, d_out.data_ptr(), d_in.data_ptr())
+            for _ in range(reps):
+                if cold:
+                    flush.add_(1.0)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                fdm.mul_dev(api.OP_MTM, d_out.data_ptr(), d_in.data_ptr())
+                b.record(stream)
+                b.synchronize()
+                ts.append(a.elapsed_time(b) * 1e-3)
+        return float(np.mean(ts))
+
+    t_cold, t_hot = time_matvec(True), time_matvec(False)
+    peak, peak_src = measured_peak()
+    traffic = None
+    try:
+        traffic = json.load(open(ITERS_FILE)).get("mtm_dram_bytes_per_launch")
+    except Exception:
+        pass
+    iters_per_traj = iters_total / args.steps
+    matvecs_per_traj = iters_per_traj + 2 * (NT + 1)
+    roofline = {"bound": "hbm", "kernel": "k_fdm_fused<2> (fused M^T M v)", "achieved": B / t_cold / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": B / t_cold / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": B, "us_per_launch_cold_l2": t_cold * 1e6, "us_per_launch_hot_l2": t_hot * 1e6,
+                "achieved_hot_l2": B / t_hot / 1e9, "frac_hot_l2": B / t_hot / 1e9 / peak,
+                "matvecs_per_s_hot_l2": 1.0 / t_hot,
+                "share_of_step": iters_per_traj * t_hot / (ms_dev * 1e-3 / args.steps),
+                "tuning": fdm.tuning}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, cores, sample, detail = cpu_sample(m, x_w, precond, False, args.cpu_budget, iters_per_traj)
+        cpu = {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": sample, "detail": detail}
+
+    line = {"metric": "efa_hmc_trajectories_per_s", "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(m, precond, "gpu"),
+            "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": nx * 8, "d2h_bytes_per_step": nx * 8 + 64},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "cg_iters_per_trajectory": iters_per_traj, "matvecs_per_trajectory": matvecs_per_traj,
+            "acceptance": accepted / args.steps}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="cfg4")
+    ap.add_argument("--precond", default=os.environ.get("SQ_BENCH_PRECOND", "off"), choices=["on", "off"])
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    import smoqyelph_b200  # noqa: F401
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

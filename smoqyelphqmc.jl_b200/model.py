@@ -98,6 +98,22 @@ class Model:
         return np.asfortranarray(x)
 
 
+def thermal_fields(model: Model, rng) -> np.ndarray:
+    """Phonon field drawn from the FREE-phonon thermal distribution exp(-S_b) (synthetic but physical
+    starting point for trajectory benchmarks): every Matsubara mode w of phonon p is Gaussian with
+    variance 1 / (dtau M (Omega^2 + 4 sin^2(pi w / L) / dtau^2))."""
+    L = model.Ltau
+    w = np.arange(L)
+    R = rng.standard_normal((model.Nph, L))
+    Rt = np.fft.fft(R, axis=1) / np.sqrt(L)
+    k = model.dtau * model.Mass[:, None] * (model.Omega[:, None] ** 2 + 4 * np.sin(np.pi * w / L)[None, :] ** 2 / model.dtau ** 2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        xt = np.where(np.isfinite(k), Rt / np.sqrt(k), 0.0)
+    x = np.real(np.fft.ifft(xt, axis=1) * np.sqrt(L))
+    x[~np.isfinite(model.Mass), :] = 0.0
+    return np.asfortranarray(x)
+
+
 def greedy_edge_colouring(nt: np.ndarray, N: int) -> np.ndarray:
     Nh = nt.shape[1]
     used = [set() for _ in range(N)]

@@ -1,0 +1,67 @@
+"""Multi-GPU host logic (one process per GPU, torch.distributed for the plumbing).
+
+Two modes:
+  * independent chains -- the reference's only parallel mode (tutorials/holstein_honeycomb_mpi.jl:60-72):
+    rank r runs its own Markov chain with seed `seed + r`; nothing is communicated during sampling and
+    the per-chain statistics are merged at the end (`merge_chain_statistics`).
+  * tau-slab partitioning -- rank g owns the contiguous slices [lo, hi) of every [l][i] array; M couples
+    slice l to l-1 and M^T to l+1, so a matvec needs one boundary slice from each ring neighbour
+    (`slab_range`, `halo_plan`).  The wrap-around link (l = 0 <- L-1) carries the antiperiodic + sign.
+
+Everything here is pure host logic and runs under the gloo backend in the CPU tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def chain_seed(seed: int, rank: int) -> int:
+    """Seed of the chain run by `rank` (the MPI tutorial uses seed + pID)."""
+    return int(seed) + int(rank)
+
+
+def slab_range(Ltau: int, world: int, rank: int):
+    """Contiguous, balanced partition of the Ltau slices: the first Ltau % world ranks get one extra slice."""
+    base, extra = divmod(int(Ltau), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def halo_plan(Ltau: int, world: int, rank: int):
+    """Ring neighbours and signs for the one-slice halos of M (needs v[lo-1]) and M^T (needs v[hi])."""
+    lo, hi = slab_range(Ltau, world, rank)
+    prev_rank, next_rank = (rank - 1) % world, (rank + 1) % world
+    return {
+        "lo": lo, "hi": hi, "prev": prev_rank, "next": next_rank,
+        # (M v)[l] = v[l] - B_l v[l-1] for l >= 1, + for l = 0: the halo received from `prev` enters with this sign
+        "sign_from_prev": 1.0 if lo == 0 else -1.0,
+        # (M^T v)[l] = v[l] - B_{l+1}^T v[l+1] for l < L-1, + for l = L-1
+        "sign_from_next": 1.0 if hi == Ltau else -1.0,
+        "halo_bytes_per_direction": None,
+    }
+
+
+def merge_chain_statistics(values, dist=None):
+    """Mean and standard error over chains of per-chain means.  `values`: 1-D array of this rank's per-chain
+    observables.  With torch.distributed initialised the chains of all ranks are gathered first."""
+    v = np.atleast_1d(np.asarray(values, dtype=np.float64))
+    if dist is not None and dist.is_initialized():
+        import torch
+        t = torch.from_numpy(v.copy())
+        out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(out, t)
+        v = torch.stack(out).numpy()          # (world, nobs)
+    else:
+        v = v[None, :]
+    mean = v.mean(axis=0)
+    err = v.std(axis=0, ddof=1) / np.sqrt(v.shape[0]) if v.shape[0] > 1 else np.zeros_like(mean)
+    return mean, err
+
+
+def max_over_ranks(seconds: float, dist=None) -> float:
+    if dist is not None and dist.is_initialized():
+        import torch
+        t = torch.tensor([seconds], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return float(seconds)

@@ -1,0 +1,133 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares, fails loudly
+without a GPU (no CPU fallback), and the host-side logic (model tables, multi-GPU plans) is right."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from smoqyelph_b200 import model as mdl, parallel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from smoqyelph_b200 import lib
+    L = lib.load()
+    declared = lib.header_symbols()
+    assert len(declared) >= 50
+    bound = set(lib.SIGNATURES) | set(lib.SPECIAL)
+    assert set(declared) == bound, (set(declared) ^ bound)
+    assert lib.MISSING == []
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.sq_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every constructor fails with a clear error (skipped on a GPU box)."""
+    from smoqyelph_b200 import lib, api
+    if lib.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(api.SqError, match="no CPU fallback"):
+        api.FermionDetMatrix(mdl.config("cfg1t"))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "smoqyelphqmc.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in txt.replace("oracle/ref_c.c", "").replace("the oracle", "").replace("CPU oracle", ""), fn
+
+
+@pytest.mark.parametrize("name,N,Nh,C,L,Nph", [("cfg1t", 18, 27, 3, 20, 18), ("cfg1", 18, 27, 3, 80, 18), ("cfg2", 64, 64, 2, 320, 64),
+                                               ("cfg3", 256, 512, 4, 200, 768), ("cfg4", 1024, 2048, 4, 400, 1024),
+                                               ("cfg5", 1152, 1728, 3, 80, 1152)])
+def test_named_configs_match_survey_table(name, N, Nh, C, L, Nph):
+    m = mdl.config(name)
+    assert (m.N, m.Nh, len(m.colors), m.Ltau, m.Nph) == (N, Nh, C, L, Nph)
+    # checkerboard validity and the permutation being a permutation
+    assert sorted(m.perm.tolist()) == list(range(Nh))
+    for lo, hi in m.colors:
+        s = m.nt_chk[:, lo:hi].ravel()
+        assert len(set(s.tolist())) == len(s)
+    assert np.array_equal(m.nt_chk, m.neighbor_table[:, m.perm])
+    # every site has the lattice coordination number
+    deg = np.bincount(m.neighbor_table.ravel(), minlength=N)
+    assert deg.min() == deg.max()
+
+
+def test_frozen_modes_and_thermal_fields():
+    m = mdl.config("cfg3")
+    rng = np.random.default_rng(0)
+    x = mdl.thermal_fields(m, rng)
+    assert x.shape == (m.Nph, m.Ltau) and np.all(x[~np.isfinite(m.Mass)] == 0)
+    # free-phonon equal-time variance: <x^2> = (1/L) sum_w 1/(dtau M (Om^2 + 4 sin^2(pi w/L)/dtau^2))
+    w = np.arange(m.Ltau)
+    var = np.mean(1.0 / (m.dtau * (1.0 + 4 * np.sin(np.pi * w / m.Ltau) ** 2 / m.dtau ** 2)))
+    got = x[np.isfinite(m.Mass)].var()
+    assert abs(got - var) < 0.05 * var
+
+
+def test_slab_partition_and_halo_plan():
+    for Lt, world in [(400, 8), (400, 3), (20, 8), (7, 2)]:
+        cover = []
+        for r in range(world):
+            lo, hi = parallel.slab_range(Lt, world, r)
+            cover += list(range(lo, hi))
+            plan = parallel.halo_plan(Lt, world, r)
+            assert plan["prev"] == (r - 1) % world and plan["next"] == (r + 1) % world
+            assert plan["sign_from_prev"] == (1.0 if lo == 0 else -1.0)
+            assert plan["sign_from_next"] == (1.0 if hi == Lt else -1.0)
+        assert cover == list(range(Lt))
+        sizes = [np.diff(parallel.slab_range(Lt, world, r))[0] for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["SQ_ROOT"])
+import numpy as np
+import torch.distributed as dist
+import smoqyelph_b200
+from smoqyelph_b200 import parallel
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+assert parallel.chain_seed(100, r) == 100 + r
+mean, err = parallel.merge_chain_statistics([1.0 + r, 10.0 * (r + 1)], dist)
+assert np.allclose(mean, [1.5, 15.0]) and np.allclose(err, [0.5, 5.0]), (mean, err)
+t = parallel.max_over_ranks(1.0 + r, dist)
+assert t == 2.0
+# tau-slab halo exchange emulated with gloo send/recv on a toy vector: M v assembled from slabs == serial M v
+L, N = 6, 3
+rng = np.random.default_rng(0)
+v = rng.standard_normal((L, N)); B = rng.standard_normal((L, N))          # diagonal toy propagators
+full = v.copy(); full[0] += B[0] * v[L - 1]; full[1:] -= B[1:] * v[:-1]
+plan = parallel.halo_plan(L, w, r)
+lo, hi = plan["lo"], plan["hi"]
+import torch
+send = torch.from_numpy(v[hi - 1].copy()); recv = torch.zeros(N, dtype=torch.float64)
+reqs = [dist.isend(send, plan["next"]), dist.irecv(recv, plan["prev"])]
+for q in reqs: q.wait()
+halo = recv.numpy()
+mine = v[lo:hi].copy()
+prev = np.vstack([halo[None, :], v[lo:hi - 1]])
+sg = np.full(hi - lo, -1.0); sg[0] = plan["sign_from_prev"]
+mine += sg[:, None] * B[lo:hi] * prev
+assert np.allclose(mine, full[lo:hi])
+dist.destroy_process_group()
+print("ok", r)
+'''
+
+
+def test_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, SQ_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29617", str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("ok") == 2
