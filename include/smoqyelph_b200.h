@@ -74,7 +74,8 @@ int sq_fdm_cg_dev(sq_fdm *f, void *d_x, const void *d_b, int zero_start, sq_kpm 
                   int64_t maxiter, int64_t *iters, double *eps);
 /* kernel configuration of the fused matvec (slices per CTA, threads per CTA; 0 = autotune) */
 int sq_fdm_set_tuning(sq_fdm *f, int slab, int threads);
-int sq_fdm_get_tuning(sq_fdm *f, int *slab, int *threads, int *path);
+int sq_fdm_get_tuning(sq_fdm *f, int *slab, int *threads, int *path);   /* path: 0 generic fused, 1 global passes, 2 fast fused */
+int sq_fdm_set_fast_path(sq_fdm *f, int enable);                       /* fast fused kernel where it applies (Sym, <= 8 colours) */
 int sq_fdm_stream(sq_fdm *f, void **cuda_stream);
 int64_t sq_fdm_launch_count(sq_fdm *f);
 

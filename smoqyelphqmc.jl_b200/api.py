@@ -121,6 +121,7 @@ class FermionDetMatrix:
         return {"slab": s.value, "threads": t.value, "path": p.value}
 
     def set_tuning(self, slab, threads): check(self.L.sq_fdm_set_tuning(self.h, slab, threads))
+    def set_fast_path(self, enable): check(self.L.sq_fdm_set_fast_path(self.h, int(enable)))
 
     @property
     def stream(self):

@@ -21,6 +21,7 @@ void fdm_destroy_impl(sq_fdm *f);
 void fdm_update_impl(sq_fdm *f, const double *V, const double *t, double dtau);
 void fdm_get_coefficients_impl(sq_fdm *f, double *expV, double *ch, double *sh);
 void fdm_mul_impl(sq_fdm *f, int op, void *out, const void *in);
+void fdm_select_tuning(sq_fdm *f);
 
 void kpm_create_impl(sq_kpm **out, sq_fdm *f, double rbuf, i64 n, double a1, double a2);
 void elph_create_impl(sq_elph **out, sq_fdm *f, double dtau, i64 Nph, const double *Om, const double *Om4, const double *M, i64 Nhol,
@@ -102,18 +103,27 @@ int sq_fdm_set_tuning(sq_fdm *f, int slab, int threads) {
     SQ_REQUIRE(f, "NULL handle");
     SQ_REQUIRE(f->path == 0, "fused path not available for this lattice size");
     SQ_REQUIRE(slab >= 1 && slab <= f->L, "slab out of range");
-    SQ_REQUIRE(threads >= 32 && threads <= 1024 && (threads & (threads - 1)) == 0, "threads must be a power of two in [32, 1024]");
+    SQ_REQUIRE(threads >= 32 && threads <= 1024 && threads % 32 == 0, "threads must be a multiple of 32 in [32, 1024]");
     SQ_REQUIRE((size_t)(2 * slab + 3) * f->N * sizeof(double2) <= f->smem_optin, "slab does not fit in shared memory");
     f->slab = slab;
     f->threads = threads;
+    f->manual_tuning = 1;
+    SQ_CATCH
+}
+int sq_fdm_set_fast_path(sq_fdm *f, int enable) {
+    SQ_TRY
+    SQ_REQUIRE(f, "NULL handle");
+    f->use_v2 = enable ? 1 : 0;
+    f->manual_tuning = 1;
     SQ_CATCH
 }
 int sq_fdm_get_tuning(sq_fdm *f, int *slab, int *threads, int *path) {
     SQ_TRY
     SQ_REQUIRE(f, "NULL handle");
+    fdm_select_tuning(f);
     if (slab) *slab = f->slab;
     if (threads) *threads = f->threads;
-    if (path) *path = f->path;
+    if (path) *path = f->path == 1 ? 1 : (f->use_v2 ? 2 : 0);
     SQ_CATCH
 }
 int sq_fdm_stream(sq_fdm *f, void **cuda_stream) {

@@ -163,6 +163,25 @@ __global__ void k_cg_update_p_prec(CgState *__restrict__ st, const CgState *__re
     if (blockIdx.x == 0 && threadIdx.x == 0) { st->rz_re = rz.x; st->rz_im = rz.y; }
 }
 
+bool fdm_v2_supported(const sq_fdm *f, int mode, int S, int T);
+void fdm_select_tuning(sq_fdm *f);
+int fdm_v2_launch_cg(sq_fdm *f, double2 *z, const double2 *p_old, double2 *p_new, const double2 *d, const CgState *cur, CgState *nxt,
+                     const double *rr_part, int nrr, const double *beta_part, int nbeta, int beta_complex, int iter, int check,
+                     double *pAp_part);
+
+// end-of-batch convergence test for the fused scheme (the in-kernel test of iteration j runs in iteration j+1)
+__global__ void k_cg_final_check(CgState *st, const double *__restrict__ rr_part, int npart, int iter) {
+    __shared__ double sh[3];
+    if (st->done) return;
+    reduce_partials(rr_part, npart, 1, sh);
+    if (threadIdx.x == 0) {
+        double eps = sqrt(sh[0]) / st->normb;
+        st->eps = eps;
+        st->iters = iter;
+        st->done = (eps < st->tol) ? 1 : ((eps == eps) ? 0 : 2);
+    }
+}
+
 static int vec_grid(const sq_fdm *f, size_t n, int threads) {
     size_t want = (n + threads - 1) / threads;
     size_t cap = (size_t)f->num_sms * 4;
@@ -211,6 +230,43 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
     i64 it = 0;
     int cur = 0;
     bool finished = false;
+    fdm_select_tuning(f);
+    const bool fused = !prec && f->path == 0 && f->use_v2 && fdm_v2_supported(f, 2, f->slab, f->threads) && !getenv("SQ_NO_CG_FUSION");
+    if (fused) {
+        // Two kernels per iteration: K_A' forms p = r + beta p on load (ping-ponged p buffers), tests the convergence of
+        // the previous iteration and applies M^T M; K_B updates x and r.  tmp1 is the second p buffer.
+        double2 *pb[2] = {p, f->tmp1.p};
+        int pc = 0;
+        while (!finished) {
+            i64 upto = std::min<i64>(maxiter, it + batch);
+            for (; it < upto;) {
+                it++;
+                const CgState *sc = st + cur;
+                CgState *sn = st + (cur ^ 1);
+                int npart = 0;
+                if (it == 1) {
+                    fdm_mul_dev(f, SQ_OP_MTM, z, pb[pc], part_pAp, &npart, sc);       // p0 = r0, nothing to fuse
+                    k_cg_update_xr<<<G, TB, 0, s>>>(sc, x, r, pb[pc], z, n, part_pAp, npart, 0, part_rr);
+                } else {
+                    npart = fdm_v2_launch_cg(f, z, pb[pc], pb[pc ^ 1], r, sc, sn, part_rr, G, part_rr, G, 0, (int)it, 1, part_pAp);
+                    pc ^= 1;
+                    cur ^= 1;
+                    k_cg_update_xr<<<G, TB, 0, s>>>(sn, x, r, pb[pc], z, n, part_pAp, npart, 0, part_rr);
+                }
+                f->launches += 1;
+            }
+            k_cg_final_check<<<1, 64, 0, s>>>(st + cur, part_rr, G, (int)it);
+            SQ_LAUNCH_CHECK();
+            f->launches++;
+            SQ_CUDA(cudaMemcpyAsync(f->h_cg, st + cur, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+            SQ_CUDA(cudaStreamSynchronize(s));
+            if (f->h_cg->done || it >= maxiter) finished = true;
+        }
+        if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+        *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
+        *eps = f->h_cg->eps;
+        return;
+    }
     // is the system already solved?  (cheap check folded into the first batch read-back)
     while (!finished) {
         i64 upto = std::min<i64>(maxiter, it + batch);

@@ -235,6 +235,7 @@ void elph_refresh_fdm(sq_elph *e) {
     SQ_LAUNCH_CHECK();
     f->launches++;
     f->coef_version++;
+    f->cs_uniform = (e->Nssh == 0) ? 1 : 0;       // no SSH coupling => hoppings (and cosh, sinh) are tau-independent
 }
 
 void elph_build_Vt(sq_elph *e) {

@@ -11,6 +11,8 @@
 // flight share one __syncthreads per step.  |w|^2 = p.A p for CG falls out of the first phase.
 #include "sq_internal.h"
 
+#include <algorithm>
+
 // ---------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------
@@ -293,6 +295,15 @@ __global__ void k_fdm_update(double *__restrict__ expV, double2 *__restrict__ cs
     }
 }
 
+// flag = 1 if any (cosh, sinh) differs from its slice-0 value
+__global__ void k_cs_nonuniform(const double2 *__restrict__ cs, int L, int Nh, int *__restrict__ flag) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)L * Nh) return;
+    int h = (int)(idx % Nh);
+    double2 a = cs[idx], b = cs[h];
+    if (a.x != b.x || a.y != b.y) *flag = 1;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // layout conversion at the host boundary: (rows x cols) with rows fastest  <->  cols fastest
 // ---------------------------------------------------------------------------------------------------
@@ -338,6 +349,12 @@ void fdm_transpose_real(sq_fdm *f, double *dst, const double *src, int rows, int
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+bool fdm_v2_supported(const sq_fdm *f, int mode, int S, int T);
+void fdm_select_tuning(sq_fdm *f);
+void fdm_v2_set_attributes(sq_fdm *f);
+void fdm_v2_launch(sq_fdm *f, int mode, int S, int T, double2 *out, const double2 *in, double *part, const CgState *skip);
+int fdm_v2_tx(const sq_fdm *f);
+
 KParams sq_fdm::kparams(int S, int T) const {
     KParams P;
     P.L = (int)L; P.N = (int)N; P.Nh = (int)Nh; P.C = (int)C; P.sym = sym; P.S = S;
@@ -360,6 +377,11 @@ static size_t fused_smem_bytes(const sq_fdm *f, int mode, int S) {
 
 template <int MODE>
 static void launch_fused(sq_fdm *f, int S, int T, double2 *out, const double2 *in, double *part, const CgState *skip) {
+    if (f->use_v2 && fdm_v2_supported(f, MODE, S, T)) {
+        fdm_v2_launch(f, MODE, S, T, out, in, part, skip);
+        return;
+    }
+    if (T & (T - 1)) T = 1 << (31 - __builtin_clz(T));       // the generic kernel needs a power-of-two block
     KParams P = f->kparams(S, T);
     size_t smem = fused_smem_bytes(f, MODE, S);
     int grid = (int)((f->L + S - 1) / S);
@@ -428,6 +450,7 @@ void fdm_mul_dev(sq_fdm *f, int op, double2 *out, const double2 *in, double *pAp
         src = f->tmp2.p;
     }
     if (f->path == 0) {
+        fdm_select_tuning(f);
         int S = f->slab, T = f->threads;
         if (op == 2) {
             launch_fused<2>(f, S, T, out, src, pAp_partials, skip);
@@ -469,7 +492,13 @@ static void fdm_autotune(sq_fdm *f) {
     if (Smax == 0) { f->path = 1; f->slab = 0; f->threads = 256; return; }
     f->path = 0;
     const char *envS = getenv("SQ_SLAB"), *envT = getenv("SQ_THREADS");
-    if (envS && envT) { f->slab = std::min(Smax, std::max(1, atoi(envS))); f->threads = atoi(envT); return; }
+    if (envS && envT) {
+        f->slab = std::min(Smax, std::max(1, atoi(envS)));
+        f->threads = atoi(envT);
+        const char *ev = getenv("SQ_V2");
+        f->use_v2 = (ev && atoi(ev) == 0) ? 0 : (fdm_v2_supported(f, 2, f->slab, f->threads) ? 1 : 0);
+        return;
+    }
     std::vector<int> Ss;
     for (int S = 1; S <= Smax; S++) {
         int nsl = (int)((f->L + S - 1) / S);
@@ -489,24 +518,49 @@ static void fdm_autotune(sq_fdm *f) {
     SQ_CUDA(cudaEventCreate(&e0));
     SQ_CUDA(cudaEventCreate(&e1));
     float best = 1e30f;
-    int bS = Ss[0], bT = 256;
+    int bS = Ss[0], bT = 256, bV = 0;
+    const char *envV = getenv("SQ_V2");
+    const bool allow_v2 = !(envV && atoi(envV) == 0);
+    std::vector<std::pair<int, int>> cands;                   // (threads, version)
+    for (int T : {256, 512, 1024}) cands.push_back({T, 0});
+    if (allow_v2 && f->sym && f->C >= 1 && f->C <= 8) {
+        int TX = fdm_v2_tx(f);
+        for (int TY = 1; TX * TY <= 1024; TY *= 2)
+            if (TX * TY >= 64) cands.push_back({TX * TY, 1});
+    }
     for (int S : Ss) {
-        for (int T : {256, 512, 1024}) {
-            for (int rep = 0; rep < 2; rep++) launch_fused<2>(f, S, T, f->z.p, f->p.p, nullptr, nullptr);
+        for (auto &cd : cands) {
+            int T = cd.first;
+            f->use_v2 = cd.second;
+            if (cd.second && !fdm_v2_supported(f, 2, S, T)) continue;
+            for (int rep = 0; rep < 2; rep++) launch_fused<2>(f, S, T, f->io2.p, f->io1.p, nullptr, nullptr);
             SQ_CUDA(cudaEventRecord(e0, f->stream));
-            for (int rep = 0; rep < 5; rep++) launch_fused<2>(f, S, T, f->z.p, f->p.p, nullptr, nullptr);
+            for (int rep = 0; rep < 5; rep++) launch_fused<2>(f, S, T, f->io2.p, f->io1.p, nullptr, nullptr);
             SQ_CUDA(cudaEventRecord(e1, f->stream));
             SQ_CUDA(cudaEventSynchronize(e1));
             float ms = 0;
             SQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-            if (ms < best) { best = ms; bS = S; bT = T; }
+            if (ms < best) { best = ms; bS = S; bT = T; bV = cd.second; }
         }
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     f->slab = bS;
     f->threads = bT;
-    f->launches = 0;
+    f->use_v2 = bV;
+}
+
+// (slab, threads, kernel) are tuned separately for tau-dependent and tau-uniform hoppings, lazily on first use
+void fdm_select_tuning(sq_fdm *f) {
+    if (f->path != 0 || f->manual_tuning) return;
+    int u = f->cs_uniform ? 1 : 0;
+    if (!f->tuned[u][0]) {
+        i64 keep = f->launches;
+        fdm_autotune(f);
+        f->launches = keep;
+        f->tuned[u][0] = 1; f->tuned[u][1] = f->slab; f->tuned[u][2] = f->threads; f->tuned[u][3] = f->use_v2;
+    }
+    f->slab = f->tuned[u][1]; f->threads = f->tuned[u][2]; f->use_v2 = f->tuned[u][3];
 }
 
 void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt, const i64 *perm, i64 C,
@@ -533,6 +587,7 @@ void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt,
         SQ_CUDA(cudaFuncSetAttribute(k_fdm_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
         SQ_CUDA(cudaFuncSetAttribute(k_fdm_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
         SQ_CUDA(cudaFuncSetAttribute(k_fdm_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        fdm_v2_set_attributes(f);
         std::vector<char> covered(N, 0);
         f->h_nt.resize(Nh);
         f->h_perm.resize(Nh);
@@ -559,6 +614,37 @@ void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt,
             }
         }
         SQ_REQUIRE(expect == Nh, "colour ranges do not cover all bonds");
+        // Shared-memory slots (fast path): the two sites of colour-0 bond b get slots b and nb0 + b, sites colour 0
+        // does not touch follow; the bonds of every other colour are then re-ordered by the slot of their first
+        // site.  Bonds of one colour commute, so any order inside a colour gives the same operator; the internal
+        // bond order (nt, perm, cs) is this refined order and h_abi_chk maps it back to the caller's.
+        f->h_slot.assign(N, -1);
+        f->h_abi_chk.resize(Nh);
+        for (i64 h = 0; h < Nh; h++) f->h_abi_chk[h] = (int)h;
+        {
+            int next = 0;
+            if (C > 0) {
+                int nb0 = f->chi[0] - f->clo[0];
+                for (int b = 0; b < nb0; b++) { f->h_slot[f->h_nt[b].x] = b; f->h_slot[f->h_nt[b].y] = nb0 + b; }
+                next = 2 * nb0;
+            }
+            for (i64 i = 0; i < N; i++) if (f->h_slot[i] < 0) f->h_slot[i] = next++;
+            for (i64 c = 1; c < C; c++) {
+                int lo = f->clo[c], hi = f->chi[c];
+                std::vector<int> idx(hi - lo);
+                for (int k = 0; k < hi - lo; k++) idx[k] = lo + k;
+                std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return f->h_slot[f->h_nt[a].x] < f->h_slot[f->h_nt[b].x]; });
+                std::vector<int2> nt2(hi - lo);
+                std::vector<int> pm2(hi - lo), ab2(hi - lo);
+                for (int k = 0; k < hi - lo; k++) { nt2[k] = f->h_nt[idx[k]]; pm2[k] = f->h_perm[idx[k]]; ab2[k] = f->h_abi_chk[idx[k]]; }
+                for (int k = 0; k < hi - lo; k++) { f->h_nt[lo + k] = nt2[k]; f->h_perm[lo + k] = pm2[k]; f->h_abi_chk[lo + k] = ab2[k]; }
+            }
+        }
+        std::vector<int2> h_nts(Nh);
+        for (i64 h = 0; h < Nh; h++) h_nts[h] = make_int2(f->h_slot[f->h_nt[h].x], f->h_slot[f->h_nt[h].y]);
+        f->nts.alloc(Nh + 1); f->nts.upload(h_nts.data(), Nh, f->stream);
+        f->slot.alloc(N); f->slot.upload(f->h_slot.data(), N, f->stream);
+        SQ_CUDA(cudaStreamSynchronize(f->stream));
         std::vector<int> unc;
         for (i64 i = 0; i < N; i++) if (!covered[i]) unc.push_back((int)i);
         f->nunc0 = (int)unc.size();
@@ -580,7 +666,9 @@ void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt,
         std::vector<double2> cs1((size_t)L * Nh + 1, make_double2(1.0, 0.0));
         f->cs.upload(cs1.data(), (size_t)L * Nh, f->stream);
         SQ_CUDA(cudaStreamSynchronize(f->stream));
-        fdm_autotune(f);
+        fdm_autotune(f);              // decides path 0 / 1; the per-mode tuning itself is refined lazily
+        if (f->path == 0) { f->tuned[0][0] = 1; f->tuned[0][1] = f->slab; f->tuned[0][2] = f->threads; f->tuned[0][3] = f->use_v2; }
+        f->launches = 0;
         SQ_CUDA(cudaStreamSynchronize(f->stream));
     } catch (...) {
         delete f;
@@ -612,7 +700,15 @@ void fdm_update_impl(sq_fdm *f, const double *V, const double *t, double dtau) {
     f->iod1.upload(V, (size_t)f->L * f->N, f->stream);
     f->iod2.upload(t, (size_t)f->L * f->Nh, f->stream);
     fdm_update_dev(f, f->iod1.p, f->iod2.p, dtau);
+    // tau-independent hoppings enable the register-resident coefficient path of the fast kernel
+    if (!f->flag.p) f->flag.alloc(1);
+    SQ_CUDA(cudaMemsetAsync(f->flag.p, 0, sizeof(int), f->stream));
+    size_t nT = (size_t)f->L * f->Nh;
+    if (nT) k_cs_nonuniform<<<(unsigned)((nT + 255) / 256), 256, 0, f->stream>>>(f->cs.p, (int)f->L, (int)f->Nh, f->flag.p);
+    int nonuni = 0;
+    SQ_CUDA(cudaMemcpyAsync(&nonuni, f->flag.p, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
     SQ_CUDA(cudaStreamSynchronize(f->stream));
+    f->cs_uniform = nonuni ? 0 : 1;
 }
 
 void fdm_get_coefficients_impl(sq_fdm *f, double *expV, double *ch, double *sh) {
@@ -625,7 +721,11 @@ void fdm_get_coefficients_impl(sq_fdm *f, double *expV, double *ch, double *sh) 
     SQ_CUDA(cudaStreamSynchronize(f->stream));
     for (i64 l = 0; l < f->L; l++) {
         for (i64 i = 0; i < f->N; i++) expV[l + i * f->L] = hV[i + l * f->N];
-        for (i64 h = 0; h < f->Nh; h++) { ch[l + h * f->L] = hcs[h + l * f->Nh].x; sh[l + h * f->L] = hcs[h + l * f->Nh].y; }
+        for (i64 h = 0; h < f->Nh; h++) {
+            i64 ha = f->h_abi_chk[h];
+            ch[l + ha * f->L] = hcs[h + l * f->Nh].x;
+            sh[l + ha * f->L] = hcs[h + l * f->Nh].y;
+        }
     }
 }
 

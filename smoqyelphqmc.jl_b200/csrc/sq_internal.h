@@ -40,6 +40,14 @@ struct sq_fdm {
     DevBuf<int2> nt;
     DevBuf<int> perm, unc0;
     int nunc0 = 0;
+    // fast path (fdm_v2.cu): shared-memory slot of every site, bonds as slot pairs
+    DevBuf<int2> nts;
+    DevBuf<int> slot;
+    std::vector<int> h_slot;
+    std::vector<int> h_abi_chk;              // internal bond index -> checkerboard index of the ABI tables
+    int use_v2 = 0;                          // chosen by the autotuner / sq_fdm_set_fast_path
+    int cs_uniform = 0;                      // (cosh, sinh) do not depend on tau (no SSH coupling): register-resident path
+    DevBuf<int> flag;                        // device scratch flag
     DevBuf<double> expV;                     // [l][i]
     DevBuf<double2> cs;                      // [l][h]
     DevBuf<double2> tmp1, tmp2, r, p, z;     // [l][i]
@@ -53,6 +61,8 @@ struct sq_fdm {
     // fused-kernel configuration
     int path = 0;                            // 0 = slices staged in shared memory, 1 = global-memory passes
     int slab = 0, threads = 0;
+    int tuned[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // per coefficient mode (general / tau-uniform): valid, slab, threads, v2
+    int manual_tuning = 0;
     int num_sms = 148;
     size_t smem_optin = 0;
     i64 launches = 0;

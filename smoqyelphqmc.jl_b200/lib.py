@@ -34,6 +34,7 @@ SIGNATURES = {
     "sq_fdm_cg_dev": [vp, vp, vp, i32, vp, f64, i64, vp, vp],
     "sq_fdm_set_tuning": [vp, i32, i32],
     "sq_fdm_get_tuning": [vp, vp, vp, vp],
+    "sq_fdm_set_fast_path": [vp, i32],
     "sq_fdm_stream": [vp, pp],
     "sq_kpm_create": [pp, vp, f64, i64, f64, f64],
     "sq_kpm_destroy": [vp],

@@ -25,6 +25,7 @@ MODELS = {
     "cfg2": lambda: mdl.config("cfg2"),
     "cfg3": lambda: mdl.config("cfg3"),
     "cfg4": lambda: mdl.config("cfg4"),
+    "cfg5": lambda: mdl.config("cfg5"),
     "mixed_odd": lambda: mdl.holstein_ssh_chain(7, 0.65),     # odd ring: 3 colours, last colour 1 bond, uncovered sites
     "tiny_L1": lambda: mdl.ossh_chain(4, 0.05),               # Ltau = 1
     "tiny_L2": lambda: mdl.ossh_chain(6, 0.10),               # Ltau = 2
@@ -60,21 +61,29 @@ def test_products_match_oracle(name, sym):
         assert relerr(got, want) < RTOL, (name, sym, op, relerr(got, want))
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4", "cfg5", "mixed_odd"])
 def test_all_tunings_agree(name):
     m, rng, ref, fdm = setup(name, True)
     v = rand_cvec(rng, m)
     want = ref.mul_MtM(v)
-    assert fdm.tuning["path"] == 0
-    for slab in (1, 2, 3, 5):
-        for threads in (128, 256, 1024):
-            try:
-                fdm.set_tuning(slab, threads)
-            except Exception:
-                continue
-            assert relerr(fdm.mul_MtM(v), want) < RTOL, (slab, threads)
-            assert relerr(fdm.mul_M(v), ref.mul_M(v)) < RTOL
-            assert relerr(fdm.mul_Mt(v), ref.mul_Mt(v)) < RTOL
+    assert fdm.tuning["path"] in (0, 2)
+    results = {}
+    for fast in (False, True):
+        fdm.set_fast_path(fast)
+        for slab in (1, 2, 3, 5):
+            for threads in (64, 128, 256, 512, 576, 1024):
+                try:
+                    fdm.set_tuning(slab, threads)
+                except Exception:
+                    continue
+                got = fdm.mul_MtM(v)
+                assert relerr(got, want) < RTOL, (fast, slab, threads)
+                assert relerr(fdm.mul_M(v), ref.mul_M(v)) < RTOL
+                assert relerr(fdm.mul_Mt(v), ref.mul_Mt(v)) < RTOL
+                results[(fast, slab, threads)] = got
+    # the fast and the generic fused kernels perform the same arithmetic: bit-identical output
+    vals = list(results.values())
+    assert all(np.array_equal(vals[0], w) for w in vals[1:])
 
 
 def test_linearity_and_adjointness_full_size():

@@ -51,15 +51,18 @@ def main():
         res["auto_us_cold"] = med
         res["auto_GBs_cold"] = B / med / 1e3
         sweep = {}
-        if auto["path"] == 0:
-            for S in (1, 2, 3, 4, 5, 6, 8, 10, 16, 20):
-                for T in (256, 512, 1024):
-                    try:
-                        fdm.set_tuning(S, T)
-                    except Exception:
-                        continue
-                    med, mn = time_op(fdm, 2, d_out, d_in, reps=20)
-                    sweep[f"S{S}_T{T}"] = round(med, 2)
+        if auto["path"] != 1:
+            for fast in (0, 1):
+                fdm.set_fast_path(fast)
+                for S in (1, 2, 3, 4, 5, 6, 8):
+                    for T in (128, 256, 512, 576, 1024):
+                        try:
+                            fdm.set_tuning(S, T)
+                        except Exception:
+                            continue
+                        med, mn = time_op(fdm, 2, d_out, d_in, reps=20)
+                        sweep[f"v{fast+1}_S{S}_T{T}"] = round(med, 2)
+            fdm.set_fast_path(auto["path"] == 2)
             fdm.set_tuning(auto["slab"], auto["threads"])
         res["sweep_us_hot"] = sweep
         for op, nm in ((0, "M"), (1, "Mt")):
