@@ -1,0 +1,252 @@
+# SmoQyElPhB200.jl -- `ccall` shim that keeps SmoQyElPhQMC's exported API for the hot path and forwards the
+# arithmetic to libsmoqyelph_b200.so (include/smoqyelph_b200.h).
+#
+# NOT EXECUTED in the build container (no `julia` binary there): this file is the reference-side binding a
+# maintainer would add; every C entry point it uses is exercised by the Python twin (smoqyelphqmc.jl_b200/api.py)
+# in tests/.  Type names, type parameters used for dispatch and method signatures follow
+# /root/reference/src/SmoQyElPhQMC.jl:60-124; struct internals are free to change (SURVEY.md 8b: no driver reads a
+# field of these structs).
+module SmoQyElPhB200
+
+using LinearAlgebra, Random
+import LinearAlgebra: mul!, lmul!, ldiv!
+import SmoQyDQMC
+import SmoQyDQMC: FermionPathIntegral, ElectronPhononParameters, hmc_update!, update_chemical_potential!
+using Checkerboard: checkerboard_decomposition!
+
+export FermionDetMatrix, SymFermionDetMatrix, AsymFermionDetMatrix, KPMPreconditioner, PFFCalculator,
+       EFAPFFHMCUpdater, GreensEstimator
+
+const LIB = get(ENV, "SMOQYELPH_B200_LIB", "libsmoqyelph_b200.so")
+
+struct B200Error <: Exception
+    msg::String
+end
+# non-zero status => throw, so the reference's try/catch "numerical instability => reject" paths keep working
+@inline function check(status::Cint)
+    status == 0 && return nothing
+    throw(B200Error(unsafe_string(ccall((:sq_last_error, LIB), Cstring, ()))))
+end
+
+# ---- FermionDetMatrix (src/FermionDetMatrix.jl:19-55, 66-111, 137-204) ------------------------------------------
+abstract type FermionDetMatrix{T<:Number, E<:AbstractFloat} end
+
+mutable struct CGConfig{E}     # keeps `fdm.cgs.tol` / `fdm.cgs.maxiter` readable (update_chemical_potential.jl:32-33)
+    maxiter::Int
+    tol::E
+end
+
+mutable struct SymFermionDetMatrix{T,E} <: FermionDetMatrix{T,E}
+    h::Ptr{Cvoid}; Lτ::Int; N::Int; cgs::CGConfig{E}
+end
+mutable struct AsymFermionDetMatrix{T,E} <: FermionDetMatrix{T,E}
+    h::Ptr{Cvoid}; Lτ::Int; N::Int; cgs::CGConfig{E}
+end
+
+function _create(::Type{F}, sym::Bool, fpi::FermionPathIntegral{T,E}; maxiter::Int, tol::E, device::Int) where {F,T,E}
+    T <: Real || error("libsmoqyelph_b200 supports real hoppings only (SURVEY.md 9 Q9)")
+    (; neighbor_table, N, Lτ) = fpi
+    nt = copy(neighbor_table)
+    perm, colors = checkerboard_decomposition!(nt)          # src/FermionDetMatrix.jl:95-97
+    lo = Int64[first(r) for r in colors]; hi = Int64[last(r) for r in colors]
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sq_fdm_create, LIB), Cint,
+                (Ref{Ptr{Cvoid}}, Cint, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Cdouble, Int64, Cint),
+                h, sym, Lτ, N, size(nt, 2), nt, Vector{Int64}(perm), length(colors), lo, hi, tol, maxiter, device))
+    fdm = F{T,E}(h[], Lτ, N, CGConfig{E}(maxiter, tol))
+    finalizer(f -> ccall((:sq_fdm_destroy, LIB), Cint, (Ptr{Cvoid},), f.h), fdm)
+    update!(fdm, fpi)
+    return fdm
+end
+SymFermionDetMatrix(fpi::FermionPathIntegral{T,E}; maxiter::Int = fpi.N * fpi.Lτ, tol::E = 1e-6, device::Int = 0) where {T,E} =
+    _create(SymFermionDetMatrix, true, fpi; maxiter, tol, device)
+AsymFermionDetMatrix(fpi::FermionPathIntegral{T,E}; maxiter::Int = fpi.N * fpi.Lτ, tol::E = 1e-6, device::Int = 0) where {T,E} =
+    _create(AsymFermionDetMatrix, false, fpi; maxiter, tol, device)
+
+Base.size(f::FermionDetMatrix) = (f.Lτ * f.N, f.Lτ * f.N)
+Base.size(f::FermionDetMatrix, ::Int) = f.Lτ * f.N
+Base.eltype(::FermionDetMatrix{T}) where {T} = T
+
+# update!(fdm, fpi): src/FermionDetMatrix.jl:208-236
+function update!(f::FermionDetMatrix{T,E}, fpi::FermionPathIntegral{T,E}) where {T,E}
+    GC.@preserve fpi check(ccall((:sq_fdm_update, LIB), Cint, (Ptr{Cvoid}, Ptr{E}, Ptr{T}, Cdouble), f.h, fpi.V, fpi.t, fpi.Δτ))
+    return nothing
+end
+
+for (name, op) in ((:mul_M!, 0), (:mul_Mt!, 1), (:mul_MtM!, 2), (:mul_MMt!, 3))     # :329-563
+    @eval function $name(v′::AbstractVecOrMat{Complex{E}}, f::FermionDetMatrix{T,E}, v::AbstractVecOrMat{Complex{E}}) where {T,E}
+        GC.@preserve v′ v check(ccall((:sq_fdm_mul, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Complex{E}}, Ptr{Complex{E}}), f.h, $op, v′, v))
+        return nothing
+    end
+end
+mul!(v′::AbstractVecOrMat, f::FermionDetMatrix, v::AbstractVecOrMat) = mul_MtM!(v′, f, v)      # :304-315
+lmul!(f::FermionDetMatrix, v::AbstractVecOrMat) = mul_MtM!(v, f, v)                           # :292-301
+lmul_M!(f::FermionDetMatrix, v) = mul_M!(v, f, v)
+lmul_Mt!(f::FermionDetMatrix, v) = mul_Mt!(v, f, v)
+
+# ---- KPMPreconditioner (src/KPMPreconditioner.jl:198-284, 554-597) ----------------------------------------------
+mutable struct KPMPreconditioner{E}
+    h::Ptr{Cvoid}; active::Bool; bounds::NTuple{2,E}
+end
+function KPMPreconditioner(f::FermionDetMatrix{T,E}; rng::AbstractRNG = Random.default_rng(), rbuf::E = 0.10, n::Int = 20,
+                           a1::E = 1.0, a2::E = 1.0) where {T,E}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sq_kpm_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Cdouble, Int64, Cdouble, Cdouble), h, f.h, rbuf, n, a1, a2))
+    P = KPMPreconditioner{E}(h[], false, (zero(E), zero(E)))
+    finalizer(p -> ccall((:sq_kpm_destroy, LIB), Cint, (Ptr{Cvoid},), p.h), P)
+    update_preconditioner!(P, f, rng)
+    return P
+end
+# the randn!(rng, v) Lanczos start is drawn in Julia so the rng stream matches the reference (:634)
+function update_preconditioner!(P::KPMPreconditioner{E}, f::FermionDetMatrix, rng::AbstractRNG) where {E}
+    start = randn(rng, E, f.N); act = Ref{Cint}(0); b = zeros(E, 2)
+    check(ccall((:sq_kpm_update, LIB), Cint, (Ptr{Cvoid}, Ptr{E}, Ref{Cint}, Ptr{E}), P.h, start, act, b))
+    P.active = act[] != 0; P.bounds = (b[1], b[2])
+    return nothing
+end
+update_preconditioner!(P, ignore...) = nothing                                                  # :600
+function ldiv!(u′::AbstractVecOrMat{Complex{E}}, P::KPMPreconditioner{E}, u::AbstractVecOrMat{Complex{E}}) where {E}
+    GC.@preserve u′ u check(ccall((:sq_kpm_ldiv, LIB), Cint, (Ptr{Cvoid}, Ptr{Complex{E}}, Ptr{Complex{E}}), P.h, u′, u))
+    return nothing
+end
+
+_kpm_handle(P::KPMPreconditioner) = P.h
+_kpm_handle(::UniformScaling) = C_NULL
+
+# ldiv!(x, fdm, b; preconditioner, rng, maxiter, tol) -> (iters, ϵ): src/FermionDetMatrix.jl:248-288
+function ldiv!(x::AbstractVecOrMat{Complex{E}}, f::FermionDetMatrix{T,E}, b::AbstractVecOrMat{Complex{E}};
+               preconditioner = I, rng::AbstractRNG = Random.default_rng(), maxiter::Int = f.cgs.maxiter, tol::E = f.cgs.tol) where {T,E}
+    start = preconditioner isa KPMPreconditioner ? randn(rng, E, f.N) : E[]
+    iters = Ref{Int64}(0); ϵ = Ref{Cdouble}(0)
+    GC.@preserve x b start check(ccall((:sq_fdm_cg, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Complex{E}}, Ptr{Complex{E}}, Cint, Ptr{Cvoid}, Cint, Ptr{E}, Cdouble, Int64, Ref{Int64}, Ref{Cdouble}),
+        f.h, x, b, x === b, _kpm_handle(preconditioner), preconditioner isa KPMPreconditioner, isempty(start) ? C_NULL : pointer(start),
+        tol, maxiter, iters, ϵ))
+    return Int(iters[]), ϵ[]
+end
+ldiv!(f::FermionDetMatrix, v::AbstractVecOrMat; kw...) = ldiv!(v, f, v; kw...)
+
+# ---- electron-phonon tables: the fields of SmoQyDQMC.ElectronPhononParameters the path reads ---------------------
+mutable struct B200ElPh
+    h::Ptr{Cvoid}
+end
+function B200ElPh(elph::ElectronPhononParameters{T,E}, fpi::FermionPathIntegral{T,E}, tbp, f::FermionDetMatrix{T,E}) where {T,E}
+    ph = elph.phonon_parameters; hol = elph.holstein_parameters_up; ssh = elph.ssh_parameters_up
+    nun = hol.nholstein == 0 ? 1 : hol.Nholstein ÷ hol.nholstein
+    phsym = Int32[hol.ph_sym_form[(c - 1) ÷ nun + 1] for c in 1:hol.Nholstein]       # expanded per coupling
+    hop_of = zeros(Int64, ssh.Nssh)                                                  # inverse of hopping_to_couplings
+    for (hop, cs) in enumerate(ssh.hopping_to_couplings), c in cs; hop_of[c] = hop; end
+    V0 = Vector{E}(tbp.ϵ .- tbp.μ); t0 = Vector{E}(real.(tbp.t))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sq_elph_create, LIB), Cint,
+        (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Cdouble, Int64, Ptr{E}, Ptr{E}, Ptr{E}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{E}, Ptr{E}, Ptr{E}, Ptr{E},
+         Ptr{Int32}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{E}, Ptr{E}, Ptr{E}, Ptr{E}, Ptr{E}, Ptr{E}),
+        h, f.h, elph.Δτ, length(ph.Ω), ph.Ω, ph.Ω4, ph.M, hol.Nholstein, Vector{Int64}(hol.coupling_to_phonon), Vector{Int64}(hol.coupling_to_site),
+        hol.α, hol.α2, hol.α3, hol.α4, phsym, ssh.Nssh, Matrix{Int64}(ssh.coupling_to_phonon), hop_of, real.(ssh.α), real.(ssh.α2),
+        real.(ssh.α3), real.(ssh.α4), V0, t0))
+    e = B200ElPh(h[])
+    finalizer(x -> ccall((:sq_elph_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), e)
+    return e
+end
+push_x!(e::B200ElPh, x::Matrix{Float64}) = check(ccall((:sq_elph_set_x, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), e.h, x))
+pull_x!(x::Matrix{Float64}, e::B200ElPh) = check(ccall((:sq_elph_get_x, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), e.h, x))
+
+# ---- PFFCalculator (src/PFFCalculator.jl:9-158) ------------------------------------------------------------------
+mutable struct PFFCalculator{E<:AbstractFloat}
+    h::Ptr{Cvoid}; elph::B200ElPh
+end
+function PFFCalculator(elph::ElectronPhononParameters{T,E}, f::FermionDetMatrix{T,E}; fermion_path_integral, tight_binding_parameters) where {T,E}
+    e = B200ElPh(elph, fermion_path_integral, tight_binding_parameters, f)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sq_pff_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cvoid}), h, e.h))
+    p = PFFCalculator{E}(h[], e)
+    finalizer(x -> ccall((:sq_pff_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), p)
+    return p
+end
+function calculate_fermionic_action!(p::PFFCalculator{E}, elph, f, preconditioner, rng::AbstractRNG, tol::E, maxiter::Int) where {E}
+    push_x!(p.elph, elph.x)
+    check(ccall((:sq_elph_refresh_fdm, LIB), Cint, (Ptr{Cvoid},), p.elph.h))
+    start = preconditioner isa KPMPreconditioner ? randn(rng, E, f.N) : E[]
+    Sf = Ref{Cdouble}(0); it = Ref{Int64}(0); ϵ = Ref{Cdouble}(0)
+    check(ccall((:sq_pff_action, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{E}, Cdouble, Int64, Ref{Cdouble}, Ref{Int64}, Ref{Cdouble}),
+                p.h, _kpm_handle(preconditioner), isempty(start) ? C_NULL : pointer(start), tol, maxiter, Sf, it, ϵ))
+    return Sf[], Int(it[]), ϵ[]
+end
+function calculate_derivative_fermionic_action!(∂Sf∂x::AbstractMatrix{E}, p::PFFCalculator{E}, elph, f, preconditioner, rng::AbstractRNG,
+                                                tol::E, maxiter::Int) where {E}
+    push_x!(p.elph, elph.x)
+    check(ccall((:sq_elph_refresh_fdm, LIB), Cint, (Ptr{Cvoid},), p.elph.h))
+    start = preconditioner isa KPMPreconditioner ? randn(rng, E, f.N) : E[]
+    Sf = Ref{Cdouble}(0); it = Ref{Int64}(0); ϵ = Ref{Cdouble}(0)
+    check(ccall((:sq_pff_force, LIB), Cint, (Ptr{Cvoid}, Ptr{E}, Ptr{Cvoid}, Ptr{E}, Cdouble, Int64, Ref{Cdouble}, Ref{Int64}, Ref{Cdouble}),
+                p.h, ∂Sf∂x, _kpm_handle(preconditioner), isempty(start) ? C_NULL : pointer(start), tol, maxiter, Sf, it, ϵ))
+    return Sf[], Int(it[]), ϵ[]
+end
+
+# ---- EFAPFFHMCUpdater (src/EFAPFFHMCUpdater.jl:9-279) -------------------------------------------------------------
+mutable struct EFAPFFHMCUpdater{E<:AbstractFloat}
+    Nt::Int; Δt::E; δ::E; η::E
+    h::Ptr{Cvoid}           # created lazily once the PFFCalculator is known (hmc_update! receives it as a keyword)
+end
+EFAPFFHMCUpdater(; electron_phonon_parameters::ElectronPhononParameters{T,E}, Nt::Int, Δt::E = π / (2 * Nt), η::E = 0.0,
+                 δ::E = 0.05) where {T,E} = EFAPFFHMCUpdater{E}(Nt, Δt, δ, η, C_NULL)
+
+# hmc_update!(elph, updater; ...) -> (accepted, iters_avg): the whole trajectory runs on the device.  x is pushed before
+# and pulled after; recenter! other than `identity` is not supported inside the device-resident trajectory.
+function hmc_update!(elph::ElectronPhononParameters{T,E}, u::EFAPFFHMCUpdater{E}; fermion_path_integral::FermionPathIntegral{T,E},
+                     fermion_det_matrix::FermionDetMatrix{T,E}, pff_calculator::PFFCalculator{E}, rng::AbstractRNG,
+                     recenter!::Function = identity, Nt::Int = u.Nt, Δt::E = u.Δt, δ::E = u.δ,
+                     tol_action::E = fermion_det_matrix.cgs.tol, tol_force::E = sqrt(fermion_det_matrix.cgs.tol),
+                     maxiter::Int = fermion_det_matrix.cgs.maxiter, preconditioner = I) where {T,E}
+    recenter! === identity || error("recenter! callbacks are not supported by the device-resident trajectory")
+    if u.h == C_NULL || Nt != u.Nt || Δt != u.Δt || δ != u.δ
+        u.h == C_NULL || ccall((:sq_hmc_destroy, LIB), Cint, (Ptr{Cvoid},), u.h)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:sq_hmc_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Int64, Cdouble, Cdouble, Cdouble, UInt64),
+                    h, pff_calculator.h, Nt, Δt, u.η, δ, rand(rng, UInt64)))
+        u.h = h[]; u.Nt = Nt; u.Δt = Δt; u.δ = δ
+    end
+    push_x!(pff_calculator.elph, elph.x)
+    check(ccall((:sq_elph_refresh_fdm, LIB), Cint, (Ptr{Cvoid},), pff_calculator.elph.h))
+    acc = Ref{Cint}(0); info = zeros(Cdouble, 8)
+    x0 = copy(elph.x)
+    check(ccall((:sq_hmc_update, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Int64, Ptr{Cdouble}, Int64, Ref{Cint}, Ptr{Cdouble}),
+                u.h, _kpm_handle(preconditioner), tol_action, tol_force, maxiter, C_NULL, 0, acc, info))
+    if acc[] != 0
+        pull_x!(elph.x, pff_calculator.elph)
+        SmoQyDQMC.update!(fermion_path_integral, elph, elph.x, x0)     # keep the host-side path integral consistent
+    end
+    return acc[] != 0, info[1]
+end
+
+# ---- GreensEstimator solves + update_chemical_potential! (src/Measurements/GreensEstimator.jl:63-175,
+#      src/update_chemical_potential.jl:21-73).  MuTuner stays in Julia. ---------------------------------------------
+mutable struct GreensEstimator{E}
+    h::Ptr{Cvoid}; Nrv::Int
+end
+function GreensEstimator(f::FermionDetMatrix{T,E}, model_geometry; Nrv::Int = 10, preconditioner = I, rng::AbstractRNG = Random.default_rng(),
+                         maxiter::Int = f.cgs.maxiter, tol::E = f.cgs.tol) where {T,E}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sq_greens_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Int64, UInt64), h, f.h, Nrv, rand(rng, UInt64)))
+    g = GreensEstimator{E}(h[], Nrv)
+    finalizer(x -> ccall((:sq_greens_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), g)
+    update_greens_estimator!(g, f; preconditioner, rng, maxiter, tol)
+    return g
+end
+function update_greens_estimator!(g::GreensEstimator{E}, f::FermionDetMatrix; preconditioner = I, rng = Random.default_rng(),
+                                  maxiter::Int, tol::E) where {E}
+    avg = Ref{Cdouble}(0)
+    check(ccall((:sq_greens_update, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Int64, Ref{Cdouble}),
+                g.h, _kpm_handle(preconditioner), C_NULL, tol, maxiter, avg))
+    return avg[]
+end
+function _measure(g::GreensEstimator)
+    n = zeros(ComplexF64, 1); d = zeros(ComplexF64, 1); N2 = zeros(ComplexF64, 1)
+    check(ccall((:sq_greens_measure, LIB), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}), g.h, n, d, N2))
+    return n[1], d[1], N2[1]
+end
+measure_n(g::GreensEstimator) = _measure(g)[1]
+measure_double_occ(g::GreensEstimator) = _measure(g)[2]
+measure_Nsqrd(g::GreensEstimator) = _measure(g)[3]
+
+end # module
