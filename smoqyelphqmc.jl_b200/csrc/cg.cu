@@ -226,7 +226,8 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
     SQ_LAUNCH_CHECK();
     f->launches += 4;
 
-    const int batch = prec ? 4 : 16;
+    int batch = prec ? 4 : 16;
+    if (const char *eb = getenv("SQ_CG_BATCH")) batch = std::max(1, atoi(eb));
     i64 it = 0;
     int cur = 0;
     bool finished = false;

@@ -133,6 +133,175 @@ k_kpm_cheb(const __grid_constant__ BbarParams P, double2 *__restrict__ z, const 
     for (int i = threadIdx.x; i < N; i += blockDim.x) zn[i] = ACC[i];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fast Chebyshev kernel (symmetric propagator, every site touched by the last colour, <= 8 colours, one bond per
+// thread per colour).  The recurrence is latency bound (156 sequential B-bar applications at cfg4), so everything
+// is arranged to shorten the dependent chain of one application:
+//   * the thread that owns bond (i, j) of the LAST colour keeps T_{k-1}, T_k and the accumulator of sites i and j in
+//     registers for the whole kernel; shared memory only holds the vector being propagated;
+//   * Gamma^T starts and Gamma ends with that same colour, so an application starts from and ends in registers:
+//     2C - 2 barriers per application instead of 2C + 3, no copy and no separate recurrence pass;
+//   * bond slots, (cosh, sinh) means and the diagonal means live in registers (no global loads in the loop);
+//   * sites are addressed through the bank-conflict-free slot numbering of the fused matvec.
+// ---------------------------------------------------------------------------------------------------
+struct BbarFast {
+    int N, C, nunc0;
+    int clo[8], chi[8];
+    const int2 *nts;        // bond -> slots
+    const int2 *nt;         // bond -> sites
+    const int *slot, *unc0;
+    const double2 *csbar;
+    const double *Dbar;
+    long long *dbg;
+};
+
+template <int CMAX>
+struct ChebEngine {
+    int c_i[CMAX], c_j[CMAX];
+    double cc[CMAX], ss[CMAX];
+    double d_i, d_j;
+    int last;                     // C - 1
+
+    __device__ __forceinline__ void init(const BbarFast &P) {
+        const int tx = threadIdx.x;
+        last = P.C - 1;
+#pragma unroll
+        for (int c = 0; c < CMAX; c++) {
+            c_i[c] = -1; c_j[c] = 0; cc[c] = 1.0; ss[c] = 0.0;
+            if (c < P.C && tx < P.chi[c] - P.clo[c]) {
+                int2 ij = __ldg(P.nts + P.clo[c] + tx);
+                double2 v = __ldg(P.csbar + P.clo[c] + tx);
+                c_i[c] = ij.x; c_j[c] = ij.y; cc[c] = v.x; ss[c] = v.y;
+            }
+        }
+        d_i = d_j = 1.0;
+        if (tx < P.chi[0] - P.clo[0]) {
+            int2 q = __ldg(P.nt + P.clo[0] + tx);
+            d_i = __ldg(P.Dbar + q.x);
+            d_j = __ldg(P.Dbar + q.y);
+        }
+    }
+    template <int Q>
+    __device__ __forceinline__ void smem_step(double2 *Y) {
+        if (c_i[Q] >= 0) {
+            double2 a = Y[c_i[Q]], b = Y[c_j[Q]];
+            rotb(a, b, cc[Q], ss[Q]);
+            Y[c_i[Q]] = a;
+            Y[c_j[Q]] = b;
+        }
+        __syncthreads();
+    }
+    template <int Q>
+    __device__ __forceinline__ void down(double2 *Y) {      // colours last-1 ... 1
+        if constexpr (Q >= 1) {
+            if (Q < last) smem_step<Q>(Y);
+            down<Q - 1>(Y);
+        }
+    }
+    template <int Q>
+    __device__ __forceinline__ void up(double2 *Y) {        // colours 1 ... last-1
+        if constexpr (Q < CMAX) {
+            if (Q < last) smem_step<Q>(Y);
+            up<Q + 1>(Y);
+        }
+    }
+    __device__ __forceinline__ void mid(double2 &a, double2 &b) {
+        rotb(a, b, cc[0], ss[0]);
+        a = make_double2(d_i * a.x, d_i * a.y);
+        b = make_double2(d_j * b.x, d_j * b.y);
+        rotb(a, b, cc[0], ss[0]);
+    }
+    // (a, b) <- (B-bar y)_{i,j} for the thread's last-colour bond; a, b enter holding y_i, y_j.
+    __device__ __forceinline__ void apply(double2 &a, double2 &b, double2 *Y, const BbarFast &P) {
+        if (last == 0) { mid(a, b); return; }            // single colour: all in registers
+        const int oi = pick_last(c_i), oj = pick_last(c_j);
+        const double cl = pick_lastd(cc), sl = pick_lastd(ss);
+        if (oi >= 0) {
+            rotb(a, b, cl, sl);
+            Y[oi] = a;
+            Y[oj] = b;
+        }
+        __syncthreads();
+        down<CMAX - 1>(Y);
+        if (c_i[0] >= 0) {
+            double2 u = Y[c_i[0]], v = Y[c_j[0]];
+            mid(u, v);
+            Y[c_i[0]] = u;
+            Y[c_j[0]] = v;
+        }
+        for (int q = threadIdx.x; q < P.nunc0; q += blockDim.x) {
+            int i = __ldg(P.unc0 + q);
+            double d = __ldg(P.Dbar + i);
+            int s = __ldg(P.slot + i);
+            double2 u = Y[s];
+            Y[s] = make_double2(d * u.x, d * u.y);
+        }
+        __syncthreads();
+        up<1>(Y);
+        if (oi >= 0) {
+            a = Y[oi];
+            b = Y[oj];
+            rotb(a, b, cl, sl);
+        }
+    }
+    __device__ __forceinline__ int pick_last(const int (&v)[CMAX]) const {
+        int r = v[0];
+#pragma unroll
+        for (int q = 1; q < CMAX; q++) r = (last == q) ? v[q] : r;
+        return r;
+    }
+    __device__ __forceinline__ double pick_lastd(const double (&v)[CMAX]) const {
+        double r = v[0];
+#pragma unroll
+        for (int q = 1; q < CMAX; q++) r = (last == q) ? v[q] : r;
+        return r;
+    }
+};
+
+template <int CMAX, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+k_kpm_cheb_fast(const __grid_constant__ BbarFast P, double2 *__restrict__ z, const int *__restrict__ sched, const int *__restrict__ order,
+                const int *__restrict__ coef_off, const double2 *__restrict__ coefs, int L, double avg, double imag_,
+                const CgState *__restrict__ skip) {
+    extern __shared__ double2 Y[];
+    if (skip && skip->done) return;
+    ChebEngine<CMAX> E;
+    E.init(P);
+    const int n = sched[blockIdx.x];
+    const int np = (n + 1 > (L + 1) / 2) ? L - 1 - n : n;
+    const int ord = order[np];
+    const double2 *c = coefs + coef_off[np];
+    double2 *zn = z + (size_t)n * P.N;
+    // owner sites of this thread: its bond in the last colour
+    int si = -1, sj = -1;
+    if (threadIdx.x < P.chi[E.last] - P.clo[E.last]) {
+        int2 q = __ldg(P.nt + P.clo[E.last] + threadIdx.x);
+        si = q.x; sj = q.y;
+    }
+    double2 t0i = make_double2(0, 0), t0j = t0i;
+    if (si >= 0) { t0i = zn[si]; t0j = zn[sj]; }
+    double2 yi = t0i, yj = t0j;
+    if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[0] = clock64();
+    E.apply(yi, yj, Y, P);
+    if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) { P.dbg[1] = clock64(); P.dbg[3] = ord; }
+    double2 t1i = make_double2((yi.x - avg * t0i.x) * imag_, (yi.y - avg * t0i.y) * imag_);
+    double2 t1j = make_double2((yj.x - avg * t0j.x) * imag_, (yj.y - avg * t0j.y) * imag_);
+    double2 c0 = c[0], c1 = c[1];
+    double2 acci = cadd(cmul(c0, t0i), cmul(c1, t1i)), accj = cadd(cmul(c0, t0j), cmul(c1, t1j));
+    for (int q = 2; q < ord; q++) {
+        yi = t1i; yj = t1j;
+        E.apply(yi, yj, Y, P);
+        double2 t2i = make_double2(2.0 * (yi.x - avg * t1i.x) * imag_ - t0i.x, 2.0 * (yi.y - avg * t1i.y) * imag_ - t0i.y);
+        double2 t2j = make_double2(2.0 * (yj.x - avg * t1j.x) * imag_ - t0j.x, 2.0 * (yj.y - avg * t1j.y) * imag_ - t0j.y);
+        double2 cq = c[q];
+        acci = cadd(acci, cmul(cq, t2i));
+        accj = cadd(accj, cmul(cq, t2j));
+        t0i = t1i; t0j = t1j; t1i = t2i; t1j = t2j;
+    }
+    if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[2] = clock64();
+    if (si >= 0) { zn[si] = acci; zn[sj] = accj; }
+}
+
 // tau-means of the operator coefficients (update_B̄!, :604-621): grid over sites/bonds, 32 x 8 threads
 __global__ void k_tau_means(double *__restrict__ Dbar, double2 *__restrict__ csbar, const double *__restrict__ expV,
                             const double2 *__restrict__ cs, int L, int N, int Nh) {
@@ -227,6 +396,22 @@ static int kpm_threads(const sq_kpm *k) {
     int t = 32;
     while (t < nbmax && t < 1024) t <<= 1;
     return t;
+}
+
+// the fast Chebyshev kernel needs: Sym, <= 8 colours, one bond per thread per colour, every site in the last colour
+static bool kpm_fast_ok(const sq_kpm *k) {
+    const sq_fdm *f = k->f;
+    if (!f->sym || f->C < 1 || f->C > 8 || getenv("SQ_KPM_SLOW")) return false;
+    int nbmax = 0;
+    for (int c = 0; c < f->C; c++) nbmax = std::max(nbmax, f->chi[c] - f->clo[c]);
+    if (nbmax > 1024) return false;
+    int last = (int)f->C - 1;
+    return 2 * (f->chi[last] - f->clo[last]) == f->N;
+}
+static int kpm_fast_threads(const sq_kpm *k) {
+    int nbmax = 1;
+    for (int c = 0; c < k->f->C; c++) nbmax = std::max(nbmax, k->f->chi[c] - k->f->clo[c]);
+    return ((nbmax + 31) / 32) * 32;
 }
 
 static void sturm_extremes(const std::vector<double> &a, const std::vector<double> &b, int n, double *emin, double *emax) {
@@ -377,6 +562,10 @@ void kpm_create_impl(sq_kpm **out, sq_fdm *f, double rbuf, i64 n, double a1, dou
         k->lan_start.alloc(f->N);
         SQ_CUDA(cudaFuncSetAttribute(k_kpm_cheb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
         SQ_CUDA(cudaFuncSetAttribute(k_lanczos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        SQ_CUDA(cudaFuncSetAttribute(k_kpm_cheb_fast<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        SQ_CUDA(cudaFuncSetAttribute(k_kpm_cheb_fast<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        SQ_CUDA(cudaFuncSetAttribute(k_kpm_cheb_fast<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        SQ_CUDA(cudaFuncSetAttribute(k_kpm_cheb_fast<8, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
     } catch (...) {
         delete k;
         throw;
@@ -443,7 +632,30 @@ int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *
     double2 *zt = k->ztmp.p;
     tau_fft_launch(f->stream, k->radices, (int)f->L, (int)f->N, zt, in, false, true, k->tw.p, k->theta.p, k->d_scale1.p, nullptr, nullptr,
                    skip, f->smem_optin);
-    if (k->nsched > 0) {
+    if (k->nsched > 0 && kpm_fast_ok(k)) {
+        BbarFast Q;
+        Q.N = (int)f->N; Q.C = (int)f->C; Q.nunc0 = f->nunc0;
+        for (int c = 0; c < 8; c++) { Q.clo[c] = c < f->C ? f->clo[c] : 0; Q.chi[c] = c < f->C ? f->chi[c] : 0; }
+        Q.nts = f->nts.p; Q.nt = f->nt.p; Q.slot = f->slot.p; Q.unc0 = f->unc0.p; Q.csbar = k->csbar.p; Q.Dbar = k->Dbar.p;
+        static long long *dbg = nullptr;
+        if (!dbg && getenv("SQ_DEBUG_STAMPS")) { SQ_CUDA(cudaMallocManaged((void **)&dbg, 8 * sizeof(long long))); for (int q = 0; q < 8; q++) dbg[q] = 0; }
+        Q.dbg = dbg;
+        if (dbg && getenv("SQ_DEBUG_PRINT")) {
+            cudaStreamSynchronize(f->stream);
+            fprintf(stderr, "cheb stamps: first apply %lld cycles, whole recurrence %lld cycles, order %lld -> %.0f cycles/step\n", dbg[1] - dbg[0],
+                    dbg[2] - dbg[0], dbg[3], (double)(dbg[2] - dbg[0]) / (double)std::max<long long>(1, dbg[3] - 1));
+        }
+        double avg = 0.5 * (k->bounds[1] + k->bounds[0]), mag = 0.5 * (k->bounds[1] - k->bounds[0]);
+        size_t smem = f->N * sizeof(double2);
+        const int T = kpm_fast_threads(k);
+#define SQ_CHEB(CM, MT) k_kpm_cheb_fast<CM, MT><<<k->nsched, T, smem, f->stream>>>(Q, zt, k->d_freq_sched.p, k->d_order.p, k->d_coef_off.p, \
+                                                                                    k->d_coefs.p, (int)f->L, avg, 1.0 / mag, skip)
+        if (f->C <= 4) { if (T <= 512) SQ_CHEB(4, 512); else SQ_CHEB(4, 1024); }
+        else { if (T <= 512) SQ_CHEB(8, 512); else SQ_CHEB(8, 1024); }
+#undef SQ_CHEB
+        SQ_LAUNCH_CHECK();
+        f->launches++;
+    } else if (k->nsched > 0) {
         BbarParams P = bbar_params(k);
         double avg = 0.5 * (k->bounds[1] + k->bounds[0]), mag = 0.5 * (k->bounds[1] - k->bounds[0]);
         k_kpm_cheb<<<k->nsched, kpm_threads(k), 4 * f->N * sizeof(double2), f->stream>>>(P, zt, k->d_freq_sched.p, k->d_order.p,
