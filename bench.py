@@ -281,6 +281,34 @@ def run_native(args):
     barrier()
     e2e_value = world * args.steps / float(t.item())
 
+    # ---- tau-slab strong scaling of the CG solve (N > 1): the same M^T M system partitioned over the ranks with
+    #      NCCL halo exchange + all-reduced dot products, against the single-GPU solve timed on every rank first
+    tau_slab = None
+    if world > 1:
+        n = m.N * m.Ltau
+        d_b = torch.randn(n, 2, dtype=torch.float64, device=dev)
+        d_x = torch.zeros_like(d_b)
+        nit = 400
+
+        def timed_cg():
+            fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=40)
+            barrier()
+            t0 = time.perf_counter()
+            fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=nit)
+            torch.cuda.synchronize()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item()) / nit * 1e6
+        us1 = timed_cg()
+        ids = [api.FermionDetMatrix.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        fdm.init_slab(rank, world, ids[0])
+        usN = timed_cg()
+        tau_slab = {"what": "unpreconditioned CG iterations on M^T M, cfg4, tau-slab partitioned (strong scaling)",
+                    "cg_us_per_iter_1gpu": us1, "cg_us_per_iter": usN, "n_gpus": world,
+                    "cg_iters_per_s": 1e6 / usN, "speedup_vs_1gpu": us1 / usN,
+                    "comm": "NCCL send/recv halos (2 x 16 KB) + 2 scalar all-reduces per iteration, host-launched"}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -356,7 +384,7 @@ def run_native(args):
             "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": nx * 8, "d2h_bytes_per_step": nx * 8 + 64},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "cg_iters_per_trajectory": iters_per_traj, "matvecs_per_trajectory": matvecs_per_traj,
-            "acceptance": accepted / args.steps}
+            "acceptance": accepted / args.steps, "tau_slab": tau_slab}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -77,6 +77,15 @@ int sq_fdm_set_tuning(sq_fdm *f, int slab, int threads);
 int sq_fdm_get_tuning(sq_fdm *f, int *slab, int *threads, int *path);   /* path: 0 generic fused, 1 global passes, 2 fast fused */
 int sq_fdm_set_fast_path(sq_fdm *f, int enable);                       /* fast fused kernel where it applies (Sym, <= 8 colours) */
 int sq_fdm_stream(sq_fdm *f, void **cuda_stream);
+/* tau-slab partitioning over the GPUs of one node (the reference is single-process).  Rank g of `world`
+ * produces the contiguous slices [lo, hi) of every vector; arrays stay full length and sq_fdm_mul_dev / sq_fdm_cg_dev
+ * exchange the one-slice halos with the ring neighbours over NCCL (libnccl is dlopen'ed).  id128 comes from
+ * sq_nccl_unique_id on rank 0 and is broadcast by the host (MPI / torch.distributed).  Only the slices [lo, hi) of
+ * the outputs are defined; unpreconditioned CG only. */
+int sq_nccl_unique_id(char *out128);
+int sq_fdm_init_slab(sq_fdm *f, int rank, int world, const char *id128);
+int sq_fdm_set_slab_range(sq_fdm *f, int64_t lo, int64_t hi);      /* single-process testing of the range logic */
+int sq_fdm_get_slab(sq_fdm *f, int64_t *lo, int64_t *hi, int *rank, int *world);
 int64_t sq_fdm_launch_count(sq_fdm *f);
 
 /* ---- KPMPreconditioner ----------------------------------------------------------------------- */

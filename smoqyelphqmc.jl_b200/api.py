@@ -123,6 +123,25 @@ class FermionDetMatrix:
     def set_tuning(self, slab, threads): check(self.L.sq_fdm_set_tuning(self.h, slab, threads))
     def set_fast_path(self, enable): check(self.L.sq_fdm_set_fast_path(self.h, int(enable)))
 
+    # ---- tau-slab partitioning (multi-GPU) ----
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(_l.load().sq_nccl_unique_id(buf))
+        return buf.raw
+
+    def init_slab(self, rank, world, unique_id=None):
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        check(self.L.sq_fdm_init_slab(self.h, int(rank), int(world), buf))
+
+    def set_slab_range(self, lo, hi): check(self.L.sq_fdm_set_slab_range(self.h, int(lo), int(hi)))
+
+    @property
+    def slab(self):
+        lo, hi, r, w = C.c_int64(0), C.c_int64(0), C.c_int(0), C.c_int(0)
+        check(self.L.sq_fdm_get_slab(self.h, C.byref(lo), C.byref(hi), C.byref(r), C.byref(w)))
+        return {"lo": lo.value, "hi": hi.value, "rank": r.value, "world": w.value}
+
     @property
     def stream(self):
         s = C.c_void_p()

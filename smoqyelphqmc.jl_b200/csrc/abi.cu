@@ -22,6 +22,9 @@ void fdm_update_impl(sq_fdm *f, const double *V, const double *t, double dtau);
 void fdm_get_coefficients_impl(sq_fdm *f, double *expV, double *ch, double *sh);
 void fdm_mul_impl(sq_fdm *f, int op, void *out, const void *in);
 void fdm_select_tuning(sq_fdm *f);
+void slab_unique_id(char *out128);
+void slab_init(sq_fdm *f, int rank, int world, const char *id128);
+void slab_set_range(sq_fdm *f, int lo, int hi);
 
 void kpm_create_impl(sq_kpm **out, sq_fdm *f, double rbuf, i64 n, double a1, double a2);
 void elph_create_impl(sq_elph **out, sq_fdm *f, double dtau, i64 Nph, const double *Om, const double *Om4, const double *M, i64 Nhol,
@@ -91,10 +94,41 @@ int sq_fdm_get_coefficients(sq_fdm *f, double *expV, double *cosh_t, double *sin
     fdm_get_coefficients_impl(f, expV, cosh_t, sinh_t);
     SQ_CATCH
 }
+int sq_nccl_unique_id(char *out128) {
+    SQ_TRY
+    SQ_REQUIRE(out128, "NULL argument");
+    slab_unique_id(out128);
+    SQ_CATCH
+}
+int sq_fdm_init_slab(sq_fdm *f, int rank, int world, const char *id128) {
+    SQ_TRY
+    SQ_REQUIRE(f && (id128 || world == 1), "NULL argument");
+    slab_init(f, rank, world, id128);
+    SQ_CATCH
+}
+int sq_fdm_set_slab_range(sq_fdm *f, int64_t lo, int64_t hi) {
+    SQ_TRY
+    SQ_REQUIRE(f, "NULL handle");
+    slab_set_range(f, (int)lo, (int)hi);
+    SQ_CATCH
+}
+int sq_fdm_get_slab(sq_fdm *f, int64_t *lo, int64_t *hi, int *rank, int *world) {
+    SQ_TRY
+    SQ_REQUIRE(f, "NULL handle");
+    if (lo) *lo = f->slab_lo;
+    if (hi) *hi = f->slab_hi;
+    if (rank) *rank = f->rank;
+    if (world) *world = f->world;
+    SQ_CATCH
+}
 int sq_fdm_mul_dev(sq_fdm *f, int op, void *d_out, const void *d_in) {
     SQ_TRY
     SQ_REQUIRE(f && d_out && d_in, "NULL argument");
     SQ_CUDA(cudaSetDevice(f->device));
+    if (f->world > 1) {
+        SQ_REQUIRE(op != SQ_OP_MMT, "M M^T is not available in tau-slab mode");
+        fdm_halo_exchange(f, (double2 *)d_in);       // the neighbours' boundary slices are written into d_in at their global index
+    }
     fdm_mul_dev(f, op, (double2 *)d_out, (const double2 *)d_in);
     SQ_CATCH
 }

@@ -126,8 +126,8 @@ k_fdm_fused(const __grid_constant__ KParams P, double2 *__restrict__ out, const 
     if (skip && skip->done) return;
     const TIdx t = tidx(P);
     const int L = P.L, N = P.N;
-    const int l0 = blockIdx.x * P.S;
-    const int ns = min(P.S, L - l0);
+    const int l0 = P.lb + blockIdx.x * P.S;
+    const int ns = min(P.S, P.le - l0);
     const int T = blockDim.x;
 
     if (MODE == 2) {
@@ -358,6 +358,7 @@ int fdm_v2_tx(const sq_fdm *f);
 KParams sq_fdm::kparams(int S, int T) const {
     KParams P;
     P.L = (int)L; P.N = (int)N; P.Nh = (int)Nh; P.C = (int)C; P.sym = sym; P.S = S;
+    P.lb = slab_lo; P.le = slab_hi;
     int nbmax = 1;
     for (int c = 0; c < C; c++) { P.clo[c] = clo[c]; P.chi[c] = chi[c]; nbmax = std::max(nbmax, chi[c] - clo[c]); }
     for (int c = (int)C; c < SQ_MAXC; c++) { P.clo[c] = 0; P.chi[c] = 0; }
@@ -384,7 +385,7 @@ static void launch_fused(sq_fdm *f, int S, int T, double2 *out, const double2 *i
     if (T & (T - 1)) T = 1 << (31 - __builtin_clz(T));       // the generic kernel needs a power-of-two block
     KParams P = f->kparams(S, T);
     size_t smem = fused_smem_bytes(f, MODE, S);
-    int grid = (int)((f->L + S - 1) / S);
+    int grid = (f->slab_hi - f->slab_lo + S - 1) / S;
     k_fdm_fused<MODE><<<grid, T, smem, f->stream>>>(P, out, in, part, skip);
     SQ_LAUNCH_CHECK();
     f->launches++;
@@ -454,7 +455,7 @@ void fdm_mul_dev(sq_fdm *f, int op, double2 *out, const double2 *in, double *pAp
         int S = f->slab, T = f->threads;
         if (op == 2) {
             launch_fused<2>(f, S, T, out, src, pAp_partials, skip);
-            if (npart) *npart = (int)((f->L + S - 1) / S);
+            if (npart) *npart = (f->slab_hi - f->slab_lo + S - 1) / S;
         } else if (op == 0) launch_fused<0>(f, S, T, out, src, nullptr, skip);
         else if (op == 1) launch_fused<1>(f, S, T, out, src, nullptr, skip);
         else {
@@ -579,6 +580,7 @@ void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt,
     try {
         f->device = device; f->sym = sym ? 1 : 0; f->L = L; f->N = N; f->Nh = Nh; f->C = C;
         f->tol = tol; f->maxiter = maxiter;
+        f->slab_lo = 0; f->slab_hi = (int)L;
         cudaDeviceProp prop;
         SQ_CUDA(cudaGetDeviceProperties(&prop, device));
         f->num_sms = prop.multiProcessorCount;
@@ -677,9 +679,11 @@ void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt,
     *out = f;
 }
 
+void slab_destroy(sq_fdm *f);
 void fdm_destroy_impl(sq_fdm *f) {
     if (!f) return;
     cudaSetDevice(f->device);
+    slab_destroy(f);
     if (f->stream) { cudaStreamSynchronize(f->stream); cudaStreamDestroy(f->stream); }
     if (f->h_cg) cudaFreeHost(f->h_cg);
     delete f;

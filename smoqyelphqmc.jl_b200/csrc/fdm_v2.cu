@@ -19,6 +19,7 @@
 
 struct K2Params {
     int L, N, Nh, C, S, TX;
+    int lb, le;             // slices [lb, le) produced by this launch
     int clo[SQ_MAXC], chi[SQ_MAXC];
     int nunc0;
     const int2 *nts;        // bond -> (slot_i, slot_j)
@@ -317,8 +318,8 @@ k_fdm_fused_v2(const __grid_constant__ K2Params P, double2 *__restrict__ out, co
     E.init(P);
     SQ_STAMP(1);
     const int L = P.L, N = P.N, T = blockDim.x;
-    const int l0 = blockIdx.x * P.S;
-    const int ns = min(P.S, L - l0);
+    const int l0 = P.lb + blockIdx.x * P.S;
+    const int ns = min(P.S, P.le - l0);
     // A: input slices; W: work slices.  MODE 2: A[k] = v[l0-1+k] (k <= ns+1), W[k] = A[k] (k <= ns).
     // MODE 0: A[k] = v[l0-1+k] (k <= ns), W[k] = A[k] (k < ns).  MODE 1: A[k] = v[l0+k] (k <= ns), W[k] = A[k+1] (k < ns).
     const int nA = (MODE == 2) ? ns + 2 : ns + 1;
@@ -494,6 +495,7 @@ void fdm_v2_launch(sq_fdm *f, int mode, int S, int T, double2 *out, const double
         P.cg_beta_complex = g_fuse->beta_complex; P.cg_iter = g_fuse->iter; P.cg_check = g_fuse->check;
     }
     P.L = (int)f->L; P.N = (int)f->N; P.Nh = (int)f->Nh; P.C = (int)f->C; P.S = S; P.TX = fdm_v2_tx(f);
+    P.lb = f->slab_lo; P.le = f->slab_hi;
     for (int c = 0; c < SQ_MAXC; c++) { P.clo[c] = c < f->C ? f->clo[c] : 0; P.chi[c] = c < f->C ? f->chi[c] : 0; }
     P.nunc0 = f->nunc0;
     static long long *dbg = nullptr;
@@ -514,7 +516,7 @@ void fdm_v2_launch(sq_fdm *f, int mode, int S, int T, double2 *out, const double
     KMAX = KMAX <= 1 ? 1 : (KMAX <= 2 ? 2 : 4);
     size_t slices = (mode == 2) ? (size_t)(2 * S + 3) : (size_t)(2 * S + 1);
     size_t smem = slices * f->N * sizeof(double2);
-    int grid = (int)((f->L + S - 1) / S);
+    int grid = (f->slab_hi - f->slab_lo + S - 1) / S;
     v2_kernel_t k = pick(mode, (int)f->C, KMAX, f->cs_uniform);
     k<<<grid, T, smem, f->stream>>>(P, out, in, part, skip);
     SQ_LAUNCH_CHECK();
@@ -531,5 +533,5 @@ int fdm_v2_launch_cg(sq_fdm *f, double2 *z, const double2 *p_old, double2 *p_new
         fdm_v2_launch(f, 2, f->slab, f->threads, z, p_old, pAp_part, cur);
     } catch (...) { g_fuse = nullptr; throw; }
     g_fuse = nullptr;
-    return (int)((f->L + f->slab - 1) / f->slab);
+    return (f->slab_hi - f->slab_lo + f->slab - 1) / f->slab;
 }

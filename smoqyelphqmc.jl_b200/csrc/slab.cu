@@ -1,0 +1,256 @@
+// slab.cu -- tau-slab partitioning of the space-time vector over the GPUs of one node.
+//
+// Rank g owns the contiguous slices [slab_lo, slab_hi).  M couples slice l to l-1 and M^T to l+1, so the fused
+// M^T M kernel of a slab needs exactly one boundary slice from each ring neighbour; the wrap-around link carries the
+// antiperiodic + sign, which the kernels already derive from the GLOBAL slice index.  Every rank keeps full-length
+// arrays (6.5 MB per vector at the named size -- memory is not the constraint) and only produces its own slices, so a
+// halo is simply the neighbour's boundary slice written at its global position:
+//     send v[slab_lo]   -> previous rank (it is their v[hi]),      send v[slab_hi-1] -> next rank (their v[lo-1]).
+// Per CG iteration: one halo exchange of p (2 x 16 N bytes each way) and two all-reduces of one double.
+// The plumbing is NCCL (ncclSend/ncclRecv grouped, ncclAllReduce) on the library stream; libnccl is resolved at run
+// time with dlopen so that the library has no link-time dependency and shares the NCCL already loaded by the host
+// process (torch's), if any.  The reference has no counterpart: it is single-process (its MPI mode = independent
+// chains, which needs no code here).
+#include "sq_internal.h"
+
+#include <dlfcn.h>
+
+#include <cstring>
+
+// minimal NCCL surface (types as in nccl.h)
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclSum = 0 };
+enum { ncclChar = 0, ncclDouble = 8 };
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static void nccl_load() {
+    if (g_nccl.lib) return;
+    const char *names[] = {getenv("SQ_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        if (!n) continue;
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) throw SqError("tau-slab mode needs NCCL: could not dlopen libnccl.so.2 (set SQ_NCCL_LIB)");
+#define SQ_SYM(field, name)                                                   \
+    *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, name);                      \
+    if (!g_nccl.field) throw SqError(std::string("libnccl lacks symbol ") + name)
+    SQ_SYM(GetUniqueId, "ncclGetUniqueId");
+    SQ_SYM(CommInitRank, "ncclCommInitRank");
+    SQ_SYM(CommDestroy, "ncclCommDestroy");
+    SQ_SYM(Send, "ncclSend");
+    SQ_SYM(Recv, "ncclRecv");
+    SQ_SYM(AllReduce, "ncclAllReduce");
+    SQ_SYM(GroupStart, "ncclGroupStart");
+    SQ_SYM(GroupEnd, "ncclGroupEnd");
+    SQ_SYM(GetErrorString, "ncclGetErrorString");
+#undef SQ_SYM
+}
+#define SQ_NCCL(expr)                                                                                              \
+    do {                                                                                                           \
+        ncclResult_t _r = (expr);                                                                                  \
+        if (_r != 0) throw SqError(std::string("NCCL error '") + g_nccl.GetErrorString(_r) + "' in " #expr);       \
+    } while (0)
+
+void slab_unique_id(char *out128) {
+    nccl_load();
+    ncclUniqueId id;
+    SQ_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out128, id.internal, 128);
+}
+
+// balanced contiguous partition: the first L % world ranks get one extra slice
+static void slab_range(int L, int world, int rank, int *lo, int *hi) {
+    int base = L / world, extra = L % world;
+    *lo = rank * base + std::min(rank, extra);
+    *hi = *lo + base + (rank < extra ? 1 : 0);
+}
+
+void slab_set_range(sq_fdm *f, int lo, int hi) {
+    SQ_REQUIRE(lo >= 0 && hi > lo && hi <= f->L, "slab range out of bounds");
+    f->slab_lo = lo;
+    f->slab_hi = hi;
+    f->tuned[0][0] = f->tuned[1][0] = 0;         // the best (slab, threads) depends on the number of local slices
+    f->manual_tuning = 0;
+}
+
+void slab_init(sq_fdm *f, int rank, int world, const char *id128) {
+    SQ_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank / world size");
+    SQ_REQUIRE(world <= f->L, "more ranks than time slices");
+    SQ_CUDA(cudaSetDevice(f->device));
+    f->rank = rank;
+    f->world = world;
+    int lo, hi;
+    slab_range((int)f->L, world, rank, &lo, &hi);
+    slab_set_range(f, lo, hi);
+    if (!f->scal.p) f->scal.alloc(16);
+    if (world > 1) {
+        nccl_load();
+        ncclUniqueId id;
+        memcpy(id.internal, id128, 128);
+        ncclComm_t c;
+        SQ_NCCL(g_nccl.CommInitRank(&c, world, id, rank));
+        f->comm = (void *)c;
+    }
+}
+
+void slab_destroy(sq_fdm *f) {
+    if (f->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)f->comm);
+    f->comm = nullptr;
+}
+
+// exchange the boundary slices of v with the ring neighbours (in place, at their global index)
+void fdm_halo_exchange(sq_fdm *f, double2 *v) {
+    if (f->world <= 1) return;
+    const int L = (int)f->L;
+    const size_t nb = (size_t)f->N * sizeof(double2);
+    const int prev = (f->rank + f->world - 1) % f->world, next = (f->rank + 1) % f->world;
+    const int lo = f->slab_lo, hi = f->slab_hi;
+    const size_t N = (size_t)f->N;
+    ncclComm_t c = (ncclComm_t)f->comm;
+    SQ_NCCL(g_nccl.GroupStart());
+    SQ_NCCL(g_nccl.Send(v + (size_t)lo * N, nb, ncclChar, prev, c, f->stream));                    // their v[hi]
+    SQ_NCCL(g_nccl.Send(v + (size_t)(hi - 1) * N, nb, ncclChar, next, c, f->stream));              // their v[lo-1]
+    SQ_NCCL(g_nccl.Recv(v + (size_t)(hi % L) * N, nb, ncclChar, next, c, f->stream));              // next's first slice
+    SQ_NCCL(g_nccl.Recv(v + (size_t)((lo - 1 + L) % L) * N, nb, ncclChar, prev, c, f->stream));    // prev's last slice
+    SQ_NCCL(g_nccl.GroupEnd());
+}
+
+void fdm_allreduce_sum(sq_fdm *f, double *d_buf, int count) {
+    if (f->world <= 1) return;
+    SQ_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)count, ncclDouble, ncclSum, (ncclComm_t)f->comm, f->stream));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CG on a tau-slab: the reference recurrence (ConjugateGradient.jl:93-167) with local vector updates, one halo
+// exchange and two scalar all-reduces per iteration.  scal[]: 0 |b|^2, 1 rr_old, 2 pAp, 3 rr_new, 4 done flag.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_pack_sum(const double *__restrict__ part, int n, double *__restrict__ dst) {
+    double s = warp_sum_partials(part, n);
+    if (threadIdx.x == 0) *dst = s;
+}
+__global__ void k_norm2_part(const double2 *__restrict__ a, size_t n, double *__restrict__ part) {
+    __shared__ double red[32];
+    double acc = 0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        double2 v = a[k];
+        acc += v.x * v.x + v.y * v.y;
+    }
+    double v[1] = {acc};
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = v[0];
+}
+__global__ void k_sub(double2 *__restrict__ r, const double2 *__restrict__ b, size_t n) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+        r[k] = make_double2(b[k].x - r[k].x, b[k].y - r[k].y);
+}
+// x += alpha p ; r -= alpha z ; partial |r|^2 ; alpha = rr_old / pAp (both already all-reduced)
+__global__ void k_slab_update_xr(const double *__restrict__ scal, double2 *__restrict__ x, double2 *__restrict__ r,
+                                 const double2 *__restrict__ p, const double2 *__restrict__ z, size_t n, double *__restrict__ part) {
+    __shared__ double red[32];
+    if (scal[4] != 0.0) return;
+    double alpha = scal[1] / scal[2];
+    double acc = 0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        double2 pk = p[k], zk = z[k], xk = x[k], rk = r[k];
+        xk = make_double2(fma(alpha, pk.x, xk.x), fma(alpha, pk.y, xk.y));
+        rk = make_double2(fma(-alpha, zk.x, rk.x), fma(-alpha, zk.y, rk.y));
+        x[k] = xk;
+        r[k] = rk;
+        acc += rk.x * rk.x + rk.y * rk.y;
+    }
+    double v[1] = {acc};
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = v[0];
+}
+// eps test, beta = rr_new / rr_old, p = r + beta p ; block 0 rolls the scalars afterwards (separate tiny kernel)
+__global__ void k_slab_update_p(const double *__restrict__ scal, double2 *__restrict__ p, const double2 *__restrict__ r, size_t n, double tol) {
+    if (scal[4] != 0.0) return;
+    double eps = sqrt(scal[3] / scal[0]);
+    if (eps < tol || !(eps == eps)) return;
+    double beta = scal[3] / scal[1];
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        double2 pk = p[k], rk = r[k];
+        p[k] = make_double2(fma(beta, pk.x, rk.x), fma(beta, pk.y, rk.y));
+    }
+}
+__global__ void k_slab_roll(double *scal, double tol, int iter) {
+    if (scal[4] != 0.0) return;
+    double eps = sqrt(scal[3] / scal[0]);
+    scal[5] = eps;
+    scal[6] = (double)iter;
+    if (eps < tol) scal[4] = 1.0;
+    else if (!(eps == eps)) scal[4] = 2.0;
+    else scal[1] = scal[3];
+}
+
+void fdm_cg_slab(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, double tol, i64 maxiter, i64 *iters, double *eps) {
+    const size_t N = (size_t)f->N;
+    const size_t off = (size_t)f->slab_lo * N, n = (size_t)(f->slab_hi - f->slab_lo) * N;
+    const int TB = 256;
+    const int G = (int)std::max<size_t>(1, std::min<size_t>((n + TB - 1) / TB, (size_t)f->num_sms * 4));
+    cudaStream_t s = f->stream;
+    double *part = f->part.p, *scal = f->scal.p;
+    double2 *r = f->r.p, *p = f->p.p, *z = f->z.p;
+    SQ_CUDA(cudaMemsetAsync(scal, 0, 16 * sizeof(double), s));
+    k_norm2_part<<<G, TB, 0, s>>>(b + off, n, part);
+    k_pack_sum<<<1, 32, 0, s>>>(part, G, scal + 0);
+    if (zero_start) {
+        SQ_CUDA(cudaMemcpyAsync(r + off, b + off, n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+        SQ_CUDA(cudaMemsetAsync(x + off, 0, n * sizeof(double2), s));
+    } else {
+        fdm_halo_exchange(f, x);
+        fdm_mul_dev(f, SQ_OP_MTM, r, x);
+        k_sub<<<G, TB, 0, s>>>(r + off, b + off, n);
+    }
+    SQ_CUDA(cudaMemcpyAsync(p + off, r + off, n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+    k_norm2_part<<<G, TB, 0, s>>>(r + off, n, part);
+    k_pack_sum<<<1, 32, 0, s>>>(part, G, scal + 1);
+    fdm_allreduce_sum(f, scal, 2);
+    SQ_CUDA(cudaMemcpyAsync(scal + 3, scal + 1, sizeof(double), cudaMemcpyDeviceToDevice, s));
+    k_slab_roll<<<1, 1, 0, s>>>(scal, tol, 0);                                   // initial eps test (iter 0)
+    f->launches += 5;
+    i64 it = 0;
+    const int batch = 16;
+    double h[8];
+    bool finished = false;
+    while (!finished) {
+        i64 upto = std::min<i64>(maxiter, it + batch);
+        for (; it < upto;) {
+            it++;
+            fdm_halo_exchange(f, p);
+            int npart = 0;
+            fdm_mul_dev(f, SQ_OP_MTM, z, p, part, &npart, nullptr);               // z = M^T M p on the slab, |Mp|^2 partials
+            k_pack_sum<<<1, 32, 0, s>>>(part, npart, scal + 2);
+            fdm_allreduce_sum(f, scal + 2, 1);
+            k_slab_update_xr<<<G, TB, 0, s>>>(scal, x + off, r + off, p + off, z + off, n, part);
+            k_pack_sum<<<1, 32, 0, s>>>(part, G, scal + 3);
+            fdm_allreduce_sum(f, scal + 3, 1);
+            k_slab_update_p<<<G, TB, 0, s>>>(scal, p + off, r + off, n, tol);
+            k_slab_roll<<<1, 1, 0, s>>>(scal, tol, (int)it);
+            f->launches += 5;
+        }
+        SQ_LAUNCH_CHECK();
+        SQ_CUDA(cudaMemcpyAsync(h, scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        SQ_CUDA(cudaStreamSynchronize(s));
+        if (h[4] != 0.0 || it >= maxiter) finished = true;
+    }
+    if (h[4] == 2.0) throw SqError("conjugate gradient (tau-slab): NaN encountered in the residual");
+    *iters = h[4] != 0.0 ? (i64)h[6] : maxiter;
+    *eps = h[5];
+}

@@ -12,6 +12,7 @@
 struct KParams {            // by-value kernel parameter block of the operator kernels
     int L, N, Nh, C, sym;
     int S;                  // slices owned by one CTA (fused kernels)
+    int lb, le;             // slices [lb, le) this launch produces (whole axis, or this rank's tau-slab)
     int TX, TXshift;        // threads along the bond / site index (power of two)
     int clo[SQ_MAXC], chi[SQ_MAXC];
     int nunc0;              // sites not touched by colour 0 (fused middle step)
@@ -67,6 +68,12 @@ struct sq_fdm {
     size_t smem_optin = 0;
     i64 launches = 0;
     i64 coef_version = 0;                    // bumped by every operator refresh (KPM B-bar cache)
+    // tau-slab partitioning (multi-GPU): this rank produces slices [slab_lo, slab_hi); arrays stay full length and the
+    // one-slice halos are exchanged in place at their global index (slab.cu)
+    int slab_lo = 0, slab_hi = 0;
+    int rank = 0, world = 1;
+    void *comm = nullptr;                    // ncclComm_t
+    DevBuf<double> scal;                     // packed scalars for all-reduces
 
     KParams kparams(int S, int T) const;
     size_t vec_bytes() const { return (size_t)L * N * sizeof(double2); }
@@ -184,5 +191,9 @@ int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, 
                    double *dot_part, const CgState *skip, size_t smem_limit);
 void rng_fill_normal(double *d_out, size_t n, uint64_t seed, uint64_t stream, cudaStream_t s);
 void rng_fill_uniform(double *d_out, size_t n, uint64_t seed, uint64_t stream, cudaStream_t s);
+void fdm_select_tuning(sq_fdm *f);
+void fdm_halo_exchange(sq_fdm *f, double2 *v);
+void fdm_allreduce_sum(sq_fdm *f, double *d_buf, int count);
+void fdm_cg_slab(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, double tol, i64 maxiter, i64 *iters, double *eps);
 void fft_radices(i64 n, std::vector<int> &rad);
 void fft_make_twiddles(i64 n, std::vector<double2> &tw);
