@@ -281,6 +281,68 @@ def run_native(args):
     barrier()
     e2e_value = world * args.steps / float(t.item())
 
+    roofline = None
+    iters_per_traj = iters_total / args.steps
+    matvecs_per_traj = iters_per_traj + 2 * (NT + 1)
+    if rank == 0:
+        # ---- roofline of the dominant kernel (k_fdm_fused<2>), rank 0: CUDA events around single launches
+        n = m.N * m.Ltau
+        d_in = torch.randn(n, 2, dtype=torch.float64, device=dev)
+        d_out = torch.zeros_like(d_in)
+        flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)          # 256 MB > 126 MB L2
+        B = algorithmic_bytes(m)
+
+        def time_matvec(cold, reps=40):
+            ts = []
+            with torch.cuda.stream(stream):
+                for _ in range(5):
+                    fdm.mul_dev(api.OP_MTM, d_out.data_ptr(), d_in.data_ptr())
+                if cold:
+                    for _ in range(reps):
+                        flush.add_(1.0)                      # the launch below queues behind the flush: no host latency inside the events
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record(stream)
+                        fdm.mul_dev(api.OP_MTM, d_out.data_ptr(), d_in.data_ptr())
+                        b.record(stream)
+                        b.synchronize()
+                        ts.append(a.elapsed_time(b) * 1e-3)
+                else:
+                    for _ in range(5):                       # back-to-back launches, as inside a CG solve
+                        flush[:1024].add_(1.0)
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record(stream)
+                        for _ in range(reps):
+                            fdm.mul_dev(api.OP_MTM, d_out.data_ptr(), d_in.data_ptr())
+                        b.record(stream)
+                        b.synchronize()
+                        ts.append(a.elapsed_time(b) * 1e-3 / reps)
+            return float(np.mean(ts))
+
+        t_cold, t_hot = time_matvec(True), time_matvec(False)
+        peak, peak_src = measured_peak()
+        traffic = None
+        try:
+            traffic = json.load(open(ITERS_FILE)).get("mtm_dram_bytes_per_launch")
+        except Exception:
+            pass
+        # Models without SSH coupling have tau-independent hoppings: the fast kernel then reads (cosh, sinh) once per
+        # kernel instead of once per slice, so the bytes it must move are 40 N Ltau + 16 Nh, not the generic figure.
+        uniform = (m.Nssh == 0) and fdm.tuning["path"] == 2
+        Bk = (40 * m.N * m.Ltau + 16 * m.Nh) if uniform else B
+        roofline = {"bound": "hbm", "kernel": "k_fdm_fused_v2<2> (fused M^T M v)" if fdm.tuning["path"] == 2 else "k_fdm_fused<2> (fused M^T M v)",
+                    "achieved": Bk / t_cold / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": Bk / t_cold / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": Bk, "generic_formula_bytes_per_launch": B,
+                    "bytes_note": "tau-uniform hoppings: (cosh, sinh) read once per kernel" if uniform else "generic (40 N + 16 Nh) Ltau",
+                    "achieved_generic_formula": B / t_cold / 1e9, "frac_generic_formula": B / t_cold / 1e9 / peak,
+                    "us_per_launch_cold_l2": t_cold * 1e6, "us_per_launch_hot_l2": t_hot * 1e6,
+                    "achieved_hot_l2": Bk / t_hot / 1e9, "frac_hot_l2": Bk / t_hot / 1e9 / peak,
+                    "limiter": "shared-memory crossbar + barrier latency (DESIGN.md section 4), not HBM",
+                    "matvecs_per_s_hot_l2": 1.0 / t_hot,
+                    "share_of_step": iters_per_traj * t_hot / (ms_dev * 1e-3 / args.steps),
+                    "tuning": fdm.tuning}
+
+    barrier()
     # ---- tau-slab strong scaling of the CG solve (N > 1): the same M^T M system partitioned over the ranks with
     #      NCCL halo exchange + all-reduced dot products, against the single-GPU solve timed on every rank first
     tau_slab = None
@@ -313,65 +375,6 @@ def run_native(args):
         if dist is not None:
             dist.destroy_process_group()
         return
-
-    # ---- roofline of the dominant kernel (k_fdm_fused<2>), rank 0: CUDA events around single launches
-    n = m.N * m.Ltau
-    d_in = torch.randn(n, 2, dtype=torch.float64, device=dev)
-    d_out = torch.zeros_like(d_in)
-    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)          # 256 MB > 126 MB L2
-    B = algorithmic_bytes(m)
-
-    def time_matvec(cold, reps=40):
-        ts = []
-        with torch.cuda.stream(stream):
-            for _ in range(5):
-                fdm.mul_dev(api.OP_MTM, d_out.data_ptr(), d_in.data_ptr())
-            if cold:
-                for _ in range(reps):
-                    flush.add_(1.0)                      # the launch below queues behind the flush: no host latency inside the events
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record(stream)
-                    fdm.mul_dev(api.OP_MTM, d_out.data_ptr(), d_in.data_ptr())
-                    b.record(stream)
-                    b.synchronize()
-                    ts.append(a.elapsed_time(b) * 1e-3)
-            else:
-                for _ in range(5):                       # back-to-back launches, as inside a CG solve
-                    flush[:1024].add_(1.0)
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record(stream)
-                    for _ in range(reps):
-                        fdm.mul_dev(api.OP_MTM, d_out.data_ptr(), d_in.data_ptr())
-                    b.record(stream)
-                    b.synchronize()
-                    ts.append(a.elapsed_time(b) * 1e-3 / reps)
-        return float(np.mean(ts))
-
-    t_cold, t_hot = time_matvec(True), time_matvec(False)
-    peak, peak_src = measured_peak()
-    traffic = None
-    try:
-        traffic = json.load(open(ITERS_FILE)).get("mtm_dram_bytes_per_launch")
-    except Exception:
-        pass
-    iters_per_traj = iters_total / args.steps
-    matvecs_per_traj = iters_per_traj + 2 * (NT + 1)
-    # Models without SSH coupling have tau-independent hoppings: the fast kernel then reads (cosh, sinh) once per
-    # kernel instead of once per slice, so the bytes it must move are 40 N Ltau + 16 Nh, not the generic figure.
-    uniform = (m.Nssh == 0) and fdm.tuning["path"] == 2
-    Bk = (40 * m.N * m.Ltau + 16 * m.Nh) if uniform else B
-    roofline = {"bound": "hbm", "kernel": "k_fdm_fused_v2<2> (fused M^T M v)" if fdm.tuning["path"] == 2 else "k_fdm_fused<2> (fused M^T M v)",
-                "achieved": Bk / t_cold / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": Bk / t_cold / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": Bk, "generic_formula_bytes_per_launch": B,
-                "bytes_note": "tau-uniform hoppings: (cosh, sinh) read once per kernel" if uniform else "generic (40 N + 16 Nh) Ltau",
-                "achieved_generic_formula": B / t_cold / 1e9, "frac_generic_formula": B / t_cold / 1e9 / peak,
-                "us_per_launch_cold_l2": t_cold * 1e6, "us_per_launch_hot_l2": t_hot * 1e6,
-                "achieved_hot_l2": Bk / t_hot / 1e9, "frac_hot_l2": Bk / t_hot / 1e9 / peak,
-                "limiter": "shared-memory crossbar + barrier latency (DESIGN.md section 4), not HBM",
-                "matvecs_per_s_hot_l2": 1.0 / t_hot,
-                "share_of_step": iters_per_traj * t_hot / (ms_dev * 1e-3 / args.steps),
-                "tuning": fdm.tuning}
 
     cpu = None
     if world == 1 and not args.no_cpu:

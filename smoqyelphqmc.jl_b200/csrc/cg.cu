@@ -165,6 +165,8 @@ __global__ void k_cg_update_p_prec(CgState *__restrict__ st, const CgState *__re
 
 bool fdm_v2_supported(const sq_fdm *f, int mode, int S, int T);
 void fdm_select_tuning(sq_fdm *f);
+bool fdm_v2_cg_persistent(sq_fdm *f, double2 *x, double2 *r, double2 *p0, double2 *p1, CgState *state, double *part_a, double *part_b,
+                          i64 maxiter);
 int fdm_v2_launch_cg(sq_fdm *f, double2 *z, const double2 *p_old, double2 *p_new, const double2 *d, const CgState *cur, CgState *nxt,
                      const double *rr_part, int nrr, const double *beta_part, int nbeta, int beta_complex, int iter, int check,
                      double *pAp_part);
@@ -238,6 +240,23 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
     bool finished = false;
     fdm_select_tuning(f);
     const bool fused = !prec && f->path == 0 && f->use_v2 && fdm_v2_supported(f, 2, f->slab, f->threads) && !getenv("SQ_NO_CG_FUSION");
+    if (fused && !getenv("SQ_NO_PERSISTENT_CG") && maxiter > 0) {
+        // One cooperative launch for the whole solve (fdm_v2.cu: k_cg_persistent).  The state prepared by k_cg_init holds
+        // |r0|^2, |b| and tol; an already converged system (eps0 < tol) is caught first.
+        SQ_CUDA(cudaMemcpyAsync(f->h_cg, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+        SQ_CUDA(cudaStreamSynchronize(s));
+        if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+        if (f->h_cg->done) { *iters = 0; *eps = f->h_cg->eps; return; }
+        if (fdm_v2_cg_persistent(f, x, r, p, f->tmp1.p, st, part_pAp, part_rr, maxiter)) {
+            SQ_CUDA(cudaMemcpyAsync(f->h_cg, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+            SQ_CUDA(cudaStreamSynchronize(s));
+            if (f->h_cg->done == 3) throw SqError("conjugate gradient: grid barrier timed out in the persistent kernel");
+            if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+            *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
+            *eps = f->h_cg->eps;
+            return;
+        }
+    }
     if (fused) {
         // Two kernels per iteration: K_A' forms p = r + beta p on load (ping-ponged p buffers), tests the convergence of
         // the previous iteration and applies M^T M; K_B updates x and r.  tmp1 is the second p buffer.

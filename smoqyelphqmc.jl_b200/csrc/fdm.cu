@@ -705,7 +705,7 @@ void fdm_update_impl(sq_fdm *f, const double *V, const double *t, double dtau) {
     f->iod2.upload(t, (size_t)f->L * f->Nh, f->stream);
     fdm_update_dev(f, f->iod1.p, f->iod2.p, dtau);
     // tau-independent hoppings enable the register-resident coefficient path of the fast kernel
-    if (!f->flag.p) f->flag.alloc(1);
+    if (!f->flag.p) f->flag.alloc(4);
     SQ_CUDA(cudaMemsetAsync(f->flag.p, 0, sizeof(int), f->stream));
     size_t nT = (size_t)f->L * f->Nh;
     if (nT) k_cs_nonuniform<<<(unsigned)((nT + 255) / 256), 256, 0, f->stream>>>(f->cs.p, (int)f->L, (int)f->Nh, f->flag.p);

@@ -15,6 +15,7 @@
 // results; tests/test_gpu_fdm.py checks one against the other and both against the oracle.
 #include "sq_internal.h"
 
+#include <cstring>
 #include <type_traits>
 
 struct K2Params {
@@ -534,4 +535,223 @@ int fdm_v2_launch_cg(sq_fdm *f, double2 *z, const double2 *p_old, double2 *p_new
     } catch (...) { g_fuse = nullptr; throw; }
     g_fuse = nullptr;
     return (f->slab_hi - f->slab_lo + f->slab - 1) / f->slab;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent cooperative CG: the whole unpreconditioned solve in ONE launch.
+//
+// The named problem is latency bound (hard part 1): one fused M^T M v is ~14 us of work per CTA while
+// every extra launch, host hand-off and separate BLAS-1 pass costs several us.  Here every CTA keeps its tau-slab for
+// the whole solve and iterates
+//     load p = r + beta p_old (own + halo slices, p written to the other ping-pong buffer)  ->  w = M p, |w|^2 partial
+//     -> z = M^T w kept in shared memory  -> [grid barrier] -> alpha -> x += alpha p, r -= alpha z (own slices), |r|^2
+//     partial -> [grid barrier] -> eps test, beta
+// with two grid-wide barriers per iteration (an atomic counter in L2) instead of kernel boundaries: no launches, no z
+// round trip through memory, reductions still fixed-order (bit reproducible).  Launched with
+// cudaLaunchCooperativeKernel so that all CTAs are co-resident; vectors other CTAs write are read with ld.global.cg.
+// A watchdog turns a barrier that does not complete within ~2 s into an error instead of a hang.
+// ---------------------------------------------------------------------------------------------------
+struct CgPersist {
+    double2 *x, *r, *p0, *p1;
+    CgState *state;             // in: rz (= |r0|^2), normb, tol ; out: iters, eps, done
+    double *part_a, *part_b;    // per-CTA partials (pAp, rr)
+    unsigned int *barrier;      // monotonically increasing arrival counter (zeroed by the host)
+    int *abort_flag;
+    int maxiter;
+};
+
+__device__ __forceinline__ bool grid_barrier(unsigned int *counter, unsigned int &epoch, int *abort_flag) {
+    __syncthreads();
+    epoch++;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned int target = epoch * gridDim.x;
+        long long t0 = clock64();
+        while (true) {
+            unsigned int v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v >= target) break;
+            if (clock64() - t0 > 4000000000LL) { atomicExch(abort_flag, 1); break; }
+            __nanosleep(20);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    return *((volatile int *)abort_flag) == 0;
+}
+
+template <int CMAX, int KMAX, int UNI>
+__global__ void __launch_bounds__(1024, 1)
+k_cg_persistent(const __grid_constant__ K2Params P, const CgPersist C) {
+    extern __shared__ double2 smem[];
+    __shared__ double red[32];
+    __shared__ double sh[2];
+    typename std::conditional<UNI != 0, EngineU<CMAX, KMAX>, Engine<CMAX, KMAX>>::type E;
+    E.init(P);
+    const int L = P.L, N = P.N, T = blockDim.x;
+    const int l0 = P.lb + blockIdx.x * P.S;
+    const int ns = min(P.S, P.le - l0);
+    double2 *A = smem, *W = smem + (P.S + 2) * N;
+    const double normb = C.state->normb, tol = C.state->tol;
+    double rz = C.state->rz_re;                       // |r_j|^2 (real for P = I)
+    double beta = 0.0, eps = C.state->eps;
+    unsigned int epoch = 0;
+    int it = 0, done = 0, pc = 0;
+    while (it < C.maxiter) {
+        it++;
+        const double2 *p_old = pc ? C.p1 : C.p0;
+        double2 *p_new = pc ? C.p0 : C.p1;
+        // ---- load p = r + beta p_old for own + halo slices
+        for (int i = threadIdx.x; i < N; i += T) {
+            const int s = __ldg(P.slot + i);
+            for (int k = 0; k <= ns + 1; k++) {
+                int l = l0 - 1 + k;
+                l = l < 0 ? l + L : (l >= L ? l - L : l);
+                double2 rv = __ldcg(C.r + l * N + i), pv = __ldcg(p_old + l * N + i);
+                double2 v = make_double2(fma(beta, pv.x, rv.x), fma(beta, pv.y, rv.y));
+                if (k >= 1 && k <= ns) p_new[l * N + i] = v;
+                A[k * N + s] = v;
+                if (k <= ns) W[k * N + s] = v;
+            }
+        }
+        __syncthreads();
+        E.apply_B(W, ns + 1, l0 >= L ? l0 - L : l0, P);
+        if (UNI) __syncthreads();
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < N; i += T) {
+            for (int k = 0; k <= ns; k++) {
+                int l = l0 + k;
+                l = l >= L ? l - L : l;
+                double sg = (l == 0) ? 1.0 : -1.0;
+                double2 a = A[(k + 1) * N + i], b = W[k * N + i];
+                double2 w = make_double2(fma(sg, b.x, a.x), fma(sg, b.y, a.y));
+                W[k * N + i] = w;
+                if (k >= 1) A[(k + 1) * N + i] = w;
+                if (k < ns) acc += w.x * w.x + w.y * w.y;
+            }
+        }
+        __syncthreads();
+        {
+            int lf = l0 + 1;
+            E.apply_B(A + 2 * N, ns, lf >= L ? lf - L : lf, P);
+        }
+        if (UNI) __syncthreads();
+        // z[l0+k] = w[l0+k] -/+ B^T w[l0+k+1], kept in shared memory (W[k], slot order)
+        for (int i = threadIdx.x; i < N; i += T) {
+            for (int k = 0; k < ns; k++) {
+                int lb = l0 + k + 1;
+                lb = lb >= L ? lb - L : lb;
+                double sg = (lb == 0) ? 1.0 : -1.0;
+                double2 a = W[k * N + i], b = A[(k + 2) * N + i];
+                W[k * N + i] = make_double2(fma(sg, b.x, a.x), fma(sg, b.y, a.y));
+            }
+        }
+        {
+            double v[1] = {acc};
+            block_sum<1>(v, red);
+            if (threadIdx.x == 0) C.part_a[blockIdx.x] = v[0];
+        }
+        if (!grid_barrier(C.barrier, epoch, C.abort_flag)) { done = 3; break; }
+        if (threadIdx.x < 32) {
+            double s = 0.0;
+            for (int q = threadIdx.x; q < (int)gridDim.x; q += 32) s += __ldcg(C.part_a + q);
+            s = warp_sum(s);
+            if (threadIdx.x == 0) sh[0] = s;
+        }
+        __syncthreads();
+        const double alpha = rz / sh[0];
+        // ---- x += alpha p ; r -= alpha z (own slices) ; |r|^2 partial
+        acc = 0.0;
+        for (int i = threadIdx.x; i < N; i += T) {
+            const int s = __ldg(P.slot + i);
+            for (int k = 0; k < ns; k++) {
+                const int g = (l0 + k) * N + i;
+                double2 pv = p_new[g], zv = W[k * N + s], xv = C.x[g], rv = __ldcg(C.r + g);
+                xv = make_double2(fma(alpha, pv.x, xv.x), fma(alpha, pv.y, xv.y));
+                rv = make_double2(fma(-alpha, zv.x, rv.x), fma(-alpha, zv.y, rv.y));
+                C.x[g] = xv;
+                C.r[g] = rv;
+                acc += rv.x * rv.x + rv.y * rv.y;
+            }
+        }
+        {
+            double v[1] = {acc};
+            block_sum<1>(v, red);
+            if (threadIdx.x == 0) C.part_b[blockIdx.x] = v[0];
+        }
+        if (!grid_barrier(C.barrier, epoch, C.abort_flag)) { done = 3; break; }
+        if (threadIdx.x < 32) {
+            double s = 0.0;
+            for (int q = threadIdx.x; q < (int)gridDim.x; q += 32) s += __ldcg(C.part_b + q);
+            s = warp_sum(s);
+            if (threadIdx.x == 0) sh[1] = s;
+        }
+        __syncthreads();
+        const double rr = sh[1];
+        eps = sqrt(rr) / normb;
+        if (eps < tol) { done = 1; break; }
+        if (!(eps == eps)) { done = 2; break; }
+        beta = rr / rz;
+        rz = rr;
+        pc ^= 1;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        CgState s = *C.state;
+        s.iters = it;
+        s.eps = eps;
+        s.done = done;
+        s.rz_re = rz;
+        *C.state = s;
+    }
+}
+
+typedef void (*persist_kernel_t)(const K2Params, const CgPersist);
+template <int CMAX, int UNI>
+static persist_kernel_t pick_pk(int KMAX) {
+    switch (KMAX) {
+        case 1: return k_cg_persistent<CMAX, 1, UNI>;
+        case 2: return k_cg_persistent<CMAX, 2, UNI>;
+        default: return k_cg_persistent<CMAX, 4, UNI>;
+    }
+}
+static persist_kernel_t pick_persist(int ncol, int KMAX, int uni) {
+    if (ncol <= 4) return uni ? pick_pk<4, 1>(KMAX) : pick_pk<4, 0>(KMAX);
+    return uni ? pick_pk<8, 1>(KMAX) : pick_pk<8, 0>(KMAX);
+}
+
+// Runs the persistent solve if all CTAs of the current tuning can be co-resident.  x, r, state are prepared by the
+// caller (cg.cu); p0/p1 are the two p buffers (zeroed here).  Returns false if the cooperative launch is not possible.
+bool fdm_v2_cg_persistent(sq_fdm *f, double2 *x, double2 *r, double2 *p0, double2 *p1, CgState *state, double *part_a, double *part_b,
+                          i64 maxiter) {
+    const int S = f->slab, T = f->threads;
+    if (!fdm_v2_supported(f, 2, S, T)) return false;
+    K2Params P;
+    memset(&P, 0, sizeof(P));
+    P.L = (int)f->L; P.N = (int)f->N; P.Nh = (int)f->Nh; P.C = (int)f->C; P.S = S; P.TX = fdm_v2_tx(f);
+    P.lb = f->slab_lo; P.le = f->slab_hi;
+    for (int c = 0; c < SQ_MAXC; c++) { P.clo[c] = c < f->C ? f->clo[c] : 0; P.chi[c] = c < f->C ? f->chi[c] : 0; }
+    P.nunc0 = f->nunc0;
+    P.nts = f->nts.p; P.nt = f->nt.p; P.slot = f->slot.p; P.unc0 = f->unc0.p; P.cs = f->cs.p; P.expV = f->expV.p;
+    int TY = T / P.TX, nsl = S + 1;
+    int KMAX = (nsl + TY - 1) / TY;
+    KMAX = KMAX <= 1 ? 1 : (KMAX <= 2 ? 2 : 4);
+    size_t smem = (size_t)(2 * S + 3) * f->N * sizeof(double2);
+    int grid = (f->slab_hi - f->slab_lo + S - 1) / S;
+    persist_kernel_t k = pick_persist((int)f->C, KMAX, f->cs_uniform);
+    SQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+    int per_sm = 0;
+    SQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, T, smem));
+    if (per_sm * f->num_sms < grid) return false;
+    if (!f->flag.p) f->flag.alloc(4);
+    SQ_CUDA(cudaMemsetAsync(f->flag.p, 0, 4 * sizeof(int), f->stream));
+    SQ_CUDA(cudaMemsetAsync(p0, 0, f->vec_bytes(), f->stream));
+    SQ_CUDA(cudaMemsetAsync(p1, 0, f->vec_bytes(), f->stream));
+    CgPersist C;
+    C.x = x; C.r = r; C.p0 = p0; C.p1 = p1; C.state = state; C.part_a = part_a; C.part_b = part_b;
+    C.barrier = (unsigned int *)f->flag.p; C.abort_flag = f->flag.p + 1; C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
+    void *args[] = {(void *)&P, (void *)&C};
+    SQ_CUDA(cudaLaunchCooperativeKernel((const void *)k, dim3(grid), dim3(T), args, smem, f->stream));
+    f->launches++;
+    return true;
 }

@@ -48,7 +48,7 @@ struct sq_fdm {
     std::vector<int> h_abi_chk;              // internal bond index -> checkerboard index of the ABI tables
     int use_v2 = 0;                          // chosen by the autotuner / sq_fdm_set_fast_path
     int cs_uniform = 0;                      // (cosh, sinh) do not depend on tau (no SSH coupling): register-resident path
-    DevBuf<int> flag;                        // device scratch flag
+    DevBuf<int> flag;                        // device scratch flags (4 ints: uniformity probe / grid barrier / abort)
     DevBuf<double> expV;                     // [l][i]
     DevBuf<double2> cs;                      // [l][h]
     DevBuf<double2> tmp1, tmp2, r, p, z;     // [l][i]
