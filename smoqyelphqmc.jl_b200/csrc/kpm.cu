@@ -155,13 +155,22 @@ struct BbarFast {
     long long *dbg;
 };
 
+// B-bar is real, so the real and imaginary parts of a frequency vector are two independent real recurrences: they
+// run in two CTAs on different SMs.  A colour step is bound by the shared-memory port of its SM (measured with
+// tools/ubench/stage_latency.cu: ~0.6 cycles per bond item of 64 B, i.e. 85 % of 128 B/clk), so halving the bytes
+// per item (LDS.64 / STS.64 on doubles) halves the length of the critical path.
 template <int CMAX>
 struct ChebEngine {
-    int c_i[CMAX], c_j[CMAX];
+    int c_i[CMAX], c_j[CMAX];      // slots of this thread's bond in every colour (-1: none)
     double cc[CMAX], ss[CMAX];
     double d_i, d_j;
-    int last;                     // C - 1
+    int last;                      // C - 1
 
+    __device__ __forceinline__ static void rot(double &a, double &b, double c, double s) {
+        double na = fma(s, b, c * a), nb = fma(s, a, c * b);
+        a = na;
+        b = nb;
+    }
     __device__ __forceinline__ void init(const BbarFast &P) {
         const int tx = threadIdx.x;
         last = P.C - 1;
@@ -182,124 +191,110 @@ struct ChebEngine {
         }
     }
     template <int Q>
-    __device__ __forceinline__ void smem_step(double2 *Y) {
+    __device__ __forceinline__ void smem_step(double *Y) {
         if (c_i[Q] >= 0) {
-            double2 a = Y[c_i[Q]], b = Y[c_j[Q]];
-            rotb(a, b, cc[Q], ss[Q]);
+            double a = Y[c_i[Q]], b = Y[c_j[Q]];
+            rot(a, b, cc[Q], ss[Q]);
             Y[c_i[Q]] = a;
             Y[c_j[Q]] = b;
         }
         __syncthreads();
     }
     template <int Q>
-    __device__ __forceinline__ void down(double2 *Y) {      // colours last-1 ... 1
+    __device__ __forceinline__ void down(double *Y) {       // colours last-1 ... 1
         if constexpr (Q >= 1) {
             if (Q < last) smem_step<Q>(Y);
             down<Q - 1>(Y);
         }
     }
     template <int Q>
-    __device__ __forceinline__ void up(double2 *Y) {        // colours 1 ... last-1
+    __device__ __forceinline__ void up(double *Y) {         // colours 1 ... last-1
         if constexpr (Q < CMAX) {
             if (Q < last) smem_step<Q>(Y);
             up<Q + 1>(Y);
         }
     }
-    __device__ __forceinline__ void mid(double2 &a, double2 &b) {
-        rotb(a, b, cc[0], ss[0]);
-        a = make_double2(d_i * a.x, d_i * a.y);
-        b = make_double2(d_j * b.x, d_j * b.y);
-        rotb(a, b, cc[0], ss[0]);
+    __device__ __forceinline__ void mid(double &a, double &b) {
+        rot(a, b, cc[0], ss[0]);
+        a *= d_i;
+        b *= d_j;
+        rot(a, b, cc[0], ss[0]);
     }
-    // (a, b) <- (B-bar y)_{i,j} for the thread's last-colour bond; a, b enter holding y_i, y_j.
-    __device__ __forceinline__ void apply(double2 &a, double2 &b, double2 *Y, const BbarFast &P) {
-        if (last == 0) { mid(a, b); return; }            // single colour: all in registers
-        const int oi = pick_last(c_i), oj = pick_last(c_j);
-        const double cl = pick_lastd(cc), sl = pick_lastd(ss);
+    // (a, b) <- (B-bar y)_{i,j} for the thread's last-colour bond (slots oi, oj; coefficients cl, sl)
+    __device__ __forceinline__ void apply(double &a, double &b, double *Y, const BbarFast &P, int oi, int oj, double cl, double sl) {
+        if (last == 0) { mid(a, b); return; }             // single colour: all in registers
         if (oi >= 0) {
-            rotb(a, b, cl, sl);
+            rot(a, b, cl, sl);
             Y[oi] = a;
             Y[oj] = b;
         }
         __syncthreads();
         down<CMAX - 1>(Y);
         if (c_i[0] >= 0) {
-            double2 u = Y[c_i[0]], v = Y[c_j[0]];
+            double u = Y[c_i[0]], v = Y[c_j[0]];
             mid(u, v);
             Y[c_i[0]] = u;
             Y[c_j[0]] = v;
         }
         for (int q = threadIdx.x; q < P.nunc0; q += blockDim.x) {
             int i = __ldg(P.unc0 + q);
-            double d = __ldg(P.Dbar + i);
             int s = __ldg(P.slot + i);
-            double2 u = Y[s];
-            Y[s] = make_double2(d * u.x, d * u.y);
+            Y[s] *= __ldg(P.Dbar + i);
         }
         __syncthreads();
         up<1>(Y);
         if (oi >= 0) {
             a = Y[oi];
             b = Y[oj];
-            rotb(a, b, cl, sl);
+            rot(a, b, cl, sl);
         }
-    }
-    __device__ __forceinline__ int pick_last(const int (&v)[CMAX]) const {
-        int r = v[0];
-#pragma unroll
-        for (int q = 1; q < CMAX; q++) r = (last == q) ? v[q] : r;
-        return r;
-    }
-    __device__ __forceinline__ double pick_lastd(const double (&v)[CMAX]) const {
-        double r = v[0];
-#pragma unroll
-        for (int q = 1; q < CMAX; q++) r = (last == q) ? v[q] : r;
-        return r;
     }
 };
 
+// grid = 2 * (#frequencies with order > 1): blockIdx.x = 2 * schedule index + (0: real part, 1: imaginary part)
 template <int CMAX, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 k_kpm_cheb_fast(const __grid_constant__ BbarFast P, double2 *__restrict__ z, const int *__restrict__ sched, const int *__restrict__ order,
                 const int *__restrict__ coef_off, const double2 *__restrict__ coefs, int L, double avg, double imag_,
                 const CgState *__restrict__ skip) {
-    extern __shared__ double2 Y[];
+    extern __shared__ double Yr[];
     if (skip && skip->done) return;
     ChebEngine<CMAX> E;
     E.init(P);
-    const int n = sched[blockIdx.x];
+    const int n = sched[blockIdx.x >> 1], part = blockIdx.x & 1;
     const int np = (n + 1 > (L + 1) / 2) ? L - 1 - n : n;
     const int ord = order[np];
-    const double2 *c = coefs + coef_off[np];
-    double2 *zn = z + (size_t)n * P.N;
-    // owner sites of this thread: its bond in the last colour
-    int si = -1, sj = -1;
+    const double2 *c = coefs + coef_off[np];                 // real coefficients (Sym): .x
+    double *zn = reinterpret_cast<double *>(z + (size_t)n * P.N) + part;
+    // the thread owns the two sites of its bond in the last colour
+    int si = -1, sj = -1, oi = -1, oj = 0;
+    double cl = 1.0, sl = 0.0;
     if (threadIdx.x < P.chi[E.last] - P.clo[E.last]) {
         int2 q = __ldg(P.nt + P.clo[E.last] + threadIdx.x);
-        si = q.x; sj = q.y;
+        int2 o = __ldg(P.nts + P.clo[E.last] + threadIdx.x);
+        double2 v = __ldg(P.csbar + P.clo[E.last] + threadIdx.x);
+        si = q.x; sj = q.y; oi = o.x; oj = o.y; cl = v.x; sl = v.y;
     }
-    double2 t0i = make_double2(0, 0), t0j = t0i;
-    if (si >= 0) { t0i = zn[si]; t0j = zn[sj]; }
-    double2 yi = t0i, yj = t0j;
+    double t0i = 0, t0j = 0;
+    if (si >= 0) { t0i = zn[2 * si]; t0j = zn[2 * sj]; }
+    double yi = t0i, yj = t0j;
     if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[0] = clock64();
-    E.apply(yi, yj, Y, P);
+    E.apply(yi, yj, Yr, P, oi, oj, cl, sl);
     if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) { P.dbg[1] = clock64(); P.dbg[3] = ord; }
-    double2 t1i = make_double2((yi.x - avg * t0i.x) * imag_, (yi.y - avg * t0i.y) * imag_);
-    double2 t1j = make_double2((yj.x - avg * t0j.x) * imag_, (yj.y - avg * t0j.y) * imag_);
-    double2 c0 = c[0], c1 = c[1];
-    double2 acci = cadd(cmul(c0, t0i), cmul(c1, t1i)), accj = cadd(cmul(c0, t0j), cmul(c1, t1j));
+    double t1i = (yi - avg * t0i) * imag_, t1j = (yj - avg * t0j) * imag_;
+    const double c0 = c[0].x, c1 = c[1].x;
+    double acci = c0 * t0i + c1 * t1i, accj = c0 * t0j + c1 * t1j;
     for (int q = 2; q < ord; q++) {
         yi = t1i; yj = t1j;
-        E.apply(yi, yj, Y, P);
-        double2 t2i = make_double2(2.0 * (yi.x - avg * t1i.x) * imag_ - t0i.x, 2.0 * (yi.y - avg * t1i.y) * imag_ - t0i.y);
-        double2 t2j = make_double2(2.0 * (yj.x - avg * t1j.x) * imag_ - t0j.x, 2.0 * (yj.y - avg * t1j.y) * imag_ - t0j.y);
-        double2 cq = c[q];
-        acci = cadd(acci, cmul(cq, t2i));
-        accj = cadd(accj, cmul(cq, t2j));
+        E.apply(yi, yj, Yr, P, oi, oj, cl, sl);
+        double t2i = 2.0 * (yi - avg * t1i) * imag_ - t0i, t2j = 2.0 * (yj - avg * t1j) * imag_ - t0j;
+        const double cq = c[q].x;
+        acci = fma(cq, t2i, acci);
+        accj = fma(cq, t2j, accj);
         t0i = t1i; t0j = t1j; t1i = t2i; t1j = t2j;
     }
     if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[2] = clock64();
-    if (si >= 0) { zn[si] = acci; zn[sj] = accj; }
+    if (si >= 0) { zn[2 * si] = acci; zn[2 * sj] = accj; }
 }
 
 // tau-means of the operator coefficients (update_B̄!, :604-621): grid over sites/bonds, 32 x 8 threads
@@ -562,10 +557,7 @@ void kpm_create_impl(sq_kpm **out, sq_fdm *f, double rbuf, i64 n, double a1, dou
         k->lan_start.alloc(f->N);
         SQ_CUDA(cudaFuncSetAttribute(k_kpm_cheb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
         SQ_CUDA(cudaFuncSetAttribute(k_lanczos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
-        SQ_CUDA(cudaFuncSetAttribute(k_kpm_cheb_fast<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
-        SQ_CUDA(cudaFuncSetAttribute(k_kpm_cheb_fast<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
-        SQ_CUDA(cudaFuncSetAttribute(k_kpm_cheb_fast<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
-        SQ_CUDA(cudaFuncSetAttribute(k_kpm_cheb_fast<8, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        // (the fast Chebyshev kernels need at most N double2 of dynamic shared memory: below the 48 KB default for N <= 3072)
     } catch (...) {
         delete k;
         throw;
@@ -648,8 +640,9 @@ int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *
         double avg = 0.5 * (k->bounds[1] + k->bounds[0]), mag = 0.5 * (k->bounds[1] - k->bounds[0]);
         size_t smem = f->N * sizeof(double2);
         const int T = kpm_fast_threads(k);
-#define SQ_CHEB(CM, MT) k_kpm_cheb_fast<CM, MT><<<k->nsched, T, smem, f->stream>>>(Q, zt, k->d_freq_sched.p, k->d_order.p, k->d_coef_off.p, \
-                                                                                    k->d_coefs.p, (int)f->L, avg, 1.0 / mag, skip)
+        smem = f->N * sizeof(double);
+#define SQ_CHEB(CM, MT) k_kpm_cheb_fast<CM, MT><<<2 * k->nsched, T, smem, f->stream>>>(Q, zt, k->d_freq_sched.p, k->d_order.p, k->d_coef_off.p, \
+                                                                                       k->d_coefs.p, (int)f->L, avg, 1.0 / mag, skip)
         if (f->C <= 4) { if (T <= 512) SQ_CHEB(4, 512); else SQ_CHEB(4, 1024); }
         else { if (T <= 512) SQ_CHEB(8, 512); else SQ_CHEB(8, 1024); }
 #undef SQ_CHEB
