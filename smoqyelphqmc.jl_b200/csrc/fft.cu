@@ -40,7 +40,7 @@ struct FftPlan {
 };
 
 template <int R>
-__device__ __forceinline__ void butterfly(double2 (&x)[R], const double2 *__restrict__ tw, int L, bool inverse) {
+__device__ __forceinline__ void butterfly(double2 (&x)[R], const double2 *tw, int L, bool inverse) {
     // in-register DFT of size R: x[q'] = sum_q x[q] w_R^(q q'),  w_R = tw[L/R] (conjugated for the inverse)
     if (R == 2) {
         double2 a = x[0], b = x[1];
@@ -74,7 +74,7 @@ __device__ __forceinline__ void butterfly(double2 (&x)[R], const double2 *__rest
 
 template <int R>
 __device__ __forceinline__ void stockham_pass(const double2 *__restrict__ src, double2 *__restrict__ dst, int L, int Ns, int SB,
-                                              const double2 *__restrict__ tw, bool inverse) {
+                                              const double2 *tw, bool inverse) {
     const int nb = L / R;                       // butterflies per column
     for (int w = threadIdx.x; w < nb * SB; w += blockDim.x) {
         int j = w / SB, col = w - j * SB;
@@ -99,7 +99,7 @@ __device__ __forceinline__ void stockham_pass(const double2 *__restrict__ src, d
 
 // generic radix (prime factors other than 2, 3, 5, 7): O(r^2), inputs re-read from shared memory
 __device__ __forceinline__ void stockham_pass_generic(const double2 *__restrict__ src, double2 *__restrict__ dst, int L, int Ns, int R,
-                                                      int SB, const double2 *__restrict__ tw, bool inverse) {
+                                                      int SB, const double2 *tw, bool inverse) {
     const int nb = L / R;
     for (int w = threadIdx.x; w < nb * SB * R; w += blockDim.x) {
         int qp = w / (nb * SB), rest = w - qp * nb * SB;
@@ -122,7 +122,7 @@ __device__ __forceinline__ void stockham_pass_generic(const double2 *__restrict_
 // scale1 (may be NULL) folds the order-1 ("scalar") frequencies of the preconditioner into the store.
 // dot_with (may be NULL): per-CTA partial sums of conj(dot_with).out (re, im) -> the CG r.z dot product.
 __global__ void k_tau_fft(const FftPlan plan, double2 *__restrict__ out, const double2 *__restrict__ in, int N, int SB, int inverse,
-                          int twist, const double2 *__restrict__ tw, const double2 *__restrict__ theta,
+                          int twist, const double2 *tw, const double2 *__restrict__ theta,
                           const double *__restrict__ scale1, const double2 *__restrict__ dot_with, double *__restrict__ dot_part,
                           const CgState *__restrict__ skip) {
     extern __shared__ double2 sm[];
@@ -130,20 +130,40 @@ __global__ void k_tau_fft(const FftPlan plan, double2 *__restrict__ out, const d
     if (skip && skip->done) return;
     const int L = plan.L;
     double2 *bufA = sm, *bufB = sm + (size_t)L * SB;
+    double2 *stw = sm + (size_t)2 * L * SB;          // twiddles staged in shared memory: no global loads inside the passes
     const int i0 = blockIdx.x * SB;
     const int ncol = min(SB, N - i0);
     const double rs = rsqrt((double)L);
-    for (int w = threadIdx.x; w < L * SB; w += blockDim.x) {
-        int l = w / SB, col = w - l * SB;
-        double2 v = make_double2(0, 0);
-        if (col < ncol) {
-            v = in[(size_t)l * N + i0 + col];
-            if (!inverse && twist) v = cmul(v, cscale(rs, theta[l]));
-            else if (!inverse) v = cscale(rs, v);
+    for (int k = threadIdx.x; k < L; k += blockDim.x) stw[k] = tw[k];
+    // tile load, 4 independent global loads in flight per thread
+    const int tot = L * SB, T = blockDim.x;
+    for (int w0 = threadIdx.x; w0 < tot; w0 += 4 * T) {
+        double2 v[4];
+        int lq[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            int w = w0 + q * T;
+            v[q] = make_double2(0, 0);
+            lq[q] = -1;
+            if (w < tot) {
+                int l = w / SB, col = w - l * SB;
+                lq[q] = l;
+                if (col < ncol) v[q] = in[(size_t)l * N + i0 + col];
+            }
         }
-        bufA[w] = v;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            int w = w0 + q * T;
+            if (w < tot) {
+                double2 x = v[q];
+                if (!inverse && twist) x = cmul(x, cscale(rs, theta[lq[q]]));
+                else if (!inverse) x = cscale(rs, x);
+                bufA[w] = x;
+            }
+        }
     }
     __syncthreads();
+    tw = stw;
     double2 *src = bufA, *dst = bufB;
     int Ns = 1;
     for (int s = 0; s < plan.nrad; s++) {
@@ -195,10 +215,10 @@ int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, 
     if (plan.nrad > 24) throw SqError("FFT length has too many prime factors");
     for (int s = 0; s < plan.nrad; s++) plan.rad[s] = radices[s];
     int SB = 8;
-    while (SB > 1 && (size_t)2 * L * SB * sizeof(double2) > smem_limit) SB >>= 1;
+    while (SB > 1 && (size_t)(2 * SB + 1) * L * sizeof(double2) > smem_limit) SB >>= 1;
     // prefer more CTAs when the lattice is small
     while (SB > 2 && (N + SB - 1) / SB < 148) SB >>= 1;
-    size_t smem = (size_t)2 * L * SB * sizeof(double2);
+    size_t smem = (size_t)(2 * SB + 1) * L * sizeof(double2);
     if (smem > smem_limit) throw SqError("imaginary-time axis too long for the shared-memory FFT");
     static bool attr = false;
     if (!attr) {
@@ -209,6 +229,8 @@ int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, 
     if (grid > SQ_MAXPART) throw SqError("lattice too large for the FFT partial-sum buffer");
     int threads = 256;
     if (L * SB >= 2048) threads = 512;
+    if (const char *e = getenv("SQ_FFT_SB")) { int v = atoi(e); if (v >= 1 && (size_t)(2 * v + 1) * L * sizeof(double2) <= smem_limit) { SB = v; smem = (size_t)(2 * SB + 1) * L * sizeof(double2); grid = (N + SB - 1) / SB; } }
+    if (const char *e = getenv("SQ_FFT_T")) threads = atoi(e);
     k_tau_fft<<<grid, threads, smem, stream>>>(plan, out, in, N, SB, inverse ? 1 : 0, twist ? 1 : 0, tw, theta, scale1, dot_with,
                                                dot_part, skip);
     SQ_LAUNCH_CHECK();

@@ -97,6 +97,8 @@ struct sq_kpm {
     DevBuf<double2> d_coefs;
     DevBuf<double> d_scale1;                 // per frequency: scalar applied by the FFT store when order == 1
     int nsched = 0;                          // frequencies with order > 1
+    int chain_ok = 0, chain_T = 0;           // chain-in-warp Chebyshev path (chain.h)
+    DevBuf<int> chain_buf[2][9];             // [mid / outer][pos_u, pos_v, nat_u, nat_v, bond_a, bond_b, next, prev, has_prev]
     DevBuf<double2> ztmp;                    // [n][i] frequency-space scratch
     DevBuf<double> lan;                      // Lanczos alpha/beta read-back
     DevBuf<double> lan_start;                // N
