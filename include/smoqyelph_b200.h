@@ -74,9 +74,15 @@ int sq_fdm_cg_dev(sq_fdm *f, void *d_x, const void *d_b, int zero_start, sq_kpm 
                   int64_t maxiter, int64_t *iters, double *eps);
 /* kernel configuration of the fused matvec (slices per CTA, threads per CTA; 0 = autotune) */
 int sq_fdm_set_tuning(sq_fdm *f, int slab, int threads);
-int sq_fdm_get_tuning(sq_fdm *f, int *slab, int *threads, int *path);   /* path: 0 generic fused, 1 global passes, 2 fast fused */
-int sq_fdm_set_fast_path(sq_fdm *f, int enable);                       /* fast fused kernel where it applies (Sym, <= 8 colours) */
+int sq_fdm_get_tuning(sq_fdm *f, int *slab, int *threads, int *path);   /* path: 0 generic fused, 1 global passes, 2 fast fused, 3 register path */
+int sq_fdm_set_fast_path(sq_fdm *f, int enable);                       /* 0 generic, 1 fast fused kernel (Sym, <= 8 colours), 2 (+ 256 S) register path (rectangular lattices) */
 int sq_fdm_stream(sq_fdm *f, void **cuda_stream);
+/* measurement aid (bench.py, tools/): `reps` back-to-back launches of op on device vectors, timed with CUDA events on the
+ * library stream; *us_per_launch = elapsed / reps (L2-hot: the working set of the named configs stays in L2).  If
+ * d_flush != NULL a write of flush_bytes to d_flush precedes every launch (L2-cold) and each launch is timed on its own;
+ * the median is returned. */
+int sq_fdm_time_mul(sq_fdm *f, int op, void *d_out, const void *d_in, int reps, void *d_flush, int64_t flush_bytes,
+                    double *us_per_launch);
 /* tau-slab partitioning over the GPUs of one node (the reference is single-process).  Rank g of `world`
  * produces the contiguous slices [lo, hi) of every vector; arrays stay full length and sq_fdm_mul_dev / sq_fdm_cg_dev
  * exchange the one-slice halos with the ring neighbours over NCCL (libnccl is dlopen'ed).  id128 comes from

@@ -123,6 +123,13 @@ class FermionDetMatrix:
     def set_tuning(self, slab, threads): check(self.L.sq_fdm_set_tuning(self.h, slab, threads))
     def set_fast_path(self, enable): check(self.L.sq_fdm_set_fast_path(self.h, int(enable)))
 
+    def time_mul(self, op, d_out, d_in, reps=200, d_flush=None, flush_bytes=0):
+        """Device time per launch in microseconds (CUDA events inside the library): back to back (L2-hot), or with a
+        flush_bytes write to d_flush before every launch (L2-cold, median)."""
+        us = C.c_double(0)
+        check(self.L.sq_fdm_time_mul(self.h, op, ptr(d_out), ptr(d_in), reps, ptr(d_flush) if d_flush else None, flush_bytes, C.byref(us)))
+        return us.value
+
     # ---- tau-slab partitioning (multi-GPU) ----
     @staticmethod
     def nccl_unique_id() -> bytes:

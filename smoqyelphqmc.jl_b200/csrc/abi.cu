@@ -2,6 +2,8 @@
 // code translation, host <-> device staging.  No compute lives here.
 #include "sq_internal.h"
 
+#include <algorithm>
+
 #include <cstring>
 #include <mutex>
 
@@ -22,6 +24,9 @@ void fdm_update_impl(sq_fdm *f, const double *V, const double *t, double dtau);
 void fdm_get_coefficients_impl(sq_fdm *f, double *expV, double *ch, double *sh);
 void fdm_mul_impl(sq_fdm *f, int op, void *out, const void *in);
 void fdm_select_tuning(sq_fdm *f);
+bool fdm_v3_supported(const sq_fdm *f, int S);
+int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native);
+void fdm_v3_prepare_native(sq_fdm *f);
 void slab_unique_id(char *out128);
 void slab_init(sq_fdm *f, int rank, int world, const char *id128);
 void slab_set_range(sq_fdm *f, int lo, int hi);
@@ -132,6 +137,52 @@ int sq_fdm_mul_dev(sq_fdm *f, int op, void *d_out, const void *d_in) {
     fdm_mul_dev(f, op, (double2 *)d_out, (const double2 *)d_in);
     SQ_CATCH
 }
+int sq_fdm_time_mul(sq_fdm *f, int op, void *d_out, const void *d_in, int reps, void *d_flush, int64_t flush_bytes,
+                    double *us_per_launch) {
+    SQ_TRY
+    SQ_REQUIRE(f && d_out && d_in && us_per_launch && reps >= 1, "bad argument");
+    SQ_REQUIRE(f->world == 1, "single-GPU measurement only");
+    SQ_CUDA(cudaSetDevice(f->device));
+    cudaEvent_t e0, e1;
+    SQ_CUDA(cudaEventCreate(&e0));
+    SQ_CUDA(cudaEventCreate(&e1));
+    // op 102: M^T M of the register path on vectors in its native order (what the CG solver runs), timing only
+    const bool native = (op == 102);
+    if (native) {
+        fdm_select_tuning(f);
+        SQ_REQUIRE(f->path == 0 && f->use_v3 && fdm_v3_supported(f, f->v3_S), "register path not active");
+        fdm_v3_prepare_native(f);
+    }
+    auto fdm_mul_dev = [&](sq_fdm *ff, int o, double2 *out, const double2 *in) {
+        if (native) fdm_v3_launch(ff, 2, ff->v3_S, out, in, nullptr, nullptr, true);
+        else ::fdm_mul_dev(ff, o, out, in);
+    };
+    for (int k = 0; k < 3; k++) fdm_mul_dev(f, op, (double2 *)d_out, (const double2 *)d_in);
+    if (!d_flush) {
+        SQ_CUDA(cudaEventRecord(e0, f->stream));
+        for (int k = 0; k < reps; k++) fdm_mul_dev(f, op, (double2 *)d_out, (const double2 *)d_in);
+        SQ_CUDA(cudaEventRecord(e1, f->stream));
+        SQ_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        SQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        *us_per_launch = 1e3 * ms / reps;
+    } else {
+        std::vector<float> t(reps);
+        for (int k = 0; k < reps; k++) {
+            SQ_CUDA(cudaMemsetAsync(d_flush, k & 1, (size_t)flush_bytes, f->stream));
+            SQ_CUDA(cudaEventRecord(e0, f->stream));
+            fdm_mul_dev(f, op, (double2 *)d_out, (const double2 *)d_in);
+            SQ_CUDA(cudaEventRecord(e1, f->stream));
+            SQ_CUDA(cudaEventSynchronize(e1));
+            SQ_CUDA(cudaEventElapsedTime(&t[k], e0, e1));
+        }
+        std::sort(t.begin(), t.end());
+        *us_per_launch = 1e3 * t[reps / 2];
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    SQ_CATCH
+}
 int sq_fdm_set_tuning(sq_fdm *f, int slab, int threads) {
     SQ_TRY
     SQ_REQUIRE(f, "NULL handle");
@@ -147,7 +198,11 @@ int sq_fdm_set_tuning(sq_fdm *f, int slab, int threads) {
 int sq_fdm_set_fast_path(sq_fdm *f, int enable) {
     SQ_TRY
     SQ_REQUIRE(f, "NULL handle");
+    // 0: generic shared-memory kernel, 1: fast shared-memory kernel (fdm_v2.cu), 2: register path (fdm_v3.cu; falls back
+    // to 1 when the lattice / coefficients do not qualify), optionally with slices-per-CTA in bits 8..: enable = 2 + 256 * S
     f->use_v2 = enable ? 1 : 0;
+    f->use_v3 = ((enable & 255) == 2) ? 1 : 0;
+    if (f->use_v3 && (enable >> 8) >= 1 && (enable >> 8) <= 7) f->v3_S = enable >> 8;
     f->manual_tuning = 1;
     SQ_CATCH
 }
@@ -158,6 +213,11 @@ int sq_fdm_get_tuning(sq_fdm *f, int *slab, int *threads, int *path) {
     if (slab) *slab = f->slab;
     if (threads) *threads = f->threads;
     if (path) *path = f->path == 1 ? 1 : (f->use_v2 ? 2 : 0);
+    if (f->path == 0 && f->use_v3 && fdm_v3_supported(f, f->v3_S)) {      // register path: one warp per slice, S + 1 warps
+        if (slab) *slab = f->v3_S;
+        if (threads) *threads = 32 * (f->v3_S + 1);
+        if (path) *path = 3;
+    }
     SQ_CATCH
 }
 int sq_fdm_stream(sq_fdm *f, void **cuda_stream) {

@@ -171,6 +171,18 @@ int fdm_v2_launch_cg(sq_fdm *f, double2 *z, const double2 *p_old, double2 *p_new
                      const double *rr_part, int nrr, const double *beta_part, int nbeta, int beta_complex, int iter, int check,
                      double *pAp_part);
 
+bool fdm_v3_supported(const sq_fdm *f, int S);
+int fdm_v3_launch_cg(sq_fdm *f, double2 *z, const double2 *p_old, double2 *p_new, const double2 *d, const CgState *cur, CgState *nxt,
+                     const double *rr_part, int nrr, const double *beta_part, int nbeta, int beta_complex, int iter, int check,
+                     double *pAp_part, bool native);
+int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native);
+void fdm_v3_prepare_native(sq_fdm *f);
+bool fdm_v3_cg_persistent(sq_fdm *f, double2 *x, double2 *r, double2 *p0, double2 *p1, CgState *state, double *part_a, double *part_b,
+                          i64 maxiter);
+bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, double2 *halo, CgState *state, double *part_a, double *part_b, i64 maxiter);
+void fdm_v3_to_native(sq_fdm *f, double2 *dst, const double2 *src);
+void fdm_v3_from_native(sq_fdm *f, double2 *dst, const double2 *src);
+
 // end-of-batch convergence test for the fused scheme (the in-kernel test of iteration j runs in iteration j+1)
 __global__ void k_cg_final_check(CgState *st, const double *__restrict__ rr_part, int npart, int iter) {
     __shared__ double sh[3];
@@ -239,8 +251,9 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
     int cur = 0;
     bool finished = false;
     fdm_select_tuning(f);
-    const bool fused = !prec && f->path == 0 && f->use_v2 && fdm_v2_supported(f, 2, f->slab, f->threads) && !getenv("SQ_NO_CG_FUSION");
-    if (fused && !getenv("SQ_NO_PERSISTENT_CG") && maxiter > 0) {
+    const bool v3 = f->path == 0 && f->use_v3 && fdm_v3_supported(f, f->v3_S);
+    const bool fused = !prec && f->path == 0 && (v3 || (f->use_v2 && fdm_v2_supported(f, 2, f->slab, f->threads))) && !getenv("SQ_NO_CG_FUSION");
+    if (fused && !v3 && !getenv("SQ_NO_PERSISTENT_CG") && maxiter > 0) {
         // One cooperative launch for the whole solve (fdm_v2.cu: k_cg_persistent).  The state prepared by k_cg_init holds
         // |r0|^2, |b| and tol; an already converged system (eps0 < tol) is caught first.
         SQ_CUDA(cudaMemcpyAsync(f->h_cg, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
@@ -260,8 +273,40 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
     if (fused) {
         // Two kernels per iteration: K_A' forms p = r + beta p on load (ping-ponged p buffers), tests the convergence of
         // the previous iteration and applies M^T M; K_B updates x and r.  tmp1 is the second p buffer.
+        // Register path: x, r, p, z live in the kernel's native order for the whole solve (every access coalesced); alpha and
+        // beta are real without a preconditioner, so the BLAS-1 kernels are order-agnostic.  x is converted back at the end.
         double2 *pb[2] = {p, f->tmp1.p};
         int pc = 0;
+        double2 *x_user = x;
+        const bool native = v3 && !getenv("SQ_V3_NO_NATIVE");
+        if (native) {
+            fdm_v3_prepare_native(f);
+            fdm_v3_to_native(f, f->v3_r.p, r);
+            if (zero_start) SQ_CUDA(cudaMemsetAsync(f->v3_x.p, 0, n * sizeof(double2), s));
+            else fdm_v3_to_native(f, f->v3_x.p, x);
+            SQ_CUDA(cudaMemcpyAsync(pb[0], f->v3_r.p, n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+            x = f->v3_x.p;
+            r = f->v3_r.p;
+            if (!getenv("SQ_NO_PERSISTENT_CG") && maxiter > 0) {
+                // one cooperative launch for the whole solve (fdm_v3.cu: k_cg_v3_persistent); k_cg_init left |r0|^2, |b|, tol in st
+                SQ_CUDA(cudaMemcpyAsync(f->h_cg, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+                SQ_CUDA(cudaStreamSynchronize(s));
+                if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+                if (f->h_cg->done) { *iters = 0; *eps = f->h_cg->eps; return; }
+                if ((!getenv("SQ_NO_RESIDENT_CG") && fdm_v3_cg_resident(f, x, r, pb[1], st, part_pAp, part_rr, maxiter)) ||
+                    fdm_v3_cg_persistent(f, x, r, pb[0], pb[1], st, part_pAp, part_rr, maxiter)) {
+                    fdm_v3_from_native(f, x_user, x);
+                    SQ_CUDA(cudaMemcpyAsync(f->h_cg, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+                    SQ_CUDA(cudaStreamSynchronize(s));
+                    if (f->h_cg->done == 3) throw SqError("conjugate gradient: grid barrier timed out in the persistent kernel");
+                    if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+                    *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
+                    *eps = f->h_cg->eps;
+                    return;
+                }
+                SQ_CUDA(cudaMemcpyAsync(pb[0], f->v3_r.p, n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+            }
+        }
         while (!finished) {
             i64 upto = std::min<i64>(maxiter, it + batch);
             for (; it < upto;) {
@@ -270,10 +315,12 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
                 CgState *sn = st + (cur ^ 1);
                 int npart = 0;
                 if (it == 1) {
-                    fdm_mul_dev(f, SQ_OP_MTM, z, pb[pc], part_pAp, &npart, sc);       // p0 = r0, nothing to fuse
+                    if (native) npart = fdm_v3_launch(f, 2, f->v3_S, z, pb[pc], part_pAp, sc, true);
+                    else fdm_mul_dev(f, SQ_OP_MTM, z, pb[pc], part_pAp, &npart, sc);       // p0 = r0, nothing to fuse
                     k_cg_update_xr<<<G, TB, 0, s>>>(sc, x, r, pb[pc], z, n, part_pAp, npart, 0, part_rr);
                 } else {
-                    npart = fdm_v2_launch_cg(f, z, pb[pc], pb[pc ^ 1], r, sc, sn, part_rr, G, part_rr, G, 0, (int)it, 1, part_pAp);
+                    npart = v3 ? fdm_v3_launch_cg(f, z, pb[pc], pb[pc ^ 1], r, sc, sn, part_rr, G, part_rr, G, 0, (int)it, 1, part_pAp, native)
+                               : fdm_v2_launch_cg(f, z, pb[pc], pb[pc ^ 1], r, sc, sn, part_rr, G, part_rr, G, 0, (int)it, 1, part_pAp);
                     pc ^= 1;
                     cur ^= 1;
                     k_cg_update_xr<<<G, TB, 0, s>>>(sn, x, r, pb[pc], z, n, part_pAp, npart, 0, part_rr);
@@ -287,6 +334,7 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
             SQ_CUDA(cudaStreamSynchronize(s));
             if (f->h_cg->done || it >= maxiter) finished = true;
         }
+        if (native) fdm_v3_from_native(f, x_user, x);
         if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
         *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
         *eps = f->h_cg->eps;

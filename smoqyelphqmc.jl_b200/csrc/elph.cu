@@ -220,6 +220,11 @@ void elph_create_impl(sq_elph **out, sq_fdm *f, double dtau, i64 Nph, const doub
         up(e->ph_ssh_ptr, cnt, s); up(e->ph_ssh_cpl, sitems, s);
         up(e->V0, std::vector<double>(V0, V0 + f->N), s);
         up(e->t0, std::vector<double>(t0 ? t0 : V0, (t0 ? t0 : V0) + (t0 ? f->Nh : 0)), s);
+        // bare hoppings equal inside every colour (|t| and sign): the register path of the fused matvec applies
+        e->t0_coluni = (t0 != nullptr && f->Nh > 0);
+        for (i64 c = 0; c < f->C && e->t0_coluni; c++)
+            for (int h = f->clo[c]; h < f->chi[c]; h++)
+                if (t0[f->h_perm[h]] != t0[f->h_perm[f->clo[c]]]) { e->t0_coluni = false; break; }
     } catch (...) {
         delete e;
         throw;
@@ -236,6 +241,7 @@ void elph_refresh_fdm(sq_elph *e) {
     f->launches++;
     f->coef_version++;
     f->cs_uniform = (e->Nssh == 0) ? 1 : 0;       // no SSH coupling => hoppings (and cosh, sinh) are tau-independent
+    f->cs_coluni = (f->cs_uniform && e->t0_coluni) ? 1 : 0;
 }
 
 void elph_build_Vt(sq_elph *e) {

@@ -296,12 +296,20 @@ __global__ void k_fdm_update(double *__restrict__ expV, double2 *__restrict__ cs
 }
 
 // flag = 1 if any (cosh, sinh) differs from its slice-0 value
-__global__ void k_cs_nonuniform(const double2 *__restrict__ cs, int L, int Nh, int *__restrict__ flag) {
+// flag[0]: (cosh, sinh) depend on tau; flag[2]: they differ between bonds of one colour (colour ranges in cr.lo / cr.hi)
+struct ColRanges { int C; int lo[SQ_MAXC], hi[SQ_MAXC]; };
+__global__ void k_cs_nonuniform(const double2 *__restrict__ cs, int L, int Nh, int *__restrict__ flag, const ColRanges cr) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)L * Nh) return;
     int h = (int)(idx % Nh);
     double2 a = cs[idx], b = cs[h];
-    if (a.x != b.x || a.y != b.y) *flag = 1;
+    if (a.x != b.x || a.y != b.y) flag[0] = 1;
+    if (idx < (size_t)Nh) {
+        int c = 0;
+        while (c < cr.C - 1 && h >= cr.hi[c]) c++;
+        double2 q = cs[cr.lo[c]];
+        if (a.x != q.x || a.y != q.y) flag[2] = 1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -354,6 +362,9 @@ void fdm_select_tuning(sq_fdm *f);
 void fdm_v2_set_attributes(sq_fdm *f);
 void fdm_v2_launch(sq_fdm *f, int mode, int S, int T, double2 *out, const double2 *in, double *part, const CgState *skip);
 int fdm_v2_tx(const sq_fdm *f);
+void fdm_v3_detect(sq_fdm *f);
+bool fdm_v3_supported(const sq_fdm *f, int S);
+int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native = false);
 
 KParams sq_fdm::kparams(int S, int T) const {
     KParams P;
@@ -376,19 +387,22 @@ static size_t fused_smem_bytes(const sq_fdm *f, int mode, int S) {
     return slices * f->N * sizeof(double2);
 }
 
+// returns the number of CTAs (= p.Ap partials written for MODE 2)
 template <int MODE>
-static void launch_fused(sq_fdm *f, int S, int T, double2 *out, const double2 *in, double *part, const CgState *skip) {
+static int launch_fused(sq_fdm *f, int S, int T, double2 *out, const double2 *in, double *part, const CgState *skip) {
+    if (f->use_v3 && fdm_v3_supported(f, f->v3_S)) return fdm_v3_launch(f, MODE, f->v3_S, out, in, part, skip);
+    int grid = (f->slab_hi - f->slab_lo + S - 1) / S;
     if (f->use_v2 && fdm_v2_supported(f, MODE, S, T)) {
         fdm_v2_launch(f, MODE, S, T, out, in, part, skip);
-        return;
+        return grid;
     }
     if (T & (T - 1)) T = 1 << (31 - __builtin_clz(T));       // the generic kernel needs a power-of-two block
     KParams P = f->kparams(S, T);
     size_t smem = fused_smem_bytes(f, MODE, S);
-    int grid = (f->slab_hi - f->slab_lo + S - 1) / S;
     k_fdm_fused<MODE><<<grid, T, smem, f->stream>>>(P, out, in, part, skip);
     SQ_LAUNCH_CHECK();
     f->launches++;
+    return grid;
 }
 
 void fdm_sweep_global(sq_fdm *f, double2 *u, int lo, int hi, bool inverse) {
@@ -454,8 +468,8 @@ void fdm_mul_dev(sq_fdm *f, int op, double2 *out, const double2 *in, double *pAp
         fdm_select_tuning(f);
         int S = f->slab, T = f->threads;
         if (op == 2) {
-            launch_fused<2>(f, S, T, out, src, pAp_partials, skip);
-            if (npart) *npart = (f->slab_hi - f->slab_lo + S - 1) / S;
+            int g = launch_fused<2>(f, S, T, out, src, pAp_partials, skip);
+            if (npart) *npart = g;
         } else if (op == 0) launch_fused<0>(f, S, T, out, src, nullptr, skip);
         else if (op == 1) launch_fused<1>(f, S, T, out, src, nullptr, skip);
         else {
@@ -544,24 +558,47 @@ static void fdm_autotune(sq_fdm *f) {
             if (ms < best) { best = ms; bS = S; bT = T; bV = cd.second; }
         }
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     f->slab = bS;
     f->threads = bT;
     f->use_v2 = bV;
+    // register path (fdm_v3.cu): slices per CTA
+    f->use_v3 = 0;
+    const char *env3 = getenv("SQ_V3");
+    if (!(env3 && atoi(env3) == 0) && fdm_v3_supported(f, 1)) {
+        int b3 = 0;
+        float best3 = 1e30f;
+        const char *envS3 = getenv("SQ_V3_SLAB");
+        for (int S3 = 1; S3 <= 7; S3++) {
+            if (envS3 && atoi(envS3) != S3) continue;
+            if (!fdm_v3_supported(f, S3)) continue;
+            for (int rep = 0; rep < 2; rep++) fdm_v3_launch(f, 2, S3, f->io2.p, f->io1.p, nullptr, nullptr);
+            SQ_CUDA(cudaEventRecord(e0, f->stream));
+            for (int rep = 0; rep < 5; rep++) fdm_v3_launch(f, 2, S3, f->io2.p, f->io1.p, nullptr, nullptr);
+            SQ_CUDA(cudaEventRecord(e1, f->stream));
+            SQ_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            SQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (ms < best3) { best3 = ms; b3 = S3; }
+        }
+        if (b3 && (best3 < best || (env3 && atoi(env3) == 2))) { f->use_v3 = 1; f->v3_S = b3; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
 }
 
 // (slab, threads, kernel) are tuned separately for tau-dependent and tau-uniform hoppings, lazily on first use
 void fdm_select_tuning(sq_fdm *f) {
     if (f->path != 0 || f->manual_tuning) return;
-    int u = f->cs_uniform ? 1 : 0;
+    int u = f->cs_uniform ? (f->cs_coluni ? 2 : 1) : 0;
     if (!f->tuned[u][0]) {
         i64 keep = f->launches;
         fdm_autotune(f);
         f->launches = keep;
         f->tuned[u][0] = 1; f->tuned[u][1] = f->slab; f->tuned[u][2] = f->threads; f->tuned[u][3] = f->use_v2;
+        f->tuned[u][4] = f->use_v3; f->tuned[u][5] = f->v3_S;
     }
     f->slab = f->tuned[u][1]; f->threads = f->tuned[u][2]; f->use_v2 = f->tuned[u][3];
+    f->use_v3 = f->tuned[u][4]; f->v3_S = f->tuned[u][5] ? f->tuned[u][5] : 3;
 }
 
 void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt, const i64 *perm, i64 C,
@@ -616,6 +653,7 @@ void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt,
             }
         }
         SQ_REQUIRE(expect == Nh, "colour ranges do not cover all bonds");
+        fdm_v3_detect(f);
         // Shared-memory slots (fast path): the two sites of colour-0 bond b get slots b and nb0 + b, sites colour 0
         // does not touch follow; the bonds of every other colour are then re-ordered by the slot of their first
         // site.  Bonds of one colour commute, so any order inside a colour gives the same operator; the internal
@@ -669,7 +707,7 @@ void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt,
         f->cs.upload(cs1.data(), (size_t)L * Nh, f->stream);
         SQ_CUDA(cudaStreamSynchronize(f->stream));
         fdm_autotune(f);              // decides path 0 / 1; the per-mode tuning itself is refined lazily
-        if (f->path == 0) { f->tuned[0][0] = 1; f->tuned[0][1] = f->slab; f->tuned[0][2] = f->threads; f->tuned[0][3] = f->use_v2; }
+        if (f->path == 0) { f->tuned[0][0] = 1; f->tuned[0][1] = f->slab; f->tuned[0][2] = f->threads; f->tuned[0][3] = f->use_v2; f->tuned[0][4] = 0; f->tuned[0][5] = 3; }
         f->launches = 0;
         SQ_CUDA(cudaStreamSynchronize(f->stream));
     } catch (...) {
@@ -706,13 +744,17 @@ void fdm_update_impl(sq_fdm *f, const double *V, const double *t, double dtau) {
     fdm_update_dev(f, f->iod1.p, f->iod2.p, dtau);
     // tau-independent hoppings enable the register-resident coefficient path of the fast kernel
     if (!f->flag.p) f->flag.alloc(4);
-    SQ_CUDA(cudaMemsetAsync(f->flag.p, 0, sizeof(int), f->stream));
+    SQ_CUDA(cudaMemsetAsync(f->flag.p, 0, 4 * sizeof(int), f->stream));
     size_t nT = (size_t)f->L * f->Nh;
-    if (nT) k_cs_nonuniform<<<(unsigned)((nT + 255) / 256), 256, 0, f->stream>>>(f->cs.p, (int)f->L, (int)f->Nh, f->flag.p);
-    int nonuni = 0;
-    SQ_CUDA(cudaMemcpyAsync(&nonuni, f->flag.p, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
+    ColRanges cr;
+    cr.C = (int)f->C;
+    for (int c = 0; c < SQ_MAXC; c++) { cr.lo[c] = c < f->C ? f->clo[c] : 0; cr.hi[c] = c < f->C ? f->chi[c] : 0; }
+    if (nT) k_cs_nonuniform<<<(unsigned)((nT + 255) / 256), 256, 0, f->stream>>>(f->cs.p, (int)f->L, (int)f->Nh, f->flag.p, cr);
+    int nonuni[4] = {0, 0, 0, 0};
+    SQ_CUDA(cudaMemcpyAsync(nonuni, f->flag.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, f->stream));
     SQ_CUDA(cudaStreamSynchronize(f->stream));
-    f->cs_uniform = nonuni ? 0 : 1;
+    f->cs_uniform = nonuni[0] ? 0 : 1;
+    f->cs_coluni = (f->cs_uniform && !nonuni[2] && nT) ? 1 : 0;
 }
 
 void fdm_get_coefficients_impl(sq_fdm *f, double *expV, double *ch, double *sh) {

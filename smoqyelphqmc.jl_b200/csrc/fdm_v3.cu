@@ -1,0 +1,1423 @@
+// fdm_v3.cu -- K1 register path: fused M / M^T / M^T M for rectangular lattices.  One warp holds one part (real or
+// imaginary) of one time slice in registers; no shared-memory round trips and no barriers inside the checkerboard sweeps.
+//
+// ncu on the shared-memory kernels (fdm.cu, fdm_v2.cu; profiles/r1_ncu_k_fdm_fused_v2_uniform_cfg4.txt) showed the fused
+// matvec bound by the shared-memory crossbar and by one CTA-wide barrier per colour step: every colour step moves every
+// site through shared memory (2C-1 = 7 round trips per propagator, ~450 B of crossbar traffic per site for 72 B of HBM
+// traffic).  On a rectangular Lx x Ly lattice with the (x-even, x-odd, y-even, y-odd) checkerboard that traffic is
+// unnecessary.  The hopping coefficients are real, so B never mixes the real and the imaginary part of a vector: the two
+// parts are independent problems (blockIdx.y).  A warp holds its part of one slice for the whole kernel:
+//
+//     lane = xl + LXL * yq                     xl : which group of 4 consecutive x      (LXL = Lx / 4 groups)
+//                                              yq : which block of RY consecutive rows  (32 / LXL blocks)
+//     v[r][j]  (RY x 4 doubles per lane)       site x = 4 xl + j,  y = RY yq + r
+//
+// so that x-even and y-even bonds are lane-local, x-odd bonds need one shuffle per 2 sites and y-odd bonds shuffle only
+// the two boundary rows of the lane's row block.  A propagator B = Gamma D Gamma^T is 8 colour steps + the diagonal, all
+// in registers; what remains is FP64 issue (2 instructions per site and part per colour step; measured on B200:
+// 64 FP64 lanes/clk/SM, latency 8.6 clk, tools/ubench/fp64_rate.cu) plus ~100 warp shuffles per slice and part.
+//
+// CTA = S+1 warps (x) one part.  Warp k loads v[l0-1+k], applies B_{l0+k}, forms w[l0+k] = v[l0+k] -/+ (.) (|w|^2 partial
+// = p.Ap), publishes w to shared memory (the only shared-memory traffic: one 8-byte store and one load per site and
+// part), applies B_{l0+k} again (B is symmetric for the symmetric propagator) and writes
+// out[l0+k-1] = w[l0+k-1] -/+ B_{l0+k} w[l0+k].  One HBM pass, as in the other fused kernels, and the same
+// floating-point expression per site (fma(s, other, c * self)), so the result is bit-identical to fdm.cu / fdm_v2.cu.
+// ~110 registers per thread: several CTAs per SM, so one warp's load latency hides behind another's arithmetic.
+//
+// Requirements (checked by fdm_v3_detect / fdm_v3_supported, otherwise the shared-memory kernels run): symmetric
+// propagator, natural site order i = x + Lx y, colour c is bond class c (x-even, x-odd, y-even, y-odd), and the
+// (cosh, sinh) of all bonds of one colour are equal and tau-independent (any Holstein-type model with uniform hopping).
+#include "sq_internal.h"
+
+#include <algorithm>
+#include <cstring>
+
+struct V3Params {
+    int L, lb, le, S, C;
+    int nphase;             // 2 for M^T M, 1 otherwise (a kernel parameter so that the phase loop stays a loop: one copy of B in the code)
+    int cls[4];             // bond class of colour c: 0 x-even, 1 x-odd, 2 y-even, 3 y-odd
+    int clo[4];
+    const double2 *cs;      // (cosh, sinh) of colour c = cs[clo[c]]
+    const double *expV;     // [l][i]
+    const double *expVn;    // native order (NAT kernels)
+    long long *dbg;         // optional clock stamps of warp 1 of CTA 0 (profiling aid, NULL in production)
+    // CG fusion, same meaning as K2Params (fdm_v2.cu)
+    const double2 *cg_d;
+    double2 *cg_pnew;
+    const CgState *cg_cur;
+    CgState *cg_nxt;
+    const double *cg_rr_part, *cg_beta_part;
+    int cg_nrr, cg_nbeta, cg_beta_complex, cg_iter, cg_check;
+};
+
+// SC = 0: the reference expression a' = c a + s b (bit-identical to fdm.cu / fdm_v2.cu).
+// SC = 1: a' = a + t b with t = s / c; the factor c is the same for every bond of the colour and every site is touched by
+// every colour (perfect matchings), so the product of all c^2 is a global scalar folded into the native copy of
+// exp(-dtau V) -- one dependent-free DFMA per site and colour step instead of DMUL + DFMA (results differ at 1e-16).
+template <int SC>
+__device__ __forceinline__ void rot1(double &a, double &b, double c, double s) {
+    if (SC) {
+        const double na = fma(s, b, a), nb = fma(s, a, b);
+        a = na;
+        b = nb;
+    } else {
+        const double na = fma(s, b, c * a), nb = fma(s, a, c * b);
+        a = na;
+        b = nb;
+    }
+}
+template <int SC>
+__device__ __forceinline__ double rot_half(double self, double other, double c, double s) {
+    return SC ? fma(s, other, self) : fma(s, other, c * self);
+}
+
+template <int LXL, int RY>
+struct V3Lane {
+    static constexpr int YH = 32 / LXL, LX = 4 * LXL, LY = RY * YH, N = LX * LY;
+    int xl, part, yh;
+    int lane_r, lane_l, lane_u, lane_d;
+    int site0;              // site of v[0][0]; v[r][j] is site0 + LX r + j
+    double cc[4], ss[4];    // per colour: cosh, sinh (scaled rotations: ss = tanh)
+
+    template <int SC>
+    __device__ __forceinline__ void init(const V3Params &P, int part_) {
+        const int lane = threadIdx.x & 31;
+        xl = lane % LXL;
+        part = part_;
+        yh = lane / LXL;
+        lane_r = lane - xl + (xl + 1) % LXL;
+        lane_l = lane - xl + (xl + LXL - 1) % LXL;
+        lane_u = xl + LXL * ((yh + 1) % YH);
+        lane_d = xl + LXL * ((yh + YH - 1) % YH);
+        site0 = LX * RY * yh + 4 * xl;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double2 q = __ldg(P.cs + P.clo[c]);
+            cc[c] = q.x; ss[c] = SC ? q.y / q.x : q.y;
+        }
+    }
+
+    template <int CL, int SC>
+    __device__ __forceinline__ void step(double (&v)[RY][4]) const {
+        const double c = cc[CL], s = ss[CL];
+        if (CL == 0) {                                            // x-even: (0,1), (2,3) inside the lane
+#pragma unroll
+            for (int r = 0; r < RY; r++) { rot1<SC>(v[r][0], v[r][1], c, s); rot1<SC>(v[r][2], v[r][3], c, s); }
+        } else if (CL == 1) {                                     // x-odd: (1,2) inside, (3 | 0 of the right neighbour)
+#pragma unroll
+            for (int r = 0; r < RY; r++) {
+                const double fromR = __shfl_sync(0xffffffffu, v[r][0], lane_r);
+                const double fromL = __shfl_sync(0xffffffffu, v[r][3], lane_l);
+                rot1<SC>(v[r][1], v[r][2], c, s);
+                v[r][3] = rot_half<SC>(v[r][3], fromR, c, s);
+                v[r][0] = rot_half<SC>(v[r][0], fromL, c, s);
+            }
+        } else if (CL == 2) {                                     // y-even: rows (2k, 2k+1)
+#pragma unroll
+            for (int r = 0; r < RY; r += 2)
+#pragma unroll
+                for (int j = 0; j < 4; j++) rot1<SC>(v[r][j], v[r + 1][j], c, s);
+        } else {                                                  // y-odd: rows (2k+1, 2k+2), block boundary by shuffle
+            if (YH > 1) {
+                double up[4], dn[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    up[j] = __shfl_sync(0xffffffffu, v[0][j], lane_u);
+                    dn[j] = __shfl_sync(0xffffffffu, v[RY - 1][j], lane_d);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    v[RY - 1][j] = rot_half<SC>(v[RY - 1][j], up[j], c, s);
+                    v[0][j] = rot_half<SC>(v[0][j], dn[j], c, s);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) rot1<SC>(v[RY - 1][j], v[0][j], c, s);
+            }
+#pragma unroll
+            for (int r = 1; r + 1 < RY; r += 2)
+#pragma unroll
+                for (int j = 0; j < 4; j++) rot1<SC>(v[r][j], v[r + 1][j], c, s);
+        }
+    }
+
+    // v <- B_l v,  B = Gamma D Gamma^T: colours 3, 2, 1, 0, D, 0, 1, 2, 3 (colour c == bond class c, checked at create)
+    template <int NAT>
+    __device__ __forceinline__ void apply_B(double (&v)[RY][4], int l, const V3Params &P) const {
+        // NAT: exp(-dtau V) x prod_c cosh_c^2 in the native order [l][r][j/2][lane][j%2] (one coalesced 16-byte load per two
+        // sites), and the scaled rotations (rot1<1>)
+        const double *ev = NAT ? P.expVn + (size_t)l * N + 2 * (threadIdx.x & 31) : P.expV + (size_t)l * N + site0;
+        step<3, NAT>(v); step<2, NAT>(v); step<1, NAT>(v); step<0, NAT>(v);
+#pragma unroll
+        for (int r = 0; r < RY; r++) {
+            const double2 e01 = __ldg((const double2 *)(ev + (NAT ? 128 * r : LX * r))), e23 = __ldg((const double2 *)(ev + (NAT ? 128 * r + 64 : LX * r + 2)));
+            v[r][0] *= e01.x; v[r][1] *= e01.y; v[r][2] *= e23.x; v[r][3] *= e23.y;
+        }
+        step<0, NAT>(v); step<1, NAT>(v); step<2, NAT>(v); step<3, NAT>(v);
+    }
+};
+
+// NAT = 1: all vectors (in, out, cg_d, cg_pnew) are in the NATIVE order of this kernel -- slice l, part q, then
+// [r][j/2][lane][j%2] doubles -- so that every load / store is one fully coalesced 16-byte access per lane.  The CG solver
+// keeps its vectors in this order for the whole solve (cg.cu); the order is converted once on entry and once on exit.
+template <int MODE, int FUSE, int NAT, int LXL, int RY>
+__global__ void __launch_bounds__(256, RY <= 8 ? 2 : 1)
+k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const double2 *__restrict__ in,
+         double *__restrict__ pAp_part, const CgState *__restrict__ skip) {
+    typedef V3Lane<LXL, RY> G;
+    constexpr int N = G::N, LX = G::LX;
+    extern __shared__ double wsm[];                     // [S][RY][4][32] (this CTA's part)
+    __shared__ double red[32];
+    if (skip && skip->done) {
+        if (FUSE && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.cg_nxt = *skip;
+        return;
+    }
+#define V3_STAMP(q) do { if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32) P.dbg[q] = clock64(); } while (0)
+    V3_STAMP(0);
+    G E;
+    E.template init<NAT>(P, blockIdx.y);
+    const int L = P.L;
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const int nper = (MODE == 2) ? P.S : P.S + 1;       // output slices per CTA
+    const int l0 = P.lb + blockIdx.x * nper;
+    const int ns = min(nper, P.le - l0);
+    double2 beta = make_double2(0.0, 0.0);
+    if (FUSE) {
+        __shared__ double sh[4];
+        const CgState st = *P.cg_cur;
+        if (threadIdx.x < 32) {
+            double rr = warp_sum_partials(P.cg_rr_part, P.cg_nrr);
+            double br = rr, bi = 0.0;
+            if (P.cg_beta_part != P.cg_rr_part) {
+                br = warp_sum_partials(P.cg_beta_part, P.cg_nbeta);
+                bi = P.cg_beta_complex ? warp_sum_partials(P.cg_beta_part + SQ_MAXPART, P.cg_nbeta) : 0.0;
+            }
+            if (threadIdx.x == 0) {
+                double eps = sqrt(rr) / st.normb;
+                int stop = 0;
+                if (P.cg_check) stop = (eps < st.tol) ? 1 : ((eps == eps) ? 0 : 2);
+                double2 b = cdiv(make_double2(br, bi), make_double2(st.rz_re, st.rz_im));
+                sh[0] = b.x; sh[1] = b.y; sh[2] = (double)stop;
+                if (blockIdx.x == 0 && blockIdx.y == 0) {
+                    CgState nx = st;
+                    if (P.cg_check) { nx.eps = eps; nx.iters = P.cg_iter - 1; nx.done = stop; }
+                    if (!stop) { nx.rz_re = br; nx.rz_im = bi; }
+                    *P.cg_nxt = nx;
+                }
+            }
+        }
+        __syncthreads();
+        if (sh[2] != 0.0) return;
+        beta = make_double2(sh[0], sh[1]);
+    }
+    // slices of this warp: propagate in[lin] with B_{lB}, combine with in[lself]
+    bool active;
+    int lin, lself, lB;
+    if (MODE == 2) { active = k <= ns; lin = l0 - 1 + k; lself = l0 + k; lB = l0 + k; }
+    else if (MODE == 0) { active = k < ns; lin = l0 + k - 1; lself = l0 + k; lB = l0 + k; }
+    else { active = k < ns; lin = l0 + k + 1; lself = l0 + k; lB = l0 + k + 1; }
+    lin = lin < 0 ? lin + L : (lin >= L ? lin - L : lin);
+    lB = lB >= L ? lB - L : lB;
+    lself = lself >= L ? lself - L : lself;
+    const double sg = (lB == 0) ? 1.0 : -1.0;
+    const int part = E.part;
+    const bool publish = (MODE == 2) && (k < ns);
+    double v[RY][4];
+    double acc = 0.0;
+    // two elements (r, 2 jp), (r, 2 jp + 1) of slice l, this CTA's part; with CG fusion the vector is p = d + beta * in
+    // formed on the fly (beta is real in the native-order solver: unpreconditioned CG)
+    auto off = [&](int l, int r, int jp) -> size_t {     // offset in doubles of the first of the two elements
+        if (NAT) return ((size_t)l * 2 + part) * N + ((r * 2 + jp) * 32 + lane) * 2;
+        return 2 * ((size_t)l * N + E.site0 + LX * r + 2 * jp) + part;
+    };
+    auto ld2 = [&](const double2 *src, size_t o) -> double2 {
+        const double *q = reinterpret_cast<const double *>(src) + o;
+        if (NAT) return *reinterpret_cast<const double2 *>(q);
+        return make_double2(q[0], q[2]);
+    };
+    auto st2 = [&](double2 *dst, size_t o, double a, double b) {
+        double *q = reinterpret_cast<double *>(dst) + o;
+        if (NAT) *reinterpret_cast<double2 *>(q) = make_double2(a, b);
+        else { q[0] = a; q[2] = b; }
+    };
+    auto load2 = [&](int l, int r, int jp) -> double2 {
+        const size_t o = off(l, r, jp);
+        if (!FUSE) return ld2(in, o);
+        if (NAT) {
+            const double2 a = ld2(in, o), d = ld2(P.cg_d, o);
+            return make_double2(__dadd_rn(d.x, __dmul_rn(beta.x, a.x)), __dadd_rn(d.y, __dmul_rn(beta.x, a.y)));
+        }
+        const size_t g = (size_t)l * N + E.site0 + LX * r + 2 * jp;
+        const double2 p0 = cadd(P.cg_d[g], cmul(beta, in[g])), p1 = cadd(P.cg_d[g + 1], cmul(beta, in[g + 1]));
+        return part ? make_double2(p0.y, p1.y) : make_double2(p0.x, p1.x);
+    };
+    const int nphase = (MODE == 2) ? P.nphase : 1;
+#pragma unroll 1
+    for (int ph = 0; ph < nphase; ph++) {
+        int phase = ph;
+        asm volatile("" : "+r"(phase));                  // opaque: keeps the compiler from peeling the loop into two copies of B
+        const bool work = active && (phase == 0 || k >= 1);
+        if (work) {
+            if (phase == 0) {
+#pragma unroll
+                for (int r = 0; r < RY; r++)
+#pragma unroll
+                    for (int jp = 0; jp < 2; jp++) {
+                        const double2 q = load2(lin, r, jp);
+                        v[r][2 * jp] = q.x; v[r][2 * jp + 1] = q.y;
+                    }
+                if (P.dbg) { double t = 0; for (int r = 0; r < RY; r++) t += v[r][0]; if (t == 1.2345e300) P.dbg[15] = 1; }   // wait for the loads
+                V3_STAMP(1);
+            }
+            E.template apply_B<NAT>(v, lB, P);
+            if (P.dbg) { double t = 0; for (int r = 0; r < RY; r++) t += v[r][0]; if (t == 1.2345e300) P.dbg[15] = 1; }
+            V3_STAMP(2 + 3 * phase);
+        }
+        if (phase == 0) {
+            if (work) {
+#pragma unroll
+                for (int r = 0; r < RY; r++) {
+#pragma unroll
+                    for (int jp = 0; jp < 2; jp++) {
+                        const double2 self = load2(lself, r, jp);
+                        const double w0 = fma(sg, v[r][2 * jp], self.x), w1 = fma(sg, v[r][2 * jp + 1], self.y);
+                        if (MODE == 2) {
+                            v[r][2 * jp] = w0; v[r][2 * jp + 1] = w1;
+                            if (publish) {
+                                acc += w0 * w0;
+                                acc += w1 * w1;
+                                reinterpret_cast<double2 *>(wsm)[((k * RY + r) * 2 + jp) * 32 + lane] = make_double2(w0, w1);
+                                if (FUSE) st2(P.cg_pnew, off(lself, r, jp), self.x, self.y);
+                            }
+                        } else {
+                            st2(out, off(lself, r, jp), w0, w1);
+                        }
+                    }
+                }
+            }
+            V3_STAMP(3);
+        } else {
+            __syncthreads();
+            V3_STAMP(6);
+            if (work) {
+                const int lo = l0 + k - 1;                  // < le <= L: no wrap
+#pragma unroll
+                for (int r = 0; r < RY; r++)
+#pragma unroll
+                    for (int jp = 0; jp < 2; jp++) {
+                        const double2 w = reinterpret_cast<const double2 *>(wsm)[(((k - 1) * RY + r) * 2 + jp) * 32 + lane];
+                        st2(out, off(lo, r, jp), fma(sg, v[r][2 * jp], w.x), fma(sg, v[r][2 * jp + 1], w.y));
+                    }
+            }
+        }
+    }
+    V3_STAMP(7);
+    if (MODE == 2 && pAp_part) {
+        double a[1] = {acc};
+        block_sum<1>(a, red);
+        if (threadIdx.x == 0) pAp_part[blockIdx.x + gridDim.x * blockIdx.y] = a[0];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent cooperative CG on the register path: the whole unpreconditioned solve in ONE launch.
+//
+// Back-to-back dependent launches on this system are paced in ~2 us steps and every launch re-pays the load latency of a
+// single-wave kernel, so the solver keeps every CTA resident and iterates
+//     p = r + beta p_old formed on load (own + halo slice), B, w = M p (|w|^2 partial), B, z = M^T w kept in REGISTERS
+//     -> [grid barrier] -> alpha -> x += alpha p, r -= alpha z (own slices), |r|^2 partial -> [grid barrier] -> eps, beta
+// with all vectors in the native order (coalesced 16-byte accesses) and two grid-wide barriers per iteration (an
+// arrival counter in L2).  Reductions are fixed-order sums of per-CTA partials: bit-reproducible run to run.  Vectors
+// written by other CTAs are read with ld.global.cg.  A watchdog turns a barrier that does not complete into an error.
+// ---------------------------------------------------------------------------------------------------
+struct CgPersist3 {
+    double *x, *r, *p0, *p1;    // native order
+    CgState *state;             // in: rz (= |r0|^2), normb, tol, eps ; out: iters, eps, done
+    double *part_a, *part_b;    // per-CTA partials (p.Ap, |r|^2)
+    unsigned int *barrier;      // arrival counter (zeroed by the host)
+    int *abort_flag;
+    int maxiter;
+    unsigned int slot_stride;   // distance between the grid-sum slots of consecutive CTAs in 16-byte units (spreads them over L2 slices)
+};
+
+__device__ __forceinline__ bool v3_grid_barrier(unsigned int *counter, unsigned int &epoch, unsigned int nblk, int *abort_flag) {
+    __syncthreads();
+    epoch++;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const unsigned int target = epoch * nblk;
+        long long t0 = clock64();
+        while (true) {
+            unsigned int v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            if (v >= target) break;
+            if (clock64() - t0 > 4000000000LL) { atomicExch(abort_flag, 1); break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    return *((volatile int *)abort_flag) == 0;
+}
+
+template <int LXL, int RY>
+__global__ void __launch_bounds__(256, RY <= 8 ? 2 : 1)
+k_cg_v3_persistent(const __grid_constant__ V3Params P, const CgPersist3 C) {
+    typedef V3Lane<LXL, RY> G;
+    constexpr int N = G::N;
+    extern __shared__ double wsm[];
+    __shared__ double red[32];
+    __shared__ double sh[2];
+    G E;
+    E.template init<1>(P, blockIdx.y);
+    const int L = P.L;
+    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const int l0 = P.lb + blockIdx.x * P.S;
+    const int ns = min(P.S, P.le - l0);
+    const unsigned int nblk = gridDim.x * gridDim.y, bid = blockIdx.x + gridDim.x * blockIdx.y;
+    const bool active = k <= ns, owner = active && k >= 1, publish = k < ns;
+    int lin = l0 - 1 + k, lself = l0 + k;
+    lin = lin < 0 ? lin + L : lin;
+    lself = lself >= L ? lself - L : lself;
+    const int lB = lself, lo = l0 + k - 1;
+    const double sg = (lB == 0) ? 1.0 : -1.0;
+    const size_t o_in = ((size_t)lin * 2 + E.part) * N + 2 * lane, o_self = ((size_t)lself * 2 + E.part) * N + 2 * lane;
+    const size_t o_own = ((size_t)(lo < 0 ? 0 : lo) * 2 + E.part) * N + 2 * lane;
+    const double normb = C.state->normb, tol = C.state->tol;
+    double rz = C.state->rz_re, beta = 0.0, eps = C.state->eps;
+    unsigned int epoch = 0;
+    int it = 0, done = 0, pc = 0;
+    double v[RY][4];
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = 0;
+    const bool stamp = P.dbg && bid == 0 && threadIdx.x == 32;
+#define V3P_STAMP(q) do { if (stamp) { long long tn = clock64(); tacc[q] += tn - tprev; tprev = tn; } } while (0)
+    if (stamp) tprev = clock64();
+    auto ldcg2 = [](const double *q) -> double2 { return __ldcg(reinterpret_cast<const double2 *>(q)); };
+#pragma unroll 1
+    while (it < C.maxiter) {
+        it++;
+        const double *p_old = pc ? C.p1 : C.p0;
+        double *p_new = pc ? C.p0 : C.p1;
+        double acc = 0.0;
+        if (active) {
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const int e = (r * 2 + jp) * 64;
+                    const double2 rv = ldcg2(C.r + o_in + e), pv = ldcg2(p_old + o_in + e);
+                    v[r][2 * jp] = fma(beta, pv.x, rv.x);
+                    v[r][2 * jp + 1] = fma(beta, pv.y, rv.y);
+                }
+            E.template apply_B<1>(v, lB, P);
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const int e = (r * 2 + jp) * 64;
+                    const double2 rv = ldcg2(C.r + o_self + e), pv = ldcg2(p_old + o_self + e);
+                    const double s0 = fma(beta, pv.x, rv.x), s1 = fma(beta, pv.y, rv.y);
+                    const double w0 = fma(sg, v[r][2 * jp], s0), w1 = fma(sg, v[r][2 * jp + 1], s1);
+                    v[r][2 * jp] = w0; v[r][2 * jp + 1] = w1;
+                    if (publish) {
+                        acc += w0 * w0;
+                        acc += w1 * w1;
+                        reinterpret_cast<double2 *>(wsm)[((k * RY + r) * 2 + jp) * 32 + lane] = make_double2(w0, w1);
+                        *reinterpret_cast<double2 *>(p_new + o_self + e) = make_double2(s0, s1);
+                    }
+                }
+        }
+        V3P_STAMP(0);
+        if (owner) E.template apply_B<1>(v, lB, P);
+        __syncthreads();
+        if (owner) {                                      // z[lo] = w[lo] -/+ B w[lo + 1], stays in registers
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 w = reinterpret_cast<const double2 *>(wsm)[(((k - 1) * RY + r) * 2 + jp) * 32 + lane];
+                    v[r][2 * jp] = fma(sg, v[r][2 * jp], w.x);
+                    v[r][2 * jp + 1] = fma(sg, v[r][2 * jp + 1], w.y);
+                }
+        }
+        {
+            double a[1] = {acc};
+            block_sum<1>(a, red);
+            if (threadIdx.x == 0) C.part_a[bid] = a[0];
+        }
+        V3P_STAMP(1);
+        if (!v3_grid_barrier(C.barrier, epoch, nblk, C.abort_flag)) { done = 3; break; }
+        if (threadIdx.x < 32) {
+            double t = 0.0;
+            for (unsigned int q = threadIdx.x; q < nblk; q += 32) t += __ldcg(C.part_a + q);
+            t = warp_sum(t);
+            if (threadIdx.x == 0) sh[0] = t;
+        }
+        __syncthreads();
+        V3P_STAMP(2);
+        const double alpha = rz / sh[0];
+        acc = 0.0;
+        if (owner) {                                      // x += alpha p ; r -= alpha z ; |r|^2 partial  (slice lo)
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const int e = (r * 2 + jp) * 64;
+                    const double2 pv = ldcg2(p_new + o_own + e), xv = ldcg2(C.x + o_own + e), rv = ldcg2(C.r + o_own + e);
+                    const double r0 = fma(-alpha, v[r][2 * jp], rv.x), r1 = fma(-alpha, v[r][2 * jp + 1], rv.y);
+                    *reinterpret_cast<double2 *>(C.x + o_own + e) = make_double2(fma(alpha, pv.x, xv.x), fma(alpha, pv.y, xv.y));
+                    *reinterpret_cast<double2 *>(C.r + o_own + e) = make_double2(r0, r1);
+                    acc += r0 * r0;
+                    acc += r1 * r1;
+                }
+        }
+        {
+            double a[1] = {acc};
+            block_sum<1>(a, red);
+            if (threadIdx.x == 0) C.part_b[bid] = a[0];
+        }
+        V3P_STAMP(3);
+        if (!v3_grid_barrier(C.barrier, epoch, nblk, C.abort_flag)) { done = 3; break; }
+        if (threadIdx.x < 32) {
+            double t = 0.0;
+            for (unsigned int q = threadIdx.x; q < nblk; q += 32) t += __ldcg(C.part_b + q);
+            t = warp_sum(t);
+            if (threadIdx.x == 0) sh[1] = t;
+        }
+        __syncthreads();
+        V3P_STAMP(4);
+        const double rr = sh[1];
+        eps = sqrt(rr) / normb;
+        if (eps < tol) { done = 1; break; }
+        if (!(eps == eps)) { done = 2; break; }
+        beta = rr / rz;
+        rz = rr;
+        pc ^= 1;
+    }
+    if (stamp) { for (int q = 0; q < 5; q++) P.dbg[q] = tacc[q]; P.dbg[5] = it; }
+    if (bid == 0 && threadIdx.x == 0) {
+        CgState st = *C.state;
+        st.iters = it;
+        st.eps = eps;
+        st.done = done;
+        st.rz_re = rz;
+        *C.state = st;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef void (*v3_kernel_t)(const V3Params, double2 *, const double2 *, double *, const CgState *);
+
+template <int LXL, int RY>
+static v3_kernel_t pick_mode(int mode) {       // mode 3: M^T M with the CG p update fused into the load; +4: native order
+    switch (mode) {
+        case 0: return k_fdm_v3<0, 0, 0, LXL, RY>;
+        case 1: return k_fdm_v3<1, 0, 0, LXL, RY>;
+        case 2: return k_fdm_v3<2, 0, 0, LXL, RY>;
+        case 3: return k_fdm_v3<2, 1, 0, LXL, RY>;
+        case 6: return k_fdm_v3<2, 0, 1, LXL, RY>;
+        case 7: return k_fdm_v3<2, 1, 1, LXL, RY>;
+    }
+    return nullptr;
+}
+static v3_kernel_t pick3(int lxl, int ry, int mode) {
+    if (lxl == 8 && ry == 4) return pick_mode<8, 4>(mode);        // 32 x 16
+    if (lxl == 8 && ry == 8) return pick_mode<8, 8>(mode);        // 32 x 32
+    if (lxl == 8 && ry == 16) return pick_mode<8, 16>(mode);      // 32 x 64
+    if (lxl == 4 && ry == 2) return pick_mode<4, 2>(mode);        // 16 x 16
+    if (lxl == 4 && ry == 4) return pick_mode<4, 4>(mode);        // 16 x 32
+    if (lxl == 4 && ry == 8) return pick_mode<4, 8>(mode);        // 16 x 64
+    return nullptr;
+}
+
+// Is the lattice an Lx x Ly periodic rectangle in natural site order whose 4 colours are the 4 bond classes?
+void fdm_v3_detect(sq_fdm *f) {
+    f->v3_ok = 0;
+    if (!f->sym || f->C != 4 || f->Nh != 2 * f->N) return;
+    for (int LX : {32, 16}) {
+        if (f->N % LX) continue;
+        const int LY = (int)(f->N / LX), LXL = LX / 4, YH = 32 / LXL;
+        if (LY % YH) continue;
+        const int RY = LY / YH;
+        if (RY % 2 || !pick3(LXL, RY, 2)) continue;
+        int cls[4];
+        bool ok = true, seen[4] = {false, false, false, false};
+        for (int c = 0; c < 4 && ok; c++) {
+            if (f->chi[c] - f->clo[c] != f->N / 2) { ok = false; break; }
+            int cl = -1;
+            for (int h = f->clo[c]; h < f->chi[c] && ok; h++) {
+                const int i = f->h_nt[h].x, j = f->h_nt[h].y;
+                const int xi = i % LX, yi = i / LX, xj = j % LX, yj = j / LX;
+                int b = -1;
+                if (yi == yj) {
+                    if ((xi + 1) % LX == xj) b = xi % 2;
+                    else if ((xj + 1) % LX == xi) b = xj % 2;
+                } else if (xi == xj) {
+                    if ((yi + 1) % LY == yj) b = 2 + yi % 2;
+                    else if ((yj + 1) % LY == yi) b = 2 + yj % 2;
+                }
+                if (b < 0 || (cl >= 0 && b != cl)) ok = false;
+                cl = b;
+            }
+            if (ok && (cl < 0 || seen[cl])) ok = false;
+            if (ok) { seen[cl] = true; cls[c] = cl; }
+        }
+        for (int c = 0; c < 4 && ok; c++) ok = (cls[c] == c);     // the kernels are written for the canonical colour order
+        if (!ok) continue;
+        f->v3_ok = 1; f->v3_lxl = LXL; f->v3_ry = RY;
+        for (int c = 0; c < 4; c++) f->v3_cls[c] = cls[c];
+        for (int mode : {0, 1, 2, 3, 6, 7})
+            SQ_CUDA(cudaFuncSetAttribute(pick3(LXL, RY, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        return;
+    }
+}
+
+bool fdm_v3_supported(const sq_fdm *f, int S) {
+    if (!f->v3_ok || !f->cs_coluni) return false;
+    if (S < 1 || S > 7) return false;
+    return (size_t)S * f->N * sizeof(double) <= f->smem_optin;
+}
+
+struct CgFuse3 {
+    const double2 *d; double2 *pnew; const CgState *cur; CgState *nxt;
+    const double *rr_part, *beta_part; int nrr, nbeta, beta_complex, iter, check;
+};
+static const CgFuse3 *g_fuse3 = nullptr;
+
+// returns the number of CTAs (= p.Ap partials for mode 2)
+int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native) {
+    V3Params P;
+    memset(&P, 0, sizeof(P));
+    if (g_fuse3) {
+        P.cg_d = g_fuse3->d; P.cg_pnew = g_fuse3->pnew; P.cg_cur = g_fuse3->cur; P.cg_nxt = g_fuse3->nxt;
+        P.cg_rr_part = g_fuse3->rr_part; P.cg_beta_part = g_fuse3->beta_part; P.cg_nrr = g_fuse3->nrr; P.cg_nbeta = g_fuse3->nbeta;
+        P.cg_beta_complex = g_fuse3->beta_complex; P.cg_iter = g_fuse3->iter; P.cg_check = g_fuse3->check;
+    }
+    P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = 4; P.nphase = (mode == 2) ? 2 : 1;
+    for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = f->clo[c]; }
+    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p;
+    static long long *dbg = nullptr;
+    if (!dbg && getenv("SQ_DEBUG_STAMPS")) {
+        SQ_CUDA(cudaMallocManaged((void **)&dbg, 16 * sizeof(long long)));
+        for (int q = 0; q < 16; q++) dbg[q] = 0;
+    }
+    P.dbg = dbg;
+    if (dbg && getenv("SQ_DEBUG_PRINT")) {
+        cudaStreamSynchronize(f->stream);
+        fprintf(stderr, "v3 stamps(cycles): init+load %lld B1 %lld combine %lld B2 %lld sync %lld store %lld total %lld\n", dbg[1] - dbg[0],
+                dbg[2] - dbg[1], dbg[3] - dbg[2], dbg[5] - dbg[3], dbg[6] - dbg[5], dbg[7] - dbg[6], dbg[7] - dbg[0]);
+    }
+    const int nper = (mode == 2) ? S : S + 1;
+    const int grid = (f->slab_hi - f->slab_lo + nper - 1) / nper;
+    const size_t smem = (mode == 2) ? (size_t)S * f->N * sizeof(double) : 0;
+    if (native) SQ_REQUIRE(mode == 2 && f->v3_expVn.p && f->v3_expv_version == f->coef_version, "native-order operator not prepared");
+    v3_kernel_t k = pick3(f->v3_lxl, f->v3_ry, ((mode == 2 && g_fuse3) ? 3 : mode) + (native ? 4 : 0));
+    k<<<dim3(grid, 2), 32 * (S + 1), smem, f->stream>>>(P, out, in, part, skip);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+    return 2 * grid;
+}
+
+int fdm_v3_launch_cg(sq_fdm *f, double2 *z, const double2 *p_old, double2 *p_new, const double2 *d, const CgState *cur, CgState *nxt,
+                     const double *rr_part, int nrr, const double *beta_part, int nbeta, int beta_complex, int iter, int check,
+                     double *pAp_part, bool native) {
+    CgFuse3 a = {d, p_new, cur, nxt, rr_part, beta_part, nrr, nbeta, beta_complex, iter, check};
+    g_fuse3 = &a;
+    int n = 0;
+    try {
+        n = fdm_v3_launch(f, 2, f->v3_S, z, p_old, pAp_part, cur, native);
+    } catch (...) { g_fuse3 = nullptr; throw; }
+    g_fuse3 = nullptr;
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Resident CG: as k_cg_v3_persistent, but nothing except two boundary slices per CTA touches global memory inside the
+// iteration.  The persistent kernel above measured 21 us per iteration at cfg4 although its arithmetic is ~3 us: 75 MB
+// of L2 traffic per iteration (r, p re-read for own + halo slices, x / r / p passes of the update) and two slow grid
+// barriers.  Here one CTA per SM owns S slices (both parts: 2 (S+1) warps) for the whole solve:
+//   * x and r of the warp's slice live in REGISTERS, p (own + 2 halo slices) and the w hand-over in SHARED memory;
+//   * the neighbours' halo p is rebuilt locally from their updated boundary r (written to a small global buffer before
+//     the second grid barrier, read after it): p_halo = r_halo + beta p_halo -- no extra synchronisation;
+//   * per iteration and CTA: 2 slice-parts x 2 written + read through L2 (~9 MB at cfg4 instead of ~75 MB).
+// ---------------------------------------------------------------------------------------------------
+// Grid-wide deterministic sum without atomics or a separate barrier: every CTA publishes (value, epoch) in its own 16-byte
+// slot (fence + relaxed store of the epoch), warp 0 of every CTA polls all slots for the epoch with relaxed loads that
+// bypass L1 and adds the values in a fixed order -- the same order in every CTA, so all CTAs get the same bits.  The
+// fence orders every earlier write of the CTA (cumulative through the preceding __syncthreads), so passing the sum also
+// publishes the boundary-r halo slices.  No L1 invalidation: shared data is only ever read with L2 loads.
+struct V3Slot { double v; unsigned long long e; };
+__device__ __forceinline__ double v3_grid_sum(double acc, double *red, double *sh_out, V3Slot *slots, unsigned int stride,
+                                              unsigned long long epoch, unsigned int nblk, unsigned int bid, bool &aborted) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    int bad = 0;
+    if (warp == 0) {
+        double t = lane < nw ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(&slots[(size_t)bid * stride]), "l"(__double_as_longlong(t)), "l"(epoch) : "memory");
+        }
+        // one 16-byte load returns (value, epoch) of a slot together; up to 8 slots per lane are in flight per polling round
+        double s = 0.0;
+        const long long t0 = clock64();
+        for (unsigned int base = 0; base < nblk; base += 256) {
+            long long val[8];
+            unsigned long long ep[8];
+            while (true) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {                     // all loads first: one L2 round trip per polling round
+                    const unsigned int q = base + lane + 32 * u;
+                    ep[u] = epoch;
+                    val[u] = 0;
+                    if (q < nblk) asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(val[u]), "=l"(ep[u]) : "l"(&slots[(size_t)q * stride]) : "memory");
+                }
+                bool ready = true;
+#pragma unroll
+                for (int u = 0; u < 8; u++) ready = ready && (ep[u] >= epoch);
+                if (ready) break;
+                if (clock64() - t0 > 4000000000LL) { bad = 1; break; }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) s += __longlong_as_double(val[u]);
+        }
+        s = warp_sum(s);
+        if (lane == 0) *sh_out = s;
+    }
+    aborted = __syncthreads_or(bad) != 0;
+    return *sh_out;
+}
+
+template <int LXL, int RY>
+__global__ void __launch_bounds__(256, 1)
+k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double *__restrict__ halo) {
+    typedef V3Lane<LXL, RY> G;
+    constexpr int N = G::N;
+    extern __shared__ double smem[];
+    __shared__ double red[32];
+    __shared__ double sh[2];
+    const int S = P.S, L = P.L;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int part = wid / (S + 1), k = wid - part * (S + 1);
+    G E;
+    E.template init<1>(P, part);
+    const int l0 = P.lb + blockIdx.x * S;
+    const int ns = min(S, P.le - l0);
+    const unsigned int nblk = gridDim.x, bid = blockIdx.x;
+    const bool active = k <= ns, owner = active && k >= 1, publish = k < ns;
+    int lself = l0 + k;
+    lself = lself >= L ? lself - L : lself;
+    const int lB = lself, lo = l0 + k - 1;               // owner: slice lo
+    const double sg = (lB == 0) ? 1.0 : -1.0;
+    double2 *Pb = reinterpret_cast<double2 *>(smem) + (size_t)part * (S + 2) * (N / 2);          // [q = 0 .. S+1][N/2]
+    double2 *W = reinterpret_cast<double2 *>(smem) + (size_t)2 * (S + 2) * (N / 2) + (size_t)part * S * (N / 2);
+    auto el = [&](int r, int jp) -> int { return (r * 2 + jp) * 32 + lane; };                    // double2 index inside a slice-part
+    auto gslice = [&](const double *base, int l) -> const double2 * { return reinterpret_cast<const double2 *>(base + ((size_t)l * 2 + part) * N); };
+    // halo buffer: [cta][side][part][N] doubles; side 0 = first own slice, 1 = last own slice
+    auto hslice = [&](unsigned int cta, int side) -> double2 * { return reinterpret_cast<double2 *>(halo + (((size_t)cta * 2 + side) * 2 + part) * N); };
+    const unsigned int left = (bid + nblk - 1) % nblk, right = (bid + 1) % nblk;
+    const double normb = C.state->normb, tol = C.state->tol;
+    double rz = C.state->rz_re, beta = 0.0, eps = C.state->eps;
+    unsigned int epoch = 0;
+    int it = 0, done = 0;
+    double v[RY][4], xr[RY][4], rr_[RY][4];
+#ifdef SQ_V3_STAMPS
+    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = 0;
+    const bool stamp = P.dbg && bid == 0 && threadIdx.x == 32;
+    if (stamp) tprev = clock64();
+#define V3R_STAMP(q) do { if (stamp) { long long tn = clock64(); tacc[q] += tn - tprev; tprev = tn; } } while (0)
+#else
+#define V3R_STAMP(q) do { } while (0)
+#endif
+    // ---- initial state: x, r of the own slice in registers; p = r for own + halo slices in shared memory
+    if (owner) {
+        const double2 *gx = gslice(C.x, lo), *gr = gslice(C.r, lo);
+#pragma unroll
+        for (int r = 0; r < RY; r++)
+#pragma unroll
+            for (int jp = 0; jp < 2; jp++) {
+                const double2 a = gx[el(r, jp)], b = gr[el(r, jp)];
+                xr[r][2 * jp] = a.x; xr[r][2 * jp + 1] = a.y;
+                rr_[r][2 * jp] = b.x; rr_[r][2 * jp + 1] = b.y;
+                Pb[(size_t)k * (N / 2) + el(r, jp)] = b;
+            }
+    }
+    if (active && (k == 0 || k == ns)) {
+        const int q = (k == 0) ? 0 : ns + 1;
+        int l = (k == 0) ? l0 - 1 : l0 + ns;
+        l = l < 0 ? l + L : (l >= L ? l - L : l);
+        const double2 *gr = gslice(C.r, l);
+        for (int e = lane; e < N / 2; e += 32) Pb[(size_t)q * (N / 2) + e] = gr[e];
+    }
+#pragma unroll 1
+    while (it < C.maxiter) {
+        it++;
+        __syncthreads();                                  // p of all slices (own + halo) is in Pb
+        double acc = 0.0;
+        if (active) {
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 a = Pb[(size_t)k * (N / 2) + el(r, jp)];
+                    v[r][2 * jp] = a.x; v[r][2 * jp + 1] = a.y;
+                }
+            E.template apply_B<1>(v, lB, P);
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 self = Pb[(size_t)(k + 1) * (N / 2) + el(r, jp)];
+                    const double w0 = fma(sg, v[r][2 * jp], self.x), w1 = fma(sg, v[r][2 * jp + 1], self.y);
+                    v[r][2 * jp] = w0; v[r][2 * jp + 1] = w1;
+                    if (publish) {
+                        acc += w0 * w0;
+                        acc += w1 * w1;
+                        W[(size_t)k * (N / 2) + el(r, jp)] = make_double2(w0, w1);
+                    }
+                }
+        }
+        V3R_STAMP(0);
+        if (owner) E.template apply_B<1>(v, lB, P);
+        __syncthreads();
+        if (owner) {                                      // z[lo] = w[lo] -/+ B w[lo + 1], stays in registers
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 w = W[(size_t)(k - 1) * (N / 2) + el(r, jp)];
+                    v[r][2 * jp] = fma(sg, v[r][2 * jp], w.x);
+                    v[r][2 * jp + 1] = fma(sg, v[r][2 * jp + 1], w.y);
+                }
+        }
+        V3R_STAMP(1);
+        bool aborted;
+        const double pAp = v3_grid_sum(acc, red, &sh[0], reinterpret_cast<V3Slot *>(C.part_a), C.slot_stride, (unsigned long long)it, nblk, bid, aborted);
+        if (aborted) { done = 3; break; }
+        V3R_STAMP(2);
+        const double alpha = rz / pAp;
+        acc = 0.0;
+        if (owner) {                                      // x += alpha p ; r -= alpha z ; |r|^2 partial ; boundary r -> halo buffer
+            double2 *h0 = (k == 1) ? hslice(bid, 0) : nullptr, *h1 = (k == ns) ? hslice(bid, 1) : nullptr;
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 pv = Pb[(size_t)k * (N / 2) + el(r, jp)];
+                    xr[r][2 * jp] = fma(alpha, pv.x, xr[r][2 * jp]);
+                    xr[r][2 * jp + 1] = fma(alpha, pv.y, xr[r][2 * jp + 1]);
+                    const double r0 = fma(-alpha, v[r][2 * jp], rr_[r][2 * jp]), r1 = fma(-alpha, v[r][2 * jp + 1], rr_[r][2 * jp + 1]);
+                    rr_[r][2 * jp] = r0; rr_[r][2 * jp + 1] = r1;
+                    acc += r0 * r0;
+                    acc += r1 * r1;
+                    if (h0) h0[el(r, jp)] = make_double2(r0, r1);
+                    if (h1) h1[el(r, jp)] = make_double2(r0, r1);
+                }
+        }
+        V3R_STAMP(3);
+        const double rr = v3_grid_sum(acc, red, &sh[1], reinterpret_cast<V3Slot *>(C.part_b), C.slot_stride, (unsigned long long)it, nblk, bid, aborted);
+        if (aborted) { done = 3; break; }
+        V3R_STAMP(4);
+        eps = sqrt(rr) / normb;
+        if (eps < tol) { done = 1; break; }
+        if (!(eps == eps)) { done = 2; break; }
+        beta = rr / rz;
+        rz = rr;
+        // p = r + beta p: own slice from registers, halo slices from the neighbours' boundary r
+        if (owner) {
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 pv = Pb[(size_t)k * (N / 2) + el(r, jp)];
+                    Pb[(size_t)k * (N / 2) + el(r, jp)] = make_double2(fma(beta, pv.x, rr_[r][2 * jp]), fma(beta, pv.y, rr_[r][2 * jp + 1]));
+                }
+        }
+        if (k == 0) {                                      // warp 0 owns no slice: it rebuilds both halo slices
+#pragma unroll 1
+            for (int side = 0; side < 2; side++) {
+                const int q = side ? ns + 1 : 0;
+                const double2 *h = side ? hslice(right, 0) : hslice(left, 1);
+#pragma unroll
+                for (int u = 0; u < N / 64; u++) {
+                    const int e = lane + 32 * u;
+                    const double2 rv = __ldcg(h + e), pv = Pb[(size_t)q * (N / 2) + e];
+                    Pb[(size_t)q * (N / 2) + e] = make_double2(fma(beta, pv.x, rv.x), fma(beta, pv.y, rv.y));
+                }
+            }
+        }
+        V3R_STAMP(5);
+    }
+    if (owner) {                                          // the solution
+        double2 *gx = reinterpret_cast<double2 *>(C.x + ((size_t)lo * 2 + part) * N);
+#pragma unroll
+        for (int r = 0; r < RY; r++)
+#pragma unroll
+            for (int jp = 0; jp < 2; jp++) gx[el(r, jp)] = make_double2(xr[r][2 * jp], xr[r][2 * jp + 1]);
+    }
+#ifdef SQ_V3_STAMPS
+    if (stamp) { for (int q = 0; q < 6; q++) P.dbg[q] = tacc[q]; P.dbg[6] = it; }
+#endif
+    if (bid == 0 && threadIdx.x == 0) {
+        CgState st = *C.state;
+        st.iters = it;
+        st.eps = eps;
+        st.done = done;
+        st.rz_re = rz;
+        *C.state = st;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Resident CG, ONE grid-wide sum per iteration.
+//
+// A grid-wide sum costs ~2.4 us on this two-die part (store -> L2 -> poll: several L2 trips), more than the whole
+// arithmetic of an iteration, and the textbook recurrence needs two of them (p.Ap, then |r_new|^2).  Both scalars follow
+// from quantities available BEFORE the first sum:
+//     a = |M p|^2 = p.Ap,   b = Re r.z,   c = |z|^2,   d = |r|^2        (z = A p, r the current residual)
+//     alpha = d / a,   |r - alpha z|^2 = d - 2 alpha b + alpha^2 c,   beta = |r_new|^2 / d
+// d is the exact norm of the stored residual, recomputed every iteration, so the estimate never feeds back into itself
+// (no drift); its rounding error is a few ulp of d, the same order as the error of the updated residual itself.  The
+// estimate drives beta and the stopping test; a positive stopping test (and the maxiter exit) is confirmed with the
+// exact |r_new|^2 (one extra sum, once per solve), so the returned eps is exact and the solver never stops early.
+// After the sum every warp updates x, r and forms p = r + beta p in one go; the boundary slices of the new p go to the
+// neighbours through a small global buffer guarded by per-CTA epoch flags (point to point, no second grid-wide sync).
+// ---------------------------------------------------------------------------------------------------
+struct V3Slot4 { V3Slot q[4]; };
+// sums acc[0..3] over the grid; result (same bits in every CTA) in sh_out[0..3].  See v3_grid_sum.
+#ifdef SQ_V3_STAMPS
+#define V3G_STAMP(q) do { if (tacc && threadIdx.x == 0) { long long tn = clock64(); tacc[q] += tn - *tprev; *tprev = tn; } } while (0)
+#else
+#define V3G_STAMP(q) do { } while (0)
+#endif
+__device__ __forceinline__ void v3_grid_sum4(const double (&acc_in)[4], double *red, double *sh_out, char *slots, unsigned int stride_bytes,
+                                             unsigned long long epoch, unsigned int nblk, unsigned int bid, bool &aborted,
+                                             long long *tacc = nullptr, long long *tprev = nullptr) {
+    // The batched polling loads are weak L2 loads (ld.global.cg): strong (ld.relaxed.gpu) loads of one warp are not pipelined
+    // by the hardware -- 17 of them per lane took ~7000 cycles per round instead of one L2 round trip.
+    // Slot q < nblk: the 4 partials of CTA q; slot nblk: the 4 totals.  CTA 0 alone polls the partial slots (134 pollers
+    // on 134 slots saturated L2: measured 11k cycles per sum) and publishes the totals, everybody else polls one line.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const double t = warp_sum(acc_in[c]);
+        if (lane == 0) red[c * 8 + warp] = t;
+    }
+    __syncthreads();
+    V3G_STAMP(3);
+    int bad = 0;
+    if (warp == 0) {
+        const long long t0 = clock64();
+        // the totals are replicated in 8 lines (different L2 slices); CTA q polls copy q % 8
+        V3Slot *total = reinterpret_cast<V3Slot4 *>(slots + (size_t)(nblk + (bid & 7)) * stride_bytes)->q;
+        double mine = 0.0;
+        if (lane < 4) {                                    // lane c handles component c of this CTA
+            for (int w = 0; w < nw; w++) mine += red[lane * 8 + w];
+            V3Slot *dst = reinterpret_cast<V3Slot4 *>(slots + (size_t)bid * stride_bytes)->q + lane;
+            if (bid != 0) asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(dst), "l"(__double_as_longlong(mine)), "l"(epoch) : "memory");
+        }
+        V3G_STAMP(4);
+        if (bid == 0) {
+            double s[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) s[c] = __shfl_sync(0xffffffffu, mine, c);      // CTA 0's own partials come first (in lane 0's sum)
+            if (lane != 0) { s[0] = 0.0; s[1] = 0.0; s[2] = 0.0; s[3] = 0.0; }
+            for (unsigned int base = 1; base < nblk; base += 128) {
+                long long val[4][4];
+                unsigned long long ep[4][4];
+                while (true) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const unsigned int q = base + lane + 32 * u;
+                        const V3Slot *sl = reinterpret_cast<const V3Slot4 *>(slots + (size_t)q * stride_bytes)->q;
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            ep[u][c] = epoch; val[u][c] = 0;
+                            if (q < nblk) asm volatile("ld.global.cg.v2.b64 {%0, %1}, [%2];" : "=l"(val[u][c]), "=l"(ep[u][c]) : "l"(sl + c) : "memory");
+                        }
+                    }
+                    bool ready = true;
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+#pragma unroll
+                        for (int c = 0; c < 4; c++) ready = ready && (ep[u][c] >= epoch);
+                    if (ready) break;
+                    if (clock64() - t0 > 4000000000LL) { bad = 1; break; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) s[c] += __longlong_as_double(val[u][c]);
+            }
+            double tot = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const double t = warp_sum(s[c]);
+                if (lane == c) tot = t;
+            }
+            if (lane < 4) sh_out[lane] = tot;
+            {                                              // lane -> (copy lane / 4, component lane % 4): one store instruction for all copies
+                const double tc = __shfl_sync(0xffffffffu, tot, lane & 3);
+                V3Slot *dst = reinterpret_cast<V3Slot4 *>(slots + (size_t)(nblk + (lane >> 2)) * stride_bytes)->q + (lane & 3);
+                asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(dst), "l"(__double_as_longlong(tc)), "l"(epoch) : "memory");
+            }
+        } else if (lane < 4) {
+            long long val = 0;
+            unsigned long long e = 0;
+            while (true) {
+                asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(val), "=l"(e) : "l"(total + lane) : "memory");
+                if (e >= epoch) break;
+                if (clock64() - t0 > 4000000000LL) { bad = 1; break; }
+            }
+            sh_out[lane] = __longlong_as_double(val);
+        }
+        V3G_STAMP(5);
+    }
+    aborted = __syncthreads_or(bad) != 0;
+    V3G_STAMP(6);
+}
+
+struct CgResident {
+    double *x;                  // native order, in: start vector, out: solution
+    const double *r;            // native order, initial residual
+    CgState *state;             // in: normb, tol, eps ; out: iters, eps, done
+    char *slots_main, *slots_check;
+    unsigned int slot_stride;   // bytes
+    double *halo;               // [cta][side][part][N] boundary slices of p
+    unsigned long long *flags;  // [cta] epoch of the halo slices
+    int maxiter;
+};
+
+template <int LXL, int RY>
+__global__ void __launch_bounds__(256, 1)
+k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident C) {
+    typedef V3Lane<LXL, RY> G;
+    constexpr int N = G::N;
+    extern __shared__ double smem[];
+    __shared__ double red[32];
+    __shared__ double sh[4];
+    const int S = P.S, L = P.L;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int part = wid / (S + 1), k = wid - part * (S + 1);
+    G E;
+    E.template init<1>(P, part);
+    const int l0 = P.lb + blockIdx.x * S;
+    const int ns = min(S, P.le - l0);
+    const unsigned int nblk = gridDim.x, bid = blockIdx.x;
+    const bool active = k <= ns, owner = active && k >= 1, publish = k < ns;
+    int lself = l0 + k;
+    lself = lself >= L ? lself - L : lself;
+    const int lB = lself, lo = l0 + k - 1;               // owner: slice lo
+    const double sg = (lB == 0) ? 1.0 : -1.0;
+    double2 *Pb = reinterpret_cast<double2 *>(smem) + (size_t)part * (S + 2) * (N / 2);          // [q = 0 .. S+1][N/2]
+    double2 *W = reinterpret_cast<double2 *>(smem) + (size_t)2 * (S + 2) * (N / 2) + (size_t)part * S * (N / 2);
+    auto el = [&](int r, int jp) -> int { return (r * 2 + jp) * 32 + lane; };
+    auto gslice = [&](const double *base, int l) -> const double2 * { return reinterpret_cast<const double2 *>(base + ((size_t)l * 2 + part) * N); };
+    auto hslice = [&](unsigned int cta, int side, int pt) -> double2 * { return reinterpret_cast<double2 *>(C.halo + (((size_t)cta * 2 + side) * 2 + pt) * N); };
+    const unsigned int left = (bid + nblk - 1) % nblk, right = (bid + 1) % nblk;
+    const double normb = C.state->normb, tol = C.state->tol;
+    double eps = C.state->eps;
+    int it = 0, done = 0;
+    double v[RY][4], xr[RY][4], rr_[RY][4];
+    if (owner) {
+        const double2 *gx = gslice(C.x, lo), *gr = gslice(C.r, lo);
+#pragma unroll
+        for (int r = 0; r < RY; r++)
+#pragma unroll
+            for (int jp = 0; jp < 2; jp++) {
+                const double2 a = gx[el(r, jp)], b = gr[el(r, jp)];
+                xr[r][2 * jp] = a.x; xr[r][2 * jp + 1] = a.y;
+                rr_[r][2 * jp] = b.x; rr_[r][2 * jp + 1] = b.y;
+                Pb[(size_t)k * (N / 2) + el(r, jp)] = b;
+            }
+    }
+    if (k == 0) {                                         // p0 = r0 on the two halo slices
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            const int q = side ? ns + 1 : 0;
+            int l = side ? l0 + ns : l0 - 1;
+            l = l < 0 ? l + L : (l >= L ? l - L : l);
+            const double2 *gr = gslice(C.r, l);
+            for (int e = lane; e < N / 2; e += 32) Pb[(size_t)q * (N / 2) + e] = gr[e];
+        }
+    }
+    bool aborted = false;
+#ifdef SQ_V3_STAMPS
+    long long tacc_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev_ = clock64();
+    long long *tacc = (P.dbg && bid == (unsigned)P.cg_iter) ? tacc_ : nullptr, *tprev = &tprev_;
+#else
+    long long *tacc = nullptr, *tprev = nullptr;
+#endif
+    __syncthreads();                                      // p0 of all slices (own + halo) is in Pb
+    bool halo_pending = false;                            // warp 0: the halo slices of this iteration still have to be fetched
+#pragma unroll 1
+    while (it < C.maxiter) {
+        it++;
+        V3G_STAMP(0);
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (k == 0 && halo_pending) {
+            // warp 0 of each part owns no slice: it fetches the neighbours' boundary slices of p (upper first: warp ns needs it
+            // for its combine, while the lower one feeds this warp's own B).  The owners are already running their B meanwhile.
+            const long long t0 = clock64();
+#pragma unroll 1
+            for (int side = 1; side >= 0; side--) {
+                const unsigned int nb = side ? right : left;
+                unsigned long long e;
+                while (true) {
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(e) : "l"(C.flags + nb) : "memory");
+#ifdef SQ_V3_STAMPS
+                    if (P.cg_check & 2) break;
+#endif
+                    if (e >= (unsigned long long)(it - 1)) break;
+                    if (clock64() - t0 > 4000000000LL) break;       // the next grid sum times out and reports it
+                }
+                V3G_STAMP(8 + side);
+                const int q = side ? ns + 1 : 0;
+                const double2 *h = hslice(nb, side ? 0 : 1, part);
+#pragma unroll
+                for (int u = 0; u < N / 64; u++) Pb[(size_t)q * (N / 2) + lane + 32 * u] = __ldcg(h + lane + 32 * u);
+                if (side == 1) {
+                    __threadfence_block();
+                    asm volatile("bar.arrive %0, 64;" ::"r"(1 + part) : "memory");
+                }
+            }
+            __syncwarp();
+        }
+        if (active) {
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 a = Pb[(size_t)k * (N / 2) + el(r, jp)];
+                    v[r][2 * jp] = a.x; v[r][2 * jp + 1] = a.y;
+                }
+#ifdef SQ_V3_STAMPS
+            if (!(P.cg_check & 1))
+#endif
+            E.template apply_B<1>(v, lB, P);
+            if (k == ns && it > 1) asm volatile("bar.sync %0, 64;" ::"r"(1 + part) : "memory");   // upper halo slice is in Pb
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 self = Pb[(size_t)(k + 1) * (N / 2) + el(r, jp)];
+                    const double w0 = fma(sg, v[r][2 * jp], self.x), w1 = fma(sg, v[r][2 * jp + 1], self.y);
+                    v[r][2 * jp] = w0; v[r][2 * jp + 1] = w1;
+                    if (publish) {
+                        acc[0] += w0 * w0;
+                        acc[0] += w1 * w1;
+                        W[(size_t)k * (N / 2) + el(r, jp)] = make_double2(w0, w1);
+                    }
+                }
+        }
+        V3G_STAMP(1);
+#ifdef SQ_V3_STAMPS
+        if (!(P.cg_check & 1))
+#endif
+        if (owner) E.template apply_B<1>(v, lB, P);
+        __syncthreads();
+        V3G_STAMP(2);
+        if (owner) {                                      // z[lo] = w[lo] -/+ B w[lo + 1] in registers; r.z, |z|^2, |r|^2
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 w = W[(size_t)(k - 1) * (N / 2) + el(r, jp)];
+                    const double z0 = fma(sg, v[r][2 * jp], w.x), z1 = fma(sg, v[r][2 * jp + 1], w.y);
+                    v[r][2 * jp] = z0; v[r][2 * jp + 1] = z1;
+                    const double r0 = rr_[r][2 * jp], r1 = rr_[r][2 * jp + 1];
+                    acc[1] += r0 * z0; acc[1] += r1 * z1;
+                    acc[2] += z0 * z0; acc[2] += z1 * z1;
+                    acc[3] += r0 * r0; acc[3] += r1 * r1;
+                }
+        }
+#ifdef SQ_V3_STAMPS
+        if (P.cg_check & 4) { __syncthreads(); if (threadIdx.x < 4) sh[threadIdx.x] = 1.0 + threadIdx.x; __syncthreads(); } else
+#endif
+        v3_grid_sum4(acc, red, sh, C.slots_main, C.slot_stride, (unsigned long long)it, nblk, bid, aborted, tacc, tprev);
+        if (aborted) { done = 3; break; }
+        const double pAp = sh[0], rz = sh[1], zz = sh[2], rr_old = sh[3];
+        const double alpha = rr_old / pAp;
+        double rr_new = fma(alpha, fma(alpha, zz, -2.0 * rz), rr_old);       // |r - alpha z|^2
+        rr_new = rr_new > 0.0 ? rr_new : (rr_new == rr_new ? 0.0 : rr_new);
+        eps = sqrt(rr_new) / normb;
+        const bool stop_est = (eps < tol) || !(eps == eps) || it == C.maxiter;
+        const double beta = rr_new / rr_old;
+        double chk[4] = {0.0, 0.0, 0.0, 0.0};
+        if (owner) {                                      // x += alpha p ; r -= alpha z ; p = r + beta p
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 pv = Pb[(size_t)k * (N / 2) + el(r, jp)];
+                    xr[r][2 * jp] = fma(alpha, pv.x, xr[r][2 * jp]);
+                    xr[r][2 * jp + 1] = fma(alpha, pv.y, xr[r][2 * jp + 1]);
+                    const double r0 = fma(-alpha, v[r][2 * jp], rr_[r][2 * jp]), r1 = fma(-alpha, v[r][2 * jp + 1], rr_[r][2 * jp + 1]);
+                    rr_[r][2 * jp] = r0; rr_[r][2 * jp + 1] = r1;
+                    chk[0] += r0 * r0; chk[0] += r1 * r1;
+                    const double2 pn = make_double2(fma(beta, pv.x, r0), fma(beta, pv.y, r1));
+                    Pb[(size_t)k * (N / 2) + el(r, jp)] = pn;
+                    if (k == 1) hslice(bid, 0, part)[el(r, jp)] = pn;
+                    if (k == ns) hslice(bid, 1, part)[el(r, jp)] = pn;
+                }
+        }
+        if (stop_est) {                                   // confirm with the exact |r_new|^2 (all CTAs take this branch together)
+            v3_grid_sum4(chk, red, sh, C.slots_check, C.slot_stride, (unsigned long long)it, nblk, bid, aborted);
+            if (aborted) { done = 3; break; }
+            eps = sqrt(sh[0]) / normb;
+            if (eps < tol) { done = 1; break; }
+            if (!(eps == eps)) { done = 2; break; }
+            if (it == C.maxiter) break;
+        }
+        __syncthreads();                                  // own p slices are in Pb, the boundary slices have been stored
+        V3G_STAMP(7);
+        if (threadIdx.x == 0) {                           // publish the boundary slices: fence (cumulative over the CTA), then the epoch flag
+            __threadfence();
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(C.flags + bid), "l"((unsigned long long)it) : "memory");
+        }
+        halo_pending = true;
+    }
+#ifdef SQ_V3_STAMPS
+    if (tacc && threadIdx.x == 0) { for (int q = 0; q < 12; q++) P.dbg[q] = tacc_[q]; P.dbg[12] = it; }
+#endif
+    if (owner) {                                          // the solution
+        double2 *gx = reinterpret_cast<double2 *>(C.x + ((size_t)lo * 2 + part) * N);
+#pragma unroll
+        for (int r = 0; r < RY; r++)
+#pragma unroll
+            for (int jp = 0; jp < 2; jp++) gx[el(r, jp)] = make_double2(xr[r][2 * jp], xr[r][2 * jp + 1]);
+    }
+    if (bid == 0 && threadIdx.x == 0) {
+        CgState st = *C.state;
+        st.iters = it;
+        st.eps = eps;
+        st.done = done;
+        *C.state = st;
+    }
+}
+
+typedef void (*v3_resident_t)(const V3Params, const CgPersist3, double *);
+static v3_resident_t pick3_resident(int lxl, int ry) {
+    if (lxl == 8 && ry == 4) return k_cg_v3_resident<8, 4>;
+    if (lxl == 8 && ry == 8) return k_cg_v3_resident<8, 8>;
+    if (lxl == 4 && ry == 2) return k_cg_v3_resident<4, 2>;
+    if (lxl == 4 && ry == 4) return k_cg_v3_resident<4, 4>;
+    if (lxl == 4 && ry == 8) return k_cg_v3_resident<4, 8>;
+    return nullptr;
+}
+typedef void (*v3_resident1_t)(const V3Params, const CgResident);
+static v3_resident1_t pick3_resident1(int lxl, int ry) {
+    if (lxl == 8 && ry == 4) return k_cg_v3_resident1<8, 4>;
+    if (lxl == 8 && ry == 8) return k_cg_v3_resident1<8, 8>;
+    if (lxl == 4 && ry == 2) return k_cg_v3_resident1<4, 2>;
+    if (lxl == 4 && ry == 4) return k_cg_v3_resident1<4, 4>;
+    if (lxl == 4 && ry == 8) return k_cg_v3_resident1<4, 8>;
+    return nullptr;
+}
+
+// One CTA per SM.  x (in/out) and r (in) are native-order vectors; `halo` is scratch of at least one vector.
+// Default is the two-sum kernel (k_cg_v3_resident); SQ_V3_RESIDENT=1 selects the one-sum kernel (k_cg_v3_resident1), which is
+// equally fast today (both ~11-12 us per iteration at cfg4, bounded by grid-sum and hand-shake latency, not arithmetic).
+bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, double2 *halo, CgState *state, double *part_a, double *part_b, i64 maxiter) {
+    const char *sel = getenv("SQ_V3_RESIDENT");
+    const bool two_sums = !(sel && atoi(sel) == 1);
+    v3_resident_t k2 = pick3_resident(f->v3_lxl, f->v3_ry);
+    v3_resident1_t k1 = pick3_resident1(f->v3_lxl, f->v3_ry);
+    if (!k1 || !k2 || !f->v3_ok || !f->cs_coluni) return false;
+    const void *kern = two_sums ? (const void *)k2 : (const void *)k1;
+    const int nsl = f->slab_hi - f->slab_lo;
+    int S = (nsl + f->num_sms - 1) / f->num_sms;                 // fewest slices per CTA with one CTA per SM
+    if (const char *e = getenv("SQ_V3_RESIDENT_SLAB")) S = atoi(e);
+    S = std::max(S, 2);
+    if (S > 3 || nsl < S) return false;                          // 2 (S+1) warps <= 8
+    const int grid = (nsl + S - 1) / S, T = 64 * (S + 1);
+    const size_t smem = (size_t)2 * (2 * S + 2) * f->N * sizeof(double);
+    if (smem > f->smem_optin || grid > f->num_sms || grid < 2) return false;
+    if ((size_t)grid * 4 * f->N > (size_t)2 * f->L * f->N) return false;      // halo scratch is one vector
+    V3Params P;
+    memset(&P, 0, sizeof(P));
+    P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = 4; P.nphase = 2;
+    for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = f->clo[c]; }
+    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p;
+    SQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
+    if (per_sm * f->num_sms < grid) return false;
+    if (!f->flag.p) f->flag.alloc(4);
+    SQ_CUDA(cudaMemsetAsync(f->flag.p, 0, 4 * sizeof(int), f->stream));
+    // slots of the grid sums, one per CTA, spread over the L2 slices; then the halo epoch flags
+    unsigned int stride_bytes = 1024;
+    if (const char *e = getenv("SQ_V3_SLOT_STRIDE")) stride_bytes = (unsigned)atoi(e);
+    stride_bytes = std::max(64u, stride_bytes / 64 * 64);
+    const size_t slot_bytes = (size_t)(grid + 8) * stride_bytes;       // + 8: replicated totals
+    const size_t need = 2 * slot_bytes + (size_t)grid * sizeof(unsigned long long);
+    if (f->v3_slots.n < need) f->v3_slots.alloc(need);
+    SQ_CUDA(cudaMemsetAsync(f->v3_slots.p, 0, need, f->stream));
+    (void)part_a; (void)part_b;
+    static long long *dbg = nullptr;
+    if (!dbg && getenv("SQ_DEBUG_STAMPS")) {
+        SQ_CUDA(cudaMallocManaged((void **)&dbg, 16 * sizeof(long long)));
+        for (int q = 0; q < 16; q++) dbg[q] = 0;
+    }
+    P.dbg = dbg;
+    if (const char *e = getenv("SQ_V3_STAMP_CTA")) P.cg_iter = atoi(e);      // which CTA records the stamps (debug builds)
+    if (const char *e = getenv("SQ_V3_SKIP")) P.cg_check = atoi(e);            // debug builds: 1 skip B, 2 skip halo wait, 4 skip grid sum
+    if (two_sums) {
+        CgPersist3 C;
+        memset(&C, 0, sizeof(C));
+        C.x = (double *)x; C.r = (double *)r; C.state = state; C.part_a = (double *)f->v3_slots.p; C.part_b = (double *)(f->v3_slots.p + slot_bytes);
+        C.slot_stride = stride_bytes / 16;
+        C.barrier = (unsigned int *)f->flag.p; C.abort_flag = f->flag.p + 1; C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
+        double *h = (double *)halo;
+        void *args[] = {(void *)&P, (void *)&C, (void *)&h};
+        SQ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(T), args, smem, f->stream));
+    } else {
+        CgResident C;
+        memset(&C, 0, sizeof(C));
+        C.x = (double *)x; C.r = (const double *)r; C.state = state;
+        C.slots_main = f->v3_slots.p; C.slots_check = f->v3_slots.p + slot_bytes; C.slot_stride = stride_bytes;
+        C.halo = (double *)halo; C.flags = (unsigned long long *)(f->v3_slots.p + 2 * slot_bytes);
+        C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
+        void *args[] = {(void *)&P, (void *)&C};
+        SQ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(T), args, smem, f->stream));
+    }
+    f->launches++;
+#ifdef SQ_V3_STAMPS
+    if (dbg && !two_sums) {
+        cudaStreamSynchronize(f->stream);
+        double n = (double)std::max<long long>(dbg[12], 1);
+        fprintf(stderr, "v3 resident1 CG, cycles/iteration, CTA 1 thread 0 (%lld its, S=%d, %d CTAs): topsync %.0f | B1+combine %.0f | wait B2 sync %.0f | sum: reduce+sync %.0f  publish %.0f  poll+add %.0f  sync_or %.0f | update+sync %.0f | flagL %.0f flagR(+loadL) %.0f\n",
+                dbg[12], S, grid, dbg[0] / n, dbg[1] / n, dbg[2] / n, dbg[3] / n, dbg[4] / n, dbg[5] / n, dbg[6] / n, dbg[7] / n, dbg[8] / n, dbg[9] / n);
+    }
+    if (dbg && two_sums) {
+        cudaStreamSynchronize(f->stream);
+        double n = (double)std::max<long long>(dbg[6], 1);
+        fprintf(stderr, "v3 resident CG, cycles/iteration (CTA 0, warp 1; %lld iterations, S=%d, %d CTAs): B+combine %.0f  B+z+partial %.0f  barrier1+sum %.0f  update+partial %.0f  barrier2+sum %.0f  p update %.0f\n",
+                dbg[6], S, grid, dbg[0] / n, dbg[1] / n, dbg[2] / n, dbg[3] / n, dbg[4] / n, dbg[5] / n);
+    }
+#endif
+    return true;
+}
+
+typedef void (*v3_persist_t)(const V3Params, const CgPersist3);
+static v3_persist_t pick3_persist(int lxl, int ry) {
+    if (lxl == 8 && ry == 4) return k_cg_v3_persistent<8, 4>;
+    if (lxl == 8 && ry == 8) return k_cg_v3_persistent<8, 8>;
+    if (lxl == 8 && ry == 16) return k_cg_v3_persistent<8, 16>;
+    if (lxl == 4 && ry == 2) return k_cg_v3_persistent<4, 2>;
+    if (lxl == 4 && ry == 4) return k_cg_v3_persistent<4, 4>;
+    if (lxl == 4 && ry == 8) return k_cg_v3_persistent<4, 8>;
+    return nullptr;
+}
+
+// x, r: native order, prepared by the caller (cg.cu); p0 / p1: the two p buffers (zeroed here).  Returns false if the
+// cooperative launch is not possible (not all CTAs co-resident).
+bool fdm_v3_cg_persistent(sq_fdm *f, double2 *x, double2 *r, double2 *p0, double2 *p1, CgState *state, double *part_a, double *part_b,
+                          i64 maxiter) {
+    int S = f->v3_S;
+    if (const char *e = getenv("SQ_V3_PERSIST_SLAB")) S = atoi(e);
+    if (!fdm_v3_supported(f, S)) return false;
+    V3Params P;
+    memset(&P, 0, sizeof(P));
+    P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = 4; P.nphase = 2;
+    for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = f->clo[c]; }
+    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p;
+    const int grid = (f->slab_hi - f->slab_lo + S - 1) / S, T = 32 * (S + 1);
+    if (2 * grid > SQ_MAXPART) return false;
+    const size_t smem = (size_t)S * f->N * sizeof(double);
+    v3_persist_t k = pick3_persist(f->v3_lxl, f->v3_ry);
+    SQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+    int per_sm = 0;
+    SQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, T, smem));
+    if (per_sm * f->num_sms < 2 * grid) return false;
+    if (!f->flag.p) f->flag.alloc(4);
+    SQ_CUDA(cudaMemsetAsync(f->flag.p, 0, 4 * sizeof(int), f->stream));
+    SQ_CUDA(cudaMemsetAsync(p0, 0, f->vec_bytes(), f->stream));
+    SQ_CUDA(cudaMemsetAsync(p1, 0, f->vec_bytes(), f->stream));
+    CgPersist3 C;
+    C.x = (double *)x; C.r = (double *)r; C.p0 = (double *)p0; C.p1 = (double *)p1; C.state = state; C.part_a = part_a; C.part_b = part_b;
+    C.barrier = (unsigned int *)f->flag.p; C.abort_flag = f->flag.p + 1; C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
+    static long long *dbg = nullptr;
+    if (!dbg && getenv("SQ_DEBUG_STAMPS")) {
+        SQ_CUDA(cudaMallocManaged((void **)&dbg, 16 * sizeof(long long)));
+        for (int q = 0; q < 16; q++) dbg[q] = 0;
+    }
+    P.dbg = dbg;
+    void *args[] = {(void *)&P, (void *)&C};
+    SQ_CUDA(cudaLaunchCooperativeKernel((const void *)k, dim3(grid, 2), dim3(T), args, smem, f->stream));
+    f->launches++;
+    if (dbg) {
+        cudaStreamSynchronize(f->stream);
+        double n = (double)std::max<long long>(dbg[5], 1);
+        fprintf(stderr, "v3 persistent CG, cycles/iteration (CTA 0, warp 1; %lld iterations, S=%d, %d CTAs): load+B+combine %.0f  B+z+partial %.0f  barrier1+sum %.0f  update+partial %.0f  barrier2+sum %.0f\n",
+                dbg[5], S, 2 * grid, dbg[0] / n, dbg[1] / n, dbg[2] / n, dbg[3] / n, dbg[4] / n);
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// native order  <->  library order [l][i] (complex interleaved)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t v3_native_index(int i, int lxl, int ry) {      // offset inside one slice-part (doubles)
+    const int LX = 4 * lxl, x = i % LX, y = i / LX;
+    const int lane = x / 4 + lxl * (y / ry), r = y % ry, j = x % 4;
+    return (size_t)((r * 2 + j / 2) * 32 + lane) * 2 + (j & 1);
+}
+__global__ void k_v3_to_native(double *__restrict__ dst, const double2 *__restrict__ src, int L, int N, int lxl, int ry) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)L * N) return;
+    const int l = (int)(idx / N), i = (int)(idx % N);
+    const double2 v = src[idx];
+    const size_t o = v3_native_index(i, lxl, ry);
+    dst[((size_t)l * 2) * N + o] = v.x;
+    dst[((size_t)l * 2 + 1) * N + o] = v.y;
+}
+__global__ void k_v3_from_native(double2 *__restrict__ dst, const double *__restrict__ src, int L, int N, int lxl, int ry) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)L * N) return;
+    const int l = (int)(idx / N), i = (int)(idx % N);
+    const size_t o = v3_native_index(i, lxl, ry);
+    dst[idx] = make_double2(src[((size_t)l * 2) * N + o], src[((size_t)l * 2 + 1) * N + o]);
+}
+struct V3Clo { int lo[4]; };
+__global__ void k_v3_expV_native(double *__restrict__ dst, const double *__restrict__ src, int L, int N, int lxl, int ry,
+                                 const double2 *__restrict__ cs, const V3Clo clo) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)L * N) return;
+    const int l = (int)(idx / N), i = (int)(idx % N);
+    double g = 1.0;                                            // prod_c cosh_c^2 (each colour is applied twice in B)
+#pragma unroll
+    for (int c = 0; c < 4; c++) { const double ch = __ldg(cs + clo.lo[c]).x; g *= ch * ch; }
+    dst[(size_t)l * N + v3_native_index(i, lxl, ry)] = g * src[idx];
+}
+
+void fdm_v3_to_native(sq_fdm *f, double2 *dst, const double2 *src) {
+    const size_t n = (size_t)f->L * f->N;
+    k_v3_to_native<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>((double *)dst, src, (int)f->L, (int)f->N, f->v3_lxl, f->v3_ry);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+}
+void fdm_v3_from_native(sq_fdm *f, double2 *dst, const double2 *src) {
+    const size_t n = (size_t)f->L * f->N;
+    k_v3_from_native<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>(dst, (const double *)src, (int)f->L, (int)f->N, f->v3_lxl, f->v3_ry);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+}
+// native-order copy of exp(-dtau V), refreshed when the operator changed
+void fdm_v3_prepare_native(sq_fdm *f) {
+    const size_t n = (size_t)f->L * f->N;
+    if (!f->v3_expVn.p) { f->v3_expVn.alloc(n); f->v3_x.alloc(n); f->v3_r.alloc(n); f->v3_expv_version = -1; }
+    if (f->v3_expv_version == f->coef_version) return;
+    V3Clo clo;
+    for (int c = 0; c < 4; c++) clo.lo[c] = f->clo[c];
+    k_v3_expV_native<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>(f->v3_expVn.p, f->expV.p, (int)f->L, (int)f->N, f->v3_lxl, f->v3_ry,
+                                                                        f->cs.p, clo);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+    f->v3_expv_version = f->coef_version;
+}

@@ -85,7 +85,7 @@ void slab_set_range(sq_fdm *f, int lo, int hi) {
     SQ_REQUIRE(lo >= 0 && hi > lo && hi <= f->L, "slab range out of bounds");
     f->slab_lo = lo;
     f->slab_hi = hi;
-    f->tuned[0][0] = f->tuned[1][0] = 0;         // the best (slab, threads) depends on the number of local slices
+    f->tuned[0][0] = f->tuned[1][0] = f->tuned[2][0] = 0;         // the best (slab, threads) depends on the number of local slices
     f->manual_tuning = 0;
 }
 

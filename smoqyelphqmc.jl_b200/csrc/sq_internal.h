@@ -48,6 +48,15 @@ struct sq_fdm {
     std::vector<int> h_abi_chk;              // internal bond index -> checkerboard index of the ABI tables
     int use_v2 = 0;                          // chosen by the autotuner / sq_fdm_set_fast_path
     int cs_uniform = 0;                      // (cosh, sinh) do not depend on tau (no SSH coupling): register-resident path
+    int cs_coluni = 0;                       // ... and are equal for all bonds of one colour (uniform hopping): fdm_v3.cu
+    // register path (fdm_v3.cu): rectangular lattice, one warp per slice
+    int v3_ok = 0, v3_lxl = 0, v3_ry = 0, v3_cls[4] = {0, 0, 0, 0};
+    int v3_S = 3;                            // slices per CTA of the register path
+    int use_v3 = 0;
+    DevBuf<double> v3_expVn;                 // exp(-dtau V) in the native order of the register path
+    DevBuf<double2> v3_x, v3_r;              // CG vectors in native order
+    i64 v3_expv_version = -1;
+    DevBuf<char> v3_slots;                   // grid-sum slots of the resident CG kernel
     DevBuf<int> flag;                        // device scratch flags (4 ints: uniformity probe / grid barrier / abort)
     DevBuf<double> expV;                     // [l][i]
     DevBuf<double2> cs;                      // [l][h]
@@ -62,7 +71,7 @@ struct sq_fdm {
     // fused-kernel configuration
     int path = 0;                            // 0 = slices staged in shared memory, 1 = global-memory passes
     int slab = 0, threads = 0;
-    int tuned[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // per coefficient mode (general / tau-uniform): valid, slab, threads, v2
+    int tuned[3][6] = {{0}, {0}, {0}};         // per coefficient mode (general / tau-uniform / colour-uniform): valid, slab, threads, v2, v3, v3_S
     int manual_tuning = 0;
     int num_sms = 148;
     size_t smem_optin = 0;
@@ -131,6 +140,7 @@ struct sq_elph {
     DevBuf<double> V0, t0;                   // bare on-site energy (N), bare hopping (Nh, ORIGINAL order)
     DevBuf<double> V, t;                     // materialised only by sq_elph_get_Vt: [l][i], [l][h] original order
     bool any_phsym = false;
+    bool t0_coluni = false;                  // bare hopping uniform inside every colour
 };
 
 struct sq_pff {

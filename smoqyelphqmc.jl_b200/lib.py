@@ -35,6 +35,7 @@ SIGNATURES = {
     "sq_fdm_set_tuning": [vp, i32, i32],
     "sq_fdm_get_tuning": [vp, vp, vp, vp],
     "sq_fdm_set_fast_path": [vp, i32],
+    "sq_fdm_time_mul": [vp, i32, vp, vp, i32, vp, i64, vp],
     "sq_fdm_stream": [vp, pp],
     "sq_nccl_unique_id": [vp],
     "sq_fdm_init_slab": [vp, i32, i32, vp],
