@@ -285,62 +285,63 @@ def run_native(args):
     iters_per_traj = iters_total / args.steps
     matvecs_per_traj = iters_per_traj + 2 * (NT + 1)
     if rank == 0:
-        # ---- roofline of the dominant kernel (k_fdm_fused<2>), rank 0: CUDA events around single launches
+        # ---- roofline, rank 0.  Two kernels matter: the fused M^T M v kernel on its own (what north_star names), timed by
+        #      the library with CUDA events on its stream (back to back = L2-hot as inside a solve; and L2-cold with a 256 MB
+        #      write between launches), and the kernel the trajectory actually spends its time in -- with the register path
+        #      the whole CG solve is ONE resident launch that applies M^T M once per iteration.
         n = m.N * m.Ltau
         d_in = torch.randn(n, 2, dtype=torch.float64, device=dev)
         d_out = torch.zeros_like(d_in)
         flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)          # 256 MB > 126 MB L2
         B = algorithmic_bytes(m)
-
-        def time_matvec(cold, reps=40):
-            ts = []
-            with torch.cuda.stream(stream):
-                for _ in range(5):
-                    fdm.mul_dev(api.OP_MTM, d_out.data_ptr(), d_in.data_ptr())
-                if cold:
-                    for _ in range(reps):
-                        flush.add_(1.0)                      # the launch below queues behind the flush: no host latency inside the events
-                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        a.record(stream)
-                        fdm.mul_dev(api.OP_MTM, d_out.data_ptr(), d_in.data_ptr())
-                        b.record(stream)
-                        b.synchronize()
-                        ts.append(a.elapsed_time(b) * 1e-3)
-                else:
-                    for _ in range(5):                       # back-to-back launches, as inside a CG solve
-                        flush[:1024].add_(1.0)
-                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        a.record(stream)
-                        for _ in range(reps):
-                            fdm.mul_dev(api.OP_MTM, d_out.data_ptr(), d_in.data_ptr())
-                        b.record(stream)
-                        b.synchronize()
-                        ts.append(a.elapsed_time(b) * 1e-3 / reps)
-            return float(np.mean(ts))
-
-        t_cold, t_hot = time_matvec(True), time_matvec(False)
+        tuning = fdm.tuning
+        path = tuning["path"]
+        op = 102 if path == 3 else api.OP_MTM                # 102: the register-path kernel on native-order vectors (as in CG)
+        t_hot = fdm.time_mul(op, d_out.data_ptr(), d_in.data_ptr(), 400) * 1e-6
+        t_cold = fdm.time_mul(op, d_out.data_ptr(), d_in.data_ptr(), 60, flush.data_ptr(), flush.numel() * 4) * 1e-6
+        # CG iteration time: fixed iteration count, device-resident vectors (one launch per solve on the register path)
+        nit = 2000
+        fdm.cg_dev(d_out.data_ptr(), d_in.data_ptr(), True, preconditioner=P, tol=1e-300, maxiter=200)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fdm.cg_dev(d_out.data_ptr(), d_in.data_ptr(), True, preconditioner=P, tol=1e-300, maxiter=nit)
+        torch.cuda.synchronize()
+        t_iter = (time.perf_counter() - t0) / nit
         peak, peak_src = measured_peak()
-        traffic = None
+        state = {}
         try:
-            traffic = json.load(open(ITERS_FILE)).get("mtm_dram_bytes_per_launch")
+            state = json.load(open(ITERS_FILE))
         except Exception:
             pass
-        # Models without SSH coupling have tau-independent hoppings: the fast kernel then reads (cosh, sinh) once per
-        # kernel instead of once per slice, so the bytes it must move are 40 N Ltau + 16 Nh, not the generic figure.
-        uniform = (m.Nssh == 0) and fdm.tuning["path"] == 2
+        # Models without SSH coupling have tau-independent hoppings: the fast kernels read (cosh, sinh) once per kernel
+        # instead of once per slice, so the bytes they must move are 40 N Ltau + 16 Nh, not the generic figure.
+        uniform = (m.Nssh == 0) and path in (2, 3)
         Bk = (40 * m.N * m.Ltau + 16 * m.Nh) if uniform else B
-        roofline = {"bound": "hbm", "kernel": "k_fdm_fused_v2<2> (fused M^T M v)" if fdm.tuning["path"] == 2 else "k_fdm_fused<2> (fused M^T M v)",
-                    "achieved": Bk / t_cold / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": Bk / t_cold / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": Bk, "generic_formula_bytes_per_launch": B,
-                    "bytes_note": "tau-uniform hoppings: (cosh, sinh) read once per kernel" if uniform else "generic (40 N + 16 Nh) Ltau",
-                    "achieved_generic_formula": B / t_cold / 1e9, "frac_generic_formula": B / t_cold / 1e9 / peak,
-                    "us_per_launch_cold_l2": t_cold * 1e6, "us_per_launch_hot_l2": t_hot * 1e6,
-                    "achieved_hot_l2": Bk / t_hot / 1e9, "frac_hot_l2": Bk / t_hot / 1e9 / peak,
-                    "limiter": "shared-memory crossbar + barrier latency (DESIGN.md section 4), not HBM",
-                    "matvecs_per_s_hot_l2": 1.0 / t_hot,
-                    "share_of_step": iters_per_traj * t_hot / (ms_dev * 1e-3 / args.steps),
-                    "tuning": fdm.tuning}
+        names = {0: "k_fdm_fused<2>", 2: "k_fdm_fused_v2<2>", 3: "k_fdm_v3<2,0,1> (register path, native order)"}
+        resident = (path == 3) and not precond
+        step_s = ms_dev * 1e-3 / args.steps
+        matvec = {"kernel": names.get(path, "global passes") + " (fused M^T M v)", "us_per_launch_cold_l2": t_cold * 1e6,
+                  "us_per_launch_hot_l2": t_hot * 1e6, "achieved_cold_l2": Bk / t_cold / 1e9, "frac_cold_l2": Bk / t_cold / 1e9 / peak,
+                  "achieved_hot_l2": Bk / t_hot / 1e9, "frac_hot_l2": Bk / t_hot / 1e9 / peak, "matvecs_per_s_hot_l2": 1.0 / t_hot,
+                  "traffic": state.get("mtm_dram_bytes_per_launch"),
+                  "note": "back-to-back launches on this system are paced in ~2 us steps (profiles/README.md); a single-wave kernel of "
+                          "~6 us cannot be timed below that from the host, which is why the solver is one resident launch"}
+        if resident:
+            roofline = {"bound": "hbm", "kernel": "k_cg_v3_resident (whole CG solve in one launch; M^T M v once per iteration, x r p resident on chip)",
+                        "achieved": Bk / t_iter / 1e9, "peak": peak, "unit": "GB/s", "frac": Bk / t_iter / 1e9 / peak,
+                        "traffic": state.get("cg_resident_dram_bytes_per_iteration"), "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": Bk * nit, "algorithmic_bytes_per_unit": Bk, "unit_of_work": "one CG iteration = one fused M^T M v",
+                        "units_per_launch": nit, "us_per_unit": t_iter * 1e6,
+                        "limiter": "latency: two grid-wide sums per iteration (~2 us each on this two-die part, tools/ubench/grid_sum.cu) + "
+                                   "FP64 issue of one wave; HBM traffic per iteration is ~0.1 MB because the working set stays on chip"}
+        else:
+            roofline = {"bound": "hbm", "kernel": matvec["kernel"], "achieved": Bk / t_cold / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": Bk / t_cold / 1e9 / peak, "traffic": matvec["traffic"], "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": Bk, "limiter": "shared-memory crossbar + barrier latency (DESIGN.md section 4), not HBM"}
+        roofline.update({"generic_formula_bytes_per_unit": B,
+                         "bytes_note": "tau-uniform hoppings: (cosh, sinh) read once per kernel" if uniform else "generic (40 N + 16 Nh) Ltau",
+                         "cg_us_per_iteration": t_iter * 1e6, "cg_iterations_per_s": 1.0 / t_iter,
+                         "share_of_step": iters_per_traj * t_iter / step_s, "matvec_kernel": matvec, "tuning": tuning})
 
     barrier()
     # ---- tau-slab strong scaling of the CG solve (N > 1): the same M^T M system partitioned over the ranks with

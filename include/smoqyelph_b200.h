@@ -79,8 +79,8 @@ int sq_fdm_set_fast_path(sq_fdm *f, int enable);                       /* 0 gene
 int sq_fdm_stream(sq_fdm *f, void **cuda_stream);
 /* measurement aid (bench.py, tools/): `reps` back-to-back launches of op on device vectors, timed with CUDA events on the
  * library stream; *us_per_launch = elapsed / reps (L2-hot: the working set of the named configs stays in L2).  If
- * d_flush != NULL a write of flush_bytes to d_flush precedes every launch (L2-cold) and each launch is timed on its own;
- * the median is returned. */
+ * d_flush != NULL a write of flush_bytes to d_flush precedes every launch (L2-cold); the time of the same flushes alone is
+ * subtracted.  op 102 = M^T M of the register path on vectors in its native order (the kernel the CG solver runs). */
 int sq_fdm_time_mul(sq_fdm *f, int op, void *d_out, const void *d_in, int reps, void *d_flush, int64_t flush_bytes,
                     double *us_per_launch);
 /* tau-slab partitioning over the GPUs of one node (the reference is single-process).  Rank g of `world`

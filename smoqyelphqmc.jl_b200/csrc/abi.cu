@@ -167,17 +167,24 @@ int sq_fdm_time_mul(sq_fdm *f, int op, void *d_out, const void *d_in, int reps, 
         SQ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         *us_per_launch = 1e3 * ms / reps;
     } else {
-        std::vector<float> t(reps);
+        // L2-cold: (flush + launch) x reps minus flush x reps, both timed as a whole -- single launches are too short for the
+        // ~2 us granularity of back-to-back event pairs on this system
+        float ms_both = 0, ms_flush = 0;
+        SQ_CUDA(cudaMemsetAsync(d_flush, 0, (size_t)flush_bytes, f->stream));
+        SQ_CUDA(cudaEventRecord(e0, f->stream));
         for (int k = 0; k < reps; k++) {
             SQ_CUDA(cudaMemsetAsync(d_flush, k & 1, (size_t)flush_bytes, f->stream));
-            SQ_CUDA(cudaEventRecord(e0, f->stream));
             fdm_mul_dev(f, op, (double2 *)d_out, (const double2 *)d_in);
-            SQ_CUDA(cudaEventRecord(e1, f->stream));
-            SQ_CUDA(cudaEventSynchronize(e1));
-            SQ_CUDA(cudaEventElapsedTime(&t[k], e0, e1));
         }
-        std::sort(t.begin(), t.end());
-        *us_per_launch = 1e3 * t[reps / 2];
+        SQ_CUDA(cudaEventRecord(e1, f->stream));
+        SQ_CUDA(cudaEventSynchronize(e1));
+        SQ_CUDA(cudaEventElapsedTime(&ms_both, e0, e1));
+        SQ_CUDA(cudaEventRecord(e0, f->stream));
+        for (int k = 0; k < reps; k++) SQ_CUDA(cudaMemsetAsync(d_flush, k & 1, (size_t)flush_bytes, f->stream));
+        SQ_CUDA(cudaEventRecord(e1, f->stream));
+        SQ_CUDA(cudaEventSynchronize(e1));
+        SQ_CUDA(cudaEventElapsedTime(&ms_flush, e0, e1));
+        *us_per_launch = 1e3 * (ms_both - ms_flush) / reps;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

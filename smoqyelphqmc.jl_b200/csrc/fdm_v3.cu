@@ -40,6 +40,7 @@ struct V3Params {
     const double2 *cs;      // (cosh, sinh) of colour c = cs[clo[c]]
     const double *expV;     // [l][i]
     const double *expVn;    // native order (NAT kernels)
+    const double2 *ctn;     // (cosh, tanh) per colour, prepared with expVn (the in-kernel divisions were 18 % of the stall samples)
     long long *dbg;         // optional clock stamps of warp 1 of CTA 0 (profiling aid, NULL in production)
     // CG fusion, same meaning as K2Params (fdm_v2.cu)
     const double2 *cg_d;
@@ -92,8 +93,8 @@ struct V3Lane {
         site0 = LX * RY * yh + 4 * xl;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const double2 q = __ldg(P.cs + P.clo[c]);
-            cc[c] = q.x; ss[c] = SC ? q.y / q.x : q.y;
+            const double2 q = SC ? __ldg(P.ctn + c) : __ldg(P.cs + P.clo[c]);
+            cc[c] = q.x; ss[c] = q.y;
         }
     }
 
@@ -597,7 +598,7 @@ int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, d
     }
     P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = 4; P.nphase = (mode == 2) ? 2 : 1;
     for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = f->clo[c]; }
-    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p;
+    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p;
     static long long *dbg = nullptr;
     if (!dbg && getenv("SQ_DEBUG_STAMPS")) {
         SQ_CUDA(cudaMallocManaged((void **)&dbg, 16 * sizeof(long long)));
@@ -1243,7 +1244,7 @@ bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, double2 *halo, CgStat
     memset(&P, 0, sizeof(P));
     P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = 4; P.nphase = 2;
     for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = f->clo[c]; }
-    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p;
+    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p;
     SQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
@@ -1326,7 +1327,7 @@ bool fdm_v3_cg_persistent(sq_fdm *f, double2 *x, double2 *r, double2 *p0, double
     memset(&P, 0, sizeof(P));
     P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = 4; P.nphase = 2;
     for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = f->clo[c]; }
-    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p;
+    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p;
     const int grid = (f->slab_hi - f->slab_lo + S - 1) / S, T = 32 * (S + 1);
     if (2 * grid > SQ_MAXPART) return false;
     const size_t smem = (size_t)S * f->N * sizeof(double);
@@ -1386,8 +1387,9 @@ __global__ void k_v3_from_native(double2 *__restrict__ dst, const double *__rest
 }
 struct V3Clo { int lo[4]; };
 __global__ void k_v3_expV_native(double *__restrict__ dst, const double *__restrict__ src, int L, int N, int lxl, int ry,
-                                 const double2 *__restrict__ cs, const V3Clo clo) {
+                                 const double2 *__restrict__ cs, const V3Clo clo, double2 *__restrict__ ctn) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < 4) { const double2 q = __ldg(cs + clo.lo[idx]); ctn[idx] = make_double2(q.x, q.y / q.x); }
     if (idx >= (size_t)L * N) return;
     const int l = (int)(idx / N), i = (int)(idx % N);
     double g = 1.0;                                            // prod_c cosh_c^2 (each colour is applied twice in B)
@@ -1411,12 +1413,12 @@ void fdm_v3_from_native(sq_fdm *f, double2 *dst, const double2 *src) {
 // native-order copy of exp(-dtau V), refreshed when the operator changed
 void fdm_v3_prepare_native(sq_fdm *f) {
     const size_t n = (size_t)f->L * f->N;
-    if (!f->v3_expVn.p) { f->v3_expVn.alloc(n); f->v3_x.alloc(n); f->v3_r.alloc(n); f->v3_expv_version = -1; }
+    if (!f->v3_expVn.p) { f->v3_expVn.alloc(n); f->v3_ctn.alloc(4); f->v3_x.alloc(n); f->v3_r.alloc(n); f->v3_expv_version = -1; }
     if (f->v3_expv_version == f->coef_version) return;
     V3Clo clo;
     for (int c = 0; c < 4; c++) clo.lo[c] = f->clo[c];
     k_v3_expV_native<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>(f->v3_expVn.p, f->expV.p, (int)f->L, (int)f->N, f->v3_lxl, f->v3_ry,
-                                                                        f->cs.p, clo);
+                                                                        f->cs.p, clo, f->v3_ctn.p);
     SQ_LAUNCH_CHECK();
     f->launches++;
     f->v3_expv_version = f->coef_version;

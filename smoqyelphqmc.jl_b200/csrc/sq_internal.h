@@ -53,6 +53,7 @@ struct sq_fdm {
     int v3_ok = 0, v3_lxl = 0, v3_ry = 0, v3_cls[4] = {0, 0, 0, 0};
     int v3_S = 3;                            // slices per CTA of the register path
     int use_v3 = 0;
+    DevBuf<double2> v3_ctn;                  // (cosh, tanh) per colour for the scaled rotations
     DevBuf<double> v3_expVn;                 // exp(-dtau V) in the native order of the register path
     DevBuf<double2> v3_x, v3_r;              // CG vectors in native order
     i64 v3_expv_version = -1;
