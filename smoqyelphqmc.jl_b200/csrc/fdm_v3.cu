@@ -874,334 +874,6 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Resident CG, ONE grid-wide sum per iteration.
-//
-// A grid-wide sum costs ~2.4 us on this two-die part (store -> L2 -> poll: several L2 trips), more than the whole
-// arithmetic of an iteration, and the textbook recurrence needs two of them (p.Ap, then |r_new|^2).  Both scalars follow
-// from quantities available BEFORE the first sum:
-//     a = |M p|^2 = p.Ap,   b = Re r.z,   c = |z|^2,   d = |r|^2        (z = A p, r the current residual)
-//     alpha = d / a,   |r - alpha z|^2 = d - 2 alpha b + alpha^2 c,   beta = |r_new|^2 / d
-// d is the exact norm of the stored residual, recomputed every iteration, so the estimate never feeds back into itself
-// (no drift); its rounding error is a few ulp of d, the same order as the error of the updated residual itself.  The
-// estimate drives beta and the stopping test; a positive stopping test (and the maxiter exit) is confirmed with the
-// exact |r_new|^2 (one extra sum, once per solve), so the returned eps is exact and the solver never stops early.
-// After the sum every warp updates x, r and forms p = r + beta p in one go; the boundary slices of the new p go to the
-// neighbours through a small global buffer guarded by per-CTA epoch flags (point to point, no second grid-wide sync).
-// ---------------------------------------------------------------------------------------------------
-struct V3Slot4 { V3Slot q[4]; };
-// sums acc[0..3] over the grid; result (same bits in every CTA) in sh_out[0..3].  See v3_grid_sum.
-#ifdef SQ_V3_STAMPS
-#define V3G_STAMP(q) do { if (tacc && threadIdx.x == 0) { long long tn = clock64(); tacc[q] += tn - *tprev; *tprev = tn; } } while (0)
-#else
-#define V3G_STAMP(q) do { } while (0)
-#endif
-__device__ __forceinline__ void v3_grid_sum4(const double (&acc_in)[4], double *red, double *sh_out, char *slots, unsigned int stride_bytes,
-                                             unsigned long long epoch, unsigned int nblk, unsigned int bid, bool &aborted,
-                                             long long *tacc = nullptr, long long *tprev = nullptr) {
-    // The batched polling loads are weak L2 loads (ld.global.cg): strong (ld.relaxed.gpu) loads of one warp are not pipelined
-    // by the hardware -- 17 of them per lane took ~7000 cycles per round instead of one L2 round trip.
-    // Slot q < nblk: the 4 partials of CTA q; slot nblk: the 4 totals.  CTA 0 alone polls the partial slots (134 pollers
-    // on 134 slots saturated L2: measured 11k cycles per sum) and publishes the totals, everybody else polls one line.
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        const double t = warp_sum(acc_in[c]);
-        if (lane == 0) red[c * 8 + warp] = t;
-    }
-    __syncthreads();
-    V3G_STAMP(3);
-    int bad = 0;
-    if (warp == 0) {
-        const long long t0 = clock64();
-        // the totals are replicated in 8 lines (different L2 slices); CTA q polls copy q % 8
-        V3Slot *total = reinterpret_cast<V3Slot4 *>(slots + (size_t)(nblk + (bid & 7)) * stride_bytes)->q;
-        double mine = 0.0;
-        if (lane < 4) {                                    // lane c handles component c of this CTA
-            for (int w = 0; w < nw; w++) mine += red[lane * 8 + w];
-            V3Slot *dst = reinterpret_cast<V3Slot4 *>(slots + (size_t)bid * stride_bytes)->q + lane;
-            if (bid != 0) asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(dst), "l"(__double_as_longlong(mine)), "l"(epoch) : "memory");
-        }
-        V3G_STAMP(4);
-        if (bid == 0) {
-            double s[4];
-#pragma unroll
-            for (int c = 0; c < 4; c++) s[c] = __shfl_sync(0xffffffffu, mine, c);      // CTA 0's own partials come first (in lane 0's sum)
-            if (lane != 0) { s[0] = 0.0; s[1] = 0.0; s[2] = 0.0; s[3] = 0.0; }
-            for (unsigned int base = 1; base < nblk; base += 128) {
-                long long val[4][4];
-                unsigned long long ep[4][4];
-                while (true) {
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const unsigned int q = base + lane + 32 * u;
-                        const V3Slot *sl = reinterpret_cast<const V3Slot4 *>(slots + (size_t)q * stride_bytes)->q;
-#pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            ep[u][c] = epoch; val[u][c] = 0;
-                            if (q < nblk) asm volatile("ld.global.cg.v2.b64 {%0, %1}, [%2];" : "=l"(val[u][c]), "=l"(ep[u][c]) : "l"(sl + c) : "memory");
-                        }
-                    }
-                    bool ready = true;
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-#pragma unroll
-                        for (int c = 0; c < 4; c++) ready = ready && (ep[u][c] >= epoch);
-                    if (ready) break;
-                    if (clock64() - t0 > 4000000000LL) { bad = 1; break; }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-#pragma unroll
-                    for (int c = 0; c < 4; c++) s[c] += __longlong_as_double(val[u][c]);
-            }
-            double tot = 0.0;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const double t = warp_sum(s[c]);
-                if (lane == c) tot = t;
-            }
-            if (lane < 4) sh_out[lane] = tot;
-            {                                              // lane -> (copy lane / 4, component lane % 4): one store instruction for all copies
-                const double tc = __shfl_sync(0xffffffffu, tot, lane & 3);
-                V3Slot *dst = reinterpret_cast<V3Slot4 *>(slots + (size_t)(nblk + (lane >> 2)) * stride_bytes)->q + (lane & 3);
-                asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(dst), "l"(__double_as_longlong(tc)), "l"(epoch) : "memory");
-            }
-        } else if (lane < 4) {
-            long long val = 0;
-            unsigned long long e = 0;
-            while (true) {
-                asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(val), "=l"(e) : "l"(total + lane) : "memory");
-                if (e >= epoch) break;
-                if (clock64() - t0 > 4000000000LL) { bad = 1; break; }
-            }
-            sh_out[lane] = __longlong_as_double(val);
-        }
-        V3G_STAMP(5);
-    }
-    aborted = __syncthreads_or(bad) != 0;
-    V3G_STAMP(6);
-}
-
-struct CgResident {
-    double *x;                  // native order, in: start vector, out: solution
-    const double *r;            // native order, initial residual
-    CgState *state;             // in: normb, tol, eps ; out: iters, eps, done
-    char *slots_main, *slots_check;
-    unsigned int slot_stride;   // bytes
-    double *halo;               // [cta][side][part][N] boundary slices of p
-    unsigned long long *flags;  // [cta] epoch of the halo slices
-    int maxiter;
-};
-
-template <int LXL, int RY>
-__global__ void __launch_bounds__(256, 1)
-k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident C) {
-    typedef V3Lane<LXL, RY> G;
-    constexpr int N = G::N;
-    extern __shared__ double smem[];
-    __shared__ double red[32];
-    __shared__ double sh[4];
-    const int S = P.S, L = P.L;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int part = wid / (S + 1), k = wid - part * (S + 1);
-    G E;
-    E.template init<1>(P, part);
-    const int l0 = P.lb + blockIdx.x * S;
-    const int ns = min(S, P.le - l0);
-    const unsigned int nblk = gridDim.x, bid = blockIdx.x;
-    const bool active = k <= ns, owner = active && k >= 1, publish = k < ns;
-    int lself = l0 + k;
-    lself = lself >= L ? lself - L : lself;
-    const int lB = lself, lo = l0 + k - 1;               // owner: slice lo
-    const double sg = (lB == 0) ? 1.0 : -1.0;
-    double2 *Pb = reinterpret_cast<double2 *>(smem) + (size_t)part * (S + 2) * (N / 2);          // [q = 0 .. S+1][N/2]
-    double2 *W = reinterpret_cast<double2 *>(smem) + (size_t)2 * (S + 2) * (N / 2) + (size_t)part * S * (N / 2);
-    auto el = [&](int r, int jp) -> int { return (r * 2 + jp) * 32 + lane; };
-    auto gslice = [&](const double *base, int l) -> const double2 * { return reinterpret_cast<const double2 *>(base + ((size_t)l * 2 + part) * N); };
-    auto hslice = [&](unsigned int cta, int side, int pt) -> double2 * { return reinterpret_cast<double2 *>(C.halo + (((size_t)cta * 2 + side) * 2 + pt) * N); };
-    const unsigned int left = (bid + nblk - 1) % nblk, right = (bid + 1) % nblk;
-    const double normb = C.state->normb, tol = C.state->tol;
-    double eps = C.state->eps;
-    int it = 0, done = 0;
-    double v[RY][4], xr[RY][4], rr_[RY][4];
-    if (owner) {
-        const double2 *gx = gslice(C.x, lo), *gr = gslice(C.r, lo);
-#pragma unroll
-        for (int r = 0; r < RY; r++)
-#pragma unroll
-            for (int jp = 0; jp < 2; jp++) {
-                const double2 a = gx[el(r, jp)], b = gr[el(r, jp)];
-                xr[r][2 * jp] = a.x; xr[r][2 * jp + 1] = a.y;
-                rr_[r][2 * jp] = b.x; rr_[r][2 * jp + 1] = b.y;
-                Pb[(size_t)k * (N / 2) + el(r, jp)] = b;
-            }
-    }
-    if (k == 0) {                                         // p0 = r0 on the two halo slices
-#pragma unroll 1
-        for (int side = 0; side < 2; side++) {
-            const int q = side ? ns + 1 : 0;
-            int l = side ? l0 + ns : l0 - 1;
-            l = l < 0 ? l + L : (l >= L ? l - L : l);
-            const double2 *gr = gslice(C.r, l);
-            for (int e = lane; e < N / 2; e += 32) Pb[(size_t)q * (N / 2) + e] = gr[e];
-        }
-    }
-    bool aborted = false;
-#ifdef SQ_V3_STAMPS
-    long long tacc_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev_ = clock64();
-    long long *tacc = (P.dbg && bid == (unsigned)P.cg_iter) ? tacc_ : nullptr, *tprev = &tprev_;
-#else
-    long long *tacc = nullptr, *tprev = nullptr;
-#endif
-    __syncthreads();                                      // p0 of all slices (own + halo) is in Pb
-    bool halo_pending = false;                            // warp 0: the halo slices of this iteration still have to be fetched
-#pragma unroll 1
-    while (it < C.maxiter) {
-        it++;
-        V3G_STAMP(0);
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        if (k == 0 && halo_pending) {
-            // warp 0 of each part owns no slice: it fetches the neighbours' boundary slices of p (upper first: warp ns needs it
-            // for its combine, while the lower one feeds this warp's own B).  The owners are already running their B meanwhile.
-            const long long t0 = clock64();
-#pragma unroll 1
-            for (int side = 1; side >= 0; side--) {
-                const unsigned int nb = side ? right : left;
-                unsigned long long e;
-                while (true) {
-                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(e) : "l"(C.flags + nb) : "memory");
-#ifdef SQ_V3_STAMPS
-                    if (P.cg_check & 2) break;
-#endif
-                    if (e >= (unsigned long long)(it - 1)) break;
-                    if (clock64() - t0 > 4000000000LL) break;       // the next grid sum times out and reports it
-                }
-                V3G_STAMP(8 + side);
-                const int q = side ? ns + 1 : 0;
-                const double2 *h = hslice(nb, side ? 0 : 1, part);
-#pragma unroll
-                for (int u = 0; u < N / 64; u++) Pb[(size_t)q * (N / 2) + lane + 32 * u] = __ldcg(h + lane + 32 * u);
-                if (side == 1) {
-                    __threadfence_block();
-                    asm volatile("bar.arrive %0, 64;" ::"r"(1 + part) : "memory");
-                }
-            }
-            __syncwarp();
-        }
-        if (active) {
-#pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 a = Pb[(size_t)k * (N / 2) + el(r, jp)];
-                    v[r][2 * jp] = a.x; v[r][2 * jp + 1] = a.y;
-                }
-#ifdef SQ_V3_STAMPS
-            if (!(P.cg_check & 1))
-#endif
-            E.template apply_B<1>(v, lB, P);
-            if (k == ns && it > 1) asm volatile("bar.sync %0, 64;" ::"r"(1 + part) : "memory");   // upper halo slice is in Pb
-#pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 self = Pb[(size_t)(k + 1) * (N / 2) + el(r, jp)];
-                    const double w0 = fma(sg, v[r][2 * jp], self.x), w1 = fma(sg, v[r][2 * jp + 1], self.y);
-                    v[r][2 * jp] = w0; v[r][2 * jp + 1] = w1;
-                    if (publish) {
-                        acc[0] += w0 * w0;
-                        acc[0] += w1 * w1;
-                        W[(size_t)k * (N / 2) + el(r, jp)] = make_double2(w0, w1);
-                    }
-                }
-        }
-        V3G_STAMP(1);
-#ifdef SQ_V3_STAMPS
-        if (!(P.cg_check & 1))
-#endif
-        if (owner) E.template apply_B<1>(v, lB, P);
-        __syncthreads();
-        V3G_STAMP(2);
-        if (owner) {                                      // z[lo] = w[lo] -/+ B w[lo + 1] in registers; r.z, |z|^2, |r|^2
-#pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 w = W[(size_t)(k - 1) * (N / 2) + el(r, jp)];
-                    const double z0 = fma(sg, v[r][2 * jp], w.x), z1 = fma(sg, v[r][2 * jp + 1], w.y);
-                    v[r][2 * jp] = z0; v[r][2 * jp + 1] = z1;
-                    const double r0 = rr_[r][2 * jp], r1 = rr_[r][2 * jp + 1];
-                    acc[1] += r0 * z0; acc[1] += r1 * z1;
-                    acc[2] += z0 * z0; acc[2] += z1 * z1;
-                    acc[3] += r0 * r0; acc[3] += r1 * r1;
-                }
-        }
-#ifdef SQ_V3_STAMPS
-        if (P.cg_check & 4) { __syncthreads(); if (threadIdx.x < 4) sh[threadIdx.x] = 1.0 + threadIdx.x; __syncthreads(); } else
-#endif
-        v3_grid_sum4(acc, red, sh, C.slots_main, C.slot_stride, (unsigned long long)it, nblk, bid, aborted, tacc, tprev);
-        if (aborted) { done = 3; break; }
-        const double pAp = sh[0], rz = sh[1], zz = sh[2], rr_old = sh[3];
-        const double alpha = rr_old / pAp;
-        double rr_new = fma(alpha, fma(alpha, zz, -2.0 * rz), rr_old);       // |r - alpha z|^2
-        rr_new = rr_new > 0.0 ? rr_new : (rr_new == rr_new ? 0.0 : rr_new);
-        eps = sqrt(rr_new) / normb;
-        const bool stop_est = (eps < tol) || !(eps == eps) || it == C.maxiter;
-        const double beta = rr_new / rr_old;
-        double chk[4] = {0.0, 0.0, 0.0, 0.0};
-        if (owner) {                                      // x += alpha p ; r -= alpha z ; p = r + beta p
-#pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 pv = Pb[(size_t)k * (N / 2) + el(r, jp)];
-                    xr[r][2 * jp] = fma(alpha, pv.x, xr[r][2 * jp]);
-                    xr[r][2 * jp + 1] = fma(alpha, pv.y, xr[r][2 * jp + 1]);
-                    const double r0 = fma(-alpha, v[r][2 * jp], rr_[r][2 * jp]), r1 = fma(-alpha, v[r][2 * jp + 1], rr_[r][2 * jp + 1]);
-                    rr_[r][2 * jp] = r0; rr_[r][2 * jp + 1] = r1;
-                    chk[0] += r0 * r0; chk[0] += r1 * r1;
-                    const double2 pn = make_double2(fma(beta, pv.x, r0), fma(beta, pv.y, r1));
-                    Pb[(size_t)k * (N / 2) + el(r, jp)] = pn;
-                    if (k == 1) hslice(bid, 0, part)[el(r, jp)] = pn;
-                    if (k == ns) hslice(bid, 1, part)[el(r, jp)] = pn;
-                }
-        }
-        if (stop_est) {                                   // confirm with the exact |r_new|^2 (all CTAs take this branch together)
-            v3_grid_sum4(chk, red, sh, C.slots_check, C.slot_stride, (unsigned long long)it, nblk, bid, aborted);
-            if (aborted) { done = 3; break; }
-            eps = sqrt(sh[0]) / normb;
-            if (eps < tol) { done = 1; break; }
-            if (!(eps == eps)) { done = 2; break; }
-            if (it == C.maxiter) break;
-        }
-        __syncthreads();                                  // own p slices are in Pb, the boundary slices have been stored
-        V3G_STAMP(7);
-        if (threadIdx.x == 0) {                           // publish the boundary slices: fence (cumulative over the CTA), then the epoch flag
-            __threadfence();
-            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(C.flags + bid), "l"((unsigned long long)it) : "memory");
-        }
-        halo_pending = true;
-    }
-#ifdef SQ_V3_STAMPS
-    if (tacc && threadIdx.x == 0) { for (int q = 0; q < 12; q++) P.dbg[q] = tacc_[q]; P.dbg[12] = it; }
-#endif
-    if (owner) {                                          // the solution
-        double2 *gx = reinterpret_cast<double2 *>(C.x + ((size_t)lo * 2 + part) * N);
-#pragma unroll
-        for (int r = 0; r < RY; r++)
-#pragma unroll
-            for (int jp = 0; jp < 2; jp++) gx[el(r, jp)] = make_double2(xr[r][2 * jp], xr[r][2 * jp + 1]);
-    }
-    if (bid == 0 && threadIdx.x == 0) {
-        CgState st = *C.state;
-        st.iters = it;
-        st.eps = eps;
-        st.done = done;
-        *C.state = st;
-    }
-}
-
 typedef void (*v3_resident_t)(const V3Params, const CgPersist3, double *);
 static v3_resident_t pick3_resident(int lxl, int ry) {
     if (lxl == 8 && ry == 4) return k_cg_v3_resident<8, 4>;
@@ -1211,26 +883,14 @@ static v3_resident_t pick3_resident(int lxl, int ry) {
     if (lxl == 4 && ry == 8) return k_cg_v3_resident<4, 8>;
     return nullptr;
 }
-typedef void (*v3_resident1_t)(const V3Params, const CgResident);
-static v3_resident1_t pick3_resident1(int lxl, int ry) {
-    if (lxl == 8 && ry == 4) return k_cg_v3_resident1<8, 4>;
-    if (lxl == 8 && ry == 8) return k_cg_v3_resident1<8, 8>;
-    if (lxl == 4 && ry == 2) return k_cg_v3_resident1<4, 2>;
-    if (lxl == 4 && ry == 4) return k_cg_v3_resident1<4, 4>;
-    if (lxl == 4 && ry == 8) return k_cg_v3_resident1<4, 8>;
-    return nullptr;
-}
-
 // One CTA per SM.  x (in/out) and r (in) are native-order vectors; `halo` is scratch of at least one vector.
-// Default is the two-sum kernel (k_cg_v3_resident); SQ_V3_RESIDENT=1 selects the one-sum kernel (k_cg_v3_resident1), which is
-// equally fast today (both ~11-12 us per iteration at cfg4, bounded by grid-sum and hand-shake latency, not arithmetic).
+// (A one-sum-per-iteration variant -- |r_new|^2 from d - 2 alpha b + alpha^2 c, halo slices of p through epoch flags -- was
+// built and measured at the same 11-12 us per iteration: the iteration is bounded by signalling latency, not by the number
+// of sums.  It is not in the tree; see DESIGN.md.)
 bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, double2 *halo, CgState *state, double *part_a, double *part_b, i64 maxiter) {
-    const char *sel = getenv("SQ_V3_RESIDENT");
-    const bool two_sums = !(sel && atoi(sel) == 1);
     v3_resident_t k2 = pick3_resident(f->v3_lxl, f->v3_ry);
-    v3_resident1_t k1 = pick3_resident1(f->v3_lxl, f->v3_ry);
-    if (!k1 || !k2 || !f->v3_ok || !f->cs_coluni) return false;
-    const void *kern = two_sums ? (const void *)k2 : (const void *)k1;
+    if (!k2 || !f->v3_ok || !f->cs_coluni) return false;
+    const void *kern = (const void *)k2;
     const int nsl = f->slab_hi - f->slab_lo;
     int S = (nsl + f->num_sms - 1) / f->num_sms;                 // fewest slices per CTA with one CTA per SM
     if (const char *e = getenv("SQ_V3_RESIDENT_SLAB")) S = atoi(e);
@@ -1254,9 +914,9 @@ bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, double2 *halo, CgStat
     // slots of the grid sums, one per CTA, spread over the L2 slices; then the halo epoch flags
     unsigned int stride_bytes = 1024;
     if (const char *e = getenv("SQ_V3_SLOT_STRIDE")) stride_bytes = (unsigned)atoi(e);
-    stride_bytes = std::max(64u, stride_bytes / 64 * 64);
-    const size_t slot_bytes = (size_t)(grid + 8) * stride_bytes;       // + 8: replicated totals
-    const size_t need = 2 * slot_bytes + (size_t)grid * sizeof(unsigned long long);
+    stride_bytes = std::max(16u, stride_bytes / 16 * 16);
+    const size_t slot_bytes = (size_t)grid * stride_bytes;
+    const size_t need = 2 * slot_bytes;
     if (f->v3_slots.n < need) f->v3_slots.alloc(need);
     SQ_CUDA(cudaMemsetAsync(f->v3_slots.p, 0, need, f->stream));
     (void)part_a; (void)part_b;
@@ -1266,36 +926,17 @@ bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, double2 *halo, CgStat
         for (int q = 0; q < 16; q++) dbg[q] = 0;
     }
     P.dbg = dbg;
-    if (const char *e = getenv("SQ_V3_STAMP_CTA")) P.cg_iter = atoi(e);      // which CTA records the stamps (debug builds)
-    if (const char *e = getenv("SQ_V3_SKIP")) P.cg_check = atoi(e);            // debug builds: 1 skip B, 2 skip halo wait, 4 skip grid sum
-    if (two_sums) {
-        CgPersist3 C;
-        memset(&C, 0, sizeof(C));
-        C.x = (double *)x; C.r = (double *)r; C.state = state; C.part_a = (double *)f->v3_slots.p; C.part_b = (double *)(f->v3_slots.p + slot_bytes);
-        C.slot_stride = stride_bytes / 16;
-        C.barrier = (unsigned int *)f->flag.p; C.abort_flag = f->flag.p + 1; C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
-        double *h = (double *)halo;
-        void *args[] = {(void *)&P, (void *)&C, (void *)&h};
-        SQ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(T), args, smem, f->stream));
-    } else {
-        CgResident C;
-        memset(&C, 0, sizeof(C));
-        C.x = (double *)x; C.r = (const double *)r; C.state = state;
-        C.slots_main = f->v3_slots.p; C.slots_check = f->v3_slots.p + slot_bytes; C.slot_stride = stride_bytes;
-        C.halo = (double *)halo; C.flags = (unsigned long long *)(f->v3_slots.p + 2 * slot_bytes);
-        C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
-        void *args[] = {(void *)&P, (void *)&C};
-        SQ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(T), args, smem, f->stream));
-    }
+    CgPersist3 C;
+    memset(&C, 0, sizeof(C));
+    C.x = (double *)x; C.r = (double *)r; C.state = state; C.part_a = (double *)f->v3_slots.p; C.part_b = (double *)(f->v3_slots.p + slot_bytes);
+    C.slot_stride = stride_bytes / 16;
+    C.barrier = (unsigned int *)f->flag.p; C.abort_flag = f->flag.p + 1; C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
+    double *h = (double *)halo;
+    void *args[] = {(void *)&P, (void *)&C, (void *)&h};
+    SQ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(T), args, smem, f->stream));
     f->launches++;
 #ifdef SQ_V3_STAMPS
-    if (dbg && !two_sums) {
-        cudaStreamSynchronize(f->stream);
-        double n = (double)std::max<long long>(dbg[12], 1);
-        fprintf(stderr, "v3 resident1 CG, cycles/iteration, CTA 1 thread 0 (%lld its, S=%d, %d CTAs): topsync %.0f | B1+combine %.0f | wait B2 sync %.0f | sum: reduce+sync %.0f  publish %.0f  poll+add %.0f  sync_or %.0f | update+sync %.0f | flagL %.0f flagR(+loadL) %.0f\n",
-                dbg[12], S, grid, dbg[0] / n, dbg[1] / n, dbg[2] / n, dbg[3] / n, dbg[4] / n, dbg[5] / n, dbg[6] / n, dbg[7] / n, dbg[8] / n, dbg[9] / n);
-    }
-    if (dbg && two_sums) {
+    if (dbg) {
         cudaStreamSynchronize(f->stream);
         double n = (double)std::max<long long>(dbg[6], 1);
         fprintf(stderr, "v3 resident CG, cycles/iteration (CTA 0, warp 1; %lld iterations, S=%d, %d CTAs): B+combine %.0f  B+z+partial %.0f  barrier1+sum %.0f  update+partial %.0f  barrier2+sum %.0f  p update %.0f\n",

@@ -123,3 +123,102 @@ def test_cg_matches_oracle(name, sym):
     assert it0 == 0
     _, itc, epsc = fdm.ldiv(b, tol=1e-14, maxiter=3)
     assert itc == 3 and epsc > 1e-14
+
+
+# ---- register path (fdm_v3.cu) and the resident CG solver -----------------------------------------------------
+SQUARES = {
+    "h16x16": lambda: mdl.holstein_square(16, 16, 2.0),
+    "h32x16": lambda: mdl.holstein_square(32, 16, 1.0),
+    "h16x32": lambda: mdl.holstein_square(16, 32, 1.0),
+    "h32x32": lambda: mdl.holstein_square(32, 32, 1.5),
+    "h16x64": lambda: mdl.holstein_square(16, 64, 0.5),
+    "h32x64": lambda: mdl.holstein_square(32, 64, 0.35),    # 64 rows: 16 rows per lane, Ltau = 7 (ragged last CTA)
+}
+
+
+def setup_square(name, seed=0):
+    from smoqyelph_b200 import api
+    m = SQUARES[name]()
+    rng = np.random.default_rng(seed)
+    V, t = dr.build_Vt(m, m.random_fields(rng))
+    ref = orc.RefFDM(m, sym=True)
+    ref.update(V, t)
+    fdm = api.FermionDetMatrix(m, sym=True)
+    fdm.update(V, t)
+    return m, rng, ref, fdm
+
+
+@pytest.mark.parametrize("name", list(SQUARES))
+def test_register_path_products(name):
+    """One warp per slice-part, colour sweeps in registers: same bits as the shared-memory kernels, 1e-12 vs the oracle."""
+    m, rng, ref, fdm = setup_square(name)
+    v = rand_cvec(rng, m)
+    fdm.set_fast_path(1)
+    base = {op: getattr(fdm, op)(v) for op in ("mul_M", "mul_Mt", "mul_MtM", "mul_MMt")}
+    for S in (1, 2, 3, 4, 7):
+        fdm.set_fast_path(2 + 256 * S)
+        assert fdm.tuning["path"] == 3, (name, S, fdm.tuning)
+        for op, want in base.items():
+            got = getattr(fdm, op)(v)
+            assert relerr(got, getattr(ref, op)(v)) < RTOL, (name, S, op)
+            assert np.array_equal(got, want), (name, S, op, "register path differs from the shared-memory kernel")
+
+
+def test_register_path_requires_uniform_colours_and_canonical_order():
+    """Disordered hoppings or a permuted colour order must fall back to the shared-memory kernels (and stay correct)."""
+    from smoqyelph_b200 import api
+    m = mdl.holstein_square(16, 16, 0.5)
+    rng = np.random.default_rng(3)
+    V, t = dr.build_Vt(m, m.random_fields(rng))
+    t = t * (1.0 + 0.1 * rng.standard_normal(t.shape[0]))[:, None]          # bond disorder: colours no longer uniform
+    ref = orc.RefFDM(m, sym=True)
+    ref.update(V, t)
+    fdm = api.FermionDetMatrix(m, sym=True)
+    fdm.update(V, t)
+    fdm.set_fast_path(2)
+    assert fdm.tuning["path"] != 3
+    v = rand_cvec(rng, m)
+    assert relerr(fdm.mul_MtM(v), ref.mul_MtM(v)) < RTOL
+    # y colours before x colours: a valid checkerboard, but not the order the register kernels are written for
+    nt, col, _ = mdl._square_bonds(16, 16)
+    m2 = mdl.holstein_square(16, 16, 0.5)
+    m2.finalize((np.asarray(col) + 2) % 4)
+    V2, t2 = dr.build_Vt(m2, m2.random_fields(rng))
+    ref2 = orc.RefFDM(m2, sym=True)
+    ref2.update(V2, t2)
+    fdm2 = api.FermionDetMatrix(m2, sym=True)
+    fdm2.update(V2, t2)
+    fdm2.set_fast_path(2)
+    assert fdm2.tuning["path"] != 3
+    assert relerr(fdm2.mul_MtM(v), ref2.mul_MtM(v)) < RTOL
+
+
+@pytest.mark.parametrize("solver", ["resident", "persistent", "launches"])
+@pytest.mark.parametrize("name", ["h16x16", "h32x16", "h32x32"])
+def test_register_path_cg(name, solver, monkeypatch):
+    """CG on the register path in native order: the resident kernel, the persistent kernel and the
+    two-launches-per-iteration loop against the oracle's CG."""
+    m, rng, ref, fdm = setup_square(name)
+    b = rand_cvec(rng, m)
+    fdm.set_fast_path(2 + 256 * 3)
+    if solver == "persistent":
+        monkeypatch.setenv("SQ_NO_RESIDENT_CG", "1")
+    elif solver == "launches":
+        monkeypatch.setenv("SQ_NO_PERSISTENT_CG", "1")
+    xr, itr, epsr = ref.cg(b, tol=1e-14, maxiter=20000)
+    xg, itg, epsg = fdm.ldiv(b, tol=1e-14, maxiter=20000)
+    assert epsg < 1e-14 and epsr < 1e-14
+    assert relerr(xg, xr) < 1e-11
+    for tol in (1e-5, 1e-10):
+        _, itr, _ = ref.cg(b, tol=tol, maxiter=20000)
+        xg, itg, epsg = fdm.ldiv(b, tol=tol, maxiter=20000)
+        assert abs(itg - itr) <= 1, (name, solver, tol, itg, itr)
+        assert epsg < tol
+        assert abs(relerr(ref.mul_MtM(xg), b) - epsg) < 1e-3 * tol + 1e-13       # the returned eps is the true residual
+    _, it0, _ = fdm.ldiv(b, x0=xg, tol=1e-9)
+    assert it0 == 0
+    _, itc, epsc = fdm.ldiv(b, tol=1e-14, maxiter=3)
+    assert itc == 3 and epsc > 1e-14
+    # warm start from a perturbed solution converges to the same answer
+    x2, it2, _ = fdm.ldiv(b, x0=xg * (1 + 1e-3), tol=1e-12)
+    assert relerr(x2, xr) < 1e-9 and it2 > 0
