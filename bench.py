@@ -28,6 +28,25 @@ TOL_ACTION, TOL_FORCE, MAXITER = 1e-10, 1e-5, 10000        # tutorials/holstein_
 ITERS_FILE = os.path.join(ROOT, "profiles", "bench_state.json")
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries loaded along the way (NCCL prints its version banner to stdout
+    when a communicator is created) must not add to it: point fd 1 at stderr for the run and keep the real stdout aside."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def cdw_start(m, seed):
     """Synthetic but physical start: the staggered (charge-density-wave) phonon order of the half-filled
     Holstein model at beta = 20, plus free-phonon thermal fluctuations.  Warm-up trajectories relax it."""
@@ -169,7 +188,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "trajectories/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "detail": info}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(m, precond, where):
@@ -389,12 +408,13 @@ def run_native(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "cg_iters_per_trajectory": iters_per_traj, "matvecs_per_trajectory": matvecs_per_traj,
             "acceptance": accepted / args.steps, "tau_slab": tau_slab}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

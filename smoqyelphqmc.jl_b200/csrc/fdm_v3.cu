@@ -650,6 +650,39 @@ int fdm_v3_launch_cg(sq_fdm *f, double2 *z, const double2 *p_old, double2 *p_new
 // fence orders every earlier write of the CTA (cumulative through the preceding __syncthreads), so passing the sum also
 // publishes the boundary-r halo slices.  No L1 invalidation: shared data is only ever read with L2 loads.
 struct V3Slot { double v; unsigned long long e; };
+// warp-level part: `t` is this CTA's partial (same value in all lanes); returns the grid total (all lanes)
+__device__ __forceinline__ double v3_slot_sum(double t, V3Slot *slots, unsigned int stride, unsigned long long epoch, unsigned int nblk,
+                                              unsigned int bid, bool &bad) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(&slots[(size_t)bid * stride]), "l"(__double_as_longlong(t)), "l"(epoch) : "memory");
+    }
+    // one 16-byte load returns (value, epoch) of a slot together; up to 8 slots per lane are in flight per polling round
+    double s = 0.0;
+    const long long t0 = clock64();
+    for (unsigned int base = 0; base < nblk; base += 256) {
+        long long val[8];
+        unsigned long long ep[8];
+        while (true) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {                         // all loads first: one L2 round trip per polling round
+                const unsigned int q = base + lane + 32 * u;
+                ep[u] = epoch;
+                val[u] = 0;
+                if (q < nblk) asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(val[u]), "=l"(ep[u]) : "l"(&slots[(size_t)q * stride]) : "memory");
+            }
+            bool ready = true;
+#pragma unroll
+            for (int u = 0; u < 8; u++) ready = ready && (ep[u] >= epoch);
+            if (ready) break;
+            if (clock64() - t0 > 4000000000LL) { bad = true; break; }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) s += __longlong_as_double(val[u]);
+    }
+    return warp_sum(s);
+}
 __device__ __forceinline__ double v3_grid_sum(double acc, double *red, double *sh_out, V3Slot *slots, unsigned int stride,
                                               unsigned long long epoch, unsigned int nblk, unsigned int bid, bool &aborted) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -660,34 +693,9 @@ __device__ __forceinline__ double v3_grid_sum(double acc, double *red, double *s
     if (warp == 0) {
         double t = lane < nw ? red[lane] : 0.0;
         t = warp_sum(t);
-        if (lane == 0) {
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
-            asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(&slots[(size_t)bid * stride]), "l"(__double_as_longlong(t)), "l"(epoch) : "memory");
-        }
-        // one 16-byte load returns (value, epoch) of a slot together; up to 8 slots per lane are in flight per polling round
-        double s = 0.0;
-        const long long t0 = clock64();
-        for (unsigned int base = 0; base < nblk; base += 256) {
-            long long val[8];
-            unsigned long long ep[8];
-            while (true) {
-#pragma unroll
-                for (int u = 0; u < 8; u++) {                     // all loads first: one L2 round trip per polling round
-                    const unsigned int q = base + lane + 32 * u;
-                    ep[u] = epoch;
-                    val[u] = 0;
-                    if (q < nblk) asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(val[u]), "=l"(ep[u]) : "l"(&slots[(size_t)q * stride]) : "memory");
-                }
-                bool ready = true;
-#pragma unroll
-                for (int u = 0; u < 8; u++) ready = ready && (ep[u] >= epoch);
-                if (ready) break;
-                if (clock64() - t0 > 4000000000LL) { bad = 1; break; }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) s += __longlong_as_double(val[u]);
-        }
-        s = warp_sum(s);
+        bool b = false;
+        const double s = v3_slot_sum(t, slots, stride, epoch, nblk, bid, b);
+        bad = b ? 1 : 0;
         if (lane == 0) *sh_out = s;
     }
     aborted = __syncthreads_or(bad) != 0;
@@ -701,7 +709,7 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
     constexpr int N = G::N;
     extern __shared__ double smem[];
     __shared__ double red[32];
-    __shared__ double sh[2];
+    __shared__ double sh[3];
     const int S = P.S, L = P.L;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int part = wid / (S + 1), k = wid - part * (S + 1);
@@ -755,10 +763,10 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
         const double2 *gr = gslice(C.r, l);
         for (int e = lane; e < N / 2; e += 32) Pb[(size_t)q * (N / 2) + e] = gr[e];
     }
+    __syncthreads();                                      // p0 of all slices (own + halo) is in Pb
 #pragma unroll 1
     while (it < C.maxiter) {
         it++;
-        __syncthreads();                                  // p of all slices (own + halo) is in Pb
         double acc = 0.0;
         if (active) {
 #pragma unroll
@@ -769,6 +777,7 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
                     v[r][2 * jp] = a.x; v[r][2 * jp + 1] = a.y;
                 }
             E.template apply_B<1>(v, lB, P);
+            if (k == ns && it > 1) asm volatile("bar.sync %0, 64;" ::"r"(1 + part) : "memory");       // upper halo slice rebuilt by warp 0
 #pragma unroll
             for (int r = 0; r < RY; r++)
 #pragma unroll
@@ -784,8 +793,29 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
                 }
         }
         V3R_STAMP(0);
-        if (owner) E.template apply_B<1>(v, lB, P);
-        __syncthreads();
+        // First grid-wide sum (p.Ap = |M p|^2), overlapped with the second B: every warp leaves its partial in shared memory
+        // and arrives at a named barrier without waiting; warp 0 (which owns no slice and would idle through the second
+        // B) adds them up, publishes the CTA's slot and collects the grid total while the owners compute.
+        {
+            const double t = warp_sum(acc);
+            if (lane == 0) red[wid] = t;
+        }
+        if (wid != 0) {
+            __threadfence_block();
+            asm volatile("bar.arrive 3, %0;" ::"r"((int)blockDim.x) : "memory");
+            if (owner) E.template apply_B<1>(v, lB, P);
+        } else {
+            asm volatile("bar.sync 3, %0;" ::"r"((int)blockDim.x) : "memory");
+            const int nw = blockDim.x >> 5;
+            double t = lane < nw ? red[lane] : 0.0;
+            t = warp_sum(t);
+            bool bad = false;
+            const double tot = v3_slot_sum(t, reinterpret_cast<V3Slot *>(C.part_a), C.slot_stride, (unsigned long long)it, nblk, bid, bad);
+            if (lane == 0) { sh[0] = tot; sh[1] = bad ? 1.0 : 0.0; }
+        }
+        __syncthreads();                                  // w of all slices is in W, p.Ap in sh[0]
+        if (sh[1] != 0.0) { done = 3; break; }
+        const double pAp = sh[0];
         if (owner) {                                      // z[lo] = w[lo] -/+ B w[lo + 1], stays in registers
 #pragma unroll
             for (int r = 0; r < RY; r++)
@@ -798,8 +828,6 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
         }
         V3R_STAMP(1);
         bool aborted;
-        const double pAp = v3_grid_sum(acc, red, &sh[0], reinterpret_cast<V3Slot *>(C.part_a), C.slot_stride, (unsigned long long)it, nblk, bid, aborted);
-        if (aborted) { done = 3; break; }
         V3R_STAMP(2);
         const double alpha = rz / pAp;
         acc = 0.0;
@@ -821,7 +849,7 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
                 }
         }
         V3R_STAMP(3);
-        const double rr = v3_grid_sum(acc, red, &sh[1], reinterpret_cast<V3Slot *>(C.part_b), C.slot_stride, (unsigned long long)it, nblk, bid, aborted);
+        const double rr = v3_grid_sum(acc, red, &sh[2], reinterpret_cast<V3Slot *>(C.part_b), C.slot_stride, (unsigned long long)it, nblk, bid, aborted);
         if (aborted) { done = 3; break; }
         V3R_STAMP(4);
         eps = sqrt(rr) / normb;
@@ -829,7 +857,7 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
         if (!(eps == eps)) { done = 2; break; }
         beta = rr / rz;
         rz = rr;
-        // p = r + beta p: own slice from registers, halo slices from the neighbours' boundary r
+        // p = r + beta p: own slice from registers
         if (owner) {
 #pragma unroll
             for (int r = 0; r < RY; r++)
@@ -839,18 +867,32 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
                     Pb[(size_t)k * (N / 2) + el(r, jp)] = make_double2(fma(beta, pv.x, rr_[r][2 * jp]), fma(beta, pv.y, rr_[r][2 * jp + 1]));
                 }
         }
-        if (k == 0) {                                      // warp 0 owns no slice: it rebuilds both halo slices
-#pragma unroll 1
-            for (int side = 0; side < 2; side++) {
-                const int q = side ? ns + 1 : 0;
-                const double2 *h = side ? hslice(right, 0) : hslice(left, 1);
+        __syncthreads();                                  // own p slices are in Pb: the owners start the next B right away
+        if (k == 0) {
+            // Warp 0 of each part owns no slice: it rebuilds the two halo slices from the neighbours' boundary r while the
+            // owners already run their first B.  All L2 loads are issued first (one round trip); the upper slice is
+            // finished first and handed to warp ns (named barrier), the lower one feeds this warp's own B.
+            double2 hu[N / 64], hl[N / 64];
+            const double2 *gu = hslice(right, 0), *gl = hslice(left, 1);
 #pragma unroll
-                for (int u = 0; u < N / 64; u++) {
-                    const int e = lane + 32 * u;
-                    const double2 rv = __ldcg(h + e), pv = Pb[(size_t)q * (N / 2) + e];
-                    Pb[(size_t)q * (N / 2) + e] = make_double2(fma(beta, pv.x, rv.x), fma(beta, pv.y, rv.y));
-                }
+            for (int u = 0; u < N / 64; u++) hu[u] = __ldcg(gu + lane + 32 * u);
+#pragma unroll
+            for (int u = 0; u < N / 64; u++) hl[u] = __ldcg(gl + lane + 32 * u);
+#pragma unroll
+            for (int u = 0; u < N / 64; u++) {
+                const size_t e = (size_t)(ns + 1) * (N / 2) + lane + 32 * u;
+                const double2 pv = Pb[e];
+                Pb[e] = make_double2(fma(beta, pv.x, hu[u].x), fma(beta, pv.y, hu[u].y));
             }
+            __threadfence_block();
+            asm volatile("bar.arrive %0, 64;" ::"r"(1 + part) : "memory");
+#pragma unroll
+            for (int u = 0; u < N / 64; u++) {
+                const size_t e = lane + 32 * u;
+                const double2 pv = Pb[e];
+                Pb[e] = make_double2(fma(beta, pv.x, hl[u].x), fma(beta, pv.y, hl[u].y));
+            }
+            __syncwarp();
         }
         V3R_STAMP(5);
     }

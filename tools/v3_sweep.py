@@ -1,0 +1,38 @@
+"""Size sweep of the fused M^T M v kernel (register path, native order): 32 x 32 Holstein lattice, growing number of time
+slices.  Shows where the kernel stops being latency bound (one wave of warps at the named size) and what fraction of the
+measured HBM peak it reaches once the vectors leave L2.  Prints one JSON line per size."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+from smoqyelph_b200 import model as mdl, api
+import bench
+
+peak, src = bench.measured_peak()
+flush = torch.zeros(64 * 1024 * 1024, device="cuda")
+for Lx, Ly, beta in ((32, 32, 20.0), (32, 32, 40.0), (32, 32, 80.0), (32, 32, 160.0), (32, 32, 320.0), (32, 32, 640.0), (32, 64, 320.0)):
+    m = mdl.holstein_square(Lx, Ly, beta)
+    fdm = api.FermionDetMatrix(m, sym=True)
+    elph = api.ElectronPhononParameters(m, fdm)
+    rng = np.random.default_rng(0)
+    elph.x = m.random_fields(rng, smooth=True); elph.update_fdm()
+    n = m.N * m.Ltau
+    d_in = torch.randn(n, 2, dtype=torch.float64, device="cuda"); d_out = torch.zeros_like(d_in)
+    B = 40 * m.N * m.Ltau + 16 * m.Nh
+    best = None
+    for S in (1, 2, 3, 4, 5, 7):
+        fdm.set_fast_path(2 + 256 * S)
+        if fdm.tuning["path"] != 3:
+            continue
+        hot = fdm.time_mul(102, d_out.data_ptr(), d_in.data_ptr(), 100)
+        if best is None or hot < best[1]:
+            best = (S, hot)
+    fdm.set_fast_path(2 + 256 * best[0])
+    cold = fdm.time_mul(102, d_out.data_ptr(), d_in.data_ptr(), 30, flush.data_ptr(), flush.numel() * 4)
+    print(json.dumps({"lattice": f"{Lx}x{Ly}", "Ltau": m.Ltau, "vector_MB": round(n * 16 / 1e6, 1), "S": best[0],
+                      "us_back_to_back": round(best[1], 2), "us_l2_flushed": round(cold, 2), "algorithmic_MB": round(B / 1e6, 2),
+                      "GBs_back_to_back": round(B / best[1] / 1e3), "frac_back_to_back": round(B / best[1] / 1e3 / peak, 3),
+                      "GBs_l2_flushed": round(B / cold / 1e3), "frac_l2_flushed": round(B / cold / 1e3 / peak, 3),
+                      "fp64_issue_floor_us": round(2 * m.Ltau * m.N * 2 * 36 / (148 * 64 * 1.965e3), 2)}), flush=True)
+    del fdm, elph
