@@ -147,11 +147,16 @@ struct V3Lane {
     __device__ __forceinline__ void apply_B(double (&v)[RY][4], int l, const V3Params &P) const {
         // NAT: exp(-dtau V) x prod_c cosh_c^2 in the native order [l][r][j/2][lane][j%2] (one coalesced 16-byte load per two
         // sites), and the scaled rotations (rot1<1>)
-        const double *ev = NAT ? P.expVn + (size_t)l * N + 2 * (threadIdx.x & 31) : P.expV + (size_t)l * N + site0;
+        apply_B_ev<NAT, 0>(v, NAT ? P.expVn + (size_t)l * N + 2 * (threadIdx.x & 31) : P.expV + (size_t)l * N + site0);
+    }
+    // ev: this lane's first diagonal element of the slice; SM = 1: the slice (native order) is in shared memory
+    template <int NAT, int SM>
+    __device__ __forceinline__ void apply_B_ev(double (&v)[RY][4], const double *ev) const {
         step<3, NAT>(v); step<2, NAT>(v); step<1, NAT>(v); step<0, NAT>(v);
 #pragma unroll
         for (int r = 0; r < RY; r++) {
-            const double2 e01 = __ldg((const double2 *)(ev + (NAT ? 128 * r : LX * r))), e23 = __ldg((const double2 *)(ev + (NAT ? 128 * r + 64 : LX * r + 2)));
+            const double2 *q01 = (const double2 *)(ev + (NAT ? 128 * r : LX * r)), *q23 = (const double2 *)(ev + (NAT ? 128 * r + 64 : LX * r + 2));
+            const double2 e01 = SM ? *q01 : __ldg(q01), e23 = SM ? *q23 : __ldg(q23);
             v[r][0] *= e01.x; v[r][1] *= e01.y; v[r][2] *= e23.x; v[r][3] *= e23.y;
         }
         step<0, NAT>(v); step<1, NAT>(v); step<2, NAT>(v); step<3, NAT>(v);
@@ -650,7 +655,9 @@ int fdm_v3_launch_cg(sq_fdm *f, double2 *z, const double2 *p_old, double2 *p_new
 // fence orders every earlier write of the CTA (cumulative through the preceding __syncthreads), so passing the sum also
 // publishes the boundary-r halo slices.  No L1 invalidation: shared data is only ever read with L2 loads.
 struct V3Slot { double v; unsigned long long e; };
-// warp-level part: `t` is this CTA's partial (same value in all lanes); returns the grid total (all lanes)
+// warp-level: `t` is this CTA's partial (same value in all lanes); publishes it and returns the grid total (all lanes).
+// One warp polls with up to 8 slots per lane in flight per round.  (Measured alternatives: every thread of the CTA polling
+// one slot each, or two warps sharing the slots, were 0.5 - 1 us SLOWER per sum -- more pollers, more L2 contention.)
 __device__ __forceinline__ double v3_slot_sum(double t, V3Slot *slots, unsigned int stride, unsigned long long epoch, unsigned int nblk,
                                               unsigned int bid, bool &bad) {
     const int lane = threadIdx.x & 31;
@@ -658,7 +665,6 @@ __device__ __forceinline__ double v3_slot_sum(double t, V3Slot *slots, unsigned 
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
         asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(&slots[(size_t)bid * stride]), "l"(__double_as_longlong(t)), "l"(epoch) : "memory");
     }
-    // one 16-byte load returns (value, epoch) of a slot together; up to 8 slots per lane are in flight per polling round
     double s = 0.0;
     const long long t0 = clock64();
     for (unsigned int base = 0; base < nblk; base += 256) {
@@ -666,7 +672,7 @@ __device__ __forceinline__ double v3_slot_sum(double t, V3Slot *slots, unsigned 
         unsigned long long ep[8];
         while (true) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) {                         // all loads first: one L2 round trip per polling round
+            for (int u = 0; u < 8; u++) {                         // all loads first, then the checks
                 const unsigned int q = base + lane + 32 * u;
                 ep[u] = epoch;
                 val[u] = 0;
@@ -708,8 +714,8 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
     typedef V3Lane<LXL, RY> G;
     constexpr int N = G::N;
     extern __shared__ double smem[];
-    __shared__ double red[32];
-    __shared__ double sh[3];
+    __shared__ double red[64];
+    __shared__ double sh[4];
     const int S = P.S, L = P.L;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int part = wid / (S + 1), k = wid - part * (S + 1);
@@ -725,6 +731,10 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
     const double sg = (lB == 0) ? 1.0 : -1.0;
     double2 *Pb = reinterpret_cast<double2 *>(smem) + (size_t)part * (S + 2) * (N / 2);          // [q = 0 .. S+1][N/2]
     double2 *W = reinterpret_cast<double2 *>(smem) + (size_t)2 * (S + 2) * (N / 2) + (size_t)part * S * (N / 2);
+    // exp(-dtau V) (native order, scaled) of the S+1 slices this CTA applies, shared by both parts: the grid-wide sums fence at
+    // gpu scope, which invalidates L1, so global loads inside B would go to L2 in every iteration
+    double *EV = smem + (size_t)2 * (2 * S + 2) * N;
+    const double *evk = EV + (size_t)k * N + 2 * lane;
     auto el = [&](int r, int jp) -> int { return (r * 2 + jp) * 32 + lane; };                    // double2 index inside a slice-part
     auto gslice = [&](const double *base, int l) -> const double2 * { return reinterpret_cast<const double2 *>(base + ((size_t)l * 2 + part) * N); };
     // halo buffer: [cta][side][part][N] doubles; side 0 = first own slice, 1 = last own slice
@@ -735,6 +745,7 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
     unsigned int epoch = 0;
     int it = 0, done = 0;
     double v[RY][4], xr[RY][4], rr_[RY][4];
+    if (threadIdx.x == 0) sh[3] = 0.0;
 #ifdef SQ_V3_STAMPS
     long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = 0;
     const bool stamp = P.dbg && bid == 0 && threadIdx.x == 32;
@@ -743,6 +754,10 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
 #else
 #define V3R_STAMP(q) do { } while (0)
 #endif
+    if (part == 0 && active) {
+        const double2 *g = reinterpret_cast<const double2 *>(P.expVn + (size_t)lB * N);
+        for (int e = lane; e < N / 2; e += 32) reinterpret_cast<double2 *>(EV + (size_t)k * N)[e] = __ldg(g + e);
+    }
     // ---- initial state: x, r of the own slice in registers; p = r for own + halo slices in shared memory
     if (owner) {
         const double2 *gx = gslice(C.x, lo), *gr = gslice(C.r, lo);
@@ -776,7 +791,7 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
                     const double2 a = Pb[(size_t)k * (N / 2) + el(r, jp)];
                     v[r][2 * jp] = a.x; v[r][2 * jp + 1] = a.y;
                 }
-            E.template apply_B<1>(v, lB, P);
+            E.template apply_B_ev<1, 1>(v, evk);
             if (k == ns && it > 1) asm volatile("bar.sync %0, 64;" ::"r"(1 + part) : "memory");       // upper halo slice rebuilt by warp 0
 #pragma unroll
             for (int r = 0; r < RY; r++)
@@ -803,7 +818,7 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
         if (wid != 0) {
             __threadfence_block();
             asm volatile("bar.arrive 3, %0;" ::"r"((int)blockDim.x) : "memory");
-            if (owner) E.template apply_B<1>(v, lB, P);
+            if (owner) E.template apply_B_ev<1, 1>(v, evk);
         } else {
             asm volatile("bar.sync 3, %0;" ::"r"((int)blockDim.x) : "memory");
             const int nw = blockDim.x >> 5;
@@ -811,10 +826,10 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
             t = warp_sum(t);
             bool bad = false;
             const double tot = v3_slot_sum(t, reinterpret_cast<V3Slot *>(C.part_a), C.slot_stride, (unsigned long long)it, nblk, bid, bad);
-            if (lane == 0) { sh[0] = tot; sh[1] = bad ? 1.0 : 0.0; }
+            if (lane == 0) { sh[0] = tot; if (bad) sh[3] = 1.0; }
         }
         __syncthreads();                                  // w of all slices is in W, p.Ap in sh[0]
-        if (sh[1] != 0.0) { done = 3; break; }
+        if (sh[3] != 0.0) { done = 3; break; }
         const double pAp = sh[0];
         if (owner) {                                      // z[lo] = w[lo] -/+ B w[lo + 1], stays in registers
 #pragma unroll
@@ -939,7 +954,7 @@ bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, double2 *halo, CgStat
     S = std::max(S, 2);
     if (S > 3 || nsl < S) return false;                          // 2 (S+1) warps <= 8
     const int grid = (nsl + S - 1) / S, T = 64 * (S + 1);
-    const size_t smem = (size_t)2 * (2 * S + 2) * f->N * sizeof(double);
+    const size_t smem = ((size_t)2 * (2 * S + 2) + (S + 1)) * f->N * sizeof(double);
     if (smem > f->smem_optin || grid > f->num_sms || grid < 2) return false;
     if ((size_t)grid * 4 * f->N > (size_t)2 * f->L * f->N) return false;      // halo scratch is one vector
     V3Params P;
