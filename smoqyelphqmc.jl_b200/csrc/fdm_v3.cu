@@ -931,6 +931,282 @@ k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Resident CG with ONE grid-wide sum per iteration.
+//
+// A grid-wide sum costs >= 2 us on this two-die part and the textbook recurrence needs two (p.Ap, then |r_new|^2).  Both
+// follow from four sums taken BEFORE the update:
+//     a = |M p|^2 = p.Ap,   b = r.z,   c = |z|^2,   d = |r|^2            (z = A p, r the current residual)
+//     alpha = d / a,   |r - alpha z|^2 = d - 2 alpha b + alpha^2 c,   beta = |r_new|^2 / d
+// d is the exact norm of the stored residual, recomputed every iteration, so the estimate never feeds back into itself (no
+// drift); its rounding error is a few ulp of d, the order of the error of the updated residual itself.  The estimate drives
+// beta and the stopping test; a positive test (and the maxiter exit) is confirmed with the exact |r_new|^2 -- one extra
+// sum, once per solve -- so the returned eps is exact and the solver never stops early.
+// Halo: with alpha and beta known to everybody, a CTA can update its copies of the neighbours' boundary r and p itself
+// if it knows their boundary z: r_h -= alpha z_h, p_h = r_h + beta p_h (the same fma's the owner executes: same bits).
+// So the boundary slices of z are stored before the sum -- its fence publishes them -- and read after it.
+// The four partials travel as two 16-byte stores per CTA; the two low mantissa bits of every double carry the iteration
+// count mod 4 as validity tag (slot arrays alternate with the parity of the iteration), so one polling load returns two
+// values and their tag together.
+// ---------------------------------------------------------------------------------------------------
+struct CgResident1 {
+    double *x;                  // native order, in: start vector, out: solution
+    const double *r;            // native order, initial residual
+    CgState *state;             // in: normb, tol, eps ; out: iters, eps, done
+    char *slots;                // 2 arrays (iteration parity) x nblk x slot_stride bytes: (a, b), (c, d) of every CTA
+    char *slots_check;          // nblk x slot_stride bytes: (value, epoch) slots of the exact check
+    unsigned int slot_stride;   // bytes
+    size_t slot_array_bytes;
+    double *halo;               // [cta][side][part][N] boundary slices of z
+    int maxiter;
+};
+
+__device__ __forceinline__ double v3_tag(double x, long long tag) { return __longlong_as_double((__double_as_longlong(x) & ~3LL) | tag); }
+
+// Two warps share the work: warp `half` (0 or 1) publishes and polls the 16-byte half `half` of every slot -- (a, b) or (c, d).
+// All lanes hold the CTA's two partials of that half in t[]; returns the two grid totals (identical bits in every CTA).
+__device__ __forceinline__ void v3_slot_sum2(double (&t)[2], int half, char *slots, unsigned int stride_bytes, long long tag, unsigned int nblk,
+                                             unsigned int bid, bool &bad) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        char *mine = slots + (size_t)bid * stride_bytes + 16 * half;
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(mine), "d"(v3_tag(t[0], tag)), "d"(v3_tag(t[1], tag)) : "memory");
+    }
+    double s[2] = {0.0, 0.0};
+    const long long t0 = clock64();
+    for (unsigned int base = 0; base < nblk; base += 256) {
+        long long val[8][2];
+        while (true) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {                         // all loads first, then the checks
+                const unsigned int q = base + lane + 32 * u;
+                val[u][0] = val[u][1] = tag;
+                if (q < nblk) asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(val[u][0]), "=l"(val[u][1]) : "l"(slots + (size_t)q * stride_bytes + 16 * half) : "memory");
+            }
+            bool ready = true;
+#pragma unroll
+            for (int u = 0; u < 8; u++) ready = ready && ((val[u][0] & 3LL) == tag) && ((val[u][1] & 3LL) == tag);
+            if (ready) break;
+            if (clock64() - t0 > 4000000000LL) { bad = true; break; }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const unsigned int q = base + lane + 32 * u;
+            if (q < nblk) { s[0] += __longlong_as_double(val[u][0]); s[1] += __longlong_as_double(val[u][1]); }
+        }
+    }
+    t[0] = warp_sum(s[0]);
+    t[1] = warp_sum(s[1]);
+}
+
+template <int LXL, int RY>
+__global__ void __launch_bounds__(256, 1)
+k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
+    typedef V3Lane<LXL, RY> G;
+    constexpr int N = G::N;
+    extern __shared__ double smem[];
+    __shared__ double red[4 * 8];
+    __shared__ double sh[6];
+    const int S = P.S, L = P.L;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int part = wid / (S + 1), k = wid - part * (S + 1);
+    G E;
+    E.template init<1>(P, part);
+    const int l0 = P.lb + blockIdx.x * S;
+    const int ns = min(S, P.le - l0);
+    const unsigned int nblk = gridDim.x, bid = blockIdx.x;
+    const bool active = k <= ns, owner = active && k >= 1, publish = k < ns;
+    int lself = l0 + k;
+    lself = lself >= L ? lself - L : lself;
+    const int lB = lself, lo = l0 + k - 1;               // owner: slice lo
+    const double sg = (lB == 0) ? 1.0 : -1.0;
+    // shared memory (doubles): p [part][S+2][N] | w [part][S][N] | exp(-dtau V) [S+1][N] | r of the halo slices [part][2][N]
+    double2 *Pb = reinterpret_cast<double2 *>(smem) + (size_t)part * (S + 2) * (N / 2);
+    double2 *W = reinterpret_cast<double2 *>(smem) + (size_t)2 * (S + 2) * (N / 2) + (size_t)part * S * (N / 2);
+    double *EV = smem + (size_t)2 * (2 * S + 2) * N;
+    double2 *Rh = reinterpret_cast<double2 *>(EV + (size_t)(S + 1) * N) + (size_t)part * 2 * (N / 2);
+    const double *evk = EV + (size_t)k * N + 2 * lane;
+    auto el = [&](int r, int jp) -> int { return (r * 2 + jp) * 32 + lane; };
+    auto gslice = [&](const double *base, int l) -> const double2 * { return reinterpret_cast<const double2 *>(base + ((size_t)l * 2 + part) * N); };
+    // boundary z: [parity of the iteration][cta][side][part][N]; side 0 = first own slice, 1 = last own slice
+    auto hslice = [&](int par, unsigned int cta, int side) -> double2 * { return reinterpret_cast<double2 *>(C.halo + ((((size_t)par * nblk + cta) * 2 + side) * 2 + part) * N); };
+    const unsigned int left = (bid + nblk - 1) % nblk, right = (bid + 1) % nblk;
+    const double normb = C.state->normb, tol = C.state->tol;
+    double eps = C.state->eps;
+    int it = 0, done = 0;
+    double v[RY][4], xr[RY][4], rr_[RY][4];
+    if (threadIdx.x == 0) sh[5] = 0.0;
+    if (part == 0 && active) {
+        const double2 *g = reinterpret_cast<const double2 *>(P.expVn + (size_t)lB * N);
+        for (int e = lane; e < N / 2; e += 32) reinterpret_cast<double2 *>(EV + (size_t)k * N)[e] = __ldg(g + e);
+    }
+    if (owner) {
+        const double2 *gx = gslice(C.x, lo), *gr = gslice(C.r, lo);
+#pragma unroll
+        for (int r = 0; r < RY; r++)
+#pragma unroll
+            for (int jp = 0; jp < 2; jp++) {
+                const double2 a = gx[el(r, jp)], b = gr[el(r, jp)];
+                xr[r][2 * jp] = a.x; xr[r][2 * jp + 1] = a.y;
+                rr_[r][2 * jp] = b.x; rr_[r][2 * jp + 1] = b.y;
+                Pb[(size_t)k * (N / 2) + el(r, jp)] = b;
+            }
+    }
+    if (k == 0) {                                         // r0 = p0 of the two halo slices
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            const int q = side ? ns + 1 : 0;
+            int l = side ? l0 + ns : l0 - 1;
+            l = l < 0 ? l + L : (l >= L ? l - L : l);
+            const double2 *gr = gslice(C.r, l);
+            for (int e = lane; e < N / 2; e += 32) { const double2 t = gr[e]; Pb[(size_t)q * (N / 2) + e] = t; Rh[(size_t)side * (N / 2) + e] = t; }
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    while (it < C.maxiter) {
+        it++;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (active) {
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 a = Pb[(size_t)k * (N / 2) + el(r, jp)];
+                    v[r][2 * jp] = a.x; v[r][2 * jp + 1] = a.y;
+                }
+            E.template apply_B_ev<1, 1>(v, evk);
+            if (k == ns && it > 1) asm volatile("bar.sync %0, 64;" ::"r"(1 + part) : "memory");       // upper halo slice rebuilt by warp 0
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 self = Pb[(size_t)(k + 1) * (N / 2) + el(r, jp)];
+                    const double w0 = fma(sg, v[r][2 * jp], self.x), w1 = fma(sg, v[r][2 * jp + 1], self.y);
+                    v[r][2 * jp] = w0; v[r][2 * jp + 1] = w1;
+                    if (publish) {
+                        acc[0] += w0 * w0;
+                        acc[0] += w1 * w1;
+                        W[(size_t)k * (N / 2) + el(r, jp)] = make_double2(w0, w1);
+                    }
+                }
+        }
+        if (owner) E.template apply_B_ev<1, 1>(v, evk);
+        __syncthreads();                                  // w of all slices is in W
+        if (owner) {                                      // z[lo] in registers; r.z, |z|^2, |r|^2; boundary z for the neighbours
+            double2 *h0 = (k == 1) ? hslice(it & 1, bid, 0) : nullptr, *h1 = (k == ns) ? hslice(it & 1, bid, 1) : nullptr;
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 w = W[(size_t)(k - 1) * (N / 2) + el(r, jp)];
+                    const double z0 = fma(sg, v[r][2 * jp], w.x), z1 = fma(sg, v[r][2 * jp + 1], w.y);
+                    v[r][2 * jp] = z0; v[r][2 * jp + 1] = z1;
+                    const double r0 = rr_[r][2 * jp], r1 = rr_[r][2 * jp + 1];
+                    acc[1] += r0 * z0; acc[1] += r1 * z1;
+                    acc[2] += z0 * z0; acc[2] += z1 * z1;
+                    acc[3] += r0 * r0; acc[3] += r1 * r1;
+                    if (h0) h0[el(r, jp)] = make_double2(z0, z1);
+                    if (h1) h1[el(r, jp)] = make_double2(z0, z1);
+                }
+        }
+        // ---- the grid-wide sum of (a, b, c, d)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double t = warp_sum(acc[c]);
+            if (lane == 0) red[c * 8 + wid] = t;
+        }
+        __syncthreads();
+        if (wid < 2) {                                    // warp 0: (a, b), warp 1: (c, d)
+            const int nw = blockDim.x >> 5;
+            double t[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) { t[c] = 0.0; for (int w = 0; w < nw; w++) t[c] += red[(2 * wid + c) * 8 + w]; }
+            bool bad = false;
+            v3_slot_sum2(t, wid, C.slots + (size_t)(it & 1) * C.slot_array_bytes, C.slot_stride, (long long)(it & 3), nblk, bid, bad);
+            if (lane == 0) { sh[2 * wid] = t[0]; sh[2 * wid + 1] = t[1]; if (bad) sh[5] = 1.0; }
+        }
+        __syncthreads();
+        if (sh[5] != 0.0) { done = 3; break; }
+        const double pAp = sh[0], rz = sh[1], zz = sh[2], rr_old = sh[3];
+        const double alpha = rr_old / pAp;
+        double rr_new = fma(alpha, fma(alpha, zz, -2.0 * rz), rr_old);       // |r - alpha z|^2
+        rr_new = rr_new > 0.0 ? rr_new : (rr_new == rr_new ? 0.0 : rr_new);
+        eps = sqrt(rr_new) / normb;
+        const bool stop_est = (eps < tol) || !(eps == eps) || it == C.maxiter;
+        const double beta = rr_new / rr_old;
+        double chk = 0.0;
+        if (owner) {                                      // x += alpha p ; r -= alpha z ; p = r + beta p
+#pragma unroll
+            for (int r = 0; r < RY; r++)
+#pragma unroll
+                for (int jp = 0; jp < 2; jp++) {
+                    const double2 pv = Pb[(size_t)k * (N / 2) + el(r, jp)];
+                    xr[r][2 * jp] = fma(alpha, pv.x, xr[r][2 * jp]);
+                    xr[r][2 * jp + 1] = fma(alpha, pv.y, xr[r][2 * jp + 1]);
+                    const double r0 = fma(-alpha, v[r][2 * jp], rr_[r][2 * jp]), r1 = fma(-alpha, v[r][2 * jp + 1], rr_[r][2 * jp + 1]);
+                    rr_[r][2 * jp] = r0; rr_[r][2 * jp + 1] = r1;
+                    chk += r0 * r0; chk += r1 * r1;
+                    Pb[(size_t)k * (N / 2) + el(r, jp)] = make_double2(fma(beta, pv.x, r0), fma(beta, pv.y, r1));
+                }
+        }
+        if (stop_est) {                                   // confirm with the exact |r_new|^2 (every CTA takes this branch together)
+            bool aborted;
+            const double rr_exact = v3_grid_sum(chk, red, &sh[4], reinterpret_cast<V3Slot *>(C.slots_check), C.slot_stride / 16, (unsigned long long)it, nblk, bid, aborted);
+            if (aborted) { done = 3; break; }
+            eps = sqrt(rr_exact) / normb;
+            if (eps < tol) { done = 1; break; }
+            if (!(eps == eps)) { done = 2; break; }
+            if (it == C.maxiter) break;
+        }
+        __syncthreads();                                  // own p slices are in Pb: the owners start the next B right away
+        if (k == 0) {
+            // warp 0 of each part owns no slice: it updates the copies of the neighbours' boundary r and p from their boundary z
+            // (visible since the sum) while the owners run their first B; upper slice first (handed to warp ns)
+            double2 zu[N / 64], zl[N / 64];
+            const double2 *gu = hslice(it & 1, right, 0), *gl = hslice(it & 1, left, 1);
+#pragma unroll
+            for (int u = 0; u < N / 64; u++) zu[u] = __ldcg(gu + lane + 32 * u);
+#pragma unroll
+            for (int u = 0; u < N / 64; u++) zl[u] = __ldcg(gl + lane + 32 * u);
+#pragma unroll
+            for (int u = 0; u < N / 64; u++) {
+                const size_t e = lane + 32 * u;
+                const double2 rv = Rh[(size_t)1 * (N / 2) + e], pv = Pb[(size_t)(ns + 1) * (N / 2) + e];
+                const double r0 = fma(-alpha, zu[u].x, rv.x), r1 = fma(-alpha, zu[u].y, rv.y);
+                Rh[(size_t)1 * (N / 2) + e] = make_double2(r0, r1);
+                Pb[(size_t)(ns + 1) * (N / 2) + e] = make_double2(fma(beta, pv.x, r0), fma(beta, pv.y, r1));
+            }
+            __threadfence_block();
+            asm volatile("bar.arrive %0, 64;" ::"r"(1 + part) : "memory");
+#pragma unroll
+            for (int u = 0; u < N / 64; u++) {
+                const size_t e = lane + 32 * u;
+                const double2 rv = Rh[e], pv = Pb[e];
+                const double r0 = fma(-alpha, zl[u].x, rv.x), r1 = fma(-alpha, zl[u].y, rv.y);
+                Rh[e] = make_double2(r0, r1);
+                Pb[e] = make_double2(fma(beta, pv.x, r0), fma(beta, pv.y, r1));
+            }
+            __syncwarp();
+        }
+    }
+    if (owner) {                                          // the solution
+        double2 *gx = reinterpret_cast<double2 *>(C.x + ((size_t)lo * 2 + part) * N);
+#pragma unroll
+        for (int r = 0; r < RY; r++)
+#pragma unroll
+            for (int jp = 0; jp < 2; jp++) gx[el(r, jp)] = make_double2(xr[r][2 * jp], xr[r][2 * jp + 1]);
+    }
+    if (bid == 0 && threadIdx.x == 0) {
+        CgState st = *C.state;
+        st.iters = it;
+        st.eps = eps;
+        st.done = done;
+        *C.state = st;
+    }
+}
+
 typedef void (*v3_resident_t)(const V3Params, const CgPersist3, double *);
 static v3_resident_t pick3_resident(int lxl, int ry) {
     if (lxl == 8 && ry == 4) return k_cg_v3_resident<8, 4>;
@@ -940,11 +1216,66 @@ static v3_resident_t pick3_resident(int lxl, int ry) {
     if (lxl == 4 && ry == 8) return k_cg_v3_resident<4, 8>;
     return nullptr;
 }
+typedef void (*v3_resident1_t)(const V3Params, const CgResident1);
+static v3_resident1_t pick3_resident1(int lxl, int ry) {
+    if (lxl == 8 && ry == 4) return k_cg_v3_resident1<8, 4>;
+    if (lxl == 8 && ry == 8) return k_cg_v3_resident1<8, 8>;
+    if (lxl == 4 && ry == 2) return k_cg_v3_resident1<4, 2>;
+    if (lxl == 4 && ry == 4) return k_cg_v3_resident1<4, 4>;
+    if (lxl == 4 && ry == 8) return k_cg_v3_resident1<4, 8>;
+    return nullptr;
+}
+
+// One-sum resident kernel (k_cg_v3_resident1).  Returns false if it cannot run (the caller falls back to the two-sum kernel).
+static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *state, i64 maxiter) {
+    v3_resident1_t k = pick3_resident1(f->v3_lxl, f->v3_ry);
+    if (!k || !f->v3_ok || !f->cs_coluni) return false;
+    const int nsl = f->slab_hi - f->slab_lo;
+    int S = (nsl + f->num_sms - 1) / f->num_sms;
+    if (const char *e = getenv("SQ_V3_RESIDENT_SLAB")) S = atoi(e);
+    S = std::max(S, 2);
+    if (S > 3 || nsl < S) return false;
+    const int grid = (nsl + S - 1) / S, T = 64 * (S + 1);
+    const size_t smem = (size_t)(5 * S + 9) * f->N * sizeof(double);
+    if (smem > f->smem_optin || grid > f->num_sms || grid < 2) return false;
+    V3Params P;
+    memset(&P, 0, sizeof(P));
+    P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = 4; P.nphase = 2;
+    for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = f->clo[c]; }
+    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p;
+    SQ_CUDA(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k, T, smem));
+    if (per_sm * f->num_sms < grid) return false;
+    unsigned int stride_bytes = 1024;
+    if (const char *e = getenv("SQ_V3_SLOT_STRIDE")) stride_bytes = (unsigned)atoi(e);
+    stride_bytes = std::max(32u, stride_bytes / 32 * 32);
+    const size_t arr = (size_t)grid * stride_bytes;
+    if (f->v3_slots.n < 3 * arr) f->v3_slots.alloc(3 * arr);
+    SQ_CUDA(cudaMemsetAsync(f->v3_slots.p, 0, 3 * arr, f->stream));
+    const size_t nh = (size_t)8 * grid * f->N;
+    if (f->v3_halo.n < nh) f->v3_halo.alloc(nh);
+    CgResident1 C;
+    memset(&C, 0, sizeof(C));
+    C.x = (double *)x; C.r = (const double *)r; C.state = state;
+    C.slots = f->v3_slots.p; C.slot_array_bytes = arr; C.slots_check = f->v3_slots.p + 2 * arr; C.slot_stride = stride_bytes;
+    C.halo = f->v3_halo.p; C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
+    void *args[] = {(void *)&P, (void *)&C};
+    SQ_CUDA(cudaLaunchCooperativeKernel((const void *)k, dim3(grid), dim3(T), args, smem, f->stream));
+    f->launches++;
+    return true;
+}
+
 // One CTA per SM.  x (in/out) and r (in) are native-order vectors; `halo` is scratch of at least one vector.
+// SQ_V3_RESIDENT=2 selects the two-sum kernel; the default is the one-sum kernel where it fits.
 // (A one-sum-per-iteration variant -- |r_new|^2 from d - 2 alpha b + alpha^2 c, halo slices of p through epoch flags -- was
 // built and measured at the same 11-12 us per iteration: the iteration is bounded by signalling latency, not by the number
 // of sums.  It is not in the tree; see DESIGN.md.)
 bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, double2 *halo, CgState *state, double *part_a, double *part_b, i64 maxiter) {
+    {
+        const char *sel = getenv("SQ_V3_RESIDENT");
+        if (!(sel && atoi(sel) == 2) && fdm_v3_cg_resident1(f, x, r, state, maxiter)) return true;
+    }
     v3_resident_t k2 = pick3_resident(f->v3_lxl, f->v3_ry);
     if (!k2 || !f->v3_ok || !f->cs_coluni) return false;
     const void *kern = (const void *)k2;

@@ -57,6 +57,7 @@ struct sq_fdm {
     DevBuf<double> v3_expVn;                 // exp(-dtau V) in the native order of the register path
     DevBuf<double2> v3_x, v3_r;              // CG vectors in native order
     i64 v3_expv_version = -1;
+    DevBuf<double> v3_halo;                  // boundary slices exchanged by the one-sum resident CG kernel
     DevBuf<char> v3_slots;                   // grid-sum slots of the resident CG kernel
     DevBuf<int> flag;                        // device scratch flags (4 ints: uniformity probe / grid barrier / abort)
     DevBuf<double> expV;                     // [l][i]
