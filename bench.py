@@ -346,12 +346,12 @@ def run_native(args):
                   "note": "back-to-back launches on this system are paced in ~2 us steps (profiles/README.md); a single-wave kernel of "
                           "~6 us cannot be timed below that from the host, which is why the solver is one resident launch"}
         if resident:
-            roofline = {"bound": "hbm", "kernel": "k_cg_v3_resident (whole CG solve in one launch; M^T M v once per iteration, x r p resident on chip)",
+            roofline = {"bound": "hbm", "kernel": "k_cg_v3_resident1 (whole CG solve in one launch; M^T M v once per iteration, x r p resident on chip)",
                         "achieved": Bk / t_iter / 1e9, "peak": peak, "unit": "GB/s", "frac": Bk / t_iter / 1e9 / peak,
                         "traffic": state.get("cg_resident_dram_bytes_per_iteration"), "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": Bk * nit, "algorithmic_bytes_per_unit": Bk, "unit_of_work": "one CG iteration = one fused M^T M v",
                         "units_per_launch": nit, "us_per_unit": t_iter * 1e6,
-                        "limiter": "latency: two grid-wide sums per iteration (~2 us each on this two-die part, tools/ubench/grid_sum.cu) + "
+                        "limiter": "latency: one grid-wide sum per iteration (>= 2 us on this two-die part, tools/ubench/grid_sum.cu) + "
                                    "FP64 issue of one wave; HBM traffic per iteration is ~0.1 MB because the working set stays on chip"}
         else:
             roofline = {"bound": "hbm", "kernel": matvec["kernel"], "achieved": Bk / t_cold / 1e9, "peak": peak, "unit": "GB/s",

@@ -1268,9 +1268,6 @@ static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *stat
 
 // One CTA per SM.  x (in/out) and r (in) are native-order vectors; `halo` is scratch of at least one vector.
 // SQ_V3_RESIDENT=2 selects the two-sum kernel; the default is the one-sum kernel where it fits.
-// (A one-sum-per-iteration variant -- |r_new|^2 from d - 2 alpha b + alpha^2 c, halo slices of p through epoch flags -- was
-// built and measured at the same 11-12 us per iteration: the iteration is bounded by signalling latency, not by the number
-// of sums.  It is not in the tree; see DESIGN.md.)
 bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, double2 *halo, CgState *state, double *part_a, double *part_b, i64 maxiter) {
     {
         const char *sel = getenv("SQ_V3_RESIDENT");
