@@ -126,6 +126,15 @@ int sq_elph_create(sq_elph **out, sq_fdm *f, double dtau, int64_t Nph, const dou
 int sq_elph_destroy(sq_elph *e);
 int sq_elph_set_x(sq_elph *e, const double *x);          /* (Nph x Ltau) */
 int sq_elph_get_x(sq_elph *e, double *x);
+/* x-mutations of the global moves, on the device (phonon indices 1-based, ranges inclusive):
+ *   reflection_update!  src/reflection_update.jl:94   `@. x_i = -x_i`            -> sq_elph_scale_x(e, p, p, -1)
+ *   swap_update!        src/swap_update.jl:95         `SmoQyDQMC.swap!(x_i, x_j)` -> sq_elph_swap_x(e, p_i, p_j)
+ *   radial_update!      src/radial_update.jl:114      `@. x' = expγ * x'`         -> sq_elph_scale_x(e, first, last, exp(γ))
+ * backup / restore implement the rejection branch (the reference undoes the mutation arithmetically, :152-166). */
+int sq_elph_scale_x(sq_elph *e, int64_t p_first, int64_t p_last, double factor);
+int sq_elph_swap_x(sq_elph *e, int64_t p_i, int64_t p_j);
+int sq_elph_backup_x(sq_elph *e);
+int sq_elph_restore_x(sq_elph *e);
 int sq_elph_shift_mu(sq_elph *e, double dmu);             /* V += -mu' + mu: update_chemical_potential.jl:66-67 */
 /* SmoQyDQMC.update!(fpi, elph, x, +1) followed by update!(fdm, fpi) (EFAPFFHMCUpdater.jl:152-153), on device */
 int sq_elph_refresh_fdm(sq_elph *e);

@@ -11,7 +11,8 @@ module SmoQyElPhB200
 using LinearAlgebra, Random
 import LinearAlgebra: mul!, lmul!, ldiv!
 import SmoQyDQMC
-import SmoQyDQMC: FermionPathIntegral, ElectronPhononParameters, hmc_update!, update_chemical_potential!
+import SmoQyDQMC: FermionPathIntegral, ElectronPhononParameters, hmc_update!, update_chemical_potential!,
+                  reflection_update!, swap_update!, radial_update!
 using Checkerboard: checkerboard_decomposition!
 
 export FermionDetMatrix, SymFermionDetMatrix, AsymFermionDetMatrix, KPMPreconditioner, PFFCalculator,
@@ -217,6 +218,70 @@ function hmc_update!(elph::ElectronPhononParameters{T,E}, u::EFAPFFHMCUpdater{E}
         SmoQyDQMC.update!(fermion_path_integral, elph, elph.x, x0)     # keep the host-side path integral consistent
     end
     return acc[] != 0, info[1]
+end
+
+
+# ---- global moves (src/reflection_update.jl, src/swap_update.jl, src/radial_update.jl) ---------------------------------
+# The mode sampling and the Metropolis test stay in Julia (SmoQyDQMC._sample_phonon_mode*, rand(rng)); the x-mutation, the
+# operator refresh and the two action evaluations run on the device.  Rejection restores the device copy of x exactly.
+function _global_move!(elph, p::PFFCalculator{E}, mutate_dev!::Function, mutate_host!::Function, logJ::E; fermion_path_integral,
+                       fermion_det_matrix, rng, preconditioner, tol::E, maxiter::Int) where {E}
+    e = p.elph
+    push_x!(e, elph.x)
+    check(ccall((:sq_elph_refresh_fdm, LIB), Cint, (Ptr{Cvoid},), e.h))
+    Sf = sample_pseudofermion_fields!(p, elph, fermion_det_matrix, rng)
+    Sb = Ref{Cdouble}(0); check(ccall((:sq_elph_bosonic_action, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}), e.h, Sb))
+    check(ccall((:sq_elph_backup_x, LIB), Cint, (Ptr{Cvoid},), e.h))
+    mutate_dev!(e)
+    check(ccall((:sq_elph_refresh_fdm, LIB), Cint, (Ptr{Cvoid},), e.h))
+    P = 0.0; iters = 0
+    try
+        Sf′, iters, ϵ = calculate_fermionic_action!(p, elph, fermion_det_matrix, preconditioner, rng, tol, maxiter)
+        Sb′ = Ref{Cdouble}(0); check(ccall((:sq_elph_bosonic_action, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}), e.h, Sb′))
+        P = min(1.0, exp(-((Sf′ + Sb′[]) - (Sf + Sb[])) + logJ))
+    catch err
+        err isa B200Error || rethrow()
+        @info "Failed to evaluate the fermionic action for the proposed state, update rejected." exception = err
+    end
+    if rand(rng) < P
+        x0 = copy(elph.x)
+        mutate_host!(elph.x)
+        SmoQyDQMC.update!(fermion_path_integral, elph, elph.x, x0)
+        return true, iters
+    end
+    check(ccall((:sq_elph_restore_x, LIB), Cint, (Ptr{Cvoid},), e.h))
+    check(ccall((:sq_elph_refresh_fdm, LIB), Cint, (Ptr{Cvoid},), e.h))
+    return false, iters
+end
+
+function reflection_update!(elph::ElectronPhononParameters{T,E}, p::PFFCalculator{E}; fermion_path_integral::FermionPathIntegral{T,E},
+                            fermion_det_matrix::FermionDetMatrix{T,E}, rng::AbstractRNG, preconditioner = I,
+                            tol::E = fermion_det_matrix.cgs.tol, maxiter::Int = fermion_det_matrix.cgs.maxiter, phonon_types = nothing) where {T,E}
+    pp = elph.phonon_parameters
+    mode = SmoQyDQMC._sample_phonon_mode(rng, pp.nphonon, pp.Nphonon ÷ pp.nphonon, pp.M, phonon_types)
+    _global_move!(elph, p, e -> check(ccall((:sq_elph_scale_x, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Cdouble), e.h, mode, mode, -1.0)),
+                  x -> (@views @. x[mode, :] = -x[mode, :]), zero(E); fermion_path_integral, fermion_det_matrix, rng, preconditioner, tol, maxiter)
+end
+
+function swap_update!(elph::ElectronPhononParameters{T,E}, p::PFFCalculator{E}; fermion_path_integral::FermionPathIntegral{T,E},
+                      fermion_det_matrix::FermionDetMatrix{T,E}, rng::AbstractRNG, preconditioner = I,
+                      tol::E = fermion_det_matrix.cgs.tol, maxiter::Int = fermion_det_matrix.cgs.maxiter, phonon_type_pairs = nothing) where {T,E}
+    pp = elph.phonon_parameters
+    i, j = SmoQyDQMC._sample_phonon_mode_pair(rng, pp.nphonon, pp.Nphonon ÷ pp.nphonon, pp.M, phonon_type_pairs)
+    _global_move!(elph, p, e -> check(ccall((:sq_elph_swap_x, LIB), Cint, (Ptr{Cvoid}, Int64, Int64), e.h, i, j)),
+                  x -> SmoQyDQMC.swap!(view(x, i, :), view(x, j, :)), zero(E); fermion_path_integral, fermion_det_matrix, rng, preconditioner, tol, maxiter)
+end
+
+function radial_update!(elph::ElectronPhononParameters{T,E}, p::PFFCalculator{E}; fermion_path_integral::FermionPathIntegral{T,E},
+                        fermion_det_matrix::FermionDetMatrix{T,E}, rng::AbstractRNG, preconditioner = I,
+                        tol::E = fermion_det_matrix.cgs.tol, maxiter::Int = fermion_det_matrix.cgs.maxiter, phonon_id = nothing, σ::E = 1.0) where {T,E}
+    pp = elph.phonon_parameters
+    Nc = pp.Nphonon ÷ pp.nphonon
+    first, last = isnothing(phonon_id) ? (1, pp.Nphonon) : ((phonon_id - 1) * Nc + 1, phonon_id * Nc)
+    d = count(isfinite, view(pp.M, first:last)) * fermion_path_integral.Lτ
+    γ = randn(rng) * σ / sqrt(d)
+    _global_move!(elph, p, e -> check(ccall((:sq_elph_scale_x, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Cdouble), e.h, first, last, exp(γ))),
+                  x -> (@views @. x[first:last, :] = exp(γ) * x[first:last, :]), d * γ; fermion_path_integral, fermion_det_matrix, rng, preconditioner, tol, maxiter)
 end
 
 # ---- GreensEstimator solves + update_chemical_potential! (src/Measurements/GreensEstimator.jl:63-175,

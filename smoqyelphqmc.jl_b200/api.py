@@ -271,6 +271,12 @@ class ElectronPhononParameters:
         check(self.L.sq_elph_bosonic_action(self.h, C.byref(s)))
         return s.value
 
+    # x-mutations of the global moves, on the device (0-based phonon indices here, 1-based in the C ABI)
+    def scale_x(self, p_first, p_last, factor): check(self.L.sq_elph_scale_x(self.h, int(p_first) + 1, int(p_last) + 1, float(factor)))
+    def swap_x(self, p_i, p_j): check(self.L.sq_elph_swap_x(self.h, int(p_i) + 1, int(p_j) + 1))
+    def backup_x(self): check(self.L.sq_elph_backup_x(self.h))
+    def restore_x(self): check(self.L.sq_elph_restore_x(self.h))
+
 
 class PFFCalculator:
     """PFFCalculator(elph, fdm) (src/PFFCalculator.jl:30-53)."""
@@ -442,3 +448,101 @@ def update_chemical_potential(fdm, greens, elph, mu, mu_new_fn, preconditioner=N
     elph.shift_mu(mu_new - mu)
     elph.update_fdm()
     return mu_new, iters
+
+
+# ------------------------------------------------------------------------------------------------------
+# global moves: reflection_update!, swap_update!, radial_update!
+# ------------------------------------------------------------------------------------------------------
+def _sample_phonon_mode(rng, model, phonon_types=None):
+    """SmoQyDQMC._sample_phonon_mode [unvendored]: a phonon type among `phonon_types` (all if None), then a unit cell,
+    uniformly; modes with infinite mass are frozen and never proposed."""
+    types = list(range(model.nphonon)) if phonon_types is None else list(phonon_types)
+    ncell = model.n_unit_cells
+    for _ in range(10000):
+        mode = int(types[rng.integers(len(types))]) * ncell + int(rng.integers(ncell))
+        if np.isfinite(model.Mass[mode]):
+            return mode
+    raise SqError("no phonon mode with finite mass among the requested phonon types")
+
+
+def _sample_phonon_mode_pair(rng, model, phonon_type_pairs=None):
+    """SmoQyDQMC._sample_phonon_mode_pair [unvendored]: a pair of phonon types, then two different unit cells."""
+    nph, ncell = model.nphonon, model.n_unit_cells
+    pairs = [(a, b) for a in range(nph) for b in range(nph)] if phonon_type_pairs is None else list(phonon_type_pairs)
+    for _ in range(10000):
+        a, b = pairs[int(rng.integers(len(pairs)))]
+        i, j = int(a) * ncell + int(rng.integers(ncell)), int(b) * ncell + int(rng.integers(ncell))
+        if i != j and np.isfinite(model.Mass[i]) and np.isfinite(model.Mass[j]):
+            return i, j
+    raise SqError("no pair of phonon modes with finite mass among the requested phonon type pairs")
+
+
+def _global_move(elph, pff, mutate, log_jacobian, preconditioner, tol, maxiter, R, u_accept, rng):
+    """Common body of the three moves (src/reflection_update.jl:67-176, swap_update.jl:68-176, radial_update.jl:88-193):
+    S = Sf + Sb on fresh pseudofermion fields, mutate x, refresh the operator, S' with the same fields, Metropolis test;
+    a failed solve (numerical instability) rejects the move.  Returns (accepted, iters, info)."""
+    Sf = pff.sample_pseudofermion_fields(R)
+    Sb = elph.bosonic_action()
+    elph.backup_x()
+    mutate()
+    elph.update_fdm()
+    dS, iters, stable = np.inf, 0, True
+    try:
+        Sf2, iters, _ = pff.calculate_fermionic_action(preconditioner=preconditioner, tol=tol, maxiter=maxiter)
+        dS = (Sf2 + elph.bosonic_action()) - (Sf + Sb)
+        stable = np.isfinite(dS)
+    except SqError:
+        stable = False
+    P = min(1.0, float(np.exp(-dS + log_jacobian))) if stable else 0.0
+    u = float(rng.random()) if u_accept is None else float(u_accept)
+    accepted = u < P
+    if not accepted:
+        elph.restore_x()
+        elph.update_fdm()
+    return accepted, int(iters), {"dS": float(dS), "P": P, "stable": stable}
+
+
+def reflection_update(elph, pff, rng=None, preconditioner=None, tol=None, maxiter=None, phonon_types=None, randoms=None):
+    """reflection_update!(elph, pff; fermion_path_integral, fermion_det_matrix, rng, preconditioner, tol, maxiter,
+    phonon_types) -> (accepted, iters)  (src/reflection_update.jl:23-177): x_p -> -x_p for one random phonon mode p.
+    `randoms` = {"mode": p, "R": ..., "u": ...} replaces the random draws (parity tests)."""
+    rng = np.random.default_rng() if rng is None else rng
+    rd = randoms or {}
+    mode = rd["mode"] if "mode" in rd else _sample_phonon_mode(rng, elph.model, phonon_types)
+    acc, iters, info = _global_move(elph, pff, lambda: elph.scale_x(mode, mode, -1.0), 0.0, preconditioner,
+                                    elph.fdm.tol if tol is None else tol, elph.fdm.maxiter if maxiter is None else maxiter,
+                                    rd.get("R"), rd.get("u"), rng)
+    reflection_update.last = dict(info, mode=mode)
+    return acc, iters
+
+
+def swap_update(elph, pff, rng=None, preconditioner=None, tol=None, maxiter=None, phonon_type_pairs=None, randoms=None):
+    """swap_update!(...) -> (accepted, iters)  (src/swap_update.jl:22-177): exchange the fields of two random modes.
+    `randoms` = {"modes": (i, j), "R": ..., "u": ...}."""
+    rng = np.random.default_rng() if rng is None else rng
+    rd = randoms or {}
+    i, j = rd["modes"] if "modes" in rd else _sample_phonon_mode_pair(rng, elph.model, phonon_type_pairs)
+    acc, iters, info = _global_move(elph, pff, lambda: elph.swap_x(i, j), 0.0, preconditioner,
+                                    elph.fdm.tol if tol is None else tol, elph.fdm.maxiter if maxiter is None else maxiter,
+                                    rd.get("R"), rd.get("u"), rng)
+    swap_update.last = dict(info, modes=(i, j))
+    return acc, iters
+
+
+def radial_update(elph, pff, rng=None, preconditioner=None, tol=None, maxiter=None, phonon_id=None, sigma=1.0, randoms=None):
+    """radial_update!(...; phonon_id, σ) -> (accepted, iters)  (src/radial_update.jl:23-195): x' -> e^γ x' for all modes (or all
+    modes of one phonon type), γ ~ N(0, σ²/d), d = (# finite-mass modes) Lτ, acceptance min(1, exp(-ΔS + d γ)).
+    `randoms` = {"gamma_normal": standard normal, "R": ..., "u": ...}."""
+    rng = np.random.default_rng() if rng is None else rng
+    rd = randoms or {}
+    m = elph.model
+    ncell = m.n_unit_cells
+    first, last = (0, m.Nph - 1) if phonon_id is None else (int(phonon_id) * ncell, (int(phonon_id) + 1) * ncell - 1)
+    d = int(np.count_nonzero(np.isfinite(m.Mass[first:last + 1]))) * m.Ltau
+    g = rd["gamma_normal"] if "gamma_normal" in rd else rng.standard_normal()
+    gamma = float(g) * sigma / np.sqrt(d)
+    acc, iters, info = _global_move(elph, pff, lambda: elph.scale_x(first, last, float(np.exp(gamma))), d * gamma, preconditioner,
+                                    elph.fdm.tol if tol is None else tol, elph.fdm.maxiter if maxiter is None else maxiter,
+                                    rd.get("R"), rd.get("u"), rng)
+    radial_update.last = dict(info, gamma=gamma, d=d)
+    return acc, iters

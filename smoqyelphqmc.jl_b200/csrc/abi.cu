@@ -370,6 +370,67 @@ int sq_elph_get_x(sq_elph *e, double *x) {
     SQ_CUDA(cudaStreamSynchronize(e->f->stream));
     SQ_CATCH
 }
+// x-mutations of the global moves (reflection_update!, swap_update!, radial_update!): device resident, phonon indices 1-based
+// like the Julia arrays.  x is [l][p] on the device.
+__global__ void k_x_scale_rows(double *x, int L, int Nph, int p_lo, int p_hi, double factor) {
+    const int np = p_hi - p_lo;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)L * np) return;
+    const int l = (int)(idx / np), p = p_lo + (int)(idx % np);
+    x[(size_t)l * Nph + p] *= factor;
+}
+__global__ void k_x_swap_rows(double *x, int L, int Nph, int pi, int pj) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    const double a = x[(size_t)l * Nph + pi], b = x[(size_t)l * Nph + pj];
+    x[(size_t)l * Nph + pi] = b;
+    x[(size_t)l * Nph + pj] = a;
+}
+int sq_elph_scale_x(sq_elph *e, int64_t p_first, int64_t p_last, double factor) {
+    SQ_TRY
+    SQ_REQUIRE(e, "NULL handle");
+    SQ_REQUIRE(p_first >= 1 && p_last >= p_first && p_last <= e->Nph, "phonon range out of bounds");
+    sq_fdm *f = e->f;
+    SQ_CUDA(cudaSetDevice(f->device));
+    const size_t tot = (size_t)f->L * (size_t)(p_last - p_first + 1);
+    k_x_scale_rows<<<(unsigned)((tot + 255) / 256), 256, 0, f->stream>>>(e->x.p, (int)f->L, (int)e->Nph, (int)p_first - 1, (int)p_last, factor);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+    SQ_CATCH
+}
+int sq_elph_swap_x(sq_elph *e, int64_t p_i, int64_t p_j) {
+    SQ_TRY
+    SQ_REQUIRE(e, "NULL handle");
+    SQ_REQUIRE(p_i >= 1 && p_i <= e->Nph && p_j >= 1 && p_j <= e->Nph, "phonon index out of bounds");
+    sq_fdm *f = e->f;
+    SQ_CUDA(cudaSetDevice(f->device));
+    if (p_i != p_j) {
+        k_x_swap_rows<<<(unsigned)((f->L + 127) / 128), 128, 0, f->stream>>>(e->x.p, (int)f->L, (int)e->Nph, (int)p_i - 1, (int)p_j - 1);
+        SQ_LAUNCH_CHECK();
+        f->launches++;
+    }
+    SQ_CATCH
+}
+int sq_elph_backup_x(sq_elph *e) {
+    SQ_TRY
+    SQ_REQUIRE(e, "NULL handle");
+    sq_fdm *f = e->f;
+    SQ_CUDA(cudaSetDevice(f->device));
+    const size_t n = (size_t)f->L * e->Nph;
+    if (e->x_backup.n < n) e->x_backup.alloc(n, false);
+    SQ_CUDA(cudaMemcpyAsync(e->x_backup.p, e->x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, f->stream));
+    SQ_CATCH
+}
+int sq_elph_restore_x(sq_elph *e) {
+    SQ_TRY
+    SQ_REQUIRE(e, "NULL handle");
+    sq_fdm *f = e->f;
+    SQ_CUDA(cudaSetDevice(f->device));
+    const size_t n = (size_t)f->L * e->Nph;
+    SQ_REQUIRE(e->x_backup.n >= n, "no backup of the phonon field");
+    SQ_CUDA(cudaMemcpyAsync(e->x.p, e->x_backup.p, n * sizeof(double), cudaMemcpyDeviceToDevice, f->stream));
+    SQ_CATCH
+}
 int sq_elph_shift_mu(sq_elph *e, double dmu) {
     SQ_TRY
     SQ_REQUIRE(e, "NULL handle");

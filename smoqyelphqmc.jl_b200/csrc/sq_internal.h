@@ -126,6 +126,7 @@ struct sq_elph {
     i64 Nph = 0, Nhol = 0, Nssh = 0;
     std::vector<double> h_M;
     DevBuf<double> x;                        // [l][p]
+    DevBuf<double> x_backup;                 // copy taken by a global move, restored on rejection
     DevBuf<double> Om, Om4, M;
     DevBuf<int> fin;                         // isfinite(M[p])
     // Holstein couplings

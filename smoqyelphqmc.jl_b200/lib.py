@@ -54,6 +54,10 @@ SIGNATURES = {
     "sq_elph_destroy": [vp],
     "sq_elph_set_x": [vp, vp],
     "sq_elph_get_x": [vp, vp],
+    "sq_elph_scale_x": [vp, i64, i64, f64],
+    "sq_elph_swap_x": [vp, i64, i64],
+    "sq_elph_backup_x": [vp],
+    "sq_elph_restore_x": [vp],
     "sq_elph_shift_mu": [vp, f64],
     "sq_elph_refresh_fdm": [vp],
     "sq_elph_get_Vt": [vp, vp, vp],

@@ -58,6 +58,15 @@ class Model:
         return self.Omega.shape[0]
 
     @property
+    def n_unit_cells(self) -> int:
+        return int(np.prod(self.lattice_dims)) if self.lattice_dims else self.N
+
+    @property
+    def nphonon(self) -> int:
+        """Phonon modes per unit cell (PhononParameters.nphonon); phonons are laid out type-major."""
+        return self.Nph // self.n_unit_cells
+
+    @property
     def Nhol(self) -> int:
         return self.hol_phonon.shape[0]
 
