@@ -75,6 +75,10 @@ __device__ __forceinline__ double rot_half(double self, double other, double c, 
 template <int LXL, int RY>
 struct V3Lane {
     static constexpr int YH = 32 / LXL, LX = 4 * LXL, LY = RY * YH, N = LX * LY;
+    // engine interface of the kernels: NV values per lane, stored as NP pairs; pair u of lane `lane` is the double2
+    // u * 32 + lane of a slice-part in native order, and the two consecutive sites pair_site(u), pair_site(u) + 1 in library order
+    static constexpr int NV = 4 * RY, NP = 2 * RY, NCOL = 4;
+    static constexpr int REGS_LIGHT = RY <= 8;          // two CTAs per SM fit
     int xl, part, yh;
     int lane_r, lane_l, lane_u, lane_d;
     int site0;              // site of v[0][0]; v[r][j] is site0 + LX r + j
@@ -143,6 +147,12 @@ struct V3Lane {
     }
 
     // v <- B_l v,  B = Gamma D Gamma^T: colours 3, 2, 1, 0, D, 0, 1, 2, 3 (colour c == bond class c, checked at create)
+    __device__ __forceinline__ int pair_site(int u) const { return site0 + LX * (u >> 1) + 2 * (u & 1); }
+    // flat-array overload: ev = slice base of exp(-dtau V) (+ 2 lane in native order)
+    template <int NAT, int SM>
+    __device__ __forceinline__ void apply_B_ev(double (&v)[NV], const double *ev) const {
+        apply_B_ev<NAT, SM>(reinterpret_cast<double (&)[RY][4]>(v), NAT ? ev : ev + site0);
+    }
     template <int NAT>
     __device__ __forceinline__ void apply_B(double (&v)[RY][4], int l, const V3Params &P) const {
         // NAT: exp(-dtau V) x prod_c cosh_c^2 in the native order [l][r][j/2][lane][j%2] (one coalesced 16-byte load per two
@@ -166,13 +176,12 @@ struct V3Lane {
 // NAT = 1: all vectors (in, out, cg_d, cg_pnew) are in the NATIVE order of this kernel -- slice l, part q, then
 // [r][j/2][lane][j%2] doubles -- so that every load / store is one fully coalesced 16-byte access per lane.  The CG solver
 // keeps its vectors in this order for the whole solve (cg.cu); the order is converted once on entry and once on exit.
-template <int MODE, int FUSE, int NAT, int LXL, int RY>
-__global__ void __launch_bounds__(256, RY <= 8 ? 2 : 1)
+template <int MODE, int FUSE, int NAT, class G>
+__global__ void __launch_bounds__(256, G::REGS_LIGHT ? 2 : 1)
 k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const double2 *__restrict__ in,
          double *__restrict__ pAp_part, const CgState *__restrict__ skip) {
-    typedef V3Lane<LXL, RY> G;
-    constexpr int N = G::N, LX = G::LX;
-    extern __shared__ double wsm[];                     // [S][RY][4][32] (this CTA's part)
+    constexpr int N = G::N, NP = G::NP;
+    extern __shared__ double wsm[];                     // [S][NP][32] double2 (this CTA's part)
     __shared__ double red[32];
     if (skip && skip->done) {
         if (FUSE && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.cg_nxt = *skip;
@@ -228,13 +237,13 @@ k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const do
     const double sg = (lB == 0) ? 1.0 : -1.0;
     const int part = E.part;
     const bool publish = (MODE == 2) && (k < ns);
-    double v[RY][4];
+    double v[G::NV];
     double acc = 0.0;
     // two elements (r, 2 jp), (r, 2 jp + 1) of slice l, this CTA's part; with CG fusion the vector is p = d + beta * in
     // formed on the fly (beta is real in the native-order solver: unpreconditioned CG)
-    auto off = [&](int l, int r, int jp) -> size_t {     // offset in doubles of the first of the two elements
-        if (NAT) return ((size_t)l * 2 + part) * N + ((r * 2 + jp) * 32 + lane) * 2;
-        return 2 * ((size_t)l * N + E.site0 + LX * r + 2 * jp) + part;
+    auto off = [&](int l, int u) -> size_t {             // offset in doubles of the first of the two elements of pair u
+        if (NAT) return ((size_t)l * 2 + part) * N + (u * 32 + lane) * 2;
+        return 2 * ((size_t)l * N + E.pair_site(u)) + part;
     };
     auto ld2 = [&](const double2 *src, size_t o) -> double2 {
         const double *q = reinterpret_cast<const double *>(src) + o;
@@ -246,14 +255,14 @@ k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const do
         if (NAT) *reinterpret_cast<double2 *>(q) = make_double2(a, b);
         else { q[0] = a; q[2] = b; }
     };
-    auto load2 = [&](int l, int r, int jp) -> double2 {
-        const size_t o = off(l, r, jp);
+    auto load2 = [&](int l, int u) -> double2 {
+        const size_t o = off(l, u);
         if (!FUSE) return ld2(in, o);
         if (NAT) {
             const double2 a = ld2(in, o), d = ld2(P.cg_d, o);
             return make_double2(__dadd_rn(d.x, __dmul_rn(beta.x, a.x)), __dadd_rn(d.y, __dmul_rn(beta.x, a.y)));
         }
-        const size_t g = (size_t)l * N + E.site0 + LX * r + 2 * jp;
+        const size_t g = (size_t)l * N + E.pair_site(u);
         const double2 p0 = cadd(P.cg_d[g], cmul(beta, in[g])), p1 = cadd(P.cg_d[g + 1], cmul(beta, in[g + 1]));
         return part ? make_double2(p0.y, p1.y) : make_double2(p0.x, p1.x);
     };
@@ -266,38 +275,33 @@ k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const do
         if (work) {
             if (phase == 0) {
 #pragma unroll
-                for (int r = 0; r < RY; r++)
-#pragma unroll
-                    for (int jp = 0; jp < 2; jp++) {
-                        const double2 q = load2(lin, r, jp);
-                        v[r][2 * jp] = q.x; v[r][2 * jp + 1] = q.y;
-                    }
-                if (P.dbg) { double t = 0; for (int r = 0; r < RY; r++) t += v[r][0]; if (t == 1.2345e300) P.dbg[15] = 1; }   // wait for the loads
+                for (int u = 0; u < NP; u++) {
+                    const double2 q = load2(lin, u);
+                    v[2 * u] = q.x; v[2 * u + 1] = q.y;
+                }
+                if (P.dbg) { double t = 0; for (int u = 0; u < NP; u++) t += v[2 * u]; if (t == 1.2345e300) P.dbg[15] = 1; }   // wait for the loads
                 V3_STAMP(1);
             }
-            E.template apply_B<NAT>(v, lB, P);
-            if (P.dbg) { double t = 0; for (int r = 0; r < RY; r++) t += v[r][0]; if (t == 1.2345e300) P.dbg[15] = 1; }
+            E.template apply_B_ev<NAT, 0>(v, NAT ? P.expVn + (size_t)lB * N + 2 * lane : P.expV + (size_t)lB * N);
+            if (P.dbg) { double t = 0; for (int u = 0; u < NP; u++) t += v[2 * u]; if (t == 1.2345e300) P.dbg[15] = 1; }
             V3_STAMP(2 + 3 * phase);
         }
         if (phase == 0) {
             if (work) {
 #pragma unroll
-                for (int r = 0; r < RY; r++) {
-#pragma unroll
-                    for (int jp = 0; jp < 2; jp++) {
-                        const double2 self = load2(lself, r, jp);
-                        const double w0 = fma(sg, v[r][2 * jp], self.x), w1 = fma(sg, v[r][2 * jp + 1], self.y);
-                        if (MODE == 2) {
-                            v[r][2 * jp] = w0; v[r][2 * jp + 1] = w1;
-                            if (publish) {
-                                acc += w0 * w0;
-                                acc += w1 * w1;
-                                reinterpret_cast<double2 *>(wsm)[((k * RY + r) * 2 + jp) * 32 + lane] = make_double2(w0, w1);
-                                if (FUSE) st2(P.cg_pnew, off(lself, r, jp), self.x, self.y);
-                            }
-                        } else {
-                            st2(out, off(lself, r, jp), w0, w1);
+                for (int u = 0; u < NP; u++) {
+                    const double2 self = load2(lself, u);
+                    const double w0 = fma(sg, v[2 * u], self.x), w1 = fma(sg, v[2 * u + 1], self.y);
+                    if (MODE == 2) {
+                        v[2 * u] = w0; v[2 * u + 1] = w1;
+                        if (publish) {
+                            acc += w0 * w0;
+                            acc += w1 * w1;
+                            reinterpret_cast<double2 *>(wsm)[(k * NP + u) * 32 + lane] = make_double2(w0, w1);
+                            if (FUSE) st2(P.cg_pnew, off(lself, u), self.x, self.y);
                         }
+                    } else {
+                        st2(out, off(lself, u), w0, w1);
                     }
                 }
             }
@@ -308,12 +312,10 @@ k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const do
             if (work) {
                 const int lo = l0 + k - 1;                  // < le <= L: no wrap
 #pragma unroll
-                for (int r = 0; r < RY; r++)
-#pragma unroll
-                    for (int jp = 0; jp < 2; jp++) {
-                        const double2 w = reinterpret_cast<const double2 *>(wsm)[(((k - 1) * RY + r) * 2 + jp) * 32 + lane];
-                        st2(out, off(lo, r, jp), fma(sg, v[r][2 * jp], w.x), fma(sg, v[r][2 * jp + 1], w.y));
-                    }
+                for (int u = 0; u < NP; u++) {
+                    const double2 w = reinterpret_cast<const double2 *>(wsm)[((k - 1) * NP + u) * 32 + lane];
+                    st2(out, off(lo, u), fma(sg, v[2 * u], w.x), fma(sg, v[2 * u + 1], w.y));
+                }
             }
         }
     }
@@ -519,12 +521,12 @@ typedef void (*v3_kernel_t)(const V3Params, double2 *, const double2 *, double *
 template <int LXL, int RY>
 static v3_kernel_t pick_mode(int mode) {       // mode 3: M^T M with the CG p update fused into the load; +4: native order
     switch (mode) {
-        case 0: return k_fdm_v3<0, 0, 0, LXL, RY>;
-        case 1: return k_fdm_v3<1, 0, 0, LXL, RY>;
-        case 2: return k_fdm_v3<2, 0, 0, LXL, RY>;
-        case 3: return k_fdm_v3<2, 1, 0, LXL, RY>;
-        case 6: return k_fdm_v3<2, 0, 1, LXL, RY>;
-        case 7: return k_fdm_v3<2, 1, 1, LXL, RY>;
+        case 0: return k_fdm_v3<0, 0, 0, V3Lane<LXL, RY>>;
+        case 1: return k_fdm_v3<1, 0, 0, V3Lane<LXL, RY>>;
+        case 2: return k_fdm_v3<2, 0, 0, V3Lane<LXL, RY>>;
+        case 3: return k_fdm_v3<2, 1, 0, V3Lane<LXL, RY>>;
+        case 6: return k_fdm_v3<2, 0, 1, V3Lane<LXL, RY>>;
+        case 7: return k_fdm_v3<2, 1, 1, V3Lane<LXL, RY>>;
     }
     return nullptr;
 }
@@ -1000,11 +1002,10 @@ __device__ __forceinline__ void v3_slot_sum2(double (&t)[2], int half, char *slo
     t[1] = warp_sum(s[1]);
 }
 
-template <int LXL, int RY>
+template <class G>
 __global__ void __launch_bounds__(256, 1)
 k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
-    typedef V3Lane<LXL, RY> G;
-    constexpr int N = G::N;
+    constexpr int N = G::N, NP = G::NP;
     extern __shared__ double smem[];
     __shared__ double red[4 * 8];
     __shared__ double sh[6];
@@ -1027,7 +1028,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     double *EV = smem + (size_t)2 * (2 * S + 2) * N;
     double2 *Rh = reinterpret_cast<double2 *>(EV + (size_t)(S + 1) * N) + (size_t)part * 2 * (N / 2);
     const double *evk = EV + (size_t)k * N + 2 * lane;
-    auto el = [&](int r, int jp) -> int { return (r * 2 + jp) * 32 + lane; };
+    auto el = [&](int u) -> int { return u * 32 + lane; };
     auto gslice = [&](const double *base, int l) -> const double2 * { return reinterpret_cast<const double2 *>(base + ((size_t)l * 2 + part) * N); };
     // boundary z: [parity of the iteration][cta][side][part][N]; side 0 = first own slice, 1 = last own slice
     auto hslice = [&](int par, unsigned int cta, int side) -> double2 * { return reinterpret_cast<double2 *>(C.halo + ((((size_t)par * nblk + cta) * 2 + side) * 2 + part) * N); };
@@ -1035,7 +1036,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     const double normb = C.state->normb, tol = C.state->tol;
     double eps = C.state->eps;
     int it = 0, done = 0;
-    double v[RY][4], xr[RY][4], rr_[RY][4];
+    double v[G::NV], xr[G::NV], rr_[G::NV];
     if (threadIdx.x == 0) sh[5] = 0.0;
     if (part == 0 && active) {
         const double2 *g = reinterpret_cast<const double2 *>(P.expVn + (size_t)lB * N);
@@ -1044,13 +1045,11 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     if (owner) {
         const double2 *gx = gslice(C.x, lo), *gr = gslice(C.r, lo);
 #pragma unroll
-        for (int r = 0; r < RY; r++)
-#pragma unroll
-            for (int jp = 0; jp < 2; jp++) {
-                const double2 a = gx[el(r, jp)], b = gr[el(r, jp)];
-                xr[r][2 * jp] = a.x; xr[r][2 * jp + 1] = a.y;
-                rr_[r][2 * jp] = b.x; rr_[r][2 * jp + 1] = b.y;
-                Pb[(size_t)k * (N / 2) + el(r, jp)] = b;
+        for (int u = 0; u < NP; u++) {
+                const double2 a = gx[el(u)], b = gr[el(u)];
+                xr[2 * u] = a.x; xr[2 * u + 1] = a.y;
+                rr_[2 * u] = b.x; rr_[2 * u + 1] = b.y;
+                Pb[(size_t)k * (N / 2) + el(u)] = b;
             }
     }
     if (k == 0) {                                         // r0 = p0 of the two halo slices
@@ -1070,25 +1069,21 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         if (active) {
 #pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 a = Pb[(size_t)k * (N / 2) + el(r, jp)];
-                    v[r][2 * jp] = a.x; v[r][2 * jp + 1] = a.y;
+            for (int u = 0; u < NP; u++) {
+                    const double2 a = Pb[(size_t)k * (N / 2) + el(u)];
+                    v[2 * u] = a.x; v[2 * u + 1] = a.y;
                 }
             E.template apply_B_ev<1, 1>(v, evk);
             if (k == ns && it > 1) asm volatile("bar.sync %0, 64;" ::"r"(1 + part) : "memory");       // upper halo slice rebuilt by warp 0
 #pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 self = Pb[(size_t)(k + 1) * (N / 2) + el(r, jp)];
-                    const double w0 = fma(sg, v[r][2 * jp], self.x), w1 = fma(sg, v[r][2 * jp + 1], self.y);
-                    v[r][2 * jp] = w0; v[r][2 * jp + 1] = w1;
+            for (int u = 0; u < NP; u++) {
+                    const double2 self = Pb[(size_t)(k + 1) * (N / 2) + el(u)];
+                    const double w0 = fma(sg, v[2 * u], self.x), w1 = fma(sg, v[2 * u + 1], self.y);
+                    v[2 * u] = w0; v[2 * u + 1] = w1;
                     if (publish) {
                         acc[0] += w0 * w0;
                         acc[0] += w1 * w1;
-                        W[(size_t)k * (N / 2) + el(r, jp)] = make_double2(w0, w1);
+                        W[(size_t)k * (N / 2) + el(u)] = make_double2(w0, w1);
                     }
                 }
         }
@@ -1097,18 +1092,16 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
         if (owner) {                                      // z[lo] in registers; r.z, |z|^2, |r|^2; boundary z for the neighbours
             double2 *h0 = (k == 1) ? hslice(it & 1, bid, 0) : nullptr, *h1 = (k == ns) ? hslice(it & 1, bid, 1) : nullptr;
 #pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 w = W[(size_t)(k - 1) * (N / 2) + el(r, jp)];
-                    const double z0 = fma(sg, v[r][2 * jp], w.x), z1 = fma(sg, v[r][2 * jp + 1], w.y);
-                    v[r][2 * jp] = z0; v[r][2 * jp + 1] = z1;
-                    const double r0 = rr_[r][2 * jp], r1 = rr_[r][2 * jp + 1];
+            for (int u = 0; u < NP; u++) {
+                    const double2 w = W[(size_t)(k - 1) * (N / 2) + el(u)];
+                    const double z0 = fma(sg, v[2 * u], w.x), z1 = fma(sg, v[2 * u + 1], w.y);
+                    v[2 * u] = z0; v[2 * u + 1] = z1;
+                    const double r0 = rr_[2 * u], r1 = rr_[2 * u + 1];
                     acc[1] += r0 * z0; acc[1] += r1 * z1;
                     acc[2] += z0 * z0; acc[2] += z1 * z1;
                     acc[3] += r0 * r0; acc[3] += r1 * r1;
-                    if (h0) h0[el(r, jp)] = make_double2(z0, z1);
-                    if (h1) h1[el(r, jp)] = make_double2(z0, z1);
+                    if (h0) h0[el(u)] = make_double2(z0, z1);
+                    if (h1) h1[el(u)] = make_double2(z0, z1);
                 }
         }
         // ---- the grid-wide sum of (a, b, c, d)
@@ -1139,16 +1132,14 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
         double chk = 0.0;
         if (owner) {                                      // x += alpha p ; r -= alpha z ; p = r + beta p
 #pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 pv = Pb[(size_t)k * (N / 2) + el(r, jp)];
-                    xr[r][2 * jp] = fma(alpha, pv.x, xr[r][2 * jp]);
-                    xr[r][2 * jp + 1] = fma(alpha, pv.y, xr[r][2 * jp + 1]);
-                    const double r0 = fma(-alpha, v[r][2 * jp], rr_[r][2 * jp]), r1 = fma(-alpha, v[r][2 * jp + 1], rr_[r][2 * jp + 1]);
-                    rr_[r][2 * jp] = r0; rr_[r][2 * jp + 1] = r1;
+            for (int u = 0; u < NP; u++) {
+                    const double2 pv = Pb[(size_t)k * (N / 2) + el(u)];
+                    xr[2 * u] = fma(alpha, pv.x, xr[2 * u]);
+                    xr[2 * u + 1] = fma(alpha, pv.y, xr[2 * u + 1]);
+                    const double r0 = fma(-alpha, v[2 * u], rr_[2 * u]), r1 = fma(-alpha, v[2 * u + 1], rr_[2 * u + 1]);
+                    rr_[2 * u] = r0; rr_[2 * u + 1] = r1;
                     chk += r0 * r0; chk += r1 * r1;
-                    Pb[(size_t)k * (N / 2) + el(r, jp)] = make_double2(fma(beta, pv.x, r0), fma(beta, pv.y, r1));
+                    Pb[(size_t)k * (N / 2) + el(u)] = make_double2(fma(beta, pv.x, r0), fma(beta, pv.y, r1));
                 }
         }
         if (stop_est) {                                   // confirm with the exact |r_new|^2 (every CTA takes this branch together)
@@ -1194,9 +1185,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     if (owner) {                                          // the solution
         double2 *gx = reinterpret_cast<double2 *>(C.x + ((size_t)lo * 2 + part) * N);
 #pragma unroll
-        for (int r = 0; r < RY; r++)
-#pragma unroll
-            for (int jp = 0; jp < 2; jp++) gx[el(r, jp)] = make_double2(xr[r][2 * jp], xr[r][2 * jp + 1]);
+        for (int u = 0; u < NP; u++) gx[el(u)] = make_double2(xr[2 * u], xr[2 * u + 1]);
     }
     if (bid == 0 && threadIdx.x == 0) {
         CgState st = *C.state;
@@ -1218,11 +1207,11 @@ static v3_resident_t pick3_resident(int lxl, int ry) {
 }
 typedef void (*v3_resident1_t)(const V3Params, const CgResident1);
 static v3_resident1_t pick3_resident1(int lxl, int ry) {
-    if (lxl == 8 && ry == 4) return k_cg_v3_resident1<8, 4>;
-    if (lxl == 8 && ry == 8) return k_cg_v3_resident1<8, 8>;
-    if (lxl == 4 && ry == 2) return k_cg_v3_resident1<4, 2>;
-    if (lxl == 4 && ry == 4) return k_cg_v3_resident1<4, 4>;
-    if (lxl == 4 && ry == 8) return k_cg_v3_resident1<4, 8>;
+    if (lxl == 8 && ry == 4) return k_cg_v3_resident1<V3Lane<8, 4>>;
+    if (lxl == 8 && ry == 8) return k_cg_v3_resident1<V3Lane<8, 8>>;
+    if (lxl == 4 && ry == 2) return k_cg_v3_resident1<V3Lane<4, 2>>;
+    if (lxl == 4 && ry == 4) return k_cg_v3_resident1<V3Lane<4, 4>>;
+    if (lxl == 4 && ry == 8) return k_cg_v3_resident1<V3Lane<4, 8>>;
     return nullptr;
 }
 
