@@ -210,6 +210,7 @@ int sq_fdm_set_fast_path(sq_fdm *f, int enable) {
     f->use_v2 = enable ? 1 : 0;
     f->use_v3 = ((enable & 255) == 2) ? 1 : 0;
     if (f->use_v3 && (enable >> 8) >= 1 && (enable >> 8) <= 7) f->v3_S = enable >> 8;
+    f->v3_cg = f->use_v3;
     f->manual_tuning = 1;
     SQ_CATCH
 }

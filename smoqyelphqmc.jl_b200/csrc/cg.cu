@@ -251,7 +251,7 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
     int cur = 0;
     bool finished = false;
     fdm_select_tuning(f);
-    const bool v3 = f->path == 0 && f->use_v3 && fdm_v3_supported(f, f->v3_S);
+    const bool v3 = f->path == 0 && f->v3_cg && fdm_v3_supported(f, f->v3_S);
     const bool fused = !prec && f->path == 0 && (v3 || (f->use_v2 && fdm_v2_supported(f, 2, f->slab, f->threads))) && !getenv("SQ_NO_CG_FUSION");
     if (fused && !v3 && !getenv("SQ_NO_PERSISTENT_CG") && maxiter > 0) {
         // One cooperative launch for the whole solve (fdm_v2.cu: k_cg_persistent).  The state prepared by k_cg_init holds

@@ -599,6 +599,10 @@ void fdm_select_tuning(sq_fdm *f) {
     }
     f->slab = f->tuned[u][1]; f->threads = f->tuned[u][2]; f->use_v2 = f->tuned[u][3];
     f->use_v3 = f->tuned[u][4]; f->v3_S = f->tuned[u][5] ? f->tuned[u][5] : 3;
+    // The solver does not follow the stand-alone timing: in native order with the resident kernel the register path wins
+    // wherever it applies (cfg5: 8.6 us per iteration against 15.0 us, although the stand-alone v2 matvec is faster there)
+    const char *env3 = getenv("SQ_V3");
+    f->v3_cg = (!(env3 && atoi(env3) == 0) && fdm_v3_supported(f, f->v3_S)) ? 1 : 0;
 }
 
 void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt, const i64 *perm, i64 C,

@@ -25,7 +25,8 @@
 // ~110 registers per thread: several CTAs per SM, so one warp's load latency hides behind another's arithmetic.
 //
 // Requirements (checked by fdm_v3_detect / fdm_v3_supported, otherwise the shared-memory kernels run): symmetric
-// propagator, natural site order i = x + Lx y, colour c is bond class c (x-even, x-odd, y-even, y-odd), and the
+// propagator, natural site order i = x + Lx y, colour c is bond class c (x-even, x-odd, y-even, y-odd) -- or the honeycomb
+// lattice of the V3Honey engine below -- and the
 // (cosh, sinh) of all bonds of one colour are equal and tau-independent (any Holstein-type model with uniform hopping).
 #include "sq_internal.h"
 
@@ -170,6 +171,98 @@ struct V3Lane {
             v[r][0] *= e01.x; v[r][1] *= e01.y; v[r][2] *= e23.x; v[r][3] *= e23.y;
         }
         step<0, NAT>(v); step<1, NAT>(v); step<2, NAT>(v); step<3, NAT>(v);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Honeycomb engine: two orbitals per cell, site = orb + 2 (c1 + L1 c2), three bond types = three colours
+//     colour 0: A(c1, c2) - B(c1, c2)        colour 1: A(c1, c2) - B(c1 - 1, c2)        colour 2: A(c1, c2) - B(c1, c2 - 1)
+// (the lattice of the reference's tutorials, tutorials/holstein_honeycomb.jl).  lane = g1 + G1 g2 holds an R1 x R2 block
+// of cells, L1 = G1 R1, L2 = (32 / G1) R2; pair u = a2 R1 + a1 is the cell (a1, a2) of the block: v[2u] = A, v[2u + 1] = B.
+// Colour 0 is lane-local; colours 1 / 2 are local except for the first column / row of the block, which pairs with the B
+// orbitals of the last column / row of the neighbouring lane (one shuffle per boundary cell).
+// ---------------------------------------------------------------------------------------------------
+template <int G1, int R1, int R2>
+struct V3Honey {
+    static constexpr int G2 = 32 / G1, L1 = G1 * R1, L2 = G2 * R2;
+    static constexpr int NP = R1 * R2, NV = 2 * NP, N = 2 * L1 * L2, NCOL = 3;
+    static constexpr int REGS_LIGHT = NV <= 36;
+    int g1, g2, part;
+    int lane_r, lane_l, lane_u, lane_d;
+    double cc[3], ss[3];
+
+    template <int SC>
+    __device__ __forceinline__ void init(const V3Params &P, int part_) {
+        const int lane = threadIdx.x & 31;
+        g1 = lane % G1;
+        g2 = lane / G1;
+        part = part_;
+        lane_r = (g1 + 1) % G1 + G1 * g2;
+        lane_l = (g1 + G1 - 1) % G1 + G1 * g2;
+        lane_u = g1 + G1 * ((g2 + 1) % G2);
+        lane_d = g1 + G1 * ((g2 + G2 - 1) % G2);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double2 q = SC ? __ldg(P.ctn + c) : __ldg(P.cs + P.clo[c]);
+            cc[c] = q.x; ss[c] = q.y;
+        }
+    }
+    __device__ __forceinline__ int pair_site(int u) const { return 2 * ((R1 * g1 + u % R1) + L1 * (R2 * g2 + u / R1)); }
+
+    template <int CL, int SC>
+    __device__ __forceinline__ void step(double (&v)[NV]) const {
+        const double c = cc[CL], s = ss[CL];
+        if (CL == 0) {
+#pragma unroll
+            for (int u = 0; u < NP; u++) rot1<SC>(v[2 * u], v[2 * u + 1], c, s);
+        } else if (CL == 1) {                             // A(a1, a2) - B(a1 - 1, a2)
+#pragma unroll
+            for (int a2 = 0; a2 < R2; a2++) {
+                const int u0 = a2 * R1, u1 = a2 * R1 + R1 - 1;
+                if (G1 > 1) {
+                    const double fromL = __shfl_sync(0xffffffffu, v[2 * u1 + 1], lane_l);     // B of the left lane's last column
+                    const double fromR = __shfl_sync(0xffffffffu, v[2 * u0], lane_r);         // A of the right lane's first column
+#pragma unroll
+                    for (int a1 = R1 - 1; a1 >= 1; a1--) rot1<SC>(v[2 * (u0 + a1)], v[2 * (u0 + a1 - 1) + 1], c, s);
+                    // the two boundary values: A(0, a2) with fromL; B(R1 - 1, a2) with fromR -- after the inner bonds when R1 > 1
+                    // touches neither (A(0) and B(R1-1) are not part of an inner bond)
+                    v[2 * u0] = rot_half<SC>(v[2 * u0], fromL, c, s);
+                    v[2 * u1 + 1] = rot_half<SC>(v[2 * u1 + 1], fromR, c, s);
+                } else {
+#pragma unroll
+                    for (int a1 = 0; a1 < R1; a1++) rot1<SC>(v[2 * (u0 + a1)], v[2 * (u0 + (a1 + R1 - 1) % R1) + 1], c, s);
+                }
+            }
+        } else {                                          // A(a1, a2) - B(a1, a2 - 1)
+#pragma unroll
+            for (int a1 = 0; a1 < R1; a1++) {
+                const int u0 = a1, u1 = (R2 - 1) * R1 + a1;
+                if (G2 > 1) {
+                    const double fromD = __shfl_sync(0xffffffffu, v[2 * u1 + 1], lane_d);
+                    const double fromU = __shfl_sync(0xffffffffu, v[2 * u0], lane_u);
+#pragma unroll
+                    for (int a2 = R2 - 1; a2 >= 1; a2--) rot1<SC>(v[2 * (a2 * R1 + a1)], v[2 * ((a2 - 1) * R1 + a1) + 1], c, s);
+                    v[2 * u0] = rot_half<SC>(v[2 * u0], fromD, c, s);
+                    v[2 * u1 + 1] = rot_half<SC>(v[2 * u1 + 1], fromU, c, s);
+                } else {
+#pragma unroll
+                    for (int a2 = 0; a2 < R2; a2++) rot1<SC>(v[2 * (a2 * R1 + a1)], v[2 * (((a2 + R2 - 1) % R2) * R1 + a1) + 1], c, s);
+                }
+            }
+        }
+    }
+
+    // v <- B v,  B = Gamma D Gamma^T: colours 2, 1, 0, D, 0, 1, 2.  ev: slice base of exp(-dtau V) (+ 2 lane in native order)
+    template <int NAT, int SM>
+    __device__ __forceinline__ void apply_B_ev(double (&v)[NV], const double *ev) const {
+        step<2, NAT>(v); step<1, NAT>(v); step<0, NAT>(v);
+#pragma unroll
+        for (int u = 0; u < NP; u++) {
+            const double2 *q = (const double2 *)(ev + (NAT ? 64 * u : pair_site(u)));
+            const double2 e = SM ? *q : __ldg(q);
+            v[2 * u] *= e.x; v[2 * u + 1] *= e.y;
+        }
+        step<0, NAT>(v); step<1, NAT>(v); step<2, NAT>(v);
     }
 };
 
@@ -530,6 +623,26 @@ static v3_kernel_t pick_mode(int mode) {       // mode 3: M^T M with the CG p up
     }
     return nullptr;
 }
+template <int G1, int R1, int R2>
+static v3_kernel_t pick_mode_h(int mode) {
+    typedef V3Honey<G1, R1, R2> H;
+    switch (mode) {
+        case 0: return k_fdm_v3<0, 0, 0, H>;
+        case 1: return k_fdm_v3<1, 0, 0, H>;
+        case 2: return k_fdm_v3<2, 0, 0, H>;
+        case 3: return k_fdm_v3<2, 1, 0, H>;
+        case 6: return k_fdm_v3<2, 0, 1, H>;
+        case 7: return k_fdm_v3<2, 1, 1, H>;
+    }
+    return nullptr;
+}
+// honeycomb geometries: (lxl, ry) hold (L1, L2) with kind = 1
+static v3_kernel_t pick3h(int L1, int L2, int mode) {
+    if (L1 == 24 && L2 == 24) return pick_mode_h<8, 3, 6>(mode);
+    if (L1 == 16 && L2 == 16) return pick_mode_h<4, 4, 2>(mode);
+    if (L1 == 8 && L2 == 8) return pick_mode_h<4, 2, 1>(mode);
+    return nullptr;
+}
 static v3_kernel_t pick3(int lxl, int ry, int mode) {
     if (lxl == 8 && ry == 4) return pick_mode<8, 4>(mode);        // 32 x 16
     if (lxl == 8 && ry == 8) return pick_mode<8, 8>(mode);        // 32 x 32
@@ -541,8 +654,37 @@ static v3_kernel_t pick3(int lxl, int ry, int mode) {
 }
 
 // Is the lattice an Lx x Ly periodic rectangle in natural site order whose 4 colours are the 4 bond classes?
+// honeycomb: site = orb + 2 (c1 + L1 c2), colour c = bond type c: A(c1, c2) - B(c1 + d1, c2 + d2), d = (0,0), (-1,0), (0,-1)
+static bool fdm_v3_detect_honeycomb(sq_fdm *f) {
+    if (!f->sym || f->C != 3 || 2 * f->Nh != 3 * f->N) return false;
+    for (int L : {24, 16, 8}) {
+        if (f->N != 2 * L * L || !pick3h(L, L, 2)) continue;
+        static const int d1[3] = {0, -1, 0}, d2[3] = {0, 0, -1};
+        bool ok = true;
+        for (int c = 0; c < 3 && ok; c++) {
+            if (f->chi[c] - f->clo[c] != f->N / 2) { ok = false; break; }
+            for (int h = f->clo[c]; h < f->chi[c] && ok; h++) {
+                int a = f->h_nt[h].x, b = f->h_nt[h].y;
+                if (a & 1) std::swap(a, b);                   // a: A orbital, b: B orbital
+                if ((a & 1) || !(b & 1)) { ok = false; break; }
+                const int ca = a / 2, cb = b / 2, a1 = ca % L, a2 = ca / L, b1 = cb % L, b2 = cb / L;
+                ok = (b1 == (a1 + d1[c] + L) % L) && (b2 == (a2 + d2[c] + L) % L);
+            }
+        }
+        if (!ok) continue;
+        f->v3_ok = 1; f->v3_kind = 1; f->v3_lxl = L; f->v3_ry = L;
+        for (int c = 0; c < 4; c++) f->v3_cls[c] = c;
+        for (int mode : {0, 1, 2, 3, 6, 7})
+            SQ_CUDA(cudaFuncSetAttribute(pick3h(L, L, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        return true;
+    }
+    return false;
+}
+
 void fdm_v3_detect(sq_fdm *f) {
     f->v3_ok = 0;
+    f->v3_kind = 0;
+    if (fdm_v3_detect_honeycomb(f)) return;
     if (!f->sym || f->C != 4 || f->Nh != 2 * f->N) return;
     for (int LX : {32, 16}) {
         if (f->N % LX) continue;
@@ -603,8 +745,8 @@ int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, d
         P.cg_rr_part = g_fuse3->rr_part; P.cg_beta_part = g_fuse3->beta_part; P.cg_nrr = g_fuse3->nrr; P.cg_nbeta = g_fuse3->nbeta;
         P.cg_beta_complex = g_fuse3->beta_complex; P.cg_iter = g_fuse3->iter; P.cg_check = g_fuse3->check;
     }
-    P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = 4; P.nphase = (mode == 2) ? 2 : 1;
-    for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = f->clo[c]; }
+    P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = (int)f->C; P.nphase = (mode == 2) ? 2 : 1;
+    for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = c < f->C ? f->clo[c] : 0; }
     P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p;
     static long long *dbg = nullptr;
     if (!dbg && getenv("SQ_DEBUG_STAMPS")) {
@@ -621,7 +763,8 @@ int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, d
     const int grid = (f->slab_hi - f->slab_lo + nper - 1) / nper;
     const size_t smem = (mode == 2) ? (size_t)S * f->N * sizeof(double) : 0;
     if (native) SQ_REQUIRE(mode == 2 && f->v3_expVn.p && f->v3_expv_version == f->coef_version, "native-order operator not prepared");
-    v3_kernel_t k = pick3(f->v3_lxl, f->v3_ry, ((mode == 2 && g_fuse3) ? 3 : mode) + (native ? 4 : 0));
+    const int kmode = ((mode == 2 && g_fuse3) ? 3 : mode) + (native ? 4 : 0);
+    v3_kernel_t k = f->v3_kind == 1 ? pick3h(f->v3_lxl, f->v3_ry, kmode) : pick3(f->v3_lxl, f->v3_ry, kmode);
     k<<<dim3(grid, 2), 32 * (S + 1), smem, f->stream>>>(P, out, in, part, skip);
     SQ_LAUNCH_CHECK();
     f->launches++;
@@ -1214,10 +1357,16 @@ static v3_resident1_t pick3_resident1(int lxl, int ry) {
     if (lxl == 4 && ry == 8) return k_cg_v3_resident1<V3Lane<4, 8>>;
     return nullptr;
 }
+static v3_resident1_t pick3h_resident1(int L1, int L2) {
+    if (L1 == 24 && L2 == 24) return k_cg_v3_resident1<V3Honey<8, 3, 6>>;
+    if (L1 == 16 && L2 == 16) return k_cg_v3_resident1<V3Honey<4, 4, 2>>;
+    if (L1 == 8 && L2 == 8) return k_cg_v3_resident1<V3Honey<4, 2, 1>>;
+    return nullptr;
+}
 
 // One-sum resident kernel (k_cg_v3_resident1).  Returns false if it cannot run (the caller falls back to the two-sum kernel).
 static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *state, i64 maxiter) {
-    v3_resident1_t k = pick3_resident1(f->v3_lxl, f->v3_ry);
+    v3_resident1_t k = f->v3_kind == 1 ? pick3h_resident1(f->v3_lxl, f->v3_ry) : pick3_resident1(f->v3_lxl, f->v3_ry);
     if (!k || !f->v3_ok || !f->cs_coluni) return false;
     const int nsl = f->slab_hi - f->slab_lo;
     int S = (nsl + f->num_sms - 1) / f->num_sms;
@@ -1229,8 +1378,8 @@ static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *stat
     if (smem > f->smem_optin || grid > f->num_sms || grid < 2) return false;
     V3Params P;
     memset(&P, 0, sizeof(P));
-    P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = 4; P.nphase = 2;
-    for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = f->clo[c]; }
+    P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = (int)f->C; P.nphase = 2;
+    for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = c < f->C ? f->clo[c] : 0; }
     P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p;
     SQ_CUDA(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -1262,7 +1411,7 @@ bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, double2 *halo, CgStat
         const char *sel = getenv("SQ_V3_RESIDENT");
         if (!(sel && atoi(sel) == 2) && fdm_v3_cg_resident1(f, x, r, state, maxiter)) return true;
     }
-    v3_resident_t k2 = pick3_resident(f->v3_lxl, f->v3_ry);
+    v3_resident_t k2 = f->v3_kind == 0 ? pick3_resident(f->v3_lxl, f->v3_ry) : nullptr;
     if (!k2 || !f->v3_ok || !f->cs_coluni) return false;
     const void *kern = (const void *)k2;
     const int nsl = f->slab_hi - f->slab_lo;
@@ -1337,7 +1486,7 @@ bool fdm_v3_cg_persistent(sq_fdm *f, double2 *x, double2 *r, double2 *p0, double
                           i64 maxiter) {
     int S = f->v3_S;
     if (const char *e = getenv("SQ_V3_PERSIST_SLAB")) S = atoi(e);
-    if (!fdm_v3_supported(f, S)) return false;
+    if (!fdm_v3_supported(f, S) || f->v3_kind != 0) return false;
     V3Params P;
     memset(&P, 0, sizeof(P));
     P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = 4; P.nphase = 2;
@@ -1379,49 +1528,57 @@ bool fdm_v3_cg_persistent(sq_fdm *f, double2 *x, double2 *r, double2 *p0, double
 // ---------------------------------------------------------------------------------------------------
 // native order  <->  library order [l][i] (complex interleaved)
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ size_t v3_native_index(int i, int lxl, int ry) {      // offset inside one slice-part (doubles)
+// offset inside one slice-part (doubles).  kind 0: square (lxl, ry); kind 1: honeycomb (lxl = L1, ry = L2, block sizes from the
+// engine table: G1 = 8 for L1 = 24, else 4)
+__device__ __forceinline__ size_t v3_native_index(int i, int lxl, int ry, int kind) {
+    if (kind == 1) {
+        const int L1 = lxl, L2 = ry, G1 = (L1 == 24) ? 8 : 4, G2 = 32 / G1, R1 = L1 / G1, R2 = L2 / G2;
+        const int orb = i & 1, c = i >> 1, c1 = c % L1, c2 = c / L1;
+        const int lane = c1 / R1 + G1 * (c2 / R2), u = (c2 % R2) * R1 + c1 % R1;
+        return (size_t)(u * 32 + lane) * 2 + orb;
+    }
     const int LX = 4 * lxl, x = i % LX, y = i / LX;
     const int lane = x / 4 + lxl * (y / ry), r = y % ry, j = x % 4;
     return (size_t)((r * 2 + j / 2) * 32 + lane) * 2 + (j & 1);
 }
-__global__ void k_v3_to_native(double *__restrict__ dst, const double2 *__restrict__ src, int L, int N, int lxl, int ry) {
+__global__ void k_v3_to_native(double *__restrict__ dst, const double2 *__restrict__ src, int L, int N, int lxl, int ry, int kind) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)L * N) return;
     const int l = (int)(idx / N), i = (int)(idx % N);
     const double2 v = src[idx];
-    const size_t o = v3_native_index(i, lxl, ry);
+    const size_t o = v3_native_index(i, lxl, ry, kind);
     dst[((size_t)l * 2) * N + o] = v.x;
     dst[((size_t)l * 2 + 1) * N + o] = v.y;
 }
-__global__ void k_v3_from_native(double2 *__restrict__ dst, const double *__restrict__ src, int L, int N, int lxl, int ry) {
+__global__ void k_v3_from_native(double2 *__restrict__ dst, const double *__restrict__ src, int L, int N, int lxl, int ry, int kind) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)L * N) return;
     const int l = (int)(idx / N), i = (int)(idx % N);
-    const size_t o = v3_native_index(i, lxl, ry);
+    const size_t o = v3_native_index(i, lxl, ry, kind);
     dst[idx] = make_double2(src[((size_t)l * 2) * N + o], src[((size_t)l * 2 + 1) * N + o]);
 }
 struct V3Clo { int lo[4]; };
 __global__ void k_v3_expV_native(double *__restrict__ dst, const double *__restrict__ src, int L, int N, int lxl, int ry,
-                                 const double2 *__restrict__ cs, const V3Clo clo, double2 *__restrict__ ctn) {
+                                 const double2 *__restrict__ cs, const V3Clo clo, double2 *__restrict__ ctn, int kind, int ncol) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < 4) { const double2 q = __ldg(cs + clo.lo[idx]); ctn[idx] = make_double2(q.x, q.y / q.x); }
+    if (idx < (size_t)ncol) { const double2 q = __ldg(cs + clo.lo[idx]); ctn[idx] = make_double2(q.x, q.y / q.x); }
     if (idx >= (size_t)L * N) return;
     const int l = (int)(idx / N), i = (int)(idx % N);
     double g = 1.0;                                            // prod_c cosh_c^2 (each colour is applied twice in B)
 #pragma unroll
-    for (int c = 0; c < 4; c++) { const double ch = __ldg(cs + clo.lo[c]).x; g *= ch * ch; }
-    dst[(size_t)l * N + v3_native_index(i, lxl, ry)] = g * src[idx];
+    for (int c = 0; c < ncol; c++) { const double ch = __ldg(cs + clo.lo[c]).x; g *= ch * ch; }
+    dst[(size_t)l * N + v3_native_index(i, lxl, ry, kind)] = g * src[idx];
 }
 
 void fdm_v3_to_native(sq_fdm *f, double2 *dst, const double2 *src) {
     const size_t n = (size_t)f->L * f->N;
-    k_v3_to_native<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>((double *)dst, src, (int)f->L, (int)f->N, f->v3_lxl, f->v3_ry);
+    k_v3_to_native<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>((double *)dst, src, (int)f->L, (int)f->N, f->v3_lxl, f->v3_ry, f->v3_kind);
     SQ_LAUNCH_CHECK();
     f->launches++;
 }
 void fdm_v3_from_native(sq_fdm *f, double2 *dst, const double2 *src) {
     const size_t n = (size_t)f->L * f->N;
-    k_v3_from_native<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>(dst, (const double *)src, (int)f->L, (int)f->N, f->v3_lxl, f->v3_ry);
+    k_v3_from_native<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>(dst, (const double *)src, (int)f->L, (int)f->N, f->v3_lxl, f->v3_ry, f->v3_kind);
     SQ_LAUNCH_CHECK();
     f->launches++;
 }
@@ -1431,9 +1588,9 @@ void fdm_v3_prepare_native(sq_fdm *f) {
     if (!f->v3_expVn.p) { f->v3_expVn.alloc(n); f->v3_ctn.alloc(4); f->v3_x.alloc(n); f->v3_r.alloc(n); f->v3_expv_version = -1; }
     if (f->v3_expv_version == f->coef_version) return;
     V3Clo clo;
-    for (int c = 0; c < 4; c++) clo.lo[c] = f->clo[c];
+    for (int c = 0; c < 4; c++) clo.lo[c] = c < f->C ? f->clo[c] : 0;
     k_v3_expV_native<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>(f->v3_expVn.p, f->expV.p, (int)f->L, (int)f->N, f->v3_lxl, f->v3_ry,
-                                                                        f->cs.p, clo, f->v3_ctn.p);
+                                                                        f->cs.p, clo, f->v3_ctn.p, f->v3_kind, (int)f->C);
     SQ_LAUNCH_CHECK();
     f->launches++;
     f->v3_expv_version = f->coef_version;

@@ -51,8 +51,10 @@ struct sq_fdm {
     int cs_coluni = 0;                       // ... and are equal for all bonds of one colour (uniform hopping): fdm_v3.cu
     // register path (fdm_v3.cu): rectangular lattice, one warp per slice
     int v3_ok = 0, v3_lxl = 0, v3_ry = 0, v3_cls[4] = {0, 0, 0, 0};
+    int v3_kind = 0;                         // 0: square (v3_lxl = Lx / 4, v3_ry = rows per lane), 1: honeycomb (v3_lxl = L1, v3_ry = L2)
     int v3_S = 3;                            // slices per CTA of the register path
-    int use_v3 = 0;
+    int use_v3 = 0;                          // stand-alone products (library-order vectors): chosen by timing
+    int v3_cg = 0;                           // CG solves: register path whenever it applies (native order + resident kernel)
     DevBuf<double2> v3_ctn;                  // (cosh, tanh) per colour for the scaled rotations
     DevBuf<double> v3_expVn;                 // exp(-dtau V) in the native order of the register path
     DevBuf<double2> v3_x, v3_r;              // CG vectors in native order

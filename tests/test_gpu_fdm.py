@@ -133,6 +133,10 @@ SQUARES = {
     "h32x32": lambda: mdl.holstein_square(32, 32, 1.5),
     "h16x64": lambda: mdl.holstein_square(16, 64, 0.5),
     "h32x64": lambda: mdl.holstein_square(32, 64, 0.35),    # 64 rows: 16 rows per lane, Ltau = 7 (ragged last CTA)
+    # honeycomb lattices (the reference's tutorial lattice; 24 x 24 is BASELINE config 5): honeycomb engine of fdm_v3.cu
+    "hc8": lambda: mdl.holstein_honeycomb(8, 1.0),
+    "hc16": lambda: mdl.holstein_honeycomb(16, 0.6),
+    "hc24": lambda: mdl.holstein_honeycomb(24, 0.5),
 }
 
 
@@ -194,7 +198,7 @@ def test_register_path_requires_uniform_colours_and_canonical_order():
 
 
 @pytest.mark.parametrize("solver", ["resident", "persistent", "launches"])
-@pytest.mark.parametrize("name", ["h16x16", "h32x16", "h32x32"])
+@pytest.mark.parametrize("name", ["h16x16", "h32x16", "h32x32", "hc8", "hc24"])
 def test_register_path_cg(name, solver, monkeypatch):
     """CG on the register path in native order: the resident kernel, the persistent kernel and the
     two-launches-per-iteration loop against the oracle's CG."""
