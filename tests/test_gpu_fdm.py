@@ -197,15 +197,17 @@ def test_register_path_requires_uniform_colours_and_canonical_order():
     assert relerr(fdm2.mul_MtM(v), ref2.mul_MtM(v)) < RTOL
 
 
-@pytest.mark.parametrize("solver", ["resident", "persistent", "launches"])
+@pytest.mark.parametrize("solver", ["resident", "resident2", "persistent", "launches"])
 @pytest.mark.parametrize("name", ["h16x16", "h32x16", "h32x32", "hc8", "hc24"])
 def test_register_path_cg(name, solver, monkeypatch):
-    """CG on the register path in native order: the resident kernel, the persistent kernel and the
-    two-launches-per-iteration loop against the oracle's CG."""
+    """CG on the register path in native order: the resident kernels (one / two grid-wide sums per iteration), the
+    persistent kernel and the two-launches-per-iteration loop against the oracle's CG."""
     m, rng, ref, fdm = setup_square(name)
     b = rand_cvec(rng, m)
     fdm.set_fast_path(2 + 256 * 3)
-    if solver == "persistent":
+    if solver == "resident2":                       # the two-sums-per-iteration resident kernel (square lattices)
+        monkeypatch.setenv("SQ_V3_RESIDENT", "2")
+    elif solver == "persistent":
         monkeypatch.setenv("SQ_NO_RESIDENT_CG", "1")
     elif solver == "launches":
         monkeypatch.setenv("SQ_NO_PERSISTENT_CG", "1")
