@@ -185,6 +185,11 @@ int sq_greens_get(sq_greens *g, sq_complex *R, sq_complex *GR);
 int sq_greens_set_GR(sq_greens *g, const sq_complex *GR);
 /* measure_n :15, measure_double_occ :112, measure_Nsqrd :31 of src/Measurements/scalar_measurements.jl */
 int sq_greens_measure(sq_greens *g, sq_complex *n, sq_complex *double_occ, sq_complex *Nsqrd);
+/* measure_GΔ0!(correlation, greens_estimator, (a, b))  src/Measurements/GreensEstimator.jl:177-233: the translation-averaged
+ * time-displaced Green's function G_ab(Δτ, Δr) from the current R, G R.  norb orbitals per unit cell (site = orbital + norb x
+ * cell), dims[0..ndim) unit cells per direction (first fastest), a, b 1-based.  out: (Ltau + 1) x dims... complex, tau fastest
+ * (the reference's CΔ0; the caller adds it to `correlation` with the tau axis moved last, :718-729). */
+int sq_greens_measure_GD0(sq_greens *g, int norb, int ndim, const int64_t *dims, int a, int b, sq_complex *out);
 /* update_chemical_potential! minus the MuTuner scalar logic (stays in Julia): returns n, N^2 then
  * applies the new mu via sq_elph_shift_mu + sq_elph_refresh_fdm.  src/update_chemical_potential.jl:21-73 */
 

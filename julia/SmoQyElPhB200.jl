@@ -310,6 +310,18 @@ function _measure(g::GreensEstimator)
     check(ccall((:sq_greens_measure, LIB), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}), g.h, n, d, N2))
     return n[1], d[1], N2[1]
 end
+# measure_GΔ0!(correlation, g, (a, b)) (src/Measurements/GreensEstimator.jl:177-233): the translation-averaged time-displaced Green's
+# function is evaluated on the device (aperiodic extension, (D+1)-dimensional FFT cross-correlation, average over the random vectors)
+# and added to `correlation` with the imaginary-time axis last, as add_contraction_to_correlation! does (:718-729).
+function measure_GΔ0!(correlation::AbstractArray{Complex{E}}, g::GreensEstimator{E}, orbitals::NTuple{2,Int}; n::Int, L::NTuple{D,Int}) where {E,D}
+    Lτ = size(correlation, D + 1) - 1
+    GΔ0 = zeros(Complex{E}, Lτ + 1, L...)
+    dims = collect(Int64, L)
+    GC.@preserve GΔ0 dims check(ccall((:sq_greens_measure_GD0, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Cint, Cint, Ptr{Complex{E}}),
+                                      g.h, n, D, dims, orbitals[1], orbitals[2], GΔ0))
+    @. correlation += $PermutedDimsArray(GΔ0, (2:D+1..., 1))
+    return nothing
+end
 measure_n(g::GreensEstimator) = _measure(g)[1]
 measure_double_occ(g::GreensEstimator) = _measure(g)[2]
 measure_Nsqrd(g::GreensEstimator) = _measure(g)[3]

@@ -429,6 +429,18 @@ class GreensEstimator:
 
     def set_GR(self, GR): check(self.L.sq_greens_set_GR(self.h, ptr(np.asfortranarray(GR, np.complex128))))
 
+    def measure_GD0(self, orbitals=(0, 0), norb=None, dims=None):
+        """measure_GΔ0! (src/Measurements/GreensEstimator.jl:177-233): G_ab(Δr, Δτ) averaged over translations, returned with
+        the reference's `correlation` axes (L..., Ltau + 1).  orbitals are 0-based here."""
+        m = self.fdm.model
+        dims = tuple(m.lattice_dims) if dims is None else tuple(dims)
+        ncell = int(np.prod(dims))
+        norb = m.N // ncell if norb is None else int(norb)
+        d = _i64(dims, one_based=False)
+        out = np.zeros((m.Ltau + 1,) + dims, np.complex128, order="F")
+        check(self.L.sq_greens_measure_GD0(self.h, norb, len(dims), ptr(d), int(orbitals[0]) + 1, int(orbitals[1]) + 1, ptr(out)))
+        return np.moveaxis(out, 0, -1)
+
     def measure(self):
         out = np.zeros((3, 2))
         check(self.L.sq_greens_measure(self.h, ptr(out[0]), ptr(out[1]), ptr(out[2])))

@@ -55,6 +55,7 @@ double hmc_kinetic_dev(sq_hmc *h, const double *pm);
 void greens_create_impl(sq_greens **out, sq_fdm *f, i64 Nrv, uint64_t seed);
 double greens_update_impl(sq_greens *g, sq_kpm *kpm, const void *h_R, double tol, i64 maxiter);
 void greens_measure_impl(sq_greens *g, double *out);
+void greens_measure_GD0_impl(sq_greens *g, int norb, int ndim, const i64 *dims, int a, int b, void *h_out);
 
 extern "C" {
 
@@ -278,7 +279,7 @@ int sq_kpm_create(sq_kpm **out, sq_fdm *f, double rbuf, int64_t n, double a1, do
 }
 int sq_kpm_destroy(sq_kpm *k) {
     SQ_TRY
-    if (k) { cudaSetDevice(k->f->device); cudaStreamSynchronize(k->f->stream); delete k; }
+    if (k) { fdm_sync_if_alive(k->f); delete k; }
     SQ_CATCH
 }
 int sq_kpm_update(sq_kpm *k, const double *lanczos_start, int *active, double *bounds) {
@@ -352,7 +353,7 @@ int sq_elph_create(sq_elph **out, sq_fdm *f, double dtau, int64_t Nph, const dou
 }
 int sq_elph_destroy(sq_elph *e) {
     SQ_TRY
-    if (e) { cudaSetDevice(e->f->device); cudaStreamSynchronize(e->f->stream); delete e; }
+    if (e) { fdm_sync_if_alive(e->f); delete e; }
     SQ_CATCH
 }
 int sq_elph_set_x(sq_elph *e, const double *x) {
@@ -480,7 +481,7 @@ int sq_pff_create(sq_pff **out, sq_elph *e) {
 }
 int sq_pff_destroy(sq_pff *p) {
     SQ_TRY
-    if (p) { cudaSetDevice(p->e->f->device); cudaStreamSynchronize(p->e->f->stream); delete p; }
+    if (p) { fdm_sync_if_alive(p->owner); delete p; }
     SQ_CATCH
 }
 int sq_pff_set_exact_holstein(sq_pff *p, int flag) {
@@ -582,7 +583,7 @@ int sq_hmc_create(sq_hmc **out, sq_pff *p, int64_t Nt, double dt, double eta, do
 }
 int sq_hmc_destroy(sq_hmc *h) {
     SQ_TRY
-    if (h) { cudaSetDevice(h->p->e->f->device); cudaStreamSynchronize(h->p->e->f->stream); delete h; }
+    if (h) { fdm_sync_if_alive(h->owner); delete h; }
     SQ_CATCH
 }
 int sq_hmc_update(sq_hmc *h, sq_kpm *kpm, double tol_action, double tol_force, int64_t maxiter, const double *randoms,
@@ -636,7 +637,7 @@ int sq_greens_create(sq_greens **out, sq_fdm *f, int64_t Nrv, uint64_t seed) {
 }
 int sq_greens_destroy(sq_greens *g) {
     SQ_TRY
-    if (g) { cudaSetDevice(g->f->device); cudaStreamSynchronize(g->f->stream); delete g; }
+    if (g) { fdm_sync_if_alive(g->f); delete g; }
     SQ_CATCH
 }
 int sq_greens_update(sq_greens *g, sq_kpm *kpm, const sq_complex *R, double tol, int64_t maxiter, double *avg_iters) {
@@ -665,6 +666,12 @@ int sq_greens_set_GR(sq_greens *g, const sq_complex *GR) {
     size_t V = (size_t)f->L * f->N;
     for (i64 n = 0; n < g->Nrv; n++) fdm_host_to_dev(f, g->GR.p + n * V, GR + n * V);
     SQ_CUDA(cudaStreamSynchronize(f->stream));
+    SQ_CATCH
+}
+int sq_greens_measure_GD0(sq_greens *g, int norb, int ndim, const int64_t *dims, int a, int b, sq_complex *out) {
+    SQ_TRY
+    SQ_REQUIRE(g && out, "NULL argument");
+    greens_measure_GD0_impl(g, norb, ndim, dims, a, b, out);
     SQ_CATCH
 }
 int sq_greens_measure(sq_greens *g, sq_complex *n, sq_complex *double_occ, sq_complex *Nsqrd) {

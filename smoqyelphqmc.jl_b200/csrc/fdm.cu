@@ -11,6 +11,9 @@
 // flight share one __syncthreads per step.  |w|^2 = p.A p for CG falls out of the first phase.
 #include "sq_internal.h"
 
+#include <mutex>
+#include <set>
+
 #include <algorithm>
 
 // ---------------------------------------------------------------------------------------------------
@@ -605,6 +608,18 @@ void fdm_select_tuning(sq_fdm *f) {
     f->v3_cg = (!(env3 && atoi(env3) == 0) && fdm_v3_supported(f, f->v3_S)) ? 1 : 0;
 }
 
+// Child handles (preconditioner, elph, pff, hmc, greens) keep a raw pointer to their operator.  Host languages with garbage
+// collection may finalise parent and child in any order, so the destroy paths must not dereference a dead operator.
+static std::mutex g_live_mutex;
+static std::set<const sq_fdm *> g_live;
+static void fdm_register(sq_fdm *f) { std::lock_guard<std::mutex> lk(g_live_mutex); g_live.insert(f); }
+void fdm_sync_if_alive(sq_fdm *f) {
+    bool alive;
+    { std::lock_guard<std::mutex> lk(g_live_mutex); alive = g_live.count(f) != 0; }
+    if (alive) { cudaSetDevice(f->device); cudaStreamSynchronize(f->stream); }
+    else cudaDeviceSynchronize();
+}
+
 void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt, const i64 *perm, i64 C,
                      const i64 *clo, const i64 *chi, double tol, i64 maxiter, int device) {
     SQ_REQUIRE(out != nullptr, "out handle pointer is NULL");
@@ -718,12 +733,14 @@ void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt,
         delete f;
         throw;
     }
+    fdm_register(f);
     *out = f;
 }
 
 void slab_destroy(sq_fdm *f);
 void fdm_destroy_impl(sq_fdm *f) {
     if (!f) return;
+    { std::lock_guard<std::mutex> lk(g_live_mutex); g_live.erase(f); }
     cudaSetDevice(f->device);
     slab_destroy(f);
     if (f->stream) { cudaStreamSynchronize(f->stream); cudaStreamDestroy(f->stream); }

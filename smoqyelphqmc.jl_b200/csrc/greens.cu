@@ -6,6 +6,8 @@
 #include "sq_internal.h"
 
 #include <cmath>
+#include <map>
+#include <memory>
 
 // R <- R / |R| (unit-modulus random phases, GreensEstimator.jl:141-142)
 __global__ void k_unit_modulus(double2 *__restrict__ v, size_t n) {
@@ -152,4 +154,130 @@ void greens_measure_impl(sq_greens *g, double *out) {
     double TrGr = tr / (Nrv * L), TrGi = ti / (Nrv * L);
     out[4] = Nbr + 2 * TrGr / L - 2 * T2r;
     out[5] = Nbi + 2 * TrGi / L - 2 * T2i;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Time-displaced Green's function G_ab(Delta) = G(r + Delta_r, tau + Delta_tau | r, tau), averaged over translations:
+// measure_GΔ0! (src/Measurements/GreensEstimator.jl:177-233) with its helpers _aperiodic_copyto! (:656-671),
+// _translational_average! (:674-705).  For every random vector the G R_a and conj(R)_b fields are extended
+// antiperiodically to 2 Ltau slices, cross-correlated over the (D+1)-dimensional space-time torus by FFT, and averaged;
+// the tau = beta slice is -G(tau = 0) (+ 1 at zero displacement for equal orbitals).
+// The (D+1)-dimensional transform is the library's own tau-FFT kernel (fft.cu) applied to the outermost axis, followed by a
+// transpose that rotates the axes -- D+1 times.  The products are accumulated in frequency space, so there is one inverse
+// transform per orbital pair instead of one per random vector.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_gd0_fill(double2 *__restrict__ A, double2 *__restrict__ B, const double2 *__restrict__ GR, const double2 *__restrict__ R,
+                           int Lt, int N, int Nc, int norb, int a, int b) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)Lt * Nc) return;
+    const int l = (int)(idx / Nc), c = (int)(idx % Nc);
+    const double2 g = GR[(size_t)l * N + a + norb * c], r = R[(size_t)l * N + b + norb * c];
+    A[idx] = g;
+    A[idx + (size_t)Lt * Nc] = make_double2(-g.x, -g.y);
+    B[idx] = make_double2(r.x, -r.y);                              // Rt = conj(R)
+    B[idx + (size_t)Lt * Nc] = make_double2(-r.x, r.y);
+}
+__global__ void k_cmul_acc(double2 *__restrict__ C, const double2 *__restrict__ A, const double2 *__restrict__ B, size_t n) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) C[k] = cadd(C[k], cmul(A[k], B[k]));
+}
+// src [rows][cols] (cols fastest) -> dst [cols][rows]
+__global__ void k_transpose_c(double2 *__restrict__ dst, const double2 *__restrict__ src, int rows, int cols) {
+    __shared__ double2 tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int r = r0 + dy, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[dy][threadIdx.x] = src[(size_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+        const int c = c0 + dy, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][dy];
+    }
+}
+// out: (Ltau + 1, cells) tau fastest.  s: [tau'][cell]
+__global__ void k_gd0_finish(double2 *__restrict__ out, const double2 *__restrict__ s, int Lt, int Nc, double scale, int same_orbital) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)(Lt + 1) * Nc) return;
+    const int c = (int)(idx / (Lt + 1)), t = (int)(idx % (Lt + 1));
+    double2 v;
+    if (t < Lt) {
+        v = cscale(scale, s[(size_t)t * Nc + c]);
+    } else {
+        v = cscale(-scale, s[c]);                                   // G(r, beta) = delta(r) - G(r, 0)
+        if (same_orbital && c == 0) v.x += 1.0;
+    }
+    out[idx] = v;
+}
+
+// (D+1)-dimensional DFT of buf (axes outermost -> innermost: dims[0..nd)), each axis scaled by 1/sqrt(length); tmp is scratch.
+// On return the data is in *buf (the pointers may have been exchanged).
+static void greens_fftnd(sq_greens *g, double2 **buf, double2 **tmp, const std::vector<int> &dims, bool inverse) {
+    sq_fdm *f = g->f;
+    size_t M = 1;
+    for (int d : dims) M *= (size_t)d;
+    for (size_t ax = 0; ax < dims.size(); ax++) {
+        const int L = dims[ax];
+        const size_t ncol = M / L;
+        if (L == 1) continue;                                       // [1][M] -> [M][1]: the rotation is the identity
+        auto it = g->fft_tw.find(L);
+        if (it == g->fft_tw.end()) {
+            std::vector<double2> tw;
+            fft_make_twiddles(L, tw);
+            auto ins = g->fft_tw.emplace(L, std::unique_ptr<DevBuf<double2>>(new DevBuf<double2>()));
+            it = ins.first;
+            it->second->from_vector(tw, f->stream);
+        }
+        std::vector<int> rad;
+        fft_radices(L, rad);
+        SQ_REQUIRE(ncol < ((size_t)1 << 31), "correlation array too large");
+        tau_fft_launch(f->stream, rad, L, (int)ncol, *buf, *buf, inverse, false, it->second->p, nullptr, nullptr, nullptr, nullptr, nullptr,
+                       f->smem_optin);
+        dim3 grid((unsigned)((ncol + 31) / 32), (unsigned)((L + 31) / 32));
+        k_transpose_c<<<grid, dim3(32, 8), 0, f->stream>>>(*tmp, *buf, L, (int)ncol);
+        SQ_LAUNCH_CHECK();
+        f->launches += 2;
+        std::swap(*buf, *tmp);
+    }
+}
+
+// h_out: (Ltau + 1) x cells complex, tau fastest (the CΔ0 array of the reference).  dims: unit cells per direction, first fastest.
+void greens_measure_GD0_impl(sq_greens *g, int norb, int ndim, const i64 *dims, int a, int b, void *h_out) {
+    sq_fdm *f = g->f;
+    SQ_CUDA(cudaSetDevice(f->device));
+    SQ_REQUIRE(norb >= 1 && ndim >= 1 && ndim <= 3 && dims && h_out, "bad argument");
+    SQ_REQUIRE(a >= 1 && a <= norb && b >= 1 && b <= norb, "orbital index out of range");
+    size_t Nc = 1;
+    for (int d = 0; d < ndim; d++) { SQ_REQUIRE(dims[d] >= 1, "bad lattice dimension"); Nc *= (size_t)dims[d]; }
+    SQ_REQUIRE((i64)(Nc * norb) == f->N, "unit cells x orbitals does not match the number of sites");
+    const int Lt = (int)f->L;
+    const size_t M = (size_t)2 * Lt * Nc, V = (size_t)f->L * f->N;
+    if (g->wa.n < M) { g->wa.alloc(M, false); g->wb.alloc(M, false); g->wc.alloc(M, false); g->wt.alloc(M, false); }
+    std::vector<int> ax;                                            // outermost -> innermost: tau', then the slowest lattice direction ...
+    ax.push_back(2 * Lt);
+    for (int d = ndim - 1; d >= 0; d--) ax.push_back((int)dims[d]);
+    SQ_CUDA(cudaMemsetAsync(g->wc.p, 0, M * sizeof(double2), f->stream));
+    double2 *A = g->wa.p, *B = g->wb.p, *C = g->wc.p, *T = g->wt.p;
+    const size_t half = (size_t)Lt * Nc;
+    for (i64 n = 0; n < g->Nrv; n++) {
+        k_gd0_fill<<<(unsigned)((half + 255) / 256), 256, 0, f->stream>>>(A, B, g->GR.p + n * V, g->R.p + n * V, Lt, (int)f->N, (int)Nc, norb, a - 1, b - 1);
+        SQ_LAUNCH_CHECK();
+        greens_fftnd(g, &A, &T, ax, false);
+        greens_fftnd(g, &B, &T, ax, true);
+        k_cmul_acc<<<f->num_sms * 4, 256, 0, f->stream>>>(C, A, B, M);
+        SQ_LAUNCH_CHECK();
+        f->launches += 2;
+    }
+    greens_fftnd(g, &C, &T, ax, true);
+    // the library's transforms carry 1/sqrt(M) each; the reference is ifft(fft(A) .* ifft(B)) with FFTW's 1/M in ifft
+    const double scale = 1.0 / (std::sqrt((double)M) * (double)g->Nrv);
+    const size_t nout = (size_t)(Lt + 1) * Nc;
+    double2 *dout = (C == g->wa.p || T == g->wa.p) ? nullptr : nullptr;
+    (void)dout;
+    double2 *O = (A != C && A != T) ? A : B;                        // any work buffer that is not C or the scratch T
+    k_gd0_finish<<<(unsigned)((nout + 255) / 256), 256, 0, f->stream>>>(O, C, Lt, (int)Nc, scale, a == b ? 1 : 0);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+    SQ_CUDA(cudaMemcpyAsync(h_out, O, nout * sizeof(double2), cudaMemcpyDeviceToHost, f->stream));
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
 }

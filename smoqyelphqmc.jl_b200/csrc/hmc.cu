@@ -99,7 +99,7 @@ void hmc_create_impl(sq_hmc **out, sq_pff *q, i64 Nt, double dt, double eta, dou
     SQ_CUDA(cudaSetDevice(f->device));
     sq_hmc *h = new sq_hmc();
     try {
-        h->p = q; h->Nt = Nt; h->dt = dt; h->eta = eta; h->delta = delta; h->seed = seed;
+        h->p = q; h->owner = f; h->Nt = Nt; h->dt = dt; h->eta = eta; h->delta = delta; h->seed = seed;
         i64 L = f->L, Nph = e->Nph;
         size_t nx = (size_t)L * Nph;
         h->x0.alloc(nx); h->pm.alloc(nx); h->dS.alloc(nx);

@@ -152,6 +152,7 @@ void pff_create_impl(sq_pff **out, sq_elph *e) {
     sq_pff *q = new sq_pff();
     try {
         q->e = e;
+        q->owner = f;
         size_t V = (size_t)f->L * f->N;
         q->Phi.alloc(V); q->u.alloc(V); q->up.alloc(V); q->upp.alloc(V); q->w1.alloc(V); q->w2.alloc(V);
         q->Lam.alloc(V);

@@ -1,6 +1,9 @@
 // sq_internal.h -- handle definitions behind the opaque types of include/smoqyelph_b200.h
 #pragma once
 #include "common.cuh"
+
+#include <map>
+#include <memory>
 #include "smoqyelph_b200.h"
 
 #define SQ_MAXC 32          // maximum number of checkerboard colours
@@ -150,6 +153,7 @@ struct sq_elph {
 
 struct sq_pff {
     sq_elph *e = nullptr;
+    sq_fdm *owner = nullptr;                 // = e->f, kept for the destroy path (the parents may already be gone)
     DevBuf<double2> Phi, u, up, upp, w1, w2; // [l][i]
     DevBuf<double> Lam;                      // [l][i]
     DevBuf<double> F;                        // [l][p] force accumulator on the device
@@ -161,6 +165,7 @@ struct sq_pff {
 
 struct sq_hmc {
     sq_pff *p = nullptr;
+    sq_fdm *owner = nullptr;                 // = p->e->f
     i64 Nt = 0;
     double dt = 0, eta = 0, delta = 0;
     uint64_t seed = 0, counter = 0;
@@ -178,6 +183,8 @@ struct sq_greens {
     i64 Nrv = 0;
     uint64_t seed = 0, counter = 0;
     DevBuf<double2> R, GR, MtR;              // Nrv vectors, [l][i] each
+    DevBuf<double2> wa, wb, wc, wt;          // work arrays of the correlation measurements (2 Ltau x cells)
+    std::map<int, std::unique_ptr<DevBuf<double2>>> fft_tw;   // twiddles per transform length
     DevBuf<double> part;
 };
 
@@ -209,6 +216,7 @@ int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, 
 void rng_fill_normal(double *d_out, size_t n, uint64_t seed, uint64_t stream, cudaStream_t s);
 void rng_fill_uniform(double *d_out, size_t n, uint64_t seed, uint64_t stream, cudaStream_t s);
 void fdm_select_tuning(sq_fdm *f);
+void fdm_sync_if_alive(sq_fdm *f);       // stream-synchronise f if it has not been destroyed yet, else the device
 void fdm_halo_exchange(sq_fdm *f, double2 *v);
 void fdm_allreduce_sum(sq_fdm *f, double *d_buf, int count);
 void fdm_cg_slab(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, double tol, i64 maxiter, i64 *iters, double *eps);

@@ -1,0 +1,104 @@
+"""Device-side correlation measurements against a numpy restatement of the reference:
+measure_GΔ0! (/root/reference/src/Measurements/GreensEstimator.jl:177-233) with _aperiodic_copyto! (:656-671),
+_translational_average! (:674-705) and add_contraction_to_correlation! (:718-729)."""
+import numpy as np
+import pytest
+
+from smoqyelph_b200 import model as mdl
+import dense_ref as dr
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_measure_GD0(R, GR, Ltau, norb, dims, a, b):
+    """Literal restatement.  R, GR: (V, Nrv) columns in the reference layout (tau fastest, then orbital, then cells)."""
+    Nrv = R.shape[1]
+    shape = (Ltau, norb) + tuple(dims)
+    Rt = np.conj(R).reshape(shape + (Nrv,), order="F")
+    G = GR.reshape(shape + (Nrv,), order="F")
+    S = np.zeros((Ltau + 1,) + tuple(dims), complex)
+    for i in range(Nrv):
+        A = np.concatenate([G[:, a, ..., i], -G[:, a, ..., i]], axis=0)          # aperiodic copy to 2 Ltau
+        B = np.concatenate([Rt[:, b, ..., i], -Rt[:, b, ..., i]], axis=0)
+        c = np.fft.ifftn(np.fft.fftn(A) * np.fft.ifftn(B))                        # FFTW: fft unnormalised, ifft 1/M
+        S[:Ltau] += c[:Ltau]
+        S[Ltau] += c[0]
+    S /= Nrv
+    S[Ltau] = -S[Ltau]
+    if a == b:
+        S[(Ltau,) + (0,) * len(dims)] += 1.0
+    return np.moveaxis(S, 0, -1)                                                  # correlation axes: (L..., Ltau + 1)
+
+
+def direct_translational_average(R, GR, Ltau, norb, dims, a, b, dl, dr_):
+    """Independent O(V) check of one displacement: (1/(2 Ltau Nc)) sum over the doubled torus of A(x + D) B(x)."""
+    Nrv = R.shape[1]
+    shape = (Ltau, norb) + tuple(dims)
+    Rt = np.conj(R).reshape(shape + (Nrv,), order="F")
+    G = GR.reshape(shape + (Nrv,), order="F")
+    tot = 0.0
+    for i in range(Nrv):
+        A = np.concatenate([G[:, a, ..., i], -G[:, a, ..., i]], axis=0)
+        B = np.concatenate([Rt[:, b, ..., i], -Rt[:, b, ..., i]], axis=0)
+        Ash = np.roll(A, shift=[-dl] + [-d for d in dr_], axis=tuple(range(A.ndim)))
+        tot += np.mean(Ash * B)
+    return tot / Nrv
+
+
+@pytest.mark.parametrize("name", ["honeycomb", "square", "chain"])
+def test_measure_GD0_matches_reference_formula(name):
+    from smoqyelph_b200 import api
+    m = {"honeycomb": lambda: mdl.holstein_honeycomb(3, 1.0, mu=0.2), "square": lambda: mdl.holstein_square(16, 16, 0.5),
+         "chain": lambda: mdl.ossh_chain(12, 0.6)}[name]()
+    rng = np.random.default_rng(4)
+    V, t = dr.build_Vt(m, m.random_fields(rng, smooth=True))
+    fdm = api.SymFermionDetMatrix(m, tol=1e-12, maxiter=20000)
+    fdm.update(V, t)
+    g = api.GreensEstimator(fdm, Nrv=5, seed=1)
+    g.update_greens_estimator(tol=1e-12)
+    R, GR = g.get()
+    dims = tuple(m.lattice_dims)
+    norb = m.N // int(np.prod(dims))
+    for a in range(norb):
+        for b in range(norb):
+            got = g.measure_GD0((a, b))
+            want = ref_measure_GD0(R, GR, m.Ltau, norb, dims, a, b)
+            assert got.shape == want.shape == dims + (m.Ltau + 1,)
+            assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max()), (name, a, b, np.abs(got - want).max())
+    # one displacement against the direct sum (checks the restatement itself)
+    dl, dsp = 3 % m.Ltau, [1] + [0] * (len(dims) - 1)
+    got = g.measure_GD0((0, norb - 1))
+    direct = direct_translational_average(R, GR, m.Ltau, norb, dims, 0, norb - 1, dl, dsp)
+    assert abs(got[tuple(dsp) + (dl,)] - direct) < 1e-12
+
+
+def test_GD0_of_free_fermions_is_the_exact_greens_function():
+    """alpha = 0: the stochastic estimator averaged over many random vectors reproduces the exact equal-time and
+    time-displaced free-fermion Green's function G(r, tau) = (1/N) sum_k e^{ikr} e^{-tau eps_k} / (1 + e^{-beta eps_k})
+    of the checkerboard-decomposed propagator to the statistical error of the estimator (~1/sqrt(Nrv V))."""
+    from smoqyelph_b200 import api
+    m = mdl.holstein_square(16, 16, 0.4, alpha=0.0, mu=-0.3)
+    V, t = dr.build_Vt(m, np.zeros((m.Nph, m.Ltau)))
+    fdm = api.SymFermionDetMatrix(m, tol=1e-12, maxiter=20000)
+    fdm.update(V, t)
+    g = api.GreensEstimator(fdm, Nrv=40, seed=3)
+    g.update_greens_estimator(tol=1e-12)
+    G = g.measure_GD0((0, 0)).real
+    # exact G(r, tau) through the dense propagator of the same checkerboard operator (tau-independent fields)
+    B = dr.propagators(m, V, t, sym=True)[0]
+    G0 = np.linalg.inv(np.eye(m.N) + np.linalg.matrix_power(B, m.Ltau))
+    Lx, Ly = m.lattice_dims
+    idx = np.arange(m.N)
+    x, y = idx % Lx, idx // Lx
+
+    def averaged(Gl, dx, dy):                               # (1/N) sum_r G(r + d | r)
+        j = ((x + dx) % Lx) + Lx * ((y + dy) % Ly)
+        return np.mean(Gl[j, idx])
+
+    err = 10.0 / np.sqrt(40 * m.N)                           # estimator noise per displacement ~ 1 / sqrt(Nrv N Ltau) x O(1)
+    for l in (0, 1, m.Ltau // 2, m.Ltau - 1):
+        Gl = np.linalg.matrix_power(B, l) @ G0
+        for d in ((0, 0), (1, 0), (0, 1), (3, 2)):
+            assert abs(G[d[0], d[1], l] - averaged(Gl, *d)) < err, (l, d, G[d[0], d[1], l], averaged(Gl, *d))
+    assert abs(G[0, 0, m.Ltau] - (1.0 - averaged(G0, 0, 0))) < err
+    assert abs(G[1, 0, m.Ltau] + averaged(G0, 1, 0)) < err
