@@ -190,6 +190,14 @@ int sq_greens_measure(sq_greens *g, sq_complex *n, sq_complex *double_occ, sq_co
  * cell), dims[0..ndim) unit cells per direction (first fastest), a, b 1-based.  out: (Ltau + 1) x dims... complex, tau fastest
  * (the reference's CΔ0; the caller adds it to `correlation` with the tau axis moved last, :718-729). */
 int sq_greens_measure_GD0(sq_greens *g, int norb, int ndim, const int64_t *dims, int a, int b, sq_complex *out);
+/* The four-point contractions of src/Measurements/GreensEstimator.jl (no hopping weights tΔ / t0):
+ *   kind 0  measure_GΔ0_GΔ0!  :236-388      kind 1  measure_GΔΔ_G00!  :391-467      kind 2  measure_G0Δ_GΔ0!  :470-606
+ * orbitals[4] = (a, b, c, d) 1-based, r = the static displacements r1..r4 in unit cells, 4 x ndim (r1 first).  out as above;
+ * the caller multiplies by `coef` and adds it to `correlation` (add_contraction_to_correlation!, :718-729). */
+int sq_greens_measure_contraction(sq_greens *g, int kind, int norb, int ndim, const int64_t *dims, const int *orbitals, const int64_t *r,
+                                  sq_complex *out);
+/* measure_n(greens_estimator, orbital)  src/Measurements/scalar_measurements.jl:2-12 */
+int sq_greens_measure_n_orbital(sq_greens *g, int norb, int a, sq_complex *n);
 /* update_chemical_potential! minus the MuTuner scalar logic (stays in Julia): returns n, N^2 then
  * applies the new mu via sq_elph_shift_mu + sq_elph_refresh_fdm.  src/update_chemical_potential.jl:21-73 */
 

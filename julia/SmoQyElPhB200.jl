@@ -322,6 +322,26 @@ function measure_GΔ0!(correlation::AbstractArray{Complex{E}}, g::GreensEstimato
     @. correlation += $PermutedDimsArray(GΔ0, (2:D+1..., 1))
     return nothing
 end
+# The four-point contractions (src/Measurements/GreensEstimator.jl:236-606) without hopping weights; the correlation functions built on
+# them (density.jl, pair.jl, spin.jl) call these exactly as in the reference.
+function _contraction!(correlation::AbstractArray{Complex{E}}, g::GreensEstimator{E}, kind::Int, orbitals::NTuple{4,Int}, r1, r2, r3, r4, coef;
+                       n::Int, L::NTuple{D,Int}) where {E,D}
+    Lτ = size(correlation, D + 1) - 1
+    C = zeros(Complex{E}, Lτ + 1, L...)
+    dims = collect(Int64, L); orb = collect(Cint, orbitals); r = Int64[r1..., r2..., r3..., r4...]
+    GC.@preserve C dims orb r check(ccall((:sq_greens_measure_contraction, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Ptr{Cint}, Ptr{Int64}, Ptr{Complex{E}}), g.h, kind, n, D, dims, orb, r, C))
+    @. correlation += coef * $PermutedDimsArray(C, (2:D+1..., 1))
+    return nothing
+end
+measure_GΔ0_GΔ0!(corr, g::GreensEstimator, orbitals, r1, r2, r3, r4, coef; kw...) = _contraction!(corr, g, 0, orbitals, r1, r2, r3, r4, coef; kw...)
+measure_GΔΔ_G00!(corr, g::GreensEstimator, orbitals, r1, r2, r3, r4, coef; kw...) = _contraction!(corr, g, 1, orbitals, r1, r2, r3, r4, coef; kw...)
+measure_G0Δ_GΔ0!(corr, g::GreensEstimator, orbitals, r1, r2, r3, r4, coef; kw...) = _contraction!(corr, g, 2, orbitals, r1, r2, r3, r4, coef; kw...)
+function measure_n(g::GreensEstimator{E}, orbital::Int; n::Int) where {E}
+    out = zeros(Complex{E}, 1)
+    check(ccall((:sq_greens_measure_n_orbital, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Complex{E}}), g.h, n, orbital, out))
+    return out[1]
+end
 measure_n(g::GreensEstimator) = _measure(g)[1]
 measure_double_occ(g::GreensEstimator) = _measure(g)[2]
 measure_Nsqrd(g::GreensEstimator) = _measure(g)[3]

@@ -441,6 +441,50 @@ class GreensEstimator:
         check(self.L.sq_greens_measure_GD0(self.h, norb, len(dims), ptr(d), int(orbitals[0]) + 1, int(orbitals[1]) + 1, ptr(out)))
         return np.moveaxis(out, 0, -1)
 
+    def _geom(self, norb, dims):
+        m = self.fdm.model
+        dims = tuple(m.lattice_dims) if dims is None else tuple(dims)
+        return (m.N // int(np.prod(dims)) if norb is None else int(norb)), dims
+
+    def measure_contraction(self, kind, orbitals, r=None, norb=None, dims=None):
+        """kind: "GD0_GD0" (measure_GΔ0_GΔ0!), "GDD_G00" (measure_GΔΔ_G00!) or "G0D_GD0" (measure_G0Δ_GΔ0!)
+        (src/Measurements/GreensEstimator.jl:236-606); orbitals (a, b, c, d) 0-based, r = (r1, r2, r3, r4) displacement tuples
+        (default all zero).  Returns the contraction with the reference's `correlation` axes (L..., Ltau + 1), coef = 1."""
+        m = self.fdm.model
+        norb, dims = self._geom(norb, dims)
+        code = {"GD0_GD0": 0, "GDD_G00": 1, "G0D_GD0": 2}[kind]
+        rr = np.zeros((4, len(dims)), np.int64) if r is None else np.ascontiguousarray(r, np.int64).reshape(4, len(dims))
+        orb = np.ascontiguousarray(np.asarray(orbitals, np.int32) + 1)
+        out = np.zeros((m.Ltau + 1,) + dims, np.complex128, order="F")
+        check(self.L.sq_greens_measure_contraction(self.h, code, norb, len(dims), ptr(_i64(dims, one_based=False)), ptr(orb), ptr(rr), ptr(out)))
+        return np.moveaxis(out, 0, -1)
+
+    def measure_n_orbital(self, a, norb=None, dims=None):
+        norb, dims = self._geom(norb, dims)
+        out = np.zeros(2)
+        check(self.L.sq_greens_measure_n_orbital(self.h, norb, int(a) + 1, ptr(out)))
+        return complex(out[0], out[1])
+
+    def measure_density_correlation(self, a, b, coef=1.0, norb=None, dims=None):
+        """measure_density_correlation!(DD, greens_estimator, a, b, coef)  (src/Measurements/Correlations/density.jl:2-33):
+        DD = 4 coef (n_a + n_b - 1) + 4 coef G(Δ,Δ)G(0,0)[a,a,b,b] - 2 coef G(0,Δ)G(Δ,0)[b,a,a,b]."""
+        na, nb = self.measure_n_orbital(a, norb, dims), self.measure_n_orbital(b, norb, dims)
+        DD = 4 * coef * self.measure_contraction("GDD_G00", (a, a, b, b), norb=norb, dims=dims)
+        DD -= 2 * coef * self.measure_contraction("G0D_GD0", (b, a, a, b), norb=norb, dims=dims)
+        return DD + 4 * coef * (na + nb - 1)
+
+    def measure_pair_correlation(self, bond1, bond2, coef=1.0, norb=None, dims=None):
+        """measure_pair_correlation!(PP, greens_estimator, b', b'', coef)  (src/Measurements/Correlations/pair.jl:2-21).
+        A bond is ((orbital_1, orbital_2), displacement); b, a = b'.orbitals, d, c = b''.orbitals."""
+        (b, a), r1 = bond1
+        (d, c), r2 = bond2
+        z = (0,) * len(tuple(r1))
+        return coef * self.measure_contraction("GD0_GD0", (a, c, b, d), (tuple(r1), tuple(r2), z, z), norb=norb, dims=dims)
+
+    def measure_spin_correlation(self, a, b, coef=1.0, norb=None, dims=None):
+        """measure_spin_correlation!(SzSz, greens_estimator, a, b, coef)  (src/Measurements/Correlations/spin.jl:2-15)."""
+        return -0.5 * coef * self.measure_contraction("G0D_GD0", (b, a, a, b), norb=norb, dims=dims)
+
     def measure(self):
         out = np.zeros((3, 2))
         check(self.L.sq_greens_measure(self.h, ptr(out[0]), ptr(out[1]), ptr(out[2])))

@@ -55,6 +55,8 @@ double hmc_kinetic_dev(sq_hmc *h, const double *pm);
 void greens_create_impl(sq_greens **out, sq_fdm *f, i64 Nrv, uint64_t seed);
 double greens_update_impl(sq_greens *g, sq_kpm *kpm, const void *h_R, double tol, i64 maxiter);
 void greens_measure_impl(sq_greens *g, double *out);
+void greens_measure_c4_impl(sq_greens *g, int kind, int norb, int ndim, const i64 *dims, const int *orb, const i64 *r, void *h_out);
+void greens_measure_n_orbital_impl(sq_greens *g, int norb, int a, double *out);
 void greens_measure_GD0_impl(sq_greens *g, int norb, int ndim, const i64 *dims, int a, int b, void *h_out);
 
 extern "C" {
@@ -672,6 +674,19 @@ int sq_greens_measure_GD0(sq_greens *g, int norb, int ndim, const int64_t *dims,
     SQ_TRY
     SQ_REQUIRE(g && out, "NULL argument");
     greens_measure_GD0_impl(g, norb, ndim, dims, a, b, out);
+    SQ_CATCH
+}
+int sq_greens_measure_contraction(sq_greens *g, int kind, int norb, int ndim, const int64_t *dims, const int *orbitals, const int64_t *r,
+                                  sq_complex *out) {
+    SQ_TRY
+    SQ_REQUIRE(g && out, "NULL argument");
+    greens_measure_c4_impl(g, kind, norb, ndim, dims, orbitals, r, out);
+    SQ_CATCH
+}
+int sq_greens_measure_n_orbital(sq_greens *g, int norb, int a, sq_complex *n) {
+    SQ_TRY
+    SQ_REQUIRE(g && n, "NULL argument");
+    greens_measure_n_orbital_impl(g, norb, a, (double *)n);
     SQ_CATCH
 }
 int sq_greens_measure(sq_greens *g, sq_complex *n, sq_complex *double_occ, sq_complex *Nsqrd) {

@@ -6,6 +6,7 @@
 #include "sq_internal.h"
 
 #include <cmath>
+#include <cstring>
 #include <map>
 #include <memory>
 
@@ -280,4 +281,190 @@ void greens_measure_GD0_impl(sq_greens *g, int norb, int ndim, const i64 *dims, 
     f->launches++;
     SQ_CUDA(cudaMemcpyAsync(h_out, O, nout * sizeof(double2), cudaMemcpyDeviceToHost, f->stream));
     SQ_CUDA(cudaStreamSynchronize(f->stream));
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Four-point contractions built from pairs of random vectors (src/Measurements/GreensEstimator.jl:236-652):
+//   kind 0  measure_GΔ0_GΔ0!   G(a,i+r+r1,τ | b,i+r2,0) G(c,i+r+r3,τ | d,i+r4,0)     :236-388
+//   kind 1  measure_GΔΔ_G00!   G(a,i+r+r1,τ | b,i+r+r2,τ) G(c,i+r3,0 | d,i+r4,0)     :391-467
+//   kind 2  measure_G0Δ_GΔ0!   G(a,i+r1,0 | b,i+r+r2,τ) G(c,i+r+r3,τ | d,i+r4,0)     :470-606
+// each = average over pairs n < m of the translational average (_measure_CΔ0!, :610-652, periodic Ltau x L... torus) of two
+// element-wise products of G R / conj(R) fields, plus delta-function terms at τ = 0 / β.  No hopping weights (tΔ, t0 = nothing):
+// that covers the density, pair and spin correlations.  As for G(Δ,0) the products are accumulated in frequency space.
+// ---------------------------------------------------------------------------------------------------
+struct C4Field { const double2 *v; int orb, conj, sh[3]; };
+struct C4Geom { int Lt, N, norb, nd, d[3]; size_t Nc; };
+
+__device__ __forceinline__ double2 c4_value(const C4Field &f, const C4Geom &G, int l, size_t c) {
+    // value at cell c displaced by sh (the reference's circshift by -r: result[i] = field[i + r])
+    size_t cs = 0, mul = 1;
+    size_t rem = c;
+    for (int k = 0; k < G.nd; k++) {
+        int ck = (int)(rem % G.d[k]);
+        rem /= G.d[k];
+        int q = (ck + f.sh[k]) % G.d[k];
+        if (q < 0) q += G.d[k];
+        cs += (size_t)q * mul;
+        mul *= G.d[k];
+    }
+    double2 x = f.v[(size_t)l * G.N + f.orb + G.norb * cs];
+    if (f.conj) x.y = -x.y;
+    return x;
+}
+__global__ void k_c4_fill(double2 *__restrict__ X, double2 *__restrict__ Y, const C4Field f1, const C4Field f2, const C4Field f3, const C4Field f4,
+                          const C4Geom G) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)G.Lt * G.Nc) return;
+    const int l = (int)(idx / G.Nc);
+    const size_t c = idx % G.Nc;
+    X[idx] = cmul(c4_value(f1, G, l, c), c4_value(f2, G, l, c));
+    Y[idx] = cmul(c4_value(f3, G, l, c), c4_value(f4, G, l, c));
+}
+// partial sums of sum_{l, c} f1(l, c) f2(l, c)
+__global__ void k_c4_dot(double *__restrict__ part, const C4Field f1, const C4Field f2, const C4Geom G) {
+    __shared__ double red[2 * 32];
+    double v[2] = {0, 0};
+    const size_t tot = (size_t)G.Lt * G.Nc;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (size_t)gridDim.x * blockDim.x) {
+        const double2 p = cmul(c4_value(f1, G, (int)(idx / G.Nc), idx % G.Nc), c4_value(f2, G, (int)(idx / G.Nc), idx % G.Nc));
+        v[0] += p.x;
+        v[1] += p.y;
+    }
+    block_sum<2>(v, red);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = v[0]; part[2 * blockIdx.x + 1] = v[1]; }
+}
+__global__ void k_c4_finish(double2 *__restrict__ out, const double2 *__restrict__ s, int Lt, size_t Nc, double scale) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)(Lt + 1) * Nc) return;
+    const size_t c = idx / (Lt + 1);
+    const int t = (int)(idx % (Lt + 1));
+    out[idx] = cscale(scale, s[(size_t)(t < Lt ? t : 0) * Nc + c]);          // S[beta] = S[0]
+}
+
+// sum over random vectors of mean_{tau, cells} GR(orb_g, cell + sh) conj(R)(orb_r, cell), divided by Nrv
+static void c4_mean_GR_Rt(sq_greens *g, const C4Geom &G, int orb_g, const int *sh, int orb_r, double *re, double *im) {
+    sq_fdm *f = g->f;
+    const size_t V = (size_t)f->L * f->N;
+    const int nb = 64;
+    std::vector<double> h(2 * nb);
+    double sr = 0, si = 0;
+    for (i64 n = 0; n < g->Nrv; n++) {
+        C4Field a = {g->GR.p + n * V, orb_g, 0, {sh[0], sh[1], sh[2]}}, b = {g->R.p + n * V, orb_r, 1, {0, 0, 0}};
+        k_c4_dot<<<nb, 256, 0, f->stream>>>(g->part.p, a, b, G);
+        SQ_LAUNCH_CHECK();
+        f->launches++;
+        SQ_CUDA(cudaMemcpyAsync(h.data(), g->part.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+        SQ_CUDA(cudaStreamSynchronize(f->stream));
+        for (int k = 0; k < nb; k++) { sr += h[2 * k]; si += h[2 * k + 1]; }
+    }
+    const double den = (double)g->Nrv * (double)G.Lt * (double)G.Nc;
+    *re = sr / den;
+    *im = si / den;
+}
+
+// orbital-resolved density  n_a = 1 - dot(R_a, GR_a) / length   (scalar_measurements.jl:2-27)
+void greens_measure_n_orbital_impl(sq_greens *g, int norb, int a, double *out) {
+    sq_fdm *f = g->f;
+    SQ_CUDA(cudaSetDevice(f->device));
+    SQ_REQUIRE(norb >= 1 && a >= 1 && a <= norb && f->N % norb == 0, "bad orbital");
+    C4Geom G = {(int)f->L, (int)f->N, norb, 1, {(int)(f->N / norb), 1, 1}, (size_t)(f->N / norb)};
+    const int z[3] = {0, 0, 0};
+    double re, im;
+    c4_mean_GR_Rt(g, G, a - 1, z, a - 1, &re, &im);
+    out[0] = 1.0 - re;
+    out[1] = -im;
+}
+
+// h_out: (Ltau + 1) x cells complex, tau fastest.  orb[4] 1-based orbitals (a, b, c, d); r: 4 x ndim static displacements.
+void greens_measure_c4_impl(sq_greens *g, int kind, int norb, int ndim, const i64 *dims, const int *orb, const i64 *r, void *h_out) {
+    sq_fdm *f = g->f;
+    SQ_CUDA(cudaSetDevice(f->device));
+    SQ_REQUIRE(kind >= 0 && kind <= 2 && norb >= 1 && ndim >= 1 && ndim <= 3 && dims && orb && r && h_out, "bad argument");
+    SQ_REQUIRE(g->Nrv >= 2, "the four-point contractions need at least two random vectors");
+    C4Geom G;
+    G.Lt = (int)f->L; G.N = (int)f->N; G.norb = norb; G.nd = ndim; G.Nc = 1;
+    for (int k = 0; k < 3; k++) G.d[k] = 1;
+    for (int k = 0; k < ndim; k++) { SQ_REQUIRE(dims[k] >= 1, "bad lattice dimension"); G.d[k] = (int)dims[k]; G.Nc *= (size_t)dims[k]; }
+    SQ_REQUIRE((i64)(G.Nc * norb) == f->N, "unit cells x orbitals does not match the number of sites");
+    for (int q = 0; q < 4; q++) SQ_REQUIRE(orb[q] >= 1 && orb[q] <= norb, "orbital index out of range");
+    const int a = orb[0] - 1, b = orb[1] - 1, c = orb[2] - 1, d = orb[3] - 1;
+    int R[4][3] = {{0}};
+    for (int q = 0; q < 4; q++) for (int k = 0; k < ndim; k++) R[q][k] = (int)r[q * ndim + k];
+    const int Lt = G.Lt;
+    const size_t M = (size_t)Lt * G.Nc, V = (size_t)f->L * f->N;
+    if (g->wa.n < 2 * M) { g->wa.alloc(2 * M, false); g->wb.alloc(2 * M, false); g->wc.alloc(2 * M, false); g->wt.alloc(2 * M, false); }
+    std::vector<int> ax;
+    ax.push_back(Lt);
+    for (int k = ndim - 1; k >= 0; k--) ax.push_back(G.d[k]);
+    SQ_CUDA(cudaMemsetAsync(g->wc.p, 0, M * sizeof(double2), f->stream));
+    double2 *X = g->wa.p, *Y = g->wb.p, *C = g->wc.p, *T = g->wt.p;
+    auto field = [&](bool gr, i64 n, int o, const int *sh) {
+        C4Field x = {(gr ? g->GR.p : g->R.p) + n * V, o, gr ? 0 : 1, {sh[0], sh[1], sh[2]}};
+        return x;
+    };
+    for (i64 n = 0; n + 1 < g->Nrv; n++)
+        for (i64 m = n + 1; m < g->Nrv; m++) {
+            const C4Field GRa = field(true, n, a, R[0]), Rtb = field(false, n, b, R[1]), GRc = field(true, m, c, R[2]), Rtd = field(false, m, d, R[3]);
+            if (kind == 0) k_c4_fill<<<(unsigned)((M + 255) / 256), 256, 0, f->stream>>>(X, Y, GRa, GRc, Rtb, Rtd, G);
+            else if (kind == 1) k_c4_fill<<<(unsigned)((M + 255) / 256), 256, 0, f->stream>>>(X, Y, GRa, Rtb, GRc, Rtd, G);
+            else k_c4_fill<<<(unsigned)((M + 255) / 256), 256, 0, f->stream>>>(X, Y, Rtb, GRc, GRa, Rtd, G);
+            SQ_LAUNCH_CHECK();
+            greens_fftnd(g, &X, &T, ax, false);
+            greens_fftnd(g, &Y, &T, ax, true);
+            k_cmul_acc<<<f->num_sms * 4, 256, 0, f->stream>>>(C, X, Y, M);
+            SQ_LAUNCH_CHECK();
+            f->launches += 2;
+        }
+    greens_fftnd(g, &C, &T, ax, true);
+    const double npairs = 0.5 * (double)g->Nrv * (double)(g->Nrv - 1);
+    const size_t nout = (size_t)(Lt + 1) * G.Nc;
+    k_c4_finish<<<(unsigned)((nout + 255) / 256), 256, 0, f->stream>>>(X, C, Lt, G.Nc, 1.0 / (std::sqrt((double)M) * npairs));
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+    std::vector<double2> out(nout);
+    SQ_CUDA(cudaMemcpyAsync(out.data(), X, nout * sizeof(double2), cudaMemcpyDeviceToHost, f->stream));
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
+    // ---- delta-function terms
+    auto cell_index = [&](const int *v) {                         // 0-based cell of the displacement v (mod L)
+        size_t cidx = 0, mul = 1;
+        for (int k = 0; k < ndim; k++) { int q = ((v[k] % G.d[k]) + G.d[k]) % G.d[k]; cidx += (size_t)q * mul; mul *= G.d[k]; }
+        return cidx;
+    };
+    auto add = [&](int tau, const int *v, double re, double im) {
+        double2 &o = out[(size_t)tau + (size_t)(Lt + 1) * cell_index(v)];
+        o.x += re; o.y += im;
+    };
+    int sh[3] = {0, 0, 0}, at[3] = {0, 0, 0};
+    double re, im;
+    if (kind == 0) {
+        if (a == b) {                                              // :305-337   -δ(a,b) δ(r, r2-r1) GR(i-r1+r2+r3-r4, c) R(i, d) at τ = β
+            for (int k = 0; k < ndim; k++) { sh[k] = -(R[0][k] - R[1][k] - R[2][k] + R[3][k]); at[k] = -R[0][k] + R[1][k]; }
+            c4_mean_GR_Rt(g, G, c, sh, d, &re, &im);
+            add(Lt, at, -re, -im);
+        }
+        if (c == d) {                                              // :339-366
+            for (int k = 0; k < ndim; k++) { sh[k] = -(-R[0][k] + R[1][k] + R[2][k] - R[3][k]); at[k] = -R[2][k] + R[3][k]; }
+            c4_mean_GR_Rt(g, G, a, sh, b, &re, &im);
+            add(Lt, at, -re, -im);
+        }
+        bool same = (a == b) && (c == d);
+        for (int k = 0; k < ndim && same; k++) same = (((R[1][k] - R[0][k]) % G.d[k] + G.d[k]) % G.d[k]) == (((R[3][k] - R[2][k]) % G.d[k] + G.d[k]) % G.d[k]);
+        if (same) {                                                // :368-385
+            for (int k = 0; k < ndim; k++) at[k] = R[1][k] - R[0][k];
+            add(Lt, at, 1.0, 0.0);
+        }
+    } else if (kind == 2) {
+        if (a == b) {                                              // :546-573   at τ = 0, displacement r1 - r2
+            for (int k = 0; k < ndim; k++) { sh[k] = -(-R[0][k] + R[1][k] - R[2][k] + R[3][k]); at[k] = R[0][k] - R[1][k]; }
+            c4_mean_GR_Rt(g, G, c, sh, d, &re, &im);
+            add(0, at, -re, -im);
+        }
+        if (c == d) {                                              // :575-602   at τ = β, displacement r4 - r3
+            for (int k = 0; k < ndim; k++) { sh[k] = -(-R[0][k] + R[1][k] - R[2][k] + R[3][k]); at[k] = R[3][k] - R[2][k]; }
+            c4_mean_GR_Rt(g, G, a, sh, b, &re, &im);
+            add(Lt, at, -re, -im);
+        }
+    }
+    memcpy(h_out, out.data(), nout * sizeof(double2));
 }

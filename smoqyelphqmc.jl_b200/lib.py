@@ -86,6 +86,8 @@ SIGNATURES = {
     "sq_greens_set_GR": [vp, vp],
     "sq_greens_measure": [vp, vp, vp, vp],
     "sq_greens_measure_GD0": [vp, i32, i32, vp, i32, i32, vp],
+    "sq_greens_measure_contraction": [vp, i32, i32, i32, vp, vp, vp, vp],
+    "sq_greens_measure_n_orbital": [vp, i32, i32, vp],
 }
 SPECIAL = {"sq_last_error": (C.c_char_p, []), "sq_version": (i32, []), "sq_fdm_launch_count": (i64, [vp])}
 

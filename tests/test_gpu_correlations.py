@@ -102,3 +102,99 @@ def test_GD0_of_free_fermions_is_the_exact_greens_function():
             assert abs(G[d[0], d[1], l] - averaged(Gl, *d)) < err, (l, d, G[d[0], d[1], l], averaged(Gl, *d))
     assert abs(G[0, 0, m.Ltau] - (1.0 - averaged(G0, 0, 0))) < err
     assert abs(G[1, 0, m.Ltau] + averaged(G0, 1, 0)) < err
+
+
+# ---- four-point contractions (src/Measurements/GreensEstimator.jl:236-652) -----------------------------------------------
+def _fields(R, GR, Ltau, norb, dims):
+    Nrv = R.shape[1]
+    shape = (Ltau, norb) + tuple(dims) + (Nrv,)
+    return np.conj(R).reshape(shape, order="F"), GR.reshape(shape, order="F")
+
+
+def _shift(x, r):
+    """ShiftedArrays.circshift(x, (0, (-r)...)): result[tau, i] = x[tau, i + r]."""
+    return np.roll(x, shift=[-int(q) for q in r], axis=tuple(range(1, 1 + len(r))))
+
+
+def _tavg(S, A, B, Ltau):
+    """_translational_average! (:674-705) on the periodic Ltau x L... torus."""
+    c = np.fft.ifftn(np.fft.fftn(A) * np.fft.ifftn(B))
+    S[:Ltau] += c[:Ltau]
+    S[Ltau] += c[0]
+
+
+def ref_contraction(kind, R, GR, Ltau, norb, dims, orbitals, r):
+    Rt, G = _fields(R, GR, Ltau, norb, dims)
+    Nrv, D = R.shape[1], len(dims)
+    a, b, c, d = orbitals
+    r1, r2, r3, r4 = (np.asarray(q) for q in r)
+    S = np.zeros((Ltau + 1,) + tuple(dims), complex)
+    for n in range(Nrv - 1):
+        for m in range(n + 1, Nrv):
+            GRa, Rtb = _shift(G[:, a, ..., n], r1), _shift(Rt[:, b, ..., n], r2)
+            GRc, Rtd = _shift(G[:, c, ..., m], r3), _shift(Rt[:, d, ..., m], r4)
+            if kind == "GD0_GD0":
+                _tavg(S, GRa * GRc, Rtb * Rtd, Ltau)
+            elif kind == "GDD_G00":
+                _tavg(S, GRa * Rtb, GRc * Rtd, Ltau)
+            else:
+                _tavg(S, Rtb * GRc, GRa * Rtd, Ltau)
+    S /= Nrv * (Nrv - 1) / 2
+
+    def mean_shifted(orb_g, shift, orb_r):
+        """sum over rv of sum(circshift(GR, (0, shift...)) .* Rt) / (Nrv * length): circshift by +s: result[i] = GR[i - s]."""
+        tot = 0.0
+        for n in range(Nrv):
+            g = np.roll(G[:, orb_g, ..., n], shift=[int(q) for q in shift], axis=tuple(range(1, 1 + D)))
+            tot += np.sum(g * Rt[:, orb_r, ..., n]) / g.size
+        return tot / Nrv
+
+    def at(v):
+        return tuple(int(q) % L for q, L in zip(v, dims))
+
+    if kind == "GD0_GD0":
+        if a == b:
+            S[(Ltau,) + at(-r1 + r2)] -= mean_shifted(c, r1 - r2 - r3 + r4, d)
+        if c == d:
+            S[(Ltau,) + at(-r3 + r4)] -= mean_shifted(a, -r1 + r2 + r3 - r4, b)
+        if a == b and c == d and at(r2 - r1) == at(r4 - r3):
+            S[(Ltau,) + at(r2 - r1)] += 1
+    elif kind == "G0D_GD0":
+        if a == b:
+            S[(0,) + at(r1 - r2)] -= mean_shifted(c, -r1 + r2 - r3 + r4, d)
+        if c == d:
+            S[(Ltau,) + at(r4 - r3)] -= mean_shifted(a, -r1 + r2 - r3 + r4, b)
+    return np.moveaxis(S, 0, -1)
+
+
+@pytest.mark.parametrize("name", ["honeycomb", "square"])
+def test_four_point_contractions_and_density_correlation(name):
+    from smoqyelph_b200 import api
+    m = {"honeycomb": lambda: mdl.holstein_honeycomb(3, 0.6, mu=0.2), "square": lambda: mdl.holstein_square(16, 16, 0.3)}[name]()
+    rng = np.random.default_rng(8)
+    V, t = dr.build_Vt(m, m.random_fields(rng, smooth=True))
+    fdm = api.SymFermionDetMatrix(m, tol=1e-12, maxiter=20000)
+    fdm.update(V, t)
+    g = api.GreensEstimator(fdm, Nrv=4, seed=5)
+    g.update_greens_estimator(tol=1e-12)
+    R, GR = g.get()
+    dims = tuple(m.lattice_dims)
+    norb = m.N // int(np.prod(dims))
+    zero = [(0,) * len(dims)] * 4
+    shifted = [(1, 0), (0, 2), (2, 1), (0, 0)]
+    cases = [((0, 0, 0, 0), zero), ((norb - 1, 0, 0, norb - 1), zero), ((0, 0, norb - 1, norb - 1), shifted), ((0, norb - 1, norb - 1, 0), shifted)]
+    for kind in ("GD0_GD0", "GDD_G00", "G0D_GD0"):
+        for orbs, r in cases:
+            got = g.measure_contraction(kind, orbs, r)
+            want = ref_contraction(kind, R, GR, m.Ltau, norb, dims, orbs, r)
+            assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max()), (name, kind, orbs, r, np.abs(got - want).max())
+    # density correlation (src/Measurements/Correlations/density.jl:2-33) assembled from the contractions
+    Rt, G = _fields(R, GR, m.Ltau, norb, dims)
+    for a, b in ((0, 0), (0, norb - 1)):
+        na = 1 - np.sum(G[:, a] * Rt[:, a]) / G[:, a].size
+        nb = 1 - np.sum(G[:, b] * Rt[:, b]) / G[:, b].size
+        assert abs(g.measure_n_orbital(a) - na) < 1e-13
+        want = 4 * (na + nb - 1) + 4 * ref_contraction("GDD_G00", R, GR, m.Ltau, norb, dims, (a, a, b, b), zero) \
+            - 2 * ref_contraction("G0D_GD0", R, GR, m.Ltau, norb, dims, (b, a, a, b), zero)
+        got = g.measure_density_correlation(a, b)
+        assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
