@@ -226,7 +226,7 @@ int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, 
         attr = true;
     }
     int grid = (N + SB - 1) / SB;
-    if (grid > SQ_MAXPART) throw SqError("lattice too large for the FFT partial-sum buffer");
+    if (dot_with && grid > SQ_MAXPART) throw SqError("lattice too large for the FFT partial-sum buffer");
     int threads = 256;
     if (L * SB >= 2048) threads = 512;
     if (const char *e = getenv("SQ_FFT_SB")) { int v = atoi(e); if (v >= 1 && (size_t)(2 * v + 1) * L * sizeof(double2) <= smem_limit) { SB = v; smem = (size_t)(2 * SB + 1) * L * sizeof(double2); grid = (N + SB - 1) / SB; } }
