@@ -97,3 +97,22 @@ def test_observables_agree_within_error_bars():
     # sanity: away from half filling, attractive (Holstein) interaction => double occupancy above the uncorrelated value n^2
     n, d = report["n"][0], report["d"][0]
     assert abs(n - 0.5) > 0.02 and d > n * n
+
+
+def test_tutorial_loop_runs_end_to_end():
+    """The reference's own tests are `isnothing(run_simulation(...))` smoke runs of the tutorials: the same loop --
+    reflection, swap, HMC, estimator solves, scalar and correlation measurements -- on the library, with sanity bounds."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "holstein_honeycomb.py")
+    spec = importlib.util.spec_from_file_location("holstein_honeycomb_example", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    m, obs, meta = mod.run_simulation(L=3, beta=1.0, N_therm=4, N_measurements=4, Nt=4, Nrv=4, tol=1e-8)
+    assert 0.5 < obs["density"] < 1.5                      # half filling up to noise (mu = 0, particle-hole symmetric coupling)
+    assert 0.0 < obs["double_occ"] < 1.0
+    assert meta["hmc_acceptance_rate"] > 0.25 and meta["hmc_iters"] > 0 and meta["measurement_iters"] > 0
+    G = obs["greens"]
+    assert G.shape == tuple(m.lattice_dims) + (m.Ltau + 1,)
+    assert abs(G[0, 0, 0].real + G[0, 0, m.Ltau].real - 1.0) < 1e-10      # G(0, beta) = 1 - G(0, 0)
+    assert np.all(np.isfinite(obs["density_corr"])) and np.all(np.isfinite(obs["pair_corr"])) and np.all(np.isfinite(obs["spin_z_corr"]))
