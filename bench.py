@@ -122,6 +122,8 @@ def algorithmic_bytes(m):
 def cpu_sample(m, x, precond, omp, budget_s, iters_per_traj):
     from oracle import oracle as orc
     rng = np.random.default_rng(7)
+    if omp:                                                  # all host cores this process may use, whatever OMP_NUM_THREADS the launcher exported
+        orc.lib(True).ref_set_num_threads(len(os.sched_getaffinity(0)))
     f = orc.RefFDM(m, sym=True, tol=TOL_FORCE, maxiter=MAXITER, omp=omp)
     e = orc.RefElPh(m, omp=omp)
     e.set_x(x)

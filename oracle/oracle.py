@@ -43,6 +43,7 @@ def lib(omp=False):
     L = C.CDLL(os.path.join(_HERE, "_build", "libref_c_omp.so" if omp else "libref_c.so"))
     sig = {
         "ref_num_threads": (C.c_int, []),
+        "ref_set_num_threads": (None, [C.c_int]),
         "ref_fdm_create": (c_vp, [C.c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_dbl, c_i64]),
         "ref_fdm_destroy": (None, [c_vp]),
         "ref_fdm_update": (None, [c_vp, c_vp, c_vp, c_dbl]),

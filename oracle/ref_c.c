@@ -56,6 +56,15 @@ static inline void tau_range(i64 L, i64 *lo, i64 *hi) {
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the timed CPU arm asks for the cores it may use explicitly */
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int ref_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
