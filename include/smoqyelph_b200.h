@@ -196,6 +196,14 @@ int sq_greens_measure_GD0(sq_greens *g, int norb, int ndim, const int64_t *dims,
  * the caller multiplies by `coef` and adds it to `correlation` (add_contraction_to_correlation!, :718-729). */
 int sq_greens_measure_contraction(sq_greens *g, int kind, int norb, int ndim, const int64_t *dims, const int *orbitals, const int64_t *r,
                                   sq_complex *out);
+/* Building blocks of the local measurements (src/Measurements/tight_binding_measurements.jl:43-133,
+ * electron_phonon_measurements.jl: measure_holstein_energy, measure_ssh_energy):
+ *   weighted_density: sum_{i,l} w[i,l] n(l,i),  n(l,i) = mean_rv (1 - GR[l,i,rv] Rt[l,i,rv]);  w (N x Ltau) real, site fastest
+ *   weighted_bonds:   sum_{m,l} w[m,l] h(l; i_m->f_m) + conj(w[m,l]) h(l; f_m->i_m),  h(l; i->f) = mean_rv GR[l,i,rv] Rt[l,f,rv];
+ *                     bonds 2 x nbonds 1-based sites, w (nbonds x Ltau) complex, bond fastest
+ * The normalisation (1/N, 1/Ltau, ...) is part of the weights. */
+int sq_greens_weighted_density(sq_greens *g, const double *w, sq_complex *out);
+int sq_greens_weighted_bonds(sq_greens *g, int64_t nbonds, const int64_t *bonds, const sq_complex *w, sq_complex *out);
 /* measure_n(greens_estimator, orbital)  src/Measurements/scalar_measurements.jl:2-12 */
 int sq_greens_measure_n_orbital(sq_greens *g, int norb, int a, sq_complex *n);
 /* update_chemical_potential! minus the MuTuner scalar logic (stays in Julia): returns n, N^2 then

@@ -485,6 +485,59 @@ class GreensEstimator:
         """measure_spin_correlation!(SzSz, greens_estimator, a, b, coef)  (src/Measurements/Correlations/spin.jl:2-15)."""
         return -0.5 * coef * self.measure_contraction("G0D_GD0", (b, a, a, b), norb=norb, dims=dims)
 
+    # ---- local measurements (tight_binding_measurements.jl, electron_phonon_measurements.jl) ----
+    def weighted_density(self, w):
+        """sum_{i,l} w[i,l] n(l,i) with n(l,i) = mean_rv (1 - GR Rt); w: (N, Ltau) real."""
+        m = self.fdm.model
+        w = np.asfortranarray(w, np.float64)
+        assert w.shape == (m.N, m.Ltau)
+        out = np.zeros(2)
+        check(self.L.sq_greens_weighted_density(self.h, ptr(w), ptr(out)))
+        return complex(out[0], out[1])
+
+    def weighted_bonds(self, bonds, w):
+        """sum_{m,l} w[m,l] <GR[l,i_m] Rt[l,f_m]> + conj(w[m,l]) <GR[l,f_m] Rt[l,i_m]>; bonds (2, nb) 0-based, w (nb, Ltau) complex."""
+        m = self.fdm.model
+        bonds = np.asarray(bonds)
+        w = np.asfortranarray(w, np.complex128)
+        assert bonds.shape[0] == 2 and w.shape == (bonds.shape[1], m.Ltau)
+        out = np.zeros(2)
+        check(self.L.sq_greens_weighted_bonds(self.h, bonds.shape[1], ptr(_i64(bonds.T)), ptr(w), ptr(out)))
+        return complex(out[0], out[1])
+
+    def measure_onsite_energy(self, orbital, eps, mu, norb=None, dims=None):
+        """measure_onsite_energy (tight_binding_measurements.jl:43-63): eps (N,) on-site energies."""
+        m = self.fdm.model
+        norb, dims = self._geom(norb, dims)
+        w = np.zeros((m.N, m.Ltau))
+        sel = np.arange(m.N) % norb == orbital
+        w[sel, :] = ((np.asarray(eps, float)[sel] - mu) / (m.Ltau * (m.N // norb)))[:, None]
+        return self.weighted_density(w)
+
+    def measure_hopping_energy(self, bonds, t):
+        """measure_bare_hopping_energy / measure_hopping_energy (tight_binding_measurements.jl:66-133): bonds (2, nb) of one hopping
+        id, t (nb,) bare or (nb, Ltau) modulated amplitudes."""
+        m = self.fdm.model
+        t = np.asarray(t, np.complex128)
+        w = np.broadcast_to(t[:, None] if t.ndim == 1 else t, (np.asarray(bonds).shape[1], m.Ltau)) / (m.Ltau * m.N)
+        return self.weighted_bonds(bonds, w)
+
+    def measure_holstein_energy(self, x, holstein_id=0):
+        """measure_holstein_energy (electron_phonon_measurements.jl): couplings of one Holstein id (one per unit cell)."""
+        m = self.fdm.model
+        nc = m.n_unit_cells
+        sl = slice(holstein_id * nc, (holstein_id + 1) * nc)
+        site, ph = m.hol_site[sl], m.hol_phonon[sl]
+        a1, a2, a3, a4 = (m.hol_alpha[k][sl][:, None] for k in range(4))
+        xs = np.asarray(x)[ph, :]
+        even, odd = a2 * xs ** 2 + a4 * xs ** 4, a1 * xs + a3 * xs ** 2          # the reference uses x^2 with alpha3 (:127-128)
+        w = np.zeros((m.N, m.Ltau))
+        w[site, :] = (even + odd) / (nc * m.Ltau)
+        e = self.weighted_density(w)
+        if m.hol_phsym[sl][0]:
+            e -= 0.5 * np.sum(odd) / (nc * m.Ltau)
+        return e
+
     def measure(self):
         out = np.zeros((3, 2))
         check(self.L.sq_greens_measure(self.h, ptr(out[0]), ptr(out[1]), ptr(out[2])))

@@ -57,6 +57,8 @@ double greens_update_impl(sq_greens *g, sq_kpm *kpm, const void *h_R, double tol
 void greens_measure_impl(sq_greens *g, double *out);
 void greens_measure_c4_impl(sq_greens *g, int kind, int norb, int ndim, const i64 *dims, const int *orb, const i64 *r, void *h_out);
 void greens_measure_n_orbital_impl(sq_greens *g, int norb, int a, double *out);
+void greens_weighted_density_impl(sq_greens *g, const double *h_w, double *out);
+void greens_weighted_bonds_impl(sq_greens *g, i64 nbonds, const i64 *bonds, const void *h_w, double *out);
 void greens_measure_GD0_impl(sq_greens *g, int norb, int ndim, const i64 *dims, int a, int b, void *h_out);
 
 extern "C" {
@@ -687,6 +689,18 @@ int sq_greens_measure_n_orbital(sq_greens *g, int norb, int a, sq_complex *n) {
     SQ_TRY
     SQ_REQUIRE(g && n, "NULL argument");
     greens_measure_n_orbital_impl(g, norb, a, (double *)n);
+    SQ_CATCH
+}
+int sq_greens_weighted_density(sq_greens *g, const double *w, sq_complex *out) {
+    SQ_TRY
+    SQ_REQUIRE(g && w && out, "NULL argument");
+    greens_weighted_density_impl(g, w, (double *)out);
+    SQ_CATCH
+}
+int sq_greens_weighted_bonds(sq_greens *g, int64_t nbonds, const int64_t *bonds, const sq_complex *w, sq_complex *out) {
+    SQ_TRY
+    SQ_REQUIRE(g && out, "NULL argument");
+    greens_weighted_bonds_impl(g, nbonds, bonds, w, (double *)out);
     SQ_CATCH
 }
 int sq_greens_measure(sq_greens *g, sq_complex *n, sq_complex *double_occ, sq_complex *Nsqrd) {

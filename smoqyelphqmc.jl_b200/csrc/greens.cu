@@ -468,3 +468,100 @@ void greens_measure_c4_impl(sq_greens *g, int kind, int norb, int ndim, const i6
     }
     memcpy(h_out, out.data(), nout * sizeof(double2));
 }
+
+
+// ---------------------------------------------------------------------------------------------------
+// Local measurements: every estimator in tight_binding_measurements.jl / electron_phonon_measurements.jl is a weighted sum of
+//   n(l, i)       = mean_rv (1 - GR[l,i,rv] Rt[l,i,rv])                         (measure_onsite_energy :43-63, measure_holstein_energy)
+//   h(l; i -> f)  = mean_rv GR[l,i,rv] Rt[l,f,rv]                                (measure_bare_hopping_energy :66-98,
+//                                                                                 measure_hopping_energy :101-133, measure_ssh_energy)
+// over space-time.  The weights come from the host (they are model data: on-site energies, couplings times powers of x, hoppings).
+// ---------------------------------------------------------------------------------------------------
+// sum_{l,i} w[l][i] n(l, i); w in the device layout [l][i]
+__global__ void k_weighted_density(double *__restrict__ part, const double2 *__restrict__ R, const double2 *__restrict__ GR, const double *__restrict__ w,
+                                   size_t V, int Nrv) {
+    __shared__ double red[2 * 32];
+    double v[2] = {0, 0};
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < V; k += (size_t)gridDim.x * blockDim.x) {
+        double sr = 0, si = 0;
+        for (int n = 0; n < Nrv; n++) {
+            const double2 r = R[(size_t)n * V + k], g = GR[(size_t)n * V + k];
+            sr += 1.0 - (g.x * r.x + g.y * r.y);                 // 1 - g conj(r)
+            si += -(g.y * r.x - g.x * r.y);
+        }
+        v[0] += w[k] * sr / Nrv;
+        v[1] += w[k] * si / Nrv;
+    }
+    block_sum<2>(v, red);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = v[0]; part[2 * blockIdx.x + 1] = v[1]; }
+}
+// sum_{m,l} [ w[l][m] h(l; i_m -> f_m) + conj(w[l][m]) h(l; f_m -> i_m) ]; w complex in the layout [l][m]
+__global__ void k_weighted_bonds(double *__restrict__ part, const double2 *__restrict__ R, const double2 *__restrict__ GR, const int2 *__restrict__ bonds,
+                                 const double2 *__restrict__ w, int L, int N, int nb, int Nrv) {
+    __shared__ double red[2 * 32];
+    double v[2] = {0, 0};
+    const size_t V = (size_t)L * N, tot = (size_t)L * nb;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < tot; k += (size_t)gridDim.x * blockDim.x) {
+        const int l = (int)(k / nb), m = (int)(k % nb);
+        const int2 b = bonds[m];
+        double2 hf = make_double2(0, 0), hr = make_double2(0, 0);
+        for (int n = 0; n < Nrv; n++) {
+            const double2 gi = GR[(size_t)n * V + (size_t)l * N + b.x], gf = GR[(size_t)n * V + (size_t)l * N + b.y];
+            double2 ri = R[(size_t)n * V + (size_t)l * N + b.x], rf = R[(size_t)n * V + (size_t)l * N + b.y];
+            ri.y = -ri.y; rf.y = -rf.y;                             // Rt = conj(R)
+            hf = cadd(hf, cmul(gi, rf));
+            hr = cadd(hr, cmul(gf, ri));
+        }
+        const double2 wk = w[k];
+        const double2 t = cadd(cmul(wk, hf), cmul(make_double2(wk.x, -wk.y), hr));
+        v[0] += t.x / Nrv;
+        v[1] += t.y / Nrv;
+    }
+    block_sum<2>(v, red);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = v[0]; part[2 * blockIdx.x + 1] = v[1]; }
+}
+
+static void greens_reduce_part(sq_greens *g, int nb, double *out) {
+    sq_fdm *f = g->f;
+    std::vector<double> h(2 * nb);
+    SQ_CUDA(cudaMemcpyAsync(h.data(), g->part.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
+    out[0] = out[1] = 0.0;
+    for (int k = 0; k < nb; k++) { out[0] += h[2 * k]; out[1] += h[2 * k + 1]; }
+}
+
+// h_w: (N x Ltau) real weights, site fastest (the layout of fermion_path_integral.V).  out = sum_{i,l} w[i,l] n(l,i)
+void greens_weighted_density_impl(sq_greens *g, const double *h_w, double *out) {
+    sq_fdm *f = g->f;
+    SQ_CUDA(cudaSetDevice(f->device));
+    const size_t V = (size_t)f->L * f->N;
+    if (g->wreal.n < V) g->wreal.alloc(V, false);
+    g->wreal.upload(h_w, V, f->stream);
+    const int nb = 128;
+    k_weighted_density<<<nb, 256, 0, f->stream>>>(g->part.p, g->R.p, g->GR.p, g->wreal.p, V, (int)g->Nrv);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+    greens_reduce_part(g, nb, out);
+}
+// bonds: nb pairs of 1-based sites (initial, final); h_w: (nb x Ltau) complex weights, bond fastest
+void greens_weighted_bonds_impl(sq_greens *g, i64 nbonds, const i64 *bonds, const void *h_w, double *out) {
+    sq_fdm *f = g->f;
+    SQ_CUDA(cudaSetDevice(f->device));
+    SQ_REQUIRE(nbonds >= 1 && bonds && h_w, "bad argument");
+    std::vector<int2> hb(nbonds);
+    for (i64 m = 0; m < nbonds; m++) {
+        const i64 i = bonds[2 * m] - 1, j = bonds[2 * m + 1] - 1;
+        SQ_REQUIRE(i >= 0 && i < f->N && j >= 0 && j < f->N, "bond site out of range");
+        hb[m] = make_int2((int)i, (int)j);
+    }
+    const size_t nw = (size_t)f->L * nbonds;
+    if (g->wcplx.n < nw) g->wcplx.alloc(nw, false);
+    if (g->wbond.n < (size_t)nbonds) g->wbond.alloc(nbonds, false);
+    g->wcplx.upload((const double2 *)h_w, nw, f->stream);
+    g->wbond.upload(hb.data(), nbonds, f->stream);
+    const int nb = 128;
+    k_weighted_bonds<<<nb, 256, 0, f->stream>>>(g->part.p, g->R.p, g->GR.p, g->wbond.p, g->wcplx.p, (int)f->L, (int)f->N, (int)nbonds, (int)g->Nrv);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+    greens_reduce_part(g, nb, out);
+}

@@ -184,6 +184,9 @@ struct sq_greens {
     uint64_t seed = 0, counter = 0;
     DevBuf<double2> R, GR, MtR;              // Nrv vectors, [l][i] each
     DevBuf<double2> wa, wb, wc, wt;          // work arrays of the correlation measurements (2 Ltau x cells)
+    DevBuf<double> wreal;                    // weights of the local measurements
+    DevBuf<double2> wcplx;
+    DevBuf<int2> wbond;
     std::map<int, std::unique_ptr<DevBuf<double2>>> fft_tw;   // twiddles per transform length
     DevBuf<double> part;
 };

@@ -88,6 +88,8 @@ SIGNATURES = {
     "sq_greens_measure_GD0": [vp, i32, i32, vp, i32, i32, vp],
     "sq_greens_measure_contraction": [vp, i32, i32, i32, vp, vp, vp, vp],
     "sq_greens_measure_n_orbital": [vp, i32, i32, vp],
+    "sq_greens_weighted_density": [vp, vp, vp],
+    "sq_greens_weighted_bonds": [vp, i64, vp, vp, vp],
 }
 SPECIAL = {"sq_last_error": (C.c_char_p, []), "sq_version": (i32, []), "sq_fdm_launch_count": (i64, [vp])}
 

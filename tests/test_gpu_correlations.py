@@ -198,3 +198,55 @@ def test_four_point_contractions_and_density_correlation(name):
             - 2 * ref_contraction("G0D_GD0", R, GR, m.Ltau, norb, dims, (b, a, a, b), zero)
         got = g.measure_density_correlation(a, b)
         assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+
+
+# ---- local measurements (tight_binding_measurements.jl:43-133, electron_phonon_measurements.jl) ---------------------------
+@pytest.mark.parametrize("name", ["honeycomb", "bssh"])
+def test_local_measurements(name):
+    from smoqyelph_b200 import api
+    m = {"honeycomb": lambda: mdl.holstein_honeycomb(3, 0.6, mu=0.2), "bssh": lambda: mdl.bssh_square(4, 4, 0.5)}[name]()
+    rng = np.random.default_rng(12)
+    x = m.random_fields(rng, smooth=True)
+    V, t = dr.build_Vt(m, x)
+    fdm = api.SymFermionDetMatrix(m, tol=1e-12, maxiter=20000)
+    fdm.update(V, t)
+    g = api.GreensEstimator(fdm, Nrv=5, seed=2)
+    g.update_greens_estimator(tol=1e-12)
+    R, GR = g.get()
+    Nrv, Lt, N = R.shape[1], m.Ltau, m.N
+    Rt = np.conj(R).reshape((Lt, N, Nrv), order="F")
+    G = GR.reshape((Lt, N, Nrv), order="F")
+    dims = tuple(m.lattice_dims)
+    norb = N // int(np.prod(dims))
+    ncell = N // norb
+    # on-site energy, literal restatement of :43-63
+    eps, mu = rng.standard_normal(N), 0.3
+    for orb in range(norb):
+        e = 0.0
+        for u in range(ncell):
+            i = orb + norb * u
+            e += (eps[i] - mu) * np.sum(1 - G[:, i, :] * Rt[:, i, :]) / (Lt * Nrv)
+        e /= ncell
+        assert abs(g.measure_onsite_energy(orb, eps, mu) - e) < 1e-12 * max(1.0, abs(e))
+    # bare and modulated hopping energy of the first hopping id (:66-133)
+    nt = m.neighbor_table[:, :ncell]
+    for tt in (m.t0[:ncell] * (1 + 0.1j), t[:ncell, :].astype(complex)):
+        h = 0.0
+        for mm in range(ncell):
+            i, f = nt[0, mm], nt[1, mm]
+            tl = np.broadcast_to(tt[mm], (Lt,))
+            h += np.sum(tl[:, None] * G[:, i, :] * Rt[:, f, :] + np.conj(tl)[:, None] * G[:, f, :] * Rt[:, i, :])
+        h /= Lt * N * Nrv
+        assert abs(g.measure_hopping_energy(nt, tt) - h) < 1e-12 * max(1.0, abs(h))
+    if m.Nhol:                                                       # Holstein energy (electron_phonon_measurements.jl)
+        want = 0.0
+        for c in range(ncell):
+            i, p = m.hol_site[c], m.hol_phonon[c]
+            a1, a2, a3, a4 = m.hol_alpha[:, c]
+            for l in range(Lt):
+                n_li = np.sum(1 - G[l, i, :] * Rt[l, i, :]) / Nrv
+                xv = x[p, l]
+                want += (a2 * xv ** 2 + a4 * xv ** 4) * n_li
+                want += (a1 * xv + a3 * xv ** 2) * (n_li - 0.5 if m.hol_phsym[c] else n_li)
+        want /= ncell * Lt
+        assert abs(g.measure_holstein_energy(x, 0) - want) < 1e-12 * max(1.0, abs(want))
