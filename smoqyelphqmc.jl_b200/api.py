@@ -481,6 +481,20 @@ class GreensEstimator:
         z = (0,) * len(tuple(r1))
         return coef * self.measure_contraction("GD0_GD0", (a, c, b, d), (tuple(r1), tuple(r2), z, z), norb=norb, dims=dims)
 
+    def measure_bond_correlation(self, bond1, bond2, coef=1.0, norb=None, dims=None):
+        """measure_bond_correlation!(BB, greens_estimator, b', b'', coef)  (src/Measurements/Correlations/bond.jl:2-48): four
+        G(Δ,Δ)G(0,0) and four G(0,Δ)G(Δ,0) contractions.  A bond is ((orbital_1, orbital_2), displacement)."""
+        (b, a), r1 = bond1
+        (d, c), r2 = bond2
+        r1, r2 = tuple(r1), tuple(r2)
+        z = (0,) * len(r1)
+        mc = lambda kind, orbs, r: self.measure_contraction(kind, orbs, r, norb=norb, dims=dims)
+        BB = 4 * coef * (mc("GDD_G00", (a, b, c, d), (r1, z, r2, z)) + mc("GDD_G00", (a, b, d, c), (r1, z, z, r2))
+                         + mc("GDD_G00", (b, a, c, d), (z, r1, r2, z)) + mc("GDD_G00", (b, a, d, c), (z, r1, z, r2)))
+        BB -= 2 * coef * (mc("G0D_GD0", (c, b, a, d), (r2, z, r1, z)) + mc("G0D_GD0", (d, b, a, c), (z, z, r1, r2))
+                          + mc("G0D_GD0", (c, a, b, d), (r2, r1, z, z)) + mc("G0D_GD0", (d, a, b, c), (z, r1, z, r2)))
+        return BB
+
     def measure_spin_correlation(self, a, b, coef=1.0, norb=None, dims=None):
         """measure_spin_correlation!(SzSz, greens_estimator, a, b, coef)  (src/Measurements/Correlations/spin.jl:2-15)."""
         return -0.5 * coef * self.measure_contraction("G0D_GD0", (b, a, a, b), norb=norb, dims=dims)

@@ -188,6 +188,19 @@ def test_four_point_contractions_and_density_correlation(name):
             got = g.measure_contraction(kind, orbs, r)
             want = ref_contraction(kind, R, GR, m.Ltau, norb, dims, orbs, r)
             assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max()), (name, kind, orbs, r, np.abs(got - want).max())
+    # bond correlation (src/Measurements/Correlations/bond.jl:2-48): 8 contractions with the bond displacements
+    b1 = ((norb - 1, 0), (1,) + (0,) * (len(dims) - 1))
+    b2 = ((0, norb - 1), (0,) * (len(dims) - 1) + (1,))
+    (bb, ba), r1 = b1
+    (bd, bc), r2 = b2
+    z = (0,) * len(dims)
+    rc = lambda kind, orbs, r: ref_contraction(kind, R, GR, m.Ltau, norb, dims, orbs, r)
+    want = 4 * (rc("GDD_G00", (ba, bb, bc, bd), (r1, z, r2, z)) + rc("GDD_G00", (ba, bb, bd, bc), (r1, z, z, r2))
+                + rc("GDD_G00", (bb, ba, bc, bd), (z, r1, r2, z)) + rc("GDD_G00", (bb, ba, bd, bc), (z, r1, z, r2))) \
+        - 2 * (rc("G0D_GD0", (bc, bb, ba, bd), (r2, z, r1, z)) + rc("G0D_GD0", (bd, bb, ba, bc), (z, z, r1, r2))
+               + rc("G0D_GD0", (bc, ba, bb, bd), (r2, r1, z, z)) + rc("G0D_GD0", (bd, ba, bb, bc), (z, r1, z, r2)))
+    got = g.measure_bond_correlation(b1, b2)
+    assert np.abs(got - want).max() < 1e-11 * max(1.0, np.abs(want).max())
     # density correlation (src/Measurements/Correlations/density.jl:2-33) assembled from the contractions
     Rt, G = _fields(R, GR, m.Ltau, norb, dims)
     for a, b in ((0, 0), (0, norb - 1)):
