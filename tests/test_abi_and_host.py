@@ -131,3 +131,22 @@ def test_world_size_2_gloo(tmp_path):
                           "--master-port", "29617", str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count("ok") == 2
+
+
+def test_global_move_sampling_helpers():
+    """Host logic of the global moves (no GPU): phonon layout helpers and the mode / pair sampling rules."""
+    import numpy as np
+    from smoqyelph_b200 import api, model as mdl
+    m = mdl.bssh_square(4, 4, 0.5)                       # 3 phonon types per cell, the third frozen (M = inf)
+    assert m.n_unit_cells == 16 and m.nphonon == 3
+    rng = np.random.default_rng(0)
+    modes = [api._sample_phonon_mode(rng, m) for _ in range(200)]
+    assert all(np.isfinite(m.Mass[p]) for p in modes) and {p // 16 for p in modes} == {0, 1}
+    assert all(api._sample_phonon_mode(rng, m, phonon_types=[1]) // 16 == 1 for _ in range(50))
+    pairs = [api._sample_phonon_mode_pair(rng, m, phonon_type_pairs=[(0, 1)]) for _ in range(50)]
+    assert all(i // 16 == 0 and j // 16 == 1 for i, j in pairs)
+    h = mdl.holstein_honeycomb(3, 1.0)
+    assert h.n_unit_cells == 9 and h.nphonon == 2
+    import pytest
+    with pytest.raises(api.SqError):
+        api._sample_phonon_mode(rng, m, phonon_types=[2])    # only frozen modes: nothing to propose
