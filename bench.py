@@ -387,11 +387,18 @@ def run_native(args):
         ids = [api.FermionDetMatrix.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         fdm.init_slab(rank, world, ids[0])
+        os.environ["SQ_NO_RESIDENT_CG"] = "1"                 # (a) host-launched NCCL loop
+        us_nccl = timed_cg()
+        del os.environ["SQ_NO_RESIDENT_CG"]
+        handles = [None] * world                              # (b) resident kernels + peer-mapped mailboxes (CUDA IPC over NVLink)
+        dist.all_gather_object(handles, fdm.mailbox_handle())
+        fdm.mailbox_open(handles)
         usN = timed_cg()
         tau_slab = {"what": "unpreconditioned CG iterations on M^T M, cfg4, tau-slab partitioned (strong scaling)",
-                    "cg_us_per_iter_1gpu": us1, "cg_us_per_iter": usN, "n_gpus": world,
+                    "cg_us_per_iter_1gpu": us1, "cg_us_per_iter": usN, "cg_us_per_iter_nccl_loop": us_nccl, "n_gpus": world,
                     "cg_iters_per_s": 1e6 / usN, "speedup_vs_1gpu": us1 / usN,
-                    "comm": "NCCL send/recv halos (2 x 16 KB) + 2 scalar all-reduces per iteration, host-launched"}
+                    "comm": "resident kernel per rank; grid-wide sums and boundary slices as device-initiated stores into peer-mapped "
+                            "mailboxes (CUDA IPC over NVLink); cg_us_per_iter_nccl_loop = host-launched NCCL send/recv + all-reduces"}
 
     if rank != 0:
         if dist is not None:

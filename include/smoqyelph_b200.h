@@ -90,6 +90,12 @@ int sq_fdm_time_mul(sq_fdm *f, int op, void *d_out, const void *d_in, int reps, 
  * the outputs are defined; unpreconditioned CG only. */
 int sq_nccl_unique_id(char *out128);
 int sq_fdm_init_slab(sq_fdm *f, int rank, int world, const char *id128);
+/* Optional, after sq_fdm_init_slab: peer-mapped mailboxes (CUDA IPC) for the resident multi-GPU CG -- the whole solve is one
+ * launch per rank, dot products and boundary slices travel as device-initiated NVLink stores instead of NCCL calls.
+ * create returns this rank's 64-byte IPC handle; the host gathers the handles of all ranks (rank-major, world x 64 bytes)
+ * and passes them to open.  Without mailboxes (or for lattices without the register path) the NCCL loop runs. */
+int sq_fdm_mailbox_create(sq_fdm *f, char *handle64);
+int sq_fdm_mailbox_open(sq_fdm *f, const char *handles64);
 int sq_fdm_set_slab_range(sq_fdm *f, int64_t lo, int64_t hi);      /* single-process testing of the range logic */
 int sq_fdm_get_slab(sq_fdm *f, int64_t *lo, int64_t *hi, int *rank, int *world);
 int64_t sq_fdm_launch_count(sq_fdm *f);

@@ -141,6 +141,17 @@ class FermionDetMatrix:
         buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
         check(self.L.sq_fdm_init_slab(self.h, int(rank), int(world), buf))
 
+    def mailbox_handle(self) -> bytes:
+        """This rank's CUDA IPC handle of the mailbox used by the resident multi-GPU CG (call after init_slab)."""
+        buf = C.create_string_buffer(64)
+        check(self.L.sq_fdm_mailbox_create(self.h, buf))
+        return buf.raw
+
+    def mailbox_open(self, handles):
+        """handles: the mailbox handles of all ranks in rank order (e.g. from torch.distributed.all_gather_object)."""
+        blob = b"".join(handles)
+        check(self.L.sq_fdm_mailbox_open(self.h, C.create_string_buffer(blob, len(blob))))
+
     def set_slab_range(self, lo, hi): check(self.L.sq_fdm_set_slab_range(self.h, int(lo), int(hi)))
 
     @property

@@ -30,6 +30,8 @@ void fdm_v3_prepare_native(sq_fdm *f);
 void slab_unique_id(char *out128);
 void slab_init(sq_fdm *f, int rank, int world, const char *id128);
 void slab_set_range(sq_fdm *f, int lo, int hi);
+void slab_mailbox_create(sq_fdm *f, char *out64);
+void slab_mailbox_open(sq_fdm *f, const char *handles64);
 
 void kpm_create_impl(sq_kpm **out, sq_fdm *f, double rbuf, i64 n, double a1, double a2);
 void elph_create_impl(sq_elph **out, sq_fdm *f, double dtau, i64 Nph, const double *Om, const double *Om4, const double *M, i64 Nhol,
@@ -114,6 +116,18 @@ int sq_fdm_init_slab(sq_fdm *f, int rank, int world, const char *id128) {
     SQ_TRY
     SQ_REQUIRE(f && (id128 || world == 1), "NULL argument");
     slab_init(f, rank, world, id128);
+    SQ_CATCH
+}
+int sq_fdm_mailbox_create(sq_fdm *f, char *out64) {
+    SQ_TRY
+    SQ_REQUIRE(f && out64, "NULL argument");
+    slab_mailbox_create(f, out64);
+    SQ_CATCH
+}
+int sq_fdm_mailbox_open(sq_fdm *f, const char *handles64) {
+    SQ_TRY
+    SQ_REQUIRE(f && handles64, "NULL argument");
+    slab_mailbox_open(f, handles64);
     SQ_CATCH
 }
 int sq_fdm_set_slab_range(sq_fdm *f, int64_t lo, int64_t hi) {

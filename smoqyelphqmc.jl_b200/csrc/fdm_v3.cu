@@ -1104,6 +1104,17 @@ struct CgResident1 {
     size_t slot_array_bytes;
     double *halo;               // [cta][side][part][N] boundary slices of z
     int maxiter;
+    // tau-slab mode over several GPUs (MULTI kernels): every rank runs this kernel on its slab; the grid-wide sums run over the
+    // CTAs of ALL ranks and the boundary z of the first / last CTA travels to the neighbour rank.  Each rank owns a mailbox
+    // (peer-mapped through CUDA IPC): slots of all global CTAs, then the check slots, then the halo inbox
+    // [parity][side: 0 from the left rank, 1 from the right rank][part][N].  Producers PUSH into the consumers' mailboxes
+    // (posted NVLink stores), consumers poll their own memory.  it_base continues the iteration count across solves so that
+    // the validity tags never repeat within a slot (no mailbox reset between solves, which would race with early peers).
+    int world, rank;
+    unsigned int gid0, gtot;    // first global CTA index of this rank, number of CTAs of all ranks
+    unsigned long long it_base;
+    char *mail[8];
+    size_t off_check, off_inbox;
 };
 
 __device__ __forceinline__ double v3_tag(double x, long long tag) { return __longlong_as_double((__double_as_longlong(x) & ~3LL) | tag); }
@@ -1145,12 +1156,87 @@ __device__ __forceinline__ void v3_slot_sum2(double (&t)[2], int half, char *slo
     t[1] = warp_sum(s[1]);
 }
 
-template <class G>
+// Multi-GPU versions: publish into every rank's mailbox (system scope), poll the own one.
+__device__ __forceinline__ void v3_slot_sum2_multi(double (&t)[2], int half, char *const *mail, int world, int rank, size_t slot_off,
+                                                   unsigned int stride_bytes, long long tag, unsigned int gtot, unsigned int gid, bool &bad) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        for (int q = 0; q < world; q++) {
+            char *dst = mail[q] + slot_off + (size_t)gid * stride_bytes + 16 * half;
+            asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(v3_tag(t[0], tag)), "d"(v3_tag(t[1], tag)) : "memory");
+        }
+    }
+    const char *slots = mail[rank] + slot_off;
+    double s[2] = {0.0, 0.0};
+    const long long t0 = clock64();
+    for (unsigned int base = 0; base < gtot; base += 256) {
+        long long val[8][2];
+        while (true) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const unsigned int q = base + lane + 32 * u;
+                val[u][0] = val[u][1] = tag;
+                if (q < gtot) asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(val[u][0]), "=l"(val[u][1]) : "l"(slots + (size_t)q * stride_bytes + 16 * half) : "memory");
+            }
+            bool ready = true;
+#pragma unroll
+            for (int u = 0; u < 8; u++) ready = ready && ((val[u][0] & 3LL) == tag) && ((val[u][1] & 3LL) == tag);
+            if (ready) break;
+            if (clock64() - t0 > 8000000000LL) { bad = true; break; }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const unsigned int q = base + lane + 32 * u;
+            if (q < gtot) { s[0] += __longlong_as_double(val[u][0]); s[1] += __longlong_as_double(val[u][1]); }
+        }
+    }
+    t[0] = warp_sum(s[0]);
+    t[1] = warp_sum(s[1]);
+}
+// exact check sum over all ranks: (value, epoch) slots at mail[.] + off
+__device__ __forceinline__ double v3_grid_sum_multi(double acc, double *red, char *const *mail, int world, int rank, size_t off,
+                                                    unsigned int stride_bytes, unsigned long long epoch, unsigned int gtot, unsigned int gid,
+                                                    bool &aborted) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    int bad = 0;
+    if (warp == 0) {
+        double t = lane < nw ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) {
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            for (int q = 0; q < world; q++)
+                asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(mail[q] + off + (size_t)gid * stride_bytes), "l"(__double_as_longlong(t)), "l"(epoch) : "memory");
+        }
+        const char *slots = mail[rank] + off;
+        double s = 0.0;
+        const long long t0 = clock64();
+        for (unsigned int q = lane; q < gtot; q += 32) {
+            long long val;
+            unsigned long long ep;
+            while (true) {
+                asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(val), "=l"(ep) : "l"(slots + (size_t)q * stride_bytes) : "memory");
+                if (ep >= epoch) break;
+                if (clock64() - t0 > 8000000000LL) { bad = 1; break; }
+            }
+            s += __longlong_as_double(val);
+        }
+        s = warp_sum(s);
+        if (lane == 0) red[32] = s;
+    }
+    aborted = __syncthreads_or(bad) != 0;
+    return red[32];
+}
+
+template <class G, int MULTI>
 __global__ void __launch_bounds__(256, 1)
 k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     constexpr int N = G::N, NP = G::NP;
     extern __shared__ double smem[];
-    __shared__ double red[4 * 8];
+    __shared__ double red[4 * 8 + 1];
     __shared__ double sh[6];
     const int S = P.S, L = P.L;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1160,6 +1246,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     const int l0 = P.lb + blockIdx.x * S;
     const int ns = min(S, P.le - l0);
     const unsigned int nblk = gridDim.x, bid = blockIdx.x;
+    const unsigned int gtot = MULTI ? C.gtot : nblk, gid = MULTI ? C.gid0 + bid : bid;
     const bool active = k <= ns, owner = active && k >= 1, publish = k < ns;
     int lself = l0 + k;
     lself = lself >= L ? lself - L : lself;
@@ -1176,6 +1263,9 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     // boundary z: [parity of the iteration][cta][side][part][N]; side 0 = first own slice, 1 = last own slice
     auto hslice = [&](int par, unsigned int cta, int side) -> double2 * { return reinterpret_cast<double2 *>(C.halo + ((((size_t)par * nblk + cta) * 2 + side) * 2 + part) * N); };
     const unsigned int left = (bid + nblk - 1) % nblk, right = (bid + 1) % nblk;
+    // MULTI: halo inbox of rank q, [parity][side][part][N] doubles
+    auto inbox = [&](int q, int par, int side) -> double2 * { return reinterpret_cast<double2 *>(C.mail[q] + C.off_inbox) + ((size_t)(par * 2 + side) * 2 + part) * (N / 2); };
+    const int rank_l = MULTI ? (C.rank + C.world - 1) % C.world : 0, rank_r = MULTI ? (C.rank + 1) % C.world : 0;
     const double normb = C.state->normb, tol = C.state->tol;
     double eps = C.state->eps;
     int it = 0, done = 0;
@@ -1209,6 +1299,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
 #pragma unroll 1
     while (it < C.maxiter) {
         it++;
+        const unsigned long long itg = MULTI ? C.it_base + (unsigned long long)it : (unsigned long long)it;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         if (active) {
 #pragma unroll
@@ -1233,7 +1324,11 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
         if (owner) E.template apply_B_ev<1, 1>(v, evk);
         __syncthreads();                                  // w of all slices is in W
         if (owner) {                                      // z[lo] in registers; r.z, |z|^2, |r|^2; boundary z for the neighbours
-            double2 *h0 = (k == 1) ? hslice(it & 1, bid, 0) : nullptr, *h1 = (k == ns) ? hslice(it & 1, bid, 1) : nullptr;
+            double2 *h0 = (k == 1) ? hslice((int)(itg & 1), bid, 0) : nullptr, *h1 = (k == ns) ? hslice((int)(itg & 1), bid, 1) : nullptr;
+            if (MULTI) {                                  // the slab's outer boundaries go to the neighbour ranks' inboxes
+                if (k == 1 && bid == 0) h0 = inbox(rank_l, (int)(itg & 1), 1);            // I am their right neighbour
+                if (k == ns && bid == nblk - 1) h1 = inbox(rank_r, (int)(itg & 1), 0);    // I am their left neighbour
+            }
 #pragma unroll
             for (int u = 0; u < NP; u++) {
                     const double2 w = W[(size_t)(k - 1) * (N / 2) + el(u)];
@@ -1260,7 +1355,8 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
 #pragma unroll
             for (int c = 0; c < 2; c++) { t[c] = 0.0; for (int w = 0; w < nw; w++) t[c] += red[(2 * wid + c) * 8 + w]; }
             bool bad = false;
-            v3_slot_sum2(t, wid, C.slots + (size_t)(it & 1) * C.slot_array_bytes, C.slot_stride, (long long)(it & 3), nblk, bid, bad);
+            if (MULTI) v3_slot_sum2_multi(t, wid, C.mail, C.world, C.rank, (size_t)(itg & 1) * C.slot_array_bytes, C.slot_stride, (long long)(itg & 3), gtot, gid, bad);
+            else v3_slot_sum2(t, wid, C.slots + (size_t)(it & 1) * C.slot_array_bytes, C.slot_stride, (long long)(it & 3), nblk, bid, bad);
             if (lane == 0) { sh[2 * wid] = t[0]; sh[2 * wid + 1] = t[1]; if (bad) sh[5] = 1.0; }
         }
         __syncthreads();
@@ -1287,7 +1383,8 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
         }
         if (stop_est) {                                   // confirm with the exact |r_new|^2 (every CTA takes this branch together)
             bool aborted;
-            const double rr_exact = v3_grid_sum(chk, red, &sh[4], reinterpret_cast<V3Slot *>(C.slots_check), C.slot_stride / 16, (unsigned long long)it, nblk, bid, aborted);
+            const double rr_exact = MULTI ? v3_grid_sum_multi(chk, red, C.mail, C.world, C.rank, C.off_check, C.slot_stride, itg, gtot, gid, aborted)
+                                          : v3_grid_sum(chk, red, &sh[4], reinterpret_cast<V3Slot *>(C.slots_check), C.slot_stride / 16, (unsigned long long)it, nblk, bid, aborted);
             if (aborted) { done = 3; break; }
             eps = sqrt(rr_exact) / normb;
             if (eps < tol) { done = 1; break; }
@@ -1299,7 +1396,11 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
             // warp 0 of each part owns no slice: it updates the copies of the neighbours' boundary r and p from their boundary z
             // (visible since the sum) while the owners run their first B; upper slice first (handed to warp ns)
             double2 zu[N / 64], zl[N / 64];
-            const double2 *gu = hslice(it & 1, right, 0), *gl = hslice(it & 1, left, 1);
+            const double2 *gu = hslice((int)(itg & 1), right, 0), *gl = hslice((int)(itg & 1), left, 1);
+            if (MULTI) {
+                if (bid == nblk - 1) gu = inbox(C.rank, (int)(itg & 1), 1);
+                if (bid == 0) gl = inbox(C.rank, (int)(itg & 1), 0);
+            }
 #pragma unroll
             for (int u = 0; u < N / 64; u++) zu[u] = __ldcg(gu + lane + 32 * u);
 #pragma unroll
@@ -1350,17 +1451,25 @@ static v3_resident_t pick3_resident(int lxl, int ry) {
 }
 typedef void (*v3_resident1_t)(const V3Params, const CgResident1);
 static v3_resident1_t pick3_resident1(int lxl, int ry) {
-    if (lxl == 8 && ry == 4) return k_cg_v3_resident1<V3Lane<8, 4>>;
-    if (lxl == 8 && ry == 8) return k_cg_v3_resident1<V3Lane<8, 8>>;
-    if (lxl == 4 && ry == 2) return k_cg_v3_resident1<V3Lane<4, 2>>;
-    if (lxl == 4 && ry == 4) return k_cg_v3_resident1<V3Lane<4, 4>>;
-    if (lxl == 4 && ry == 8) return k_cg_v3_resident1<V3Lane<4, 8>>;
+    if (lxl == 8 && ry == 4) return k_cg_v3_resident1<V3Lane<8, 4>, 0>;
+    if (lxl == 8 && ry == 8) return k_cg_v3_resident1<V3Lane<8, 8>, 0>;
+    if (lxl == 4 && ry == 2) return k_cg_v3_resident1<V3Lane<4, 2>, 0>;
+    if (lxl == 4 && ry == 4) return k_cg_v3_resident1<V3Lane<4, 4>, 0>;
+    if (lxl == 4 && ry == 8) return k_cg_v3_resident1<V3Lane<4, 8>, 0>;
     return nullptr;
 }
 static v3_resident1_t pick3h_resident1(int L1, int L2) {
-    if (L1 == 24 && L2 == 24) return k_cg_v3_resident1<V3Honey<8, 3, 6>>;
-    if (L1 == 16 && L2 == 16) return k_cg_v3_resident1<V3Honey<4, 4, 2>>;
-    if (L1 == 8 && L2 == 8) return k_cg_v3_resident1<V3Honey<4, 2, 1>>;
+    if (L1 == 24 && L2 == 24) return k_cg_v3_resident1<V3Honey<8, 3, 6>, 0>;
+    if (L1 == 16 && L2 == 16) return k_cg_v3_resident1<V3Honey<4, 4, 2>, 0>;
+    if (L1 == 8 && L2 == 8) return k_cg_v3_resident1<V3Honey<4, 2, 1>, 0>;
+    return nullptr;
+}
+// tau-slab over several GPUs: the geometries of the named multi-GPU configurations
+static v3_resident1_t pick3_resident1_multi(int kind, int a, int b) {
+    if (kind == 0 && a == 8 && b == 8) return k_cg_v3_resident1<V3Lane<8, 8>, 1>;          // 32 x 32 square
+    if (kind == 0 && a == 4 && b == 2) return k_cg_v3_resident1<V3Lane<4, 2>, 1>;          // 16 x 16 square
+    if (kind == 1 && a == 24 && b == 24) return k_cg_v3_resident1<V3Honey<8, 3, 6>, 1>;    // 24 x 24 honeycomb
+    if (kind == 1 && a == 8 && b == 8) return k_cg_v3_resident1<V3Honey<4, 2, 1>, 1>;      // 8 x 8 honeycomb
     return nullptr;
 }
 
@@ -1398,6 +1507,74 @@ static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *stat
     C.x = (double *)x; C.r = (const double *)r; C.state = state;
     C.slots = f->v3_slots.p; C.slot_array_bytes = arr; C.slots_check = f->v3_slots.p + 2 * arr; C.slot_stride = stride_bytes;
     C.halo = f->v3_halo.p; C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
+    void *args[] = {(void *)&P, (void *)&C};
+    SQ_CUDA(cudaLaunchCooperativeKernel((const void *)k, dim3(grid), dim3(T), args, smem, f->stream));
+    f->launches++;
+    return true;
+}
+
+// ---- tau-slab over several GPUs ---------------------------------------------------------------------
+// Mailbox layout (bytes): [2 parity][gtot_max] main slots | [gtot_max] check slots | halo inbox [2][2][2][N] doubles
+static const size_t V3_MAIL_STRIDE = 64, V3_MAIL_MAXCTA = 148 * 8;
+static size_t v3_mail_off_check() { return 2 * V3_MAIL_MAXCTA * V3_MAIL_STRIDE; }
+static size_t v3_mail_off_inbox() { return 3 * V3_MAIL_MAXCTA * V3_MAIL_STRIDE; }
+size_t fdm_v3_mailbox_bytes(const sq_fdm *f) { return v3_mail_off_inbox() + (size_t)8 * f->N * sizeof(double); }
+
+// Can this slab configuration run the multi-GPU resident kernel?  Fills S and the CTA counts of all ranks.
+static bool v3_multi_plan(const sq_fdm *f, int *S_out, std::vector<int> *ctas) {
+    if (f->world < 2 || f->world > 8 || !f->v3_ok || !f->cs_coluni || !f->mail_ready) return false;
+    if (!pick3_resident1_multi(f->v3_kind, f->v3_lxl, f->v3_ry)) return false;
+    const int L = (int)f->L, W = f->world, base = L / W, extra = L % W;
+    int nmax = base + (extra ? 1 : 0);
+    int S = std::max(2, (nmax + f->num_sms - 1) / f->num_sms);
+    if (S > 3 || base < S) return false;
+    ctas->clear();
+    size_t tot = 0;
+    for (int q = 0; q < W; q++) {
+        const int n = base + (q < extra ? 1 : 0);
+        ctas->push_back((n + S - 1) / S);
+        tot += ctas->back();
+    }
+    if (tot > V3_MAIL_MAXCTA) return false;
+    *S_out = S;
+    return true;
+}
+bool fdm_v3_multi_possible(const sq_fdm *f) {
+    int S;
+    std::vector<int> c;
+    return v3_multi_plan(f, &S, &c);
+}
+
+// x (in/out), r (in): native order, own slab + the two halo slices of r valid.  state: normb / tol / eps0 set by the caller (global
+// values).  Every rank calls this collectively.
+bool fdm_v3_cg_resident1_multi(sq_fdm *f, double2 *x, double2 *r, CgState *state, i64 maxiter) {
+    int S;
+    std::vector<int> ctas;
+    if (!v3_multi_plan(f, &S, &ctas)) return false;
+    v3_resident1_t k = pick3_resident1_multi(f->v3_kind, f->v3_lxl, f->v3_ry);
+    const int grid = ctas[f->rank], T = 64 * (S + 1);
+    const size_t smem = (size_t)(5 * S + 9) * f->N * sizeof(double);
+    if (smem > f->smem_optin || grid > f->num_sms) return false;
+    V3Params P;
+    memset(&P, 0, sizeof(P));
+    P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = (int)f->C; P.nphase = 2;
+    for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = c < f->C ? f->clo[c] : 0; }
+    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p;
+    SQ_CUDA(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k, T, smem));
+    if (per_sm * f->num_sms < grid) return false;
+    const size_t nh = (size_t)8 * grid * f->N;
+    if (f->v3_halo.n < nh) f->v3_halo.alloc(nh);
+    CgResident1 C;
+    memset(&C, 0, sizeof(C));
+    C.x = (double *)x; C.r = (const double *)r; C.state = state;
+    C.slot_stride = (unsigned)V3_MAIL_STRIDE; C.slot_array_bytes = V3_MAIL_MAXCTA * V3_MAIL_STRIDE;
+    C.halo = f->v3_halo.p; C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
+    C.world = f->world; C.rank = f->rank; C.gtot = 0; C.gid0 = 0;
+    for (int q = 0; q < f->world; q++) { if (q < f->rank) C.gid0 += ctas[q]; C.gtot += ctas[q]; C.mail[q] = (char *)f->mail_ptr[q]; }
+    C.it_base = f->v3_it_base;
+    C.off_check = v3_mail_off_check(); C.off_inbox = v3_mail_off_inbox();
     void *args[] = {(void *)&P, (void *)&C};
     SQ_CUDA(cudaLaunchCooperativeKernel((const void *)k, dim3(grid), dim3(T), args, smem, f->stream));
     f->launches++;

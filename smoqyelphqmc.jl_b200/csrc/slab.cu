@@ -109,7 +109,38 @@ void slab_init(sq_fdm *f, int rank, int world, const char *id128) {
     }
 }
 
+// ---- mailboxes of the multi-GPU resident CG: one buffer per rank, mapped into every peer through CUDA IPC -------------------
+size_t fdm_v3_mailbox_bytes(const sq_fdm *f);
+void slab_mailbox_create(sq_fdm *f, char *out64) {
+    SQ_REQUIRE(f->world >= 1 && f->world <= 8, "mailboxes support up to 8 ranks");
+    SQ_CUDA(cudaSetDevice(f->device));
+    const size_t bytes = fdm_v3_mailbox_bytes(f);
+    if (!f->mail.p) f->mail.alloc(bytes);            // zero-filled: validity tag 0 / epoch 0
+    f->mail_ptr[f->rank] = f->mail.p;
+    cudaIpcMemHandle_t h;
+    SQ_CUDA(cudaIpcGetMemHandle(&h, f->mail.p));
+    static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+    memcpy(out64, &h, 64);
+}
+// handles64: world x 64 bytes, rank-major (every rank passes the same gathered array)
+void slab_mailbox_open(sq_fdm *f, const char *handles64) {
+    SQ_REQUIRE(f->mail.p != nullptr, "create the own mailbox first");
+    SQ_CUDA(cudaSetDevice(f->device));
+    for (int q = 0; q < f->world; q++) {
+        if (q == f->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles64 + 64 * q, 64);
+        void *p = nullptr;
+        SQ_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        f->mail_ptr[q] = p;
+    }
+    f->mail_ready = 1;
+}
+
 void slab_destroy(sq_fdm *f) {
+    for (int q = 0; q < 8; q++)
+        if (f->mail_ready && q != f->rank && f->mail_ptr[q]) { cudaIpcCloseMemHandle(f->mail_ptr[q]); f->mail_ptr[q] = nullptr; }
+    f->mail_ready = 0;
     if (f->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)f->comm);
     f->comm = nullptr;
 }
@@ -199,7 +230,70 @@ __global__ void k_slab_roll(double *scal, double tol, int iter) {
     else scal[1] = scal[3];
 }
 
+bool fdm_v3_multi_possible(const sq_fdm *f);
+bool fdm_v3_cg_resident1_multi(sq_fdm *f, double2 *x, double2 *r, CgState *state, i64 maxiter);
+void fdm_v3_prepare_native(sq_fdm *f);
+void fdm_v3_to_native(sq_fdm *f, double2 *dst, const double2 *src);
+void fdm_v3_from_native(sq_fdm *f, double2 *dst, const double2 *src);
+
+// Resident multi-GPU solve (fdm_v3.cu, MULTI kernels): the whole solve is one cooperative launch per rank; sums and halos travel
+// through the peer-mapped mailboxes.  Returns false if the configuration does not qualify (the NCCL loop below runs instead).
+static bool cg_slab_resident(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, double tol, i64 maxiter, i64 *iters, double *eps) {
+    if (getenv("SQ_NO_RESIDENT_CG") || maxiter <= 0) return false;
+    fdm_select_tuning(f);
+    if (!fdm_v3_multi_possible(f)) return false;
+    const size_t N = (size_t)f->N, V = (size_t)f->L * N;
+    const size_t off = (size_t)f->slab_lo * N, n = (size_t)(f->slab_hi - f->slab_lo) * N;
+    const int TB = 256;
+    const int G = (int)std::max<size_t>(1, std::min<size_t>((n + TB - 1) / TB, (size_t)f->num_sms * 4));
+    cudaStream_t s = f->stream;
+    double *part = f->part.p, *scal = f->scal.p;
+    double2 *r = f->r.p;
+    SQ_CUDA(cudaMemsetAsync(scal, 0, 16 * sizeof(double), s));
+    k_norm2_part<<<G, TB, 0, s>>>(b + off, n, part);
+    k_pack_sum<<<1, 32, 0, s>>>(part, G, scal + 0);
+    if (zero_start) {
+        SQ_CUDA(cudaMemcpyAsync(r + off, b + off, n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+        SQ_CUDA(cudaMemsetAsync(x + off, 0, n * sizeof(double2), s));
+    } else {
+        fdm_halo_exchange(f, x);
+        fdm_mul_dev(f, SQ_OP_MTM, r, x);
+        k_sub<<<G, TB, 0, s>>>(r + off, b + off, n);
+    }
+    k_norm2_part<<<G, TB, 0, s>>>(r + off, n, part);
+    k_pack_sum<<<1, 32, 0, s>>>(part, G, scal + 1);
+    fdm_allreduce_sum(f, scal, 2);
+    double h[2];
+    SQ_CUDA(cudaMemcpyAsync(h, scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+    const double normb = std::sqrt(h[0]), eps0 = std::sqrt(h[1]) / normb;
+    if (!(eps0 == eps0)) throw SqError("conjugate gradient (tau-slab): NaN encountered in the residual");
+    if (eps0 < tol) { *iters = 0; *eps = eps0; return true; }
+    fdm_halo_exchange(f, r);                                   // p0 = r0 of the neighbours' boundary slices
+    fdm_v3_prepare_native(f);
+    fdm_v3_to_native(f, f->v3_r.p, r);
+    if (zero_start) SQ_CUDA(cudaMemsetAsync(f->v3_x.p, 0, V * sizeof(double2), s));
+    else fdm_v3_to_native(f, f->v3_x.p, x);
+    CgState st;
+    memset(&st, 0, sizeof(st));
+    st.normb = normb; st.tol = tol; st.eps = eps0; st.rz_re = h[1];
+    *f->h_cg = st;
+    SQ_CUDA(cudaMemcpyAsync(f->cg.p, f->h_cg, sizeof(CgState), cudaMemcpyHostToDevice, s));
+    if (!fdm_v3_cg_resident1_multi(f, f->v3_x.p, f->v3_r.p, f->cg.p, maxiter)) return false;
+    fdm_v3_from_native(f, f->tmp2.p, f->v3_x.p);
+    SQ_CUDA(cudaMemcpyAsync(x + off, f->tmp2.p + off, n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+    SQ_CUDA(cudaMemcpyAsync(f->h_cg, f->cg.p, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+    f->v3_it_base += (unsigned long long)f->h_cg->iters + 4;      // identical on every rank: the tags of the next solve continue
+    if (f->h_cg->done == 3) throw SqError("conjugate gradient (tau-slab): a grid-wide sum over the GPUs timed out");
+    if (f->h_cg->done == 2) throw SqError("conjugate gradient (tau-slab): NaN encountered in the residual");
+    *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
+    *eps = f->h_cg->eps;
+    return true;
+}
+
 void fdm_cg_slab(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, double tol, i64 maxiter, i64 *iters, double *eps) {
+    if (cg_slab_resident(f, x, b, zero_start, tol, maxiter, iters, eps)) return;
     const size_t N = (size_t)f->N;
     const size_t off = (size_t)f->slab_lo * N, n = (size_t)(f->slab_hi - f->slab_lo) * N;
     const int TB = 256;

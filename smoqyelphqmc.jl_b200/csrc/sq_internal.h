@@ -90,6 +90,11 @@ struct sq_fdm {
     int rank = 0, world = 1;
     void *comm = nullptr;                    // ncclComm_t
     DevBuf<double> scal;                     // packed scalars for all-reduces
+    // mailboxes of the multi-GPU resident CG (peer-mapped through CUDA IPC): own buffer + the peers' mappings
+    DevBuf<char> mail;
+    void *mail_ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int mail_ready = 0;
+    unsigned long long v3_it_base = 0;       // iteration count carried across multi-GPU solves (slot validity tags)
 
     KParams kparams(int S, int T) const;
     size_t vec_bytes() const { return (size_t)L * N * sizeof(double2); }

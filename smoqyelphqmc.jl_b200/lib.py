@@ -39,6 +39,8 @@ SIGNATURES = {
     "sq_fdm_stream": [vp, pp],
     "sq_nccl_unique_id": [vp],
     "sq_fdm_init_slab": [vp, i32, i32, vp],
+    "sq_fdm_mailbox_create": [vp, vp],
+    "sq_fdm_mailbox_open": [vp, vp],
     "sq_fdm_set_slab_range": [vp, i64, i64],
     "sq_fdm_get_slab": [vp, vp, vp, vp, vp],
     "sq_kpm_create": [pp, vp, f64, i64, f64, f64],

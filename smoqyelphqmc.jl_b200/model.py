@@ -262,6 +262,10 @@ def config(name: str) -> Model:
         "cfg3": lambda: bssh_square(16, 16, 10.0, name="cfg3"),
         "cfg4": lambda: holstein_square(32, 32, 20.0, name="cfg4"),
         "cfg5": lambda: holstein_honeycomb(24, 4.0, name="cfg5"),
+        "h16": lambda: holstein_square(16, 16, 2.0, name="h16"),                      # small register-path lattice (multi-GPU tests)
+        "hc8": lambda: holstein_honeycomb(8, 2.0, name="hc8"),
+        "b40": lambda: holstein_square(32, 32, 40.0, name="b40"),                     # Ltau = 800: more slices than one GPU keeps resident
+        "b80": lambda: holstein_square(32, 32, 80.0, name="b80"),                     # Ltau = 1600
         "sweep64": lambda: holstein_square(64, 64, 20.0, name="sweep64"),
         "sweep128": lambda: holstein_square(128, 128, 20.0, name="sweep128"),
     }

@@ -71,7 +71,8 @@ def test_two_gpu_halo_exchange_and_cg():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    for name in ("cfg3", "cfg1"):
+    # cfg3 / cfg1: shared-memory kernels + NCCL loop; h16 / hc8: register path + resident multi-GPU solver over the mailboxes
+    for name in ("cfg3", "cfg1", "h16", "hc8"):
         res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                               "--master-port", "29641", os.path.join(ROOT, "tools", "slab_worker.py"), name, "check", "100"],
                              env=env, capture_output=True, text=True, timeout=600)

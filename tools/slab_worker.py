@@ -26,6 +26,10 @@ elph.update_fdm()
 ids = [api.FermionDetMatrix.nccl_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(ids, src=0)
 fdm.init_slab(rank, world, ids[0])
+if os.environ.get("SQ_SLAB_MAILBOX", "1") != "0":           # peer-mapped mailboxes: the resident multi-GPU CG where it applies
+    handles = [None] * world
+    dist.all_gather_object(handles, fdm.mailbox_handle())
+    fdm.mailbox_open(handles)
 lo, hi = fdm.slab["lo"], fdm.slab["hi"]
 out = {"config": name, "world": world}
 b = np.asfortranarray(rng.standard_normal((m.Ltau, m.N)) + 1j * rng.standard_normal((m.Ltau, m.N)))
@@ -72,6 +76,7 @@ torch.cuda.synchronize()
 dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
 out["cg_us_per_iter"] = float(dt.item()) / niter * 1e6
+out["resident"] = os.environ.get("SQ_SLAB_MAILBOX", "1") != "0" and not os.environ.get("SQ_NO_RESIDENT_CG")
 out["slab"] = [lo, hi]
 out["tuning"] = fdm.tuning
 if rank == 0:
