@@ -240,7 +240,7 @@ void fdm_v3_from_native(sq_fdm *f, double2 *dst, const double2 *src);
 // through the peer-mapped mailboxes.  Returns false if the configuration does not qualify (the NCCL loop below runs instead).
 static bool cg_slab_resident(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, double tol, i64 maxiter, i64 *iters, double *eps) {
     if (getenv("SQ_NO_RESIDENT_CG") || maxiter <= 0) return false;
-    fdm_select_tuning(f);
+    // (no fdm_select_tuning here: the autotuner's trial launches write the staging buffers the caller's b may still live in)
     if (!fdm_v3_multi_possible(f)) return false;
     const size_t N = (size_t)f->N, V = (size_t)f->L * N;
     const size_t off = (size_t)f->slab_lo * N, n = (size_t)(f->slab_hi - f->slab_lo) * N;
