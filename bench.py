@@ -367,38 +367,78 @@ def run_native(args):
     barrier()
     # ---- tau-slab strong scaling of the CG solve (N > 1): the same M^T M system partitioned over the ranks with
     #      NCCL halo exchange + all-reduced dot products, against the single-GPU solve timed on every rank first
+    def finish(tau_slab, cpu=None):
+        line = {"metric": "efa_hmc_trajectories_per_s", "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(m, precond, "gpu"),
+                "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": nx * 8, "d2h_bytes_per_step": nx * 8 + 64},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "cg_iters_per_trajectory": iters_per_traj, "matvecs_per_trajectory": matvecs_per_traj,
+                "acceptance": accepted / args.steps, "tau_slab": tau_slab}
+        emit(line)
+
     tau_slab = None
     if world > 1:
+        # the strong-scaling section is an extra: a watchdog makes sure the headline line is printed even if it stalls
+        import threading
+        stage = ["start"]
+
+        def bail():
+            if rank == 0:
+                finish({"error": "tau-slab section exceeded its time limit at stage '%s'" % stage[0]})
+            os._exit(0)
+        dog = threading.Timer(240.0, bail)
+        dog.daemon = True
+        dog.start()
         n = m.N * m.Ltau
         d_b = torch.randn(n, 2, dtype=torch.float64, device=dev)
         d_x = torch.zeros_like(d_b)
         nit = 400
 
         def timed_cg():
-            fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=40)
+            """us per iteration (max over ranks), or None if any rank failed -- every rank always takes part in the collectives"""
+            bad = 0.0
+            try:
+                fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=40)
+            except Exception as e:                            # noqa: BLE001
+                bad = 1.0
+                sys.stderr.write("rank %d: tau-slab CG failed at stage %s: %s\n" % (rank, stage[0], e))
             barrier()
             t0 = time.perf_counter()
-            fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=nit)
-            torch.cuda.synchronize()
-            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if not bad:
+                try:
+                    fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=nit)
+                    torch.cuda.synchronize()
+                except Exception as e:                        # noqa: BLE001
+                    bad = 1.0
+                    sys.stderr.write("rank %d: tau-slab CG failed at stage %s: %s\n" % (rank, stage[0], e))
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt, bad], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            return float(tt.item()) / nit * 1e6
+            return None if tt[1].item() > 0 else float(tt[0].item()) / nit * 1e6
+
+        stage[0] = "one GPU"
         us1 = timed_cg()
         ids = [api.FermionDetMatrix.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         fdm.init_slab(rank, world, ids[0])
+        stage[0] = "NCCL loop"
         os.environ["SQ_NO_RESIDENT_CG"] = "1"                 # (a) host-launched NCCL loop
         us_nccl = timed_cg()
         del os.environ["SQ_NO_RESIDENT_CG"]
+        stage[0] = "mailboxes"
         handles = [None] * world                              # (b) resident kernels + peer-mapped mailboxes (CUDA IPC over NVLink)
         dist.all_gather_object(handles, fdm.mailbox_handle())
         fdm.mailbox_open(handles)
-        usN = timed_cg()
+        stage[0] = "resident"
+        usN = timed_cg() if us_nccl is not None else None
+        best = min([u for u in (usN, us_nccl) if u is not None], default=None)
         tau_slab = {"what": "unpreconditioned CG iterations on M^T M, cfg4, tau-slab partitioned (strong scaling)",
                     "cg_us_per_iter_1gpu": us1, "cg_us_per_iter": usN, "cg_us_per_iter_nccl_loop": us_nccl, "n_gpus": world,
-                    "cg_iters_per_s": 1e6 / usN, "speedup_vs_1gpu": us1 / usN,
+                    "cg_iters_per_s": 1e6 / best if best else None, "speedup_vs_1gpu": us1 / best if best and us1 else None,
                     "comm": "resident kernel per rank; grid-wide sums and boundary slices as device-initiated stores into peer-mapped "
                             "mailboxes (CUDA IPC over NVLink); cg_us_per_iter_nccl_loop = host-launched NCCL send/recv + all-reduces"}
+        dog.cancel()
 
     if rank != 0:
         if dist is not None:
@@ -410,14 +450,7 @@ def run_native(args):
         v, cores, sample, detail = cpu_sample(m, x_w, precond, False, args.cpu_budget, iters_per_traj)
         cpu = {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": sample, "detail": detail}
 
-    line = {"metric": "efa_hmc_trajectories_per_s", "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(m, precond, "gpu"),
-            "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": nx * 8, "d2h_bytes_per_step": nx * 8 + 64},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "cg_iters_per_trajectory": iters_per_traj, "matvecs_per_trajectory": matvecs_per_traj,
-            "acceptance": accepted / args.steps, "tau_slab": tau_slab}
-    emit(line)
+    finish(tau_slab, cpu)
     if dist is not None:
         dist.destroy_process_group()
 
