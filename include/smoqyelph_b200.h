@@ -202,6 +202,12 @@ int sq_greens_measure_GD0(sq_greens *g, int norb, int ndim, const int64_t *dims,
  * the caller multiplies by `coef` and adds it to `correlation` (add_contraction_to_correlation!, :718-729). */
 int sq_greens_measure_contraction(sq_greens *g, int kind, int norb, int ndim, const int64_t *dims, const int *orbitals, const int64_t *r,
                                   sq_complex *out);
+/* The same contractions with the hopping weights tΔ, t0 of _measure_CΔ0! (:610-652) -- the building block of
+ * measure_current_correlation! (src/Measurements/Correlations/current.jl:2-151).  tD, t0: real, Ltau x cells, tau fastest (the
+ * PermutedDimsArray of fermion_path_integral.t built in make_measurements.jl:316-320), either may be NULL (= nothing); the
+ * delta-function terms need both.  Real hoppings only, so conj_tΔ / conj_t0 have no effect and are not arguments. */
+int sq_greens_measure_contraction_weighted(sq_greens *g, int kind, int norb, int ndim, const int64_t *dims, const int *orbitals, const int64_t *r,
+                                           const double *tD, const double *t0, sq_complex *out);
 /* Building blocks of the local measurements (src/Measurements/tight_binding_measurements.jl:43-133,
  * electron_phonon_measurements.jl: measure_holstein_energy, measure_ssh_energy):
  *   weighted_density: sum_{i,l} w[i,l] n(l,i),  n(l,i) = mean_rv (1 - GR[l,i,rv] Rt[l,i,rv]);  w (N x Ltau) real, site fastest

@@ -322,21 +322,46 @@ function measure_GΔ0!(correlation::AbstractArray{Complex{E}}, g::GreensEstimato
     @. correlation += $PermutedDimsArray(GΔ0, (2:D+1..., 1))
     return nothing
 end
-# The four-point contractions (src/Measurements/GreensEstimator.jl:236-606) without hopping weights; the correlation functions built on
+# The four-point contractions (src/Measurements/GreensEstimator.jl:236-606), with or without hopping weights; the correlation functions built on
 # them (density.jl, pair.jl, spin.jl) call these exactly as in the reference.
-function _contraction!(correlation::AbstractArray{Complex{E}}, g::GreensEstimator{E}, kind::Int, orbitals::NTuple{4,Int}, r1, r2, r3, r4, coef;
-                       n::Int, L::NTuple{D,Int}) where {E,D}
+function _contraction!(correlation::AbstractArray{Complex{E}}, g::GreensEstimator{E}, kind::Int, orbitals::NTuple{4,Int}, r1, r2, r3, r4, coef,
+                       tΔ = nothing, t0 = nothing, conj_tΔ::Bool = false, conj_t0::Bool = false; n::Int, L::NTuple{D,Int}) where {E,D}
     Lτ = size(correlation, D + 1) - 1
     C = zeros(Complex{E}, Lτ + 1, L...)
     dims = collect(Int64, L); orb = collect(Cint, orbitals); r = Int64[r1..., r2..., r3..., r4...]
-    GC.@preserve C dims orb r check(ccall((:sq_greens_measure_contraction, LIB), Cint,
-        (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Ptr{Cint}, Ptr{Int64}, Ptr{Complex{E}}), g.h, kind, n, D, dims, orb, r, C))
+    if isnothing(tΔ) && isnothing(t0)
+        GC.@preserve C dims orb r check(ccall((:sq_greens_measure_contraction, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Ptr{Cint}, Ptr{Int64}, Ptr{Complex{E}}), g.h, kind, n, D, dims, orb, r, C))
+    else
+        # real hoppings only (conj_tΔ / conj_t0 are no-ops); the weights are materialised as dense (Lτ, L...) arrays
+        wΔ = isnothing(tΔ) ? E[] : collect(E, tΔ); w0 = isnothing(t0) ? E[] : collect(E, t0)
+        GC.@preserve C dims orb r wΔ w0 check(ccall((:sq_greens_measure_contraction_weighted, LIB), Cint,
+            (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Ptr{Cint}, Ptr{Int64}, Ptr{E}, Ptr{E}, Ptr{Complex{E}}), g.h, kind, n, D, dims, orb, r,
+            isnothing(tΔ) ? C_NULL : pointer(wΔ), isnothing(t0) ? C_NULL : pointer(w0), C))
+    end
     @. correlation += coef * $PermutedDimsArray(C, (2:D+1..., 1))
     return nothing
 end
-measure_GΔ0_GΔ0!(corr, g::GreensEstimator, orbitals, r1, r2, r3, r4, coef; kw...) = _contraction!(corr, g, 0, orbitals, r1, r2, r3, r4, coef; kw...)
-measure_GΔΔ_G00!(corr, g::GreensEstimator, orbitals, r1, r2, r3, r4, coef; kw...) = _contraction!(corr, g, 1, orbitals, r1, r2, r3, r4, coef; kw...)
-measure_G0Δ_GΔ0!(corr, g::GreensEstimator, orbitals, r1, r2, r3, r4, coef; kw...) = _contraction!(corr, g, 2, orbitals, r1, r2, r3, r4, coef; kw...)
+measure_GΔ0_GΔ0!(corr, g::GreensEstimator, orbitals, r1, r2, r3, r4, coef, t...; kw...) = _contraction!(corr, g, 0, orbitals, r1, r2, r3, r4, coef, t...; kw...)
+measure_GΔΔ_G00!(corr, g::GreensEstimator, orbitals, r1, r2, r3, r4, coef, t...; kw...) = _contraction!(corr, g, 1, orbitals, r1, r2, r3, r4, coef, t...; kw...)
+measure_G0Δ_GΔ0!(corr, g::GreensEstimator, orbitals, r1, r2, r3, r4, coef, t...; kw...) = _contraction!(corr, g, 2, orbitals, r1, r2, r3, r4, coef, t...; kw...)
+# measure_current_correlation! (src/Measurements/Correlations/current.jl:2-151) in terms of the weighted contractions; a bond is given as
+# (orbitals = (b, a), displacement); σ = nothing: the spin-summed form
+function measure_current_correlation!(CC, g::GreensEstimator, b′, b″, t′, t″, σ = nothing, coef = 1.0; kw...)
+    (b, a), r′ = b′; (d, c), r″ = b″
+    z = ntuple(_ -> 0, length(r′))
+    f1, f2 = isnothing(σ) ? (4.0, 2.0) : (1.0, σ[1] == σ[2] ? 1.0 : 0.0)
+    measure_GΔΔ_G00!(CC, g, (a, b, d, c), r′, z, z, r″, +f1 * coef, t′, t″, true, false; kw...)
+    measure_GΔΔ_G00!(CC, g, (a, b, c, d), r′, z, r″, z, -f1 * coef, t′, t″, true, true; kw...)
+    measure_GΔΔ_G00!(CC, g, (b, a, d, c), z, r′, z, r″, -f1 * coef, t′, t″, false, false; kw...)
+    measure_GΔΔ_G00!(CC, g, (b, a, c, d), z, r′, r″, z, +f1 * coef, t′, t″, false, true; kw...)
+    f2 == 0 && return nothing
+    measure_G0Δ_GΔ0!(CC, g, (b, a, c, d), z, z, r′, r″, -f2 * coef, t′, t″, true, false; kw...)
+    measure_G0Δ_GΔ0!(CC, g, (b, a, d, c), r″, z, r′, z, +f2 * coef, t′, t″, true, true; kw...)
+    measure_G0Δ_GΔ0!(CC, g, (d, a, b, c), z, r′, z, r″, +f2 * coef, t′, t″, false, false; kw...)
+    measure_G0Δ_GΔ0!(CC, g, (c, a, b, d), r″, r′, z, z, -f2 * coef, t′, t″, false, true; kw...)
+    return nothing
+end
 function measure_n(g::GreensEstimator{E}, orbital::Int; n::Int) where {E}
     out = zeros(Complex{E}, 1)
     check(ccall((:sq_greens_measure_n_orbital, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Complex{E}}), g.h, n, orbital, out))

@@ -457,18 +457,52 @@ class GreensEstimator:
         dims = tuple(m.lattice_dims) if dims is None else tuple(dims)
         return (m.N // int(np.prod(dims)) if norb is None else int(norb)), dims
 
-    def measure_contraction(self, kind, orbitals, r=None, norb=None, dims=None):
+    def measure_contraction(self, kind, orbitals, r=None, norb=None, dims=None, tD=None, t0=None):
         """kind: "GD0_GD0" (measure_GΔ0_GΔ0!), "GDD_G00" (measure_GΔΔ_G00!) or "G0D_GD0" (measure_G0Δ_GΔ0!)
         (src/Measurements/GreensEstimator.jl:236-606); orbitals (a, b, c, d) 0-based, r = (r1, r2, r3, r4) displacement tuples
-        (default all zero).  Returns the contraction with the reference's `correlation` axes (L..., Ltau + 1), coef = 1."""
+        (default all zero); tD, t0: optional real hopping weights of shape (Ltau, L...) (the reference's tΔ, t0).
+        Returns the contraction with the reference's `correlation` axes (L..., Ltau + 1), coef = 1."""
         m = self.fdm.model
         norb, dims = self._geom(norb, dims)
         code = {"GD0_GD0": 0, "GDD_G00": 1, "G0D_GD0": 2}[kind]
         rr = np.zeros((4, len(dims)), np.int64) if r is None else np.ascontiguousarray(r, np.int64).reshape(4, len(dims))
         orb = np.ascontiguousarray(np.asarray(orbitals, np.int32) + 1)
         out = np.zeros((m.Ltau + 1,) + dims, np.complex128, order="F")
-        check(self.L.sq_greens_measure_contraction(self.h, code, norb, len(dims), ptr(_i64(dims, one_based=False)), ptr(orb), ptr(rr), ptr(out)))
+        if tD is None and t0 is None:
+            check(self.L.sq_greens_measure_contraction(self.h, code, norb, len(dims), ptr(_i64(dims, one_based=False)), ptr(orb), ptr(rr), ptr(out)))
+        else:
+            w = []
+            for t in (tD, t0):
+                if t is None:
+                    w.append(None)
+                    continue
+                t = np.asarray(t)
+                if np.iscomplexobj(t):
+                    raise ValueError("real hoppings only")
+                t = np.asfortranarray(t, np.float64)
+                assert t.shape == (m.Ltau,) + dims, "hopping weights have the shape (Ltau, L...)"
+                w.append(t)
+            check(self.L.sq_greens_measure_contraction_weighted(self.h, code, norb, len(dims), ptr(_i64(dims, one_based=False)), ptr(orb), ptr(rr),
+                                                                ptr(w[0]) if w[0] is not None else None, ptr(w[1]) if w[1] is not None else None, ptr(out)))
         return np.moveaxis(out, 0, -1)
+
+    def measure_current_correlation(self, bond1, bond2, t1, t2, coef=1.0, spins=None, norb=None, dims=None):
+        """measure_current_correlation!(CC, greens_estimator, b', b'', t', t'', [σ', σ''], coef)
+        (src/Measurements/Correlations/current.jl:2-151): four hopping-weighted G(Δ,Δ)G(0,0) and four G(0,Δ)G(Δ,0) contractions.
+        A bond is ((orbital_1, orbital_2), displacement); t1, t2 = the effective hoppings of the two bonds, shape (Ltau, L...)
+        (make_measurements.jl:316-320).  spins = None: the spin-summed form (factors 4 and 2); (σ', σ''): the spin-resolved one."""
+        (b, a), r1 = bond1
+        (d, c), r2 = bond2
+        r1, r2 = tuple(r1), tuple(r2)
+        z = (0,) * len(r1)
+        mc = lambda kind, orbs, r: self.measure_contraction(kind, orbs, r, norb=norb, dims=dims, tD=t1, t0=t2)
+        f1, f2 = (4.0, 2.0) if spins is None else (1.0, 1.0 if spins[0] == spins[1] else 0.0)
+        CC = f1 * coef * (mc("GDD_G00", (a, b, d, c), (r1, z, z, r2)) - mc("GDD_G00", (a, b, c, d), (r1, z, r2, z))
+                          - mc("GDD_G00", (b, a, d, c), (z, r1, z, r2)) + mc("GDD_G00", (b, a, c, d), (z, r1, r2, z)))
+        if f2:
+            CC += f2 * coef * (-mc("G0D_GD0", (b, a, c, d), (z, z, r1, r2)) + mc("G0D_GD0", (b, a, d, c), (r2, z, r1, z))
+                               + mc("G0D_GD0", (d, a, b, c), (z, r1, z, r2)) - mc("G0D_GD0", (c, a, b, d), (r2, r1, z, z)))
+        return CC
 
     def measure_n_orbital(self, a, norb=None, dims=None):
         norb, dims = self._geom(norb, dims)

@@ -290,8 +290,8 @@ void greens_measure_GD0_impl(sq_greens *g, int norb, int ndim, const i64 *dims, 
 //   kind 1  measure_GΔΔ_G00!   G(a,i+r+r1,τ | b,i+r+r2,τ) G(c,i+r3,0 | d,i+r4,0)     :391-467
 //   kind 2  measure_G0Δ_GΔ0!   G(a,i+r1,0 | b,i+r+r2,τ) G(c,i+r+r3,τ | d,i+r4,0)     :470-606
 // each = average over pairs n < m of the translational average (_measure_CΔ0!, :610-652, periodic Ltau x L... torus) of two
-// element-wise products of G R / conj(R) fields, plus delta-function terms at τ = 0 / β.  No hopping weights (tΔ, t0 = nothing):
-// that covers the density, pair and spin correlations.  As for G(Δ,0) the products are accumulated in frequency space.
+// element-wise products of G R / conj(R) fields, plus delta-function terms at τ = 0 / β.  Without hopping weights (tΔ, t0 = nothing)
+// that covers the density, pair, spin and bond correlations; with them the current correlation (Correlations/current.jl).  As for G(Δ,0) the products are accumulated in frequency space.
 // ---------------------------------------------------------------------------------------------------
 struct C4Field { const double2 *v; int orb, conj, sh[3]; };
 struct C4Geom { int Lt, N, norb, nd, d[3]; size_t Nc; };
@@ -312,22 +312,43 @@ __device__ __forceinline__ double2 c4_value(const C4Field &f, const C4Geom &G, i
     if (f.conj) x.y = -x.y;
     return x;
 }
+// tD, t0: optional real hopping weights (Ltau x cells, tau fastest) of _measure_CΔ0! (:626-646)
 __global__ void k_c4_fill(double2 *__restrict__ X, double2 *__restrict__ Y, const C4Field f1, const C4Field f2, const C4Field f3, const C4Field f4,
-                          const C4Geom G) {
+                          const C4Geom G, const double *__restrict__ tD, const double *__restrict__ t0) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)G.Lt * G.Nc) return;
     const int l = (int)(idx / G.Nc);
     const size_t c = idx % G.Nc;
-    X[idx] = cmul(c4_value(f1, G, l, c), c4_value(f2, G, l, c));
-    Y[idx] = cmul(c4_value(f3, G, l, c), c4_value(f4, G, l, c));
+    double2 x = cmul(c4_value(f1, G, l, c), c4_value(f2, G, l, c));
+    double2 y = cmul(c4_value(f3, G, l, c), c4_value(f4, G, l, c));
+    if (tD) x = cscale(tD[(size_t)l + (size_t)G.Lt * c], x);
+    if (t0) y = cscale(t0[(size_t)l + (size_t)G.Lt * c], y);
+    X[idx] = x;
+    Y[idx] = y;
+}
+// the weight tD displaced by sh cells (circshift by -sh), times t0, at (l, c); 1 without weights
+struct C4Weight { const double *tD, *t0; int sh[3]; };
+__device__ __forceinline__ double c4_weight(const C4Weight &w, const C4Geom &G, int l, size_t c) {
+    if (!w.tD) return 1.0;
+    size_t cs = 0, mul = 1, rem = c;
+    for (int k = 0; k < G.nd; k++) {
+        int ck = (int)(rem % G.d[k]);
+        rem /= G.d[k];
+        int q = (ck + w.sh[k]) % G.d[k];
+        if (q < 0) q += G.d[k];
+        cs += (size_t)q * mul;
+        mul *= G.d[k];
+    }
+    return w.tD[(size_t)l + (size_t)G.Lt * cs] * w.t0[(size_t)l + (size_t)G.Lt * c];
 }
 // partial sums of sum_{l, c} f1(l, c) f2(l, c)
-__global__ void k_c4_dot(double *__restrict__ part, const C4Field f1, const C4Field f2, const C4Geom G) {
+__global__ void k_c4_dot(double *__restrict__ part, const C4Field f1, const C4Field f2, const C4Geom G, const C4Weight w) {
     __shared__ double red[2 * 32];
     double v[2] = {0, 0};
     const size_t tot = (size_t)G.Lt * G.Nc;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (size_t)gridDim.x * blockDim.x) {
-        const double2 p = cmul(c4_value(f1, G, (int)(idx / G.Nc), idx % G.Nc), c4_value(f2, G, (int)(idx / G.Nc), idx % G.Nc));
+        double2 p = cmul(c4_value(f1, G, (int)(idx / G.Nc), idx % G.Nc), c4_value(f2, G, (int)(idx / G.Nc), idx % G.Nc));
+        p = cscale(c4_weight(w, G, (int)(idx / G.Nc), idx % G.Nc), p);
         v[0] += p.x;
         v[1] += p.y;
     }
@@ -343,7 +364,8 @@ __global__ void k_c4_finish(double2 *__restrict__ out, const double2 *__restrict
 }
 
 // sum over random vectors of mean_{tau, cells} GR(orb_g, cell + sh) conj(R)(orb_r, cell), divided by Nrv
-static void c4_mean_GR_Rt(sq_greens *g, const C4Geom &G, int orb_g, const int *sh, int orb_r, double *re, double *im) {
+static void c4_mean_GR_Rt(sq_greens *g, const C4Geom &G, int orb_g, const int *sh, int orb_r, double *re, double *im,
+                          const C4Weight w = C4Weight{nullptr, nullptr, {0, 0, 0}}) {
     sq_fdm *f = g->f;
     const size_t V = (size_t)f->L * f->N;
     const int nb = 64;
@@ -351,7 +373,7 @@ static void c4_mean_GR_Rt(sq_greens *g, const C4Geom &G, int orb_g, const int *s
     double sr = 0, si = 0;
     for (i64 n = 0; n < g->Nrv; n++) {
         C4Field a = {g->GR.p + n * V, orb_g, 0, {sh[0], sh[1], sh[2]}}, b = {g->R.p + n * V, orb_r, 1, {0, 0, 0}};
-        k_c4_dot<<<nb, 256, 0, f->stream>>>(g->part.p, a, b, G);
+        k_c4_dot<<<nb, 256, 0, f->stream>>>(g->part.p, a, b, G, w);
         SQ_LAUNCH_CHECK();
         f->launches++;
         SQ_CUDA(cudaMemcpyAsync(h.data(), g->part.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
@@ -377,7 +399,10 @@ void greens_measure_n_orbital_impl(sq_greens *g, int norb, int a, double *out) {
 }
 
 // h_out: (Ltau + 1) x cells complex, tau fastest.  orb[4] 1-based orbitals (a, b, c, d); r: 4 x ndim static displacements.
-void greens_measure_c4_impl(sq_greens *g, int kind, int norb, int ndim, const i64 *dims, const int *orb, const i64 *r, void *h_out) {
+// h_tD, h_t0: optional real hopping weights tΔ, t0 (Ltau x cells, tau fastest; the reference's PermutedDimsArray of fermion_path_integral.t,
+// make_measurements.jl:316-320); real hoppings only, so the reference's conj_tΔ / conj_t0 switches have no effect.
+void greens_measure_c4_impl(sq_greens *g, int kind, int norb, int ndim, const i64 *dims, const int *orb, const i64 *r, void *h_out,
+                            const double *h_tD, const double *h_t0) {
     sq_fdm *f = g->f;
     SQ_CUDA(cudaSetDevice(f->device));
     SQ_REQUIRE(kind >= 0 && kind <= 2 && norb >= 1 && ndim >= 1 && ndim <= 3 && dims && orb && r && h_out, "bad argument");
@@ -399,6 +424,13 @@ void greens_measure_c4_impl(sq_greens *g, int kind, int norb, int ndim, const i6
     for (int k = ndim - 1; k >= 0; k--) ax.push_back(G.d[k]);
     SQ_CUDA(cudaMemsetAsync(g->wc.p, 0, M * sizeof(double2), f->stream));
     double2 *X = g->wa.p, *Y = g->wb.p, *C = g->wc.p, *T = g->wt.p;
+    const double *tD = nullptr, *t0 = nullptr;
+    if (h_tD || h_t0) {
+        if (g->wreal.n < 2 * M) g->wreal.alloc(2 * M, false);
+        if (h_tD) { SQ_CUDA(cudaMemcpyAsync(g->wreal.p, h_tD, M * sizeof(double), cudaMemcpyHostToDevice, f->stream)); tD = g->wreal.p; }
+        if (h_t0) { SQ_CUDA(cudaMemcpyAsync(g->wreal.p + M, h_t0, M * sizeof(double), cudaMemcpyHostToDevice, f->stream)); t0 = g->wreal.p + M; }
+    }
+    const bool weighted = tD || t0;
     auto field = [&](bool gr, i64 n, int o, const int *sh) {
         C4Field x = {(gr ? g->GR.p : g->R.p) + n * V, o, gr ? 0 : 1, {sh[0], sh[1], sh[2]}};
         return x;
@@ -406,9 +438,9 @@ void greens_measure_c4_impl(sq_greens *g, int kind, int norb, int ndim, const i6
     for (i64 n = 0; n + 1 < g->Nrv; n++)
         for (i64 m = n + 1; m < g->Nrv; m++) {
             const C4Field GRa = field(true, n, a, R[0]), Rtb = field(false, n, b, R[1]), GRc = field(true, m, c, R[2]), Rtd = field(false, m, d, R[3]);
-            if (kind == 0) k_c4_fill<<<(unsigned)((M + 255) / 256), 256, 0, f->stream>>>(X, Y, GRa, GRc, Rtb, Rtd, G);
-            else if (kind == 1) k_c4_fill<<<(unsigned)((M + 255) / 256), 256, 0, f->stream>>>(X, Y, GRa, Rtb, GRc, Rtd, G);
-            else k_c4_fill<<<(unsigned)((M + 255) / 256), 256, 0, f->stream>>>(X, Y, Rtb, GRc, GRa, Rtd, G);
+            if (kind == 0) k_c4_fill<<<(unsigned)((M + 255) / 256), 256, 0, f->stream>>>(X, Y, GRa, GRc, Rtb, Rtd, G, tD, t0);
+            else if (kind == 1) k_c4_fill<<<(unsigned)((M + 255) / 256), 256, 0, f->stream>>>(X, Y, GRa, Rtb, GRc, Rtd, G, tD, t0);
+            else k_c4_fill<<<(unsigned)((M + 255) / 256), 256, 0, f->stream>>>(X, Y, Rtb, GRc, GRa, Rtd, G, tD, t0);
             SQ_LAUNCH_CHECK();
             greens_fftnd(g, &X, &T, ax, false);
             greens_fftnd(g, &Y, &T, ax, true);
@@ -437,32 +469,50 @@ void greens_measure_c4_impl(sq_greens *g, int kind, int norb, int ndim, const i6
     };
     int sh[3] = {0, 0, 0}, at[3] = {0, 0, 0};
     double re, im;
+    // with weights the delta terms carry tΔ (displaced) times t0 inside the mean (:318-326, :346-353, :560-568, :589-597)
+    const bool need_delta = (kind == 0 && (a == b || c == d)) || (kind == 2 && (a == b || c == d));
+    if (weighted && need_delta) SQ_REQUIRE(tD && t0, "the delta-function terms need both hopping weights (the reference shifts tΔ and multiplies by t0)");
+    C4Weight W = {tD, t0, {0, 0, 0}};
     if (kind == 0) {
         if (a == b) {                                              // :305-337   -δ(a,b) δ(r, r2-r1) GR(i-r1+r2+r3-r4, c) R(i, d) at τ = β
-            for (int k = 0; k < ndim; k++) { sh[k] = -(R[0][k] - R[1][k] - R[2][k] + R[3][k]); at[k] = -R[0][k] + R[1][k]; }
-            c4_mean_GR_Rt(g, G, c, sh, d, &re, &im);
+            for (int k = 0; k < ndim; k++) { sh[k] = -(R[0][k] - R[1][k] - R[2][k] + R[3][k]); at[k] = -R[0][k] + R[1][k]; W.sh[k] = -(R[0][k] - R[1][k]); }
+            c4_mean_GR_Rt(g, G, c, sh, d, &re, &im, W);
             add(Lt, at, -re, -im);
         }
         if (c == d) {                                              // :339-366
-            for (int k = 0; k < ndim; k++) { sh[k] = -(-R[0][k] + R[1][k] + R[2][k] - R[3][k]); at[k] = -R[2][k] + R[3][k]; }
-            c4_mean_GR_Rt(g, G, a, sh, b, &re, &im);
+            for (int k = 0; k < ndim; k++) { sh[k] = -(-R[0][k] + R[1][k] + R[2][k] - R[3][k]); at[k] = -R[2][k] + R[3][k]; W.sh[k] = -(R[2][k] - R[3][k]); }
+            c4_mean_GR_Rt(g, G, a, sh, b, &re, &im, W);
             add(Lt, at, -re, -im);
         }
         bool same = (a == b) && (c == d);
         for (int k = 0; k < ndim && same; k++) same = (((R[1][k] - R[0][k]) % G.d[k] + G.d[k]) % G.d[k]) == (((R[3][k] - R[2][k]) % G.d[k] + G.d[k]) % G.d[k]);
-        if (same) {                                                // :368-385
+        if (same) {                                                // :368-385 (the weighted branch of the reference has a typo, `bonj`, and throws; its evident intent is computed)
             for (int k = 0; k < ndim; k++) at[k] = R[1][k] - R[0][k];
-            add(Lt, at, 1.0, 0.0);
+            double wmean = 1.0;
+            if (weighted) {
+                wmean = 0;
+                for (size_t cc = 0; cc < G.Nc; cc++) {
+                    size_t cs = 0, mul = 1, rem = cc;
+                    for (int k = 0; k < ndim; k++) {
+                        int ck = (int)(rem % G.d[k]); rem /= G.d[k];
+                        int q = (((ck - (R[0][k] - R[1][k])) % G.d[k]) + G.d[k]) % G.d[k];
+                        cs += (size_t)q * mul; mul *= G.d[k];
+                    }
+                    for (int l = 0; l < Lt; l++) wmean += h_tD[(size_t)l + (size_t)Lt * cs] * h_t0[(size_t)l + (size_t)Lt * cc];
+                }
+                wmean /= (double)M;
+            }
+            add(Lt, at, wmean, 0.0);
         }
     } else if (kind == 2) {
         if (a == b) {                                              // :546-573   at τ = 0, displacement r1 - r2
-            for (int k = 0; k < ndim; k++) { sh[k] = -(-R[0][k] + R[1][k] - R[2][k] + R[3][k]); at[k] = R[0][k] - R[1][k]; }
-            c4_mean_GR_Rt(g, G, c, sh, d, &re, &im);
+            for (int k = 0; k < ndim; k++) { sh[k] = -(-R[0][k] + R[1][k] - R[2][k] + R[3][k]); at[k] = R[0][k] - R[1][k]; W.sh[k] = R[0][k] - R[1][k]; }
+            c4_mean_GR_Rt(g, G, c, sh, d, &re, &im, W);
             add(0, at, -re, -im);
         }
         if (c == d) {                                              // :575-602   at τ = β, displacement r4 - r3
-            for (int k = 0; k < ndim; k++) { sh[k] = -(-R[0][k] + R[1][k] - R[2][k] + R[3][k]); at[k] = R[3][k] - R[2][k]; }
-            c4_mean_GR_Rt(g, G, a, sh, b, &re, &im);
+            for (int k = 0; k < ndim; k++) { sh[k] = -(-R[0][k] + R[1][k] - R[2][k] + R[3][k]); at[k] = R[3][k] - R[2][k]; W.sh[k] = R[3][k] - R[2][k]; }
+            c4_mean_GR_Rt(g, G, a, sh, b, &re, &im, W);
             add(Lt, at, -re, -im);
         }
     }

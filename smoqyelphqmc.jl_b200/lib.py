@@ -89,6 +89,7 @@ SIGNATURES = {
     "sq_greens_measure": [vp, vp, vp, vp],
     "sq_greens_measure_GD0": [vp, i32, i32, vp, i32, i32, vp],
     "sq_greens_measure_contraction": [vp, i32, i32, i32, vp, vp, vp, vp],
+    "sq_greens_measure_contraction_weighted": [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     "sq_greens_measure_n_orbital": [vp, i32, i32, vp],
     "sq_greens_weighted_density": [vp, vp, vp],
     "sq_greens_weighted_bonds": [vp, i64, vp, vp, vp],

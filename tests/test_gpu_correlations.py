@@ -123,8 +123,11 @@ def _tavg(S, A, B, Ltau):
     S[Ltau] += c[0]
 
 
-def ref_contraction(kind, R, GR, Ltau, norb, dims, orbitals, r):
+def ref_contraction(kind, R, GR, Ltau, norb, dims, orbitals, r, tD=None, t0=None):
+    """tD, t0: optional hopping weights (Ltau, L...) of _measure_CΔ0! (:626-646) and of the weighted delta terms."""
     Rt, G = _fields(R, GR, Ltau, norb, dims)
+    wD = 1.0 if tD is None else tD
+    w0 = 1.0 if t0 is None else t0
     Nrv, D = R.shape[1], len(dims)
     a, b, c, d = orbitals
     r1, r2, r3, r4 = (np.asarray(q) for q in r)
@@ -134,19 +137,23 @@ def ref_contraction(kind, R, GR, Ltau, norb, dims, orbitals, r):
             GRa, Rtb = _shift(G[:, a, ..., n], r1), _shift(Rt[:, b, ..., n], r2)
             GRc, Rtd = _shift(G[:, c, ..., m], r3), _shift(Rt[:, d, ..., m], r4)
             if kind == "GD0_GD0":
-                _tavg(S, GRa * GRc, Rtb * Rtd, Ltau)
+                _tavg(S, wD * GRa * GRc, w0 * Rtb * Rtd, Ltau)
             elif kind == "GDD_G00":
-                _tavg(S, GRa * Rtb, GRc * Rtd, Ltau)
+                _tavg(S, wD * GRa * Rtb, w0 * GRc * Rtd, Ltau)
             else:
-                _tavg(S, Rtb * GRc, GRa * Rtd, Ltau)
+                _tavg(S, wD * Rtb * GRc, w0 * GRa * Rtd, Ltau)
     S /= Nrv * (Nrv - 1) / 2
 
-    def mean_shifted(orb_g, shift, orb_r):
-        """sum over rv of sum(circshift(GR, (0, shift...)) .* Rt) / (Nrv * length): circshift by +s: result[i] = GR[i - s]."""
+    def mean_shifted(orb_g, shift, orb_r, tshift=None):
+        """sum over rv of sum(circshift(GR, (0, shift...)) .* Rt) / (Nrv * length): circshift by +s: result[i] = GR[i - s];
+        with weights: times circshift(tΔ, (0, tshift...)) .* t0 (:318-326, :560-568)."""
         tot = 0.0
+        w = 1.0
+        if tD is not None:
+            w = np.roll(tD, shift=[int(q) for q in tshift], axis=tuple(range(1, 1 + D))) * t0
         for n in range(Nrv):
             g = np.roll(G[:, orb_g, ..., n], shift=[int(q) for q in shift], axis=tuple(range(1, 1 + D)))
-            tot += np.sum(g * Rt[:, orb_r, ..., n]) / g.size
+            tot += np.sum(w * g * Rt[:, orb_r, ..., n]) / g.size
         return tot / Nrv
 
     def at(v):
@@ -154,16 +161,16 @@ def ref_contraction(kind, R, GR, Ltau, norb, dims, orbitals, r):
 
     if kind == "GD0_GD0":
         if a == b:
-            S[(Ltau,) + at(-r1 + r2)] -= mean_shifted(c, r1 - r2 - r3 + r4, d)
+            S[(Ltau,) + at(-r1 + r2)] -= mean_shifted(c, r1 - r2 - r3 + r4, d, r1 - r2)
         if c == d:
-            S[(Ltau,) + at(-r3 + r4)] -= mean_shifted(a, -r1 + r2 + r3 - r4, b)
+            S[(Ltau,) + at(-r3 + r4)] -= mean_shifted(a, -r1 + r2 + r3 - r4, b, r3 - r4)
         if a == b and c == d and at(r2 - r1) == at(r4 - r3):
-            S[(Ltau,) + at(r2 - r1)] += 1
+            S[(Ltau,) + at(r2 - r1)] += 1 if tD is None else np.mean(np.roll(tD, shift=[int(q) for q in r1 - r2], axis=tuple(range(1, 1 + D))) * t0)
     elif kind == "G0D_GD0":
         if a == b:
-            S[(0,) + at(r1 - r2)] -= mean_shifted(c, -r1 + r2 - r3 + r4, d)
+            S[(0,) + at(r1 - r2)] -= mean_shifted(c, -r1 + r2 - r3 + r4, d, -r1 + r2)
         if c == d:
-            S[(Ltau,) + at(r4 - r3)] -= mean_shifted(a, -r1 + r2 - r3 + r4, b)
+            S[(Ltau,) + at(r4 - r3)] -= mean_shifted(a, -r1 + r2 - r3 + r4, b, -r4 + r3)
     return np.moveaxis(S, 0, -1)
 
 
@@ -211,6 +218,50 @@ def test_four_point_contractions_and_density_correlation(name):
             - 2 * ref_contraction("G0D_GD0", R, GR, m.Ltau, norb, dims, (b, a, a, b), zero)
         got = g.measure_density_correlation(a, b)
         assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("name", ["honeycomb", "square"])
+def test_hopping_weighted_contractions_and_current_correlation(name):
+    """tΔ / t0 arguments of the contractions and measure_current_correlation! (Correlations/current.jl:2-151)."""
+    from smoqyelph_b200 import api
+    m = {"honeycomb": lambda: mdl.holstein_honeycomb(3, 0.6, mu=0.2), "square": lambda: mdl.holstein_square(16, 16, 0.3)}[name]()
+    rng = np.random.default_rng(9)
+    V, t = dr.build_Vt(m, m.random_fields(rng, smooth=True))
+    fdm = api.SymFermionDetMatrix(m, tol=1e-12, maxiter=20000)
+    fdm.update(V, t)
+    g = api.GreensEstimator(fdm, Nrv=3, seed=6)
+    g.update_greens_estimator(tol=1e-12)
+    R, GR = g.get()
+    dims = tuple(m.lattice_dims)
+    norb = m.N // int(np.prod(dims))
+    t1 = 1.0 + 0.3 * rng.standard_normal((m.Ltau,) + dims)          # space-time dependent hoppings (as in an SSH model)
+    t2 = 1.0 + 0.3 * rng.standard_normal((m.Ltau,) + dims)
+    zero = [(0,) * len(dims)] * 4
+    shifted = [(1, 0), (0, 2), (2, 1), (0, 0)]
+    cases = [((0, 0, 0, 0), zero), ((0, 0, norb - 1, norb - 1), shifted), ((0, norb - 1, norb - 1, 0), shifted), ((norb - 1, norb - 1, 0, 0), shifted)]
+    for kind in ("GD0_GD0", "GDD_G00", "G0D_GD0"):
+        for orbs, r in cases:
+            got = g.measure_contraction(kind, orbs, r, tD=t1, t0=t2)
+            want = ref_contraction(kind, R, GR, m.Ltau, norb, dims, orbs, r, t1, t2)
+            assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max()), (name, kind, orbs, r, np.abs(got - want).max())
+    # one-sided weights (tΔ only) where no delta term needs both
+    got = g.measure_contraction("GDD_G00", (0, 0, norb - 1, norb - 1), shifted, tD=t1)
+    want = ref_contraction("GDD_G00", R, GR, m.Ltau, norb, dims, (0, 0, norb - 1, norb - 1), shifted, t1, None)
+    assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+    # current correlation: literal restatement of the eight terms
+    for b1, b2 in ((((norb - 1, 0), (1,) + (0,) * (len(dims) - 1)), ((0, norb - 1), (0,) * (len(dims) - 1) + (1,))),
+                   (((0, 0), (1,) + (0,) * (len(dims) - 1)), ((0, 0), (1,) + (0,) * (len(dims) - 1)))):
+        (bb, ba), r1 = b1
+        (bd, bc), r2 = b2
+        z = (0,) * len(dims)
+        rc = lambda kind, orbs, r: ref_contraction(kind, R, GR, m.Ltau, norb, dims, orbs, r, t1, t2)
+        gdd = rc("GDD_G00", (ba, bb, bd, bc), (r1, z, z, r2)) - rc("GDD_G00", (ba, bb, bc, bd), (r1, z, r2, z)) \
+            - rc("GDD_G00", (bb, ba, bd, bc), (z, r1, z, r2)) + rc("GDD_G00", (bb, ba, bc, bd), (z, r1, r2, z))
+        g0d = -rc("G0D_GD0", (bb, ba, bc, bd), (z, z, r1, r2)) + rc("G0D_GD0", (bb, ba, bd, bc), (r2, z, r1, z)) \
+            + rc("G0D_GD0", (bd, ba, bb, bc), (z, r1, z, r2)) - rc("G0D_GD0", (bc, ba, bb, bd), (r2, r1, z, z))
+        for spins, want in ((None, 4 * gdd + 2 * g0d), ((+1, +1), gdd + g0d), ((+1, -1), gdd)):
+            got = g.measure_current_correlation(b1, b2, t1, t2, spins=spins)
+            assert np.abs(got - want).max() < 1e-11 * max(1.0, np.abs(want).max()), (name, b1, b2, spins)
 
 
 # ---- local measurements (tight_binding_measurements.jl:43-133, electron_phonon_measurements.jl) ---------------------------
