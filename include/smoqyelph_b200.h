@@ -96,6 +96,11 @@ int sq_fdm_init_slab(sq_fdm *f, int rank, int world, const char *id128);
  * and passes them to open.  Without mailboxes (or for lattices without the register path) the NCCL loop runs. */
 int sq_fdm_mailbox_create(sq_fdm *f, char *handle64);
 int sq_fdm_mailbox_open(sq_fdm *f, const char *handles64);
+/* One Markov chain over several GPUs ("sharded solve"), after sq_fdm_init_slab (+ mailboxes): every rank keeps the FULL state and runs
+ * everything but the CG solves redundantly and deterministically (same seeds => same chain on every rank); each unpreconditioned solve is
+ * partitioned into tau-slabs and its solution broadcast back, so PFFCalculator, EFAPFFHMCUpdater and GreensEstimator work unchanged on
+ * full-length vectors.  With a KPM preconditioner the solve stays local (replicated). */
+int sq_fdm_set_sharded_solve(sq_fdm *f, int enable);
 int sq_fdm_set_slab_range(sq_fdm *f, int64_t lo, int64_t hi);      /* single-process testing of the range logic */
 int sq_fdm_get_slab(sq_fdm *f, int64_t *lo, int64_t *hi, int *rank, int *world);
 int64_t sq_fdm_launch_count(sq_fdm *f);

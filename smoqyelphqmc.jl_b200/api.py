@@ -154,6 +154,21 @@ class FermionDetMatrix:
 
     def set_slab_range(self, lo, hi): check(self.L.sq_fdm_set_slab_range(self.h, int(lo), int(hi)))
 
+    def set_sharded_solve(self, enable=True):
+        """One chain over several GPUs: full state on every rank, only the CG solves are tau-slab partitioned (after init_slab)."""
+        check(self.L.sq_fdm_set_sharded_solve(self.h, 1 if enable else 0))
+
+    def init_sharded_solve(self, dist):
+        """Convenience for torch.distributed programs: communicator, peer-mapped mailboxes and the sharded-solve switch."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ids = [FermionDetMatrix.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        self.init_slab(rank, world, ids[0])
+        handles = [None] * world
+        dist.all_gather_object(handles, self.mailbox_handle())
+        self.mailbox_open(handles)
+        self.set_sharded_solve(True)
+
     @property
     def slab(self):
         lo, hi, r, w = C.c_int64(0), C.c_int64(0), C.c_int(0), C.c_int(0)

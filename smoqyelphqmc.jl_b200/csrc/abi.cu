@@ -131,6 +131,12 @@ int sq_fdm_mailbox_open(sq_fdm *f, const char *handles64) {
     slab_mailbox_open(f, handles64);
     SQ_CATCH
 }
+int sq_fdm_set_sharded_solve(sq_fdm *f, int enable) {
+    SQ_TRY
+    SQ_REQUIRE(f, "NULL handle");
+    slab_set_sharded(f, enable);
+    SQ_CATCH
+}
 int sq_fdm_set_slab_range(sq_fdm *f, int64_t lo, int64_t hi) {
     SQ_TRY
     SQ_REQUIRE(f, "NULL handle");
@@ -150,7 +156,7 @@ int sq_fdm_mul_dev(sq_fdm *f, int op, void *d_out, const void *d_in) {
     SQ_TRY
     SQ_REQUIRE(f && d_out && d_in, "NULL argument");
     SQ_CUDA(cudaSetDevice(f->device));
-    if (f->world > 1) {
+    if (f->world > 1 && !f->sharded) {
         SQ_REQUIRE(op != SQ_OP_MMT, "M M^T is not available in tau-slab mode");
         fdm_halo_exchange(f, (double2 *)d_in);       // the neighbours' boundary slices are written into d_in at their global index
     }
@@ -161,7 +167,7 @@ int sq_fdm_time_mul(sq_fdm *f, int op, void *d_out, const void *d_in, int reps, 
                     double *us_per_launch) {
     SQ_TRY
     SQ_REQUIRE(f && d_out && d_in && us_per_launch && reps >= 1, "bad argument");
-    SQ_REQUIRE(f->world == 1, "single-GPU measurement only");
+    SQ_REQUIRE(f->world == 1 || f->sharded, "single-GPU measurement only");
     SQ_CUDA(cudaSetDevice(f->device));
     cudaEvent_t e0, e1;
     SQ_CUDA(cudaEventCreate(&e0));

@@ -207,7 +207,11 @@ static int vec_grid(const sq_fdm *f, size_t n, int threads) {
 // Solve M^T M x = b.  x, b device vectors in the [l][i] layout.  Follows cg_solve! step by step.
 void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter,
                 i64 *iters, double *eps) {
-    if (f->world > 1 || f->slab_lo != 0 || f->slab_hi != (int)f->L || (!kpm && getenv("SQ_FORCE_SLAB_CG"))) {
+    if (f->sharded && !kpm) {                 // one chain over several GPUs: partitioned solve, solution gathered on every rank
+        fdm_cg_sharded(f, x, b, zero_start, tol, maxiter, iters, eps);
+        return;
+    }
+    if ((f->world > 1 && !f->sharded) || f->slab_lo != 0 || f->slab_hi != (int)f->L || (!kpm && getenv("SQ_FORCE_SLAB_CG"))) {
         if (kpm) throw SqError("the KPM preconditioner is not available in tau-slab mode (its tau-FFT needs an all-to-all; not built yet)");
         fdm_cg_slab(f, x, b, zero_start, tol, maxiter, iters, eps);
         return;

@@ -34,6 +34,7 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -58,6 +59,7 @@ static void nccl_load() {
     SQ_SYM(AllReduce, "ncclAllReduce");
     SQ_SYM(GroupStart, "ncclGroupStart");
     SQ_SYM(GroupEnd, "ncclGroupEnd");
+    SQ_SYM(Broadcast, "ncclBroadcast");
     SQ_SYM(GetErrorString, "ncclGetErrorString");
 #undef SQ_SYM
 }
@@ -106,6 +108,52 @@ void slab_init(sq_fdm *f, int rank, int world, const char *id128) {
         ncclComm_t c;
         SQ_NCCL(g_nccl.CommInitRank(&c, world, id, rank));
         f->comm = (void *)c;
+    }
+}
+
+// ---- sharded solve: full state on every rank, only the CG solves are partitioned --------------------------------------------
+void slab_set_sharded(sq_fdm *f, int enable) {
+    SQ_REQUIRE(f->world >= 1 && (f->world == 1 || f->comm), "call sq_fdm_init_slab first");
+    if (enable && !f->sharded) {
+        f->shard_lo = f->slab_lo; f->shard_hi = f->slab_hi;
+        memcpy(f->tuned_shard, f->tuned, sizeof(f->tuned));
+        memset(f->tuned, 0, sizeof(f->tuned));
+        f->slab_lo = 0; f->slab_hi = (int)f->L;
+        f->sharded = 1;
+    } else if (!enable && f->sharded) {
+        memcpy(f->tuned, f->tuned_shard, sizeof(f->tuned));
+        f->slab_lo = f->shard_lo; f->slab_hi = f->shard_hi;
+        f->sharded = 0;
+    }
+    f->manual_tuning = 0;
+}
+static void shard_swap(sq_fdm *f, bool enter) {
+    int tmp[3][6];
+    memcpy(tmp, f->tuned, sizeof(tmp));
+    memcpy(f->tuned, f->tuned_shard, sizeof(tmp));
+    memcpy(f->tuned_shard, tmp, sizeof(tmp));
+    if (enter) { f->slab_lo = f->shard_lo; f->slab_hi = f->shard_hi; }
+    else { f->slab_lo = 0; f->slab_hi = (int)f->L; }
+}
+// one solve of the sharded mode: slab solve, then every rank broadcasts its slab of the solution to the others
+void fdm_cg_sharded(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, double tol, i64 maxiter, i64 *iters, double *eps) {
+    shard_swap(f, true);
+    try {
+        fdm_cg_slab(f, x, b, zero_start, tol, maxiter, iters, eps);
+    } catch (...) {
+        shard_swap(f, false);
+        throw;
+    }
+    shard_swap(f, false);
+    if (f->world > 1) {
+        SQ_NCCL(g_nccl.GroupStart());
+        for (int q = 0; q < f->world; q++) {
+            int lo, hi;
+            slab_range((int)f->L, f->world, q, &lo, &hi);
+            double2 *seg = x + (size_t)lo * f->N;
+            SQ_NCCL(g_nccl.Broadcast(seg, seg, (size_t)(hi - lo) * f->N * 2, /*ncclDouble*/ 8, q, (ncclComm_t)f->comm, f->stream));
+        }
+        SQ_NCCL(g_nccl.GroupEnd());
     }
 }
 

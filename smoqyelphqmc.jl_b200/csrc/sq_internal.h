@@ -95,6 +95,10 @@ struct sq_fdm {
     void *mail_ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int mail_ready = 0;
     unsigned long long v3_it_base = 0;       // iteration count carried across multi-GPU solves (slot validity tags)
+    // "sharded solve" mode (one Markov chain over several GPUs): every rank keeps the full state and runs everything but the CG
+    // solves redundantly; a solve is partitioned into tau-slabs [shard_lo, shard_hi) and its solution all-gathered (slab.cu)
+    int sharded = 0, shard_lo = 0, shard_hi = 0;
+    int tuned_shard[3][6] = {{0}, {0}, {0}};   // tuning cache of the slab range while the full range is active (and vice versa)
 
     KParams kparams(int S, int T) const;
     size_t vec_bytes() const { return (size_t)L * N * sizeof(double2); }
@@ -228,5 +232,7 @@ void fdm_sync_if_alive(sq_fdm *f);       // stream-synchronise f if it has not b
 void fdm_halo_exchange(sq_fdm *f, double2 *v);
 void fdm_allreduce_sum(sq_fdm *f, double *d_buf, int count);
 void fdm_cg_slab(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, double tol, i64 maxiter, i64 *iters, double *eps);
+void fdm_cg_sharded(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, double tol, i64 maxiter, i64 *iters, double *eps);
+void slab_set_sharded(sq_fdm *f, int enable);
 void fft_radices(i64 n, std::vector<int> &rad);
 void fft_make_twiddles(i64 n, std::vector<double2> &tw);

@@ -42,6 +42,7 @@ SIGNATURES = {
     "sq_fdm_mailbox_create": [vp, vp],
     "sq_fdm_mailbox_open": [vp, vp],
     "sq_fdm_set_slab_range": [vp, i64, i64],
+    "sq_fdm_set_sharded_solve": [vp, i32],
     "sq_fdm_get_slab": [vp, vp, vp, vp, vp],
     "sq_kpm_create": [pp, vp, f64, i64, f64, f64],
     "sq_kpm_destroy": [vp],

@@ -81,3 +81,47 @@ def test_two_gpu_halo_exchange_and_cg():
         assert out["err_mul_MtM"] < 1e-12 and out["err_mul_M"] < 1e-12 and out["err_mul_Mt"] < 1e-12, out
         assert out["err_cg"] < 1e-10, out
         assert abs(out["iters"][0] - out["iters"][1]) <= 1, out
+
+
+def test_sharded_solve_single_rank_runs_the_same_trajectory():
+    """Sharded-solve mode with world = 1: the operator keeps its full range outside the solves, the solves go through the slab code;
+    a trajectory reproduces the plain one (same seeds) up to the solver tolerance."""
+    from smoqyelph_b200 import api
+    m = mdl.config("cfg1")
+    x0 = m.random_fields(np.random.default_rng(3), smooth=True)
+    out = []
+    for sharded in (False, True):
+        fdm = api.FermionDetMatrix(m, sym=True)
+        elph = api.ElectronPhononParameters(m, fdm)
+        pff = api.PFFCalculator(elph)
+        elph.x = x0
+        elph.update_fdm()
+        if sharded:
+            fdm.init_slab(0, 1)
+            fdm.set_sharded_solve(True)
+            lo, hi = fdm.slab["lo"], fdm.slab["hi"]
+            assert (lo, hi) == (0, m.Ltau)
+        hmc = api.EFAPFFHMCUpdater(elph, pff, Nt=8, seed=11)
+        acc, iters = hmc.hmc_update(tol_action=1e-10, tol_force=1e-8, maxiter=10000)
+        out.append((acc, iters, elph.x.copy()))
+    assert out[0][0] == out[1][0]
+    assert abs(out[0][1] - out[1][1]) <= 1.0
+    assert np.abs(out[0][2] - out[1][2]).max() < 1e-6 * max(1.0, np.abs(out[0][2]).max())
+
+
+def test_two_gpu_sharded_chain():
+    """One chain over 2 GPUs: every rank ends with bit-identical fields, and the chain follows the single-GPU one."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    for name in ("h16", "cfg1"):
+        res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                              "--master-port", "29643", os.path.join(ROOT, "tools", "shard_worker.py"), name, "2", "0"],
+                             env=env, capture_output=True, text=True, timeout=900)
+        assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+        out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
+        assert out["ranks_bit_identical"], out
+        assert out["accept_one_gpu"] == out["accept_sharded"], out
+        assert out["max_abs_dx"] < 1e-3 * max(1.0, out["x_scale"]), out
+        assert all(abs(a - b) <= 1.0 for a, b in zip(out["avg_iters_one_gpu"], out["avg_iters_sharded"])), out
