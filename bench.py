@@ -438,6 +438,32 @@ def run_native(args):
                     "cg_iters_per_s": 1e6 / best if best else None, "speedup_vs_1gpu": us1 / best if best and us1 else None,
                     "comm": "resident kernel per rank; grid-wide sums and boundary slices as device-initiated stores into peer-mapped "
                             "mailboxes (CUDA IPC over NVLink); cg_us_per_iter_nccl_loop = host-launched NCCL send/recv + all-reduces"}
+        # (c) whole trajectories of ONE chain over all GPUs: full state on every rank, CG solves partitioned ("sharded solve")
+        stage[0] = "sharded chain"
+        if usN is not None:
+            try:
+                fdm.set_sharded_solve(True)
+                xs = [x_w if rank == 0 else None]
+                dist.broadcast_object_list(xs, src=0)
+                elph.x = xs[0]
+                elph.update_fdm()
+                hs = api.EFAPFFHMCUpdater(elph, pff, Nt=NT, seed=4242)
+                trajectory(hs)                                # untimed: tunes the kernels for the slab range
+                torch.cuda.synchronize()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    trajectory(hs)
+                torch.cuda.synchronize()
+                tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                rate = args.steps / float(tt.item())
+                tau_slab["chain_over_all_gpus"] = {"trajectories_per_s": rate, "trajectories_per_s_one_gpu": value / world,
+                                                   "speedup_vs_1gpu": rate / (value / world),
+                                                   "note": "cfg4 is half a wave of work per GPU at N = 2: one GPU per chain is the faster "
+                                                           "choice at this size; Ltau = 800 gives 2.0x on 2 GPUs (profiles/README.md)"}
+            except Exception as e:                            # noqa: BLE001
+                tau_slab["chain_over_all_gpus"] = {"error": str(e)}
         dog.cancel()
 
     if rank != 0:
