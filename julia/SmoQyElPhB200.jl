@@ -85,6 +85,22 @@ lmul!(f::FermionDetMatrix, v::AbstractVecOrMat) = mul_MtM!(v, f, v)             
 lmul_M!(f::FermionDetMatrix, v) = mul_M!(v, f, v)
 lmul_Mt!(f::FermionDetMatrix, v) = mul_Mt!(v, f, v)
 
+# ---- one Markov chain over several GPUs (no counterpart in the reference; DESIGN.md section 5) -------------------
+# Every rank builds the same operator with `device = local_rank`; `allgather` / `bcast` are the caller's MPI wrappers
+# (e.g. `x -> MPI.Allgather(x, comm)`, `x -> MPI.bcast(x, 0, comm)`), so this file does not depend on MPI.jl.
+function init_sharded_solve!(f::FermionDetMatrix, rank::Int, world::Int; bcast::Function, allgather::Function)
+    id = zeros(UInt8, 128)
+    rank == 0 && check(ccall((:sq_nccl_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+    id = bcast(id)
+    check(ccall((:sq_fdm_init_slab, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), f.h, rank, world, id))
+    handle = zeros(UInt8, 64)
+    check(ccall((:sq_fdm_mailbox_create, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), f.h, handle))
+    handles = allgather(handle)                       # world x 64 bytes, rank-major
+    check(ccall((:sq_fdm_mailbox_open, LIB), Cint, (Ptr{Cvoid}, Ptr{UInt8}), f.h, handles))
+    check(ccall((:sq_fdm_set_sharded_solve, LIB), Cint, (Ptr{Cvoid}, Cint), f.h, 1))
+    return nothing
+end
+
 # ---- KPMPreconditioner (src/KPMPreconditioner.jl:198-284, 554-597) ----------------------------------------------
 mutable struct KPMPreconditioner{E}
     h::Ptr{Cvoid}; active::Bool; bounds::NTuple{2,E}
