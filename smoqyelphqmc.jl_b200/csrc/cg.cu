@@ -346,7 +346,12 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
     }
     // is the system already solved?  (cheap check folded into the first batch read-back)
     while (!finished) {
-        i64 upto = std::min<i64>(maxiter, it + batch);
+        // preconditioned solves take a few tens of iterations and consecutive solves of a trajectory take about the same number:
+        // the first read-back is placed shortly before the point where the previous solve of this tolerance class converged, later ones
+        // every `batch` iterations
+        i64 step = batch;
+        if (prec && it == 0 && !getenv("SQ_CG_BATCH")) step = std::max<i64>(batch, std::min<i64>((i64)(0.85 * f->prec_iters_hint[tol < 1e-7 ? 0 : 1]), 256));
+        i64 upto = std::min<i64>(maxiter, it + step);
         for (; it < upto; ) {
             it++;
             const CgState *sc = st + cur;
@@ -373,4 +378,5 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
     if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
     *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
     *eps = f->h_cg->eps;
+    if (prec && f->h_cg->done) f->prec_iters_hint[tol < 1e-7 ? 0 : 1] = (int)std::min<i64>(*iters, 1 << 20);
 }

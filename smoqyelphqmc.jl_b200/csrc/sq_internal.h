@@ -80,6 +80,7 @@ struct sq_fdm {
     int slab = 0, threads = 0;
     int tuned[3][6] = {{0}, {0}, {0}};         // per coefficient mode (general / tau-uniform / colour-uniform): valid, slab, threads, v2, v3, v3_S
     int manual_tuning = 0;
+    int prec_iters_hint[2] = {0, 0};         // iterations of the last preconditioned solve (tight / loose tolerance): places the first read-back
     int num_sms = 148;
     size_t smem_optin = 0;
     i64 launches = 0;
