@@ -1,6 +1,6 @@
 """The simulation loop of /root/reference/tutorials/holstein_honeycomb.jl:540-700 on the B200 library (Python twin of the
 Julia shim): thermalisation and measurement sweeps of reflection, swap and EFA-PFF-HMC updates, with the estimator solves,
-the scalar measurements, the time-displaced Green's function and the density / pair / spin correlations on the device.
+the scalar measurements, the time-displaced Green's function and the density / pair / spin / bond / current correlations on the device.
 The model DSL, binning and IO of SmoQyDQMC are replaced by a dictionary of running averages.
 
     python examples/holstein_honeycomb.py [L] [beta] [N_therm] [N_measurements]
@@ -45,8 +45,11 @@ def run_simulation(L=3, beta=4.0, N_therm=20, N_measurements=20, Omega=1.0, alph
     for _ in range(N_therm):
         sweep()
     norb = m.nphonon
-    obs = {"density": 0.0, "double_occ": 0.0, "greens": 0.0, "density_corr": 0.0, "pair_corr": 0.0, "spin_z_corr": 0.0}
+    obs = {"density": 0.0, "double_occ": 0.0, "greens": 0.0, "density_corr": 0.0, "pair_corr": 0.0, "spin_z_corr": 0.0,
+           "bond_corr": 0.0, "current_corr": 0.0}
     zero = (0,) * len(m.lattice_dims)
+    nn_bond = ((0, norb - 1), zero)                          # the A-B bond inside the unit cell
+    t_nn = np.ones((m.Ltau,) + tuple(m.lattice_dims))        # its effective hopping (Holstein: the bare t = 1 on every slice)
     for _ in range(N_measurements):
         sweep()
         meta["measurement_iters"] += g.update_greens_estimator(preconditioner=P, tol=tol)
@@ -57,6 +60,8 @@ def run_simulation(L=3, beta=4.0, N_therm=20, N_measurements=20, Omega=1.0, alph
         obs["density_corr"] += sum(g.measure_density_correlation(a, b) for a in range(norb) for b in range(norb)) / N_measurements
         obs["pair_corr"] += g.measure_pair_correlation(((0, 0), zero), ((0, 0), zero)) / N_measurements     # on-site s-wave, orbital A
         obs["spin_z_corr"] += g.measure_spin_correlation(0, 0) / N_measurements
+        obs["bond_corr"] += g.measure_bond_correlation(nn_bond, nn_bond) / N_measurements
+        obs["current_corr"] += g.measure_current_correlation(nn_bond, nn_bond, t_nn, t_nn) / N_measurements
     n_sweeps = N_therm + N_measurements
     for k in ("hmc_acceptance_rate", "reflection_acceptance_rate", "swap_acceptance_rate", "hmc_iters", "reflection_iters", "swap_iters"):
         meta[k] /= n_sweeps

@@ -78,10 +78,17 @@ __global__ void k_cg_init(CgState *st, const double *part_b, int nb, const doubl
 // pAp_complex != 0: p.Ap is taken from the complex partials (re, im) instead of the real |Mp|^2.
 __global__ void k_cg_update_xr(const CgState *__restrict__ st, double2 *__restrict__ x, double2 *__restrict__ r,
                                const double2 *__restrict__ p, const double2 *__restrict__ z, size_t n,
-                               const double *__restrict__ pAp_part, int npart, int pAp_complex, double *__restrict__ rr_part) {
+                               const double *__restrict__ pAp_part, int npart, int pAp_complex, double *rr_part,
+                               CgState *nxt = nullptr, unsigned *ticket = nullptr, int iter = 0) {
+    // nxt != nullptr (preconditioned loop): the block that finishes last also performs the convergence test of k_cg_check on the
+    // fixed-order sum of the |r|^2 partials, which saves one launch per iteration
     __shared__ double sh[3];
     __shared__ double red[32];
-    if (st->done) return;
+    __shared__ int last;
+    if (st->done) {
+        if (nxt && blockIdx.x == 0 && threadIdx.x == 0) *nxt = *st;
+        return;
+    }
     reduce_partials(pAp_part, npart, pAp_complex ? 2 : 1, sh);
     double2 pAp = make_double2(sh[0], pAp_complex ? sh[1] : 0.0);
     double2 alpha = cdiv(make_double2(st->rz_re, st->rz_im), pAp);
@@ -98,6 +105,29 @@ __global__ void k_cg_update_xr(const CgState *__restrict__ st, double2 *__restri
     double v[1] = {acc};
     block_sum<1>(v, red);
     if (threadIdx.x == 0) rr_part[blockIdx.x] = v[0];
+    if (!nxt) return;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 32) {
+        const volatile double *vp = rr_part;
+        double t = 0;
+        for (int k = threadIdx.x; k < (int)gridDim.x; k += 32) t += vp[k];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) {
+            CgState c = *st;
+            c.eps = sqrt(t) / st->normb;
+            c.iters = iter;
+            c.done = (c.eps < st->tol) ? 1 : 0;
+            if (!(c.eps == c.eps)) c.done = 2;
+            *nxt = c;
+            *ticket = 0;
+        }
+    }
 }
 
 // K_C (P = I): eps = |r|/|b|; stop or beta = rr_new/rr_old, p = r + beta p     (:229-245)
@@ -223,6 +253,7 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
     double *part_b = part, *part_rz = part + 3 * SQ_MAXPART, *part_pAp = part + 6 * SQ_MAXPART, *part_rr = part + 7 * SQ_MAXPART;
     double2 *r = f->r.p, *p = f->p.p, *z = f->z.p;
     CgState *st = f->cg.p;
+    unsigned *ticket = f->cg_ticket.p;
     const bool prec = (kpm != nullptr) && kpm->active;
 
     k_dot_partials<<<G, TB, 0, s>>>(b, b, n, part_b, nullptr);                      // |b|
@@ -345,6 +376,7 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
         return;
     }
     // is the system already solved?  (cheap check folded into the first batch read-back)
+    if (prec) SQ_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), s));
     while (!finished) {
         // preconditioned solves take a few tens of iterations and consecutive solves of a trajectory take about the same number:
         // the first read-back is placed shortly before the point where the previous solve of this tolerance class converged, later ones
@@ -358,15 +390,16 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
             CgState *sn = st + (cur ^ 1);
             int npart = 0;
             fdm_mul_dev(f, SQ_OP_MTM, z, p, part_pAp, &npart, sc);
-            k_cg_update_xr<<<G, TB, 0, s>>>(sc, x, r, p, z, n, part_pAp, npart, 0, part_rr);
             if (!prec) {
+                k_cg_update_xr<<<G, TB, 0, s>>>(sc, x, r, p, z, n, part_pAp, npart, 0, part_rr);
                 k_cg_update_p<<<G, TB, 0, s>>>(sc, sn, p, r, n, part_rr, G, (int)it);
                 f->launches += 2;
             } else {
-                k_cg_check<<<1, 64, 0, s>>>(sc, sn, part_rr, G, (int)it);
+                // x, r update with the convergence test (k_cg_check) done by the last block to finish
+                k_cg_update_xr<<<G, TB, 0, s>>>(sc, x, r, p, z, n, part_pAp, npart, 0, part_rr, sn, ticket, (int)it);
                 int g = kpm_ldiv_dev_dot(kpm, z, r, sn, r, part_rz);      // z = P^-1 r with the r.z partials fused in
                 k_cg_update_p_prec<<<G, TB, 0, s>>>(sn, sc, p, z, n, part_rz, g);
-                f->launches += 3;
+                f->launches += 2;
             }
             cur ^= 1;
         }

@@ -718,6 +718,7 @@ void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt,
         f->iod1.alloc(nreal); f->iod2.alloc(nreal);
         f->part.alloc(8 * SQ_MAXPART);
         f->cg.alloc(2);
+        f->cg_ticket.alloc(4);
         SQ_CUDA(cudaMallocHost((void **)&f->h_cg, 2 * sizeof(CgState)));
         // neutral operator (V = 0, t = 0) so that the autotuner runs on finite numbers
         std::vector<double> ones(V, 1.0);
