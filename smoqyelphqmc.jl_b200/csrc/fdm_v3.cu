@@ -35,6 +35,7 @@
 
 struct V3Params {
     int L, lb, le, S, C;
+    int pre;                // 2: stage the late operands of a task in shared memory with bulk async copies (NAT = 2 kernels)
     int nphase;             // 2 for M^T M, 1 otherwise (a kernel parameter so that the phase loop stays a loop: one copy of B in the code)
     int cls[4];             // bond class of colour c: 0 x-even, 1 x-odd, 2 y-even, 3 y-odd
     int clo[4];
@@ -273,8 +274,14 @@ template <int MODE, int FUSE, int NAT, class G>
 __global__ void __launch_bounds__(256, G::REGS_LIGHT ? 2 : 1)
 k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const double2 *__restrict__ in,
          double *__restrict__ pAp_part, const CgState *__restrict__ skip) {
+    // NAT = 2: native order with the two late operands of a task -- the slice combined after B and the diagonal factors used inside
+    // B -- staged in shared memory by bulk async copies (TMA, one 8 KB copy each) issued before the first load, so that a task waits
+    // for memory once instead of three times
     constexpr int N = G::N, NP = G::NP;
-    extern __shared__ double wsm[];                     // [S][NP][32] double2 (this CTA's part)
+    constexpr bool TMA = (NAT == 2);
+    constexpr int NATB = NAT ? 1 : 0;
+    extern __shared__ __align__(128) double wsm[];      // [S][NP][32] double2 (this CTA's part); TMA: [S + 1] of those + [S + 1][N] diagonal factors
+    __shared__ __align__(8) unsigned long long mbar[8];
     __shared__ double red[32];
     if (skip && skip->done) {
         if (FUSE && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.cg_nxt = *skip;
@@ -283,7 +290,7 @@ k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const do
 #define V3_STAMP(q) do { if (P.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32) P.dbg[q] = clock64(); } while (0)
     V3_STAMP(0);
     G E;
-    E.template init<NAT>(P, blockIdx.y);
+    E.template init<NATB>(P, blockIdx.y);
     const int L = P.L;
     const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
     const int nper = (MODE == 2) ? P.S : P.S + 1;       // output slices per CTA
@@ -330,6 +337,23 @@ k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const do
     const double sg = (lB == 0) ? 1.0 : -1.0;
     const int part = E.part;
     const bool publish = (MODE == 2) && (k < ns);
+    double *evsm = wsm + (size_t)(P.S + 1) * N + (size_t)k * N;
+    double2 *selfsm = reinterpret_cast<double2 *>(wsm) + (size_t)k * NP * 32;
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(&mbar[k]);
+    if (TMA && active) {
+        if (lane == 0) {
+            const unsigned bytes = (unsigned)(N * sizeof(double));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(2 * bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((unsigned)__cvta_generic_to_shared(selfsm)),
+                           "l"(reinterpret_cast<const double *>(in) + ((size_t)lself * 2 + E.part) * N), "r"(bytes), "r"(mb) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((unsigned)__cvta_generic_to_shared(evsm)), "l"(P.expVn + (size_t)lB * N), "r"(bytes), "r"(mb) : "memory");
+        }
+        __syncwarp();
+    }
     double v[G::NV];
     double acc = 0.0;
     // two elements (r, 2 jp), (r, 2 jp + 1) of slice l, this CTA's part; with CG fusion the vector is p = d + beta * in
@@ -375,7 +399,14 @@ k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const do
                 if (P.dbg) { double t = 0; for (int u = 0; u < NP; u++) t += v[2 * u]; if (t == 1.2345e300) P.dbg[15] = 1; }   // wait for the loads
                 V3_STAMP(1);
             }
-            E.template apply_B_ev<NAT, 0>(v, NAT ? P.expVn + (size_t)lB * N + 2 * lane : P.expV + (size_t)lB * N);
+            if (TMA && phase == 0) {                     // both staged operands have landed
+                unsigned ok;
+                do {
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(ok) : "r"(mb) : "memory");
+                } while (!ok);
+            }
+            E.template apply_B_ev<NATB, TMA ? 1 : 0>(v, TMA ? evsm + 2 * lane : (NAT ? P.expVn + (size_t)lB * N + 2 * lane : P.expV + (size_t)lB * N));
             if (P.dbg) { double t = 0; for (int u = 0; u < NP; u++) t += v[2 * u]; if (t == 1.2345e300) P.dbg[15] = 1; }
             V3_STAMP(2 + 3 * phase);
         }
@@ -383,7 +414,7 @@ k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const do
             if (work) {
 #pragma unroll
                 for (int u = 0; u < NP; u++) {
-                    const double2 self = load2(lself, u);
+                    const double2 self = TMA ? selfsm[u * 32 + lane] : load2(lself, u);
                     const double w0 = fma(sg, v[2 * u], self.x), w1 = fma(sg, v[2 * u + 1], self.y);
                     if (MODE == 2) {
                         v[2 * u] = w0; v[2 * u + 1] = w1;
@@ -620,6 +651,7 @@ static v3_kernel_t pick_mode(int mode) {       // mode 3: M^T M with the CG p up
         case 3: return k_fdm_v3<2, 1, 0, V3Lane<LXL, RY>>;
         case 6: return k_fdm_v3<2, 0, 1, V3Lane<LXL, RY>>;
         case 7: return k_fdm_v3<2, 1, 1, V3Lane<LXL, RY>>;
+        case 10: return k_fdm_v3<2, 0, 2, V3Lane<LXL, RY>>;
     }
     return nullptr;
 }
@@ -633,6 +665,7 @@ static v3_kernel_t pick_mode_h(int mode) {
         case 3: return k_fdm_v3<2, 1, 0, H>;
         case 6: return k_fdm_v3<2, 0, 1, H>;
         case 7: return k_fdm_v3<2, 1, 1, H>;
+        case 10: return k_fdm_v3<2, 0, 2, H>;
     }
     return nullptr;
 }
@@ -674,7 +707,7 @@ static bool fdm_v3_detect_honeycomb(sq_fdm *f) {
         if (!ok) continue;
         f->v3_ok = 1; f->v3_kind = 1; f->v3_lxl = L; f->v3_ry = L;
         for (int c = 0; c < 4; c++) f->v3_cls[c] = c;
-        for (int mode : {0, 1, 2, 3, 6, 7})
+        for (int mode : {0, 1, 2, 3, 6, 7, 10})
             SQ_CUDA(cudaFuncSetAttribute(pick3h(L, L, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
         return true;
     }
@@ -718,7 +751,7 @@ void fdm_v3_detect(sq_fdm *f) {
         if (!ok) continue;
         f->v3_ok = 1; f->v3_lxl = LXL; f->v3_ry = RY;
         for (int c = 0; c < 4; c++) f->v3_cls[c] = cls[c];
-        for (int mode : {0, 1, 2, 3, 6, 7})
+        for (int mode : {0, 1, 2, 3, 6, 7, 10})
             SQ_CUDA(cudaFuncSetAttribute(pick3(LXL, RY, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
         return;
     }
@@ -746,6 +779,13 @@ int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, d
         P.cg_beta_complex = g_fuse3->beta_complex; P.cg_iter = g_fuse3->iter; P.cg_check = g_fuse3->check;
     }
     P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = (int)f->C; P.nphase = (mode == 2) ? 2 : 1;
+    {
+        // operand staging by bulk async copies pays once the vectors stream from HBM (measured: 0.52 -> 0.61 of the HBM peak at
+        // 32 x 32 x 6400); while they fit L2 the plain loads are as fast and leave more CTAs per SM.  Tried and dropped: L1 prefetch
+        // hints (slower below 6400 slices), staging only the combined slice (slower than staging both)
+        const char *e = getenv("SQ_V3_PRE");
+        P.pre = e ? atoi(e) : ((size_t)40 * f->N * f->L > ((size_t)100 << 20) ? 2 : 0);
+    }
     for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = c < f->C ? f->clo[c] : 0; }
     P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p;
     static long long *dbg = nullptr;
@@ -761,9 +801,13 @@ int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, d
     }
     const int nper = (mode == 2) ? S : S + 1;
     const int grid = (f->slab_hi - f->slab_lo + nper - 1) / nper;
-    const size_t smem = (mode == 2) ? (size_t)S * f->N * sizeof(double) : 0;
+    size_t smem = (mode == 2) ? (size_t)S * f->N * sizeof(double) : 0;
     if (native) SQ_REQUIRE(mode == 2 && f->v3_expVn.p && f->v3_expv_version == f->coef_version, "native-order operator not prepared");
-    const int kmode = ((mode == 2 && g_fuse3) ? 3 : mode) + (native ? 4 : 0);
+    int kmode = ((mode == 2 && g_fuse3) ? 3 : mode) + (native ? 4 : 0);
+    if (kmode == 6 && P.pre == 2 && (size_t)2 * (S + 1) * f->N * sizeof(double) <= f->smem_optin) {       // TMA-staged operands
+        kmode = 10;
+        smem = (size_t)2 * (S + 1) * f->N * sizeof(double);
+    }
     v3_kernel_t k = f->v3_kind == 1 ? pick3h(f->v3_lxl, f->v3_ry, kmode) : pick3(f->v3_lxl, f->v3_ry, kmode);
     k<<<dim3(grid, 2), 32 * (S + 1), smem, f->stream>>>(P, out, in, part, skip);
     SQ_LAUNCH_CHECK();

@@ -197,7 +197,7 @@ def test_register_path_requires_uniform_colours_and_canonical_order():
     assert relerr(fdm2.mul_MtM(v), ref2.mul_MtM(v)) < RTOL
 
 
-@pytest.mark.parametrize("solver", ["resident", "resident2", "persistent", "launches"])
+@pytest.mark.parametrize("solver", ["resident", "resident2", "persistent", "launches", "launches_tma"])
 @pytest.mark.parametrize("name", ["h16x16", "h32x16", "h32x32", "hc8", "hc24"])
 def test_register_path_cg(name, solver, monkeypatch):
     """CG on the register path in native order: the resident kernels (one / two grid-wide sums per iteration), the
@@ -211,6 +211,9 @@ def test_register_path_cg(name, solver, monkeypatch):
         monkeypatch.setenv("SQ_NO_RESIDENT_CG", "1")
     elif solver == "launches":
         monkeypatch.setenv("SQ_NO_PERSISTENT_CG", "1")
+    elif solver == "launches_tma":                  # first matvec of every solve with the operands staged by bulk async copies
+        monkeypatch.setenv("SQ_NO_PERSISTENT_CG", "1")
+        monkeypatch.setenv("SQ_V3_PRE", "2")
     xr, itr, epsr = ref.cg(b, tol=1e-14, maxiter=20000)
     xg, itg, epsg = fdm.ldiv(b, tol=1e-14, maxiter=20000)
     assert epsg < 1e-14 and epsr < 1e-14
@@ -228,3 +231,27 @@ def test_register_path_cg(name, solver, monkeypatch):
     # warm start from a perturbed solution converges to the same answer
     x2, it2, _ = fdm.ldiv(b, x0=xg * (1 + 1e-3), tol=1e-12)
     assert relerr(x2, xr) < 1e-9 and it2 > 0
+
+
+@pytest.mark.parametrize("name", ["h16x16", "h32x32", "h32x64", "hc8", "hc24"])
+def test_register_path_tma_staging_is_bit_identical(name, monkeypatch):
+    """The stand-alone native-order matvec with its late operands staged in shared memory by bulk async copies (the variant used
+    once the vectors stream from HBM) computes exactly what the plain-load kernel computes, for every slab size."""
+    import torch
+    m, rng, ref, fdm = setup_square(name)
+    n = m.N * m.Ltau
+    d_in = torch.randn(n, 2, dtype=torch.float64, device="cuda")
+    outs = {}
+    for S in (1, 2, 3, 5):
+        fdm.set_fast_path(2 + 256 * S)
+        if fdm.tuning["path"] != 3:
+            continue
+        for pre in ("0", "2"):
+            monkeypatch.setenv("SQ_V3_PRE", pre)
+            d_out = torch.zeros_like(d_in)
+            fdm.time_mul(102, d_out.data_ptr(), d_in.data_ptr(), 2)
+            torch.cuda.synchronize()
+            outs[(S, pre)] = d_out
+        assert torch.equal(outs[(S, "0")], outs[(S, "2")]), (name, S)
+        assert float(outs[(S, "0")].abs().max()) > 0
+    assert outs

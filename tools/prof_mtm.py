@@ -5,7 +5,7 @@ import numpy as np, torch
 from smoqyelph_b200 import model as mdl, api
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
 op = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-m = mdl.config(name)
+m = mdl.holstein_square(*[int(q) for q in name.split(":")[1:3]], float(name.split(":")[3])) if name.startswith("sq:") else mdl.config(name)   # sq:Lx:Ly:beta
 rng = np.random.default_rng(0)
 fdm = api.FermionDetMatrix(m, sym=True)
 elph = api.ElectronPhononParameters(m, fdm)

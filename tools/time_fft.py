@@ -2,7 +2,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, ctypes as C
 from smoqyelph_b200 import model as mdl, api, lib
-m = mdl.config("cfg4")
+m = mdl.config(sys.argv[1] if len(sys.argv) > 1 else "cfg4")
 fdm = api.FermionDetMatrix(m, sym=True)
 P = api.KPMPreconditioner(fdm, update=False)
 L = lib.load()

@@ -34,5 +34,5 @@ for Lx, Ly, beta in ((32, 32, 20.0), (32, 32, 40.0), (32, 32, 80.0), (32, 32, 16
                       "us_back_to_back": round(best[1], 2), "us_l2_flushed": round(cold, 2), "algorithmic_MB": round(B / 1e6, 2),
                       "GBs_back_to_back": round(B / best[1] / 1e3), "frac_back_to_back": round(B / best[1] / 1e3 / peak, 3),
                       "GBs_l2_flushed": round(B / cold / 1e3), "frac_l2_flushed": round(B / cold / 1e3 / peak, 3),
-                      "fp64_issue_floor_us": round(2 * m.Ltau * m.N * 2 * 36 / (148 * 64 * 1.965e3), 2)}), flush=True)
+                      "fp64_issue_floor_us": round(36 * m.Ltau * m.N / (148 * 64 * 1.965e3), 2)}), flush=True)
     del fdm, elph
