@@ -304,6 +304,13 @@ def run_native(args):
 
     roofline = None
     iters_per_traj = iters_total / args.steps
+    per_rank = None
+    if dist is not None:
+        # the chains differ (seed + rank), so do their CG iteration counts: the job time is the slowest chain's
+        pr = torch.tensor([ms_dev / args.steps, iters_per_traj], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(pr) for _ in range(world)]
+        dist.all_gather(allr, pr)
+        per_rank = {"ms_per_step": [round(float(q[0]), 2) for q in allr], "cg_iters_per_trajectory": [round(float(q[1]), 1) for q in allr]}
     matvecs_per_traj = iters_per_traj + 2 * (NT + 1)
     if rank == 0:
         # ---- roofline, rank 0.  Two kernels matter: the fused M^T M v kernel on its own (what north_star names), timed by
@@ -374,7 +381,7 @@ def run_native(args):
                 "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": nx * 8, "d2h_bytes_per_step": nx * 8 + 64},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "cg_iters_per_trajectory": iters_per_traj, "matvecs_per_trajectory": matvecs_per_traj,
-                "acceptance": accepted / args.steps, "tau_slab": tau_slab}
+                "acceptance": accepted / args.steps, "per_rank": per_rank, "tau_slab": tau_slab}
         emit(line)
 
     tau_slab = None
