@@ -235,7 +235,7 @@ def run_native(args):
     elph = api.ElectronPhononParameters(m, fdm)
     pff = api.PFFCalculator(elph)
     P = api.KPMPreconditioner(fdm, update=False) if precond else None
-    elph.x = cdw_start(m, 1000 + rank)
+    elph.x = cdw_start(m, 1000)                              # every chain starts from the same relaxed configuration ...
     elph.update_fdm()
     stream = torch.cuda.ExternalStream(fdm.stream, device=dev)
     L = lib.load()
@@ -247,7 +247,7 @@ def run_native(args):
         return bool(acc.value), info
 
     # ---- warm-up (untimed): relaxes the synthetic start, warms the caches and the clocks
-    hmc = api.EFAPFFHMCUpdater(elph, pff, Nt=NT, seed=77 + rank)
+    hmc = api.EFAPFFHMCUpdater(elph, pff, Nt=NT, seed=77)
     for _ in range(args.warmup):
         trajectory(hmc)
     x_w = elph.x                                             # state every timed leg starts from
@@ -255,7 +255,7 @@ def run_native(args):
     def fresh_updater():
         elph.x = x_w
         elph.update_fdm()
-        return api.EFAPFFHMCUpdater(elph, pff, Nt=NT, seed=4242 + rank)
+        return api.EFAPFFHMCUpdater(elph, pff, Nt=NT, seed=4242 + rank)      # ... and samples with its own seed (seed + rank)
 
     # ---- value: K trajectories, x resident in HBM, timed with CUDA events on the library stream
     h = fresh_updater()
