@@ -150,3 +150,42 @@ def test_global_move_sampling_helpers():
     import pytest
     with pytest.raises(api.SqError):
         api._sample_phonon_mode(rng, m, phonon_types=[2])    # only frozen modes: nothing to propose
+
+
+def test_julia_shim_binds_only_declared_symbols_with_matching_arity():
+    """julia/SmoQyElPhB200.jl cannot be executed here (no Julia in the image): at least every `ccall` in it must name a function
+    the header declares, with as many argument types as the C prototype has parameters."""
+    import re
+    from smoqyelph_b200 import lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "julia", "SmoQyElPhB200.jl"), encoding="utf-8").read()
+    hdr = re.sub(r"/\*.*?\*/", "", open(lib.HEADER).read(), flags=re.S)
+    protos = {}
+    for mm in re.finditer(r"\b(sq_[A-Za-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = mm.group(2).strip()
+        protos[mm.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    calls = list(re.finditer(r"ccall\(\(:(sq_[A-Za-z0-9_]+), LIB\),\s*[A-Za-z{}\.]+,\s*\(", src))
+    assert len(calls) > 30
+    for mm in calls:
+        name = mm.group(1)
+        assert name in protos, f"{name} is not declared in the header"
+        # the argument-type tuple: balanced parentheses from the match end
+        i, depth, start = mm.end(), 1, mm.end()
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        tup = src[start:i - 1]
+        # split on top-level commas only
+        parts, d, cur = [], 0, ""
+        for ch in tup:
+            if ch in "({[":
+                d += 1
+            elif ch in ")}]":
+                d -= 1
+            if ch == "," and d == 0:
+                parts.append(cur); cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            parts.append(cur)
+        assert len(parts) == protos[name], f"{name}: {len(parts)} argument types in the shim, {protos[name]} parameters in the header"
