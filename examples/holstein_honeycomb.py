@@ -19,10 +19,10 @@ from smoqyelph_b200 import api, model as mdl
 
 
 def run_simulation(L=3, beta=4.0, N_therm=20, N_measurements=20, Omega=1.0, alpha=1.5, mu=0.0, Nt=8, Nrv=10, tol=1e-10, seed=0,
-                   use_preconditioner=False):
+                   use_preconditioner=False, device=0):
     rng = np.random.default_rng(seed)
     m = mdl.holstein_honeycomb(L, beta, Omega=Omega, alpha=alpha, mu=mu)
-    fdm = api.SymFermionDetMatrix(m, tol=tol, maxiter=10000)
+    fdm = api.SymFermionDetMatrix(m, tol=tol, maxiter=10000, device=device)
     elph = api.ElectronPhononParameters(m, fdm)
     elph.x = mdl.thermal_fields(m, rng)
     elph.update_fdm()
