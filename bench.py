@@ -397,80 +397,84 @@ def run_native(args):
         dog = threading.Timer(240.0, bail)
         dog.daemon = True
         dog.start()
-        n = m.N * m.Ltau
-        d_b = torch.randn(n, 2, dtype=torch.float64, device=dev)
-        d_x = torch.zeros_like(d_b)
-        nit = 400
+        try:
+            n = m.N * m.Ltau
+            d_b = torch.randn(n, 2, dtype=torch.float64, device=dev)
+            d_x = torch.zeros_like(d_b)
+            nit = 400
 
-        def timed_cg():
-            """us per iteration (max over ranks), or None if any rank failed -- every rank always takes part in the collectives"""
-            bad = 0.0
-            try:
-                fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=40)
-            except Exception as e:                            # noqa: BLE001
-                bad = 1.0
-                sys.stderr.write("rank %d: tau-slab CG failed at stage %s: %s\n" % (rank, stage[0], e))
-            barrier()
-            t0 = time.perf_counter()
-            if not bad:
+            def timed_cg():
+                """us per iteration (max over ranks), or None if any rank failed -- every rank always takes part in the collectives"""
+                bad = 0.0
                 try:
-                    fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=nit)
-                    torch.cuda.synchronize()
-                except Exception as e:                        # noqa: BLE001
+                    fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=40)
+                except Exception as e:                            # noqa: BLE001
                     bad = 1.0
                     sys.stderr.write("rank %d: tau-slab CG failed at stage %s: %s\n" % (rank, stage[0], e))
-            dt = time.perf_counter() - t0
-            tt = torch.tensor([dt, bad], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            return None if tt[1].item() > 0 else float(tt[0].item()) / nit * 1e6
-
-        stage[0] = "one GPU"
-        us1 = timed_cg()
-        ids = [api.FermionDetMatrix.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        fdm.init_slab(rank, world, ids[0])
-        stage[0] = "NCCL loop"
-        os.environ["SQ_NO_RESIDENT_CG"] = "1"                 # (a) host-launched NCCL loop
-        us_nccl = timed_cg()
-        del os.environ["SQ_NO_RESIDENT_CG"]
-        stage[0] = "mailboxes"
-        handles = [None] * world                              # (b) resident kernels + peer-mapped mailboxes (CUDA IPC over NVLink)
-        dist.all_gather_object(handles, fdm.mailbox_handle())
-        fdm.mailbox_open(handles)
-        stage[0] = "resident"
-        usN = timed_cg() if us_nccl is not None else None
-        best = min([u for u in (usN, us_nccl) if u is not None], default=None)
-        tau_slab = {"what": "unpreconditioned CG iterations on M^T M, cfg4, tau-slab partitioned (strong scaling)",
-                    "cg_us_per_iter_1gpu": us1, "cg_us_per_iter": usN, "cg_us_per_iter_nccl_loop": us_nccl, "n_gpus": world,
-                    "cg_iters_per_s": 1e6 / best if best else None, "speedup_vs_1gpu": us1 / best if best and us1 else None,
-                    "comm": "resident kernel per rank; grid-wide sums and boundary slices as device-initiated stores into peer-mapped "
-                            "mailboxes (CUDA IPC over NVLink); cg_us_per_iter_nccl_loop = host-launched NCCL send/recv + all-reduces"}
-        # (c) whole trajectories of ONE chain over all GPUs: full state on every rank, CG solves partitioned ("sharded solve")
-        stage[0] = "sharded chain"
-        if usN is not None:
-            try:
-                fdm.set_sharded_solve(True)
-                xs = [x_w if rank == 0 else None]
-                dist.broadcast_object_list(xs, src=0)
-                elph.x = xs[0]
-                elph.update_fdm()
-                hs = api.EFAPFFHMCUpdater(elph, pff, Nt=NT, seed=4242)
-                trajectory(hs)                                # untimed: tunes the kernels for the slab range
-                torch.cuda.synchronize()
                 barrier()
                 t0 = time.perf_counter()
-                for _ in range(args.steps):
-                    trajectory(hs)
-                torch.cuda.synchronize()
-                tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+                if not bad:
+                    try:
+                        fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=nit)
+                        torch.cuda.synchronize()
+                    except Exception as e:                        # noqa: BLE001
+                        bad = 1.0
+                        sys.stderr.write("rank %d: tau-slab CG failed at stage %s: %s\n" % (rank, stage[0], e))
+                dt = time.perf_counter() - t0
+                tt = torch.tensor([dt, bad], dtype=torch.float64, device=dev)
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                rate = args.steps / float(tt.item())
-                tau_slab["chain_over_all_gpus"] = {"trajectories_per_s": rate, "trajectories_per_s_one_gpu": value / world,
-                                                   "speedup_vs_1gpu": rate / (value / world),
-                                                   "note": "cfg4 is half a wave of work per GPU at N = 2: one GPU per chain is the faster "
-                                                           "choice at this size; Ltau = 800 gives 2.0x on 2 GPUs (profiles/README.md)"}
-            except Exception as e:                            # noqa: BLE001
-                tau_slab["chain_over_all_gpus"] = {"error": str(e)}
+                return None if tt[1].item() > 0 else float(tt[0].item()) / nit * 1e6
+
+            stage[0] = "one GPU"
+            us1 = timed_cg()
+            ids = [api.FermionDetMatrix.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            fdm.init_slab(rank, world, ids[0])
+            stage[0] = "NCCL loop"
+            os.environ["SQ_NO_RESIDENT_CG"] = "1"                 # (a) host-launched NCCL loop
+            us_nccl = timed_cg()
+            del os.environ["SQ_NO_RESIDENT_CG"]
+            stage[0] = "mailboxes"
+            handles = [None] * world                              # (b) resident kernels + peer-mapped mailboxes (CUDA IPC over NVLink)
+            dist.all_gather_object(handles, fdm.mailbox_handle())
+            fdm.mailbox_open(handles)
+            stage[0] = "resident"
+            usN = timed_cg() if us_nccl is not None else None
+            best = min([u for u in (usN, us_nccl) if u is not None], default=None)
+            tau_slab = {"what": "unpreconditioned CG iterations on M^T M, cfg4, tau-slab partitioned (strong scaling)",
+                        "cg_us_per_iter_1gpu": us1, "cg_us_per_iter": usN, "cg_us_per_iter_nccl_loop": us_nccl, "n_gpus": world,
+                        "cg_iters_per_s": 1e6 / best if best else None, "speedup_vs_1gpu": us1 / best if best and us1 else None,
+                        "comm": "resident kernel per rank; grid-wide sums and boundary slices as device-initiated stores into peer-mapped "
+                                "mailboxes (CUDA IPC over NVLink); cg_us_per_iter_nccl_loop = host-launched NCCL send/recv + all-reduces"}
+            # (c) whole trajectories of ONE chain over all GPUs: full state on every rank, CG solves partitioned ("sharded solve")
+            stage[0] = "sharded chain"
+            if usN is not None:
+                try:
+                    fdm.set_sharded_solve(True)
+                    xs = [x_w if rank == 0 else None]
+                    dist.broadcast_object_list(xs, src=0)
+                    elph.x = xs[0]
+                    elph.update_fdm()
+                    hs = api.EFAPFFHMCUpdater(elph, pff, Nt=NT, seed=4242)
+                    trajectory(hs)                                # untimed: tunes the kernels for the slab range
+                    torch.cuda.synchronize()
+                    barrier()
+                    t0 = time.perf_counter()
+                    for _ in range(args.steps):
+                        trajectory(hs)
+                    torch.cuda.synchronize()
+                    tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    rate = args.steps / float(tt.item())
+                    tau_slab["chain_over_all_gpus"] = {"trajectories_per_s": rate, "trajectories_per_s_one_gpu": value / world,
+                                                       "speedup_vs_1gpu": rate / (value / world),
+                                                       "note": "cfg4 is half a wave of work per GPU at N = 2: one GPU per chain is the faster "
+                                                               "choice at this size; Ltau = 800 gives 2.0x on 2 GPUs (profiles/README.md)"}
+                except Exception as e:                            # noqa: BLE001
+                    tau_slab["chain_over_all_gpus"] = {"error": str(e)}
+        except Exception as e:                                # noqa: BLE001  (a rank that fails here must still print / exit cleanly)
+            sys.stderr.write("rank %d: tau-slab section failed at stage %s: %s\n" % (rank, stage[0], e))
+            tau_slab = {"error": "stage '%s': %s" % (stage[0], e)}
         dog.cancel()
 
     if rank != 0:
