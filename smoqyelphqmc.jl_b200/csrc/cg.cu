@@ -377,6 +377,48 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
     }
     // is the system already solved?  (cheap check folded into the first batch read-back)
     if (prec) SQ_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), s));
+    const bool fuse_v3 = f->path == 0 && f->use_v3 && fdm_v3_supported(f, f->v3_S);
+    const bool fuse_v2 = f->path == 0 && !fuse_v3 && f->use_v2 && fdm_v2_supported(f, 2, f->slab, f->threads);
+    // (pays while the iteration is launch-bound; at cfg4 -- 410k elements -- the fused kernel's extra strided loads cost more than
+    // the launch it saves: measured 197 against 192 us per iteration)
+    if (prec && (fuse_v3 || fuse_v2) && n <= 200000 && !getenv("SQ_NO_CG_FUSION")) {
+        // Preconditioned iteration in five launches: the fused matvec forms p = z + beta p on load (beta = (r.z)_new / (r.z)_old
+        // from the partials the inverse FFT left behind) and writes M^T M p to its own buffer; the x / r update carries the
+        // convergence test; then FFT, Chebyshev, inverse FFT.  States: A = st[0] is read by the x / r update and written by the
+        // matvec, B = st[1] the other way round, so no kernel reads a state another block of the same kernel writes.
+        if (f->prec_q.n < n) f->prec_q.alloc(n, false);
+        double2 *q = f->prec_q.p, *pb[2] = {p, f->tmp1.p};
+        CgState *A = st, *B = st + 1;
+        int pc = 0, g = 0;
+        while (!finished) {
+            i64 step = batch;
+            if (it == 0 && !getenv("SQ_CG_BATCH")) step = std::max<i64>(batch, std::min<i64>((i64)(0.85 * f->prec_iters_hint[tol < 1e-7 ? 0 : 1]), 256));
+            const i64 upto = std::min<i64>(maxiter, it + step);
+            for (; it < upto;) {
+                it++;
+                int npart = 0;
+                if (it == 1) {
+                    fdm_mul_dev(f, SQ_OP_MTM, q, pb[pc], part_pAp, &npart, A);
+                } else {
+                    npart = fuse_v3 ? fdm_v3_launch_cg(f, q, pb[pc], pb[pc ^ 1], z, B, A, part_rr, G, part_rz, g, 1, (int)it, 0, part_pAp, false)
+                                    : fdm_v2_launch_cg(f, q, pb[pc], pb[pc ^ 1], z, B, A, part_rr, G, part_rz, g, 1, (int)it, 0, part_pAp);
+                    pc ^= 1;
+                }
+                k_cg_update_xr<<<G, TB, 0, s>>>(A, x, r, pb[pc], q, n, part_pAp, npart, 0, part_rr, B, ticket, (int)it);
+                g = kpm_ldiv_dev_dot(kpm, z, r, B, r, part_rz);
+                f->launches += 1;
+            }
+            SQ_LAUNCH_CHECK();
+            SQ_CUDA(cudaMemcpyAsync(f->h_cg, B, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+            SQ_CUDA(cudaStreamSynchronize(s));
+            if (f->h_cg->done || it >= maxiter) finished = true;
+        }
+        if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+        *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
+        *eps = f->h_cg->eps;
+        if (f->h_cg->done) f->prec_iters_hint[tol < 1e-7 ? 0 : 1] = (int)std::min<i64>(*iters, 1 << 20);
+        return;
+    }
     while (!finished) {
         // preconditioned solves take a few tens of iterations and consecutive solves of a trajectory take about the same number:
         // the first read-back is placed shortly before the point where the previous solve of this tolerance class converged, later ones

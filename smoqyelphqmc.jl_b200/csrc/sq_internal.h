@@ -72,6 +72,7 @@ struct sq_fdm {
     DevBuf<double> iod1, iod2;               // real staging
     DevBuf<double> part;                     // 8 * SQ_MAXPART partial sums
     DevBuf<CgState> cg;                      // 2 states
+    DevBuf<double2> prec_q;                  // M^T M p of the preconditioned solver when the p update is fused into the matvec (lazy)
     DevBuf<unsigned> cg_ticket;              // arrival counter of the last-block convergence test (zero between launches)
     CgState *h_cg = nullptr;                 // pinned
     double tol = 1e-6;
