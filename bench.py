@@ -59,10 +59,41 @@ def cdw_start(m, seed):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML from a thread of this process (no second process
+    touching the GPU while a latency-bound resident kernel runs), `nvidia-smi -lms` as the fallback."""
     FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
+        import threading
+        self.p, self.thread, self.samples, self.stop_flag = None, None, [], threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+            except Exception:                                 # noqa: BLE001
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            reasons_fn(h)
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), int(reasons_fn(h))))
+                    except Exception:                         # noqa: BLE001
+                        pass
+                    self.stop_flag.wait(0.1)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:                                     # noqa: BLE001
+            self.thread = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
@@ -72,6 +103,16 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if self.samples:
+                bits = 0
+                for _, r in self.samples:
+                    bits |= r
+                out = {"sm_mhz": float(np.median([c for c, _ in self.samples])), "sm_max_mhz": self.max_mhz,
+                       "reasons": sorted(nm for bit, nm in self.REASONS.items() if bits & bit), "samples": len(self.samples), "source": "nvml"}
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -97,7 +138,7 @@ class ClockSampler:
                     reasons.add(nm)
         os.unlink(self.f.name)
         if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
         return out
 
 
