@@ -189,3 +189,13 @@ def test_julia_shim_binds_only_declared_symbols_with_matching_arity():
         if cur.strip():
             parts.append(cur)
         assert len(parts) == protos[name], f"{name}: {len(parts)} argument types in the shim, {protos[name]} parameters in the header"
+
+
+def test_clock_sampler_degrades_without_a_gpu():
+    """bench.ClockSampler must never raise: NVML first, nvidia-smi second, empty result otherwise."""
+    import importlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    bench = importlib.import_module("bench")
+    out = bench.ClockSampler(0).stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
