@@ -223,6 +223,8 @@ int sq_greens_weighted_density(sq_greens *g, const double *w, sq_complex *out);
 int sq_greens_weighted_bonds(sq_greens *g, int64_t nbonds, const int64_t *bonds, const sq_complex *w, sq_complex *out);
 /* measure_n(greens_estimator, orbital)  src/Measurements/scalar_measurements.jl:2-12 */
 int sq_greens_measure_n_orbital(sq_greens *g, int norb, int a, sq_complex *n);
+/* measure_double_occ(greens_estimator, orbital)  src/Measurements/scalar_measurements.jl:98-109 (normalised by the total V, as there) */
+int sq_greens_measure_double_occ_orbital(sq_greens *g, int norb, int a, sq_complex *d);
 /* update_chemical_potential! minus the MuTuner scalar logic (stays in Julia): returns n, N^2 then
  * applies the new mu via sq_elph_shift_mu + sq_elph_refresh_fdm.  src/update_chemical_potential.jl:21-73 */
 

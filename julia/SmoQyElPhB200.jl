@@ -383,6 +383,22 @@ function measure_n(g::GreensEstimator{E}, orbital::Int; n::Int) where {E}
     check(ccall((:sq_greens_measure_n_orbital, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Complex{E}}), g.h, n, orbital, out))
     return out[1]
 end
+function measure_double_occ(g::GreensEstimator{E}, orbital::Int; n::Int) where {E}      # scalar_measurements.jl:98-109
+    out = zeros(Complex{E}, 1)
+    check(ccall((:sq_greens_measure_double_occ_orbital, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Complex{E}}), g.h, n, orbital, out))
+    return out[1]
+end
+# make_measurements!(measurement_container, fdm, greens_estimator; ...) -> iters  (src/Measurements/make_measurements.jl:19-90).
+# The estimator refresh runs on the device; the accumulation into SmoQyDQMC's container is the reference's own host code
+# (make_global_measurements!, make_local_measurements!, make_correlation_measurements!, :92-913), which only calls the measure_*
+# methods this module provides -- it is passed in as `accumulate!` so that this file does not duplicate it.
+function make_measurements!(measurement_container, f::FermionDetMatrix{T,E}, g::GreensEstimator{E}; model_geometry, fermion_path_integral,
+                            tight_binding_parameters, electron_phonon_parameters, preconditioner = I, rng::AbstractRNG = Random.default_rng(),
+                            tol::E = f.cgs.tol, maxiter::Int = f.cgs.maxiter, accumulate!::Function = (args...) -> nothing) where {T,E}
+    iters = update_greens_estimator!(g, f; preconditioner, rng, tol, maxiter)
+    accumulate!(measurement_container, g, model_geometry, tight_binding_parameters, electron_phonon_parameters, fermion_path_integral)
+    return iters
+end
 measure_n(g::GreensEstimator) = _measure(g)[1]
 measure_double_occ(g::GreensEstimator) = _measure(g)[2]
 measure_Nsqrd(g::GreensEstimator) = _measure(g)[3]

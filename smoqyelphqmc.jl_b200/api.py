@@ -519,6 +519,13 @@ class GreensEstimator:
                                + mc("G0D_GD0", (d, a, b, c), (z, r1, z, r2)) - mc("G0D_GD0", (c, a, b, d), (r2, r1, z, z)))
         return CC
 
+    def measure_double_occ_orbital(self, a, norb=None, dims=None):
+        """measure_double_occ(greens_estimator, orbital) (scalar_measurements.jl:98-109; normalised by the total N Ltau as there)."""
+        norb, dims = self._geom(norb, dims)
+        out = np.zeros(2)
+        check(self.L.sq_greens_measure_double_occ_orbital(self.h, norb, int(a) + 1, ptr(out)))
+        return complex(out[0], out[1])
+
     def measure_n_orbital(self, a, norb=None, dims=None):
         norb, dims = self._geom(norb, dims)
         out = np.zeros(2)
@@ -616,6 +623,54 @@ class GreensEstimator:
         out = np.zeros((3, 2))
         check(self.L.sq_greens_measure(self.h, ptr(out[0]), ptr(out[1]), ptr(out[2])))
         return {"n": complex(*out[0]), "double_occ": complex(*out[1]), "Nsqrd": complex(*out[2])}
+
+
+def make_measurements(measurements, fdm, greens, *, mu=0.0, bosonic_action=None, preconditioner=None, tol=1e-10, maxiter=10000,
+                      correlations=(), norb=None, dims=None):
+    """make_measurements!(measurement_container, fdm, greens_estimator; ...) -> iters  (src/Measurements/make_measurements.jl:19-90) with a
+    plain dictionary in place of SmoQyDQMC's container: refreshes the estimator (update_greens_estimator!), then ADDS this
+    configuration's values to `measurements` (created on first use):
+      "global"       make_global_measurements! (:93-117): sgn, density_up / density_dn / density, double_occ, Nsqrd, chemical_potential,
+                     action_bosonic (if `bosonic_action` is given: a number or a callable)
+      "local"        the density part of make_local_measurements! (:120-146): density_up / density_dn / density / double_occ per orbital
+      "correlations" one array per entry of `correlations`: ("greens", (a, b)), ("density", (a, b)), ("spin_z", (a, b)),
+                     ("pair", (bond', bond'')), ("bond", (bond', bond'')), ("current", (bond', bond'', t', t'')) -- the calls of
+                     make_correlation_measurements! (:161-394); the caller divides by the number of calls, as the container's
+                     processing does."""
+    iters = greens.update_greens_estimator(preconditioner=preconditioner, tol=tol, maxiter=maxiter)
+    norb, dims = greens._geom(norb, dims)
+    G = measurements.setdefault("global", {})
+    s = greens.measure()
+    add = lambda d, k, v: d.__setitem__(k, d.get(k, 0.0) + v)
+    add(G, "sgn", 1.0)
+    add(G, "density_up", s["n"]); add(G, "density_dn", s["n"]); add(G, "density", 2 * s["n"])
+    add(G, "double_occ", s["double_occ"]); add(G, "Nsqrd", s["Nsqrd"]); add(G, "chemical_potential", mu)
+    if bosonic_action is not None:
+        add(G, "action_bosonic", bosonic_action() if callable(bosonic_action) else bosonic_action)
+    Lm = measurements.setdefault("local", {k: np.zeros(norb, complex) for k in ("density_up", "density_dn", "density", "double_occ")})
+    for a in range(norb):
+        n = greens.measure_n_orbital(a, norb, dims)
+        Lm["density_up"][a] += n; Lm["density_dn"][a] += n; Lm["density"][a] += 2 * n
+        Lm["double_occ"][a] += greens.measure_double_occ_orbital(a, norb, dims)
+    Cm = measurements.setdefault("correlations", {})
+    for name, args in correlations:
+        key = (name,) + tuple(repr(a) if isinstance(a, np.ndarray) else a for a in args[:2])
+        if name == "greens":
+            val = greens.measure_GD0(tuple(args), norb=norb, dims=dims)
+        elif name == "density":
+            val = greens.measure_density_correlation(args[0], args[1], norb=norb, dims=dims)
+        elif name == "spin_z":
+            val = greens.measure_spin_correlation(args[0], args[1], norb=norb, dims=dims)
+        elif name == "pair":
+            val = greens.measure_pair_correlation(args[0], args[1], norb=norb, dims=dims)
+        elif name == "bond":
+            val = greens.measure_bond_correlation(args[0], args[1], norb=norb, dims=dims)
+        elif name == "current":
+            val = greens.measure_current_correlation(args[0], args[1], args[2], args[3], norb=norb, dims=dims)
+        else:
+            raise ValueError("unknown correlation " + str(name))
+        Cm[key] = Cm.get(key, 0.0) + val
+    return iters
 
 
 def update_chemical_potential(fdm, greens, elph, mu, mu_new_fn, preconditioner=None, update_greens_estimator=True, tol=1e-10, maxiter=10000):

@@ -57,6 +57,7 @@ double hmc_kinetic_dev(sq_hmc *h, const double *pm);
 void greens_create_impl(sq_greens **out, sq_fdm *f, i64 Nrv, uint64_t seed);
 double greens_update_impl(sq_greens *g, sq_kpm *kpm, const void *h_R, double tol, i64 maxiter);
 void greens_measure_impl(sq_greens *g, double *out);
+void greens_measure_double_occ_orbital_impl(sq_greens *g, int norb, int a, double *out);
 void greens_measure_c4_impl(sq_greens *g, int kind, int norb, int ndim, const i64 *dims, const int *orb, const i64 *r, void *h_out,
                             const double *h_tD, const double *h_t0);
 void greens_measure_n_orbital_impl(sq_greens *g, int norb, int a, double *out);
@@ -711,6 +712,12 @@ int sq_greens_measure_contraction_weighted(sq_greens *g, int kind, int norb, int
     SQ_TRY
     SQ_REQUIRE(g && out, "NULL argument");
     greens_measure_c4_impl(g, kind, norb, ndim, dims, orbitals, r, out, tD, t0);
+    SQ_CATCH
+}
+int sq_greens_measure_double_occ_orbital(sq_greens *g, int norb, int a, sq_complex *d) {
+    SQ_TRY
+    SQ_REQUIRE(g && d, "NULL argument");
+    greens_measure_double_occ_orbital_impl(g, norb, a, (double *)d);
     SQ_CATCH
 }
 int sq_greens_measure_n_orbital(sq_greens *g, int norb, int a, sq_complex *n) {

@@ -41,10 +41,13 @@ __global__ void k_cross_dots(const double2 *__restrict__ R, const double2 *__res
     }
 }
 // double occupancy: sum_r [ (sum_i a_i)^2 - sum_i a_i^2 ] / 2 with a_i = 1 - GR_i conj(R_i)  (pairs i<j of :130-145)
-__global__ void k_double_occ(const double2 *__restrict__ R, const double2 *__restrict__ GR, size_t V, int Nrv, double *__restrict__ part) {
+// norb > 0: only the sites of orbital `orb` (site % norb == orb) contribute (measure_double_occ(greens_estimator, orbital), :98-109)
+__global__ void k_double_occ(const double2 *__restrict__ R, const double2 *__restrict__ GR, size_t V, int Nrv, double *__restrict__ part,
+                             int N = 1, int norb = 0, int orb = 0) {
     __shared__ double red[2 * 32];
     double v[2] = {0, 0};
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < V; k += (size_t)gridDim.x * blockDim.x) {
+        if (norb > 0 && (int)((k % N) % norb) != orb) continue;
         double2 s1 = make_double2(0, 0), s2 = make_double2(0, 0);
         for (int i = 0; i < Nrv; i++) {
             double2 r = R[(size_t)i * V + k], g = GR[(size_t)i * V + k];
@@ -396,6 +399,30 @@ void greens_measure_n_orbital_impl(sq_greens *g, int norb, int a, double *out) {
     c4_mean_GR_Rt(g, G, a - 1, z, a - 1, &re, &im);
     out[0] = 1.0 - re;
     out[1] = -im;
+}
+
+// measure_double_occ(greens_estimator, orbital)  (scalar_measurements.jl:98-109): the pair average restricted to the sites of one
+// orbital, divided -- as the reference does -- by the TOTAL number of space-time points V
+void greens_measure_double_occ_orbital_impl(sq_greens *g, int norb, int a, double *out) {
+    sq_fdm *f = g->f;
+    SQ_CUDA(cudaSetDevice(f->device));
+    SQ_REQUIRE(norb >= 1 && a >= 1 && a <= norb && f->N % norb == 0, "bad orbital");
+    const size_t V = (size_t)f->L * f->N;
+    const int Nrv = (int)g->Nrv, nb = SQ_MAXPART / 4;
+    out[0] = out[1] = 0.0;
+    if (Nrv < 2) return;
+    double *pd = g->part.p + (size_t)2 * 64 * Nrv * Nrv;
+    k_double_occ<<<nb, 256, 0, f->stream>>>(g->R.p, g->GR.p, V, Nrv, pd, (int)f->N, norb, a - 1);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+    std::vector<double> hd(2 * nb);
+    SQ_CUDA(cudaMemcpyAsync(hd.data(), pd, hd.size() * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
+    double dr = 0, di = 0;
+    for (int b = 0; b < nb; b++) { dr += hd[2 * b]; di += hd[2 * b + 1]; }
+    const double npairs = 0.5 * Nrv * (Nrv - 1);
+    out[0] = dr / ((double)V * npairs);
+    out[1] = di / ((double)V * npairs);
 }
 
 // h_out: (Ltau + 1) x cells complex, tau fastest.  orb[4] 1-based orbitals (a, b, c, d); r: 4 x ndim static displacements.

@@ -92,6 +92,7 @@ SIGNATURES = {
     "sq_greens_measure_contraction": [vp, i32, i32, i32, vp, vp, vp, vp],
     "sq_greens_measure_contraction_weighted": [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     "sq_greens_measure_n_orbital": [vp, i32, i32, vp],
+    "sq_greens_measure_double_occ_orbital": [vp, i32, i32, vp],
     "sq_greens_weighted_density": [vp, vp, vp],
     "sq_greens_weighted_bonds": [vp, i64, vp, vp, vp],
 }

@@ -314,3 +314,43 @@ def test_local_measurements(name):
                 want += (a1 * xv + a3 * xv ** 2) * (n_li - 0.5 if m.hol_phsym[c] else n_li)
         want /= ncell * Lt
         assert abs(g.measure_holstein_energy(x, 0) - want) < 1e-12 * max(1.0, abs(want))
+
+
+def test_make_measurements_twin_and_orbital_double_occupancy():
+    """measure_double_occ(greens_estimator, orbital) (scalar_measurements.jl:98-109, divided by the TOTAL V as the reference does) and the
+    accumulation order of make_measurements! (make_measurements.jl:19-146) on a dictionary."""
+    from smoqyelph_b200 import api
+    m = mdl.holstein_honeycomb(3, 0.6, mu=0.2)
+    rng = np.random.default_rng(12)
+    V, t = dr.build_Vt(m, m.random_fields(rng, smooth=True))
+    fdm = api.SymFermionDetMatrix(m, tol=1e-12, maxiter=20000)
+    fdm.update(V, t)
+    g = api.GreensEstimator(fdm, Nrv=4, seed=7)
+    meas = {}
+    zero = (0, 0)
+    corr = [("greens", (0, 1)), ("density", (0, 1)), ("bond", (((0, 1), zero), ((0, 1), (1, 0))))]
+    it1 = api.make_measurements(meas, fdm, g, mu=0.2, bosonic_action=1.5, tol=1e-12, correlations=corr)
+    R, GR = g.get()
+    dims = tuple(m.lattice_dims)
+    norb = m.N // int(np.prod(dims))
+    Rt, G = _fields(R, GR, m.Ltau, norb, dims)
+    Nrv, Vtot = R.shape[1], m.N * m.Ltau
+    for a in range(norb):
+        d = 0.0
+        for i in range(Nrv - 1):
+            for j in range(i + 1, Nrv):
+                d += np.sum((1 - G[:, a, ..., i] * Rt[:, a, ..., i]) * (1 - G[:, a, ..., j] * Rt[:, a, ..., j])) / Vtot
+        d /= Nrv * (Nrv - 1) / 2
+        assert abs(g.measure_double_occ_orbital(a) - d) < 1e-13
+        assert abs(meas["local"]["double_occ"][a] - d) < 1e-13
+        n = 1 - np.sum(G[:, a] * Rt[:, a]) / G[:, a].size
+        assert abs(meas["local"]["density"][a] - 2 * n) < 1e-13
+    s = g.measure()
+    assert abs(sum(meas["local"]["double_occ"]) - s["double_occ"]) < 1e-13          # the orbital parts add up to the global value
+    assert abs(meas["global"]["density"] - 2 * s["n"]) < 1e-14 and meas["global"]["sgn"] == 1.0 and meas["global"]["action_bosonic"] == 1.5
+    key = ("density", 0, 1)
+    assert np.abs(meas["correlations"][key] - g.measure_density_correlation(0, 1)).max() < 1e-13
+    # a second configuration accumulates
+    it2 = api.make_measurements(meas, fdm, g, mu=0.2, bosonic_action=1.5, tol=1e-12, correlations=corr)
+    assert meas["global"]["sgn"] == 2.0 and it1 > 0 and it2 > 0
+    assert abs(meas["global"]["chemical_potential"] - 0.4) < 1e-15
