@@ -12,11 +12,13 @@ using LinearAlgebra, Random
 import LinearAlgebra: mul!, lmul!, ldiv!
 import SmoQyDQMC
 import SmoQyDQMC: FermionPathIntegral, ElectronPhononParameters, hmc_update!, update_chemical_potential!,
-                  reflection_update!, swap_update!, radial_update!
+                  reflection_update!, swap_update!, radial_update!, make_measurements!,
+                  measure_onsite_energy, measure_hopping_energy, measure_bare_hopping_energy
+import MuTuner
 using Checkerboard: checkerboard_decomposition!
 
-export FermionDetMatrix, SymFermionDetMatrix, AsymFermionDetMatrix, KPMPreconditioner, PFFCalculator,
-       EFAPFFHMCUpdater, GreensEstimator
+export FermionDetMatrix, SymFermionDetMatrix, AsymFermionDetMatrix, KPMPreconditioner, SymKPMPreconditioner, AsymKPMPreconditioner,
+       PFFCalculator, EFAPFFHMCUpdater, GreensEstimator
 
 const LIB = get(ENV, "SMOQYELPH_B200_LIB", "libsmoqyelph_b200.so")
 
@@ -105,6 +107,10 @@ end
 mutable struct KPMPreconditioner{E}
     h::Ptr{Cvoid}; active::Bool; bounds::NTuple{2,E}
 end
+# one handle type serves both operator forms (the library picks the Sym / Asym expansion from the operator): the reference's two
+# concrete type names (src/KPMPreconditioner.jl:61,132) are kept as aliases for code that dispatches on them
+const SymKPMPreconditioner = KPMPreconditioner
+const AsymKPMPreconditioner = KPMPreconditioner
 function KPMPreconditioner(f::FermionDetMatrix{T,E}; rng::AbstractRNG = Random.default_rng(), rbuf::E = 0.10, n::Int = 20,
                            a1::E = 1.0, a2::E = 1.0) where {T,E}
     h = Ref{Ptr{Cvoid}}(C_NULL)
@@ -147,6 +153,7 @@ ldiv!(f::FermionDetMatrix, v::AbstractVecOrMat; kw...) = ldiv!(v, f, v; kw...)
 mutable struct B200ElPh
     h::Ptr{Cvoid}
 end
+const _ELPH_OF_FDM = Dict{Ptr{Cvoid}, WeakRef}()     # operator handle -> its device-side tables (update_chemical_potential! has no other route to them)
 function B200ElPh(elph::ElectronPhononParameters{T,E}, fpi::FermionPathIntegral{T,E}, tbp, f::FermionDetMatrix{T,E}) where {T,E}
     ph = elph.phonon_parameters; hol = elph.holstein_parameters_up; ssh = elph.ssh_parameters_up
     nun = hol.nholstein == 0 ? 1 : hol.Nholstein ÷ hol.nholstein
@@ -163,6 +170,7 @@ function B200ElPh(elph::ElectronPhononParameters{T,E}, fpi::FermionPathIntegral{
         real.(ssh.α3), real.(ssh.α4), V0, t0))
     e = B200ElPh(h[])
     finalizer(x -> ccall((:sq_elph_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), e)
+    _ELPH_OF_FDM[f.h] = WeakRef(e)
     return e
 end
 push_x!(e::B200ElPh, x::Matrix{Float64}) = check(ccall((:sq_elph_set_x, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), e.h, x))
@@ -398,6 +406,68 @@ function make_measurements!(measurement_container, f::FermionDetMatrix{T,E}, g::
     iters = update_greens_estimator!(g, f; preconditioner, rng, tol, maxiter)
     accumulate!(measurement_container, g, model_geometry, tight_binding_parameters, electron_phonon_parameters, fermion_path_integral)
     return iters
+end
+# update_chemical_potential!(fdm, greens_estimator; ...) -> iters  (src/update_chemical_potential.jl:21-73): solves and the two scalar
+# measurements on the device, MuTuner.update! in Julia, then the shift V += -μ + μ′ on the host path integral AND on the device tables
+function update_chemical_potential!(f::FermionDetMatrix{T,E}, g::GreensEstimator{E}; chemical_potential_tuner, tight_binding_parameters,
+                                    fermion_path_integral::FermionPathIntegral{T,E}, preconditioner = I, rng::AbstractRNG = Random.default_rng(),
+                                    update_greens_estimator::Bool = true, tol::E = f.cgs.tol, maxiter::Int = f.cgs.maxiter) where {T,E}
+    iters = 0
+    if update_greens_estimator
+        iters = update_greens_estimator!(g, f; preconditioner, rng, maxiter, tol)
+    end
+    μ′ = tight_binding_parameters.μ
+    n = real(2 * measure_n(g))
+    Nsqrd = real(measure_Nsqrd(g))
+    μ = MuTuner.update!(chemical_potential_tuner, n, Nsqrd, one(E))
+    tight_binding_parameters.μ = μ
+    V = fermion_path_integral.V
+    @. V += -μ + μ′
+    ref = get(_ELPH_OF_FDM, f.h, nothing)
+    if ref !== nothing && ref.value !== nothing
+        check(ccall((:sq_elph_shift_mu, LIB), Cint, (Ptr{Cvoid}, Cdouble), ref.value.h, μ - μ′))
+    end
+    update!(f, fermion_path_integral)
+    return iters
+end
+
+# local measurements (src/Measurements/tight_binding_measurements.jl:58-133): the weights are assembled here exactly as the reference's
+# loops imply, the reductions over R, G R run on the device (sq_greens_weighted_density / sq_greens_weighted_bonds)
+function _weighted_density(g::GreensEstimator{E}, w::Matrix{E}) where {E}                  # w: (N sites, Lτ)
+    out = zeros(Complex{E}, 1)
+    GC.@preserve w check(ccall((:sq_greens_weighted_density, LIB), Cint, (Ptr{Cvoid}, Ptr{E}, Ptr{Complex{E}}), g.h, w, out))
+    return out[1]
+end
+function _weighted_bonds(g::GreensEstimator{E}, bonds::Matrix{Int64}, w::Matrix{Complex{E}}) where {E}     # bonds (2, nb) 1-based, w (nb, Lτ)
+    out = zeros(Complex{E}, 1)
+    GC.@preserve bonds w check(ccall((:sq_greens_weighted_bonds, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Complex{E}}, Ptr{Complex{E}}),
+                                     g.h, size(bonds, 2), bonds, w, out))
+    return out[1]
+end
+function measure_onsite_energy(g::GreensEstimator{E}, tight_binding_parameters, orbital::Int; n::Int, Lτ::Int) where {E}
+    ϵ = tight_binding_parameters.ϵ; μ = tight_binding_parameters.μ
+    Nsites = length(ϵ); Ncells = Nsites ÷ n
+    w = zeros(E, Nsites, Lτ)
+    for i in orbital:n:Nsites
+        w[i, :] .= (ϵ[i] - μ) / (Lτ * Ncells)
+    end
+    return _weighted_density(g, w)
+end
+function measure_bare_hopping_energy(g::GreensEstimator{E}, tight_binding_parameters, model_geometry, hopping_id::Int; n::Int, Lτ::Int) where {E}
+    sl = tight_binding_parameters.bond_slices[hopping_id]
+    t = tight_binding_parameters.t[sl]
+    bonds = Matrix{Int64}(tight_binding_parameters.neighbor_table[:, sl])
+    Nsites = length(tight_binding_parameters.ϵ)
+    w = Matrix{Complex{E}}(undef, length(t), Lτ)
+    for l in 1:Lτ; w[:, l] .= t ./ (Lτ * Nsites); end
+    return _weighted_bonds(g, bonds, w)
+end
+function measure_hopping_energy(g::GreensEstimator{E}, tight_binding_parameters, fermion_path_integral, hopping_id::Int; n::Int) where {E}
+    sl = tight_binding_parameters.bond_slices[hopping_id]
+    t = fermion_path_integral.t[sl, :]                                   # the modulated amplitudes t(bond, τ)
+    bonds = Matrix{Int64}(tight_binding_parameters.neighbor_table[:, sl])
+    Nsites = length(tight_binding_parameters.ϵ); Lτ = size(t, 2)
+    return _weighted_bonds(g, bonds, Matrix{Complex{E}}(t ./ (Lτ * Nsites)))
 end
 measure_n(g::GreensEstimator) = _measure(g)[1]
 measure_double_occ(g::GreensEstimator) = _measure(g)[2]
