@@ -312,12 +312,14 @@ end
 #      src/update_chemical_potential.jl:21-73).  MuTuner stays in Julia. ---------------------------------------------
 mutable struct GreensEstimator{E}
     h::Ptr{Cvoid}; Nrv::Int
+    n::Int; L::Tuple; Lτ::Int; N::Int      # orbitals per cell, lattice extents, time slices, unit cells (the reference's fields of the same names)
 end
 function GreensEstimator(f::FermionDetMatrix{T,E}, model_geometry; Nrv::Int = 10, preconditioner = I, rng::AbstractRNG = Random.default_rng(),
                          maxiter::Int = f.cgs.maxiter, tol::E = f.cgs.tol) where {T,E}
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:sq_greens_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Int64, UInt64), h, f.h, Nrv, rand(rng, UInt64)))
-    g = GreensEstimator{E}(h[], Nrv)
+    n = model_geometry.unit_cell.n; L = Tuple(model_geometry.lattice.L)
+    g = GreensEstimator{E}(h[], Nrv, n, L, f.Lτ, f.N ÷ n)
     finalizer(x -> ccall((:sq_greens_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), g)
     update_greens_estimator!(g, f; preconditioner, rng, maxiter, tol)
     return g
@@ -337,7 +339,7 @@ end
 # measure_GΔ0!(correlation, g, (a, b)) (src/Measurements/GreensEstimator.jl:177-233): the translation-averaged time-displaced Green's
 # function is evaluated on the device (aperiodic extension, (D+1)-dimensional FFT cross-correlation, average over the random vectors)
 # and added to `correlation` with the imaginary-time axis last, as add_contraction_to_correlation! does (:718-729).
-function measure_GΔ0!(correlation::AbstractArray{Complex{E}}, g::GreensEstimator{E}, orbitals::NTuple{2,Int}; n::Int, L::NTuple{D,Int}) where {E,D}
+function measure_GΔ0!(correlation::AbstractArray{Complex{E}}, g::GreensEstimator{E}, orbitals::NTuple{2,Int}; n::Int = g.n, L::NTuple{D,Int} = g.L) where {E,D}
     Lτ = size(correlation, D + 1) - 1
     GΔ0 = zeros(Complex{E}, Lτ + 1, L...)
     dims = collect(Int64, L)
@@ -349,7 +351,7 @@ end
 # The four-point contractions (src/Measurements/GreensEstimator.jl:236-606), with or without hopping weights; the correlation functions built on
 # them (density.jl, pair.jl, spin.jl) call these exactly as in the reference.
 function _contraction!(correlation::AbstractArray{Complex{E}}, g::GreensEstimator{E}, kind::Int, orbitals::NTuple{4,Int}, r1, r2, r3, r4, coef,
-                       tΔ = nothing, t0 = nothing, conj_tΔ::Bool = false, conj_t0::Bool = false; n::Int, L::NTuple{D,Int}) where {E,D}
+                       tΔ = nothing, t0 = nothing, conj_tΔ::Bool = false, conj_t0::Bool = false; n::Int = g.n, L::NTuple{D,Int} = g.L) where {E,D}
     Lτ = size(correlation, D + 1) - 1
     C = zeros(Complex{E}, Lτ + 1, L...)
     dims = collect(Int64, L); orb = collect(Cint, orbitals); r = Int64[r1..., r2..., r3..., r4...]
@@ -386,12 +388,12 @@ function measure_current_correlation!(CC, g::GreensEstimator, b′, b″, t′, 
     measure_G0Δ_GΔ0!(CC, g, (c, a, b, d), r″, r′, z, z, -f2 * coef, t′, t″, false, true; kw...)
     return nothing
 end
-function measure_n(g::GreensEstimator{E}, orbital::Int; n::Int) where {E}
+function measure_n(g::GreensEstimator{E}, orbital::Int; n::Int = g.n) where {E}
     out = zeros(Complex{E}, 1)
     check(ccall((:sq_greens_measure_n_orbital, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Complex{E}}), g.h, n, orbital, out))
     return out[1]
 end
-function measure_double_occ(g::GreensEstimator{E}, orbital::Int; n::Int) where {E}      # scalar_measurements.jl:98-109
+function measure_double_occ(g::GreensEstimator{E}, orbital::Int; n::Int = g.n) where {E}      # scalar_measurements.jl:98-109
     out = zeros(Complex{E}, 1)
     check(ccall((:sq_greens_measure_double_occ_orbital, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Complex{E}}), g.h, n, orbital, out))
     return out[1]
@@ -444,7 +446,7 @@ function _weighted_bonds(g::GreensEstimator{E}, bonds::Matrix{Int64}, w::Matrix{
                                      g.h, size(bonds, 2), bonds, w, out))
     return out[1]
 end
-function measure_onsite_energy(g::GreensEstimator{E}, tight_binding_parameters, orbital::Int; n::Int, Lτ::Int) where {E}
+function measure_onsite_energy(g::GreensEstimator{E}, tight_binding_parameters, orbital::Int; n::Int = g.n, Lτ::Int = g.Lτ) where {E}
     ϵ = tight_binding_parameters.ϵ; μ = tight_binding_parameters.μ
     Nsites = length(ϵ); Ncells = Nsites ÷ n
     w = zeros(E, Nsites, Lτ)
@@ -453,7 +455,7 @@ function measure_onsite_energy(g::GreensEstimator{E}, tight_binding_parameters, 
     end
     return _weighted_density(g, w)
 end
-function measure_bare_hopping_energy(g::GreensEstimator{E}, tight_binding_parameters, model_geometry, hopping_id::Int; n::Int, Lτ::Int) where {E}
+function measure_bare_hopping_energy(g::GreensEstimator{E}, tight_binding_parameters, model_geometry, hopping_id::Int; n::Int = g.n, Lτ::Int = g.Lτ) where {E}
     sl = tight_binding_parameters.bond_slices[hopping_id]
     t = tight_binding_parameters.t[sl]
     bonds = Matrix{Int64}(tight_binding_parameters.neighbor_table[:, sl])
@@ -462,7 +464,7 @@ function measure_bare_hopping_energy(g::GreensEstimator{E}, tight_binding_parame
     for l in 1:Lτ; w[:, l] .= t ./ (Lτ * Nsites); end
     return _weighted_bonds(g, bonds, w)
 end
-function measure_hopping_energy(g::GreensEstimator{E}, tight_binding_parameters, fermion_path_integral, hopping_id::Int; n::Int) where {E}
+function measure_hopping_energy(g::GreensEstimator{E}, tight_binding_parameters, fermion_path_integral, hopping_id::Int; n::Int = g.n) where {E}
     sl = tight_binding_parameters.bond_slices[hopping_id]
     t = fermion_path_integral.t[sl, :]                                   # the modulated amplitudes t(bond, τ)
     bonds = Matrix{Int64}(tight_binding_parameters.neighbor_table[:, sl])
