@@ -13,7 +13,7 @@ import LinearAlgebra: mul!, lmul!, ldiv!
 import SmoQyDQMC
 import SmoQyDQMC: FermionPathIntegral, ElectronPhononParameters, hmc_update!, update_chemical_potential!,
                   reflection_update!, swap_update!, radial_update!, make_measurements!,
-                  measure_onsite_energy, measure_hopping_energy, measure_bare_hopping_energy
+                  measure_onsite_energy, measure_hopping_energy, measure_bare_hopping_energy, measure_ssh_energy
 import MuTuner
 using Checkerboard: checkerboard_decomposition!
 
@@ -470,6 +470,20 @@ function measure_hopping_energy(g::GreensEstimator{E}, tight_binding_parameters,
     bonds = Matrix{Int64}(tight_binding_parameters.neighbor_table[:, sl])
     Nsites = length(tight_binding_parameters.ϵ); Lτ = size(t, 2)
     return _weighted_bonds(g, bonds, Matrix{Complex{E}}(t ./ (Lτ * Nsites)))
+end
+# measure_ssh_energy(ssh_parameters, greens_estimator, x, ssh_id)  (src/Measurements/electron_phonon_measurements.jl:124-186)
+function measure_ssh_energy(ssh_parameters, g::GreensEstimator{E}, x::Matrix{E}, ssh_id::Int) where {E}
+    N = g.N; Lτ = g.Lτ
+    sl = ((ssh_id - 1) * N + 1):(ssh_id * N)
+    bonds = Matrix{Int64}(ssh_parameters.neighbor_table[:, sl])
+    c2p = ssh_parameters.coupling_to_phonon[:, sl]
+    α1 = real.(ssh_parameters.α[sl]); α2 = real.(ssh_parameters.α2[sl]); α3 = real.(ssh_parameters.α3[sl]); α4 = real.(ssh_parameters.α4[sl])
+    w = Matrix{Complex{E}}(undef, N, Lτ)
+    for l in 1:Lτ, u in 1:N
+        Δx = x[c2p[2, u], l] - x[c2p[1, u], l]
+        w[u, l] = -(α1[u] * Δx + α2[u] * Δx^2 + α3[u] * Δx^3 + α4[u] * Δx^4) / (N * Lτ)
+    end
+    return _weighted_bonds(g, bonds, w)
 end
 measure_n(g::GreensEstimator) = _measure(g)[1]
 measure_double_occ(g::GreensEstimator) = _measure(g)[2]

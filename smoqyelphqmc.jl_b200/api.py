@@ -619,6 +619,21 @@ class GreensEstimator:
             e -= 0.5 * np.sum(odd) / (nc * m.Ltau)
         return e
 
+    def measure_ssh_energy(self, x, ssh_id=0):
+        """measure_ssh_energy (electron_phonon_measurements.jl:124-186): the couplings of one SSH id (one per unit cell),
+        eps = sum c(dx) h_forward + conj(c) h_reverse with h = -<G R Rt> and c = a1 dx + a2 dx^2 + a3 dx^3 + a4 dx^4, / (N_cells Ltau)."""
+        m = self.fdm.model
+        nc = m.n_unit_cells
+        sl = slice(ssh_id * nc, (ssh_id + 1) * nc)
+        hop = m.ssh_hopping[sl]
+        bonds = m.neighbor_table[:, hop]
+        p_i, p_f = m.ssh_phonon[0, sl], m.ssh_phonon[1, sl]
+        a1, a2, a3, a4 = (m.ssh_alpha[k][sl][:, None] for k in range(4))
+        xs = np.asarray(x)
+        dx = xs[p_f, :] - xs[p_i, :]
+        c = a1 * dx + a2 * dx ** 2 + a3 * dx ** 3 + a4 * dx ** 4
+        return self.weighted_bonds(bonds, -c.astype(np.complex128) / (nc * m.Ltau))
+
     def measure(self):
         out = np.zeros((3, 2))
         check(self.L.sq_greens_measure(self.h, ptr(out[0]), ptr(out[1]), ptr(out[2])))

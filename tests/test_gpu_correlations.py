@@ -314,6 +314,21 @@ def test_local_measurements(name):
                 want += (a1 * xv + a3 * xv ** 2) * (n_li - 0.5 if m.hol_phsym[c] else n_li)
         want /= ncell * Lt
         assert abs(g.measure_holstein_energy(x, 0) - want) < 1e-12 * max(1.0, abs(want))
+    for ssh_id in range(m.Nssh // ncell):                            # SSH energy, literal restatement of :124-186
+        want = 0.0
+        for u in range(ncell):
+            cpl = ssh_id * ncell + u
+            s_i, s_f = m.neighbor_table[:, m.ssh_hopping[cpl]]
+            p_i, p_f = m.ssh_phonon[:, cpl]
+            a1, a2, a3, a4 = m.ssh_alpha[:, cpl]
+            for l in range(Lt):
+                dx = x[p_f, l] - x[p_i, l]
+                c = a1 * dx + a2 * dx ** 2 + a3 * dx ** 3 + a4 * dx ** 4
+                hf = -np.sum(G[l, s_i, :] * Rt[l, s_f, :]) / Nrv
+                hr = -np.sum(G[l, s_f, :] * Rt[l, s_i, :]) / Nrv
+                want += c * hf + np.conj(c) * hr
+        want /= ncell * Lt
+        assert abs(g.measure_ssh_energy(x, ssh_id) - want) < 1e-12 * max(1.0, abs(want))
 
 
 def test_make_measurements_twin_and_orbital_double_occupancy():
