@@ -13,7 +13,8 @@ import LinearAlgebra: mul!, lmul!, ldiv!
 import SmoQyDQMC
 import SmoQyDQMC: FermionPathIntegral, ElectronPhononParameters, hmc_update!, update_chemical_potential!,
                   reflection_update!, swap_update!, radial_update!, make_measurements!,
-                  measure_onsite_energy, measure_hopping_energy, measure_bare_hopping_energy, measure_ssh_energy
+                  measure_onsite_energy, measure_hopping_energy, measure_bare_hopping_energy, measure_holstein_energy,
+                  measure_ssh_energy
 import MuTuner
 using Checkerboard: checkerboard_decomposition!
 
@@ -470,6 +471,28 @@ function measure_hopping_energy(g::GreensEstimator{E}, tight_binding_parameters,
     bonds = Matrix{Int64}(tight_binding_parameters.neighbor_table[:, sl])
     Nsites = length(tight_binding_parameters.ϵ); Lτ = size(t, 2)
     return _weighted_bonds(g, bonds, Matrix{Complex{E}}(t ./ (Lτ * Nsites)))
+end
+# measure_holstein_energy(holstein_parameters, greens_estimator, x, holstein_id)  (src/Measurements/electron_phonon_measurements.jl:60-122).
+# As in the reference the density is taken in the unit cell of the phonon (orbital of the first coupling of this id), the phonons of
+# the id are the contiguous rows phonon_i:phonon_f of x, and the odd terms use x and x^2 (:113).
+function measure_holstein_energy(holstein_parameters, g::GreensEstimator{E}, x::Matrix{E}, holstein_id::Int) where {E}
+    (; coupling_to_site, coupling_to_phonon, ph_sym_form) = holstein_parameters
+    N = g.N; n = g.n; Lτ = g.Lτ
+    sl = ((holstein_id - 1) * N + 1):(holstein_id * N)
+    phs = ph_sym_form[holstein_id]
+    orbital_id = mod1(coupling_to_site[first(sl)], n)
+    phonon_i = coupling_to_phonon[first(sl)]
+    α1 = holstein_parameters.α[sl]; α2 = holstein_parameters.α2[sl]; α3 = holstein_parameters.α3[sl]; α4 = holstein_parameters.α4[sl]
+    w = zeros(E, N * n, Lτ)
+    shift = zero(E)
+    for l in 1:Lτ, u in 1:N
+        xv = x[phonon_i + u - 1, l]
+        even = α2[u] * xv^2 + α4[u] * xv^4
+        odd = α1[u] * xv + α3[u] * xv^2
+        w[orbital_id + n * (u - 1), l] += (even + odd) / (N * Lτ)
+        phs && (shift += odd / (2 * N * Lτ))
+    end
+    return _weighted_density(g, w) - shift
 end
 # measure_ssh_energy(ssh_parameters, greens_estimator, x, ssh_id)  (src/Measurements/electron_phonon_measurements.jl:124-186)
 function measure_ssh_energy(ssh_parameters, g::GreensEstimator{E}, x::Matrix{E}, ssh_id::Int) where {E}
