@@ -532,13 +532,16 @@ class GreensEstimator:
         check(self.L.sq_greens_measure_n_orbital(self.h, norb, int(a) + 1, ptr(out)))
         return complex(out[0], out[1])
 
-    def measure_density_correlation(self, a, b, coef=1.0, norb=None, dims=None):
-        """measure_density_correlation!(DD, greens_estimator, a, b, coef)  (src/Measurements/Correlations/density.jl:2-33):
-        DD = 4 coef (n_a + n_b - 1) + 4 coef G(Δ,Δ)G(0,0)[a,a,b,b] - 2 coef G(0,Δ)G(Δ,0)[b,a,a,b]."""
+    def measure_density_correlation(self, a, b, coef=1.0, norb=None, dims=None, spins=None):
+        """measure_density_correlation!(DD, greens_estimator, a, b, [σ, σ'], coef)  (src/Measurements/Correlations/density.jl:2-65):
+        spin-summed  DD = 4 coef (n_a + n_b - 1) + 4 coef G(Δ,Δ)G(0,0)[a,a,b,b] - 2 coef G(0,Δ)G(Δ,0)[b,a,a,b];
+        spin-resolved (spins = (σ, σ')): factors 1, and the exchange term only for equal spins."""
         na, nb = self.measure_n_orbital(a, norb, dims), self.measure_n_orbital(b, norb, dims)
-        DD = 4 * coef * self.measure_contraction("GDD_G00", (a, a, b, b), norb=norb, dims=dims)
-        DD -= 2 * coef * self.measure_contraction("G0D_GD0", (b, a, a, b), norb=norb, dims=dims)
-        return DD + 4 * coef * (na + nb - 1)
+        f1, f2 = (4.0, 2.0) if spins is None else (1.0, 1.0 if spins[0] == spins[1] else 0.0)
+        DD = f1 * coef * self.measure_contraction("GDD_G00", (a, a, b, b), norb=norb, dims=dims)
+        if f2:
+            DD -= f2 * coef * self.measure_contraction("G0D_GD0", (b, a, a, b), norb=norb, dims=dims)
+        return DD + f1 * coef * (na + nb - 1)
 
     def measure_pair_correlation(self, bond1, bond2, coef=1.0, norb=None, dims=None):
         """measure_pair_correlation!(PP, greens_estimator, b', b'', coef)  (src/Measurements/Correlations/pair.jl:2-21).
@@ -548,18 +551,21 @@ class GreensEstimator:
         z = (0,) * len(tuple(r1))
         return coef * self.measure_contraction("GD0_GD0", (a, c, b, d), (tuple(r1), tuple(r2), z, z), norb=norb, dims=dims)
 
-    def measure_bond_correlation(self, bond1, bond2, coef=1.0, norb=None, dims=None):
-        """measure_bond_correlation!(BB, greens_estimator, b', b'', coef)  (src/Measurements/Correlations/bond.jl:2-48): four
-        G(Δ,Δ)G(0,0) and four G(0,Δ)G(Δ,0) contractions.  A bond is ((orbital_1, orbital_2), displacement)."""
+    def measure_bond_correlation(self, bond1, bond2, coef=1.0, norb=None, dims=None, spins=None):
+        """measure_bond_correlation!(BB, greens_estimator, b', b'', [σ', σ''], coef)  (src/Measurements/Correlations/bond.jl:2-131): four
+        G(Δ,Δ)G(0,0) and four G(0,Δ)G(Δ,0) contractions (spin-summed: factors 4 and 2; spin-resolved: 1, exchange terms only for equal
+        spins).  A bond is ((orbital_1, orbital_2), displacement)."""
         (b, a), r1 = bond1
         (d, c), r2 = bond2
         r1, r2 = tuple(r1), tuple(r2)
         z = (0,) * len(r1)
         mc = lambda kind, orbs, r: self.measure_contraction(kind, orbs, r, norb=norb, dims=dims)
-        BB = 4 * coef * (mc("GDD_G00", (a, b, c, d), (r1, z, r2, z)) + mc("GDD_G00", (a, b, d, c), (r1, z, z, r2))
-                         + mc("GDD_G00", (b, a, c, d), (z, r1, r2, z)) + mc("GDD_G00", (b, a, d, c), (z, r1, z, r2)))
-        BB -= 2 * coef * (mc("G0D_GD0", (c, b, a, d), (r2, z, r1, z)) + mc("G0D_GD0", (d, b, a, c), (z, z, r1, r2))
-                          + mc("G0D_GD0", (c, a, b, d), (r2, r1, z, z)) + mc("G0D_GD0", (d, a, b, c), (z, r1, z, r2)))
+        f1, f2 = (4.0, 2.0) if spins is None else (1.0, 1.0 if spins[0] == spins[1] else 0.0)
+        BB = f1 * coef * (mc("GDD_G00", (a, b, c, d), (r1, z, r2, z)) + mc("GDD_G00", (a, b, d, c), (r1, z, z, r2))
+                          + mc("GDD_G00", (b, a, c, d), (z, r1, r2, z)) + mc("GDD_G00", (b, a, d, c), (z, r1, z, r2)))
+        if f2:
+            BB -= f2 * coef * (mc("G0D_GD0", (c, b, a, d), (r2, z, r1, z)) + mc("G0D_GD0", (d, b, a, c), (z, z, r1, r2))
+                               + mc("G0D_GD0", (c, a, b, d), (r2, r1, z, z)) + mc("G0D_GD0", (d, a, b, c), (z, r1, z, r2)))
         return BB
 
     def measure_spin_correlation(self, a, b, coef=1.0, norb=None, dims=None):

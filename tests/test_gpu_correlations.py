@@ -208,6 +208,12 @@ def test_four_point_contractions_and_density_correlation(name):
                + rc("G0D_GD0", (bc, ba, bb, bd), (r2, r1, z, z)) + rc("G0D_GD0", (bd, ba, bb, bc), (z, r1, z, r2)))
     got = g.measure_bond_correlation(b1, b2)
     assert np.abs(got - want).max() < 1e-11 * max(1.0, np.abs(want).max())
+    # spin-resolved forms (bond.jl:66-131): factors 1, exchange terms only for equal spins
+    gdd = (rc("GDD_G00", (ba, bb, bc, bd), (r1, z, r2, z)) + rc("GDD_G00", (ba, bb, bd, bc), (r1, z, z, r2))
+           + rc("GDD_G00", (bb, ba, bc, bd), (z, r1, r2, z)) + rc("GDD_G00", (bb, ba, bd, bc), (z, r1, z, r2)))
+    for spins, w in (((+1, -1), gdd), ((-1, -1), gdd - (4 * gdd - want) / 2)):
+        got = g.measure_bond_correlation(b1, b2, spins=spins)
+        assert np.abs(got - w).max() < 1e-11 * max(1.0, np.abs(w).max()), spins
     # density correlation (src/Measurements/Correlations/density.jl:2-33) assembled from the contractions
     Rt, G = _fields(R, GR, m.Ltau, norb, dims)
     for a, b in ((0, 0), (0, norb - 1)):
@@ -218,6 +224,11 @@ def test_four_point_contractions_and_density_correlation(name):
             - 2 * ref_contraction("G0D_GD0", R, GR, m.Ltau, norb, dims, (b, a, a, b), zero)
         got = g.measure_density_correlation(a, b)
         assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+        # spin-resolved (density.jl:33-65)
+        dd = ref_contraction("GDD_G00", R, GR, m.Ltau, norb, dims, (a, a, b, b), zero)
+        ex = ref_contraction("G0D_GD0", R, GR, m.Ltau, norb, dims, (b, a, a, b), zero)
+        assert np.abs(g.measure_density_correlation(a, b, spins=(+1, +1)) - ((na + nb - 1) + dd - ex)).max() < 1e-12 * max(1.0, np.abs(dd).max())
+        assert np.abs(g.measure_density_correlation(a, b, spins=(+1, -1)) - ((na + nb - 1) + dd)).max() < 1e-12 * max(1.0, np.abs(dd).max())
 
 
 @pytest.mark.parametrize("name", ["honeycomb", "square"])
