@@ -8,7 +8,13 @@ plus the fused M^T M v kernel against the HBM roofline and the CPU path timed be
 A "step" is one hmc_update! trajectory (Nt = 24 leapfrog steps = 24 force solves + 1 action solve,
 src/EFAPFFHMCUpdater.jl:102-279) of one Markov chain.  `value` keeps the phonon field resident in HBM;
 `e2e` pushes x host->device before and reads it back after every trajectory through the C ABI, as the Julia
-drop-in does.  N > 1 runs one independent chain per GPU (the MPI tutorial's mode, weak scaling).
+drop-in does.  N > 1 runs one independent chain per GPU (the MPI tutorial's mode, weak scaling: every chain starts from the
+same relaxed configuration and samples with seed + rank; the job time is the slowest chain's, `per_rank` lists every chain's time
+and CG iteration count).  Extra keys of the N > 1 line, all under `tau_slab` (strong scaling of ONE chain, not part of `value`):
+CG microseconds per iteration on one GPU, tau-slab partitioned with the host-launched NCCL loop and with the resident kernels that
+exchange sums and boundary slices through peer-mapped mailboxes, and trajectories/s of one chain whose solves are sharded over all
+GPUs (`chain_over_all_gpus`).  Clocks and throttle reasons are sampled during the timed region through NVML from a thread of this
+process (`clocks.source`), `nvidia-smi -lms` being the fallback.
 """
 import argparse
 import json
