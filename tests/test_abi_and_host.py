@@ -199,3 +199,52 @@ def test_clock_sampler_degrades_without_a_gpu():
     bench = importlib.import_module("bench")
     out = bench.ClockSampler(0).stop()
     assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_make_measurements_accumulates_like_the_reference_container():
+    """Host logic of api.make_measurements (make_measurements.jl:19-146) on a stub estimator: values are ADDED per call, the per-orbital
+    entries are vectors, correlations are keyed by their arguments, and the estimator is refreshed first."""
+    from smoqyelph_b200 import api
+
+    class Stub:
+        def __init__(self):
+            self.calls = []
+
+        def update_greens_estimator(self, preconditioner=None, tol=None, maxiter=None):
+            self.calls.append("update")
+            return 7.5
+
+        def _geom(self, norb, dims):
+            return 2, (3, 3)
+
+        def measure(self):
+            self.calls.append("measure")
+            return {"n": 0.5 + 0j, "double_occ": 0.25 + 0j, "Nsqrd": 9.0 + 0j}
+
+        def measure_n_orbital(self, a, norb, dims):
+            return 0.4 + 0.1 * a
+
+        def measure_double_occ_orbital(self, a, norb, dims):
+            return 0.1 + 0.05 * a
+
+        def measure_GD0(self, orbitals, norb=None, dims=None):
+            return np.full((3, 3, 5), orbitals[0] + 10.0 * orbitals[1], complex)
+
+        def measure_density_correlation(self, a, b, norb=None, dims=None):
+            return np.ones((3, 3, 5), complex)
+
+    g = Stub()
+    meas = {}
+    corr = [("greens", (0, 1)), ("density", (1, 1))]
+    for k in range(3):
+        it = api.make_measurements(meas, None, g, mu=0.3, bosonic_action=lambda: 2.0, correlations=corr)
+        assert it == 7.5 and g.calls[2 * k] == "update" and g.calls[2 * k + 1] == "measure"
+    G = meas["global"]
+    assert G["sgn"] == 3.0 and abs(G["density"] - 3.0) < 1e-14 and abs(G["density_up"] - 1.5) < 1e-14 and abs(G["double_occ"] - 0.75) < 1e-14
+    assert abs(G["Nsqrd"] - 27.0) < 1e-14 and abs(G["chemical_potential"] - 0.9) < 1e-14 and abs(G["action_bosonic"] - 6.0) < 1e-14
+    L = meas["local"]
+    assert np.allclose(L["density"], [3 * 0.8, 3 * 1.0]) and np.allclose(L["double_occ"], [0.3, 0.45]) and L["density_up"].shape == (2,)
+    C = meas["correlations"]
+    assert np.allclose(C[("greens", 0, 1)], 30.0) and np.allclose(C[("density", 1, 1)], 3.0)
+    with pytest.raises(ValueError):
+        api.make_measurements(meas, None, g, correlations=[("nonsense", (0, 0))])
