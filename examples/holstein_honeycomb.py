@@ -26,10 +26,12 @@ def run_simulation(L=3, beta=4.0, N_therm=20, N_measurements=20, Omega=1.0, alph
     elph = api.ElectronPhononParameters(m, fdm)
     elph.x = mdl.thermal_fields(m, rng)
     elph.update_fdm()
-    pff = api.PFFCalculator(elph)
-    P = api.KPMPreconditioner(fdm) if use_preconditioner else None
-    hmc = api.EFAPFFHMCUpdater(elph, pff, Nt=Nt, seed=seed + 1)
-    g = api.GreensEstimator(fdm, Nrv=Nrv, seed=seed + 2)
+    from smoqyelph_b200.parallel import chain_seed
+    # one Philox key per component, hashed from the chain seed (consecutive integers would alias streams between chains)
+    pff = api.PFFCalculator(elph, seed=chain_seed(seed, 0, 3))
+    P = api.KPMPreconditioner(fdm, seed=chain_seed(seed, 0, 4)) if use_preconditioner else None
+    hmc = api.EFAPFFHMCUpdater(elph, pff, Nt=Nt, seed=chain_seed(seed, 0, 1))
+    g = api.GreensEstimator(fdm, Nrv=Nrv, seed=chain_seed(seed, 0, 2))
     meta = {k: 0.0 for k in ("hmc_acceptance_rate", "reflection_acceptance_rate", "swap_acceptance_rate", "hmc_iters",
                              "reflection_iters", "swap_iters", "measurement_iters")}
 

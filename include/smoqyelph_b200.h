@@ -8,6 +8,9 @@
  *
  * Conventions
  *  - Every function returns 0 on success, non-zero on failure; sq_last_error() gives the message.
+ *    Status 3 = numerical instability (NaN / non-finite residual, Lanczos coefficient or action), the
+ *    condition the reference's callers turn into a rejected update; 1 = anything else (bad argument,
+ *    CUDA / NCCL error, watchdog time-out of a resident kernel), which callers must NOT swallow.
  *    The Julia shim raises on non-zero so the reference's try/catch "numerical instability =>
  *    reject the update" semantics are preserved (src/EFAPFFHMCUpdater.jl:168-187).  CG
  *    non-convergence is NOT an error: iters == maxiter is returned (ConjugateGradient.jl:248).
@@ -104,12 +107,20 @@ int sq_fdm_set_sharded_solve(sq_fdm *f, int enable);
 int sq_fdm_set_slab_range(sq_fdm *f, int64_t lo, int64_t hi);      /* single-process testing of the range logic */
 int sq_fdm_get_slab(sq_fdm *f, int64_t *lo, int64_t *hi, int *rank, int *world);
 int64_t sq_fdm_launch_count(sq_fdm *f);
+/* Diagnostic counters since creation (no reference counterpart; the reference logs through @warn): out[0..n) =
+ *  0 CG solves, 1 by the whole-solve resident register kernel, 2 by the cooperative shared-memory kernel, 3 by the unpreconditioned
+ *  launch loop, 4 preconditioned, 5 tau-slab NCCL loop, 6 tau-slab resident kernels, 7 spin-wait watchdogs fired, 8 numerical
+ *  instabilities turned into rejections, 9 CG iterations, 10 / 11 preconditioner applies (register / shared-memory Chebyshev kernel),
+ *  12 right-hand sides solved by the batched solver, 13 tau-slab preconditioned solves. */
+int sq_fdm_stats(sq_fdm *f, int64_t *out, int n);
 
 /* ---- KPMPreconditioner ----------------------------------------------------------------------- */
 /* KPMPreconditioner(fdm; rng, rbuf, n, a1, a2): src/KPMPreconditioner.jl:198-284 (does NOT run the
  * first update; call sq_kpm_update). */
 int sq_kpm_create(sq_kpm **out, sq_fdm *f, double rbuf, int64_t n, double a1, double a2);
 int sq_kpm_destroy(sq_kpm *k);
+/* seed of the library-drawn Lanczos start vectors (`rng` of KPMPreconditioner(fdm; rng, ...), :198; the shim passes rand(rng, UInt64)) */
+int sq_kpm_set_seed(sq_kpm *k, uint64_t seed);
 /* update_preconditioner!(P, fdm, rng): :554-597.  lanczos_start: N normals (NULL = library RNG). */
 int sq_kpm_update(sq_kpm *k, const double *lanczos_start, int *active, double *bounds);
 /* test hook: refresh B-bar and force the eigenvalue bounds (identical coefficients on both sides) */
@@ -134,6 +145,10 @@ int sq_elph_create(sq_elph **out, sq_fdm *f, double dtau, int64_t Nph, const dou
                    const int32_t *hol_phsym, int64_t Nssh, const int64_t *ssh_phonon, const int64_t *ssh_hopping,
                    const double *ssh_a, const double *ssh_a2, const double *ssh_a3, const double *ssh_a4,
                    const double *V0, const double *t0);
+/* V0 / t0 may be NULL at creation -- PFFCalculator(elph, fdm) (src/PFFCalculator.jl:30-33) sees neither TightBindingParameters nor the
+ * FermionPathIntegral -- and be supplied here by the first call that does (hmc_update!, the global moves, update_chemical_potential!).
+ * Only sq_elph_refresh_fdm / sq_elph_get_Vt need them; sample / action / force work on the operator state set by sq_fdm_update. */
+int sq_elph_set_bare(sq_elph *e, const double *V0, const double *t0);
 int sq_elph_destroy(sq_elph *e);
 int sq_elph_set_x(sq_elph *e, const double *x);          /* (Nph x Ltau) */
 int sq_elph_get_x(sq_elph *e, double *x);
@@ -155,6 +170,9 @@ int sq_elph_bosonic_action(sq_elph *e, double *Sb);
 /* ---- PFFCalculator --------------------------------------------------------------------------- */
 int sq_pff_create(sq_pff **out, sq_elph *e);                                   /* src/PFFCalculator.jl:30-53 */
 int sq_pff_destroy(sq_pff *p);
+/* seed of the library-drawn pseudofermion noise (the `rng` argument of sample_pseudofermion_fields!, :56); without it
+ * sq_hmc_create derives one from the HMC seed */
+int sq_pff_set_seed(sq_pff *p, uint64_t seed);
 int sq_pff_set_exact_holstein(sq_pff *p, int flag);    /* 0 = reference behaviour, 1 = exact derivative */
 /* sample_pseudofermion_fields!: :56-76.  R = the randn!(rng, Phi) draw (Ltau x N), NULL = library RNG. */
 int sq_pff_sample(sq_pff *p, const sq_complex *R, double *Sf);
@@ -181,6 +199,11 @@ int sq_hmc_destroy(sq_hmc *h);
  * info[8] = iters_avg, dH, Sf0, Sf1, Sb0, Sb1, K0, K1. */
 int sq_hmc_update(sq_hmc *h, sq_kpm *kpm, double tol_action, double tol_force, int64_t maxiter,
                   const double *randoms, int64_t nrandoms, int *accepted, double *info);
+/* re-key the Philox stream of the next trajectories (the Julia shim passes rand(rng, UInt64) before every hmc_update!, so the
+ * caller's `rng` (:107) determines the trajectory call after call) */
+int sq_hmc_set_seed(sq_hmc *h, uint64_t seed);
+/* reason of the last forced rejection (the reference's `@warn "... rejecting update"`, :181,226), "" if the last update was stable */
+const char *sq_hmc_last_reject(sq_hmc *h);
 /* EFA pieces for parity tests: SmoQyDQMC initialize_momentum!, kinetic_energy, evolve_eom! */
 int sq_hmc_init_momentum(sq_hmc *h, const double *R, double *p, double *K);
 int sq_hmc_kinetic(sq_hmc *h, const double *p, double *K);
@@ -189,6 +212,7 @@ int sq_hmc_evolve(sq_hmc *h, double *x, double *p, double dt);
 /* ---- GreensEstimator ------------------------------------------------------------------------- */
 int sq_greens_create(sq_greens **out, sq_fdm *f, int64_t Nrv, uint64_t seed);   /* GreensEstimator.jl:63-118 */
 int sq_greens_destroy(sq_greens *g);
+int sq_greens_set_seed(sq_greens *g, uint64_t seed);      /* re-key the stream of the library-drawn random vectors (`rng` of update_greens_estimator!, :128) */
 /* update_greens_estimator!: :125-175.  R (V x Nrv) unit-modulus vectors or NULL (library RNG);
  * warm start from the previous GR as in the reference. */
 int sq_greens_update(sq_greens *g, sq_kpm *kpm, const sq_complex *R, double tol, int64_t maxiter, double *avg_iters);

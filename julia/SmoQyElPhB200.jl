@@ -26,10 +26,17 @@ const LIB = get(ENV, "SMOQYELPH_B200_LIB", "libsmoqyelph_b200.so")
 struct B200Error <: Exception
     msg::String
 end
-# non-zero status => throw, so the reference's try/catch "numerical instability => reject" paths keep working
+# status 3: NaN / non-finite residual, Lanczos coefficient or action -- the condition the reference's callers turn into a rejected
+# update (src/EFAPFFHMCUpdater.jl:168-187, src/reflection_update.jl:111-127).  Everything else (bad argument, CUDA / NCCL error,
+# watchdog time-out) is a B200Error and is never swallowed by this module.
+struct B200NumericalInstability <: Exception
+    msg::String
+end
 @inline function check(status::Cint)
     status == 0 && return nothing
-    throw(B200Error(unsafe_string(ccall((:sq_last_error, LIB), Cstring, ()))))
+    msg = unsafe_string(ccall((:sq_last_error, LIB), Cstring, ()))
+    status == 3 && throw(B200NumericalInstability(msg))
+    throw(B200Error(msg))
 end
 
 # ---- FermionDetMatrix (src/FermionDetMatrix.jl:19-55, 66-111, 137-204) ------------------------------------------
@@ -118,6 +125,7 @@ function KPMPreconditioner(f::FermionDetMatrix{T,E}; rng::AbstractRNG = Random.d
     check(ccall((:sq_kpm_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Cdouble, Int64, Cdouble, Cdouble), h, f.h, rbuf, n, a1, a2))
     P = KPMPreconditioner{E}(h[], false, (zero(E), zero(E)))
     finalizer(p -> ccall((:sq_kpm_destroy, LIB), Cint, (Ptr{Cvoid},), p.h), P)
+    check(ccall((:sq_kpm_set_seed, LIB), Cint, (Ptr{Cvoid}, UInt64), P.h, rand(rng, UInt64)))    # library-drawn Lanczos starts (solves inside device-resident trajectories)
     update_preconditioner!(P, f, rng)
     return P
 end
@@ -153,26 +161,49 @@ ldiv!(f::FermionDetMatrix, v::AbstractVecOrMat; kw...) = ldiv!(v, f, v; kw...)
 # ---- electron-phonon tables: the fields of SmoQyDQMC.ElectronPhononParameters the path reads ---------------------
 mutable struct B200ElPh
     h::Ptr{Cvoid}
+    bare_set::Bool          # bare on-site energies / hoppings uploaded (needs the FermionPathIntegral: see _ensure_bare!)
 end
 const _ELPH_OF_FDM = Dict{Ptr{Cvoid}, WeakRef}()     # operator handle -> its device-side tables (update_chemical_potential! has no other route to them)
-function B200ElPh(elph::ElectronPhononParameters{T,E}, fpi::FermionPathIntegral{T,E}, tbp, f::FermionDetMatrix{T,E}) where {T,E}
+# Only what ElectronPhononParameters itself holds is needed here, so PFFCalculator(elph, fdm) keeps the reference's two positional
+# arguments (src/PFFCalculator.jl:30-33).  Models the device path does not implement fail HERE, loudly, instead of sampling a wrong action.
+function B200ElPh(elph::ElectronPhononParameters{T,E}, f::FermionDetMatrix{T,E}) where {T,E}
+    T <: Real || error("libsmoqyelph_b200 supports real hoppings / couplings only (T = $T)")
     ph = elph.phonon_parameters; hol = elph.holstein_parameters_up; ssh = elph.ssh_parameters_up
+    disp = elph.dispersion_parameters
+    disp.Ndispersion == 0 || error("libsmoqyelph_b200: dispersive phonon couplings (Ndispersion = $(disp.Ndispersion)) are not implemented " *
+                                   "(bosonic action and eval_derivative_dispersive_action!, src/EFAPFFHMCUpdater.jl:193); use the CPU path for this model")
+    (all(iszero, imag.(ssh.α)) && all(iszero, imag.(ssh.α2)) && all(iszero, imag.(ssh.α3)) && all(iszero, imag.(ssh.α4))) ||
+        error("libsmoqyelph_b200: complex SSH couplings are not implemented")
+    (elph.holstein_parameters_up === elph.holstein_parameters_dn || elph.holstein_parameters_up.α == elph.holstein_parameters_dn.α) ||
+        error("libsmoqyelph_b200: spin-dependent Holstein couplings are not implemented")
     nun = hol.nholstein == 0 ? 1 : hol.Nholstein ÷ hol.nholstein
     phsym = Int32[hol.ph_sym_form[(c - 1) ÷ nun + 1] for c in 1:hol.Nholstein]       # expanded per coupling
     hop_of = zeros(Int64, ssh.Nssh)                                                  # inverse of hopping_to_couplings
     for (hop, cs) in enumerate(ssh.hopping_to_couplings), c in cs; hop_of[c] = hop; end
-    V0 = Vector{E}(tbp.ϵ .- tbp.μ); t0 = Vector{E}(real.(tbp.t))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:sq_elph_create, LIB), Cint,
         (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Cdouble, Int64, Ptr{E}, Ptr{E}, Ptr{E}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{E}, Ptr{E}, Ptr{E}, Ptr{E},
          Ptr{Int32}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{E}, Ptr{E}, Ptr{E}, Ptr{E}, Ptr{E}, Ptr{E}),
         h, f.h, elph.Δτ, length(ph.Ω), ph.Ω, ph.Ω4, ph.M, hol.Nholstein, Vector{Int64}(hol.coupling_to_phonon), Vector{Int64}(hol.coupling_to_site),
         hol.α, hol.α2, hol.α3, hol.α4, phsym, ssh.Nssh, Matrix{Int64}(ssh.coupling_to_phonon), hop_of, real.(ssh.α), real.(ssh.α2),
-        real.(ssh.α3), real.(ssh.α4), V0, t0))
-    e = B200ElPh(h[])
+        real.(ssh.α3), real.(ssh.α4), C_NULL, C_NULL))
+    e = B200ElPh(h[], false)
     finalizer(x -> ccall((:sq_elph_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), e)
     _ELPH_OF_FDM[f.h] = WeakRef(e)
     return e
+end
+# The bare on-site energies (eps - mu) and hoppings are what is left of the path integral once the phonon contribution is taken out --
+# the very operation the reference's trajectory performs (`SmoQyDQMC.update!(fpi, elph, x, -1)`, src/EFAPFFHMCUpdater.jl:198).  Done once,
+# by the first call that carries the FermionPathIntegral (hmc_update!, the global moves, update_chemical_potential!).
+function _ensure_bare!(e::B200ElPh, elph::ElectronPhononParameters{T,E}, fpi::FermionPathIntegral{T,E}) where {T,E}
+    e.bare_set && return nothing
+    all(iszero, imag.(fpi.t)) || error("libsmoqyelph_b200 supports real hoppings only (SURVEY.md 9 Q9)")
+    SmoQyDQMC.update!(fpi, elph, elph.x, -1)
+    V0 = Vector{E}(fpi.V[:, 1]); t0 = Vector{E}(real.(fpi.t[:, 1]))
+    SmoQyDQMC.update!(fpi, elph, elph.x, +1)
+    check(ccall((:sq_elph_set_bare, LIB), Cint, (Ptr{Cvoid}, Ptr{E}, Ptr{E}), e.h, V0, t0))
+    e.bare_set = true
+    return nothing
 end
 push_x!(e::B200ElPh, x::Matrix{Float64}) = check(ccall((:sq_elph_set_x, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), e.h, x))
 pull_x!(x::Matrix{Float64}, e::B200ElPh) = check(ccall((:sq_elph_get_x, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), e.h, x))
@@ -181,30 +212,39 @@ pull_x!(x::Matrix{Float64}, e::B200ElPh) = check(ccall((:sq_elph_get_x, LIB), Ci
 mutable struct PFFCalculator{E<:AbstractFloat}
     h::Ptr{Cvoid}; elph::B200ElPh
 end
-function PFFCalculator(elph::ElectronPhononParameters{T,E}, f::FermionDetMatrix{T,E}; fermion_path_integral, tight_binding_parameters) where {T,E}
-    e = B200ElPh(elph, fermion_path_integral, tight_binding_parameters, f)
+function PFFCalculator(elph::ElectronPhononParameters{T,E}, f::FermionDetMatrix{T,E}) where {T,E}      # src/PFFCalculator.jl:30-33
+    e = B200ElPh(elph, f)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:sq_pff_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cvoid}), h, e.h))
     p = PFFCalculator{E}(h[], e)
     finalizer(x -> ccall((:sq_pff_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), p)
     return p
 end
-function calculate_fermionic_action!(p::PFFCalculator{E}, elph, f, preconditioner, rng::AbstractRNG, tol::E, maxiter::Int) where {E}
+# The three methods below take the reference's positional arguments (src/PFFCalculator.jl:56-158).  As there, the operator is whatever the
+# caller last set with update!(fdm, fpi); only x travels (it enters Λ and the coupling derivatives).
+# sample_pseudofermion_fields!(pff, elph, fdm, rng) -> Sf: the randn!(rng, Φ) draw is made here so that the caller's rng determines Φ.
+function sample_pseudofermion_fields!(p::PFFCalculator{E}, elph, f::FermionDetMatrix, rng::AbstractRNG = Random.default_rng()) where {E}
     push_x!(p.elph, elph.x)
-    check(ccall((:sq_elph_refresh_fdm, LIB), Cint, (Ptr{Cvoid},), p.elph.h))
+    R = randn(rng, Complex{E}, f.Lτ, f.N)
+    Sf = Ref{Cdouble}(0)
+    GC.@preserve R check(ccall((:sq_pff_sample, LIB), Cint, (Ptr{Cvoid}, Ptr{Complex{E}}, Ref{Cdouble}), p.h, R, Sf))
+    return Sf[]
+end
+function calculate_fermionic_action!(p::PFFCalculator{E}, elph, f, preconditioner, rng::AbstractRNG, tol::E = f.cgs.tol,
+                                     maxiter::Int = f.cgs.maxiter) where {E}
+    push_x!(p.elph, elph.x)
     start = preconditioner isa KPMPreconditioner ? randn(rng, E, f.N) : E[]
     Sf = Ref{Cdouble}(0); it = Ref{Int64}(0); ϵ = Ref{Cdouble}(0)
-    check(ccall((:sq_pff_action, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{E}, Cdouble, Int64, Ref{Cdouble}, Ref{Int64}, Ref{Cdouble}),
+    GC.@preserve start check(ccall((:sq_pff_action, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{E}, Cdouble, Int64, Ref{Cdouble}, Ref{Int64}, Ref{Cdouble}),
                 p.h, _kpm_handle(preconditioner), isempty(start) ? C_NULL : pointer(start), tol, maxiter, Sf, it, ϵ))
     return Sf[], Int(it[]), ϵ[]
 end
 function calculate_derivative_fermionic_action!(∂Sf∂x::AbstractMatrix{E}, p::PFFCalculator{E}, elph, f, preconditioner, rng::AbstractRNG,
-                                                tol::E, maxiter::Int) where {E}
+                                                tol::E = f.cgs.tol, maxiter::Int = f.cgs.maxiter) where {E}
     push_x!(p.elph, elph.x)
-    check(ccall((:sq_elph_refresh_fdm, LIB), Cint, (Ptr{Cvoid},), p.elph.h))
     start = preconditioner isa KPMPreconditioner ? randn(rng, E, f.N) : E[]
     Sf = Ref{Cdouble}(0); it = Ref{Int64}(0); ϵ = Ref{Cdouble}(0)
-    check(ccall((:sq_pff_force, LIB), Cint, (Ptr{Cvoid}, Ptr{E}, Ptr{Cvoid}, Ptr{E}, Cdouble, Int64, Ref{Cdouble}, Ref{Int64}, Ref{Cdouble}),
+    GC.@preserve ∂Sf∂x start check(ccall((:sq_pff_force, LIB), Cint, (Ptr{Cvoid}, Ptr{E}, Ptr{Cvoid}, Ptr{E}, Cdouble, Int64, Ref{Cdouble}, Ref{Int64}, Ref{Cdouble}),
                 p.h, ∂Sf∂x, _kpm_handle(preconditioner), isempty(start) ? C_NULL : pointer(start), tol, maxiter, Sf, it, ϵ))
     return Sf[], Int(it[]), ϵ[]
 end
@@ -229,9 +269,13 @@ function hmc_update!(elph::ElectronPhononParameters{T,E}, u::EFAPFFHMCUpdater{E}
         u.h == C_NULL || ccall((:sq_hmc_destroy, LIB), Cint, (Ptr{Cvoid},), u.h)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:sq_hmc_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cvoid}, Int64, Cdouble, Cdouble, Cdouble, UInt64),
-                    h, pff_calculator.h, Nt, Δt, u.η, δ, rand(rng, UInt64)))
+                    h, pff_calculator.h, Nt, Δt, u.η, δ, UInt64(0)))
         u.h = h[]; u.Nt = Nt; u.Δt = Δt; u.δ = δ
     end
+    # every trajectory draws its device-side randoms (Φ, momenta, Lanczos starts, the two uniforms) from a Philox stream keyed by
+    # ONE draw from the caller's rng: the rng state passed in determines the trajectory, call after call
+    check(ccall((:sq_hmc_set_seed, LIB), Cint, (Ptr{Cvoid}, UInt64), u.h, rand(rng, UInt64)))
+    _ensure_bare!(pff_calculator.elph, elph, fermion_path_integral)
     push_x!(pff_calculator.elph, elph.x)
     check(ccall((:sq_elph_refresh_fdm, LIB), Cint, (Ptr{Cvoid},), pff_calculator.elph.h))
     acc = Ref{Cint}(0); info = zeros(Cdouble, 8)
@@ -252,6 +296,7 @@ end
 function _global_move!(elph, p::PFFCalculator{E}, mutate_dev!::Function, mutate_host!::Function, logJ::E; fermion_path_integral,
                        fermion_det_matrix, rng, preconditioner, tol::E, maxiter::Int) where {E}
     e = p.elph
+    _ensure_bare!(e, elph, fermion_path_integral)
     push_x!(e, elph.x)
     check(ccall((:sq_elph_refresh_fdm, LIB), Cint, (Ptr{Cvoid},), e.h))
     Sf = sample_pseudofermion_fields!(p, elph, fermion_det_matrix, rng)
@@ -265,8 +310,8 @@ function _global_move!(elph, p::PFFCalculator{E}, mutate_dev!::Function, mutate_
         Sb′ = Ref{Cdouble}(0); check(ccall((:sq_elph_bosonic_action, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}), e.h, Sb′))
         P = min(1.0, exp(-((Sf′ + Sb′[]) - (Sf + Sb[])) + logJ))
     catch err
-        err isa B200Error || rethrow()
-        @info "Failed to evaluate the fermionic action for the proposed state, update rejected." exception = err
+        err isa B200NumericalInstability || rethrow()       # CUDA / argument / watchdog errors are not instabilities
+        @warn "Failed to evaluate the fermionic action for the proposed state, update rejected." exception = err
     end
     if rand(rng) < P
         x0 = copy(elph.x)
@@ -328,6 +373,7 @@ end
 function update_greens_estimator!(g::GreensEstimator{E}, f::FermionDetMatrix; preconditioner = I, rng = Random.default_rng(),
                                   maxiter::Int, tol::E) where {E}
     avg = Ref{Cdouble}(0)
+    check(ccall((:sq_greens_set_seed, LIB), Cint, (Ptr{Cvoid}, UInt64), g.h, rand(rng, UInt64)))     # the caller's rng keys the random vectors
     check(ccall((:sq_greens_update, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Int64, Ref{Cdouble}),
                 g.h, _kpm_handle(preconditioner), C_NULL, tol, maxiter, avg))
     return avg[]
@@ -399,15 +445,88 @@ function measure_double_occ(g::GreensEstimator{E}, orbital::Int; n::Int = g.n) w
     check(ccall((:sq_greens_measure_double_occ_orbital, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Complex{E}}), g.h, n, orbital, out))
     return out[1]
 end
-# make_measurements!(measurement_container, fdm, greens_estimator; ...) -> iters  (src/Measurements/make_measurements.jl:19-90).
-# The estimator refresh runs on the device; the accumulation into SmoQyDQMC's container is the reference's own host code
-# (make_global_measurements!, make_local_measurements!, make_correlation_measurements!, :92-913), which only calls the measure_*
-# methods this module provides -- it is passed in as `accumulate!` so that this file does not duplicate it.
-function make_measurements!(measurement_container, f::FermionDetMatrix{T,E}, g::GreensEstimator{E}; model_geometry, fermion_path_integral,
+# make_measurements!(measurement_container, fdm, greens_estimator; ...) -> iters  (src/Measurements/make_measurements.jl:19-90), same
+# keywords as the reference.  The estimator refresh runs on the device; the global and the local measurements (:92-146, tight-binding and
+# electron-phonon energies, tight_binding_measurements.jl:2-133 / electron_phonon_measurements.jl) are accumulated here from this module's
+# measure_* methods.  The correlation bodies (:161-913) walk SmoQyDQMC's container and call measure_*_correlation! -- host code of the
+# reference package that works unchanged on this GreensEstimator; the integrating package registers it once:
+#     SmoQyElPhB200.CORRELATION_MEASUREMENTS[] = (mc, g, mg, tbp, fpi) -> begin
+#         SmoQyElPhQMC.make_correlation_measurements!(mc, g, mg, tbp, fpi)
+#         SmoQyElPhQMC.make_composite_correlation_measurements!(mc, g, mg, tbp, fpi)
+#     end
+# A container that requests correlations while no such function is registered is an ERROR, never a silent no-op.
+const CORRELATION_MEASUREMENTS = Ref{Union{Nothing,Function}}(nothing)
+const PHONON_GREENS_MEASUREMENTS = Ref{Union{Nothing,Function}}(nothing)     # make_phonon_greens_measurements! (pure host code on x)
+
+function make_global_measurements!(gm::AbstractDict, tight_binding_parameters, electron_phonon_parameters, g::GreensEstimator)   # :92-117
+    gm["sgn"] += 1.0
+    for k in ("sgndetGup", "sgndetGdn", "logdetGup", "logdetGdn", "action_fermionic", "action_total"); gm[k] = NaN; end
+    gm["action_bosonic"] += SmoQyDQMC.bosonic_action(electron_phonon_parameters)
+    density, docc, N2 = _measure(g)
+    gm["density_up"] += density; gm["density_dn"] += density; gm["density"] += 2 * density
+    gm["double_occ"] += docc; gm["Nsqrd"] += N2
+    gm["chemical_potential"] += tight_binding_parameters.μ
+    return nothing
+end
+function make_local_measurements!(lm::AbstractDict, model_geometry, tight_binding_parameters, electron_phonon_parameters, fermion_path_integral,
+                                  g::GreensEstimator)                                                                           # :120-146
+    for n in 1:g.n
+        density = measure_n(g, n)
+        lm["density_up"][n] += density; lm["density_dn"][n] += density; lm["density"][n] += 2 * density
+        lm["double_occ"][n] += measure_double_occ(g, n)
+    end
+    # make_tight_binding_measurements! (tight_binding_measurements.jl:2-40).  The reference adds the modulated hopping energy under the
+    # bare_hopping_energy keys as well (SURVEY.md Q8, not propagated: each value goes to its own key).
+    for n in 1:g.n
+        e = measure_onsite_energy(g, tight_binding_parameters, n)
+        lm["onsite_energy_up"][n] += e; lm["onsite_energy_dn"][n] += e; lm["onsite_energy"][n] += 2 * e
+    end
+    for hid in 1:length(tight_binding_parameters.bond_ids)
+        e0 = measure_bare_hopping_energy(g, tight_binding_parameters, model_geometry, hid)
+        lm["bare_hopping_energy_up"][hid] += e0; lm["bare_hopping_energy_dn"][hid] += e0; lm["bare_hopping_energy"][hid] += 2 * e0
+        e1 = measure_hopping_energy(g, tight_binding_parameters, fermion_path_integral, hid)
+        lm["hopping_energy_up"][hid] += e1; lm["hopping_energy_dn"][hid] += e1; lm["hopping_energy"][hid] += 2 * e1
+    end
+    # make_electron_phonon_measurements! (electron_phonon_measurements.jl:2-58): the phonon energies and moments are SmoQyDQMC's host
+    # arithmetic on x; the electron-phonon energies need the estimator
+    x = electron_phonon_parameters.x
+    hol = electron_phonon_parameters.holstein_parameters_up; ssh = electron_phonon_parameters.ssh_parameters_up
+    ph = electron_phonon_parameters.phonon_parameters
+    for id in 1:ph.nphonon
+        lm["phonon_kin_energy"][id] += SmoQyDQMC.measure_phonon_kinetic_energy(ph, x, electron_phonon_parameters.Δτ, id)
+        lm["phonon_pot_energy"][id] += SmoQyDQMC.measure_phonon_potential_energy(ph, x, id)
+        for (key, pw) in (("X", 1), ("X2", 2), ("X3", 3), ("X4", 4))
+            lm[key][id] += SmoQyDQMC.measure_phonon_position_moment(ph, x, id, pw)
+        end
+    end
+    for id in 1:hol.nholstein
+        e = measure_holstein_energy(hol, g, x, id)
+        lm["holstein_energy_up"][id] += e; lm["holstein_energy_dn"][id] += e; lm["holstein_energy"][id] += 2 * e
+    end
+    for id in 1:ssh.nssh
+        e = measure_ssh_energy(ssh, g, x, id)
+        lm["ssh_energy_up"][id] += e; lm["ssh_energy_dn"][id] += e; lm["ssh_energy"][id] += 2 * e
+    end
+    return nothing
+end
+_requests_correlations(mc) = any(k -> hasproperty(mc, k) && !isempty(getproperty(mc, k)),
+    (:equaltime_correlations, :time_displaced_correlations, :integrated_correlations,
+     :equaltime_composite_correlations, :time_displaced_composite_correlations, :integrated_composite_correlations))
+function make_measurements!(measurement_container::NamedTuple, f::FermionDetMatrix{T,E}, g::GreensEstimator{E}; model_geometry, fermion_path_integral,
                             tight_binding_parameters, electron_phonon_parameters, preconditioner = I, rng::AbstractRNG = Random.default_rng(),
-                            tol::E = f.cgs.tol, maxiter::Int = f.cgs.maxiter, accumulate!::Function = (args...) -> nothing) where {T,E}
+                            tol::E = f.cgs.tol, maxiter::Int = f.cgs.maxiter) where {T,E}
     iters = update_greens_estimator!(g, f; preconditioner, rng, tol, maxiter)
-    accumulate!(measurement_container, g, model_geometry, tight_binding_parameters, electron_phonon_parameters, fermion_path_integral)
+    make_global_measurements!(measurement_container.global_measurements, tight_binding_parameters, electron_phonon_parameters, g)
+    make_local_measurements!(measurement_container.local_measurements, model_geometry, tight_binding_parameters, electron_phonon_parameters,
+                             fermion_path_integral, g)
+    if _requests_correlations(measurement_container)
+        fn = CORRELATION_MEASUREMENTS[]
+        fn === nothing && error("make_measurements!: the measurement container requests correlation measurements, but no correlation driver is " *
+                                "registered (set SmoQyElPhB200.CORRELATION_MEASUREMENTS[], see the comment above make_measurements!)")
+        fn(measurement_container, g, model_geometry, tight_binding_parameters, fermion_path_integral)
+    end
+    pg = PHONON_GREENS_MEASUREMENTS[]
+    pg === nothing || pg(measurement_container, model_geometry, electron_phonon_parameters)
     return iters
 end
 # update_chemical_potential!(fdm, greens_estimator; ...) -> iters  (src/update_chemical_potential.jl:21-73): solves and the two scalar
@@ -427,7 +546,7 @@ function update_chemical_potential!(f::FermionDetMatrix{T,E}, g::GreensEstimator
     V = fermion_path_integral.V
     @. V += -μ + μ′
     ref = get(_ELPH_OF_FDM, f.h, nothing)
-    if ref !== nothing && ref.value !== nothing
+    if ref !== nothing && ref.value !== nothing && ref.value.bare_set       # (not yet set: _ensure_bare! will read the shifted V later)
         check(ccall((:sq_elph_shift_mu, LIB), Cint, (Ptr{Cvoid}, Cdouble), ref.value.h, μ - μ′))
     end
     update!(f, fermion_path_integral)
@@ -474,7 +593,8 @@ function measure_hopping_energy(g::GreensEstimator{E}, tight_binding_parameters,
 end
 # measure_holstein_energy(holstein_parameters, greens_estimator, x, holstein_id)  (src/Measurements/electron_phonon_measurements.jl:60-122).
 # As in the reference the density is taken in the unit cell of the phonon (orbital of the first coupling of this id), the phonons of
-# the id are the contiguous rows phonon_i:phonon_f of x, and the odd terms use x and x^2 (:113).
+# the id are the contiguous rows phonon_i:phonon_f of x.  The cubic coupling multiplies x^3 (the reference has x^2 at :115, a typo that
+# SURVEY.md Q8 says not to propagate; the two agree for every shipped model, where α3 = 0).
 function measure_holstein_energy(holstein_parameters, g::GreensEstimator{E}, x::Matrix{E}, holstein_id::Int) where {E}
     (; coupling_to_site, coupling_to_phonon, ph_sym_form) = holstein_parameters
     N = g.N; n = g.n; Lτ = g.Lτ
@@ -488,7 +608,7 @@ function measure_holstein_energy(holstein_parameters, g::GreensEstimator{E}, x::
     for l in 1:Lτ, u in 1:N
         xv = x[phonon_i + u - 1, l]
         even = α2[u] * xv^2 + α4[u] * xv^4
-        odd = α1[u] * xv + α3[u] * xv^2
+        odd = α1[u] * xv + α3[u] * xv^3
         w[orbital_id + n * (u - 1), l] += (even + odd) / (N * Lτ)
         phs && (shift += odd / (2 * N * Lτ))
     end

@@ -21,7 +21,7 @@ import ctypes as C
 import numpy as np
 
 from . import lib as _l
-from .lib import SqError, check, ptr  # noqa: F401
+from .lib import SqError, SqNumericalInstability, check, ptr  # noqa: F401
 
 OP_M, OP_MT, OP_MTM, OP_MMT = 0, 1, 2, 3
 
@@ -184,6 +184,16 @@ class FermionDetMatrix:
     @property
     def launch_count(self): return int(self.L.sq_fdm_launch_count(self.h))
 
+    STAT_NAMES = ("cg_solves", "cg_resident", "cg_persistent_smem", "cg_launch_loop", "cg_preconditioned", "cg_slab_nccl", "cg_slab_resident",
+                  "watchdog_aborts", "instabilities", "cg_iterations", "kpm_register", "kpm_smem", "cg_batched_rhs", "cg_slab_preconditioned")
+
+    @property
+    def stats(self):
+        """Diagnostic counters (sq_fdm_stats): which solver ran how often, watchdog aborts of the resident kernels, instabilities."""
+        out = np.zeros(16, np.int64)
+        check(self.L.sq_fdm_stats(self.h, ptr(out), 16))
+        return dict(zip(self.STAT_NAMES, (int(v) for v in out)))
+
 
 def SymFermionDetMatrix(model, **kw): return FermionDetMatrix(model, sym=True, **kw)
 def AsymFermionDetMatrix(model, **kw): return FermionDetMatrix(model, sym=False, **kw)
@@ -192,11 +202,13 @@ def AsymFermionDetMatrix(model, **kw): return FermionDetMatrix(model, sym=False,
 class KPMPreconditioner:
     """KPMPreconditioner(fdm; rng, rbuf, n, a1, a2) (src/KPMPreconditioner.jl:198-284)."""
 
-    def __init__(self, fdm, rbuf=0.10, n=20, a1=1.0, a2=1.0, lanczos_start=None, update=True):
+    def __init__(self, fdm, rbuf=0.10, n=20, a1=1.0, a2=1.0, lanczos_start=None, update=True, seed=None):
         self.L, self.fdm = fdm.L, fdm
         h = C.c_void_p()
         check(self.L.sq_kpm_create(C.byref(h), fdm.h, rbuf, n, a1, a2))
         self.h = h
+        if seed is not None:            # `rng` of KPMPreconditioner(fdm; rng, ...): keys the library-drawn Lanczos start vectors
+            check(self.L.sq_kpm_set_seed(self.h, int(seed) & (2 ** 64 - 1)))
         if update:
             self.update(lanczos_start)
 
@@ -307,11 +319,13 @@ class ElectronPhononParameters:
 class PFFCalculator:
     """PFFCalculator(elph, fdm) (src/PFFCalculator.jl:30-53)."""
 
-    def __init__(self, elph, fdm=None, exact_holstein=False):
+    def __init__(self, elph, fdm=None, exact_holstein=False, seed=None):
         self.L, self.elph, self.fdm = elph.L, elph, elph.fdm
         h = C.c_void_p()
         check(self.L.sq_pff_create(C.byref(h), elph.h))
         self.h = h
+        if seed is not None:            # keys the library-drawn pseudofermion noise (global moves); default: derived from the HMC seed
+            check(self.L.sq_pff_set_seed(self.h, int(seed) & (2 ** 64 - 1)))
         check(self.L.sq_pff_set_exact_holstein(self.h, int(exact_holstein)))
 
     def close(self):
@@ -403,6 +417,13 @@ class EFAPFFHMCUpdater:
                                    ptr(rnd), 0 if rnd is None else rnd.size, C.byref(acc), ptr(info)))
         self.info = info
         return bool(acc.value), info[0]
+
+    @property
+    def last_reject(self):
+        """Reason of the last forced rejection (numerical instability inside the trajectory), '' if the last update was stable."""
+        return self.L.sq_hmc_last_reject(self.h).decode()
+
+    def set_seed(self, seed): check(self.L.sq_hmc_set_seed(self.h, int(seed) & (2 ** 64 - 1)))
 
     def init_momentum(self, R):
         m = self.elph.model
@@ -746,19 +767,22 @@ def _global_move(elph, pff, mutate, log_jacobian, preconditioner, tol, maxiter, 
     mutate()
     elph.update_fdm()
     dS, iters, stable = np.inf, 0, True
+    reason = ""
     try:
         Sf2, iters, _ = pff.calculate_fermionic_action(preconditioner=preconditioner, tol=tol, maxiter=maxiter)
         dS = (Sf2 + elph.bosonic_action()) - (Sf + Sb)
         stable = np.isfinite(dS)
-    except SqError:
-        stable = False
+    except SqNumericalInstability as err:       # only instabilities reject (reflection_update.jl:111-127); CUDA / argument errors propagate
+        stable, reason = False, str(err)
+        import warnings
+        warnings.warn("Failed to evaluate the fermionic action for the proposed state, update rejected: " + reason)
     P = min(1.0, float(np.exp(-dS + log_jacobian))) if stable else 0.0
     u = float(rng.random()) if u_accept is None else float(u_accept)
     accepted = u < P
     if not accepted:
         elph.restore_x()
         elph.update_fdm()
-    return accepted, int(iters), {"dS": float(dS), "P": P, "stable": stable}
+    return accepted, int(iters), {"dS": float(dS), "P": P, "stable": stable, "reason": reason}
 
 
 def reflection_update(elph, pff, rng=None, preconditioner=None, tol=None, maxiter=None, phonon_types=None, randoms=None):

@@ -13,6 +13,7 @@ void sq_set_last_error(const std::string &m) { g_last_error = m; }
 #define SQ_TRY try {
 #define SQ_CATCH                                                              \
     }                                                                         \
+    catch (const SqNumericalInstability &e) { sq_set_last_error(e.what()); return 3; } \
     catch (const std::exception &e) { sq_set_last_error(e.what()); return 1; } \
     catch (...) { sq_set_last_error("unknown C++ exception"); return 2; }     \
     return 0;
@@ -238,6 +239,7 @@ int sq_fdm_set_fast_path(sq_fdm *f, int enable) {
     f->use_v3 = ((enable & 255) == 2) ? 1 : 0;
     if (f->use_v3 && (enable >> 8) >= 1 && (enable >> 8) <= 7) f->v3_S = enable >> 8;
     f->v3_cg = f->use_v3;
+    if (f->slab < 1) { f->slab = 1; f->threads = 256; }     // never tuned: a valid default for the shared-memory kernels
     f->manual_tuning = 1;
     SQ_CATCH
 }
@@ -262,6 +264,12 @@ int sq_fdm_stream(sq_fdm *f, void **cuda_stream) {
     SQ_CATCH
 }
 int64_t sq_fdm_launch_count(sq_fdm *f) { return f ? f->launches : -1; }
+int sq_fdm_stats(sq_fdm *f, int64_t *out, int n) {
+    SQ_TRY
+    SQ_REQUIRE(f && out && n >= 0, "bad argument");
+    for (int q = 0; q < n; q++) out[q] = q < SQ_NSTATS ? f->stats[q] : 0;
+    SQ_CATCH
+}
 
 int sq_fdm_cg(sq_fdm *f, sq_complex *x, const sq_complex *b, int zero_start, sq_kpm *kpm, int refresh_kpm,
               const double *lanczos_start, double tol, int64_t maxiter, int64_t *iters, double *eps) {
@@ -301,6 +309,13 @@ int sq_fdm_cg_dev(sq_fdm *f, void *d_x, const void *d_b, int zero_start, sq_kpm 
 int sq_kpm_create(sq_kpm **out, sq_fdm *f, double rbuf, int64_t n, double a1, double a2) {
     SQ_TRY
     kpm_create_impl(out, f, rbuf, n, a1, a2);
+    SQ_CATCH
+}
+int sq_kpm_set_seed(sq_kpm *k, uint64_t seed) {
+    SQ_TRY
+    SQ_REQUIRE(k, "NULL handle");
+    k->seed = seed;
+    k->rng_counter = 0;
     SQ_CATCH
 }
 int sq_kpm_destroy(sq_kpm *k) {
@@ -375,6 +390,13 @@ int sq_elph_create(sq_elph **out, sq_fdm *f, double dtau, int64_t Nph, const dou
     SQ_TRY
     elph_create_impl(out, f, dtau, Nph, Omega, Omega4, M, Nhol, hol_phonon, hol_site, hol_a, hol_a2, hol_a3, hol_a4, hol_phsym, Nssh,
                      ssh_phonon, ssh_hopping, ssh_a, ssh_a2, ssh_a3, ssh_a4, V0, t0);
+    SQ_CATCH
+}
+int sq_elph_set_bare(sq_elph *e, const double *V0, const double *t0) {
+    SQ_TRY
+    SQ_REQUIRE(e, "NULL handle");
+    SQ_CUDA(cudaSetDevice(e->f->device));
+    elph_set_bare(e, V0, t0);
     SQ_CATCH
 }
 int sq_elph_destroy(sq_elph *e) {
@@ -505,6 +527,14 @@ int sq_pff_create(sq_pff **out, sq_elph *e) {
     pff_create_impl(out, e);
     SQ_CATCH
 }
+int sq_pff_set_seed(sq_pff *p, uint64_t seed) {
+    SQ_TRY
+    SQ_REQUIRE(p, "NULL handle");
+    p->seed = seed;
+    p->seed_set = true;
+    p->rng_counter = 0;
+    SQ_CATCH
+}
 int sq_pff_destroy(sq_pff *p) {
     SQ_TRY
     if (p) { fdm_sync_if_alive(p->owner); delete p; }
@@ -619,6 +649,14 @@ int sq_hmc_update(sq_hmc *h, sq_kpm *kpm, double tol_action, double tol_force, i
     *accepted = hmc_update_impl(h, kpm, tol_action, tol_force, maxiter, randoms, nrandoms, info);
     SQ_CATCH
 }
+int sq_hmc_set_seed(sq_hmc *h, uint64_t seed) {
+    SQ_TRY
+    SQ_REQUIRE(h, "NULL handle");
+    h->seed = seed;
+    h->counter = 0;
+    SQ_CATCH
+}
+const char *sq_hmc_last_reject(sq_hmc *h) { return h ? h->last_reject.c_str() : ""; }
 int sq_hmc_init_momentum(sq_hmc *h, const double *R, double *p, double *K) {
     SQ_TRY
     SQ_REQUIRE(h && R && p && K, "NULL argument");
@@ -659,6 +697,13 @@ int sq_hmc_evolve(sq_hmc *h, double *x, double *p, double dt) {
 int sq_greens_create(sq_greens **out, sq_fdm *f, int64_t Nrv, uint64_t seed) {
     SQ_TRY
     greens_create_impl(out, f, Nrv, seed);
+    SQ_CATCH
+}
+int sq_greens_set_seed(sq_greens *g, uint64_t seed) {
+    SQ_TRY
+    SQ_REQUIRE(g, "NULL handle");
+    g->seed = seed;
+    g->counter = 0;
     SQ_CATCH
 }
 int sq_greens_destroy(sq_greens *g) {

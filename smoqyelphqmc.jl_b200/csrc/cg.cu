@@ -207,9 +207,7 @@ int fdm_v3_launch_cg(sq_fdm *f, double2 *z, const double2 *p_old, double2 *p_new
                      double *pAp_part, bool native);
 int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native);
 void fdm_v3_prepare_native(sq_fdm *f);
-bool fdm_v3_cg_persistent(sq_fdm *f, double2 *x, double2 *r, double2 *p0, double2 *p1, CgState *state, double *part_a, double *part_b,
-                          i64 maxiter);
-bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, double2 *halo, CgState *state, double *part_a, double *part_b, i64 maxiter);
+bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, CgState *state, i64 maxiter);
 void fdm_v3_to_native(sq_fdm *f, double2 *dst, const double2 *src);
 void fdm_v3_from_native(sq_fdm *f, double2 *dst, const double2 *src);
 
@@ -279,6 +277,15 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
     k_cg_init<<<1, 64, 0, s>>>(st, part_b, G, part_rz, G, tol);
     SQ_LAUNCH_CHECK();
     f->launches += 4;
+    f->stats[SQ_STAT_CG_SOLVES]++;
+    if (maxiter <= 0) {                     // no iteration may run: report the initial residual (nothing else has written the partials)
+        SQ_CUDA(cudaMemcpyAsync(f->h_cg, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+        SQ_CUDA(cudaStreamSynchronize(s));
+        if (f->h_cg->done == 2) throw SqNumericalInstability("conjugate gradient: NaN encountered in the residual (numerical instability)");
+        *iters = 0;
+        *eps = f->h_cg->eps;
+        return;
+    }
 
     int batch = prec ? 4 : 16;
     if (const char *eb = getenv("SQ_CG_BATCH")) batch = std::max(1, atoi(eb));
@@ -293,15 +300,17 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
         // |r0|^2, |b| and tol; an already converged system (eps0 < tol) is caught first.
         SQ_CUDA(cudaMemcpyAsync(f->h_cg, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
         SQ_CUDA(cudaStreamSynchronize(s));
-        if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+        if (f->h_cg->done == 2) throw SqNumericalInstability("conjugate gradient: NaN encountered in the residual (numerical instability)");
         if (f->h_cg->done) { *iters = 0; *eps = f->h_cg->eps; return; }
         if (fdm_v2_cg_persistent(f, x, r, p, f->tmp1.p, st, part_pAp, part_rr, maxiter)) {
             SQ_CUDA(cudaMemcpyAsync(f->h_cg, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
             SQ_CUDA(cudaStreamSynchronize(s));
-            if (f->h_cg->done == 3) throw SqError("conjugate gradient: grid barrier timed out in the persistent kernel");
-            if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+            f->stats[SQ_STAT_CG_PERSIST_V2]++;
+            if (f->h_cg->done == 3) { f->stats[SQ_STAT_WATCHDOG]++; throw SqError("conjugate gradient: grid barrier timed out in the persistent kernel (watchdog)"); }
+            if (f->h_cg->done == 2) throw SqNumericalInstability("conjugate gradient: NaN encountered in the residual (numerical instability)");
             *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
             *eps = f->h_cg->eps;
+            f->stats[SQ_STAT_CG_ITERS] += *iters;
             return;
         }
     }
@@ -326,17 +335,18 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
                 // one cooperative launch for the whole solve (fdm_v3.cu: k_cg_v3_persistent); k_cg_init left |r0|^2, |b|, tol in st
                 SQ_CUDA(cudaMemcpyAsync(f->h_cg, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
                 SQ_CUDA(cudaStreamSynchronize(s));
-                if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+                if (f->h_cg->done == 2) throw SqNumericalInstability("conjugate gradient: NaN encountered in the residual (numerical instability)");
                 if (f->h_cg->done) { *iters = 0; *eps = f->h_cg->eps; return; }
-                if ((!getenv("SQ_NO_RESIDENT_CG") && fdm_v3_cg_resident(f, x, r, pb[1], st, part_pAp, part_rr, maxiter)) ||
-                    fdm_v3_cg_persistent(f, x, r, pb[0], pb[1], st, part_pAp, part_rr, maxiter)) {
+                if (!getenv("SQ_NO_RESIDENT_CG") && fdm_v3_cg_resident(f, x, r, st, maxiter)) {
                     fdm_v3_from_native(f, x_user, x);
                     SQ_CUDA(cudaMemcpyAsync(f->h_cg, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
                     SQ_CUDA(cudaStreamSynchronize(s));
-                    if (f->h_cg->done == 3) throw SqError("conjugate gradient: grid barrier timed out in the persistent kernel");
-                    if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+                    f->stats[SQ_STAT_CG_RESIDENT]++;
+                    if (f->h_cg->done == 3) { f->stats[SQ_STAT_WATCHDOG]++; throw SqError("conjugate gradient: a grid-wide sum of the resident kernel timed out (watchdog)"); }
+                    if (f->h_cg->done == 2) throw SqNumericalInstability("conjugate gradient: NaN encountered in the residual (numerical instability)");
                     *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
                     *eps = f->h_cg->eps;
+                    f->stats[SQ_STAT_CG_ITERS] += *iters;
                     return;
                 }
                 SQ_CUDA(cudaMemcpyAsync(pb[0], f->v3_r.p, n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
@@ -370,9 +380,11 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
             if (f->h_cg->done || it >= maxiter) finished = true;
         }
         if (native) fdm_v3_from_native(f, x_user, x);
-        if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+        f->stats[SQ_STAT_CG_LOOP]++;
+        if (f->h_cg->done == 2) throw SqNumericalInstability("conjugate gradient: NaN encountered in the residual (numerical instability)");
         *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
         *eps = f->h_cg->eps;
+        f->stats[SQ_STAT_CG_ITERS] += *iters;
         return;
     }
     // is the system already solved?  (cheap check folded into the first batch read-back)
@@ -413,9 +425,11 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
             SQ_CUDA(cudaStreamSynchronize(s));
             if (f->h_cg->done || it >= maxiter) finished = true;
         }
-        if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+        if (f->h_cg->done == 2) throw SqNumericalInstability("conjugate gradient: NaN encountered in the residual (numerical instability)");
         *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
         *eps = f->h_cg->eps;
+        f->stats[SQ_STAT_CG_PREC]++;
+        f->stats[SQ_STAT_CG_ITERS] += *iters;
         if (f->h_cg->done) f->prec_iters_hint[tol < 1e-7 ? 0 : 1] = (int)std::min<i64>(*iters, 1 << 20);
         return;
     }
@@ -450,8 +464,10 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
         SQ_CUDA(cudaStreamSynchronize(s));
         if (f->h_cg->done || it >= maxiter) finished = true;
     }
-    if (f->h_cg->done == 2) throw SqError("conjugate gradient: NaN encountered in the residual (numerical instability)");
+    if (f->h_cg->done == 2) throw SqNumericalInstability("conjugate gradient: NaN encountered in the residual (numerical instability)");
     *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
     *eps = f->h_cg->eps;
+    f->stats[prec ? SQ_STAT_CG_PREC : SQ_STAT_CG_LOOP]++;
+    f->stats[SQ_STAT_CG_ITERS] += *iters;
     if (prec && f->h_cg->done) f->prec_iters_hint[tol < 1e-7 ? 0 : 1] = (int)std::min<i64>(*iters, 1 << 20);
 }

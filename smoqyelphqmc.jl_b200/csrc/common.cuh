@@ -14,6 +14,13 @@ struct SqError : public std::runtime_error {
     explicit SqError(const std::string &m) : std::runtime_error(m) {}
 };
 
+// Thrown by the NaN / non-finite checks (CG residual, Lanczos recurrence, fermionic action).  The reference signals these by
+// throwing and its callers turn them into a rejected update (src/EFAPFFHMCUpdater.jl:168-187,215-231); hmc_update and the
+// global moves catch THIS class only -- bad arguments, CUDA / NCCL errors and watchdog time-outs propagate.  ABI status 3.
+struct SqNumericalInstability : public SqError {
+    explicit SqNumericalInstability(const std::string &m) : SqError(m) {}
+};
+
 void sq_set_last_error(const std::string &m);
 
 #define SQ_CUDA(expr)                                                                                  \

@@ -159,13 +159,28 @@ static void up(DevBuf<T> &b, const std::vector<T> &v, cudaStream_t s) {
     SQ_CUDA(cudaStreamSynchronize(s));
 }
 
+// bare on-site energies (N) and hoppings (Nh, original order): eps - mu and t of TightBindingParameters
+void elph_set_bare(sq_elph *e, const double *V0, const double *t0) {
+    sq_fdm *f = e->f;
+    SQ_REQUIRE(V0 && (t0 || f->Nh == 0), "NULL model array");
+    e->V0.upload(V0, f->N, f->stream);
+    if (f->Nh) e->t0.upload(t0, f->Nh, f->stream);
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
+    // bare hoppings equal inside every colour (|t| and sign): the register path of the fused matvec applies
+    e->t0_coluni = (t0 != nullptr && f->Nh > 0);
+    for (i64 c = 0; c < f->C && e->t0_coluni; c++)
+        for (int h = f->clo[c]; h < f->chi[c]; h++)
+            if (t0[f->h_perm[h]] != t0[f->h_perm[f->clo[c]]]) { e->t0_coluni = false; break; }
+    e->bare_set = true;
+}
+
 void elph_create_impl(sq_elph **out, sq_fdm *f, double dtau, i64 Nph, const double *Om, const double *Om4, const double *M, i64 Nhol,
                       const i64 *hol_ph, const i64 *hol_site, const double *a, const double *a2, const double *a3, const double *a4,
                       const int32_t *hol_sym, i64 Nssh, const i64 *ssh_ph, const i64 *ssh_hop, const double *sa, const double *sa2,
                       const double *sa3, const double *sa4, const double *V0, const double *t0) {
     SQ_REQUIRE(out && f, "NULL argument");
     SQ_REQUIRE(Nph >= 1 && Nhol >= 0 && Nssh >= 0, "bad dimensions");
-    SQ_REQUIRE(Om && Om4 && M && V0 && (t0 || f->Nh == 0), "NULL model array");
+    SQ_REQUIRE(Om && Om4 && M && (!V0 || t0 || f->Nh == 0), "NULL model array");
     SQ_REQUIRE((size_t)f->L * (size_t)Nph < (size_t)1 << 31, "phonon field too large for 32-bit indexing");
     SQ_CUDA(cudaSetDevice(f->device));
     sq_elph *e = new sq_elph();
@@ -218,13 +233,10 @@ void elph_create_impl(sq_elph **out, sq_fdm *f, double dtau, i64 Nph, const doub
         std::vector<int> sitems(2 * Nssh), fillp(cnt.begin(), cnt.end() - 1);
         for (i64 c = 0; c < Nssh; c++) { sitems[fillp[sp[c]]++] = -(int)(c + 1); sitems[fillp[spp[c]]++] = (int)(c + 1); }
         up(e->ph_ssh_ptr, cnt, s); up(e->ph_ssh_cpl, sitems, s);
-        up(e->V0, std::vector<double>(V0, V0 + f->N), s);
-        up(e->t0, std::vector<double>(t0 ? t0 : V0, (t0 ? t0 : V0) + (t0 ? f->Nh : 0)), s);
-        // bare hoppings equal inside every colour (|t| and sign): the register path of the fused matvec applies
-        e->t0_coluni = (t0 != nullptr && f->Nh > 0);
-        for (i64 c = 0; c < f->C && e->t0_coluni; c++)
-            for (int h = f->clo[c]; h < f->chi[c]; h++)
-                if (t0[f->h_perm[h]] != t0[f->h_perm[f->clo[c]]]) { e->t0_coluni = false; break; }
+        // bare tight-binding terms: given now, or later through sq_elph_set_bare (the Julia PFFCalculator(elph, fdm) constructor has
+        // no access to them; they arrive with the first call that carries the FermionPathIntegral)
+        e->V0.alloc(f->N + 1); e->t0.alloc(f->Nh + 1);
+        if (V0) elph_set_bare(e, V0, t0);
     } catch (...) {
         delete e;
         throw;
@@ -234,6 +246,7 @@ void elph_create_impl(sq_elph **out, sq_fdm *f, double dtau, i64 Nph, const doub
 
 void elph_refresh_fdm(sq_elph *e) {
     sq_fdm *f = e->f;
+    SQ_REQUIRE(e->bare_set, "bare on-site energies / hoppings not set: create the model with V0, t0 or call sq_elph_set_bare first");
     ElphDev E = elph_dev(e);
     size_t tot = (size_t)f->L * std::max(f->N, f->Nh);
     k_refresh_from_x<<<(unsigned)((tot + 255) / 256), 256, 0, f->stream>>>(E, f->expV.p, f->cs.p, f->sym ? e->dtau / 2 : e->dtau);
@@ -246,6 +259,7 @@ void elph_refresh_fdm(sq_elph *e) {
 
 void elph_build_Vt(sq_elph *e) {
     sq_fdm *f = e->f;
+    SQ_REQUIRE(e->bare_set, "bare on-site energies / hoppings not set: create the model with V0, t0 or call sq_elph_set_bare first");
     if (!e->V.p) { e->V.alloc((size_t)f->L * f->N); e->t.alloc((size_t)f->L * f->Nh + 1); }
     ElphDev E = elph_dev(e);
     size_t tot = (size_t)f->L * std::max(f->N, f->Nh);

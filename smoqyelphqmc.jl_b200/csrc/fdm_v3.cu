@@ -452,192 +452,6 @@ k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const do
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Persistent cooperative CG on the register path: the whole unpreconditioned solve in ONE launch.
-//
-// Back-to-back dependent launches on this system are paced in ~2 us steps and every launch re-pays the load latency of a
-// single-wave kernel, so the solver keeps every CTA resident and iterates
-//     p = r + beta p_old formed on load (own + halo slice), B, w = M p (|w|^2 partial), B, z = M^T w kept in REGISTERS
-//     -> [grid barrier] -> alpha -> x += alpha p, r -= alpha z (own slices), |r|^2 partial -> [grid barrier] -> eps, beta
-// with all vectors in the native order (coalesced 16-byte accesses) and two grid-wide barriers per iteration (an
-// arrival counter in L2).  Reductions are fixed-order sums of per-CTA partials: bit-reproducible run to run.  Vectors
-// written by other CTAs are read with ld.global.cg.  A watchdog turns a barrier that does not complete into an error.
-// ---------------------------------------------------------------------------------------------------
-struct CgPersist3 {
-    double *x, *r, *p0, *p1;    // native order
-    CgState *state;             // in: rz (= |r0|^2), normb, tol, eps ; out: iters, eps, done
-    double *part_a, *part_b;    // per-CTA partials (p.Ap, |r|^2)
-    unsigned int *barrier;      // arrival counter (zeroed by the host)
-    int *abort_flag;
-    int maxiter;
-    unsigned int slot_stride;   // distance between the grid-sum slots of consecutive CTAs in 16-byte units (spreads them over L2 slices)
-};
-
-__device__ __forceinline__ bool v3_grid_barrier(unsigned int *counter, unsigned int &epoch, unsigned int nblk, int *abort_flag) {
-    __syncthreads();
-    epoch++;
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        const unsigned int target = epoch * nblk;
-        long long t0 = clock64();
-        while (true) {
-            unsigned int v;
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            if (v >= target) break;
-            if (clock64() - t0 > 4000000000LL) { atomicExch(abort_flag, 1); break; }
-        }
-        __threadfence();
-    }
-    __syncthreads();
-    return *((volatile int *)abort_flag) == 0;
-}
-
-template <int LXL, int RY>
-__global__ void __launch_bounds__(256, RY <= 8 ? 2 : 1)
-k_cg_v3_persistent(const __grid_constant__ V3Params P, const CgPersist3 C) {
-    typedef V3Lane<LXL, RY> G;
-    constexpr int N = G::N;
-    extern __shared__ double wsm[];
-    __shared__ double red[32];
-    __shared__ double sh[2];
-    G E;
-    E.template init<1>(P, blockIdx.y);
-    const int L = P.L;
-    const int lane = threadIdx.x & 31, k = threadIdx.x >> 5;
-    const int l0 = P.lb + blockIdx.x * P.S;
-    const int ns = min(P.S, P.le - l0);
-    const unsigned int nblk = gridDim.x * gridDim.y, bid = blockIdx.x + gridDim.x * blockIdx.y;
-    const bool active = k <= ns, owner = active && k >= 1, publish = k < ns;
-    int lin = l0 - 1 + k, lself = l0 + k;
-    lin = lin < 0 ? lin + L : lin;
-    lself = lself >= L ? lself - L : lself;
-    const int lB = lself, lo = l0 + k - 1;
-    const double sg = (lB == 0) ? 1.0 : -1.0;
-    const size_t o_in = ((size_t)lin * 2 + E.part) * N + 2 * lane, o_self = ((size_t)lself * 2 + E.part) * N + 2 * lane;
-    const size_t o_own = ((size_t)(lo < 0 ? 0 : lo) * 2 + E.part) * N + 2 * lane;
-    const double normb = C.state->normb, tol = C.state->tol;
-    double rz = C.state->rz_re, beta = 0.0, eps = C.state->eps;
-    unsigned int epoch = 0;
-    int it = 0, done = 0, pc = 0;
-    double v[RY][4];
-    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = 0;
-    const bool stamp = P.dbg && bid == 0 && threadIdx.x == 32;
-#define V3P_STAMP(q) do { if (stamp) { long long tn = clock64(); tacc[q] += tn - tprev; tprev = tn; } } while (0)
-    if (stamp) tprev = clock64();
-    auto ldcg2 = [](const double *q) -> double2 { return __ldcg(reinterpret_cast<const double2 *>(q)); };
-#pragma unroll 1
-    while (it < C.maxiter) {
-        it++;
-        const double *p_old = pc ? C.p1 : C.p0;
-        double *p_new = pc ? C.p0 : C.p1;
-        double acc = 0.0;
-        if (active) {
-#pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const int e = (r * 2 + jp) * 64;
-                    const double2 rv = ldcg2(C.r + o_in + e), pv = ldcg2(p_old + o_in + e);
-                    v[r][2 * jp] = fma(beta, pv.x, rv.x);
-                    v[r][2 * jp + 1] = fma(beta, pv.y, rv.y);
-                }
-            E.template apply_B<1>(v, lB, P);
-#pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const int e = (r * 2 + jp) * 64;
-                    const double2 rv = ldcg2(C.r + o_self + e), pv = ldcg2(p_old + o_self + e);
-                    const double s0 = fma(beta, pv.x, rv.x), s1 = fma(beta, pv.y, rv.y);
-                    const double w0 = fma(sg, v[r][2 * jp], s0), w1 = fma(sg, v[r][2 * jp + 1], s1);
-                    v[r][2 * jp] = w0; v[r][2 * jp + 1] = w1;
-                    if (publish) {
-                        acc += w0 * w0;
-                        acc += w1 * w1;
-                        reinterpret_cast<double2 *>(wsm)[((k * RY + r) * 2 + jp) * 32 + lane] = make_double2(w0, w1);
-                        *reinterpret_cast<double2 *>(p_new + o_self + e) = make_double2(s0, s1);
-                    }
-                }
-        }
-        V3P_STAMP(0);
-        if (owner) E.template apply_B<1>(v, lB, P);
-        __syncthreads();
-        if (owner) {                                      // z[lo] = w[lo] -/+ B w[lo + 1], stays in registers
-#pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 w = reinterpret_cast<const double2 *>(wsm)[(((k - 1) * RY + r) * 2 + jp) * 32 + lane];
-                    v[r][2 * jp] = fma(sg, v[r][2 * jp], w.x);
-                    v[r][2 * jp + 1] = fma(sg, v[r][2 * jp + 1], w.y);
-                }
-        }
-        {
-            double a[1] = {acc};
-            block_sum<1>(a, red);
-            if (threadIdx.x == 0) C.part_a[bid] = a[0];
-        }
-        V3P_STAMP(1);
-        if (!v3_grid_barrier(C.barrier, epoch, nblk, C.abort_flag)) { done = 3; break; }
-        if (threadIdx.x < 32) {
-            double t = 0.0;
-            for (unsigned int q = threadIdx.x; q < nblk; q += 32) t += __ldcg(C.part_a + q);
-            t = warp_sum(t);
-            if (threadIdx.x == 0) sh[0] = t;
-        }
-        __syncthreads();
-        V3P_STAMP(2);
-        const double alpha = rz / sh[0];
-        acc = 0.0;
-        if (owner) {                                      // x += alpha p ; r -= alpha z ; |r|^2 partial  (slice lo)
-#pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const int e = (r * 2 + jp) * 64;
-                    const double2 pv = ldcg2(p_new + o_own + e), xv = ldcg2(C.x + o_own + e), rv = ldcg2(C.r + o_own + e);
-                    const double r0 = fma(-alpha, v[r][2 * jp], rv.x), r1 = fma(-alpha, v[r][2 * jp + 1], rv.y);
-                    *reinterpret_cast<double2 *>(C.x + o_own + e) = make_double2(fma(alpha, pv.x, xv.x), fma(alpha, pv.y, xv.y));
-                    *reinterpret_cast<double2 *>(C.r + o_own + e) = make_double2(r0, r1);
-                    acc += r0 * r0;
-                    acc += r1 * r1;
-                }
-        }
-        {
-            double a[1] = {acc};
-            block_sum<1>(a, red);
-            if (threadIdx.x == 0) C.part_b[bid] = a[0];
-        }
-        V3P_STAMP(3);
-        if (!v3_grid_barrier(C.barrier, epoch, nblk, C.abort_flag)) { done = 3; break; }
-        if (threadIdx.x < 32) {
-            double t = 0.0;
-            for (unsigned int q = threadIdx.x; q < nblk; q += 32) t += __ldcg(C.part_b + q);
-            t = warp_sum(t);
-            if (threadIdx.x == 0) sh[1] = t;
-        }
-        __syncthreads();
-        V3P_STAMP(4);
-        const double rr = sh[1];
-        eps = sqrt(rr) / normb;
-        if (eps < tol) { done = 1; break; }
-        if (!(eps == eps)) { done = 2; break; }
-        beta = rr / rz;
-        rz = rr;
-        pc ^= 1;
-    }
-    if (stamp) { for (int q = 0; q < 5; q++) P.dbg[q] = tacc[q]; P.dbg[5] = it; }
-    if (bid == 0 && threadIdx.x == 0) {
-        CgState st = *C.state;
-        st.iters = it;
-        st.eps = eps;
-        st.done = done;
-        st.rz_re = rz;
-        *C.state = st;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 typedef void (*v3_kernel_t)(const V3Params, double2 *, const double2 *, double *, const CgState *);
@@ -829,14 +643,12 @@ int fdm_v3_launch_cg(sq_fdm *f, double2 *z, const double2 *p_old, double2 *p_new
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Resident CG: as k_cg_v3_persistent, but nothing except two boundary slices per CTA touches global memory inside the
-// iteration.  The persistent kernel above measured 21 us per iteration at cfg4 although its arithmetic is ~3 us: 75 MB
-// of L2 traffic per iteration (r, p re-read for own + halo slices, x / r / p passes of the update) and two slow grid
-// barriers.  Here one CTA per SM owns S slices (both parts: 2 (S+1) warps) for the whole solve:
+// Resident CG: the whole unpreconditioned solve in ONE cooperative launch.  One CTA per SM owns S slices (both parts:
+// 2 (S+1) warps) for the whole solve and nothing except two boundary slices per CTA touches global memory inside an iteration:
 //   * x and r of the warp's slice live in REGISTERS, p (own + 2 halo slices) and the w hand-over in SHARED memory;
-//   * the neighbours' halo p is rebuilt locally from their updated boundary r (written to a small global buffer before
-//     the second grid barrier, read after it): p_halo = r_halo + beta p_halo -- no extra synchronisation;
-//   * per iteration and CTA: 2 slice-parts x 2 written + read through L2 (~9 MB at cfg4 instead of ~75 MB).
+//   * the neighbours' halo slices are rebuilt locally (see k_cg_v3_resident1 below) -- no extra synchronisation.
+// (Earlier generations -- a persistent kernel that streamed r / p / x through L2, 21 us per iteration at cfg4, and a resident
+// kernel with two grid-wide sums, 9.4 us -- were removed in round 2; the launch loop in cg.cu is the only fallback.)
 // ---------------------------------------------------------------------------------------------------
 // Grid-wide deterministic sum without atomics or a separate barrier: every CTA publishes (value, epoch) in its own 16-byte
 // slot (fence + relaxed store of the epoch), warp 0 of every CTA polls all slots for the epoch with relaxed loads that
@@ -895,229 +707,6 @@ __device__ __forceinline__ double v3_grid_sum(double acc, double *red, double *s
     }
     aborted = __syncthreads_or(bad) != 0;
     return *sh_out;
-}
-
-template <int LXL, int RY>
-__global__ void __launch_bounds__(256, 1)
-k_cg_v3_resident(const __grid_constant__ V3Params P, const CgPersist3 C, double *__restrict__ halo) {
-    typedef V3Lane<LXL, RY> G;
-    constexpr int N = G::N;
-    extern __shared__ double smem[];
-    __shared__ double red[64];
-    __shared__ double sh[4];
-    const int S = P.S, L = P.L;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int part = wid / (S + 1), k = wid - part * (S + 1);
-    G E;
-    E.template init<1>(P, part);
-    const int l0 = P.lb + blockIdx.x * S;
-    const int ns = min(S, P.le - l0);
-    const unsigned int nblk = gridDim.x, bid = blockIdx.x;
-    const bool active = k <= ns, owner = active && k >= 1, publish = k < ns;
-    int lself = l0 + k;
-    lself = lself >= L ? lself - L : lself;
-    const int lB = lself, lo = l0 + k - 1;               // owner: slice lo
-    const double sg = (lB == 0) ? 1.0 : -1.0;
-    double2 *Pb = reinterpret_cast<double2 *>(smem) + (size_t)part * (S + 2) * (N / 2);          // [q = 0 .. S+1][N/2]
-    double2 *W = reinterpret_cast<double2 *>(smem) + (size_t)2 * (S + 2) * (N / 2) + (size_t)part * S * (N / 2);
-    // exp(-dtau V) (native order, scaled) of the S+1 slices this CTA applies, shared by both parts: the grid-wide sums fence at
-    // gpu scope, which invalidates L1, so global loads inside B would go to L2 in every iteration
-    double *EV = smem + (size_t)2 * (2 * S + 2) * N;
-    const double *evk = EV + (size_t)k * N + 2 * lane;
-    auto el = [&](int r, int jp) -> int { return (r * 2 + jp) * 32 + lane; };                    // double2 index inside a slice-part
-    auto gslice = [&](const double *base, int l) -> const double2 * { return reinterpret_cast<const double2 *>(base + ((size_t)l * 2 + part) * N); };
-    // halo buffer: [cta][side][part][N] doubles; side 0 = first own slice, 1 = last own slice
-    auto hslice = [&](unsigned int cta, int side) -> double2 * { return reinterpret_cast<double2 *>(halo + (((size_t)cta * 2 + side) * 2 + part) * N); };
-    const unsigned int left = (bid + nblk - 1) % nblk, right = (bid + 1) % nblk;
-    const double normb = C.state->normb, tol = C.state->tol;
-    double rz = C.state->rz_re, beta = 0.0, eps = C.state->eps;
-    unsigned int epoch = 0;
-    int it = 0, done = 0;
-    double v[RY][4], xr[RY][4], rr_[RY][4];
-    if (threadIdx.x == 0) sh[3] = 0.0;
-#ifdef SQ_V3_STAMPS
-    long long tacc[6] = {0, 0, 0, 0, 0, 0}, tprev = 0;
-    const bool stamp = P.dbg && bid == 0 && threadIdx.x == 32;
-    if (stamp) tprev = clock64();
-#define V3R_STAMP(q) do { if (stamp) { long long tn = clock64(); tacc[q] += tn - tprev; tprev = tn; } } while (0)
-#else
-#define V3R_STAMP(q) do { } while (0)
-#endif
-    if (part == 0 && active) {
-        const double2 *g = reinterpret_cast<const double2 *>(P.expVn + (size_t)lB * N);
-        for (int e = lane; e < N / 2; e += 32) reinterpret_cast<double2 *>(EV + (size_t)k * N)[e] = __ldg(g + e);
-    }
-    // ---- initial state: x, r of the own slice in registers; p = r for own + halo slices in shared memory
-    if (owner) {
-        const double2 *gx = gslice(C.x, lo), *gr = gslice(C.r, lo);
-#pragma unroll
-        for (int r = 0; r < RY; r++)
-#pragma unroll
-            for (int jp = 0; jp < 2; jp++) {
-                const double2 a = gx[el(r, jp)], b = gr[el(r, jp)];
-                xr[r][2 * jp] = a.x; xr[r][2 * jp + 1] = a.y;
-                rr_[r][2 * jp] = b.x; rr_[r][2 * jp + 1] = b.y;
-                Pb[(size_t)k * (N / 2) + el(r, jp)] = b;
-            }
-    }
-    if (active && (k == 0 || k == ns)) {
-        const int q = (k == 0) ? 0 : ns + 1;
-        int l = (k == 0) ? l0 - 1 : l0 + ns;
-        l = l < 0 ? l + L : (l >= L ? l - L : l);
-        const double2 *gr = gslice(C.r, l);
-        for (int e = lane; e < N / 2; e += 32) Pb[(size_t)q * (N / 2) + e] = gr[e];
-    }
-    __syncthreads();                                      // p0 of all slices (own + halo) is in Pb
-#pragma unroll 1
-    while (it < C.maxiter) {
-        it++;
-        double acc = 0.0;
-        if (active) {
-#pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 a = Pb[(size_t)k * (N / 2) + el(r, jp)];
-                    v[r][2 * jp] = a.x; v[r][2 * jp + 1] = a.y;
-                }
-            E.template apply_B_ev<1, 1>(v, evk);
-            if (k == ns && it > 1) asm volatile("bar.sync %0, 64;" ::"r"(1 + part) : "memory");       // upper halo slice rebuilt by warp 0
-#pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 self = Pb[(size_t)(k + 1) * (N / 2) + el(r, jp)];
-                    const double w0 = fma(sg, v[r][2 * jp], self.x), w1 = fma(sg, v[r][2 * jp + 1], self.y);
-                    v[r][2 * jp] = w0; v[r][2 * jp + 1] = w1;
-                    if (publish) {
-                        acc += w0 * w0;
-                        acc += w1 * w1;
-                        W[(size_t)k * (N / 2) + el(r, jp)] = make_double2(w0, w1);
-                    }
-                }
-        }
-        V3R_STAMP(0);
-        // First grid-wide sum (p.Ap = |M p|^2), overlapped with the second B: every warp leaves its partial in shared memory
-        // and arrives at a named barrier without waiting; warp 0 (which owns no slice and would idle through the second
-        // B) adds them up, publishes the CTA's slot and collects the grid total while the owners compute.
-        {
-            const double t = warp_sum(acc);
-            if (lane == 0) red[wid] = t;
-        }
-        if (wid != 0) {
-            __threadfence_block();
-            asm volatile("bar.arrive 3, %0;" ::"r"((int)blockDim.x) : "memory");
-            if (owner) E.template apply_B_ev<1, 1>(v, evk);
-        } else {
-            asm volatile("bar.sync 3, %0;" ::"r"((int)blockDim.x) : "memory");
-            const int nw = blockDim.x >> 5;
-            double t = lane < nw ? red[lane] : 0.0;
-            t = warp_sum(t);
-            bool bad = false;
-            const double tot = v3_slot_sum(t, reinterpret_cast<V3Slot *>(C.part_a), C.slot_stride, (unsigned long long)it, nblk, bid, bad);
-            if (lane == 0) { sh[0] = tot; if (bad) sh[3] = 1.0; }
-        }
-        __syncthreads();                                  // w of all slices is in W, p.Ap in sh[0]
-        if (sh[3] != 0.0) { done = 3; break; }
-        const double pAp = sh[0];
-        if (owner) {                                      // z[lo] = w[lo] -/+ B w[lo + 1], stays in registers
-#pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 w = W[(size_t)(k - 1) * (N / 2) + el(r, jp)];
-                    v[r][2 * jp] = fma(sg, v[r][2 * jp], w.x);
-                    v[r][2 * jp + 1] = fma(sg, v[r][2 * jp + 1], w.y);
-                }
-        }
-        V3R_STAMP(1);
-        bool aborted;
-        V3R_STAMP(2);
-        const double alpha = rz / pAp;
-        acc = 0.0;
-        if (owner) {                                      // x += alpha p ; r -= alpha z ; |r|^2 partial ; boundary r -> halo buffer
-            double2 *h0 = (k == 1) ? hslice(bid, 0) : nullptr, *h1 = (k == ns) ? hslice(bid, 1) : nullptr;
-#pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 pv = Pb[(size_t)k * (N / 2) + el(r, jp)];
-                    xr[r][2 * jp] = fma(alpha, pv.x, xr[r][2 * jp]);
-                    xr[r][2 * jp + 1] = fma(alpha, pv.y, xr[r][2 * jp + 1]);
-                    const double r0 = fma(-alpha, v[r][2 * jp], rr_[r][2 * jp]), r1 = fma(-alpha, v[r][2 * jp + 1], rr_[r][2 * jp + 1]);
-                    rr_[r][2 * jp] = r0; rr_[r][2 * jp + 1] = r1;
-                    acc += r0 * r0;
-                    acc += r1 * r1;
-                    if (h0) h0[el(r, jp)] = make_double2(r0, r1);
-                    if (h1) h1[el(r, jp)] = make_double2(r0, r1);
-                }
-        }
-        V3R_STAMP(3);
-        const double rr = v3_grid_sum(acc, red, &sh[2], reinterpret_cast<V3Slot *>(C.part_b), C.slot_stride, (unsigned long long)it, nblk, bid, aborted);
-        if (aborted) { done = 3; break; }
-        V3R_STAMP(4);
-        eps = sqrt(rr) / normb;
-        if (eps < tol) { done = 1; break; }
-        if (!(eps == eps)) { done = 2; break; }
-        beta = rr / rz;
-        rz = rr;
-        // p = r + beta p: own slice from registers
-        if (owner) {
-#pragma unroll
-            for (int r = 0; r < RY; r++)
-#pragma unroll
-                for (int jp = 0; jp < 2; jp++) {
-                    const double2 pv = Pb[(size_t)k * (N / 2) + el(r, jp)];
-                    Pb[(size_t)k * (N / 2) + el(r, jp)] = make_double2(fma(beta, pv.x, rr_[r][2 * jp]), fma(beta, pv.y, rr_[r][2 * jp + 1]));
-                }
-        }
-        __syncthreads();                                  // own p slices are in Pb: the owners start the next B right away
-        if (k == 0) {
-            // Warp 0 of each part owns no slice: it rebuilds the two halo slices from the neighbours' boundary r while the
-            // owners already run their first B.  All L2 loads are issued first (one round trip); the upper slice is
-            // finished first and handed to warp ns (named barrier), the lower one feeds this warp's own B.
-            double2 hu[N / 64], hl[N / 64];
-            const double2 *gu = hslice(right, 0), *gl = hslice(left, 1);
-#pragma unroll
-            for (int u = 0; u < N / 64; u++) hu[u] = __ldcg(gu + lane + 32 * u);
-#pragma unroll
-            for (int u = 0; u < N / 64; u++) hl[u] = __ldcg(gl + lane + 32 * u);
-#pragma unroll
-            for (int u = 0; u < N / 64; u++) {
-                const size_t e = (size_t)(ns + 1) * (N / 2) + lane + 32 * u;
-                const double2 pv = Pb[e];
-                Pb[e] = make_double2(fma(beta, pv.x, hu[u].x), fma(beta, pv.y, hu[u].y));
-            }
-            __threadfence_block();
-            asm volatile("bar.arrive %0, 64;" ::"r"(1 + part) : "memory");
-#pragma unroll
-            for (int u = 0; u < N / 64; u++) {
-                const size_t e = lane + 32 * u;
-                const double2 pv = Pb[e];
-                Pb[e] = make_double2(fma(beta, pv.x, hl[u].x), fma(beta, pv.y, hl[u].y));
-            }
-            __syncwarp();
-        }
-        V3R_STAMP(5);
-    }
-    if (owner) {                                          // the solution
-        double2 *gx = reinterpret_cast<double2 *>(C.x + ((size_t)lo * 2 + part) * N);
-#pragma unroll
-        for (int r = 0; r < RY; r++)
-#pragma unroll
-            for (int jp = 0; jp < 2; jp++) gx[el(r, jp)] = make_double2(xr[r][2 * jp], xr[r][2 * jp + 1]);
-    }
-#ifdef SQ_V3_STAMPS
-    if (stamp) { for (int q = 0; q < 6; q++) P.dbg[q] = tacc[q]; P.dbg[6] = it; }
-#endif
-    if (bid == 0 && threadIdx.x == 0) {
-        CgState st = *C.state;
-        st.iters = it;
-        st.eps = eps;
-        st.done = done;
-        st.rz_re = rz;
-        *C.state = st;
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1484,15 +1073,6 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     }
 }
 
-typedef void (*v3_resident_t)(const V3Params, const CgPersist3, double *);
-static v3_resident_t pick3_resident(int lxl, int ry) {
-    if (lxl == 8 && ry == 4) return k_cg_v3_resident<8, 4>;
-    if (lxl == 8 && ry == 8) return k_cg_v3_resident<8, 8>;
-    if (lxl == 4 && ry == 2) return k_cg_v3_resident<4, 2>;
-    if (lxl == 4 && ry == 4) return k_cg_v3_resident<4, 4>;
-    if (lxl == 4 && ry == 8) return k_cg_v3_resident<4, 8>;
-    return nullptr;
-}
 typedef void (*v3_resident1_t)(const V3Params, const CgResident1);
 static v3_resident1_t pick3_resident1(int lxl, int ry) {
     if (lxl == 8 && ry == 4) return k_cg_v3_resident1<V3Lane<8, 4>, 0>;
@@ -1625,125 +1205,11 @@ bool fdm_v3_cg_resident1_multi(sq_fdm *f, double2 *x, double2 *r, CgState *state
     return true;
 }
 
-// One CTA per SM.  x (in/out) and r (in) are native-order vectors; `halo` is scratch of at least one vector.
-// SQ_V3_RESIDENT=2 selects the two-sum kernel; the default is the one-sum kernel where it fits.
-bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, double2 *halo, CgState *state, double *part_a, double *part_b, i64 maxiter) {
-    {
-        const char *sel = getenv("SQ_V3_RESIDENT");
-        if (!(sel && atoi(sel) == 2) && fdm_v3_cg_resident1(f, x, r, state, maxiter)) return true;
-    }
-    v3_resident_t k2 = f->v3_kind == 0 ? pick3_resident(f->v3_lxl, f->v3_ry) : nullptr;
-    if (!k2 || !f->v3_ok || !f->cs_coluni) return false;
-    const void *kern = (const void *)k2;
-    const int nsl = f->slab_hi - f->slab_lo;
-    int S = (nsl + f->num_sms - 1) / f->num_sms;                 // fewest slices per CTA with one CTA per SM
-    if (const char *e = getenv("SQ_V3_RESIDENT_SLAB")) S = atoi(e);
-    S = std::max(S, 2);
-    if (S > 3 || nsl < S) return false;                          // 2 (S+1) warps <= 8
-    const int grid = (nsl + S - 1) / S, T = 64 * (S + 1);
-    const size_t smem = ((size_t)2 * (2 * S + 2) + (S + 1)) * f->N * sizeof(double);
-    if (smem > f->smem_optin || grid > f->num_sms || grid < 2) return false;
-    if ((size_t)grid * 4 * f->N > (size_t)2 * f->L * f->N) return false;      // halo scratch is one vector
-    V3Params P;
-    memset(&P, 0, sizeof(P));
-    P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = 4; P.nphase = 2;
-    for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = f->clo[c]; }
-    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p;
-    SQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    SQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
-    if (per_sm * f->num_sms < grid) return false;
-    if (!f->flag.p) f->flag.alloc(4);
-    SQ_CUDA(cudaMemsetAsync(f->flag.p, 0, 4 * sizeof(int), f->stream));
-    // slots of the grid sums, one per CTA, spread over the L2 slices; then the halo epoch flags
-    unsigned int stride_bytes = 1024;
-    if (const char *e = getenv("SQ_V3_SLOT_STRIDE")) stride_bytes = (unsigned)atoi(e);
-    stride_bytes = std::max(16u, stride_bytes / 16 * 16);
-    const size_t slot_bytes = (size_t)grid * stride_bytes;
-    const size_t need = 2 * slot_bytes;
-    if (f->v3_slots.n < need) f->v3_slots.alloc(need);
-    SQ_CUDA(cudaMemsetAsync(f->v3_slots.p, 0, need, f->stream));
-    (void)part_a; (void)part_b;
-    static long long *dbg = nullptr;
-    if (!dbg && getenv("SQ_DEBUG_STAMPS")) {
-        SQ_CUDA(cudaMallocManaged((void **)&dbg, 16 * sizeof(long long)));
-        for (int q = 0; q < 16; q++) dbg[q] = 0;
-    }
-    P.dbg = dbg;
-    CgPersist3 C;
-    memset(&C, 0, sizeof(C));
-    C.x = (double *)x; C.r = (double *)r; C.state = state; C.part_a = (double *)f->v3_slots.p; C.part_b = (double *)(f->v3_slots.p + slot_bytes);
-    C.slot_stride = stride_bytes / 16;
-    C.barrier = (unsigned int *)f->flag.p; C.abort_flag = f->flag.p + 1; C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
-    double *h = (double *)halo;
-    void *args[] = {(void *)&P, (void *)&C, (void *)&h};
-    SQ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(T), args, smem, f->stream));
-    f->launches++;
-#ifdef SQ_V3_STAMPS
-    if (dbg) {
-        cudaStreamSynchronize(f->stream);
-        double n = (double)std::max<long long>(dbg[6], 1);
-        fprintf(stderr, "v3 resident CG, cycles/iteration (CTA 0, warp 1; %lld iterations, S=%d, %d CTAs): B+combine %.0f  B+z+partial %.0f  barrier1+sum %.0f  update+partial %.0f  barrier2+sum %.0f  p update %.0f\n",
-                dbg[6], S, grid, dbg[0] / n, dbg[1] / n, dbg[2] / n, dbg[3] / n, dbg[4] / n, dbg[5] / n);
-    }
-#endif
-    return true;
-}
-
-typedef void (*v3_persist_t)(const V3Params, const CgPersist3);
-static v3_persist_t pick3_persist(int lxl, int ry) {
-    if (lxl == 8 && ry == 4) return k_cg_v3_persistent<8, 4>;
-    if (lxl == 8 && ry == 8) return k_cg_v3_persistent<8, 8>;
-    if (lxl == 8 && ry == 16) return k_cg_v3_persistent<8, 16>;
-    if (lxl == 4 && ry == 2) return k_cg_v3_persistent<4, 2>;
-    if (lxl == 4 && ry == 4) return k_cg_v3_persistent<4, 4>;
-    if (lxl == 4 && ry == 8) return k_cg_v3_persistent<4, 8>;
-    return nullptr;
-}
-
-// x, r: native order, prepared by the caller (cg.cu); p0 / p1: the two p buffers (zeroed here).  Returns false if the
-// cooperative launch is not possible (not all CTAs co-resident).
-bool fdm_v3_cg_persistent(sq_fdm *f, double2 *x, double2 *r, double2 *p0, double2 *p1, CgState *state, double *part_a, double *part_b,
-                          i64 maxiter) {
-    int S = f->v3_S;
-    if (const char *e = getenv("SQ_V3_PERSIST_SLAB")) S = atoi(e);
-    if (!fdm_v3_supported(f, S) || f->v3_kind != 0) return false;
-    V3Params P;
-    memset(&P, 0, sizeof(P));
-    P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = 4; P.nphase = 2;
-    for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = f->clo[c]; }
-    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p;
-    const int grid = (f->slab_hi - f->slab_lo + S - 1) / S, T = 32 * (S + 1);
-    if (2 * grid > SQ_MAXPART) return false;
-    const size_t smem = (size_t)S * f->N * sizeof(double);
-    v3_persist_t k = pick3_persist(f->v3_lxl, f->v3_ry);
-    SQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
-    int per_sm = 0;
-    SQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, T, smem));
-    if (per_sm * f->num_sms < 2 * grid) return false;
-    if (!f->flag.p) f->flag.alloc(4);
-    SQ_CUDA(cudaMemsetAsync(f->flag.p, 0, 4 * sizeof(int), f->stream));
-    SQ_CUDA(cudaMemsetAsync(p0, 0, f->vec_bytes(), f->stream));
-    SQ_CUDA(cudaMemsetAsync(p1, 0, f->vec_bytes(), f->stream));
-    CgPersist3 C;
-    C.x = (double *)x; C.r = (double *)r; C.p0 = (double *)p0; C.p1 = (double *)p1; C.state = state; C.part_a = part_a; C.part_b = part_b;
-    C.barrier = (unsigned int *)f->flag.p; C.abort_flag = f->flag.p + 1; C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
-    static long long *dbg = nullptr;
-    if (!dbg && getenv("SQ_DEBUG_STAMPS")) {
-        SQ_CUDA(cudaMallocManaged((void **)&dbg, 16 * sizeof(long long)));
-        for (int q = 0; q < 16; q++) dbg[q] = 0;
-    }
-    P.dbg = dbg;
-    void *args[] = {(void *)&P, (void *)&C};
-    SQ_CUDA(cudaLaunchCooperativeKernel((const void *)k, dim3(grid, 2), dim3(T), args, smem, f->stream));
-    f->launches++;
-    if (dbg) {
-        cudaStreamSynchronize(f->stream);
-        double n = (double)std::max<long long>(dbg[5], 1);
-        fprintf(stderr, "v3 persistent CG, cycles/iteration (CTA 0, warp 1; %lld iterations, S=%d, %d CTAs): load+B+combine %.0f  B+z+partial %.0f  barrier1+sum %.0f  update+partial %.0f  barrier2+sum %.0f\n",
-                dbg[5], S, 2 * grid, dbg[0] / n, dbg[1] / n, dbg[2] / n, dbg[3] / n, dbg[4] / n);
-    }
-    return true;
+// Whole-solve resident kernel (one CTA per SM, one grid-wide sum per iteration).  x (in/out) and r (in) are native-order
+// vectors.  Returns false when the problem does not fit (more than 3 slices per SM, lattice without a register engine): the
+// caller then runs the two-launches-per-iteration loop.
+bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, CgState *state, i64 maxiter) {
+    return fdm_v3_cg_resident1(f, x, r, state, maxiter);
 }
 
 // ---------------------------------------------------------------------------------------------------

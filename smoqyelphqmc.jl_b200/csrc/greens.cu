@@ -88,7 +88,7 @@ double greens_update_impl(sq_greens *g, sq_kpm *kpm, const void *h_R, double tol
     if (h_R) {
         for (i64 n = 0; n < g->Nrv; n++) fdm_host_to_dev(f, g->R.p + n * V, (const char *)h_R + n * V * sizeof(double2));
     } else {
-        rng_fill_normal((double *)g->R.p, 2 * V * g->Nrv, g->seed, g->counter++, f->stream);
+        rng_fill_normal((double *)g->R.p, 2 * V * g->Nrv, g->seed, sq_rng_stream(SQ_RNG_GREENS, g->counter++), f->stream);
         k_unit_modulus<<<f->num_sms * 4, 256, 0, f->stream>>>(g->R.p, V * g->Nrv);
         SQ_LAUNCH_CHECK();
         f->launches++;

@@ -100,6 +100,7 @@ void hmc_create_impl(sq_hmc **out, sq_pff *q, i64 Nt, double dt, double eta, dou
     sq_hmc *h = new sq_hmc();
     try {
         h->p = q; h->owner = f; h->Nt = Nt; h->dt = dt; h->eta = eta; h->delta = delta; h->seed = seed;
+        if (!q->seed_set) q->seed = sq_mix_seed(seed, SQ_RNG_PFF);    // chains with different HMC seeds draw different pseudofermion noise in the global moves
         i64 L = f->L, Nph = e->Nph;
         size_t nx = (size_t)L * Nph;
         h->x0.alloc(nx); h->pm.alloc(nx); h->dS.alloc(nx);
@@ -203,9 +204,9 @@ int hmc_update_impl(sq_hmc *h, sq_kpm *kpm, double tol_action, double tol_force,
         u_acc = randoms[need - 1];
     } else {
         // Philox: normals everywhere, the two uniforms separately
-        rng_fill_normal(h->rnd.p, need, h->seed, 2 * h->counter, f->stream);
+        rng_fill_normal(h->rnd.p, need, h->seed, sq_rng_stream(SQ_RNG_HMC, 2 * h->counter), f->stream);
         double uu[2];
-        rng_fill_uniform(h->part.p, 2, h->seed, 2 * h->counter + 1, f->stream);
+        rng_fill_uniform(h->part.p, 2, h->seed, sq_rng_stream(SQ_RNG_HMC, 2 * h->counter + 1), f->stream);
         SQ_CUDA(cudaMemcpyAsync(uu, h->part.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, f->stream));
         SQ_CUDA(cudaStreamSynchronize(f->stream));
         u_dt = uu[0];
@@ -216,6 +217,7 @@ int hmc_update_impl(sq_hmc *h, sq_kpm *kpm, double tol_action, double tol_force,
     double dt = h->dt * (1.0 + (2 * u_dt - 1) * h->delta);                                   // :125
     SQ_CUDA(cudaMemcpyAsync(h->x0.p, e->x.p, nx * sizeof(double), cudaMemcpyDeviceToDevice, f->stream));   // :128
     bool stable = true;
+    h->last_reject.clear();
     double Sf0 = 0, Sb0 = 0, K0 = 0, Sf1 = 0, Sb1 = 0, K1 = 0, iters_avg = 0, dH = 0;
     int solve = 0;
     try {
@@ -244,11 +246,13 @@ int hmc_update_impl(sq_hmc *h, sq_kpm *kpm, double tol_action, double tol_force,
         iters_avg += (double)it / (double)(Nt + 1);
         Sb1 = elph_bosonic_action(e);                                                       // :238
         K1 = hmc_kinetic_dev(h, h->pm.p);                                                   // :244
-    } catch (const SqError &err) {
-        // numerical instability inside the trajectory => reject (EFAPFFHMCUpdater.jl:168-187,215-231)
-        std::string m = err.what();
-        if (m.find("CUDA error") != std::string::npos) throw;                               // real failures still propagate
+    } catch (const SqNumericalInstability &err) {
+        // numerical instability inside the trajectory => warn and reject (EFAPFFHMCUpdater.jl:168-187,215-231: `@warn ... rejecting
+        // update`).  Only this class is caught: bad arguments, CUDA / NCCL errors and watchdog time-outs propagate to the caller.
         stable = false;
+        f->stats[SQ_STAT_INSTABILITY]++;
+        h->last_reject = err.what();
+        fprintf(stderr, "[smoqyelph_b200] warning: numerical instability in the EFA-PFF-HMC trajectory (solve %d), rejecting update: %s\n", solve, err.what());
     }
     double Pacc = 0.0;
     if (stable) {

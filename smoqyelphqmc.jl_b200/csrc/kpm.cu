@@ -12,7 +12,6 @@
 // Frequencies are scheduled longest-recurrence-first.  Bounds, orders and coefficients are tiny scalar
 // work and are computed on the host in double precision exactly as the reference does.
 #include "sq_internal.h"
-#include "chain.h"
 
 #include <algorithm>
 #include <cmath>
@@ -298,128 +297,6 @@ k_kpm_cheb_fast(const __grid_constant__ BbarFast P, double2 *__restrict__ z, con
     if (si >= 0) { zn[2 * si] = acci; zn[2 * sj] = accj; }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Chain-in-warp Chebyshev kernel (chain.h): colours are processed in pairs (a, b) whose union is a set of rings of at
-// most 32 a-bonds.  Within a pair nothing touches shared memory: the a-rotation is thread local, the b-rotation is two
-// warp shuffles.  Shared memory (double buffered, one barrier each) is only used to go from the outer pair (colours
-// 2, 3) to the middle pair (colours 0, 1) and back: 2 barriers per B-bar application instead of 6.
-// ---------------------------------------------------------------------------------------------------
-struct ChainDev {
-    int T;                         // padded thread count
-    int has_b;
-    const int *pos_u, *pos_v;      // shared-memory positions of the two sites
-    const int *nat_u, *nat_v;      // natural site indices (-1: idle lane)
-    const int *bond_a, *bond_b;    // internal bond indices (-1: none)
-    const int *next, *prev, *has_prev;
-};
-struct ChebChainParams {
-    int N, C, ypad;                // ypad: doubles per shared buffer
-    ChainDev mid, outer;           // mid: colours (0, 1); outer: colours (2, 3) (C >= 3)
-    const double2 *csbar;
-    const double *Dbar;
-    long long *dbg;
-};
-
-struct LaneChain {
-    int pu, pv, nx, pr, hp;
-    double ca, sa, cb, sb;
-    __device__ __forceinline__ void load(const ChainDev &L, const double2 *csbar) {
-        const int t = threadIdx.x;
-        pu = L.pos_u[t]; pv = L.pos_v[t]; nx = L.next[t]; pr = L.prev[t]; hp = L.has_prev[t];
-        ca = 1.0; sa = 0.0; cb = 1.0; sb = 0.0;
-        int ba = L.bond_a[t], bb = L.bond_b[t];
-        if (ba >= 0) { double2 v = __ldg(csbar + ba); ca = v.x; sa = v.y; }
-        if (bb >= 0) { double2 v = __ldg(csbar + bb); cb = v.x; sb = v.y; }
-    }
-    __device__ __forceinline__ static void rot(double &a, double &b, double c, double s) {
-        double na = fma(s, b, c * a), nb = fma(s, a, c * b);
-        a = na;
-        b = nb;
-    }
-    __device__ __forceinline__ void astep(double &u, double &v) const { rot(u, v, ca, sa); }
-    // b-bond (v of this lane, u of the next lane along the ring)
-    __device__ __forceinline__ void bstep(double &u, double &v) const {
-        double un = __shfl_sync(0xffffffffu, u, nx);
-        rot(v, un, cb, sb);
-        double ub = __shfl_sync(0xffffffffu, un, pr);
-        if (hp) u = ub;
-    }
-};
-
-__global__ void __launch_bounds__(1024, 1)
-k_kpm_cheb_chain(const __grid_constant__ ChebChainParams P, double2 *__restrict__ z, const int *__restrict__ sched,
-                 const int *__restrict__ order, const int *__restrict__ coef_off, const double2 *__restrict__ coefs, int L, double avg,
-                 double imag_, const CgState *__restrict__ skip) {
-    extern __shared__ double Yc[];
-    if (skip && skip->done) return;
-    double *Y0 = Yc, *Y1 = Yc + P.ypad;
-    const bool two = (P.C >= 3);
-    LaneChain M, O;
-    M.load(P.mid, P.csbar);
-    if (two) O.load(P.outer, P.csbar); else O = M;
-    const int t = threadIdx.x;
-    double dmu = 1.0, dmv = 1.0;
-    { int a = P.mid.nat_u[t], b = P.mid.nat_v[t]; if (a >= 0) { dmu = __ldg(P.Dbar + a); dmv = __ldg(P.Dbar + b); } }
-    const int n = sched[blockIdx.x >> 1], part = blockIdx.x & 1;
-    const int np = (n + 1 > (L + 1) / 2) ? L - 1 - n : n;
-    const int ord = order[np];
-    const double2 *c = coefs + coef_off[np];
-    double *zn = reinterpret_cast<double *>(z + (size_t)n * P.N) + part;
-    // registers live in the owner layout: outer if it exists, else mid
-    const ChainDev &OW = two ? P.outer : P.mid;
-    const int su = OW.nat_u[t], sv = OW.nat_v[t];
-    const int has_ob = P.outer.has_b, has_mb = P.mid.has_b;
-    double t0u = 0, t0v = 0;
-    if (su >= 0) { t0u = zn[2 * su]; t0v = zn[2 * sv]; }
-    const bool prof = (P.dbg != nullptr) && blockIdx.x == 0 && t == 0;
-    long long acc_t[5] = {0, 0, 0, 0, 0};
-    auto apply = [&](double &u, double &v) {
-        long long c0 = prof ? clock64() : 0;
-        if (two) {
-            if (has_ob) O.bstep(u, v);                     // colour 3
-            O.astep(u, v);                                 // colour 2
-            if (prof) { long long c1 = clock64(); acc_t[0] += c1 - c0; c0 = c1; }
-            Y0[O.pu] = u; Y0[O.pv] = v;
-            __syncthreads();
-            u = Y0[M.pu]; v = Y0[M.pv];
-            if (prof) { long long c1 = clock64(); acc_t[1] += c1 - c0; c0 = c1; }
-        }
-        if (has_mb) M.bstep(u, v);                         // colour 1
-        M.astep(u, v);                                     // colour 0
-        u *= dmu; v *= dmv;                                // D-bar
-        M.astep(u, v);                                     // colour 0
-        if (has_mb) M.bstep(u, v);                         // colour 1
-        if (prof) { long long c1 = clock64(); acc_t[2] += c1 - c0; c0 = c1; }
-        if (two) {
-            Y1[M.pu] = u; Y1[M.pv] = v;
-            __syncthreads();
-            u = Y1[O.pu]; v = Y1[O.pv];
-            if (prof) { long long c1 = clock64(); acc_t[3] += c1 - c0; c0 = c1; }
-            O.astep(u, v);                                 // colour 2
-            if (has_ob) O.bstep(u, v);                     // colour 3
-            if (prof) { long long c1 = clock64(); acc_t[4] += c1 - c0; c0 = c1; }
-        }
-    };
-    if (P.dbg && blockIdx.x == 0 && t == 0) P.dbg[0] = clock64();
-    double yu = t0u, yv = t0v;
-    apply(yu, yv);
-    if (P.dbg && blockIdx.x == 0 && t == 0) { P.dbg[1] = clock64(); P.dbg[3] = ord; }
-    double t1u = (yu - avg * t0u) * imag_, t1v = (yv - avg * t0v) * imag_;
-    const double c0 = c[0].x, c1 = c[1].x;
-    double accu = c0 * t0u + c1 * t1u, accv = c0 * t0v + c1 * t1v;
-    for (int q = 2; q < ord; q++) {
-        yu = t1u; yv = t1v;
-        apply(yu, yv);
-        double t2u = 2.0 * (yu - avg * t1u) * imag_ - t0u, t2v = 2.0 * (yv - avg * t1v) * imag_ - t0v;
-        const double cq = c[q].x;
-        accu = fma(cq, t2u, accu);
-        accv = fma(cq, t2v, accv);
-        t0u = t1u; t0v = t1v; t1u = t2u; t1v = t2v;
-    }
-    if (P.dbg && blockIdx.x == 0 && t == 0) { P.dbg[2] = clock64(); P.dbg[4] = acc_t[0]; P.dbg[5] = acc_t[1]; P.dbg[6] = acc_t[2]; P.dbg[7] = acc_t[3]; P.dbg[8] = acc_t[4]; }
-    if (su >= 0) { zn[2 * su] = accu; zn[2 * sv] = accv; }
-}
-
 // tau-means of the operator coefficients (update_B̄!, :604-621): grid over sites/bonds, 32 x 8 threads
 __global__ void k_tau_means(double *__restrict__ Dbar, double2 *__restrict__ csbar, const double *__restrict__ expV,
                             const double2 *__restrict__ cs, int L, int N, int Nh) {
@@ -530,56 +407,6 @@ static int kpm_fast_threads(const sq_kpm *k) {
     int nbmax = 1;
     for (int c = 0; c < k->f->C; c++) nbmax = std::max(nbmax, k->f->chi[c] - k->f->clo[c]);
     return ((nbmax + 31) / 32) * 32;
-}
-
-// ---- chain-in-warp path: device copies of the layouts -------------------------------------------------
-static int chain_pos(int site) { return site + (site >> 6); }       // one pad per 64 doubles: odd strides for column walks
-
-static void chain_upload(sq_kpm *k, int which, const ChainLayout &Lh, int T) {
-    sq_fdm *f = k->f;
-    std::vector<int> pu(T), pv(T), nu(T, -1), nv(T, -1), ba(T, -1), bb(T, -1), nx(T), pr(T), hp(T, 0);
-    const int dummy = chain_pos((int)f->N) + 1;                      // idle lanes read / write a scratch slot
-    for (int t = 0; t < T; t++) { pu[t] = dummy; pv[t] = dummy + 1; nx[t] = pr[t] = t & 31; }
-    for (int t = 0; t < Lh.T; t++) {
-        if (Lh.site_u[t] < 0) continue;
-        pu[t] = chain_pos(Lh.site_u[t]); pv[t] = chain_pos(Lh.site_v[t]);
-        nu[t] = Lh.site_u[t]; nv[t] = Lh.site_v[t]; ba[t] = Lh.bond_a[t]; bb[t] = Lh.bond_b[t];
-        nx[t] = Lh.next[t]; pr[t] = Lh.prev[t]; hp[t] = Lh.has_prev[t];
-    }
-    DevBuf<int> *dst = k->chain_buf[which];
-    const std::vector<int> *src[9] = {&pu, &pv, &nu, &nv, &ba, &bb, &nx, &pr, &hp};
-    for (int q = 0; q < 9; q++) { dst[q].alloc(T, false); dst[q].upload(src[q]->data(), T, f->stream); }
-    SQ_CUDA(cudaStreamSynchronize(f->stream));
-}
-
-static void kpm_chain_setup(sq_kpm *k) {
-    sq_fdm *f = k->f;
-    k->chain_ok = 0;
-    // Measured at cfg4 (B200): 1794 cycles per Chebyshev step against 1736 for the shared-memory kernel -- the recurrence
-    // is bound by the latency of its ~23 dependent FP64 operations (~25 cycles each) and the shuffle round trips
-    // (~150 cycles per shuffled colour), not by the 2 vs 6 barriers.  Kept as an opt-in experiment.
-    if (!f->sym || f->C < 1 || f->C > 4 || !getenv("SQ_KPM_CHAIN")) return;
-    ChainLayout mid = chain_build(f, 0, f->C >= 2 ? 1 : -1);
-    if (!mid.ok) return;
-    ChainLayout outer;
-    if (f->C >= 3) {
-        outer = chain_build(f, 2, f->C >= 4 ? 3 : -1);
-        if (!outer.ok) return;
-    }
-    int T = std::max(mid.T, f->C >= 3 ? outer.T : 0);
-    chain_upload(k, 0, mid, T);
-    if (f->C >= 3) chain_upload(k, 1, outer, T);
-    k->chain_T = T;
-    k->chain_ok = 1;
-}
-
-static ChainDev chain_dev(sq_kpm *k, int which, int has_b) {
-    ChainDev D;
-    DevBuf<int> *b = k->chain_buf[which];
-    D.T = k->chain_T; D.has_b = has_b;
-    D.pos_u = b[0].p; D.pos_v = b[1].p; D.nat_u = b[2].p; D.nat_v = b[3].p; D.bond_a = b[4].p; D.bond_b = b[5].p;
-    D.next = b[6].p; D.prev = b[7].p; D.has_prev = b[8].p;
-    return D;
 }
 
 static void sturm_extremes(const std::vector<double> &a, const std::vector<double> &b, int n, double *emin, double *emax) {
@@ -725,7 +552,6 @@ void kpm_create_impl(sq_kpm **out, sq_fdm *f, double rbuf, i64 n, double a1, dou
         k->theta.alloc(f->L, false); k->theta.upload(th.data(), f->L, f->stream);
         SQ_CUDA(cudaStreamSynchronize(f->stream));
         fft_radices(f->L, k->radices);
-        kpm_chain_setup(k);
         k->ztmp.alloc((size_t)f->L * f->N);
         k->lan.alloc(2 * n);
         k->lan_start.alloc(f->N);
@@ -752,7 +578,7 @@ void kpm_lanczos(sq_kpm *k, const double *h_start, const double *d_start, double
     const double *start = d_start;
     if (!start) {
         if (h_start) k->lan_start.upload(h_start, f->N, f->stream);
-        else rng_fill_normal(k->lan_start.p, f->N, 0x5eedULL, k->rng_counter++, f->stream);
+        else rng_fill_normal(k->lan_start.p, f->N, k->seed, sq_rng_stream(SQ_RNG_KPM, k->rng_counter++), f->stream);
         start = k->lan_start.p;
     }
     int n = (int)k->nlanczos;
@@ -766,7 +592,7 @@ void kpm_lanczos(sq_kpm *k, const double *h_start, const double *d_start, double
     std::vector<double> a(h.begin(), h.begin() + n), b(h.begin() + n, h.begin() + 2 * n - 1);
     int used = n;
     for (int j = 0; j < n - 1; j++) if (!(b[j] >= 1e-300)) { used = j + 1; break; }
-    for (int j = 0; j < used; j++) if (!(a[j] == a[j])) throw SqError("KPM preconditioner: NaN in the Lanczos recurrence");
+    for (int j = 0; j < used; j++) if (!(a[j] == a[j])) throw SqNumericalInstability("KPM preconditioner: NaN in the Lanczos recurrence");
     sturm_extremes(a, b, used, emin, emax);
     if (!f->sym) { *emin = sqrt(*emin); *emax = sqrt(*emax); }          // :655
 }
@@ -798,29 +624,7 @@ int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *
     double2 *zt = k->ztmp.p;
     tau_fft_launch(f->stream, k->radices, (int)f->L, (int)f->N, zt, in, false, true, k->tw.p, k->theta.p, k->d_scale1.p, nullptr, nullptr,
                    skip, f->smem_optin);
-    if (k->nsched > 0 && k->chain_ok) {
-        ChebChainParams Q;
-        Q.N = (int)f->N; Q.C = (int)f->C;
-        Q.ypad = chain_pos((int)f->N) + 8;
-        Q.mid = chain_dev(k, 0, f->C >= 2);
-        Q.outer = chain_dev(k, f->C >= 3 ? 1 : 0, f->C >= 4);
-        Q.csbar = k->csbar.p; Q.Dbar = k->Dbar.p;
-        static long long *dbg = nullptr;
-        if (!dbg && getenv("SQ_DEBUG_STAMPS")) { SQ_CUDA(cudaMallocManaged((void **)&dbg, 16 * sizeof(long long))); for (int q = 0; q < 16; q++) dbg[q] = 0; }
-        Q.dbg = dbg;
-        if (dbg && getenv("SQ_DEBUG_PRINT")) {
-            cudaStreamSynchronize(f->stream);
-            double st = (double)std::max<long long>(1, dbg[3] - 1);
-            fprintf(stderr, "cheb(chain) stamps: whole recurrence %lld cycles, order %lld -> %.0f cycles/step [outer-in %.0f, xchg1 %.0f, mid %.0f, xchg2 %.0f, outer-out %.0f]\n",
-                    dbg[2] - dbg[0], dbg[3], (double)(dbg[2] - dbg[0]) / st, dbg[4] / st, dbg[5] / st, dbg[6] / st, dbg[7] / st, dbg[8] / st);
-        }
-        double avg = 0.5 * (k->bounds[1] + k->bounds[0]), mag = 0.5 * (k->bounds[1] - k->bounds[0]);
-        k_kpm_cheb_chain<<<2 * k->nsched, k->chain_T, 2 * Q.ypad * sizeof(double), f->stream>>>(Q, zt, k->d_freq_sched.p, k->d_order.p,
-                                                                                                k->d_coef_off.p, k->d_coefs.p, (int)f->L, avg,
-                                                                                                1.0 / mag, skip);
-        SQ_LAUNCH_CHECK();
-        f->launches++;
-    } else if (k->nsched > 0 && kpm_fast_ok(k)) {
+    if (k->nsched > 0 && kpm_fast_ok(k)) {
         BbarFast Q;
         Q.N = (int)f->N; Q.C = (int)f->C; Q.nunc0 = f->nunc0;
         for (int c = 0; c < 8; c++) { Q.clo[c] = c < f->C ? f->clo[c] : 0; Q.chi[c] = c < f->C ? f->chi[c] : 0; }

@@ -198,7 +198,7 @@ double pff_action_dev(sq_pff *q, sq_kpm *kpm, bool refresh, const double *h_lanc
     SQ_LAUNCH_CHECK();
     f->launches++;
     double Sf = reduce_partials_host(f, q->part.p, g);
-    if (!(Sf == Sf) || std::isinf(Sf)) throw SqError("fermionic action is not finite (numerical instability)");
+    if (!(Sf == Sf) || std::isinf(Sf)) throw SqNumericalInstability("fermionic action is not finite (numerical instability)");
     return Sf;
 }
 
@@ -339,7 +339,7 @@ void pff_fill_phi_normals(sq_pff *q, const void *h_R, const double *d_stream) {
         k_complex_normals_from_host_stream<<<nblk(V), 256, 0, f->stream>>>(q->Phi.p, d_stream, (int)f->L, (int)f->N);
         SQ_LAUNCH_CHECK();
     } else {
-        rng_fill_normal((double *)q->Phi.p, 2 * V, q->seed, q->rng_counter++, f->stream);
+        rng_fill_normal((double *)q->Phi.p, 2 * V, q->seed, sq_rng_stream(SQ_RNG_PFF, q->rng_counter++), f->stream);
         k_scale_to_complex_normals<<<red_grid(f), 256, 0, f->stream>>>(q->Phi.p, V);
         SQ_LAUNCH_CHECK();
     }

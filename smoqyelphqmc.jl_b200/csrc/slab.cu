@@ -315,7 +315,7 @@ static bool cg_slab_resident(sq_fdm *f, double2 *x, const double2 *b, bool zero_
     SQ_CUDA(cudaMemcpyAsync(h, scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
     SQ_CUDA(cudaStreamSynchronize(s));
     const double normb = std::sqrt(h[0]), eps0 = std::sqrt(h[1]) / normb;
-    if (!(eps0 == eps0)) throw SqError("conjugate gradient (tau-slab): NaN encountered in the residual");
+    if (!(eps0 == eps0)) throw SqNumericalInstability("conjugate gradient (tau-slab): NaN encountered in the residual");
     if (eps0 < tol) { *iters = 0; *eps = eps0; return true; }
     fdm_halo_exchange(f, r);                                   // p0 = r0 of the neighbours' boundary slices
     fdm_v3_prepare_native(f);
@@ -333,10 +333,12 @@ static bool cg_slab_resident(sq_fdm *f, double2 *x, const double2 *b, bool zero_
     SQ_CUDA(cudaMemcpyAsync(f->h_cg, f->cg.p, sizeof(CgState), cudaMemcpyDeviceToHost, s));
     SQ_CUDA(cudaStreamSynchronize(s));
     f->v3_it_base += (unsigned long long)f->h_cg->iters + 4;      // identical on every rank: the tags of the next solve continue
-    if (f->h_cg->done == 3) throw SqError("conjugate gradient (tau-slab): a grid-wide sum over the GPUs timed out");
-    if (f->h_cg->done == 2) throw SqError("conjugate gradient (tau-slab): NaN encountered in the residual");
+    f->stats[SQ_STAT_CG_SOLVES]++; f->stats[SQ_STAT_CG_SLAB_RESIDENT]++;
+    if (f->h_cg->done == 3) { f->stats[SQ_STAT_WATCHDOG]++; throw SqError("conjugate gradient (tau-slab): a grid-wide sum over the GPUs timed out (watchdog)"); }
+    if (f->h_cg->done == 2) throw SqNumericalInstability("conjugate gradient (tau-slab): NaN encountered in the residual");
     *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
     *eps = f->h_cg->eps;
+    f->stats[SQ_STAT_CG_ITERS] += *iters;
     return true;
 }
 
@@ -392,7 +394,9 @@ void fdm_cg_slab(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, doubl
         SQ_CUDA(cudaStreamSynchronize(s));
         if (h[4] != 0.0 || it >= maxiter) finished = true;
     }
-    if (h[4] == 2.0) throw SqError("conjugate gradient (tau-slab): NaN encountered in the residual");
+    if (h[4] == 2.0) throw SqNumericalInstability("conjugate gradient (tau-slab): NaN encountered in the residual");
     *iters = h[4] != 0.0 ? (i64)h[6] : maxiter;
     *eps = h[5];
+    f->stats[SQ_STAT_CG_SOLVES]++; f->stats[SQ_STAT_CG_SLAB_NCCL]++;
+    f->stats[SQ_STAT_CG_ITERS] += *iters;
 }

@@ -4,6 +4,7 @@
 
 #include <map>
 #include <memory>
+#include <string>
 #include "smoqyelph_b200.h"
 
 #define SQ_MAXC 32          // maximum number of checkerboard colours
@@ -33,8 +34,28 @@ struct CgState {            // device-resident CG scalars, ping-ponged between i
     int iters, done;
 };
 
+// diagnostic counters behind sq_fdm_stats (which solver ran, how often a watchdog or a NaN check fired)
+enum {
+    SQ_STAT_CG_SOLVES = 0,      // CG solves entered
+    SQ_STAT_CG_RESIDENT = 1,    // ... run by the whole-solve resident register kernel (k_cg_v3_resident1)
+    SQ_STAT_CG_PERSIST_V2 = 2,  // ... by the cooperative shared-memory kernel (k_cg_persistent)
+    SQ_STAT_CG_LOOP = 3,        // ... by the launch loop, unpreconditioned
+    SQ_STAT_CG_PREC = 4,        // ... preconditioned (launch loop)
+    SQ_STAT_CG_SLAB_NCCL = 5,   // tau-slab solves through the NCCL loop
+    SQ_STAT_CG_SLAB_RESIDENT = 6, // tau-slab solves through the resident kernels + peer mailboxes
+    SQ_STAT_WATCHDOG = 7,       // spin-wait watchdogs that fired (a stalled resident kernel)
+    SQ_STAT_INSTABILITY = 8,    // numerical instabilities converted into rejected updates
+    SQ_STAT_CG_ITERS = 9,       // CG iterations, all solves
+    SQ_STAT_KPM_REG = 10,       // preconditioner applies with the register Chebyshev kernel
+    SQ_STAT_KPM_SMEM = 11,      // ... with the shared-memory Chebyshev kernels
+    SQ_STAT_CG_BATCHED = 12,    // right-hand sides solved by the batched (multi-RHS) solver
+    SQ_STAT_CG_SLAB_PREC = 13,  // tau-slab preconditioned solves (frequency-sharded KPM, all-to-all)
+    SQ_NSTATS = 16
+};
+
 struct sq_fdm {
     int device = 0;
+    i64 stats[SQ_NSTATS] = {0};
     cudaStream_t stream = nullptr;
     int sym = 1;
     i64 L = 0, N = 0, Nh = 0, C = 0;
@@ -125,8 +146,6 @@ struct sq_kpm {
     DevBuf<double2> d_coefs;
     DevBuf<double> d_scale1;                 // per frequency: scalar applied by the FFT store when order == 1
     int nsched = 0;                          // frequencies with order > 1
-    int chain_ok = 0, chain_T = 0;           // chain-in-warp Chebyshev path (chain.h)
-    DevBuf<int> chain_buf[2][9];             // [mid / outer][pos_u, pos_v, nat_u, nat_v, bond_a, bond_b, next, prev, has_prev]
     DevBuf<double2> ztmp;                    // [n][i] frequency-space scratch
     DevBuf<double> lan;                      // Lanczos alpha/beta read-back
     DevBuf<double> lan_start;                // N
@@ -134,7 +153,7 @@ struct sq_kpm {
     std::vector<int> radices;
     i64 bbar_version = -1;
     int max_order = 0;
-    uint64_t rng_counter = 0;
+    uint64_t seed = 0x5eed, rng_counter = 0;  // Lanczos start vectors (sq_kpm_set_seed)
 };
 
 struct sq_elph {
@@ -161,6 +180,7 @@ struct sq_elph {
     DevBuf<double> V, t;                     // materialised only by sq_elph_get_Vt: [l][i], [l][h] original order
     bool any_phsym = false;
     bool t0_coluni = false;                  // bare hopping uniform inside every colour
+    bool bare_set = false;                   // V0 / t0 known (sq_elph_create with non-NULL arrays, or sq_elph_set_bare)
 };
 
 struct sq_pff {
@@ -172,7 +192,8 @@ struct sq_pff {
     DevBuf<double> HV, HL, SV;               // per-coupling force contributions [l][c]
     DevBuf<double> part;                     // reduction partials
     int exact_holstein = 0;
-    uint64_t seed = 0x0ff1ce, rng_counter = 0;
+    uint64_t seed = 0x0ff1ce, rng_counter = 0;   // pseudofermion noise (sq_pff_set_seed; sq_hmc_create derives it from the HMC seed)
+    bool seed_set = false;
 };
 
 struct sq_hmc {
@@ -188,6 +209,7 @@ struct sq_hmc {
     DevBuf<double> rnd;                      // random stream of one trajectory
     DevBuf<double> part;
     std::vector<int> radices;
+    std::string last_reject;                 // reason of the last forced rejection (numerical instability), "" if none
 };
 
 struct sq_greens {
@@ -202,6 +224,19 @@ struct sq_greens {
     std::map<int, std::unique_ptr<DevBuf<double2>>> fft_tw;   // twiddles per transform length
     DevBuf<double> part;
 };
+
+// Philox (seed, stream) namespaces: the component tag sits in the top byte of the stream index, so that two components created
+// with the same seed (the Python / Julia defaults) never draw the same normals (round-1 ADVICE: HMC, Greens and PFF all
+// counted their streams from 0).
+enum { SQ_RNG_HMC = 1, SQ_RNG_GREENS = 2, SQ_RNG_PFF = 3, SQ_RNG_KPM = 4 };
+static inline uint64_t sq_rng_stream(int component, uint64_t counter) { return ((uint64_t)component << 56) | (counter & 0x00ffffffffffffffULL); }
+// splitmix64 finaliser: derives a child seed from (seed, tag) -- chain seeds, component seeds
+static inline uint64_t sq_mix_seed(uint64_t seed, uint64_t tag) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (tag + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
 
 // ---- functions shared between translation units (all enqueue on f->stream) ------------------------
 void fdm_mul_dev(sq_fdm *f, int op, double2 *out, const double2 *in, double *pAp_partials = nullptr,
@@ -220,6 +255,7 @@ void kpm_lanczos(sq_kpm *k, const double *h_start, const double *d_start, double
 void kpm_update(sq_kpm *k, const double *h_lanczos_start, const double *d_lanczos_start);
 void kpm_set_bounds(sq_kpm *k, double emin, double emax);
 void elph_refresh_fdm(sq_elph *e);
+void elph_set_bare(sq_elph *e, const double *V0, const double *t0);
 double elph_bosonic_action(sq_elph *e);
 void elph_update_lambda(sq_elph *e, double *Lam);
 void elph_lambda_op(sq_elph *e, int which, double2 *out, const double2 *in, const double *Lam);

@@ -37,6 +37,7 @@ SIGNATURES = {
     "sq_fdm_set_fast_path": [vp, i32],
     "sq_fdm_time_mul": [vp, i32, vp, vp, i32, vp, i64, vp],
     "sq_fdm_stream": [vp, pp],
+    "sq_fdm_stats": [vp, vp, i32],
     "sq_nccl_unique_id": [vp],
     "sq_fdm_init_slab": [vp, i32, i32, vp],
     "sq_fdm_mailbox_create": [vp, vp],
@@ -46,6 +47,7 @@ SIGNATURES = {
     "sq_fdm_get_slab": [vp, vp, vp, vp, vp],
     "sq_kpm_create": [pp, vp, f64, i64, f64, f64],
     "sq_kpm_destroy": [vp],
+    "sq_kpm_set_seed": [vp, C.c_uint64],
     "sq_kpm_update": [vp, vp, vp, vp],
     "sq_kpm_set_bounds": [vp, f64, f64],
     "sq_kpm_get_orders": [vp, vp, vp],
@@ -54,6 +56,7 @@ SIGNATURES = {
     "sq_kpm_ldiv_dev": [vp, vp, vp],
     "sq_kpm_fourier": [vp, vp, i32],
     "sq_elph_create": [pp, vp, f64, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp],
+    "sq_elph_set_bare": [vp, vp, vp],
     "sq_elph_destroy": [vp],
     "sq_elph_set_x": [vp, vp],
     "sq_elph_get_x": [vp, vp],
@@ -67,6 +70,7 @@ SIGNATURES = {
     "sq_elph_bosonic_action": [vp, vp],
     "sq_pff_create": [pp, vp],
     "sq_pff_destroy": [vp],
+    "sq_pff_set_seed": [vp, C.c_uint64],
     "sq_pff_set_exact_holstein": [vp, i32],
     "sq_pff_sample": [vp, vp, vp],
     "sq_pff_action": [vp, vp, vp, f64, i64, vp, vp, vp],
@@ -78,12 +82,14 @@ SIGNATURES = {
     "sq_pff_dLambda_dx": [vp, vp, f64, vp, vp],
     "sq_hmc_create": [pp, vp, i64, f64, f64, f64, C.c_uint64],
     "sq_hmc_destroy": [vp],
+    "sq_hmc_set_seed": [vp, C.c_uint64],
     "sq_hmc_update": [vp, vp, f64, f64, i64, vp, i64, vp, vp],
     "sq_hmc_init_momentum": [vp, vp, vp, vp],
     "sq_hmc_kinetic": [vp, vp, vp],
     "sq_hmc_evolve": [vp, vp, vp, f64],
     "sq_greens_create": [pp, vp, i64, C.c_uint64],
     "sq_greens_destroy": [vp],
+    "sq_greens_set_seed": [vp, C.c_uint64],
     "sq_greens_update": [vp, vp, vp, f64, i64, vp],
     "sq_greens_get": [vp, vp, vp],
     "sq_greens_set_GR": [vp, vp],
@@ -96,7 +102,8 @@ SIGNATURES = {
     "sq_greens_weighted_density": [vp, vp, vp],
     "sq_greens_weighted_bonds": [vp, i64, vp, vp, vp],
 }
-SPECIAL = {"sq_last_error": (C.c_char_p, []), "sq_version": (i32, []), "sq_fdm_launch_count": (i64, [vp])}
+SPECIAL = {"sq_last_error": (C.c_char_p, []), "sq_version": (i32, []), "sq_fdm_launch_count": (i64, [vp]),
+           "sq_hmc_last_reject": (C.c_char_p, [vp])}
 
 
 def header_symbols():
@@ -119,6 +126,11 @@ def build(verbose=False):
 
 class SqError(RuntimeError):
     pass
+
+
+class SqNumericalInstability(SqError):
+    """ABI status 3: NaN / non-finite residual, Lanczos coefficient or action.  The reference's callers turn this -- and only
+    this -- into a rejected update (src/EFAPFFHMCUpdater.jl:168-187, src/reflection_update.jl:111-127)."""
 
 
 _lib = None
@@ -151,6 +163,8 @@ def load():
 
 
 def check(status):
+    if status == 3:
+        raise SqNumericalInstability(load().sq_last_error().decode())
     if status != 0:
         raise SqError(load().sq_last_error().decode())
 

@@ -2,7 +2,7 @@
 
 Two modes:
   * independent chains -- the reference's only parallel mode (tutorials/holstein_honeycomb_mpi.jl:60-72):
-    rank r runs its own Markov chain with seed `seed + r`; nothing is communicated during sampling and
+    rank r runs its own Markov chain with seeds `chain_seed(seed, r, component)`; nothing is communicated during sampling and
     the per-chain statistics are merged at the end (`merge_chain_statistics`).
   * tau-slab partitioning -- rank g owns the contiguous slices [lo, hi) of every [l][i] array; M couples
     slice l to l-1 and M^T to l+1, so a matvec needs one boundary slice from each ring neighbour
@@ -15,9 +15,15 @@ from __future__ import annotations
 import numpy as np
 
 
-def chain_seed(seed: int, rank: int) -> int:
-    """Seed of the chain run by `rank` (the MPI tutorial uses seed + pID)."""
-    return int(seed) + int(rank)
+def chain_seed(seed: int, rank: int, component: int = 0) -> int:
+    """Seed of the chain run by `rank` (the MPI tutorial seeds its Xoshiro with seed + pID; for the counter-based Philox streams of
+    this library consecutive integers would make chain r's Greens stream equal chain r + 1's HMC stream, so the seed is a splitmix64
+    hash of (seed, rank, component) -- component 0 the chain's numpy rng, 1 HMC, 2 GreensEstimator, 3 pseudofermion noise, 4 KPM)."""
+    m = (1 << 64) - 1
+    z = (int(seed) + 0x9E3779B97F4A7C15 * (1 + int(rank) + 1000003 * int(component))) & m
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & m
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & m
+    return (z ^ (z >> 31)) & m
 
 
 def slab_range(Ltau: int, world: int, rank: int):
@@ -37,7 +43,6 @@ def halo_plan(Ltau: int, world: int, rank: int):
         "sign_from_prev": 1.0 if lo == 0 else -1.0,
         # (M^T v)[l] = v[l] - B_{l+1}^T v[l+1] for l < L-1, + for l = L-1
         "sign_from_next": 1.0 if hi == Ltau else -1.0,
-        "halo_bytes_per_direction": None,
     }
 
 

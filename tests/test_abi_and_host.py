@@ -96,7 +96,8 @@ import smoqyelph_b200
 from smoqyelph_b200 import parallel
 dist.init_process_group("gloo")
 r, w = dist.get_rank(), dist.get_world_size()
-assert parallel.chain_seed(100, r) == 100 + r
+seeds = {parallel.chain_seed(100, q, c) for q in range(w) for c in range(5)}
+assert len(seeds) == 5 * w and parallel.chain_seed(100, r) != parallel.chain_seed(101, r)      # hashed, no collisions between chains / components
 mean, err = parallel.merge_chain_statistics([1.0 + r, 10.0 * (r + 1)], dist)
 assert np.allclose(mean, [1.5, 15.0]) and np.allclose(err, [0.5, 5.0]), (mean, err)
 t = parallel.max_over_ranks(1.0 + r, dist)

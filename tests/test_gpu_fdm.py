@@ -197,23 +197,20 @@ def test_register_path_requires_uniform_colours_and_canonical_order():
     assert relerr(fdm2.mul_MtM(v), ref2.mul_MtM(v)) < RTOL
 
 
-@pytest.mark.parametrize("solver", ["resident", "resident2", "persistent", "launches", "launches_tma"])
+@pytest.mark.parametrize("solver", ["resident", "launches", "launches_tma"])
 @pytest.mark.parametrize("name", ["h16x16", "h32x16", "h32x32", "hc8", "hc24"])
 def test_register_path_cg(name, solver, monkeypatch):
-    """CG on the register path in native order: the resident kernels (one / two grid-wide sums per iteration), the
-    persistent kernel and the two-launches-per-iteration loop against the oracle's CG."""
+    """CG on the register path in native order: the whole-solve resident kernel (one grid-wide sum per iteration) and the
+    two-launches-per-iteration loop (its only fallback) against the oracle's CG."""
     m, rng, ref, fdm = setup_square(name)
     b = rand_cvec(rng, m)
     fdm.set_fast_path(2 + 256 * 3)
-    if solver == "resident2":                       # the two-sums-per-iteration resident kernel (square lattices)
-        monkeypatch.setenv("SQ_V3_RESIDENT", "2")
-    elif solver == "persistent":
-        monkeypatch.setenv("SQ_NO_RESIDENT_CG", "1")
-    elif solver == "launches":
+    if solver == "launches":
         monkeypatch.setenv("SQ_NO_PERSISTENT_CG", "1")
     elif solver == "launches_tma":                  # first matvec of every solve with the operands staged by bulk async copies
         monkeypatch.setenv("SQ_NO_PERSISTENT_CG", "1")
         monkeypatch.setenv("SQ_V3_PRE", "2")
+    st0 = fdm.stats
     xr, itr, epsr = ref.cg(b, tol=1e-14, maxiter=20000)
     xg, itg, epsg = fdm.ldiv(b, tol=1e-14, maxiter=20000)
     assert epsg < 1e-14 and epsr < 1e-14
@@ -231,6 +228,41 @@ def test_register_path_cg(name, solver, monkeypatch):
     # warm start from a perturbed solution converges to the same answer
     x2, it2, _ = fdm.ldiv(b, x0=xg * (1 + 1e-3), tol=1e-12)
     assert relerr(x2, xr) < 1e-9 and it2 > 0
+    # the solver that was asked for is the one that ran (sq_fdm_stats), and no watchdog fired
+    st = fdm.stats
+    key = "cg_resident" if solver == "resident" else "cg_launch_loop"
+    assert st[key] - st0[key] >= 5, (solver, st0, st)
+    assert st["watchdog_aborts"] == 0 and st["instabilities"] == 0
+    # maxiter = 0: no iteration, the initial residual is reported (not stale partial sums of an earlier solve)
+    _, it00, eps00 = fdm.ldiv(b, tol=1e-10, maxiter=0)
+    assert it00 == 0 and abs(eps00 - 1.0) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["cfg3", "cfg4", "cfg5"])
+def test_cg_iteration_counts_at_named_sizes(name):
+    """CG iteration counts within +-1 of the reference recurrence (src/IterativeSolvers/ConjugateGradient.jl:93-167) at the FULL size of
+    the named configurations 3, 4, 5 and at the production tolerances 1e-5 / 1e-10, on tau-smooth synthetic fields.
+    cfg4 / cfg5 run the whole-solve resident register kernel the benchmark times; cfg3 the cooperative shared-memory kernel."""
+    from smoqyelph_b200 import api
+    m = mdl.config(name)
+    rng = np.random.default_rng(11)
+    V, t = dr.build_Vt(m, m.random_fields(rng, smooth=True))
+    ref = orc.RefFDM(m, sym=True, omp=True)
+    ref.update(V, t)
+    fdm = api.FermionDetMatrix(m, sym=True)
+    fdm.update(V, t)
+    b = rand_cvec(rng, m)
+    st0 = fdm.stats
+    for tol in (1e-5, 1e-10):
+        xr, itr, epsr = ref.cg(b, tol=tol, maxiter=20000)
+        xg, itg, epsg = fdm.ldiv(b, tol=tol, maxiter=20000)
+        assert abs(itg - itr) <= 1, (name, tol, itg, itr)
+        assert epsg < tol and epsr < tol
+        assert relerr(xg, xr) < 50 * tol                     # both inside the tolerance ball (cond(M^T M) ~ 10 on these fields)
+    st = fdm.stats
+    if name in ("cfg4", "cfg5"):
+        assert st["cg_resident"] - st0["cg_resident"] == 2, st
+    assert st["watchdog_aborts"] == 0
 
 
 @pytest.mark.parametrize("name", ["h16x16", "h32x32", "h32x64", "hc8", "hc24"])

@@ -26,7 +26,22 @@ MODELS = {
     "cfg3s": lambda: mdl.bssh_square(8, 8, 1.0),
     "mixed": lambda: mdl.holstein_ssh_chain(7, 0.65),
     "nosym": lambda: mdl.holstein_square(4, 4, 0.5, ph_sym=False),
+    # register-path lattices: every CG solve of these runs the whole-solve resident kernel (k_cg_v3_resident1) and the native-order
+    # conversion -- the code path the benchmark times (cfg4 = 32 x 32, cfg5 = honeycomb)
+    "sq16": lambda: mdl.holstein_square(16, 16, 0.5),
+    "sq32": lambda: mdl.holstein_square(32, 32, 0.3),
+    "hc8": lambda: mdl.holstein_honeycomb(8, 0.4),
 }
+REGISTER_PATH = ("sq16", "sq32", "hc8")
+
+
+def assert_register_path(name, sym, gf, st0):
+    """On the register-path lattices (Sym) every unpreconditioned solve since `st0` must have run the resident kernel."""
+    st = gf.stats
+    assert st["watchdog_aborts"] == 0
+    if name in REGISTER_PATH and sym:
+        d = {k: st[k] - st0[k] for k in st}
+        assert d["cg_solves"] > 0 and d["cg_resident"] == d["cg_solves"] - d["cg_preconditioned"], (name, d)
 
 
 def both(name, sym, seed=0, exact=False):
@@ -81,6 +96,7 @@ def test_refresh_and_lambda(name, sym):
 @pytest.mark.parametrize("name", list(MODELS))
 def test_action_and_force(name, sym, exact):
     m, rng, x, (rf, re, rp), (gf, ge, gp) = both(name, sym, exact=exact)
+    st0 = gf.stats
     R = rand_cvec(rng, m)
     Sr = rp.sample(R)
     Sg = gp.sample_pseudofermion_fields(R)
@@ -101,14 +117,21 @@ def test_action_and_force(name, sym, exact):
     Fr, Sr, _, _ = rp.force(tol=1e-14, maxiter=20000)
     F0 = np.asfortranarray(0.25 * np.ones((m.Nph, m.Ltau)))          # dSdx is accumulated into (+=)
     Fg, Sg, _, _ = gp.calculate_derivative_fermionic_action(dSdx=F0.copy(order="F"), tol=1e-14, maxiter=20000)
-    assert relerr(Fg - 0.25, Fr) < 1e-10      # CG solutions converged to 1e-14 on both sides; force is linear in Psi (x2)
+    # End-to-end bound: the force is linear in Psi, and Psi is only known to the solver's accuracy -- both sides stop at a relative
+    # RESIDUAL of 1e-14, i.e. a relative solution error of up to cond(M^T M) x 1e-14 (cond ~ 1e2 - 1e3 on these fields).  So: Psi to
+    # 1e-11, and the force to (a small multiple of) the Psi difference; with identical Psi the kernels agree to 1e-12
+    # (test_force_parity_at_fixed_psi_is_1e12, test_refresh_and_lambda).
     _, Psi, _ = gp.fields()
-    assert relerr(Psi, rp.Psi) < 1e-10
+    e_psi = relerr(Psi, rp.Psi)
+    e_f = relerr(Fg - 0.25, Fr)
+    assert e_psi < 1e-11, (name, sym, e_psi)
+    assert e_f < max(FORCE_RTOL, 30 * e_psi), (name, sym, e_f, e_psi)
     # production tolerances: iteration counts within +-1
     for tol in (1e-5, 1e-10):
         _, itr, _ = rp.action(tol=tol, maxiter=20000)
         _, itg, _ = gp.calculate_fermionic_action(tol=tol, maxiter=20000)
         assert abs(itg - itr) <= 1
+    assert_register_path(name, sym, gf, st0)
 
 
 def test_force_parity_at_fixed_psi_is_1e12():
@@ -137,12 +160,13 @@ def test_efa_pieces(name):
 
 
 @pytest.mark.parametrize("precond", [False, True])
-@pytest.mark.parametrize("name,sym", [("cfg1t", True), ("mixed", True), ("mixed", False), ("cfg3s", True)])
+@pytest.mark.parametrize("name,sym", [("cfg1t", True), ("mixed", True), ("mixed", False), ("cfg3s", True), ("sq16", True), ("hc8", True)])
 def test_hmc_update_matches_oracle(name, sym, precond):
     """One full hmc_update! with the same random stream on both sides: same trajectory, energies, decision."""
     from smoqyelph_b200 import api
     m, rng, x, (rf, re, rp), (gf, ge, gp) = both(name, sym, seed=5)
     Nt = 6
+    st0 = gf.stats
     ra = orc.RefEFA(re)
     hmc = api.EFAPFFHMCUpdater(ge, gp, Nt=Nt, delta=0.05)
     Pr = Pg = None
@@ -162,6 +186,9 @@ def test_hmc_update_matches_oracle(name, sym, precond):
         assert abs(info_g[k] - info_r[k]) < 1e-9 * max(1.0, abs(info_r[k])), k
     assert abs(info_g[1] - info_r[1]) < 1e-7 * max(1.0, abs(info_r[1]))
     assert abs(info_g[0] - info_r[0]) <= 1.0
+    assert hmc.last_reject == ""
+    if not precond:
+        assert_register_path(name, sym, gf, st0)
     # rejected trajectory restores x and the operator
     x_before = ge.x
     rnd[-1] = 2.0
@@ -187,10 +214,11 @@ def test_hmc_library_rng_runs_and_conserves_energy():
     assert dHs[1] < dHs[0] / 4
 
 
-@pytest.mark.parametrize("name", ["cfg1t", "mixed"])
+@pytest.mark.parametrize("name", ["cfg1t", "mixed", "sq16", "hc8"])
 def test_greens_estimator_and_scalar_measurements(name):
     from smoqyelph_b200 import api
     m, rng, x, (rf, re, rp), (gf, ge, gp) = both(name, True)
+    st0 = gf.stats
     Nrv, V = 6, m.N * m.Ltau
     R = rng.standard_normal((V, Nrv)) + 1j * rng.standard_normal((V, Nrv))
     R = np.asfortranarray(R / np.abs(R))
@@ -208,6 +236,7 @@ def test_greens_estimator_and_scalar_measurements(name):
         assert abs(meas[key] - want) < 1e-12 * max(1.0, abs(want)), key
     want = orc.measure("Nsqrd", R, GRg, Ltau=m.Ltau)
     assert abs(meas["Nsqrd"] - want) < 1e-11 * max(1.0, abs(want))
+    assert_register_path(name, True, gf, st0)
     # warm start: a second update with the same R converges immediately
     assert g.update_greens_estimator(R=R, tol=1e-10, maxiter=20000) == 0
     # library RNG path + update_chemical_potential wiring
@@ -218,3 +247,50 @@ def test_greens_estimator_and_scalar_measurements(name):
     mu_new, it = api.update_chemical_potential(gf, g2, ge, 0.0, lambda n, N2: 0.1, tol=1e-10)
     V2, _ = ge.Vt()
     np.testing.assert_allclose(V2, re.V - 0.1, atol=1e-13)
+
+
+def test_instability_is_rejected_loudly_and_other_errors_propagate(capfd):
+    """A NaN inside the trajectory (the reference's "numerical instability") rejects the update with a warning and a recorded reason;
+    anything else -- here a random stream that is too short -- is an error for the caller, not a silent rejection."""
+    from smoqyelph_b200 import api
+    m, rng, x, _, (gf, ge, gp) = both("cfg1t", True)
+    hmc = api.EFAPFFHMCUpdater(ge, gp, Nt=2, seed=5)
+    with pytest.raises(api.SqError):
+        hmc.hmc_update(randoms=np.zeros(5))
+    xb = x.copy(order="F")
+    xb[0, 0] = np.nan                                   # poisons exp(-dtau V) => NaN residual in the first force solve
+    ge.x = xb
+    ge.update_fdm()
+    acc, _ = hmc.hmc_update(tol_action=1e-10, tol_force=1e-5)
+    assert not acc
+    assert "NaN" in hmc.last_reject or "not finite" in hmc.last_reject
+    assert gf.stats["instabilities"] >= 1
+    assert "rejecting update" in capfd.readouterr().err
+    ge.x = x
+    ge.update_fdm()
+    acc, _ = hmc.hmc_update(tol_action=1e-10, tol_force=1e-5)
+    assert hmc.last_reject == ""
+
+
+def test_component_streams_and_seeds_are_independent():
+    """Same seed, different components => different normals (round-1 ADVICE: HMC, Greens and PFF all started at stream 0), and
+    the pseudofermion noise of the global moves follows the HMC seed unless it is set explicitly."""
+    from smoqyelph_b200 import api
+    m, rng, x, _, (gf, ge, gp) = both("cfg1t", True)
+    g = api.GreensEstimator(gf, Nrv=2, seed=0)
+    g.update_greens_estimator(tol=1e-8)
+    R, _ = g.get()
+    api.EFAPFFHMCUpdater(ge, gp, Nt=2, seed=0)           # derives the PFF seed from the HMC seed
+    gp.sample_pseudofermion_fields(None)
+    Phi_a, _, _ = gp.fields()
+    api.EFAPFFHMCUpdater(ge, gp, Nt=2, seed=1)
+    gp.sample_pseudofermion_fields(None)
+    Phi_b, _, _ = gp.fields()
+    assert relerr(Phi_a, Phi_b) > 0.5                      # different chains, different noise
+    gp2 = api.PFFCalculator(ge, seed=1234)
+    gp3 = api.PFFCalculator(ge, seed=1234)
+    gp2.sample_pseudofermion_fields(None)
+    gp3.sample_pseudofermion_fields(None)
+    assert np.array_equal(gp2.fields()[0], gp3.fields()[0])   # reproducible from the seed
+    ang = np.angle(R[:, 0])
+    assert abs(np.corrcoef(ang[: Phi_a.size], np.angle(Phi_a.ravel(order="F")))[0, 1]) < 0.2
