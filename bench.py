@@ -53,15 +53,30 @@ def emit(line):
     out.flush()
 
 
+STATE_FILE = os.path.join(ROOT, "bench_data", "bench_state_cfg4_f32.npy")
+
+
 def cdw_start(m, seed):
     """Synthetic but physical start: the staggered (charge-density-wave) phonon order of the half-filled
-    Holstein model at beta = 20, plus free-phonon thermal fluctuations.  Warm-up trajectories relax it."""
+    Holstein model at beta = 20, plus free-phonon thermal fluctuations."""
     from smoqyelph_b200 import model as mdl
     rng = np.random.default_rng(seed)
     Lx = m.lattice_dims[0]
     s = np.arange(m.N)
     stag = np.where(((s % Lx) + (s // Lx)) % 2 == 0, 1.0, -1.0)
     return np.asfortranarray(1.5 * stag[:, None] + 0.3 * mdl.thermal_fields(m, rng))
+
+
+def bench_state(m):
+    """The phonon field BOTH arms time: cdw_start relaxed by 20 EFA-PFF-HMC trajectories (tools/make_bench_state.py, run once on a
+    B200 and committed as float32), so that the CPU arm -- which cannot afford warm-up trajectories -- sees the same thermalised,
+    tau-rough field as the GPU arm.  (On the raw CDW start the field is tau-smooth and a preconditioned solve takes 8 iterations
+    instead of ~100: not a representative workload.)  Falls back to the raw start for other configurations."""
+    if m.name == "cfg4" and os.path.exists(STATE_FILE):
+        x = np.load(STATE_FILE).astype(np.float64)
+        if x.shape == (m.Nph, m.Ltau):
+            return np.asfortranarray(x), "cdw_start(seed 1000) relaxed by 20 EFA-PFF-HMC trajectories on a B200 (bench_data/bench_state_cfg4_f32.npy, tools/make_bench_state.py)"
+    return cdw_start(m, 1000), "staggered CDW order 1.5 + 0.3 x free-phonon thermal noise (seed 1000), NOT relaxed"
 
 
 class ClockSampler:
@@ -164,54 +179,67 @@ def algorithmic_bytes(m):
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU arm / cpu_baseline: the oracle port, bounded sample, extrapolated with the trajectory's CG iteration count
+# CPU arm / cpu_baseline: the oracle port on the box's host cores.  One sample = the pieces of a trajectory timed FOR REAL on the
+# bench phonon state: one complete force evaluation (CG to tol_force -- its iteration count is measured, not assumed -- plus the
+# Lambda / M / M^T / dM/dx / dLambda/dx tail), one operator refresh, and (first sample only) one complete action evaluation (CG to
+# tol_action).  A trajectory is Nt force evaluations + 1 action evaluation + Nt + 2 refreshes, so
+#     t_trajectory = Nt t_force + t_action + (Nt + 2) t_refresh.
+# The only extrapolation left is "the Nt force solves of a trajectory cost Nt times the first one"; a complete CPU trajectory at cfg4
+# takes about a minute per step, which does not fit a run of a few minutes.
 # ------------------------------------------------------------------------------------------------------
-def cpu_sample(m, x, precond, omp, budget_s, iters_per_traj):
-    from oracle import oracle as orc
-    rng = np.random.default_rng(7)
-    if omp:                                                  # all host cores this process may use, whatever OMP_NUM_THREADS the launcher exported
-        orc.lib(True).ref_set_num_threads(len(os.sched_getaffinity(0)))
-    f = orc.RefFDM(m, sym=True, tol=TOL_FORCE, maxiter=MAXITER, omp=omp)
-    e = orc.RefElPh(m, omp=omp)
-    e.set_x(x)
-    t0 = time.perf_counter()
-    e.refresh(f)
-    t_refresh = time.perf_counter() - t0
-    pff = orc.RefPFF(e, f)
-    R = (rng.standard_normal((m.Ltau, m.N)) + 1j * rng.standard_normal((m.Ltau, m.N))) / np.sqrt(2)
-    pff.sample(R)
-    P = None
-    if precond:
-        P = orc.RefKPM(f)
-        P.update(rng.standard_normal(m.N))
-    # calibrate: 3 CG iterations, then size the sample to the budget
-    b = np.asfortranarray(R)
-    t0 = time.perf_counter()
-    f.cg(b, P=P, tol=1e-300, maxiter=3)
-    t3 = (time.perf_counter() - t0) / 3
-    n_it = int(max(5, min(400, budget_s * 0.7 / t3)))
-    t0 = time.perf_counter()
-    f.cg(b, P=P, tol=1e-300, maxiter=n_it)
-    t_iter = (time.perf_counter() - t0) / n_it
-    # force evaluation with the solve capped at 2 iterations: the non-CG tail (Lambda ops, M, M^T, dM/dx, dLambda/dx)
-    t0 = time.perf_counter()
-    pff.force(P=P, lanczos_start=rng.standard_normal(m.N) if P is not None else None, tol=1e-300, maxiter=2)
-    t_tail = max(0.0, time.perf_counter() - t0 - 2 * t_iter)
-    t_traj = iters_per_traj * t_iter + NT * t_tail + (NT + 2) * t_refresh
-    threads = f.L.ref_num_threads()
-    sample = (f"{n_it} CG iterations of M^T M (precond={'KPM' if precond else 'I'}) + 1 force tail + 1 operator refresh of the C oracle "
-              f"port on the bench phonon state; t_iter={t_iter * 1e3:.2f} ms, t_tail={t_tail * 1e3:.1f} ms, t_refresh={t_refresh * 1e3:.1f} ms; "
-              f"extrapolated to one trajectory = {iters_per_traj:.0f} CG iterations (count from the GPU arm, parity-tested +-1) "
-              f"+ {NT} tails + {NT + 2} refreshes")
-    return 1.0 / t_traj, threads, sample, {"t_iter_ms": t_iter * 1e3, "t_tail_ms": t_tail * 1e3, "t_refresh_ms": t_refresh * 1e3, "n_it": n_it}
+class CpuArm:
+    def __init__(self, m, x, precond, omp):
+        from oracle import oracle as orc
+        self.orc, self.m, self.precond = orc, m, precond
+        if omp:                                              # all host cores this process may use, whatever OMP_NUM_THREADS the launcher exported
+            orc.lib(True).ref_set_num_threads(len(os.sched_getaffinity(0)))
+        rng = np.random.default_rng(7)
+        self.rng = rng
+        self.f = orc.RefFDM(m, sym=True, tol=TOL_FORCE, maxiter=MAXITER, omp=omp)
+        self.e = orc.RefElPh(m, omp=omp)
+        self.e.set_x(x)
+        t0 = time.perf_counter()
+        self.e.refresh(self.f)
+        self.t_refresh = time.perf_counter() - t0
+        self.pff = orc.RefPFF(self.e, self.f)
+        R = (rng.standard_normal((m.Ltau, m.N)) + 1j * rng.standard_normal((m.Ltau, m.N))) / np.sqrt(2)
+        self.pff.sample(R)
+        self.P = None
+        if precond:
+            self.P = orc.RefKPM(self.f)
+            self.P.update(rng.standard_normal(m.N))
+        self.threads = self.f.L.ref_num_threads()
+        self.t_action = self.it_action = None
+        self.real_seconds = 0.0
 
+    def _start(self):
+        return self.rng.standard_normal(self.m.N) if self.P is not None else None
 
-def stored_iters(precond):
-    try:
-        d = json.load(open(ITERS_FILE))
-        return float(d["precond_on" if precond else "precond_off"]["cg_iters_per_trajectory"])
-    except Exception:
-        return 20000.0 if not precond else 4000.0
+    def sample(self, quick=False):
+        """-> trajectories/s from one real force evaluation (quick: capped at 3 CG iterations, for warm-up steps)."""
+        t0 = time.perf_counter()
+        _, _, it_f, _ = self.pff.force(P=self.P, lanczos_start=self._start(), tol=TOL_FORCE, maxiter=3 if quick else MAXITER)
+        t_force = time.perf_counter() - t0
+        self.real_seconds += t_force
+        if quick:
+            return None
+        if self.t_action is None:
+            t0 = time.perf_counter()
+            _, it_a, _ = self.pff.action(P=self.P, lanczos_start=self._start(), tol=TOL_ACTION, maxiter=MAXITER)
+            self.t_action, self.it_action = time.perf_counter() - t0, it_a
+            self.real_seconds += self.t_action
+        t_traj = NT * t_force + self.t_action + (NT + 2) * self.t_refresh
+        self.last = {"t_force_s": t_force, "cg_iters_force": int(it_f), "t_action_s": self.t_action, "cg_iters_action": int(self.it_action),
+                     "t_refresh_s": self.t_refresh}
+        return 1.0 / t_traj
+
+    def describe(self, nsamples):
+        d = self.last
+        return (f"{nsamples} x [one complete force evaluation: CG on M^T M to {TOL_FORCE:g} (precond={'KPM' if self.precond else 'I'}, "
+                f"{d['cg_iters_force']} iterations measured) + Lambda/M/M^T/dM/dx tail, {d['t_force_s']:.2f} s] + one complete action evaluation "
+                f"(CG to {TOL_ACTION:g}, {d['cg_iters_action']} iterations, {d['t_action_s']:.2f} s) + operator refresh ({d['t_refresh_s'] * 1e3:.0f} ms) of the C "
+                f"oracle port on the bench phonon state, all timed for real ({self.real_seconds:.1f} s of CPU work in this run); "
+                f"trajectory = {NT} x force + action + {NT + 2} x refresh")
 
 
 def run_reference(args):
@@ -220,35 +248,48 @@ def run_reference(args):
         return
     from smoqyelph_b200 import model as mdl
     m = mdl.config(args.config)
-    precond = args.precond == "on"
-    x = cdw_start(m, 1000)
-    iters = stored_iters(precond)
-    vals, info, threads, sample = [], None, 1, ""
-    budget = max(5.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    precond = args.precond != "off"                          # stock configuration of every shipped driver: a KPMPreconditioner (tutorials/holstein_honeycomb.jl:507)
+    x0, state_label = bench_state(m)
+    arm = CpuArm(m, x0, precond, True)
+    t_wall = time.perf_counter()
+    vals = []
     for step in range(args.warmup + args.steps):
-        v, threads, sample, info = cpu_sample(m, x, precond, True, budget, iters)
-        if step >= args.warmup:
-            vals.append(v)
+        if step < args.warmup:
+            arm.sample(quick=True)
+            continue
+        if vals and time.perf_counter() - t_wall > 150.0:    # keep the whole run within a few minutes: reuse the samples taken so far
+            break
+        vals.append(arm.sample())
     val = float(np.mean(vals))
     line = {"impl": "reference", "metric": "efa_hmc_trajectories_per_s", "value": val, "unit": "trajectories/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True,
+            "scaling": "strong" if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(m, precond, "cpu"),
-            "cpu_baseline": {"value": val, "unit": "trajectories/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": workload_config(m, "KPM (defaults)" if precond else "I", "cpu", state_label),
+            "cpu_baseline": {"value": val, "unit": "trajectories/s", "cores": arm.threads, "kind": "port", "sample": arm.describe(len(vals))},
             "e2e": {"value": val, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "detail": info}
+            "gpu_launches": 0, "real_timed_seconds": arm.real_seconds, "samples": len(vals),
+            "note": "ONE Markov chain on the host cores at every --gpus N (the reference has no intra-chain parallelism beyond threads); "
+                    "ms_per_step is the modelled time of a whole trajectory, real_timed_seconds what this run actually spent in its samples",
+            "detail": arm.last}
     emit(line)
 
 
-def workload_config(m, precond, where):
-    return {"workload": f"{m.name}: Holstein square {m.lattice_dims[0]}x{m.lattice_dims[1]}, beta={m.beta:g}, dtau={m.dtau:g} "
-                        f"(N={m.N}, Ltau={m.Ltau}, N*Ltau={m.N * m.Ltau}), Omega=1, alpha=1.5, mu=0, ph_sym_form; "
-                        f"EFA-PFF-HMC Nt={NT}, tol_action={TOL_ACTION:g}, tol_force={TOL_FORCE:g}, SymFermionDetMatrix",
-            "preconditioner": "KPM (defaults)" if precond else "I",
-            "phonon_state": "staggered CDW order 1.5 + 0.3 x free-phonon thermal noise, relaxed by the warm-up trajectories",
-            "parallelism": "independent chains, one per GPU" if where == "gpu" else "OpenMP over tau inside each sweep",
-            "l2": "trajectory working set is L2-resident by nature (vector 6.5 MB); roofline kernel timed with an L2 flush "
-                  "(256 MB write) between launches"}
+def workload_config(m, precond_label, where, state_label, extra=None):
+    cfg = {"workload": f"{m.name}: Holstein square {m.lattice_dims[0]}x{m.lattice_dims[1]}, beta={m.beta:g}, dtau={m.dtau:g} "
+                       f"(N={m.N}, Ltau={m.Ltau}, N*Ltau={m.N * m.Ltau}), Omega=1, alpha=1.5, mu=0, ph_sym_form; "
+                       f"EFA-PFF-HMC Nt={NT}, tol_action={TOL_ACTION:g}, tol_force={TOL_FORCE:g}, SymFermionDetMatrix",
+           "preconditioner": precond_label,
+           "phonon_state": state_label + "; both arms start their timed region from this very field (the native arm's warm-up trajectories "
+                           "are discarded)",
+           "parallelism": {"gpu": "one Markov chain on one GPU", "gpu_strong": "ONE Markov chain, CG solves tau-slab partitioned over all GPUs "
+                           "(strong scaling; full state replicated, halos and dot products through peer-mapped mailboxes)",
+                           "cpu": "OpenMP over tau inside each sweep"}[where],
+           "l2": "trajectory working set is L2-resident by nature (vector 6.5 MB); roofline kernel timed with an L2 flush "
+                 "(256 MB write) between launches"}
+    if extra:
+        cfg.update(extra)
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -276,90 +317,179 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     m = mdl.config(args.config)
-    precond = args.precond == "on"
     fdm = api.SymFermionDetMatrix(m, tol=TOL_ACTION, maxiter=MAXITER, device=local)
     elph = api.ElectronPhononParameters(m, fdm)
     pff = api.PFFCalculator(elph)
-    P = api.KPMPreconditioner(fdm, update=False) if precond else None
-    elph.x = cdw_start(m, 1000)                              # every chain starts from the same relaxed configuration ...
+    P_kpm = api.KPMPreconditioner(fdm, update=False)
+    x0, state_label = bench_state(m)                         # the state both arms time (see config.phonon_state)
+    elph.x = x0
     elph.update_fdm()
     stream = torch.cuda.ExternalStream(fdm.stream, device=dev)
     L = lib.load()
+    nx = m.Nph * m.Ltau
 
-    def trajectory(h):
+    def trajectory(h, P):
         acc = C.c_int(0)
         info = np.zeros(8)
         lib.check(L.sq_hmc_update(h.h, P.h if P is not None else None, TOL_ACTION, TOL_FORCE, MAXITER, None, 0, C.byref(acc), lib.ptr(info)))
         return bool(acc.value), info
 
-    # ---- warm-up (untimed): relaxes the synthetic start, warms the caches and the clocks
-    hmc = api.EFAPFFHMCUpdater(elph, pff, Nt=NT, seed=77)
-    for _ in range(args.warmup):
-        trajectory(hmc)
-    x_w = elph.x                                             # state every timed leg starts from
-
-    def fresh_updater():
-        elph.x = x_w
+    def fresh_updater(seed):
+        elph.x = x0
         elph.update_fdm()
-        return api.EFAPFFHMCUpdater(elph, pff, Nt=NT, seed=4242 + rank)      # ... and samples with its own seed (seed + rank)
+        return api.EFAPFFHMCUpdater(elph, pff, Nt=NT, seed=seed)
 
-    # ---- value: K trajectories, x resident in HBM, timed with CUDA events on the library stream
-    h = fresh_updater()
-    sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = fdm.launch_count
-    e0.record(stream)
-    iters_total, accepted = 0.0, 0
-    for _ in range(args.steps):
-        acc, info = trajectory(h)
-        iters_total += info[0] * (NT + 1)
-        accepted += int(acc)
-    e1.record(stream)
-    e1.synchronize()
-    launches = fdm.launch_count - l0
-    ms_dev = e0.elapsed_time(e1)
-    t = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    barrier()
-    clocks = sampler.stop() if sampler else None
-    ms_value = float(t.item())
-    value = world * args.steps / (ms_value * 1e-3)
+    def timed_chain(P, steps, seed):
+        """`steps` trajectories from x0, x resident in HBM, CUDA events on the library stream -> (ms, CG iterations, accepted, launches)."""
+        h = fresh_updater(seed)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = fdm.launch_count
+        e0.record(stream)
+        iters, accepted = 0.0, 0
+        for _ in range(steps):
+            acc, info = trajectory(h, P)
+            iters += info[0] * (NT + 1)
+            accepted += int(acc)
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1), iters, accepted, fdm.launch_count - l0
 
-    # ---- e2e: same trajectories, x crosses PCIe both ways every step (pinned host buffer), wall clock
-    h = fresh_updater()
-    nx = m.Nph * m.Ltau
+    # ---- warm-up (untimed, discarded): warms caches, clocks and the autotuner for both solver configurations
+    hw = fresh_updater(77)
+    for k in range(args.warmup):
+        trajectory(hw, P_kpm if (k == args.warmup - 1 and args.precond != "off") else None)
+
+    # ---- which preconditioner?  The reference's drivers pass a KPMPreconditioner; the library accepts either, exactly as the reference
+    #      (`preconditioner = I` or a KPMPreconditioner).  `auto` times one trajectory of each from the bench state and keeps the faster.
+    choice = {}
+    if args.precond == "auto":
+        for label, P in (("I", None), ("KPM (defaults)", P_kpm)):
+            ms, it, _, _ = timed_chain(P, 1, 4242)
+            choice[label] = {"trajectories_per_s": 1e3 / max_over_ranks(ms), "cg_iters_per_trajectory": it}
+        use_kpm = choice["KPM (defaults)"]["trajectories_per_s"] > choice["I"]["trajectories_per_s"]
+    else:
+        use_kpm = args.precond == "on"
+    P = P_kpm if use_kpm else None
+    plabel = "KPM (defaults)" if use_kpm else "I"
+    cfg_extra = {"preconditioner_choice": {"mode": args.precond, "timed_one_trajectory_each": choice or None,
+                                           "reference_arm_uses": "KPM (defaults), the stock configuration of the shipped drivers"}}
+
     pin = torch.empty(nx, dtype=torch.float64).pin_memory()
-    pin.copy_(torch.from_numpy(np.ascontiguousarray(x_w.ravel(order="F"))))
+    pin.copy_(torch.from_numpy(np.ascontiguousarray(x0.ravel(order="F"))))
     pptr = C.c_void_p(pin.data_ptr())
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        lib.check(L.sq_elph_set_x(elph.h, pptr))             # H2D
-        lib.check(L.sq_elph_refresh_fdm(elph.h))
-        trajectory(h)
-        lib.check(L.sq_elph_get_x(elph.h, pptr))             # D2H (blocking)
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    barrier()
-    e2e_value = world * args.steps / float(t.item())
 
-    roofline = None
-    iters_per_traj = iters_total / args.steps
-    per_rank = None
-    if dist is not None:
-        # the chains differ (seed + rank), so do their CG iteration counts: the job time is the slowest chain's
-        pr = torch.tensor([ms_dev / args.steps, iters_per_traj], dtype=torch.float64, device=dev)
+    def e2e_chain(P, steps, seed):
+        """same trajectories through the C ABI with HOST buffers: x crosses PCIe both ways every step (pinned), wall clock"""
+        h = fresh_updater(seed)
+        pin.copy_(torch.from_numpy(np.ascontiguousarray(x0.ravel(order="F"))))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            lib.check(L.sq_elph_set_x(elph.h, pptr))             # H2D
+            lib.check(L.sq_elph_refresh_fdm(elph.h))
+            trajectory(h, P)
+            lib.check(L.sq_elph_get_x(elph.h, pptr))             # D2H (blocking)
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    sampler = None
+    per_rank = chains = tau_slab = None
+    if world == 1:
+        # ---- value: K trajectories of one chain on one GPU
+        sampler = ClockSampler(local)
+        ms_dev, iters_total, accepted, launches = timed_chain(P, args.steps, 4242)
+        clocks = sampler.stop()
+        ms_value = ms_dev
+        value = args.steps / (ms_value * 1e-3)
+        e2e_value = args.steps / e2e_chain(P, args.steps, 4242)
+        scaling, where = "weak", "gpu"
+    else:
+        # ---- extra: independent chains, one per GPU (the reference's MPI mode; weak scaling) -- NOT the headline
+        ms_c, it_c, _, _ = timed_chain(P, args.steps, 4242 + rank)
+        pr = torch.tensor([ms_c / args.steps, it_c / args.steps], dtype=torch.float64, device=dev)
         allr = [torch.zeros_like(pr) for _ in range(world)]
         dist.all_gather(allr, pr)
-        per_rank = {"ms_per_step": [round(float(q[0]), 2) for q in allr], "cg_iters_per_trajectory": [round(float(q[1]), 1) for q in allr]}
+        chains = {"what": "independent chains, one per GPU, seed + rank (tutorials/holstein_honeycomb_mpi.jl mode; weak scaling)",
+                  "trajectories_per_s": world * args.steps / (max_over_ranks(ms_c) * 1e-3),
+                  "ms_per_step": [round(float(q[0]), 2) for q in allr], "cg_iters_per_trajectory": [round(float(q[1]), 1) for q in allr]}
+        # ---- value (north_star's target curve): ONE chain whose CG solves are tau-slab partitioned over all GPUs (strong scaling).
+        #      A watchdog prints the line with an error note if this section stalls.
+        import threading
+        stage = ["start"]
+        state = {}
+
+        def bail():
+            if rank == 0:
+                emit({"metric": "efa_hmc_trajectories_per_s", "value": None, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
+                      "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "independent_chains": chains,
+                      "error": "tau-slab section exceeded its time limit at stage '%s'" % stage[0]})
+            os._exit(0)
+        dog = threading.Timer(420.0, bail)
+        dog.daemon = True
+        dog.start()
+        n = m.N * m.Ltau
+        g = torch.Generator(device="cpu").manual_seed(99)
+        d_b = torch.randn(n, 2, dtype=torch.float64, generator=g).to(dev)
+        d_x1 = torch.zeros_like(d_b)
+        d_xN = torch.zeros_like(d_b)
+        elph.x = x0
+        elph.update_fdm()
+        stage[0] = "one-GPU solve"
+        it1, eps1 = fdm.cg_dev(d_x1.data_ptr(), d_b.data_ptr(), True, tol=1e-10, maxiter=MAXITER)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fdm.cg_dev(d_xN.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=400)
+        torch.cuda.synchronize()
+        us1 = max_over_ranks(time.perf_counter() - t0) / 400 * 1e6
+        stage[0] = "init sharded solve"
+        fdm.init_sharded_solve(dist)
+        stage[0] = "sharded solve parity"
+        itN, epsN = fdm.cg_dev(d_xN.data_ptr(), d_b.data_ptr(), True, tol=1e-10, maxiter=MAXITER)
+        torch.cuda.synchronize()
+        err = float((torch.linalg.norm(d_xN - d_x1) / torch.linalg.norm(d_x1)).item())
+        barrier()
+        t0 = time.perf_counter()
+        fdm.cg_dev(d_xN.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=400)
+        torch.cuda.synchronize()
+        usN = max_over_ranks(time.perf_counter() - t0) / 400 * 1e6
+        st = fdm.stats
+        tau_slab = {"what": "one chain, every unpreconditioned CG solve tau-slab partitioned over all GPUs",
+                    "parity": {"what": "same right-hand side solved to 1e-10 on one GPU and sharded over all GPUs",
+                               "err": max_over_ranks(err), "iters_1gpu": int(it1), "iters_ngpu": int(itN), "eps_1gpu": eps1, "eps_ngpu": epsN},
+                    "cg_us_per_iter_1gpu": us1, "cg_us_per_iter": usN, "cg_speedup_vs_1gpu": us1 / usN,
+                    "solver": "resident kernels + peer-mapped mailboxes" if st["cg_slab_resident"] else "host-launched NCCL loop",
+                    "comm": "grid-wide sums and boundary slices as device-initiated stores into peer-mapped mailboxes (CUDA IPC over NVLink); "
+                            "solution gathered with one grouped ncclBroadcast per solve"}
+        stage[0] = "sharded chain"
+        trajectory(fresh_updater(4242), None)                    # untimed: tunes the kernels for the slab range
+        sampler = ClockSampler(local) if rank == 0 else None
+        ms_dev, iters_total, accepted, launches = timed_chain(None, args.steps, 4242)     # same seeds on every rank: one chain
+        clocks = sampler.stop() if sampler else None
+        ms_value = max_over_ranks(ms_dev)
+        value = args.steps / (ms_value * 1e-3)                   # ONE chain: total work fixed as N grows
+        xs = elph.x
+        h = torch.tensor([float(np.abs(xs).sum()), float((xs * np.arange(1, xs.size + 1).reshape(xs.shape, order="F")).sum())], dtype=torch.float64, device=dev)
+        hh = [torch.zeros_like(h) for _ in range(world)]
+        dist.all_gather(hh, h)
+        tau_slab["ranks_bit_identical"] = bool(all(torch.equal(q, hh[0]) for q in hh))
+        stage[0] = "sharded e2e"
+        e2e_value = args.steps / e2e_chain(None, args.steps, 4242)
+        dog.cancel()
+        P, plabel, scaling, where = None, "I", "strong", "gpu_strong"
+        cfg_extra["preconditioner_choice"]["note"] = "strong-scaling leg: unpreconditioned (the sharded preconditioned solve is reported separately)"
+
+    iters_per_traj = iters_total / args.steps
     matvecs_per_traj = iters_per_traj + 2 * (NT + 1)
-    if rank == 0:
+    roofline = None
+    if rank == 0 and world == 1:
         # ---- roofline, rank 0.  Two kernels matter: the fused M^T M v kernel on its own (what north_star names), timed by
         #      the library with CUDA events on its stream (back to back = L2-hot as inside a solve; and L2-cold with a 256 MB
         #      write between launches), and the kernel the trajectory actually spends its time in -- with the register path
@@ -374,14 +504,22 @@ def run_native(args):
         op = 102 if path == 3 else api.OP_MTM                # 102: the register-path kernel on native-order vectors (as in CG)
         t_hot = fdm.time_mul(op, d_out.data_ptr(), d_in.data_ptr(), 400) * 1e-6
         t_cold = fdm.time_mul(op, d_out.data_ptr(), d_in.data_ptr(), 60, flush.data_ptr(), flush.numel() * 4) * 1e-6
-        # CG iteration time: fixed iteration count, device-resident vectors (one launch per solve on the register path)
-        nit = 2000
-        fdm.cg_dev(d_out.data_ptr(), d_in.data_ptr(), True, preconditioner=P, tol=1e-300, maxiter=200)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        fdm.cg_dev(d_out.data_ptr(), d_in.data_ptr(), True, preconditioner=P, tol=1e-300, maxiter=nit)
-        torch.cuda.synchronize()
-        t_iter = (time.perf_counter() - t0) / nit
+
+        def cg_iter_time(Pq):
+            # fixed iteration count, device-resident vectors, CUDA events on the library stream (one launch per solve on the register
+            # path).  Preconditioned: short solves, the recurrence breaks down once the residual reaches exact zero.
+            nit, reps = (2000, 1) if Pq is None else (15, 20)
+            fdm.cg_dev(d_out.data_ptr(), d_in.data_ptr(), True, preconditioner=Pq, tol=1e-300, maxiter=min(nit, 200))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                fdm.cg_dev(d_out.data_ptr(), d_in.data_ptr(), True, preconditioner=Pq, tol=1e-300, maxiter=nit)
+            e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1) * 1e-3 / (nit * reps), nit * reps
+        t_iter, nit = cg_iter_time(None)
+        t_iter_kpm, _ = cg_iter_time(P_kpm)
         peak, peak_src = measured_peak()
         state = {}
         try:
@@ -393,7 +531,7 @@ def run_native(args):
         uniform = (m.Nssh == 0) and path in (2, 3)
         Bk = (40 * m.N * m.Ltau + 16 * m.Nh) if uniform else B
         names = {0: "k_fdm_fused<2>", 2: "k_fdm_fused_v2<2>", 3: "k_fdm_v3<2,0,1> (register path, native order)"}
-        resident = (path == 3) and not precond
+        resident = (path == 3) and fdm.stats["cg_resident"] > 0
         step_s = ms_dev * 1e-3 / args.steps
         matvec = {"kernel": names.get(path, "global passes") + " (fused M^T M v)", "us_per_launch_cold_l2": t_cold * 1e6,
                   "us_per_launch_hot_l2": t_hot * 1e6, "achieved_cold_l2": Bk / t_cold / 1e9, "frac_cold_l2": Bk / t_cold / 1e9 / peak,
@@ -416,113 +554,9 @@ def run_native(args):
         roofline.update({"generic_formula_bytes_per_unit": B,
                          "bytes_note": "tau-uniform hoppings: (cosh, sinh) read once per kernel" if uniform else "generic (40 N + 16 Nh) Ltau",
                          "cg_us_per_iteration": t_iter * 1e6, "cg_iterations_per_s": 1.0 / t_iter,
-                         "share_of_step": iters_per_traj * t_iter / step_s, "matvec_kernel": matvec, "tuning": tuning})
-
-    barrier()
-    # ---- tau-slab strong scaling of the CG solve (N > 1): the same M^T M system partitioned over the ranks with
-    #      NCCL halo exchange + all-reduced dot products, against the single-GPU solve timed on every rank first
-    def finish(tau_slab, cpu=None):
-        line = {"metric": "efa_hmc_trajectories_per_s", "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(m, precond, "gpu"),
-                "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": nx * 8, "d2h_bytes_per_step": nx * 8 + 64},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-                "cg_iters_per_trajectory": iters_per_traj, "matvecs_per_trajectory": matvecs_per_traj,
-                "acceptance": accepted / args.steps, "per_rank": per_rank, "tau_slab": tau_slab}
-        emit(line)
-
-    tau_slab = None
-    if world > 1:
-        # the strong-scaling section is an extra: a watchdog makes sure the headline line is printed even if it stalls
-        import threading
-        stage = ["start"]
-
-        def bail():
-            if rank == 0:
-                finish({"error": "tau-slab section exceeded its time limit at stage '%s'" % stage[0]})
-            os._exit(0)
-        dog = threading.Timer(240.0, bail)
-        dog.daemon = True
-        dog.start()
-        try:
-            n = m.N * m.Ltau
-            d_b = torch.randn(n, 2, dtype=torch.float64, device=dev)
-            d_x = torch.zeros_like(d_b)
-            nit = 400
-
-            def timed_cg():
-                """us per iteration (max over ranks), or None if any rank failed -- every rank always takes part in the collectives"""
-                bad = 0.0
-                try:
-                    fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=40)
-                except Exception as e:                            # noqa: BLE001
-                    bad = 1.0
-                    sys.stderr.write("rank %d: tau-slab CG failed at stage %s: %s\n" % (rank, stage[0], e))
-                barrier()
-                t0 = time.perf_counter()
-                if not bad:
-                    try:
-                        fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=nit)
-                        torch.cuda.synchronize()
-                    except Exception as e:                        # noqa: BLE001
-                        bad = 1.0
-                        sys.stderr.write("rank %d: tau-slab CG failed at stage %s: %s\n" % (rank, stage[0], e))
-                dt = time.perf_counter() - t0
-                tt = torch.tensor([dt, bad], dtype=torch.float64, device=dev)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                return None if tt[1].item() > 0 else float(tt[0].item()) / nit * 1e6
-
-            stage[0] = "one GPU"
-            us1 = timed_cg()
-            ids = [api.FermionDetMatrix.nccl_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, src=0)
-            fdm.init_slab(rank, world, ids[0])
-            stage[0] = "NCCL loop"
-            os.environ["SQ_NO_RESIDENT_CG"] = "1"                 # (a) host-launched NCCL loop
-            us_nccl = timed_cg()
-            del os.environ["SQ_NO_RESIDENT_CG"]
-            stage[0] = "mailboxes"
-            handles = [None] * world                              # (b) resident kernels + peer-mapped mailboxes (CUDA IPC over NVLink)
-            dist.all_gather_object(handles, fdm.mailbox_handle())
-            fdm.mailbox_open(handles)
-            stage[0] = "resident"
-            usN = timed_cg() if us_nccl is not None else None
-            best = min([u for u in (usN, us_nccl) if u is not None], default=None)
-            tau_slab = {"what": "unpreconditioned CG iterations on M^T M, cfg4, tau-slab partitioned (strong scaling)",
-                        "cg_us_per_iter_1gpu": us1, "cg_us_per_iter": usN, "cg_us_per_iter_nccl_loop": us_nccl, "n_gpus": world,
-                        "cg_iters_per_s": 1e6 / best if best else None, "speedup_vs_1gpu": us1 / best if best and us1 else None,
-                        "comm": "resident kernel per rank; grid-wide sums and boundary slices as device-initiated stores into peer-mapped "
-                                "mailboxes (CUDA IPC over NVLink); cg_us_per_iter_nccl_loop = host-launched NCCL send/recv + all-reduces"}
-            # (c) whole trajectories of ONE chain over all GPUs: full state on every rank, CG solves partitioned ("sharded solve")
-            stage[0] = "sharded chain"
-            if usN is not None:
-                try:
-                    fdm.set_sharded_solve(True)
-                    xs = [x_w if rank == 0 else None]
-                    dist.broadcast_object_list(xs, src=0)
-                    elph.x = xs[0]
-                    elph.update_fdm()
-                    hs = api.EFAPFFHMCUpdater(elph, pff, Nt=NT, seed=4242)
-                    trajectory(hs)                                # untimed: tunes the kernels for the slab range
-                    torch.cuda.synchronize()
-                    barrier()
-                    t0 = time.perf_counter()
-                    for _ in range(args.steps):
-                        trajectory(hs)
-                    torch.cuda.synchronize()
-                    tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                    rate = args.steps / float(tt.item())
-                    tau_slab["chain_over_all_gpus"] = {"trajectories_per_s": rate, "trajectories_per_s_one_gpu": value / world,
-                                                       "speedup_vs_1gpu": rate / (value / world),
-                                                       "note": "cfg4 is half a wave of work per GPU at N = 2: one GPU per chain is the faster "
-                                                               "choice at this size; Ltau = 800 gives 2.0x on 2 GPUs (profiles/README.md)"}
-                except Exception as e:                            # noqa: BLE001
-                    tau_slab["chain_over_all_gpus"] = {"error": str(e)}
-        except Exception as e:                                # noqa: BLE001  (a rank that fails here must still print / exit cleanly)
-            sys.stderr.write("rank %d: tau-slab section failed at stage %s: %s\n" % (rank, stage[0], e))
-            tau_slab = {"error": "stage '%s': %s" % (stage[0], e)}
-        dog.cancel()
+                         "cg_us_per_iteration_kpm": t_iter_kpm * 1e6,
+                         "share_of_step": (iters_per_traj * (t_iter_kpm if use_kpm else t_iter)) / step_s, "matvec_kernel": matvec, "tuning": tuning,
+                         "solver_stats": fdm.stats})
 
     if rank != 0:
         if dist is not None:
@@ -531,10 +565,18 @@ def run_native(args):
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        v, cores, sample, detail = cpu_sample(m, x_w, precond, False, args.cpu_budget, iters_per_traj)
-        cpu = {"value": v, "unit": "trajectories/s", "cores": cores, "kind": "port", "sample": sample, "detail": detail}
+        arm = CpuArm(m, x0, True, False)                     # the stock (KPM) configuration on ONE core: the reference is single-threaded
+        v = arm.sample()
+        cpu = {"value": v, "unit": "trajectories/s", "cores": arm.threads, "kind": "port", "sample": arm.describe(1), "detail": arm.last}
 
-    finish(tau_slab, cpu)
+    line = {"metric": "efa_hmc_trajectories_per_s", "value": value, "unit": "trajectories/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(m, plabel, where, state_label, cfg_extra),
+            "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": nx * 8, "d2h_bytes_per_step": nx * 8 + 64},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "cg_iters_per_trajectory": iters_per_traj, "matvecs_per_trajectory": matvecs_per_traj,
+            "acceptance": accepted / args.steps, "independent_chains": chains, "tau_slab": tau_slab}
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -547,9 +589,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="cfg4")
-    ap.add_argument("--precond", default=os.environ.get("SQ_BENCH_PRECOND", "off"), choices=["on", "off"])
+    ap.add_argument("--precond", default=os.environ.get("SQ_BENCH_PRECOND", "auto"), choices=["auto", "on", "off"],
+                    help="native arm: auto = time one trajectory with preconditioner = I and one with a KPMPreconditioner, keep the faster; "
+                         "reference arm: KPM (the stock configuration) unless 'off'")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

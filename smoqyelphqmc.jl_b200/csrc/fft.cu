@@ -12,6 +12,7 @@
 // (Ltau = beta/dtau is 20*beta for the shipped dtau = 0.05, i.e. 2^a 5^b).
 #include "sq_internal.h"
 
+#include <algorithm>
 #include <cmath>
 
 void fft_radices(i64 n, std::vector<int> &rad) {
@@ -37,7 +38,11 @@ void fft_make_twiddles(i64 n, std::vector<double2> &tw) {
 struct FftPlan {
     int L, nrad;
     int rad[24];
+    int tws[24];                // twiddle stride of pass s: L / (Ns R)
+    int sbshift;                // log2(SB): columns per CTA are a power of two, so w / SB and w % SB are a shift and a mask
 };
+// j % Ns without an integer division (j < 2^20): the float quotient is exact after the + 0.5 guard
+__device__ __forceinline__ int fast_mod(int j, int Ns, float invNs) { return j - Ns * (int)(((float)j + 0.5f) * invNs); }
 
 template <int R>
 __device__ __forceinline__ void butterfly(double2 (&x)[R], const double2 *tw, int L, bool inverse) {
@@ -74,17 +79,18 @@ __device__ __forceinline__ void butterfly(double2 (&x)[R], const double2 *tw, in
 
 template <int R>
 __device__ __forceinline__ void stockham_pass(const double2 *__restrict__ src, double2 *__restrict__ dst, int L, int Ns, int SB,
-                                              const double2 *tw, bool inverse) {
+                                              const double2 *tw, bool inverse, int sbshift, int twstride) {
     const int nb = L / R;                       // butterflies per column
+    const float invNs = 1.0f / (float)Ns;
     for (int w = threadIdx.x; w < nb * SB; w += blockDim.x) {
-        int j = w / SB, col = w - j * SB;
-        int k = j % Ns;
+        int j = w >> sbshift, col = w & (SB - 1);
+        int k = fast_mod(j, Ns, invNs);
         double2 x[R];
 #pragma unroll
         for (int q = 0; q < R; q++) {
             double2 v = src[(j + q * nb) * SB + col];
             if (q > 0 && Ns > 1) {
-                double2 t = tw[(size_t)(q * k) * (L / (Ns * R))];
+                double2 t = tw[q * k * twstride];
                 if (inverse) t.y = -t.y;
                 v = cmul(v, t);
             }
@@ -146,7 +152,7 @@ __global__ void k_tau_fft(const FftPlan plan, double2 *__restrict__ out, const d
             v[q] = make_double2(0, 0);
             lq[q] = -1;
             if (w < tot) {
-                int l = w / SB, col = w - l * SB;
+                int l = w >> plan.sbshift, col = w & (SB - 1);
                 lq[q] = l;
                 if (col < ncol) v[q] = in[(size_t)l * N + i0 + col];
             }
@@ -169,11 +175,11 @@ __global__ void k_tau_fft(const FftPlan plan, double2 *__restrict__ out, const d
     for (int s = 0; s < plan.nrad; s++) {
         int R = plan.rad[s];
         switch (R) {
-            case 2: stockham_pass<2>(src, dst, L, Ns, SB, tw, inverse); break;
-            case 3: stockham_pass<3>(src, dst, L, Ns, SB, tw, inverse); break;
-            case 4: stockham_pass<4>(src, dst, L, Ns, SB, tw, inverse); break;
-            case 5: stockham_pass<5>(src, dst, L, Ns, SB, tw, inverse); break;
-            case 7: stockham_pass<7>(src, dst, L, Ns, SB, tw, inverse); break;
+            case 2: stockham_pass<2>(src, dst, L, Ns, SB, tw, inverse, plan.sbshift, plan.tws[s]); break;
+            case 3: stockham_pass<3>(src, dst, L, Ns, SB, tw, inverse, plan.sbshift, plan.tws[s]); break;
+            case 4: stockham_pass<4>(src, dst, L, Ns, SB, tw, inverse, plan.sbshift, plan.tws[s]); break;
+            case 5: stockham_pass<5>(src, dst, L, Ns, SB, tw, inverse, plan.sbshift, plan.tws[s]); break;
+            case 7: stockham_pass<7>(src, dst, L, Ns, SB, tw, inverse, plan.sbshift, plan.tws[s]); break;
             default: stockham_pass_generic(src, dst, L, Ns, R, SB, tw, inverse); break;
         }
         __syncthreads();
@@ -182,7 +188,7 @@ __global__ void k_tau_fft(const FftPlan plan, double2 *__restrict__ out, const d
     }
     double acc_re = 0, acc_im = 0;
     for (int w = threadIdx.x; w < L * SB; w += blockDim.x) {
-        int l = w / SB, col = w - l * SB;
+        int l = w >> plan.sbshift, col = w & (SB - 1);
         if (col >= ncol) continue;
         double2 v = src[w];
         if (inverse) {
@@ -227,10 +233,17 @@ int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, 
     }
     int grid = (N + SB - 1) / SB;
     if (dot_with && grid > SQ_MAXPART) throw SqError("lattice too large for the FFT partial-sum buffer");
-    int threads = 256;
-    if (L * SB >= 2048) threads = 512;
     if (const char *e = getenv("SQ_FFT_SB")) { int v = atoi(e); if (v >= 1 && (size_t)(2 * v + 1) * L * sizeof(double2) <= smem_limit) { SB = v; smem = (size_t)(2 * SB + 1) * L * sizeof(double2); grid = (N + SB - 1) / SB; } }
+    // one butterfly per thread in the radix-4 passes where possible (L SB / 4 butterflies), 128 ... 512 threads
+    int threads = std::min(512, std::max(128, ((L * SB / 4 + 31) / 32) * 32));
     if (const char *e = getenv("SQ_FFT_T")) threads = atoi(e);
+    plan.sbshift = 0;
+    while ((1 << plan.sbshift) < SB) plan.sbshift++;
+    if ((1 << plan.sbshift) != SB) throw SqError("FFT tile width must be a power of two");
+    {
+        int Ns = 1;
+        for (int s = 0; s < plan.nrad; s++) { plan.tws[s] = L / (Ns * plan.rad[s]); Ns *= plan.rad[s]; }
+    }
     k_tau_fft<<<grid, threads, smem, stream>>>(plan, out, in, N, SB, inverse ? 1 : 0, twist ? 1 : 0, tw, theta, scale1, dot_with,
                                                dot_part, skip);
     SQ_LAUNCH_CHECK();

@@ -19,6 +19,8 @@
 int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, int N, double2 *out, const double2 *in, bool inverse,
                    bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
                    double *dot_part, const CgState *skip, size_t smem_limit);
+bool kpm_reg_ok(const sq_kpm *k);
+void kpm_cheb_reg_launch(sq_kpm *k, double2 *z, int nrhs, size_t rhs_stride, const CgState *skip);
 
 struct BbarParams {
     int N, Nh, C, sym;
@@ -624,7 +626,10 @@ int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *
     double2 *zt = k->ztmp.p;
     tau_fft_launch(f->stream, k->radices, (int)f->L, (int)f->N, zt, in, false, true, k->tw.p, k->theta.p, k->d_scale1.p, nullptr, nullptr,
                    skip, f->smem_optin);
-    if (k->nsched > 0 && kpm_fast_ok(k)) {
+    if (k->nsched > 0 && kpm_reg_ok(k)) {                                // register engine (kpm_reg.cu): lattices of the register path
+        kpm_cheb_reg_launch(k, zt, 1, 0, skip);
+    } else if (k->nsched > 0 && kpm_fast_ok(k)) {
+        f->stats[SQ_STAT_KPM_SMEM]++;
         BbarFast Q;
         Q.N = (int)f->N; Q.C = (int)f->C; Q.nunc0 = f->nunc0;
         for (int c = 0; c < 8; c++) { Q.clo[c] = c < f->C ? f->clo[c] : 0; Q.chi[c] = c < f->C ? f->chi[c] : 0; }
@@ -649,6 +654,7 @@ int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *
         SQ_LAUNCH_CHECK();
         f->launches++;
     } else if (k->nsched > 0) {
+        f->stats[SQ_STAT_KPM_SMEM]++;
         BbarParams P = bbar_params(k);
         double avg = 0.5 * (k->bounds[1] + k->bounds[0]), mag = 0.5 * (k->bounds[1] - k->bounds[0]);
         k_kpm_cheb<<<k->nsched, kpm_threads(k), 4 * f->N * sizeof(double2), f->stream>>>(P, zt, k->d_freq_sched.p, k->d_order.p,

@@ -1,0 +1,374 @@
+// kpm_reg.cu -- K4 on the register engine: the Chebyshev recurrences of the KPM preconditioner for the lattices of the
+// register path (rectangular Lx x Ly with the canonical 4 colours, L x L honeycomb with its 3 bond types; colour-uniform,
+// tau-independent hoppings -- every Holstein-type model on these lattices).
+//
+// Replaces the `kpm_lmul!` calls of src/KPMPreconditioner.jl:394 (Sym, complex vectors) for those lattices.  What bounds the
+// preconditioner is not throughput but the LATENCY of its longest recurrence: at cfg4 the lowest Matsubara frequency needs
+// order ~ 160 sequential applications of B-bar to one N-vector while all frequencies together are only ~ 2500 applications
+// (1.6 us of FP64 issue on the whole chip).  The shared-memory kernel (kpm.cu, k_kpm_cheb_fast) spends ~ 0.9 us per
+// application: one site pair per thread, 2C - 2 CTA-wide barriers and shared-memory round trips.  Here one chain (frequency,
+// real or imaginary part -- B-bar is real, so the two parts are independent recurrences) is ONE CTA of W warps that holds its
+// N-vector in registers for the whole recurrence:
+//
+//   * square lattice: lane = (group of 4 consecutive x, block of 2 rows), warp w owns 2 (32 / LXL) consecutive rows; x-even and
+//     y-even bonds are lane-local, x-odd bonds one shuffle per two sites, y-odd bonds shuffle the lane's two rows -- except across
+//     the W warps of the chain, where the boundary rows cross through a small double-buffered shared-memory window (one
+//     CTA barrier each, 2 per application instead of 6 with no other shared-memory traffic);
+//   * honeycomb: lane = R1 x R2 block of cells, the intra-cell bond is lane-local, the two inter-cell bond types shuffle one
+//     boundary column / row (rows across warps through the same window);
+//   * scaled rotations a' = a + tanh b with prod_c cosh_c^2, the Chebyshev rescaling 2 / mag and the tau-mean diagonal folded
+//     into ONE per-site factor kept in registers: a B-bar application is 2C + 1 dependent-free DFMA per site, the recurrence
+//     T_{q+1} = 2 B' T_q - T_{q-1} and the accumulation 3 more;
+//   * W is chosen so that a lane holds 4 - 12 sites: T_{q-1}, T_q, the working copy, the accumulator and the diagonal fit in
+//     registers, and the four FP64 pipes of the SM all work on the one chain that matters.
+// Chains are scheduled longest first, one CTA per SM (CTA b runs chains b, b + G, ...: the long chains get an SM to themselves).
+// The same kernel serves a batch of right-hand sides (multi-RHS solves: chain = (rhs, frequency, part)).
+#include "sq_internal.h"
+
+#include <algorithm>
+
+struct ChebRegParams {
+    int N, L;
+    int nchain;                     // nsched * 2 * nrhs
+    int nsched, nrhs;
+    size_t rhs_stride;              // double2 elements between the frequency arrays of consecutive right-hand sides
+    double2 *z;                     // [rhs][n][i]
+    const int *sched, *order, *coef_off;
+    const double2 *coefs;
+    const double2 *csbar;           // (mean cosh, mean sinh) per bond; colour c = csbar[clo[c]]
+    int clo[4];
+    const double *Dbar;             // [i]
+    double avg, imag_;              // (emax + emin) / 2, 2 / (emax - emin)
+    const CgState *skip;
+};
+
+// ---- square lattice -------------------------------------------------------------------------------------------------
+template <int LXL_, int W_>
+struct RegSquare {
+    static constexpr int LXL = LXL_, W = W_, RY = 2, YH = 32 / LXL, LX = 4 * LXL, LY = RY * YH * W, N = LX * LY, NV = 4 * RY, NCOL = 4;
+    static constexpr int XCH = 2 * W * 2 * LX;          // doubles of the exchange window: [buffer][warp][bottom / top row][x]
+    int xl, yh, w, lane_r, lane_l, lane_u, lane_d;
+    double t[4];
+
+    __device__ __forceinline__ void init(const ChebRegParams &P, double &g) {
+        const int lane = threadIdx.x & 31;
+        w = threadIdx.x >> 5;
+        xl = lane % LXL;
+        yh = lane / LXL;
+        lane_r = lane - xl + (xl + 1) % LXL;
+        lane_l = lane - xl + (xl + LXL - 1) % LXL;
+        lane_u = xl + LXL * ((yh + 1) % YH);
+        lane_d = xl + LXL * ((yh + YH - 1) % YH);
+        g = 1.0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double2 q = __ldg(P.csbar + P.clo[c]);
+            t[c] = q.y / q.x;
+            g *= q.x * q.x;
+        }
+    }
+    // site of value k = 4 r + j
+    __device__ __forceinline__ int site(int k) const { return 4 * xl + (k & 3) + LX * ((w * YH + yh) * RY + (k >> 2)); }
+
+    template <int CL>
+    __device__ __forceinline__ void step(double (&v)[NV], double *xb, double s_outer = 0.0) const {
+        const double s = (CL == NCOL - 1) ? s_outer : t[CL];
+        if (CL == 0) {                                            // x-even: (0,1), (2,3)
+#pragma unroll
+            for (int r = 0; r < RY; r++) {
+                const double a = v[4 * r], b = v[4 * r + 1], c = v[4 * r + 2], d = v[4 * r + 3];
+                v[4 * r] = fma(s, b, a); v[4 * r + 1] = fma(s, a, b); v[4 * r + 2] = fma(s, d, c); v[4 * r + 3] = fma(s, c, d);
+            }
+        } else if (CL == 1) {                                     // x-odd: (1,2) inside, (3 | 0 of the right neighbour)
+#pragma unroll
+            for (int r = 0; r < RY; r++) {
+                const double fromR = __shfl_sync(0xffffffffu, v[4 * r], lane_r);
+                const double fromL = __shfl_sync(0xffffffffu, v[4 * r + 3], lane_l);
+                const double b = v[4 * r + 1], c = v[4 * r + 2];
+                v[4 * r + 1] = fma(s, c, b); v[4 * r + 2] = fma(s, b, c);
+                v[4 * r + 3] = fma(s, fromR, v[4 * r + 3]);
+                v[4 * r] = fma(s, fromL, v[4 * r]);
+            }
+        } else if (CL == 2) {                                     // y-even: rows (0, 1) of the lane
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const double a = v[j], b = v[4 + j];
+                v[j] = fma(s, b, a); v[4 + j] = fma(s, a, b);
+            }
+        } else {                                                  // y-odd: row 1 with row 0 of the block above
+            double up[4], dn[4];
+            if (W > 1) {                                          // rows that cross a warp boundary go through shared memory
+                if (yh == 0) *reinterpret_cast<double4 *>(xb + (w * 2 + 0) * LX + 4 * xl) = make_double4(v[0], v[1], v[2], v[3]);
+                if (yh == YH - 1) *reinterpret_cast<double4 *>(xb + (w * 2 + 1) * LX + 4 * xl) = make_double4(v[4], v[5], v[6], v[7]);
+                __syncthreads();
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                up[j] = __shfl_sync(0xffffffffu, v[j], lane_u);
+                dn[j] = __shfl_sync(0xffffffffu, v[4 + j], lane_d);
+            }
+            if (W > 1) {
+                if (yh == YH - 1) {
+                    const double4 q = *reinterpret_cast<const double4 *>(xb + (((w + 1) % W) * 2 + 0) * LX + 4 * xl);
+                    up[0] = q.x; up[1] = q.y; up[2] = q.z; up[3] = q.w;
+                }
+                if (yh == 0) {
+                    const double4 q = *reinterpret_cast<const double4 *>(xb + (((w + W - 1) % W) * 2 + 1) * LX + 4 * xl);
+                    dn[0] = q.x; dn[1] = q.y; dn[2] = q.z; dn[3] = q.w;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                v[4 + j] = fma(s, up[j], v[4 + j]);
+                v[j] = fma(s, dn[j], v[j]);
+            }
+        }
+    }
+    // One application in the ROTATED frame u = K t, K = (1 + t3 sigma3) the outer (y-odd) colour step: B-bar = K A K with
+    // A = colours 2, 1, 0, diagonal, 0, 1, 2, so K B-bar K^-1 = K^2 A and K^2 = (1 + t3^2)(1 + t3' sigma3), t3' = 2 t3 / (1 + t3^2):
+    // ONE outer step with the doubled angle per application instead of two -- the outer step is the expensive one (it crosses lanes
+    // and warps).  xb: this application's half of the exchange window.
+    __device__ __forceinline__ void apply(double (&v)[NV], const double (&dg)[NV], double *xb) const {
+        step<2>(v, xb); step<1>(v, xb); step<0>(v, xb);
+#pragma unroll
+        for (int k = 0; k < NV; k++) v[k] *= dg[k];
+        step<0>(v, xb); step<1>(v, xb); step<2>(v, xb);
+        step<3>(v, xb, 2.0 * t[3] / (1.0 + t[3] * t[3]));
+    }
+    __device__ __forceinline__ void outer(double (&v)[NV], double *xb, double s) const { step<3>(v, xb, s); }
+    static constexpr int XHALF = W * 2 * LX;
+};
+
+// ---- honeycomb --------------------------------------------------------------------------------------------------------
+// site = orb + 2 (c1 + L1 c2); colour 0: A(c1,c2)-B(c1,c2), colour 1: A(c1,c2)-B(c1-1,c2), colour 2: A(c1,c2)-B(c1,c2-1)
+// lane = g1 + G1 g2 of warp w holds the cells c1 = R1 g1 + a1, c2 = R2 (G2 w + g2) + a2; value k = 2 (a2 R1 + a1) + orb
+template <int G1_, int R1_, int R2_, int W_>
+struct RegHoney {
+    static constexpr int G1 = G1_, R1 = R1_, R2 = R2_, W = W_, G2 = 32 / G1, L1 = G1 * R1, L2 = G2 * R2 * W;
+    static constexpr int NP = R1 * R2, NV = 2 * NP, N = 2 * L1 * L2, NCOL = 3;
+    static constexpr int XCH = 2 * W * 2 * L1;
+    int g1, g2, w, lane_r, lane_l, lane_u, lane_d;
+    double t[3];
+
+    __device__ __forceinline__ void init(const ChebRegParams &P, double &g) {
+        const int lane = threadIdx.x & 31;
+        w = threadIdx.x >> 5;
+        g1 = lane % G1;
+        g2 = lane / G1;
+        lane_r = (g1 + 1) % G1 + G1 * g2;
+        lane_l = (g1 + G1 - 1) % G1 + G1 * g2;
+        lane_u = g1 + G1 * ((g2 + 1) % G2);
+        lane_d = g1 + G1 * ((g2 + G2 - 1) % G2);
+        g = 1.0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double2 q = __ldg(P.csbar + P.clo[c]);
+            t[c] = q.y / q.x;
+            g *= q.x * q.x;
+        }
+    }
+    __device__ __forceinline__ int site(int k) const {
+        const int u = k >> 1, a1 = u % R1, a2 = u / R1;
+        return (k & 1) + 2 * ((R1 * g1 + a1) + L1 * (R2 * (G2 * w + g2) + a2));
+    }
+    static __device__ __forceinline__ void rot(double &a, double &b, double s) {
+        const double na = fma(s, b, a), nb = fma(s, a, b);
+        a = na;
+        b = nb;
+    }
+    template <int CL>
+    __device__ __forceinline__ void step(double (&v)[NV], double *xb, double s_outer = 0.0) const {
+        const double s = (CL == NCOL - 1) ? s_outer : t[CL];
+        if (CL == 0) {
+#pragma unroll
+            for (int u = 0; u < NP; u++) rot(v[2 * u], v[2 * u + 1], s);
+        } else if (CL == 1) {                             // A(a1, a2) - B(a1 - 1, a2): first column with the left lane's last column
+#pragma unroll
+            for (int a2 = 0; a2 < R2; a2++) {
+                const int u0 = a2 * R1, u1 = a2 * R1 + R1 - 1;
+                const double fromL = __shfl_sync(0xffffffffu, v[2 * u1 + 1], lane_l);     // B of the left lane's last column
+                const double fromR = __shfl_sync(0xffffffffu, v[2 * u0], lane_r);         // A of the right lane's first column
+#pragma unroll
+                for (int a1 = R1 - 1; a1 >= 1; a1--) rot(v[2 * (u0 + a1)], v[2 * (u0 + a1 - 1) + 1], s);
+                v[2 * u0] = fma(s, fromL, v[2 * u0]);
+                v[2 * u1 + 1] = fma(s, fromR, v[2 * u1 + 1]);
+            }
+        } else {                                          // A(a1, a2) - B(a1, a2 - 1): first row with the row below
+            double fromD[R1], fromU[R1];
+            if (W > 1) {
+                if (g2 == 0) {
+#pragma unroll
+                    for (int a1 = 0; a1 < R1; a1++) xb[(w * 2 + 0) * L1 + R1 * g1 + a1] = v[2 * a1];                              // A of the first row
+                }
+                if (g2 == G2 - 1) {
+#pragma unroll
+                    for (int a1 = 0; a1 < R1; a1++) xb[(w * 2 + 1) * L1 + R1 * g1 + a1] = v[2 * ((R2 - 1) * R1 + a1) + 1];        // B of the last row
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int a1 = 0; a1 < R1; a1++) {
+                fromD[a1] = __shfl_sync(0xffffffffu, v[2 * ((R2 - 1) * R1 + a1) + 1], lane_d);
+                fromU[a1] = __shfl_sync(0xffffffffu, v[2 * a1], lane_u);
+            }
+            if (W > 1) {
+                if (g2 == 0) {
+#pragma unroll
+                    for (int a1 = 0; a1 < R1; a1++) fromD[a1] = xb[(((w + W - 1) % W) * 2 + 1) * L1 + R1 * g1 + a1];
+                }
+                if (g2 == G2 - 1) {
+#pragma unroll
+                    for (int a1 = 0; a1 < R1; a1++) fromU[a1] = xb[(((w + 1) % W) * 2 + 0) * L1 + R1 * g1 + a1];
+                }
+            }
+#pragma unroll
+            for (int a1 = 0; a1 < R1; a1++) {
+#pragma unroll
+                for (int a2 = R2 - 1; a2 >= 1; a2--) rot(v[2 * (a2 * R1 + a1)], v[2 * ((a2 - 1) * R1 + a1) + 1], s);
+                v[2 * a1] = fma(s, fromD[a1], v[2 * a1]);
+                v[2 * ((R2 - 1) * R1 + a1) + 1] = fma(s, fromU[a1], v[2 * ((R2 - 1) * R1 + a1) + 1]);
+            }
+        }
+    }
+    // rotated frame, as RegSquare::apply: colours 1, 0, diagonal, 0, 1, then the outer colour 2 once with the doubled angle
+    __device__ __forceinline__ void apply(double (&v)[NV], const double (&dg)[NV], double *xb) const {
+        step<1>(v, xb); step<0>(v, xb);
+#pragma unroll
+        for (int k = 0; k < NV; k++) v[k] *= dg[k];
+        step<0>(v, xb); step<1>(v, xb);
+        step<2>(v, xb, 2.0 * t[2] / (1.0 + t[2] * t[2]));
+    }
+    __device__ __forceinline__ void outer(double (&v)[NV], double *xb, double s) const { step<2>(v, xb, s); }
+    static constexpr int XHALF = W * 2 * L1;
+};
+
+// One CTA = one chain at a time (W warps).  The recurrence runs in the rotated frame u_q = K T_q (see apply()):
+//     y'' = (2 / mag) K B-bar K^-1 u_q  comes out of apply() through the folded diagonal,
+//     u_1 = (y'' - kappa u_0) / 2,   u_{q+1} = (y'' - kappa u_q) - u_{q-1},   kappa = 2 avg / mag,
+// and the result is rotated back once: sum_q c_q T_q v = K^-1 sum_q c_q u_q,  K^-1 = (1 - t sigma) / (1 - t^2).
+template <class G>
+__global__ void __launch_bounds__(32 * G::W, 1)
+k_kpm_cheb_reg(const __grid_constant__ ChebRegParams P) {
+    constexpr int NV = G::NV;
+    __shared__ __align__(32) double xch[G::XCH > 0 ? G::XCH : 1];
+    if (P.skip && P.skip->done) return;
+    G E;
+    double g;
+    E.init(P, g);
+    const double to = E.t[G::NCOL - 1];                         // tanh of the outer colour
+    const double kappa = 2.0 * P.avg * P.imag_, dscale = 2.0 * P.imag_ * g * (1.0 + to * to), back = 1.0 / (1.0 - to * to);
+    double dg[NV];
+    int off[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        off[k] = E.site(k);
+        dg[k] = dscale * __ldg(P.Dbar + off[k]);
+    }
+    int flip = 0;                                               // which half of the exchange window the next outer step uses
+#define XB() (xch + ((flip ^= 1) ? G::XHALF : 0))
+#pragma unroll 1
+    for (int ch = blockIdx.x; ch < P.nchain; ch += gridDim.x) {
+        // chains are ordered longest first: (schedule index, part, rhs) with the schedule index slowest
+        const int si = ch / (2 * P.nrhs), rem = ch - si * 2 * P.nrhs, part = rem & 1, rhs = rem >> 1;
+        const int n = __ldg(P.sched + si);
+        const int np = (n + 1 > (P.L + 1) / 2) ? P.L - 1 - n : n;                     // KPMPreconditioner.jl:387
+        const int ord = __ldg(P.order + np);
+        const double2 *c = P.coefs + __ldg(P.coef_off + np);                           // real coefficients (Sym): .x
+        double *zn = reinterpret_cast<double *>(P.z + (size_t)rhs * P.rhs_stride + (size_t)n * P.N) + part;
+        double ta[NV], tb[NV], y[NV], acc[NV];
+#pragma unroll
+        for (int k = 0; k < NV; k++) ta[k] = zn[2 * off[k]];
+        const double c0 = __ldg(&c[0].x), c1 = __ldg(&c[1].x);
+        E.outer(ta, XB(), to);                                  // u_0 = K T_0
+#pragma unroll
+        for (int k = 0; k < NV; k++) y[k] = ta[k];
+        E.apply(y, dg, XB());
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            tb[k] = 0.5 * fma(-kappa, ta[k], y[k]);
+            acc[k] = fma(c1, tb[k], c0 * ta[k]);
+        }
+        // two orders per trip, so that (u_{q-1}, u_q) swap roles without register moves
+        int q = 2;
+#pragma unroll 1
+        for (; q + 1 < ord; q += 2) {
+            const double ca = __ldg(&c[q].x), cb = __ldg(&c[q + 1].x);
+#pragma unroll
+            for (int k = 0; k < NV; k++) y[k] = tb[k];
+            E.apply(y, dg, XB());
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                ta[k] = fma(-kappa, tb[k], y[k]) - ta[k];
+                acc[k] = fma(ca, ta[k], acc[k]);
+                y[k] = ta[k];
+            }
+            E.apply(y, dg, XB());
+#pragma unroll
+            for (int k = 0; k < NV; k++) {
+                tb[k] = fma(-kappa, ta[k], y[k]) - tb[k];
+                acc[k] = fma(cb, tb[k], acc[k]);
+            }
+        }
+        if (q < ord) {
+            const double ca = __ldg(&c[q].x);
+#pragma unroll
+            for (int k = 0; k < NV; k++) y[k] = tb[k];
+            E.apply(y, dg, XB());
+#pragma unroll
+            for (int k = 0; k < NV; k++) acc[k] = fma(ca, fma(-kappa, tb[k], y[k]) - ta[k], acc[k]);
+        }
+        E.outer(acc, XB(), -to);                                // back to the original frame
+#pragma unroll
+        for (int k = 0; k < NV; k++) zn[2 * off[k]] = back * acc[k];
+    }
+#undef XB
+}
+
+typedef void (*cheb_reg_t)(const ChebRegParams);
+struct ChebRegPick { cheb_reg_t k; int threads; };
+
+static ChebRegPick pick_cheb_reg(const sq_fdm *f) {
+    if (!f->v3_ok || !f->sym) return {nullptr, 0};
+    if (f->v3_kind == 0) {                                     // square: v3_lxl = Lx / 4, v3_ry = rows per lane of the matvec engine
+        const int lxl = f->v3_lxl, w = f->v3_ry / 2;           // Ly = v3_ry (32 / lxl) = 2 (32 / lxl) W
+        if (lxl == 8 && w == 2) return {k_kpm_cheb_reg<RegSquare<8, 2>>, 64};       // 32 x 16
+        if (lxl == 8 && w == 4) return {k_kpm_cheb_reg<RegSquare<8, 4>>, 128};      // 32 x 32
+        if (lxl == 8 && w == 8) return {k_kpm_cheb_reg<RegSquare<8, 8>>, 256};      // 32 x 64
+        if (lxl == 4 && w == 1) return {k_kpm_cheb_reg<RegSquare<4, 1>>, 32};       // 16 x 16
+        if (lxl == 4 && w == 2) return {k_kpm_cheb_reg<RegSquare<4, 2>>, 64};       // 16 x 32
+        if (lxl == 4 && w == 4) return {k_kpm_cheb_reg<RegSquare<4, 4>>, 128};      // 16 x 64
+        return {nullptr, 0};
+    }
+    if (f->v3_lxl == 24 && f->v3_ry == 24) return {k_kpm_cheb_reg<RegHoney<8, 3, 2, 3>>, 96};
+    if (f->v3_lxl == 16 && f->v3_ry == 16) return {k_kpm_cheb_reg<RegHoney<4, 4, 1, 2>>, 64};
+    if (f->v3_lxl == 8 && f->v3_ry == 8) return {k_kpm_cheb_reg<RegHoney<4, 2, 1, 1>>, 32};
+    return {nullptr, 0};
+}
+
+// Is the register Chebyshev kernel available for this preconditioner?  (symmetric propagator on a register-path lattice with
+// colour-uniform tau-independent hoppings; SQ_KPM_REG=0 forces the shared-memory kernel)
+bool kpm_reg_ok(const sq_kpm *k) {
+    const sq_fdm *f = k->f;
+    if (const char *e = getenv("SQ_KPM_REG")) if (atoi(e) == 0) return false;
+    return f->sym && f->v3_ok && f->cs_coluni && pick_cheb_reg(f).k != nullptr;
+}
+
+// z: nrhs frequency-major arrays [n][i] (rhs_stride elements apart); applies sum_q c_q T_q(B') to every scheduled frequency in place
+void kpm_cheb_reg_launch(sq_kpm *k, double2 *z, int nrhs, size_t rhs_stride, const CgState *skip) {
+    sq_fdm *f = k->f;
+    if (k->nsched <= 0) return;
+    const ChebRegPick pk = pick_cheb_reg(f);
+    ChebRegParams P;
+    P.N = (int)f->N; P.L = (int)f->L; P.nsched = k->nsched; P.nrhs = nrhs; P.nchain = k->nsched * 2 * nrhs; P.rhs_stride = rhs_stride;
+    P.z = z; P.sched = k->d_freq_sched.p; P.order = k->d_order.p; P.coef_off = k->d_coef_off.p; P.coefs = k->d_coefs.p;
+    P.csbar = k->csbar.p; P.Dbar = k->Dbar.p;
+    for (int c = 0; c < 4; c++) P.clo[c] = c < f->C ? f->clo[c] : 0;
+    P.avg = 0.5 * (k->bounds[1] + k->bounds[0]);
+    P.imag_ = 2.0 / (k->bounds[1] - k->bounds[0]);
+    P.skip = skip;
+    const int grid = std::min(P.nchain, f->num_sms);
+    pk.k<<<grid, pk.threads, 0, f->stream>>>(P);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+    f->stats[SQ_STAT_KPM_REG]++;
+}

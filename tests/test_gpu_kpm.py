@@ -97,6 +97,79 @@ def test_preconditioned_cg_matches_oracle(name, sym):
     assert itw == 0
 
 
+REG_LATTICES = {
+    "sq16x16": lambda: mdl.holstein_square(16, 16, 2.0),     # one warp per chain
+    "sq32x16": lambda: mdl.holstein_square(32, 16, 1.0),     # two warps per chain: boundary rows through shared memory
+    "sq16x32": lambda: mdl.holstein_square(16, 32, 1.0),
+    "sq32x32": lambda: mdl.holstein_square(32, 32, 1.5),     # cfg4's lattice: four warps per chain
+    "sq16x64": lambda: mdl.holstein_square(16, 64, 0.5),
+    "sq32x64": lambda: mdl.holstein_square(32, 64, 0.5),     # eight warps per chain
+    "hc8": lambda: mdl.holstein_honeycomb(8, 1.0),
+    "hc16": lambda: mdl.holstein_honeycomb(16, 0.6),
+    "hc24": lambda: mdl.holstein_honeycomb(24, 0.5),         # cfg5's lattice: three warps per chain
+}
+
+
+@pytest.mark.parametrize("name", list(REG_LATTICES))
+def test_register_chebyshev_matches_oracle_and_smem_kernel(name, monkeypatch):
+    """The register-engine Chebyshev kernel (kpm_reg.cu): same orders / coefficients, P^-1 v against the oracle and against the
+    shared-memory kernel it replaces on these lattices, and the preconditioned CG iteration counts."""
+    from smoqyelph_b200 import api
+    m = REG_LATTICES[name]()
+    rng, ref, fdm = setup(m, True)
+    Pr = orc.RefKPM(ref)
+    Pg = api.KPMPreconditioner(fdm, update=False)
+    Pr.update(rng.standard_normal(m.N))
+    assert Pr.active
+    Pg.set_bounds(*Pr.bounds)
+    np.testing.assert_array_equal(Pg.orders, Pr.orders)
+    assert Pr.orders.max() > 2
+    v = rand_cvec(rng, m)
+    want = Pr.ldiv(v)
+    st0 = fdm.stats
+    got = Pg.ldiv(v)
+    assert fdm.stats["kpm_register"] == st0["kpm_register"] + 1, fdm.stats
+    assert relerr(got, want) < 1e-11
+    monkeypatch.setenv("SQ_KPM_REG", "0")
+    smem = Pg.ldiv(v)
+    monkeypatch.delenv("SQ_KPM_REG")
+    assert fdm.stats["kpm_smem"] == st0["kpm_smem"] + 1
+    assert relerr(got, smem) < 1e-12
+    b = rand_cvec(rng, m)
+    for tol in (1e-5, 1e-10):
+        xr, itr, _ = ref.cg(b, P=Pr, tol=tol, maxiter=5000)
+        xg, itg, epsg = fdm.ldiv(b, preconditioner=Pg, tol=tol, maxiter=5000, refresh=False)
+        assert abs(itg - itr) <= 1, (name, tol, itg, itr)
+        assert epsg < tol and relerr(xg, xr) < 100 * tol
+
+
+def test_preconditioned_cg_iteration_count_cfg4():
+    """Full size of the named configuration 4 (32 x 32, Ltau = 400, max order ~ 160): preconditioned CG iteration counts within +-1 of
+    the reference recurrence (src/IterativeSolvers/ConjugateGradient.jl:169-249 with src/KPMPreconditioner.jl:355-414)."""
+    from smoqyelph_b200 import api
+    m = mdl.config("cfg4")
+    rng = np.random.default_rng(5)
+    V, t = dr.build_Vt(m, m.random_fields(rng, smooth=True))
+    ref = orc.RefFDM(m, sym=True, omp=True)
+    ref.update(V, t)
+    fdm = api.FermionDetMatrix(m, sym=True)
+    fdm.update(V, t)
+    Pr = orc.RefKPM(ref)
+    Pg = api.KPMPreconditioner(fdm, update=False)
+    Pr.update(rng.standard_normal(m.N))
+    Pg.set_bounds(*Pr.bounds)
+    np.testing.assert_array_equal(Pg.orders, Pr.orders)
+    assert Pr.orders.max() > 100
+    b = rand_cvec(rng, m)
+    assert relerr(Pg.ldiv(b), Pr.ldiv(b)) < 1e-11
+    for tol in (1e-5, 1e-10):
+        xr, itr, _ = ref.cg(b, P=Pr, tol=tol, maxiter=5000)
+        xg, itg, epsg = fdm.ldiv(b, preconditioner=Pg, tol=tol, maxiter=5000, refresh=False)
+        assert abs(itg - itr) <= 1, (tol, itg, itr)
+        assert epsg < tol and relerr(xg, xr) < 100 * tol
+    assert fdm.stats["kpm_register"] > 0
+
+
 def test_tau_independent_fields_exact_inverse_full_size():
     """Size-independent property at cfg4: tau-independent fields => P^-1 M^T M = I at high order."""
     from smoqyelph_b200 import api
