@@ -449,6 +449,22 @@ def run_native(args):
         fdm.cg_dev(d_xN.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=400)
         torch.cuda.synchronize()
         us1 = max_over_ranks(time.perf_counter() - t0) / 400 * 1e6
+        def kpm_iter_us():
+            """preconditioned CG, microseconds per iteration (short solves: the recurrence breaks down once the residual is exactly zero)"""
+            P_kpm.update(np.random.default_rng(6).standard_normal(m.N))
+            fdm.cg_dev(d_xN.data_ptr(), d_b.data_ptr(), True, preconditioner=P_kpm, tol=1e-300, maxiter=4)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(4):
+                fdm.cg_dev(d_xN.data_ptr(), d_b.data_ptr(), True, preconditioner=P_kpm, tol=1e-300, maxiter=15)
+            torch.cuda.synchronize()
+            return max_over_ranks(time.perf_counter() - t0) / 60 * 1e6
+        stage[0] = "one-GPU preconditioned solve"
+        d_xk1 = torch.zeros_like(d_b)
+        P_kpm.update(np.random.default_rng(6).standard_normal(m.N))
+        itk1, _ = fdm.cg_dev(d_xk1.data_ptr(), d_b.data_ptr(), True, preconditioner=P_kpm, tol=1e-10, maxiter=MAXITER)
+        usk1 = kpm_iter_us()
         stage[0] = "init sharded solve"
         fdm.init_sharded_solve(dist)
         stage[0] = "sharded solve parity"
@@ -460,8 +476,16 @@ def run_native(args):
         fdm.cg_dev(d_xN.data_ptr(), d_b.data_ptr(), True, tol=1e-300, maxiter=400)
         torch.cuda.synchronize()
         usN = max_over_ranks(time.perf_counter() - t0) / 400 * 1e6
+        stage[0] = "sharded preconditioned solve"
+        itkN, _ = fdm.cg_dev(d_xN.data_ptr(), d_b.data_ptr(), True, preconditioner=P_kpm, tol=1e-10, maxiter=MAXITER)
+        torch.cuda.synchronize()
+        errk = float((torch.linalg.norm(d_xN - d_xk1) / torch.linalg.norm(d_xk1)).item())
+        uskN = kpm_iter_us()
         st = fdm.stats
-        tau_slab = {"what": "one chain, every unpreconditioned CG solve tau-slab partitioned over all GPUs",
+        kpm_slab = {"what": "KPM-preconditioned CG, P^-1 sharded by Matsubara frequency: two all-to-all exchanges (grouped ncclSend/ncclRecv) per apply",
+                    "parity": {"err": max_over_ranks(errk), "iters_1gpu": int(itk1), "iters_ngpu": int(itkN)},
+                    "cg_us_per_iter_1gpu": usk1, "cg_us_per_iter": uskN, "sharded_solves": st["cg_slab_preconditioned"]}
+        tau_slab = {"what": "one chain, every unpreconditioned CG solve tau-slab partitioned over all GPUs", "preconditioned": kpm_slab,
                     "parity": {"what": "same right-hand side solved to 1e-10 on one GPU and sharded over all GPUs",
                                "err": max_over_ranks(err), "iters_1gpu": int(it1), "iters_ngpu": int(itN), "eps_1gpu": eps1, "eps_ngpu": epsN},
                     "cg_us_per_iter_1gpu": us1, "cg_us_per_iter": usN, "cg_speedup_vs_1gpu": us1 / usN,

@@ -20,7 +20,7 @@ int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, 
                    bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
                    double *dot_part, const CgState *skip, size_t smem_limit);
 bool kpm_reg_ok(const sq_kpm *k);
-void kpm_cheb_reg_launch(sq_kpm *k, double2 *z, int nrhs, size_t rhs_stride, const CgState *skip);
+void kpm_cheb_reg_launch(sq_kpm *k, double2 *z, const int *d_sched, int nsched, int nrhs, size_t rhs_stride, const CgState *skip);
 
 struct BbarParams {
     int N, Nh, C, sym;
@@ -522,6 +522,8 @@ static void kpm_update_expansions(sq_kpm *k) {
     std::vector<int> h_sched;
     for (auto &p : sched) h_sched.push_back(p.second);
     k->nsched = (int)h_sched.size();
+    k->h_sched = h_sched;
+    k->sched_version++;
     k->d_order.alloc(h_order.size() + 1, false); k->d_order.upload(h_order.data(), h_order.size(), f->stream);
     k->d_coef_off.alloc(h_off.size() + 1, false); k->d_coef_off.upload(h_off.data(), h_off.size(), f->stream);
     k->d_coefs.alloc(flat.size() + 1, false); k->d_coefs.upload(flat.data(), flat.size(), f->stream);
@@ -615,6 +617,56 @@ void kpm_update(sq_kpm *k, const double *h_start, const double *d_start) {
     } else k->active = 0;
 }
 
+// The Chebyshev stage on frequency-major arrays z ([rhs][n][i], rhs_stride elements apart): sum_q c_q T_q(B') applied in place to the
+// `nsched` frequencies listed in d_sched (the whole schedule, or one rank's share in tau-slab mode); skip[rhs].done skips a right-hand side.
+void kpm_cheb_apply(sq_kpm *k, double2 *z, const int *d_sched, int nsched, int nrhs, size_t rhs_stride, const CgState *skip) {
+    sq_fdm *f = k->f;
+    if (nsched <= 0) return;
+    if (kpm_reg_ok(k)) {                                                 // register engine (kpm_reg.cu): lattices of the register path
+        kpm_cheb_reg_launch(k, z, d_sched, nsched, nrhs, rhs_stride, skip);
+        return;
+    }
+    for (int rhs = 0; rhs < nrhs; rhs++) {
+        double2 *zt = z + (size_t)rhs * rhs_stride;
+        const CgState *sk = skip ? skip + rhs : nullptr;
+        if (kpm_fast_ok(k)) {
+            f->stats[SQ_STAT_KPM_SMEM]++;
+            BbarFast Q;
+            Q.N = (int)f->N; Q.C = (int)f->C; Q.nunc0 = f->nunc0;
+            for (int c = 0; c < 8; c++) { Q.clo[c] = c < f->C ? f->clo[c] : 0; Q.chi[c] = c < f->C ? f->chi[c] : 0; }
+            Q.nts = f->nts.p; Q.nt = f->nt.p; Q.slot = f->slot.p; Q.unc0 = f->unc0.p; Q.csbar = k->csbar.p; Q.Dbar = k->Dbar.p;
+            static long long *dbg = nullptr;
+            if (!dbg && getenv("SQ_DEBUG_STAMPS")) { SQ_CUDA(cudaMallocManaged((void **)&dbg, 8 * sizeof(long long))); for (int q = 0; q < 8; q++) dbg[q] = 0; }
+            Q.dbg = dbg;
+            if (dbg && getenv("SQ_DEBUG_PRINT")) {
+                cudaStreamSynchronize(f->stream);
+                fprintf(stderr, "cheb stamps: first apply %lld cycles, whole recurrence %lld cycles, order %lld -> %.0f cycles/step\n", dbg[1] - dbg[0],
+                        dbg[2] - dbg[0], dbg[3], (double)(dbg[2] - dbg[0]) / (double)std::max<long long>(1, dbg[3] - 1));
+            }
+            double avg = 0.5 * (k->bounds[1] + k->bounds[0]), mag = 0.5 * (k->bounds[1] - k->bounds[0]);
+            size_t smem = f->N * sizeof(double2);
+            const int T = kpm_fast_threads(k);
+            smem = f->N * sizeof(double);
+#define SQ_CHEB(CM, MT) k_kpm_cheb_fast<CM, MT><<<2 * nsched, T, smem, f->stream>>>(Q, zt, d_sched, k->d_order.p, k->d_coef_off.p, \
+                                                                                           k->d_coefs.p, (int)f->L, avg, 1.0 / mag, sk)
+            if (f->C <= 4) { if (T <= 512) SQ_CHEB(4, 512); else SQ_CHEB(4, 1024); }
+            else { if (T <= 512) SQ_CHEB(8, 512); else SQ_CHEB(8, 1024); }
+#undef SQ_CHEB
+            SQ_LAUNCH_CHECK();
+            f->launches++;
+        } else {
+            f->stats[SQ_STAT_KPM_SMEM]++;
+            BbarParams P = bbar_params(k);
+            double avg = 0.5 * (k->bounds[1] + k->bounds[0]), mag = 0.5 * (k->bounds[1] - k->bounds[0]);
+            k_kpm_cheb<<<nsched, kpm_threads(k), 4 * f->N * sizeof(double2), f->stream>>>(P, zt, d_sched, k->d_order.p,
+                                                                                            k->d_coef_off.p, k->d_coefs.p, (int)f->L, avg,
+                                                                                            1.0 / mag, sk);
+            SQ_LAUNCH_CHECK();
+            f->launches++;
+        }
+    }
+}
+
 // out = P^-1 in  on device [l][i] vectors (out may alias in).  dot partial fusion is requested by cg.cu.
 int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *skip, const double2 *dot_with, double *dot_part) {
     sq_fdm *f = k->f;
@@ -626,43 +678,7 @@ int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *
     double2 *zt = k->ztmp.p;
     tau_fft_launch(f->stream, k->radices, (int)f->L, (int)f->N, zt, in, false, true, k->tw.p, k->theta.p, k->d_scale1.p, nullptr, nullptr,
                    skip, f->smem_optin);
-    if (k->nsched > 0 && kpm_reg_ok(k)) {                                // register engine (kpm_reg.cu): lattices of the register path
-        kpm_cheb_reg_launch(k, zt, 1, 0, skip);
-    } else if (k->nsched > 0 && kpm_fast_ok(k)) {
-        f->stats[SQ_STAT_KPM_SMEM]++;
-        BbarFast Q;
-        Q.N = (int)f->N; Q.C = (int)f->C; Q.nunc0 = f->nunc0;
-        for (int c = 0; c < 8; c++) { Q.clo[c] = c < f->C ? f->clo[c] : 0; Q.chi[c] = c < f->C ? f->chi[c] : 0; }
-        Q.nts = f->nts.p; Q.nt = f->nt.p; Q.slot = f->slot.p; Q.unc0 = f->unc0.p; Q.csbar = k->csbar.p; Q.Dbar = k->Dbar.p;
-        static long long *dbg = nullptr;
-        if (!dbg && getenv("SQ_DEBUG_STAMPS")) { SQ_CUDA(cudaMallocManaged((void **)&dbg, 8 * sizeof(long long))); for (int q = 0; q < 8; q++) dbg[q] = 0; }
-        Q.dbg = dbg;
-        if (dbg && getenv("SQ_DEBUG_PRINT")) {
-            cudaStreamSynchronize(f->stream);
-            fprintf(stderr, "cheb stamps: first apply %lld cycles, whole recurrence %lld cycles, order %lld -> %.0f cycles/step\n", dbg[1] - dbg[0],
-                    dbg[2] - dbg[0], dbg[3], (double)(dbg[2] - dbg[0]) / (double)std::max<long long>(1, dbg[3] - 1));
-        }
-        double avg = 0.5 * (k->bounds[1] + k->bounds[0]), mag = 0.5 * (k->bounds[1] - k->bounds[0]);
-        size_t smem = f->N * sizeof(double2);
-        const int T = kpm_fast_threads(k);
-        smem = f->N * sizeof(double);
-#define SQ_CHEB(CM, MT) k_kpm_cheb_fast<CM, MT><<<2 * k->nsched, T, smem, f->stream>>>(Q, zt, k->d_freq_sched.p, k->d_order.p, k->d_coef_off.p, \
-                                                                                       k->d_coefs.p, (int)f->L, avg, 1.0 / mag, skip)
-        if (f->C <= 4) { if (T <= 512) SQ_CHEB(4, 512); else SQ_CHEB(4, 1024); }
-        else { if (T <= 512) SQ_CHEB(8, 512); else SQ_CHEB(8, 1024); }
-#undef SQ_CHEB
-        SQ_LAUNCH_CHECK();
-        f->launches++;
-    } else if (k->nsched > 0) {
-        f->stats[SQ_STAT_KPM_SMEM]++;
-        BbarParams P = bbar_params(k);
-        double avg = 0.5 * (k->bounds[1] + k->bounds[0]), mag = 0.5 * (k->bounds[1] - k->bounds[0]);
-        k_kpm_cheb<<<k->nsched, kpm_threads(k), 4 * f->N * sizeof(double2), f->stream>>>(P, zt, k->d_freq_sched.p, k->d_order.p,
-                                                                                        k->d_coef_off.p, k->d_coefs.p, (int)f->L, avg,
-                                                                                        1.0 / mag, skip);
-        SQ_LAUNCH_CHECK();
-        f->launches++;
-    }
+    kpm_cheb_apply(k, zt, k->d_freq_sched.p, k->nsched, 1, 0, skip);
     int g = tau_fft_launch(f->stream, k->radices, (int)f->L, (int)f->N, out, zt, true, true, k->tw.p, k->theta.p, nullptr, dot_with,
                            dot_part, skip, f->smem_optin);
     f->launches += 2;

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(32 * G::W, 1)
 k_kpm_cheb_reg(const __grid_constant__ ChebRegParams P) {
     constexpr int NV = G::NV;
     __shared__ __align__(32) double xch[G::XCH > 0 ? G::XCH : 1];
-    if (P.skip && P.skip->done) return;
+    if (P.skip && P.nrhs == 1 && P.skip->done) return;
     G E;
     double g;
     E.init(P, g);
@@ -270,6 +270,7 @@ k_kpm_cheb_reg(const __grid_constant__ ChebRegParams P) {
     for (int ch = blockIdx.x; ch < P.nchain; ch += gridDim.x) {
         // chains are ordered longest first: (schedule index, part, rhs) with the schedule index slowest
         const int si = ch / (2 * P.nrhs), rem = ch - si * 2 * P.nrhs, part = rem & 1, rhs = rem >> 1;
+        if (P.skip && P.skip[rhs].done) continue;                 // CTA-uniform: all warps skip the chain together
         const int n = __ldg(P.sched + si);
         const int np = (n + 1 > (P.L + 1) / 2) ? P.L - 1 - n : n;                     // KPMPreconditioner.jl:387
         const int ord = __ldg(P.order + np);
@@ -354,13 +355,13 @@ bool kpm_reg_ok(const sq_kpm *k) {
 }
 
 // z: nrhs frequency-major arrays [n][i] (rhs_stride elements apart); applies sum_q c_q T_q(B') to every scheduled frequency in place
-void kpm_cheb_reg_launch(sq_kpm *k, double2 *z, int nrhs, size_t rhs_stride, const CgState *skip) {
+void kpm_cheb_reg_launch(sq_kpm *k, double2 *z, const int *d_sched, int nsched, int nrhs, size_t rhs_stride, const CgState *skip) {
     sq_fdm *f = k->f;
-    if (k->nsched <= 0) return;
+    if (nsched <= 0) return;
     const ChebRegPick pk = pick_cheb_reg(f);
     ChebRegParams P;
-    P.N = (int)f->N; P.L = (int)f->L; P.nsched = k->nsched; P.nrhs = nrhs; P.nchain = k->nsched * 2 * nrhs; P.rhs_stride = rhs_stride;
-    P.z = z; P.sched = k->d_freq_sched.p; P.order = k->d_order.p; P.coef_off = k->d_coef_off.p; P.coefs = k->d_coefs.p;
+    P.N = (int)f->N; P.L = (int)f->L; P.nsched = nsched; P.nrhs = nrhs; P.nchain = nsched * 2 * nrhs; P.rhs_stride = rhs_stride;
+    P.z = z; P.sched = d_sched; P.order = k->d_order.p; P.coef_off = k->d_coef_off.p; P.coefs = k->d_coefs.p;
     P.csbar = k->csbar.p; P.Dbar = k->Dbar.p;
     for (int c = 0; c < 4; c++) P.clo[c] = c < f->C ? f->clo[c] : 0;
     P.avg = 0.5 * (k->bounds[1] + k->bounds[0]);

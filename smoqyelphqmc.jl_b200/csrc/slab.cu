@@ -136,10 +136,10 @@ static void shard_swap(sq_fdm *f, bool enter) {
     else { f->slab_lo = 0; f->slab_hi = (int)f->L; }
 }
 // one solve of the sharded mode: slab solve, then every rank broadcasts its slab of the solution to the others
-void fdm_cg_sharded(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, double tol, i64 maxiter, i64 *iters, double *eps) {
+void fdm_cg_sharded(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter, i64 *iters, double *eps) {
     shard_swap(f, true);
     try {
-        fdm_cg_slab(f, x, b, zero_start, tol, maxiter, iters, eps);
+        fdm_cg_slab(f, x, b, zero_start, kpm, tol, maxiter, iters, eps);
     } catch (...) {
         shard_swap(f, false);
         throw;
@@ -342,7 +342,233 @@ static bool cg_slab_resident(sq_fdm *f, double2 *x, const double2 *b, bool zero_
     return true;
 }
 
-void fdm_cg_slab(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, double tol, i64 maxiter, i64 *iters, double *eps) {
+
+// ---------------------------------------------------------------------------------------------------
+// KPM / tau-Fourier preconditioner in tau-slab mode: the all-to-all of SURVEY.md 8e.
+//
+// P^-1 = U^-1 f(B-bar) U mixes all time slices (U is the twisted DFT along tau), so a tau-slab vector has to change its
+// partition on the way in and on the way out.  Rank g holds slices [lo_g, hi_g); it also OWNS the Matsubara frequencies with the
+// same indices.  The DFT is linear in its input slices:
+//     forward:  every rank transforms its own slices (all others zero-padded) into partial sums for ALL frequencies, then the
+//               partial sums of the frequencies of rank q travel to rank q (grouped ncclSend / ncclRecv: the all-to-all) and are
+//               added there in fixed rank order (deterministic);
+//     middle:   rank g runs the Chebyshev recurrences of ITS frequencies (the order-1 frequencies are scalars folded into the
+//               forward transform, so only frequencies with order > 1 cost anything);
+//     inverse:  every rank transforms its frequencies (all others zero) into partial sums for ALL slices, second all-to-all, each
+//               rank adds up the pieces of its own slices.
+// Two exchanges of V 16 (P-1)/P bytes per GPU and apply, against src/KPMPreconditioner.jl:375-406 (FFT, transpose, per-frequency
+// kpm_lmul!, transpose, inverse FFT) on one process.  B-bar (tau-means of the coefficient arrays) is computed locally: every
+// rank keeps full-length coefficient arrays.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_slab_pad(double2 *__restrict__ dst, const double2 *__restrict__ src, size_t own_lo, size_t own_hi, size_t n) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
+        dst[e] = (e >= own_lo && e < own_hi) ? src[e] : make_double2(0.0, 0.0);
+}
+// dst[e] = sum over ranks q = 0 .. world-1 (in this order) of q's partial sum: the own one from `own`, the others from recv[q]
+__global__ void k_slab_sum_pieces(double2 *__restrict__ dst, const double2 *__restrict__ own, const double2 *__restrict__ recv, size_t piece,
+                                  int world, int rank, size_t n) {
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        double2 acc = make_double2(0.0, 0.0);
+        for (int q = 0; q < world; q++) {
+            const double2 v = (q == rank) ? own[e] : recv[(size_t)q * piece + e];
+            acc.x += v.x; acc.y += v.y;
+        }
+        dst[e] = acc;
+    }
+}
+// rows [lo_q, hi_q) of src (partial sums for everybody) go to rank q; the pieces of the own rows are added up into dst's own rows
+static void slab_exchange_sum(sq_fdm *f, sq_kpm *k, double2 *dst, const double2 *src) {
+    const int W = f->world, me = f->rank, L = (int)f->L;
+    const size_t N = (size_t)f->N;
+    int lo, hi;
+    slab_range(L, W, me, &lo, &hi);
+    const size_t piece = (size_t)(L / W + 1) * N, n_own = (size_t)(hi - lo) * N;
+    if (k->slab_recv.n < piece * W) k->slab_recv.alloc(piece * W, false);
+    if (W > 1) {
+        ncclComm_t c = (ncclComm_t)f->comm;
+        SQ_NCCL(g_nccl.GroupStart());
+        for (int q = 0; q < W; q++) {
+            if (q == me) continue;
+            int qlo, qhi;
+            slab_range(L, W, q, &qlo, &qhi);
+            SQ_NCCL(g_nccl.Send(src + (size_t)qlo * N, (size_t)(qhi - qlo) * N * 2, ncclDouble, q, c, f->stream));
+            SQ_NCCL(g_nccl.Recv(k->slab_recv.p + (size_t)q * piece, n_own * 2, ncclDouble, q, c, f->stream));
+        }
+        SQ_NCCL(g_nccl.GroupEnd());
+    }
+    const int G = (int)std::max<size_t>(1, std::min<size_t>((n_own + 255) / 256, (size_t)f->num_sms * 4));
+    k_slab_sum_pieces<<<G, 256, 0, f->stream>>>(dst + (size_t)lo * N, src + (size_t)lo * N, k->slab_recv.p, piece, W, me, n_own);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
+}
+
+int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, int N, double2 *out, const double2 *in, bool inverse,
+                   bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
+                   double *dot_part, const CgState *skip, size_t smem_limit);
+
+// out[own slices] = (P^-1 in)[own slices]; `in` is valid on the own slices.  The slab must be the rank's balanced share (slab_init).
+void kpm_ldiv_slab(sq_kpm *k, double2 *out, const double2 *in) {
+    sq_fdm *f = k->f;
+    const int L = (int)f->L, W = f->world, me = f->rank;
+    const size_t N = (size_t)f->N, V = (size_t)L * N;
+    int lo, hi;
+    slab_range(L, W, me, &lo, &hi);
+    SQ_REQUIRE(lo == f->slab_lo && hi == f->slab_hi, "the preconditioner in tau-slab mode needs the balanced partition of sq_fdm_init_slab");
+    if (!k->slab_a.p) { k->slab_a.alloc(V); k->slab_b.alloc(V); }
+    // this rank's share of the Chebyshev schedule: the frequencies [lo, hi) with order > 1, longest first
+    if (k->sched_slab_version != k->sched_version || k->sched_slab_lo != lo || k->sched_slab_hi != hi) {
+        std::vector<int> mine;
+        for (int n : k->h_sched) if (n >= lo && n < hi) mine.push_back(n);
+        k->nsched_slab = (int)mine.size();
+        k->d_sched_slab.alloc(mine.size() + 1, false);
+        k->d_sched_slab.upload(mine.data(), mine.size(), f->stream);
+        SQ_CUDA(cudaStreamSynchronize(f->stream));
+        k->sched_slab_version = k->sched_version; k->sched_slab_lo = lo; k->sched_slab_hi = hi;
+    }
+    const int G = (int)std::min<size_t>((V + 255) / 256, (size_t)f->num_sms * 8);
+    k_slab_pad<<<G, 256, 0, f->stream>>>(k->slab_a.p, in, (size_t)lo * N, (size_t)hi * N, V);
+    double2 *zt = k->ztmp.p;
+    tau_fft_launch(f->stream, k->radices, L, (int)N, zt, k->slab_a.p, false, true, k->tw.p, k->theta.p, k->d_scale1.p, nullptr, nullptr, nullptr,
+                   f->smem_optin);
+    SQ_CUDA(cudaMemsetAsync(k->slab_b.p, 0, V * sizeof(double2), f->stream));
+    slab_exchange_sum(f, k, k->slab_b.p, zt);                                   // all-to-all #1: tau-slab -> frequency-slab
+    kpm_cheb_apply(k, k->slab_b.p, k->d_sched_slab.p, k->nsched_slab, 1, 0, nullptr);
+    tau_fft_launch(f->stream, k->radices, L, (int)N, zt, k->slab_b.p, true, true, k->tw.p, k->theta.p, nullptr, nullptr, nullptr, nullptr,
+                   f->smem_optin);
+    slab_exchange_sum(f, k, out, zt);                                           // all-to-all #2: frequency-slab -> tau-slab
+    f->launches += 3;
+}
+
+// partials of conj(a).b (re, im) on a slab
+__global__ void k_slab_dotc_part(const double2 *__restrict__ a, const double2 *__restrict__ b, size_t n, double *__restrict__ part) {
+    __shared__ double red[2 * 32];
+    double v[2] = {0.0, 0.0};
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const double2 x = a[e], y = b[e];
+        v[0] += x.x * y.x + x.y * y.y;
+        v[1] += x.x * y.y - x.y * y.x;
+    }
+    block_sum<2>(v, red);
+    if (threadIdx.x == 0) { part[blockIdx.x] = v[0]; part[SQ_MAXPART + blockIdx.x] = v[1]; }
+}
+// scal: 0 |b|^2, 1-2 r.z (old), 3 p.Ap, 4 done, 5 eps, 6 iterations, 7 |r|^2, 8-9 r.z (new)
+__global__ void k_slab_prec_update_xr(const double *__restrict__ scal, double2 *__restrict__ x, double2 *__restrict__ r,
+                                      const double2 *__restrict__ p, const double2 *__restrict__ q, size_t n, double *__restrict__ part) {
+    __shared__ double red[32];
+    if (scal[4] != 0.0) return;
+    const double2 alpha = make_double2(scal[1] / scal[3], scal[2] / scal[3]);       // (r.z) / (p.Ap), p.Ap = |M p|^2 real
+    double acc = 0;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const double2 pk = p[e], qk = q[e];
+        const double2 xk = cadd(x[e], cmul(alpha, pk)), rk = csub(r[e], cmul(alpha, qk));
+        x[e] = xk;
+        r[e] = rk;
+        acc += rk.x * rk.x + rk.y * rk.y;
+    }
+    double v[1] = {acc};
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = v[0];
+}
+__global__ void k_slab_prec_check(double *scal, double tol, int iter) {
+    if (scal[4] != 0.0) return;
+    const double eps = sqrt(scal[7] / scal[0]);
+    scal[5] = eps;
+    scal[6] = (double)iter;
+    if (eps < tol) scal[4] = 1.0;
+    else if (!(eps == eps)) scal[4] = 2.0;
+}
+__global__ void k_slab_prec_update_p(const double *__restrict__ scal, double2 *__restrict__ p, const double2 *__restrict__ z, size_t n) {
+    if (scal[4] != 0.0) return;
+    const double2 beta = cdiv(make_double2(scal[8], scal[9]), make_double2(scal[1], scal[2]));
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
+        p[e] = cadd(z[e], cmul(beta, p[e]));
+}
+__global__ void k_slab_prec_roll(double *scal) {
+    if (scal[4] != 0.0) return;
+    scal[1] = scal[8];
+    scal[2] = scal[9];
+}
+__global__ void k_pack_sum2(const double *__restrict__ part, int n, double *__restrict__ dst) {
+    const double a = warp_sum_partials(part, n), b = warp_sum_partials(part + SQ_MAXPART, n);
+    if (threadIdx.x == 0) { dst[0] = a; dst[1] = b; }
+}
+
+// Preconditioned CG on a tau-slab: the reference recurrence (ConjugateGradient.jl:169-249) with the distributed P^-1 above, one halo
+// exchange and three small all-reduces (p.Ap, |r|^2, r.z) per iteration.
+static void cg_slab_prec(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter, i64 *iters, double *eps) {
+    SQ_REQUIRE(f->world > 1 || (f->slab_lo == 0 && f->slab_hi == (int)f->L), "a preconditioned solve on a partial slice range needs the other ranks");
+    const size_t N = (size_t)f->N;
+    const size_t off = (size_t)f->slab_lo * N, n = (size_t)(f->slab_hi - f->slab_lo) * N;
+    const int TB = 256;
+    const int G = (int)std::max<size_t>(1, std::min<size_t>((n + TB - 1) / TB, (size_t)f->num_sms * 4));
+    cudaStream_t s = f->stream;
+    double *part = f->part.p, *scal = f->scal.p;
+    double2 *r = f->r.p, *p = f->p.p, *z = f->z.p, *q = nullptr;
+    if (f->prec_q.n < (size_t)f->L * N) f->prec_q.alloc((size_t)f->L * N, false);      // (tmp1 / tmp2 are scratch of the matvec itself)
+    q = f->prec_q.p;
+    SQ_CUDA(cudaMemsetAsync(scal, 0, 16 * sizeof(double), s));
+    k_norm2_part<<<G, TB, 0, s>>>(b + off, n, part);
+    k_pack_sum<<<1, 32, 0, s>>>(part, G, scal + 0);
+    if (zero_start) {
+        SQ_CUDA(cudaMemcpyAsync(r + off, b + off, n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+        SQ_CUDA(cudaMemsetAsync(x + off, 0, n * sizeof(double2), s));
+    } else {
+        fdm_halo_exchange(f, x);
+        fdm_mul_dev(f, SQ_OP_MTM, r, x);
+        k_sub<<<G, TB, 0, s>>>(r + off, b + off, n);
+    }
+    k_norm2_part<<<G, TB, 0, s>>>(r + off, n, part);
+    k_pack_sum<<<1, 32, 0, s>>>(part, G, scal + 7);
+    fdm_allreduce_sum(f, scal, 1);
+    fdm_allreduce_sum(f, scal + 7, 1);
+    k_slab_prec_check<<<1, 1, 0, s>>>(scal, tol, 0);                              // eps0 test (:206-214)
+    kpm_ldiv_slab(kpm, z, r);
+    SQ_CUDA(cudaMemcpyAsync(p + off, z + off, n * sizeof(double2), cudaMemcpyDeviceToDevice, s));
+    k_slab_dotc_part<<<G, TB, 0, s>>>(r + off, z + off, n, part);
+    k_pack_sum2<<<1, 32, 0, s>>>(part, G, scal + 1);
+    fdm_allreduce_sum(f, scal + 1, 2);
+    f->launches += 8;
+    double h[10];
+    SQ_CUDA(cudaMemcpyAsync(h, scal, 10 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    SQ_CUDA(cudaStreamSynchronize(s));
+    i64 it = 0;
+    const int batch = 4;
+    bool finished = (h[4] != 0.0) || maxiter <= 0;
+    while (!finished) {
+        const i64 upto = std::min<i64>(maxiter, it + batch);
+        for (; it < upto;) {
+            it++;
+            fdm_halo_exchange(f, p);
+            int npart = 0;
+            fdm_mul_dev(f, SQ_OP_MTM, q, p, part, &npart, nullptr);               // q = M^T M p on the slab, |M p|^2 partials
+            k_pack_sum<<<1, 32, 0, s>>>(part, npart, scal + 3);
+            fdm_allreduce_sum(f, scal + 3, 1);
+            k_slab_prec_update_xr<<<G, TB, 0, s>>>(scal, x + off, r + off, p + off, q + off, n, part);
+            k_pack_sum<<<1, 32, 0, s>>>(part, G, scal + 7);
+            fdm_allreduce_sum(f, scal + 7, 1);
+            k_slab_prec_check<<<1, 1, 0, s>>>(scal, tol, (int)it);
+            kpm_ldiv_slab(kpm, z, r);
+            k_slab_dotc_part<<<G, TB, 0, s>>>(r + off, z + off, n, part);
+            k_pack_sum2<<<1, 32, 0, s>>>(part, G, scal + 8);
+            fdm_allreduce_sum(f, scal + 8, 2);
+            k_slab_prec_update_p<<<G, TB, 0, s>>>(scal, p + off, z + off, n);
+            k_slab_prec_roll<<<1, 1, 0, s>>>(scal);
+            f->launches += 8;
+        }
+        SQ_LAUNCH_CHECK();
+        SQ_CUDA(cudaMemcpyAsync(h, scal, 10 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        SQ_CUDA(cudaStreamSynchronize(s));
+        if (h[4] != 0.0 || it >= maxiter) finished = true;
+    }
+    f->stats[SQ_STAT_CG_SOLVES]++; f->stats[SQ_STAT_CG_SLAB_PREC]++;
+    if (h[4] == 2.0) throw SqNumericalInstability("conjugate gradient (tau-slab, preconditioned): NaN encountered in the residual");
+    *iters = h[4] != 0.0 ? (i64)h[6] : maxiter;
+    *eps = h[5];
+    f->stats[SQ_STAT_CG_ITERS] += *iters;
+}
+
+void fdm_cg_slab(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter, i64 *iters, double *eps) {
+    if (kpm && kpm->active) { cg_slab_prec(f, x, b, zero_start, kpm, tol, maxiter, iters, eps); return; }
     if (cg_slab_resident(f, x, b, zero_start, tol, maxiter, iters, eps)) return;
     const size_t N = (size_t)f->N;
     const size_t off = (size_t)f->slab_lo * N, n = (size_t)(f->slab_hi - f->slab_lo) * N;

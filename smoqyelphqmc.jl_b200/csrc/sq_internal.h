@@ -146,6 +146,14 @@ struct sq_kpm {
     DevBuf<double2> d_coefs;
     DevBuf<double> d_scale1;                 // per frequency: scalar applied by the FFT store when order == 1
     int nsched = 0;                          // frequencies with order > 1
+    std::vector<int> h_sched;                // host copy of the schedule (longest recurrence first)
+    i64 sched_version = 0;                   // bumped whenever the expansions (and with them the schedule) change
+    // tau-slab mode (slab.cu): this rank's share of the schedule and the staging buffers of the two all-to-all exchanges
+    DevBuf<int> d_sched_slab;
+    int nsched_slab = 0;
+    i64 sched_slab_version = -1;
+    int sched_slab_lo = -1, sched_slab_hi = -1;
+    DevBuf<double2> slab_a, slab_b, slab_recv;
     DevBuf<double2> ztmp;                    // [n][i] frequency-space scratch
     DevBuf<double> lan;                      // Lanczos alpha/beta read-back
     DevBuf<double> lan_start;                // N
@@ -251,6 +259,7 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
 void kpm_ldiv_dev(sq_kpm *k, double2 *out, const double2 *in, const CgState *skip_if_done = nullptr);
 int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *skip, const double2 *dot_with, double *dot_part);
 void kpm_fourier_dev(sq_kpm *k, double2 *v, bool forward);
+void kpm_cheb_apply(sq_kpm *k, double2 *z, const int *d_sched, int nsched, int nrhs, size_t rhs_stride, const CgState *skip);
 void kpm_lanczos(sq_kpm *k, const double *h_start, const double *d_start, double *emin, double *emax);
 void kpm_update(sq_kpm *k, const double *h_lanczos_start, const double *d_lanczos_start);
 void kpm_set_bounds(sq_kpm *k, double emin, double emax);
@@ -270,8 +279,8 @@ void fdm_select_tuning(sq_fdm *f);
 void fdm_sync_if_alive(sq_fdm *f);       // stream-synchronise f if it has not been destroyed yet, else the device
 void fdm_halo_exchange(sq_fdm *f, double2 *v);
 void fdm_allreduce_sum(sq_fdm *f, double *d_buf, int count);
-void fdm_cg_slab(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, double tol, i64 maxiter, i64 *iters, double *eps);
-void fdm_cg_sharded(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, double tol, i64 maxiter, i64 *iters, double *eps);
+void fdm_cg_slab(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter, i64 *iters, double *eps);
+void fdm_cg_sharded(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter, i64 *iters, double *eps);
 void slab_set_sharded(sq_fdm *f, int enable);
 void fft_radices(i64 n, std::vector<int> &rad);
 void fft_make_twiddles(i64 n, std::vector<double2> &tw);

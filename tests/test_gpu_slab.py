@@ -66,6 +66,38 @@ def test_slab_cg_recurrence_matches_oracle(monkeypatch):
     assert it0 == 0
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "h16"])
+def test_slab_preconditioned_cg_single_rank(name, monkeypatch):
+    """The tau-slab preconditioned solver (zero-padded partial DFTs, piece sums, per-rank share of the Chebyshev schedule) with
+    world = 1 through the same code: solution and iteration counts of the reference's preconditioned recurrence."""
+    from smoqyelph_b200 import api
+    monkeypatch.setenv("SQ_FORCE_SLAB_CG", "1")
+    m = mdl.config(name)
+    rng = np.random.default_rng(4)
+    V, t = dr.build_Vt(m, m.random_fields(rng, smooth=True))
+    ref = orc.RefFDM(m)
+    ref.update(V, t)
+    fdm = api.FermionDetMatrix(m)
+    fdm.update(V, t)
+    fdm.init_slab(0, 1)
+    Pr = orc.RefKPM(ref)
+    Pr.update(rng.standard_normal(m.N))
+    assert Pr.active
+    Pg = api.KPMPreconditioner(fdm, update=False)
+    Pg.set_bounds(*Pr.bounds)
+    b = np.asfortranarray(rng.standard_normal((m.Ltau, m.N)) + 1j * rng.standard_normal((m.Ltau, m.N)))
+    xr, itr, _ = ref.cg(b, P=Pr, tol=1e-13, maxiter=5000)
+    xg, itg, eps = fdm.ldiv(b, preconditioner=Pg, tol=1e-13, maxiter=5000, refresh=False)
+    assert eps < 1e-13 and relerr(xg, xr) < 1e-10
+    for tol in (1e-5, 1e-10):
+        _, itr, _ = ref.cg(b, P=Pr, tol=tol, maxiter=5000)
+        _, itg, _ = fdm.ldiv(b, preconditioner=Pg, tol=tol, maxiter=5000, refresh=False)
+        assert abs(itg - itr) <= 1
+    assert fdm.stats["cg_slab_preconditioned"] == 3
+    _, it0, _ = fdm.ldiv(b, x0=xg, preconditioner=Pg, tol=1e-10, refresh=False)
+    assert it0 == 0
+
+
 def test_two_gpu_halo_exchange_and_cg():
     import torch
     if torch.cuda.device_count() < 2:
@@ -81,6 +113,10 @@ def test_two_gpu_halo_exchange_and_cg():
         assert out["err_mul_MtM"] < 1e-12 and out["err_mul_M"] < 1e-12 and out["err_mul_Mt"] < 1e-12, out
         assert out["err_cg"] < 1e-10, out
         assert abs(out["iters"][0] - out["iters"][1]) <= 1, out
+        # preconditioned: frequency-sharded KPM apply with its two all-to-all exchanges
+        assert out["err_cg_kpm"] < 1e-11 * 10, out
+        assert abs(out["iters_kpm"][0] - out["iters_kpm"][1]) <= 1, out
+        assert out["stats"]["cg_slab_preconditioned"] >= 2, out
 
 
 def test_sharded_solve_single_rank_runs_the_same_trajectory():
@@ -115,9 +151,9 @@ def test_two_gpu_sharded_chain():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    for name in ("h16", "cfg1"):
+    for name, kpm in (("h16", ""), ("cfg1", ""), ("h16", "kpm"), ("cfg1", "kpm")):
         res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                              "--master-port", "29643", os.path.join(ROOT, "tools", "shard_worker.py"), name, "2", "0"],
+                              "--master-port", "29643", os.path.join(ROOT, "tools", "shard_worker.py"), name, "2", "0", kpm],
                              env=env, capture_output=True, text=True, timeout=900)
         assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
         out = json.loads([l for l in res.stdout.splitlines() if l.startswith("{")][-1])
@@ -125,3 +161,5 @@ def test_two_gpu_sharded_chain():
         assert out["accept_one_gpu"] == out["accept_sharded"], out
         assert out["max_abs_dx"] < 1e-3 * max(1.0, out["x_scale"]), out
         assert all(abs(a - b) <= 1.0 for a, b in zip(out["avg_iters_one_gpu"], out["avg_iters_sharded"])), out
+        if kpm:
+            assert out["stats_sharded"]["cg_slab_preconditioned"] > 0, out

@@ -17,6 +17,7 @@ dist.init_process_group("gloo")
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
 ntraj = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 nwarm = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+use_kpm = len(sys.argv) > 4 and sys.argv[4] == "kpm"
 m = mdl.config(name)
 L = lib.load()
 
@@ -31,12 +32,13 @@ def chain(sharded):
     if sharded:
         fdm.init_sharded_solve(dist)
     hmc = api.EFAPFFHMCUpdater(elph, pff, Nt=bench.NT, seed=77)
+    P = api.KPMPreconditioner(fdm, update=False) if use_kpm else None
     log = []
 
     def trajectory():
         acc = C.c_int(0)
         info = np.zeros(8)
-        lib.check(L.sq_hmc_update(hmc.h, None, bench.TOL_ACTION, bench.TOL_FORCE, bench.MAXITER, None, 0, C.byref(acc), lib.ptr(info)))
+        lib.check(L.sq_hmc_update(hmc.h, P.h if P is not None else None, bench.TOL_ACTION, bench.TOL_FORCE, bench.MAXITER, None, 0, C.byref(acc), lib.ptr(info)))
         log.append((bool(acc.value), float(info[0])))
     for _ in range(nwarm):
         trajectory()
@@ -49,8 +51,11 @@ def chain(sharded):
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     x = elph.x.copy()
-    tuning = fdm.tuning
-    hmc.close(); pff.close(); elph.close(); fdm.close()
+    tuning = dict(fdm.tuning, stats=fdm.stats)
+    hmc.close(); pff.close(); elph.close()
+    if P is not None:
+        P.close()
+    fdm.close()
     return x, log, ntraj / float(dt.item()), tuning
 
 
@@ -64,5 +69,5 @@ if rank == 0:
                       "max_abs_dx": float(np.abs(xs - x1).max()), "x_scale": float(np.abs(x1).max()),
                       "accept_one_gpu": [a for a, _ in log1], "accept_sharded": [a for a, _ in logs],
                       "avg_iters_one_gpu": [i for _, i in log1], "avg_iters_sharded": [i for _, i in logs],
-                      "ranks_bit_identical": len(set(digests)) == 1}))
+                      "ranks_bit_identical": len(set(digests)) == 1, "kpm": use_kpm, "stats_sharded": tuns["stats"]}))
 dist.destroy_process_group()

@@ -65,6 +65,19 @@ if check:
     _, itr5, _ = ref.cg(b, tol=1e-6, maxiter=50000)
     _, itg5, _ = fdm.ldiv(b, tol=1e-6, maxiter=50000)
     out["iters"] = [int(itr5), int(itg5)]
+    # preconditioned solve: P^-1 sharded by Matsubara frequency, two all-to-all exchanges per apply (slab.cu, kpm_ldiv_slab)
+    Pr = orc.RefKPM(ref)
+    Pr.update(np.random.default_rng(5).standard_normal(m.N))
+    if Pr.active:
+        Pg = api.KPMPreconditioner(fdm, update=False)
+        Pg.set_bounds(*Pr.bounds)
+        xr, itr, _ = ref.cg(b, P=Pr, tol=1e-13, maxiter=5000)
+        xg, itg, epsg = fdm.ldiv(b, preconditioner=Pg, tol=1e-13, maxiter=5000, refresh=False)
+        out["err_cg_kpm"] = rel(gather(xg), xr)
+        _, itr5, _ = ref.cg(b, P=Pr, tol=1e-6, maxiter=5000)
+        _, itg5, _ = fdm.ldiv(b, preconditioner=Pg, tol=1e-6, maxiter=5000, refresh=False)
+        out["iters_kpm"] = [int(itr5), int(itg5)]
+        out["stats"] = fdm.stats
 # throughput: fixed number of CG iterations on device-resident vectors
 n = m.N * m.Ltau
 d_b = torch.randn(n, 2, dtype=torch.float64, device="cuda"); d_x = torch.zeros_like(d_b)
@@ -76,6 +89,19 @@ torch.cuda.synchronize()
 dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
 out["cg_us_per_iter"] = float(dt.item()) / niter * 1e6
+# preconditioned iterations (frequency-sharded apply)
+Pt = api.KPMPreconditioner(fdm, update=False)
+act, _ = Pt.update(np.random.default_rng(6).standard_normal(m.N))
+if act:
+    nk = 20
+    fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, preconditioner=Pt, tol=1e-300, maxiter=4)
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    fdm.cg_dev(d_x.data_ptr(), d_b.data_ptr(), True, preconditioner=Pt, tol=1e-300, maxiter=nk)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    out["cg_kpm_us_per_iter"] = float(dt.item()) / nk * 1e6
 out["resident"] = os.environ.get("SQ_SLAB_MAILBOX", "1") != "0" and not os.environ.get("SQ_NO_RESIDENT_CG")
 out["slab"] = [lo, hi]
 out["tuning"] = fdm.tuning
