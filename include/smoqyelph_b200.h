@@ -69,6 +69,12 @@ int sq_fdm_mul(sq_fdm *f, int op, sq_complex *out, const sq_complex *in);
  * start; lanczos_start == NULL draws it from the library's Philox stream. */
 int sq_fdm_cg(sq_fdm *f, sq_complex *x, const sq_complex *b, int zero_start, sq_kpm *kpm, int refresh_kpm,
               const double *lanczos_start, double tol, int64_t maxiter, int64_t *iters, double *eps);
+/* nrhs systems M^T M x_j = b_j at once (X, B: (Ltau N) x nrhs column-major, like the GR / Rt arrays of the GreensEstimator): the loop
+ * over random vectors of update_greens_estimator! (src/Measurements/GreensEstimator.jl:152-169) as ONE lock-step solve.  Every system keeps
+ * its own scalars, convergence test and iteration count (iters[j], eps[j]) -- the recurrence per system is ldiv!'s.  With an active
+ * preconditioner on one GPU all kernels are batched over the systems; otherwise the systems are solved one by one. */
+int sq_fdm_cg_batch(sq_fdm *f, sq_complex *X, const sq_complex *B, int64_t nrhs, int zero_start, sq_kpm *kpm, int refresh_kpm,
+                    const double *lanczos_start, double tol, int64_t maxiter, int64_t *iters, double *eps);
 /* read back expnΔτV (Ltau x N), coshΔτt, sinhΔτt (Ltau x Nh) in the reference's layout (tests) */
 int sq_fdm_get_coefficients(sq_fdm *f, double *expV, double *cosh_t, double *sinh_t);
 /* device-resident variants (internal layout, no host sync) */

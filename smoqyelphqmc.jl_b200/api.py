@@ -96,6 +96,22 @@ class FermionDetMatrix:
                                self.maxiter if maxiter is None else int(maxiter), C.byref(it), C.byref(eps)))
         return x, it.value, eps.value
 
+    def ldiv_batch(self, B, X0=None, preconditioner=None, tol=None, maxiter=None, lanczos_start=None, refresh=True):
+        """nrhs systems at once: B (V, nrhs) complex Fortran (the GreensEstimator's layout) -> (X, iters[nrhs], eps[nrhs]).  Same recurrence,
+        warm start (X0) and iteration count per system as ldiv; batched over the systems when a preconditioner is active."""
+        V = self.model.Ltau * self.model.N
+        B = np.asfortranarray(B, np.complex128)
+        assert B.shape[0] == V
+        nrhs = B.shape[1]
+        zero = X0 is None
+        X = np.zeros((V, nrhs), np.complex128, order="F") if zero else np.array(X0, np.complex128, order="F", copy=True)
+        it, eps = np.zeros(nrhs, np.int64), np.zeros(nrhs)
+        ls = None if lanczos_start is None else _f64(lanczos_start)
+        check(self.L.sq_fdm_cg_batch(self.h, ptr(X), ptr(B), nrhs, int(zero), preconditioner.h if preconditioner is not None else None,
+                                     int(refresh and preconditioner is not None), ptr(ls), self.tol if tol is None else tol,
+                                     self.maxiter if maxiter is None else int(maxiter), ptr(it), ptr(eps)))
+        return X, it, eps
+
     def coefficients(self):
         m = self.model
         e = np.zeros((m.Ltau, m.N), order="F")

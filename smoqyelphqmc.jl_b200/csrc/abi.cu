@@ -26,7 +26,6 @@ void fdm_get_coefficients_impl(sq_fdm *f, double *expV, double *ch, double *sh);
 void fdm_mul_impl(sq_fdm *f, int op, void *out, const void *in);
 void fdm_select_tuning(sq_fdm *f);
 bool fdm_v3_supported(const sq_fdm *f, int S);
-int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native);
 void fdm_v3_prepare_native(sq_fdm *f);
 void slab_unique_id(char *out128);
 void slab_init(sq_fdm *f, int rank, int world, const char *id128);
@@ -290,6 +289,29 @@ int sq_fdm_cg(sq_fdm *f, sq_complex *x, const sq_complex *b, int zero_start, sq_
     fdm_dev_to_host(f, x, dx);
     *iters = it;
     *eps = e;
+    SQ_CATCH
+}
+int sq_fdm_cg_batch(sq_fdm *f, sq_complex *X, const sq_complex *B, int64_t nrhs, int zero_start, sq_kpm *kpm, int refresh_kpm,
+                    const double *lanczos_start, double tol, int64_t maxiter, int64_t *iters, double *eps) {
+    SQ_TRY
+    SQ_REQUIRE(f && X && B && iters && eps && nrhs >= 1 && nrhs <= 64, "bad argument");
+    SQ_CUDA(cudaSetDevice(f->device));
+    if (kpm && refresh_kpm) kpm_update(kpm, lanczos_start, nullptr);
+    const size_t V = (size_t)f->L * f->N;
+    DevBuf<double2> dX, dB;
+    dX.alloc(V * nrhs, false);
+    dB.alloc(V * nrhs, false);
+    for (int64_t j = 0; j < nrhs; j++) {
+        fdm_host_to_dev(f, dB.p + j * V, (const char *)B + j * V * sizeof(double2));
+        if (!zero_start) fdm_host_to_dev(f, dX.p + j * V, (const char *)X + j * V * sizeof(double2));
+    }
+    if (fdm_cg_batch_applicable(f, kpm, (int)nrhs)) {
+        fdm_cg_batch_dev(f, dX.p, dB.p, (int)nrhs, zero_start != 0, kpm, tol, maxiter, iters, eps);
+    } else {                                              // one by one (no active preconditioner, a single system, tau-slab mode)
+        for (int64_t j = 0; j < nrhs; j++) fdm_cg_dev(f, dX.p + j * V, dB.p + j * V, zero_start != 0, kpm, tol, maxiter, iters + j, eps + j);
+    }
+    for (int64_t j = 0; j < nrhs; j++) fdm_dev_to_host(f, (char *)X + j * V * sizeof(double2), dX.p + j * V);
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
     SQ_CATCH
 }
 int sq_fdm_cg_dev(sq_fdm *f, void *d_x, const void *d_b, int zero_start, sq_kpm *kpm, double tol, int64_t maxiter,

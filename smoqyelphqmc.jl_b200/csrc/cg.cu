@@ -205,7 +205,6 @@ bool fdm_v3_supported(const sq_fdm *f, int S);
 int fdm_v3_launch_cg(sq_fdm *f, double2 *z, const double2 *p_old, double2 *p_new, const double2 *d, const CgState *cur, CgState *nxt,
                      const double *rr_part, int nrr, const double *beta_part, int nbeta, int beta_complex, int iter, int check,
                      double *pAp_part, bool native);
-int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native);
 void fdm_v3_prepare_native(sq_fdm *f);
 bool fdm_v3_cg_resident(sq_fdm *f, double2 *x, double2 *r, CgState *state, i64 maxiter);
 void fdm_v3_to_native(sq_fdm *f, double2 *dst, const double2 *src);

@@ -367,7 +367,6 @@ void fdm_v2_launch(sq_fdm *f, int mode, int S, int T, double2 *out, const double
 int fdm_v2_tx(const sq_fdm *f);
 void fdm_v3_detect(sq_fdm *f);
 bool fdm_v3_supported(const sq_fdm *f, int S);
-int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native = false);
 
 KParams sq_fdm::kparams(int S, int T) const {
     KParams P;

@@ -44,6 +44,8 @@ struct V3Params {
     const double *expVn;    // native order (NAT kernels)
     const double2 *ctn;     // (cosh, tanh) per colour, prepared with expVn (the in-kernel divisions were 18 % of the stall samples)
     long long *dbg;         // optional clock stamps of warp 1 of CTA 0 (profiling aid, NULL in production)
+    size_t bstride;         // batch of vectors (blockIdx.z): elements between consecutive vectors
+    int bpart;              // ... doubles between their p.Ap partials
     // CG fusion, same meaning as K2Params (fdm_v2.cu)
     const double2 *cg_d;
     double2 *cg_pnew;
@@ -283,6 +285,12 @@ k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const do
     extern __shared__ __align__(128) double wsm[];      // [S][NP][32] double2 (this CTA's part); TMA: [S + 1] of those + [S + 1][N] diagonal factors
     __shared__ __align__(8) unsigned long long mbar[8];
     __shared__ double red[32];
+    if (!FUSE && gridDim.z > 1) {                       // multi-RHS batch: one vector, one set of partials and one solver state per blockIdx.z
+        in += (size_t)blockIdx.z * P.bstride;
+        out += (size_t)blockIdx.z * P.bstride;
+        if (pAp_part) pAp_part += (size_t)blockIdx.z * P.bpart;
+        if (skip) skip += blockIdx.z;
+    }
     if (skip && skip->done) {
         if (FUSE && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.cg_nxt = *skip;
         return;
@@ -584,9 +592,11 @@ struct CgFuse3 {
 static const CgFuse3 *g_fuse3 = nullptr;
 
 // returns the number of CTAs (= p.Ap partials for mode 2)
-int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native) {
+int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native, int nbatch,
+                  size_t bstride, int bpart) {
     V3Params P;
     memset(&P, 0, sizeof(P));
+    P.bstride = bstride; P.bpart = bpart;
     if (g_fuse3) {
         P.cg_d = g_fuse3->d; P.cg_pnew = g_fuse3->pnew; P.cg_cur = g_fuse3->cur; P.cg_nxt = g_fuse3->nxt;
         P.cg_rr_part = g_fuse3->rr_part; P.cg_beta_part = g_fuse3->beta_part; P.cg_nrr = g_fuse3->nrr; P.cg_nbeta = g_fuse3->nbeta;
@@ -623,7 +633,7 @@ int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, d
         smem = (size_t)2 * (S + 1) * f->N * sizeof(double);
     }
     v3_kernel_t k = f->v3_kind == 1 ? pick3h(f->v3_lxl, f->v3_ry, kmode) : pick3(f->v3_lxl, f->v3_ry, kmode);
-    k<<<dim3(grid, 2), 32 * (S + 1), smem, f->stream>>>(P, out, in, part, skip);
+    k<<<dim3(grid, 2, nbatch), 32 * (S + 1), smem, f->stream>>>(P, out, in, part, skip);
     SQ_LAUNCH_CHECK();
     f->launches++;
     return 2 * grid;

@@ -130,9 +130,14 @@ __device__ __forceinline__ void stockham_pass_generic(const double2 *__restrict_
 __global__ void k_tau_fft(const FftPlan plan, double2 *__restrict__ out, const double2 *__restrict__ in, int N, int SB, int inverse,
                           int twist, const double2 *tw, const double2 *__restrict__ theta,
                           const double *__restrict__ scale1, const double2 *__restrict__ dot_with, double *__restrict__ dot_part,
-                          const CgState *__restrict__ skip) {
+                          const CgState *__restrict__ skip, size_t bstride) {
     extern __shared__ double2 sm[];
     __shared__ double red[2 * 32];
+    // batch of vectors (multi-RHS solves): blockIdx.y selects the vector, its partial sums and its solver state
+    in += (size_t)blockIdx.y * bstride;
+    out += (size_t)blockIdx.y * bstride;
+    if (dot_with) { dot_with += (size_t)blockIdx.y * bstride; dot_part += (size_t)blockIdx.y * 2 * SQ_MAXPART; }
+    if (skip) skip += blockIdx.y;
     if (skip && skip->done) return;
     const int L = plan.L;
     double2 *bufA = sm, *bufB = sm + (size_t)L * SB;
@@ -212,9 +217,18 @@ __global__ void k_tau_fft(const FftPlan plan, double2 *__restrict__ out, const d
 
 // Launch helper shared by the preconditioner (complex [l][i] vectors) and the EFA (phonon fields [l][p]).
 // Returns the number of CTAs (= number of dot partials when dot_with != NULL).
+int tau_fft_launch_batch(cudaStream_t stream, const std::vector<int> &radices, int L, int N, double2 *out, const double2 *in, bool inverse,
+                         bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
+                         double *dot_part, const CgState *skip, size_t smem_limit, int nbatch, size_t bstride);
 int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, int N, double2 *out, const double2 *in, bool inverse,
                    bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
                    double *dot_part, const CgState *skip, size_t smem_limit) {
+    return tau_fft_launch_batch(stream, radices, L, N, out, in, inverse, twist, tw, theta, scale1, dot_with, dot_part, skip, smem_limit, 1, 0);
+}
+// nbatch vectors, bstride elements apart (dot_with likewise; dot_part 2 SQ_MAXPART doubles apart; skip[] one state per vector)
+int tau_fft_launch_batch(cudaStream_t stream, const std::vector<int> &radices, int L, int N, double2 *out, const double2 *in, bool inverse,
+                         bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
+                         double *dot_part, const CgState *skip, size_t smem_limit, int nbatch, size_t bstride) {
     FftPlan plan;
     plan.L = L;
     plan.nrad = (int)radices.size();
@@ -223,7 +237,7 @@ int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, 
     int SB = 8;
     while (SB > 1 && (size_t)(2 * SB + 1) * L * sizeof(double2) > smem_limit) SB >>= 1;
     // prefer more CTAs when the lattice is small
-    while (SB > 2 && (N + SB - 1) / SB < 148) SB >>= 1;
+    while (SB > 2 && (size_t)nbatch * ((N + SB - 1) / SB) < 148) SB >>= 1;
     size_t smem = (size_t)(2 * SB + 1) * L * sizeof(double2);
     if (smem > smem_limit) throw SqError("imaginary-time axis too long for the shared-memory FFT");
     static bool attr = false;
@@ -244,8 +258,8 @@ int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, 
         int Ns = 1;
         for (int s = 0; s < plan.nrad; s++) { plan.tws[s] = L / (Ns * plan.rad[s]); Ns *= plan.rad[s]; }
     }
-    k_tau_fft<<<grid, threads, smem, stream>>>(plan, out, in, N, SB, inverse ? 1 : 0, twist ? 1 : 0, tw, theta, scale1, dot_with,
-                                               dot_part, skip);
+    k_tau_fft<<<dim3(grid, nbatch), threads, smem, stream>>>(plan, out, in, N, SB, inverse ? 1 : 0, twist ? 1 : 0, tw, theta, scale1, dot_with,
+                                                             dot_part, skip, bstride);
     SQ_LAUNCH_CHECK();
     return grid;
 }

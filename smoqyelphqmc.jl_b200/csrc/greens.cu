@@ -95,6 +95,16 @@ double greens_update_impl(sq_greens *g, sq_kpm *kpm, const void *h_R, double tol
     }
     if (kpm) kpm_update(kpm, nullptr, nullptr);                            // GreensEstimator.jl:150
     double avg = 0;
+    if (fdm_cg_batch_applicable(f, kpm, (int)g->Nrv)) {
+        // all Nrv systems in lock step (cg_batch.cu): the same recurrence, warm start and iteration count per system as the loop below
+        if (g->MtRb.n < V * g->Nrv) g->MtRb.alloc(V * g->Nrv, false);
+        for (i64 n = 0; n < g->Nrv; n++) fdm_mul_dev(f, SQ_OP_MT, g->MtRb.p + n * V, g->R.p + n * V);
+        std::vector<i64> its(g->Nrv);
+        std::vector<double> epss(g->Nrv);
+        fdm_cg_batch_dev(f, g->GR.p, g->MtRb.p, (int)g->Nrv, false, kpm, tol, maxiter, its.data(), epss.data());
+        for (i64 n = 0; n < g->Nrv; n++) avg += (double)its[n];
+        return avg / (double)g->Nrv;
+    }
     for (i64 n = 0; n < g->Nrv; n++) {
         fdm_mul_dev(f, SQ_OP_MT, g->MtR.p, g->R.p + n * V);                 // :156
         i64 it = 0;

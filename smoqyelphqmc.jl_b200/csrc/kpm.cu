@@ -667,6 +667,21 @@ void kpm_cheb_apply(sq_kpm *k, double2 *z, const int *d_sched, int nsched, int n
     }
 }
 
+// out_j = P^-1 in_j for nrhs vectors `stride` elements apart (active preconditioner): forward tau-FFT (order-1 frequencies folded in),
+// Chebyshev recurrences, inverse tau-FFT with the partials of conj(dot_with_j).out_j (2 SQ_MAXPART doubles per vector) if requested.
+// zt: frequency-space scratch of the same shape.  skip[j].done skips vector j.  *npart = partials per vector.
+void kpm_fft_cheb_batch(sq_kpm *k, double2 *out, const double2 *in, double2 *zt, int nrhs, size_t stride, const CgState *skip,
+                        const double2 *dot_with, double *dot_part, int *npart) {
+    sq_fdm *f = k->f;
+    tau_fft_launch_batch(f->stream, k->radices, (int)f->L, (int)f->N, zt, in, false, true, k->tw.p, k->theta.p, k->d_scale1.p, nullptr, nullptr,
+                         skip, f->smem_optin, nrhs, stride);
+    kpm_cheb_apply(k, zt, k->d_freq_sched.p, k->nsched, nrhs, stride, skip);
+    const int g = tau_fft_launch_batch(f->stream, k->radices, (int)f->L, (int)f->N, out, zt, true, true, k->tw.p, k->theta.p, nullptr, dot_with,
+                                       dot_part, skip, f->smem_optin, nrhs, stride);
+    f->launches += 2;
+    if (npart) *npart = g;
+}
+
 // out = P^-1 in  on device [l][i] vectors (out may alias in).  dot partial fusion is requested by cg.cu.
 int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *skip, const double2 *dot_with, double *dot_part) {
     sq_fdm *f = k->f;
@@ -675,13 +690,8 @@ int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *
         if (out != in) SQ_CUDA(cudaMemcpyAsync(out, in, n * sizeof(double2), cudaMemcpyDeviceToDevice, f->stream));
         return 0;
     }
-    double2 *zt = k->ztmp.p;
-    tau_fft_launch(f->stream, k->radices, (int)f->L, (int)f->N, zt, in, false, true, k->tw.p, k->theta.p, k->d_scale1.p, nullptr, nullptr,
-                   skip, f->smem_optin);
-    kpm_cheb_apply(k, zt, k->d_freq_sched.p, k->nsched, 1, 0, skip);
-    int g = tau_fft_launch(f->stream, k->radices, (int)f->L, (int)f->N, out, zt, true, true, k->tw.p, k->theta.p, nullptr, dot_with,
-                           dot_part, skip, f->smem_optin);
-    f->launches += 2;
+    int g = 0;
+    kpm_fft_cheb_batch(k, out, in, k->ztmp.p, 1, 0, skip, dot_with, dot_part, &g);
     return g;
 }
 void kpm_ldiv_dev(sq_kpm *k, double2 *out, const double2 *in, const CgState *skip) { kpm_ldiv_dev_dot(k, out, in, skip, nullptr, nullptr); }

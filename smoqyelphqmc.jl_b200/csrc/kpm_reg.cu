@@ -367,7 +367,15 @@ void kpm_cheb_reg_launch(sq_kpm *k, double2 *z, const int *d_sched, int nsched, 
     P.avg = 0.5 * (k->bounds[1] + k->bounds[0]);
     P.imag_ = 2.0 / (k->bounds[1] - k->bounds[0]);
     P.skip = skip;
-    const int grid = std::min(P.nchain, f->num_sms);
+    // one CTA per SM while the chains are few (the long ones get an SM to themselves: latency is what counts); a batch of right-hand
+    // sides has ~10x more chains than SMs, there the FP64 pipes are the limit and several chains share an SM
+    int grid = std::min(P.nchain, f->num_sms);
+    if (P.nchain > 2 * f->num_sms) {
+        int occ = 1;
+        SQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void *)pk.k, pk.threads, 0));
+        if (const char *e = getenv("SQ_KPM_REG_OCC")) occ = std::max(1, atoi(e));
+        grid = std::min(P.nchain, f->num_sms * std::max(1, std::min(occ, 4)));
+    }
     pk.k<<<grid, pk.threads, 0, f->stream>>>(P);
     SQ_LAUNCH_CHECK();
     f->launches++;

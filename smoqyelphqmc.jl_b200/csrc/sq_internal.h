@@ -93,6 +93,12 @@ struct sq_fdm {
     DevBuf<double> iod1, iod2;               // real staging
     DevBuf<double> part;                     // 8 * SQ_MAXPART partial sums
     DevBuf<CgState> cg;                      // 2 states
+    // multi-RHS solver workspace (cg_batch.cu), nrhs vectors each, allocated on first use
+    DevBuf<double2> bt_r, bt_p, bt_z, bt_q, bt_zt;
+    DevBuf<CgState> bt_st;
+    DevBuf<double> bt_part;
+    DevBuf<unsigned> bt_ticket;
+    int bt_cap = 0;
     DevBuf<double2> prec_q;                  // M^T M p of the preconditioned solver when the p update is fused into the matvec (lazy)
     DevBuf<unsigned> cg_ticket;              // arrival counter of the last-block convergence test (zero between launches)
     CgState *h_cg = nullptr;                 // pinned
@@ -225,6 +231,7 @@ struct sq_greens {
     i64 Nrv = 0;
     uint64_t seed = 0, counter = 0;
     DevBuf<double2> R, GR, MtR;              // Nrv vectors, [l][i] each
+    DevBuf<double2> MtRb;                    // M^T R of all vectors (batched solve)
     DevBuf<double2> wa, wb, wc, wt;          // work arrays of the correlation measurements (2 Ltau x cells)
     DevBuf<double> wreal;                    // weights of the local measurements
     DevBuf<double2> wcplx;
@@ -276,6 +283,18 @@ int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, 
 void rng_fill_normal(double *d_out, size_t n, uint64_t seed, uint64_t stream, cudaStream_t s);
 void rng_fill_uniform(double *d_out, size_t n, uint64_t seed, uint64_t stream, cudaStream_t s);
 void fdm_select_tuning(sq_fdm *f);
+// register-path fused kernels (fdm_v3.cu); nbatch > 1: a batch of vectors bstride elements apart (p.Ap partials bpart doubles apart,
+// one CgState per vector in skip[])
+int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native = false,
+                  int nbatch = 1, size_t bstride = 0, int bpart = 0);
+bool fdm_v3_supported(const sq_fdm *f, int S);
+int tau_fft_launch_batch(cudaStream_t stream, const std::vector<int> &radices, int L, int N, double2 *out, const double2 *in, bool inverse,
+                         bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
+                         double *dot_part, const CgState *skip, size_t smem_limit, int nbatch, size_t bstride);
+// multi-RHS preconditioned CG (cg_batch.cu): nrhs systems M^T M x_j = b_j, vectors V elements apart
+void fdm_cg_batch_dev(sq_fdm *f, double2 *X, const double2 *B, int nrhs, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter, i64 *iters,
+                      double *eps);
+bool fdm_cg_batch_applicable(const sq_fdm *f, const sq_kpm *kpm, int nrhs);
 void fdm_sync_if_alive(sq_fdm *f);       // stream-synchronise f if it has not been destroyed yet, else the device
 void fdm_halo_exchange(sq_fdm *f, double2 *v);
 void fdm_allreduce_sum(sq_fdm *f, double *d_buf, int count);

@@ -29,6 +29,7 @@ SIGNATURES = {
     "sq_fdm_update": [vp, vp, vp, f64],
     "sq_fdm_mul": [vp, i32, vp, vp],
     "sq_fdm_cg": [vp, vp, vp, i32, vp, i32, vp, f64, i64, vp, vp],
+    "sq_fdm_cg_batch": [vp, vp, vp, i64, i32, vp, i32, vp, f64, i64, vp, vp],
     "sq_fdm_get_coefficients": [vp, vp, vp, vp],
     "sq_fdm_mul_dev": [vp, i32, vp, vp],
     "sq_fdm_cg_dev": [vp, vp, vp, i32, vp, f64, i64, vp, vp],

@@ -196,3 +196,77 @@ def test_inactive_preconditioner_is_identity():
     assert not act
     v = rand_cvec(rng, m)
     assert np.array_equal(Pg.ldiv(v), v)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg3", "sq16x16", "hc8"])
+def test_batched_multi_rhs_solve_matches_one_by_one(name, monkeypatch):
+    """Multi-RHS preconditioned CG (cg_batch.cu): every system of the batch reproduces the one-by-one solve -- solution, iteration
+    count (exactly: same recurrence per system) -- and the oracle's preconditioned CG (iterations +-1), including warm starts and
+    systems that converge at different iterations."""
+    from smoqyelph_b200 import api
+    m = REG_LATTICES[name]() if name in REG_LATTICES else mdl.config(name)
+    rng, ref, fdm = setup(m, True)
+    Pr = orc.RefKPM(ref)
+    Pg = api.KPMPreconditioner(fdm, update=False)
+    Pr.update(rng.standard_normal(m.N))
+    assert Pr.active
+    Pg.set_bounds(*Pr.bounds)
+    V, nrhs = m.N * m.Ltau, 5
+    B = np.asfortranarray(rng.standard_normal((V, nrhs)) + 1j * rng.standard_normal((V, nrhs)))
+    B[:, 1] *= 1e-3                                  # different scales / difficulty: the systems stop at different iterations
+    B[:, 3] = ref.mul_MtM(B[:, 0].reshape(m.Ltau, m.N, order="F")).ravel(order="F")
+    for tol in (1e-5, 1e-10):
+        st0 = fdm.stats
+        X, its, epss = fdm.ldiv_batch(B, preconditioner=Pg, tol=tol, maxiter=5000, refresh=False)
+        assert fdm.stats["cg_batched_rhs"] == st0["cg_batched_rhs"] + nrhs
+        for j in range(nrhs):
+            bj = B[:, j].reshape(m.Ltau, m.N, order="F")
+            x1, it1, eps1 = fdm.ldiv(bj, preconditioner=Pg, tol=tol, maxiter=5000, refresh=False)
+            assert its[j] == it1, (name, tol, j, its[j], it1)
+            assert relerr(X[:, j].reshape(m.Ltau, m.N, order="F"), x1) < 1e-12
+            assert abs(epss[j] - eps1) <= 1e-3 * tol
+            _, itr, _ = ref.cg(bj, P=Pr, tol=tol, maxiter=5000)
+            assert abs(its[j] - itr) <= 1
+    # warm start: from the solution nothing is left to do; from a perturbed solution a few iterations
+    X2, its2, _ = fdm.ldiv_batch(B, X0=X, preconditioner=Pg, tol=1e-9, maxiter=5000, refresh=False)
+    assert np.all(its2 == 0) and np.array_equal(X2, X)
+    X3, its3, _ = fdm.ldiv_batch(B, X0=X * (1 + 1e-4), preconditioner=Pg, tol=1e-10, maxiter=5000, refresh=False)
+    assert np.all(its3 > 0) and relerr(X3, X) < 1e-8
+    # maxiter cut-off and the fall-back without a preconditioner
+    _, itc, epsc = fdm.ldiv_batch(B, preconditioner=Pg, tol=1e-14, maxiter=2, refresh=False)
+    assert np.all(itc == 2) and np.all(epsc > 1e-14)
+    Xp, itp, _ = fdm.ldiv_batch(B[:, :2], tol=1e-8, maxiter=20000)
+    for j in range(2):
+        x1, it1, _ = fdm.ldiv(B[:, j].reshape(m.Ltau, m.N, order="F"), tol=1e-8, maxiter=20000)
+        assert itp[j] == it1 and relerr(Xp[:, j].reshape(m.Ltau, m.N, order="F"), x1) < 1e-12
+
+
+def test_greens_estimator_batched_update_matches_sequential(monkeypatch):
+    """update_greens_estimator! with a preconditioner runs the Nrv solves as one batch: same G R and average iteration count as the
+    one-by-one loop (SQ_NO_BATCH_CG=1), warm-start semantics included."""
+    from smoqyelph_b200 import api
+    m = REG_LATTICES["sq16x16"]()
+    rng, ref, fdm = setup(m, True)
+    P = api.KPMPreconditioner(fdm, update=False)
+    act, _ = P.update(rng.standard_normal(m.N))      # fixes the bounds: later refreshes stay inside the rbuf / 2 hysteresis
+    assert act
+    Nrv, V = 6, m.N * m.Ltau
+    R = rng.standard_normal((V, Nrv)) + 1j * rng.standard_normal((V, Nrv))
+    R = np.asfortranarray(R / np.abs(R))
+    res = {}
+    for mode in ("batch", "seq"):
+        if mode == "seq":
+            monkeypatch.setenv("SQ_NO_BATCH_CG", "1")
+        g = api.GreensEstimator(fdm, Nrv=Nrv, seed=1)
+        st0 = fdm.stats
+        a1 = g.update_greens_estimator(preconditioner=P, R=R, tol=1e-10, maxiter=5000)
+        a2 = g.update_greens_estimator(preconditioner=P, R=R, tol=1e-12, maxiter=5000)      # warm start from the previous G R
+        res[mode] = (a1, a2, g.get()[1], fdm.stats["cg_batched_rhs"] - st0["cg_batched_rhs"])
+    assert res["batch"][3] == 2 * Nrv and res["seq"][3] == 0
+    assert res["batch"][0] == res["seq"][0] and res["batch"][1] == res["seq"][1]
+    assert relerr(res["batch"][2], res["seq"][2]) < 1e-12
+    GRr = np.zeros((V, Nrv), np.complex128, order="F")
+    Pr = orc.RefKPM(ref)
+    Pr.update(rng.standard_normal(m.N))
+    orc.greens_update(ref, Pr, R, GRr, 1e-12, 5000)
+    assert relerr(res["batch"][2], GRr) < 1e-9
