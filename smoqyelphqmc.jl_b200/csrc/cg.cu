@@ -235,13 +235,15 @@ static int vec_grid(const sq_fdm *f, size_t n, int threads) {
 void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter,
                 i64 *iters, double *eps) {
     const bool kpm_on = kpm != nullptr && kpm->active;
-    if (f->sharded && (!kpm_on || (f->world > 1 && !getenv("SQ_SHARD_KPM_LOCAL")))) {
+    if (f->force_local) {
+        // (a rank of a sharded chain solving one of the distributed right-hand sides on its own: fall through to the single-GPU solvers)
+    } else if (f->sharded && (!kpm_on || (f->world > 1 && !getenv("SQ_SHARD_KPM_LOCAL")))) {
         // one chain over several GPUs: partitioned solve, solution gathered on every rank.  With an active preconditioner the apply is
         // sharded by Matsubara frequency (two all-to-all exchanges, slab.cu); SQ_SHARD_KPM_LOCAL=1 keeps such solves local and replicated
         fdm_cg_sharded(f, x, b, zero_start, kpm_on ? kpm : nullptr, tol, maxiter, iters, eps);
         return;
     }
-    if ((f->world > 1 && !f->sharded) || f->slab_lo != 0 || f->slab_hi != (int)f->L || getenv("SQ_FORCE_SLAB_CG")) {
+    if (!f->force_local && ((f->world > 1 && !f->sharded) || f->slab_lo != 0 || f->slab_hi != (int)f->L || getenv("SQ_FORCE_SLAB_CG"))) {
         fdm_cg_slab(f, x, b, zero_start, kpm_on ? kpm : nullptr, tol, maxiter, iters, eps);
         return;
     }

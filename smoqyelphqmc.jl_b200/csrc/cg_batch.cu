@@ -156,7 +156,8 @@ static int mul_batch(sq_fdm *f, double2 *out, const double2 *in, int nrhs, size_
 
 bool fdm_cg_batch_applicable(const sq_fdm *f, const sq_kpm *kpm, int nrhs) {
     if (getenv("SQ_NO_BATCH_CG")) return false;
-    return nrhs > 1 && kpm != nullptr && kpm->active && f->world == 1 && !f->sharded && f->slab_lo == 0 && f->slab_hi == (int)f->L;
+    const bool local = f->force_local || (f->world == 1 && !f->sharded);
+    return nrhs > 1 && kpm != nullptr && kpm->active && local && f->slab_lo == 0 && f->slab_hi == (int)f->L;
 }
 
 void fdm_cg_batch_dev(sq_fdm *f, double2 *X, const double2 *B, int nrhs, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter, i64 *iters,

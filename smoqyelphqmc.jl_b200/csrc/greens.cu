@@ -95,6 +95,41 @@ double greens_update_impl(sq_greens *g, sq_kpm *kpm, const void *h_R, double tol
     }
     if (kpm) kpm_update(kpm, nullptr, nullptr);                            // GreensEstimator.jl:150
     double avg = 0;
+    if (f->sharded && f->world > 1 && !getenv("SQ_GREENS_NO_RHS_SPLIT")) {
+        // One chain over several GPUs: the Nrv systems are independent, so they are DISTRIBUTED over the ranks (column j on rank
+        // j % world, solved there on the full lattice with the single-GPU solvers -- batched if preconditioned) instead of
+        // tau-slab partitioning each of them; the solutions are then broadcast.  Every rank holds the same R (same seed) and the
+        // same previous G R (warm start), and ends with the same G R.
+        const int W = f->world, me = f->rank;
+        std::vector<i64> mine;
+        for (i64 n = 0; n < g->Nrv; n++) if (n % W == me) mine.push_back(n);
+        const int nm = (int)mine.size();
+        if (g->MtRb.n < V * g->Nrv) g->MtRb.alloc(V * g->Nrv, false);
+        if (g->Xb.n < V * g->Nrv) g->Xb.alloc(V * g->Nrv, false);
+        for (int q = 0; q < nm; q++) {
+            fdm_mul_dev(f, SQ_OP_MT, g->MtRb.p + (size_t)q * V, g->R.p + mine[q] * V);
+            SQ_CUDA(cudaMemcpyAsync(g->Xb.p + (size_t)q * V, g->GR.p + mine[q] * V, V * sizeof(double2), cudaMemcpyDeviceToDevice, f->stream));
+        }
+        std::vector<i64> its(std::max(nm, 1), 0);
+        std::vector<double> epss(std::max(nm, 1), 0.0);
+        f->force_local = 1;
+        try {
+            if (nm > 0 && fdm_cg_batch_applicable(f, kpm, nm)) fdm_cg_batch_dev(f, g->Xb.p, g->MtRb.p, nm, false, kpm, tol, maxiter, its.data(), epss.data());
+            else for (int q = 0; q < nm; q++) fdm_cg_dev(f, g->Xb.p + (size_t)q * V, g->MtRb.p + (size_t)q * V, false, kpm, tol, maxiter, &its[q], &epss[q]);
+        } catch (...) { f->force_local = 0; throw; }
+        f->force_local = 0;
+        double sum = 0;
+        for (int q = 0; q < nm; q++) {
+            SQ_CUDA(cudaMemcpyAsync(g->GR.p + mine[q] * V, g->Xb.p + (size_t)q * V, V * sizeof(double2), cudaMemcpyDeviceToDevice, f->stream));
+            sum += (double)its[q];
+        }
+        slab_broadcast_columns(f, g->GR.p, V, (int)g->Nrv);
+        SQ_CUDA(cudaMemcpyAsync(f->scal.p, &sum, sizeof(double), cudaMemcpyHostToDevice, f->stream));
+        fdm_allreduce_sum(f, f->scal.p, 1);
+        SQ_CUDA(cudaMemcpyAsync(&sum, f->scal.p, sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+        SQ_CUDA(cudaStreamSynchronize(f->stream));
+        return sum / (double)g->Nrv;
+    }
     if (fdm_cg_batch_applicable(f, kpm, (int)g->Nrv)) {
         // all Nrv systems in lock step (cg_batch.cu): the same recurrence, warm start and iteration count per system as the loop below
         if (g->MtRb.n < V * g->Nrv) g->MtRb.alloc(V * g->Nrv, false);

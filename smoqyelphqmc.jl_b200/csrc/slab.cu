@@ -157,6 +157,17 @@ void fdm_cg_sharded(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq
     }
 }
 
+// column j of `cols` (V elements each) is valid on rank j % world: make all columns valid everywhere
+void slab_broadcast_columns(sq_fdm *f, double2 *cols, size_t V, int ncols) {
+    if (f->world <= 1) return;
+    SQ_NCCL(g_nccl.GroupStart());
+    for (int j = 0; j < ncols; j++) {
+        double2 *c = cols + (size_t)j * V;
+        SQ_NCCL(g_nccl.Broadcast(c, c, V * 2, ncclDouble, j % f->world, (ncclComm_t)f->comm, f->stream));
+    }
+    SQ_NCCL(g_nccl.GroupEnd());
+}
+
 // ---- mailboxes of the multi-GPU resident CG: one buffer per rank, mapped into every peer through CUDA IPC -------------------
 size_t fdm_v3_mailbox_bytes(const sq_fdm *f);
 void slab_mailbox_create(sq_fdm *f, char *out64) {

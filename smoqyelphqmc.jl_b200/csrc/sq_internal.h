@@ -128,6 +128,7 @@ struct sq_fdm {
     // "sharded solve" mode (one Markov chain over several GPUs): every rank keeps the full state and runs everything but the CG
     // solves redundantly; a solve is partitioned into tau-slabs [shard_lo, shard_hi) and its solution all-gathered (slab.cu)
     int sharded = 0, shard_lo = 0, shard_hi = 0;
+    int force_local = 0;                     // sharded chain: solve on this rank alone (right-hand sides distributed over the ranks, greens.cu)
     int tuned_shard[3][6] = {{0}, {0}, {0}};   // tuning cache of the slab range while the full range is active (and vice versa)
 
     KParams kparams(int S, int T) const;
@@ -231,7 +232,7 @@ struct sq_greens {
     i64 Nrv = 0;
     uint64_t seed = 0, counter = 0;
     DevBuf<double2> R, GR, MtR;              // Nrv vectors, [l][i] each
-    DevBuf<double2> MtRb;                    // M^T R of all vectors (batched solve)
+    DevBuf<double2> MtRb, Xb;                // M^T R (and, in a sharded chain, the start vectors) of the systems solved as a batch
     DevBuf<double2> wa, wb, wc, wt;          // work arrays of the correlation measurements (2 Ltau x cells)
     DevBuf<double> wreal;                    // weights of the local measurements
     DevBuf<double2> wcplx;
@@ -301,5 +302,6 @@ void fdm_allreduce_sum(sq_fdm *f, double *d_buf, int count);
 void fdm_cg_slab(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter, i64 *iters, double *eps);
 void fdm_cg_sharded(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter, i64 *iters, double *eps);
 void slab_set_sharded(sq_fdm *f, int enable);
+void slab_broadcast_columns(sq_fdm *f, double2 *cols, size_t V, int ncols);    // column j from rank j % world (grouped ncclBroadcast)
 void fft_radices(i64 n, std::vector<int> &rad);
 void fft_make_twiddles(i64 n, std::vector<double2> &tw);

@@ -163,3 +163,8 @@ def test_two_gpu_sharded_chain():
         assert all(abs(a - b) <= 1.0 for a, b in zip(out["avg_iters_one_gpu"], out["avg_iters_sharded"])), out
         if kpm:
             assert out["stats_sharded"]["cg_slab_preconditioned"] > 0, out
+        # measurement solves distributed over the ranks: identical G R everywhere, the single-GPU iteration count and density
+        gr = out["greens"]
+        assert gr["ranks_bit_identical"], out
+        assert abs(gr["iters_one_gpu"] - gr["iters_sharded"]) <= 1.0, out
+        assert abs(gr["n_one_gpu"] - gr["n_sharded"]) < 1e-6, out

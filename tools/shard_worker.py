@@ -51,7 +51,18 @@ def chain(sharded):
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     x = elph.x.copy()
-    tuning = dict(fdm.tuning, stats=fdm.stats)
+    # measurement solves: in the sharded chain the Nrv systems are distributed over the ranks (greens.cu)
+    g = api.GreensEstimator(fdm, Nrv=5, seed=3)
+    torch.cuda.synchronize(); dist.barrier()
+    tg = time.perf_counter()
+    git = g.update_greens_estimator(preconditioner=P, tol=1e-10)
+    torch.cuda.synchronize()
+    tg = torch.tensor([time.perf_counter() - tg], dtype=torch.float64)
+    dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+    GR = g.get()[1].copy()
+    greens = {"iters": float(git), "seconds": float(tg.item()), "GR": GR, "n": complex(g.measure()["n"]).real}
+    g.close()
+    tuning = dict(fdm.tuning, stats=fdm.stats, greens=greens)
     hmc.close(); pff.close(); elph.close()
     if P is not None:
         P.close()
@@ -63,11 +74,18 @@ x1, log1, rate1, tun1 = chain(False)
 xs, logs, rates, tuns = chain(True)
 digests = [None] * world
 dist.all_gather_object(digests, hashlib.sha256(np.ascontiguousarray(xs).tobytes()).hexdigest())
+g1, gs = tun1.pop("greens"), tuns.pop("greens")
+gd = [None] * world
+dist.all_gather_object(gd, hashlib.sha256(np.ascontiguousarray(gs["GR"]).tobytes()).hexdigest())
+# (the two chains end in slightly different fields -- solver tolerance -- so G R is compared through the sharded chain's own operator:
+#  rank-to-rank identity, the iteration count and the density it yields)
+greens_out = {"ranks_bit_identical": len(set(gd)) == 1, "iters_one_gpu": g1["iters"], "iters_sharded": gs["iters"],
+              "n_one_gpu": g1["n"], "n_sharded": gs["n"], "seconds_one_gpu": g1["seconds"], "seconds_sharded": gs["seconds"]}
 if rank == 0:
     print(json.dumps({"config": name, "world": world, "trajectories": ntraj,
                       "trajectories_per_s_one_gpu": rate1, "trajectories_per_s_sharded": rates, "speedup": rates / rate1,
                       "max_abs_dx": float(np.abs(xs - x1).max()), "x_scale": float(np.abs(x1).max()),
                       "accept_one_gpu": [a for a, _ in log1], "accept_sharded": [a for a, _ in logs],
                       "avg_iters_one_gpu": [i for _, i in log1], "avg_iters_sharded": [i for _, i in logs],
-                      "ranks_bit_identical": len(set(digests)) == 1, "kpm": use_kpm, "stats_sharded": tuns["stats"]}))
+                      "ranks_bit_identical": len(set(digests)) == 1, "kpm": use_kpm, "stats_sharded": tuns["stats"], "greens": greens_out}))
 dist.destroy_process_group()
