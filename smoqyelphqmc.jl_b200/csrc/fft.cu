@@ -127,7 +127,7 @@ __device__ __forceinline__ void stockham_pass_generic(const double2 *__restrict_
 // inverse: out[l][i] = conj(theta_l)/sqrt(L) * sum_n e^{+2 pi i n l/L} in[n][i]
 // scale1 (may be NULL) folds the order-1 ("scalar") frequencies of the preconditioner into the store.
 // dot_with (may be NULL): per-CTA partial sums of conj(dot_with).out (re, im) -> the CG r.z dot product.
-__global__ void k_tau_fft(const FftPlan plan, double2 *__restrict__ out, const double2 *__restrict__ in, int N, int SB, int inverse,
+__global__ void __launch_bounds__(256, 2) k_tau_fft(const FftPlan plan, double2 *__restrict__ out, const double2 *__restrict__ in, int N, int SB, int inverse,
                           int twist, const double2 *tw, const double2 *__restrict__ theta,
                           const double *__restrict__ scale1, const double2 *__restrict__ dot_with, double *__restrict__ dot_part,
                           const CgState *__restrict__ skip, size_t bstride) {
@@ -243,14 +243,16 @@ int tau_fft_launch_batch(cudaStream_t stream, const std::vector<int> &radices, i
     static bool attr = false;
     if (!attr) {
         SQ_CUDA(cudaFuncSetAttribute(k_tau_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit));
+        SQ_CUDA(cudaFuncSetAttribute(k_tau_fft, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
     int grid = (N + SB - 1) / SB;
     if (dot_with && grid > SQ_MAXPART) throw SqError("lattice too large for the FFT partial-sum buffer");
     if (const char *e = getenv("SQ_FFT_SB")) { int v = atoi(e); if (v >= 1 && (size_t)(2 * v + 1) * L * sizeof(double2) <= smem_limit) { SB = v; smem = (size_t)(2 * SB + 1) * L * sizeof(double2); grid = (N + SB - 1) / SB; } }
-    // one butterfly per thread in the radix-4 passes where possible (L SB / 4 butterflies), 128 ... 512 threads
-    int threads = std::min(512, std::max(128, ((L * SB / 4 + 31) / 32) * 32));
-    if (const char *e = getenv("SQ_FFT_T")) threads = atoi(e);
+    // 128 ... 256 threads: at ~90 registers per thread two CTAs of 256 threads share an SM, so the 256 CTAs of the named size run as ONE
+    // wave (416 threads = one butterfly per thread in the radix-4 passes meant one CTA per SM and two waves: ncu, profiles/r2_*fft*)
+    int threads = std::min(256, std::max(128, ((L * SB / 4 + 31) / 32) * 32));
+    if (const char *e = getenv("SQ_FFT_T")) threads = std::max(32, std::min(256, atoi(e)));
     plan.sbshift = 0;
     while ((1 << plan.sbshift) < SB) plan.sbshift++;
     if ((1 << plan.sbshift) != SB) throw SqError("FFT tile width must be a power of two");

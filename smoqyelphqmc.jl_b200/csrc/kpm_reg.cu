@@ -48,7 +48,7 @@ struct RegSquare {
     static constexpr int LXL = LXL_, W = W_, RY = 2, YH = 32 / LXL, LX = 4 * LXL, LY = RY * YH * W, N = LX * LY, NV = 4 * RY, NCOL = 4;
     static constexpr int XCH = 2 * W * 2 * LX;          // doubles of the exchange window: [buffer][warp][bottom / top row][x]
     int xl, yh, w, lane_r, lane_l, lane_u, lane_d;
-    double t[4];
+    double t[4], t2o;           // tanh per colour; doubled-angle tanh of the outer colour
 
     __device__ __forceinline__ void init(const ChebRegParams &P, double &g) {
         const int lane = threadIdx.x & 31;
@@ -66,6 +66,7 @@ struct RegSquare {
             t[c] = q.y / q.x;
             g *= q.x * q.x;
         }
+        t2o = 2.0 * t[3] / (1.0 + t[3] * t[3]);
     }
     // site of value k = 4 r + j
     __device__ __forceinline__ int site(int k) const { return 4 * xl + (k & 3) + LX * ((w * YH + yh) * RY + (k >> 2)); }
@@ -133,7 +134,7 @@ struct RegSquare {
 #pragma unroll
         for (int k = 0; k < NV; k++) v[k] *= dg[k];
         step<0>(v, xb); step<1>(v, xb); step<2>(v, xb);
-        step<3>(v, xb, 2.0 * t[3] / (1.0 + t[3] * t[3]));
+        step<3>(v, xb, t2o);
     }
     __device__ __forceinline__ void outer(double (&v)[NV], double *xb, double s) const { step<3>(v, xb, s); }
     static constexpr int XHALF = W * 2 * LX;
@@ -148,7 +149,7 @@ struct RegHoney {
     static constexpr int NP = R1 * R2, NV = 2 * NP, N = 2 * L1 * L2, NCOL = 3;
     static constexpr int XCH = 2 * W * 2 * L1;
     int g1, g2, w, lane_r, lane_l, lane_u, lane_d;
-    double t[3];
+    double t[3], t2o;
 
     __device__ __forceinline__ void init(const ChebRegParams &P, double &g) {
         const int lane = threadIdx.x & 31;
@@ -166,6 +167,7 @@ struct RegHoney {
             t[c] = q.y / q.x;
             g *= q.x * q.x;
         }
+        t2o = 2.0 * t[2] / (1.0 + t[2] * t[2]);
     }
     __device__ __forceinline__ int site(int k) const {
         const int u = k >> 1, a1 = u % R1, a2 = u / R1;
@@ -236,7 +238,7 @@ struct RegHoney {
 #pragma unroll
         for (int k = 0; k < NV; k++) v[k] *= dg[k];
         step<0>(v, xb); step<1>(v, xb);
-        step<2>(v, xb, 2.0 * t[2] / (1.0 + t[2] * t[2]));
+        step<2>(v, xb, t2o);
     }
     __device__ __forceinline__ void outer(double (&v)[NV], double *xb, double s) const { step<2>(v, xb, s); }
     static constexpr int XHALF = W * 2 * L1;
@@ -290,10 +292,14 @@ k_kpm_cheb_reg(const __grid_constant__ ChebRegParams P) {
             acc[k] = fma(c1, tb[k], c0 * ta[k]);
         }
         // two orders per trip, so that (u_{q-1}, u_q) swap roles without register moves
+        // the coefficients of a trip are loaded one trip ahead (an L2 hit costs as much as two colour steps)
         int q = 2;
+        double na = (q < ord) ? __ldg(&c[q].x) : 0.0, nb = (q + 1 < ord) ? __ldg(&c[q + 1].x) : 0.0;
 #pragma unroll 1
         for (; q + 1 < ord; q += 2) {
-            const double ca = __ldg(&c[q].x), cb = __ldg(&c[q + 1].x);
+            const double ca = na, cb = nb;
+            if (q + 2 < ord) na = __ldg(&c[q + 2].x);
+            if (q + 3 < ord) nb = __ldg(&c[q + 3].x);
 #pragma unroll
             for (int k = 0; k < NV; k++) y[k] = tb[k];
             E.apply(y, dg, XB());
@@ -311,7 +317,7 @@ k_kpm_cheb_reg(const __grid_constant__ ChebRegParams P) {
             }
         }
         if (q < ord) {
-            const double ca = __ldg(&c[q].x);
+            const double ca = na;
 #pragma unroll
             for (int k = 0; k < NV; k++) y[k] = tb[k];
             E.apply(y, dg, XB());

@@ -13,7 +13,7 @@ for name in names:
     fdm = api.FermionDetMatrix(m, sym=True)
     elph = api.ElectronPhononParameters(m, fdm)
     rng = np.random.default_rng(0)
-    elph.x = bench.cdw_start(m, 0) if (m.Nhol and len(m.lattice_dims) == 2 and m.N == m.lattice_dims[0] * m.lattice_dims[1]) else m.random_fields(rng, smooth=True)
+    elph.x = bench.bench_state(m)[0] if m.name == "cfg4" else bench.cdw_start(m, 0) if (m.Nhol and len(m.lattice_dims) == 2 and m.N == m.lattice_dims[0] * m.lattice_dims[1]) else m.random_fields(rng, smooth=True)
     elph.update_fdm()
     n = m.N * m.Ltau
     b = torch.randn(n, 2, dtype=torch.float64, device="cuda")

@@ -9,7 +9,7 @@ nit = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 m = mdl.config(name)
 fdm = api.FermionDetMatrix(m, sym=True)
 elph = api.ElectronPhononParameters(m, fdm)
-elph.x = bench.cdw_start(m, 0) if (m.Nhol and len(m.lattice_dims) == 2 and m.N == m.lattice_dims[0] * m.lattice_dims[1]) else m.random_fields(np.random.default_rng(0), smooth=True)
+elph.x = bench.bench_state(m)[0] if m.name == "cfg4" else bench.cdw_start(m, 0) if (m.Nhol and len(m.lattice_dims) == 2 and m.N == m.lattice_dims[0] * m.lattice_dims[1]) else m.random_fields(np.random.default_rng(0), smooth=True)
 elph.update_fdm()
 P = api.KPMPreconditioner(fdm)
 n = m.N * m.Ltau
