@@ -914,6 +914,14 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     int it = 0, done = 0;
     double v[G::NV], xr[G::NV], rr_[G::NV];
     if (threadIdx.x == 0) sh[5] = 0.0;
+#ifdef SQ_V3_STAMPS
+    // per-phase cycle counts of one owner warp (k = 1) and the halo warp (k = 0) of a CTA in the middle of the grid (profiling build only)
+    const bool stamp = P.dbg && !MULTI && bid == nblk / 2 && part == 0 && lane == 0 && (k == 0 || k == 1);
+    long long tph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tprev = stamp ? clock64() : 0;
+#define R1_STAMP(q) do { if (stamp) { const long long tn = clock64(); tph[q] += tn - tprev; tprev = tn; } } while (0)
+#else
+#define R1_STAMP(q) do { } while (0)
+#endif
     if (part == 0 && active) {
         const double2 *g = reinterpret_cast<const double2 *>(P.expVn + (size_t)lB * N);
         for (int e = lane; e < N / 2; e += 32) reinterpret_cast<double2 *>(EV + (size_t)k * N)[e] = __ldg(g + e);
@@ -951,6 +959,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
                     v[2 * u] = a.x; v[2 * u + 1] = a.y;
                 }
             E.template apply_B_ev<1, 1>(v, evk);
+            R1_STAMP(0);
             if (k == ns && it > 1) asm volatile("bar.sync %0, 64;" ::"r"(1 + part) : "memory");       // upper halo slice rebuilt by warp 0
 #pragma unroll
             for (int u = 0; u < NP; u++) {
@@ -963,9 +972,12 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
                         W[(size_t)k * (N / 2) + el(u)] = make_double2(w0, w1);
                     }
                 }
+            R1_STAMP(1);
         }
         if (owner) E.template apply_B_ev<1, 1>(v, evk);
+        R1_STAMP(2);
         __syncthreads();                                  // w of all slices is in W
+        R1_STAMP(3);
         if (owner) {                                      // z[lo] in registers; r.z, |z|^2, |r|^2; boundary z for the neighbours
             double2 *h0 = (k == 1) ? hslice((int)(itg & 1), bid, 0) : nullptr, *h1 = (k == ns) ? hslice((int)(itg & 1), bid, 1) : nullptr;
             if (MULTI) {                                  // the slab's outer boundaries go to the neighbour ranks' inboxes
@@ -985,6 +997,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
                     if (h1) h1[el(u)] = make_double2(z0, z1);
                 }
         }
+        R1_STAMP(4);
         // ---- the grid-wide sum of (a, b, c, d)
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -992,6 +1005,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
             if (lane == 0) red[c * 8 + wid] = t;
         }
         __syncthreads();
+        R1_STAMP(5);
         if (wid < 2) {                                    // warp 0: (a, b), warp 1: (c, d)
             const int nw = blockDim.x >> 5;
             double t[2];
@@ -1002,7 +1016,9 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
             else v3_slot_sum2(t, wid, C.slots + (size_t)(it & 1) * C.slot_array_bytes, C.slot_stride, (long long)(it & 3), nblk, bid, bad);
             if (lane == 0) { sh[2 * wid] = t[0]; sh[2 * wid + 1] = t[1]; if (bad) sh[5] = 1.0; }
         }
+        R1_STAMP(6);
         __syncthreads();
+        R1_STAMP(7);
         if (sh[5] != 0.0) { done = 3; break; }
         const double pAp = sh[0], rz = sh[1], zz = sh[2], rr_old = sh[3];
         const double alpha = rr_old / pAp;
@@ -1024,6 +1040,25 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
                     Pb[(size_t)k * (N / 2) + el(u)] = make_double2(fma(beta, pv.x, r0), fma(beta, pv.y, r1));
                 }
         }
+        // Warp 0 of each part owns no slice.  Right after the sum it fetches the neighbours' boundary z (published before the sum, so
+        // visible now) into registers -- its xr / rr_ registers, which only owners use: N / 64 double2 per lane = NV doubles -- so that
+        // the L2 round trip of the two 8 KB slices overlaps with the owners' update; the halo copies of r and p are rebuilt from them
+        // after the barrier below, overlapped with the owners' first B.  (Round 1 issued the loads after the barrier: the chain L2 load ->
+        // rebuild -> this warp's own B was then the longest of the CTA, on the critical path of every iteration.  Measured alternatives:
+        // the whole rebuild before the barrier 8.11 us, staging through shared memory with bulk async copies 7.73 us, this 7.45 us,
+        // round 1 7.95 us per iteration at cfg4.)
+        static_assert(G::NV == N / 32, "one warp holds one slice-part");
+        if (k == 0) {
+            const double2 *gu = hslice((int)(itg & 1), right, 0), *gl = hslice((int)(itg & 1), left, 1);
+            if (MULTI) {
+                if (bid == nblk - 1) gu = inbox(C.rank, (int)(itg & 1), 1);
+                if (bid == 0) gl = inbox(C.rank, (int)(itg & 1), 0);
+            }
+#pragma unroll
+            for (int u = 0; u < N / 64; u++) { const double2 q = __ldcg(gl + lane + 32 * u); xr[2 * u] = q.x; xr[2 * u + 1] = q.y; }
+#pragma unroll
+            for (int u = 0; u < N / 64; u++) { const double2 q = __ldcg(gu + lane + 32 * u); rr_[2 * u] = q.x; rr_[2 * u + 1] = q.y; }
+        }
         if (stop_est) {                                   // confirm with the exact |r_new|^2 (every CTA takes this branch together)
             bool aborted;
             const double rr_exact = MULTI ? v3_grid_sum_multi(chk, red, C.mail, C.world, C.rank, C.off_check, C.slot_stride, itg, gtot, gid, aborted)
@@ -1034,38 +1069,30 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
             if (!(eps == eps)) { done = 2; break; }
             if (it == C.maxiter) break;
         }
+        R1_STAMP(8);
         __syncthreads();                                  // own p slices are in Pb: the owners start the next B right away
+        R1_STAMP(9);
         if (k == 0) {
-            // warp 0 of each part owns no slice: it updates the copies of the neighbours' boundary r and p from their boundary z
-            // (visible since the sum) while the owners run their first B; upper slice first (handed to warp ns)
-            double2 zu[N / 64], zl[N / 64];
-            const double2 *gu = hslice((int)(itg & 1), right, 0), *gl = hslice((int)(itg & 1), left, 1);
-            if (MULTI) {
-                if (bid == nblk - 1) gu = inbox(C.rank, (int)(itg & 1), 1);
-                if (bid == 0) gl = inbox(C.rank, (int)(itg & 1), 0);
+            // r_h -= alpha z_h, p_h = r_h + beta p_h (the same fma's the owner executes): lower slice first (this warp's own B needs it),
+            // then the upper one, handed to warp ns through a named barrier
+#pragma unroll
+            for (int u = 0; u < N / 64; u++) {
+                const size_t e = lane + 32 * u;
+                const double2 rv = Rh[e], pv = Pb[e];
+                const double r0 = fma(-alpha, xr[2 * u], rv.x), r1 = fma(-alpha, xr[2 * u + 1], rv.y);
+                Rh[e] = make_double2(r0, r1);
+                Pb[e] = make_double2(fma(beta, pv.x, r0), fma(beta, pv.y, r1));
             }
-#pragma unroll
-            for (int u = 0; u < N / 64; u++) zu[u] = __ldcg(gu + lane + 32 * u);
-#pragma unroll
-            for (int u = 0; u < N / 64; u++) zl[u] = __ldcg(gl + lane + 32 * u);
 #pragma unroll
             for (int u = 0; u < N / 64; u++) {
                 const size_t e = lane + 32 * u;
                 const double2 rv = Rh[(size_t)1 * (N / 2) + e], pv = Pb[(size_t)(ns + 1) * (N / 2) + e];
-                const double r0 = fma(-alpha, zu[u].x, rv.x), r1 = fma(-alpha, zu[u].y, rv.y);
+                const double r0 = fma(-alpha, rr_[2 * u], rv.x), r1 = fma(-alpha, rr_[2 * u + 1], rv.y);
                 Rh[(size_t)1 * (N / 2) + e] = make_double2(r0, r1);
                 Pb[(size_t)(ns + 1) * (N / 2) + e] = make_double2(fma(beta, pv.x, r0), fma(beta, pv.y, r1));
             }
             __threadfence_block();
             asm volatile("bar.arrive %0, 64;" ::"r"(1 + part) : "memory");
-#pragma unroll
-            for (int u = 0; u < N / 64; u++) {
-                const size_t e = lane + 32 * u;
-                const double2 rv = Rh[e], pv = Pb[e];
-                const double r0 = fma(-alpha, zl[u].x, rv.x), r1 = fma(-alpha, zl[u].y, rv.y);
-                Rh[e] = make_double2(r0, r1);
-                Pb[e] = make_double2(fma(beta, pv.x, r0), fma(beta, pv.y, r1));
-            }
             __syncwarp();
         }
     }
@@ -1074,6 +1101,9 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
 #pragma unroll
         for (int u = 0; u < NP; u++) gx[el(u)] = make_double2(xr[2 * u], xr[2 * u + 1]);
     }
+#ifdef SQ_V3_STAMPS
+    if (stamp) { for (int q = 0; q < 10; q++) P.dbg[16 * k + q] = tph[q]; P.dbg[16 * k + 10] = it; }
+#endif
     if (bid == 0 && threadIdx.x == 0) {
         CgState st = *C.state;
         st.iters = it;
@@ -1141,9 +1171,32 @@ static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *stat
     C.x = (double *)x; C.r = (const double *)r; C.state = state;
     C.slots = f->v3_slots.p; C.slot_array_bytes = arr; C.slots_check = f->v3_slots.p + 2 * arr; C.slot_stride = stride_bytes;
     C.halo = f->v3_halo.p; C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
+#ifdef SQ_V3_STAMPS
+    static long long *dbg = nullptr;
+    if (!dbg && getenv("SQ_DEBUG_STAMPS")) {
+        SQ_CUDA(cudaMallocManaged((void **)&dbg, 64 * sizeof(long long)));
+        for (int q = 0; q < 64; q++) dbg[q] = 0;
+    }
+    P.dbg = dbg;
+#endif
     void *args[] = {(void *)&P, (void *)&C};
     SQ_CUDA(cudaLaunchCooperativeKernel((const void *)k, dim3(grid), dim3(T), args, smem, f->stream));
     f->launches++;
+#ifdef SQ_V3_STAMPS
+    if (dbg) {
+        cudaStreamSynchronize(f->stream);
+        static const char *names[10] = {"load p + B1", "halo wait + combine", "B2", "sync (w ready)", "z + dots + halo store", "warp sums + sync",
+                                        "grid-wide sum (warps 0/1) / idle", "sync (sum known)", "update x r p", "sync (p ready)"};
+        for (int w = 0; w < 2; w++) {
+            const double n = (double)std::max<long long>(dbg[16 * w + 10], 1);
+            double tot = 0;
+            for (int q = 0; q < 10; q++) tot += dbg[16 * w + q] / n;
+            fprintf(stderr, "resident1 stamps, CTA %d/%d warp k=%d (%s), %lld iterations, %.0f cycles/iteration:\n", grid / 2, grid, w,
+                    w ? "first owner" : "halo warp, sums", dbg[16 * w + 10], tot);
+            for (int q = 0; q < 10; q++) fprintf(stderr, "    %-36s %8.0f\n", names[q], dbg[16 * w + q] / n);
+        }
+    }
+#endif
     return true;
 }
 

@@ -15,7 +15,7 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libsmoqyelph_b200.so")
+LIB_PATH = os.environ.get("SMOQYELPH_B200_LIB") or os.path.join(_PKG, "libsmoqyelph_b200.so")     # (same override as the Julia shim)
 HEADER = os.path.join(_ROOT, "include", "smoqyelph_b200.h")
 
 i64, f64, vp, i32 = C.c_int64, C.c_double, C.c_void_p, C.c_int
