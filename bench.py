@@ -563,6 +563,17 @@ def run_native(args):
                   "traffic": state.get("mtm_dram_bytes_per_launch"),
                   "note": "back-to-back launches on this system are paced in ~2 us steps (profiles/README.md); a single-wave kernel of "
                           "~6 us cannot be timed below that from the host, which is why the solver is one resident launch"}
+        if path == 3:
+            # the same fused kernel on a batch of vectors at the named size (grid dimension z = vector; what a multi-RHS iteration
+            # launches): 10 x 16.4 MB leaves the 126 MB L2, so this is the kernel against HBM rather than against launch latency
+            batched = {}
+            for nb in (10, 20):
+                dbi = torch.randn(nb * n, 2, dtype=torch.float64, device=dev)
+                dbo = torch.zeros_like(dbi)
+                tb = fdm.time_mul(300 + nb, dbo.data_ptr(), dbi.data_ptr(), 30) * 1e-6
+                batched[f"n{nb}"] = {"vectors": nb, "us_per_launch": tb * 1e6, "achieved": nb * Bk / tb / 1e9, "frac": nb * Bk / tb / 1e9 / peak}
+                del dbi, dbo
+            matvec["batched_native_order"] = batched
         if resident:
             roofline = {"bound": "hbm", "kernel": "k_cg_v3_resident1 (whole CG solve in one launch; M^T M v once per iteration, x r p resident on chip)",
                         "achieved": Bk / t_iter / 1e9, "peak": peak, "unit": "GB/s", "frac": Bk / t_iter / 1e9 / peak,

@@ -180,8 +180,19 @@ int sq_fdm_time_mul(sq_fdm *f, int op, void *d_out, const void *d_in, int reps, 
         SQ_REQUIRE(f->path == 0 && f->use_v3 && fdm_v3_supported(f, f->v3_S), "register path not active");
         fdm_v3_prepare_native(f);
     }
+    // op 200 + n / 300 + n: the fused M^T M kernel of the register path on a BATCH of n vectors (V elements apart) in library / native
+    // order -- what the multi-RHS solver launches once per iteration (cg_batch.cu); d_in / d_out hold n vectors
+    const int nbatch = (op >= 300) ? op - 300 : ((op >= 200) ? op - 200 : 0);
+    const bool batch_native = op >= 300;
+    if (nbatch) {
+        SQ_REQUIRE(nbatch >= 1 && nbatch <= 64, "batch size out of range");
+        fdm_select_tuning(f);
+        SQ_REQUIRE(f->path == 0 && f->v3_ok && f->cs_coluni && fdm_v3_supported(f, f->v3_S), "register path not active");
+        if (batch_native) fdm_v3_prepare_native(f);
+    }
     auto fdm_mul_dev = [&](sq_fdm *ff, int o, double2 *out, const double2 *in) {
-        if (native) fdm_v3_launch(ff, 2, ff->v3_S, out, in, nullptr, nullptr, true);
+        if (nbatch) fdm_v3_launch(ff, 2, ff->v3_S, out, in, nullptr, nullptr, batch_native, nbatch, (size_t)ff->L * ff->N, 0);
+        else if (native) fdm_v3_launch(ff, 2, ff->v3_S, out, in, nullptr, nullptr, true);
         else ::fdm_mul_dev(ff, o, out, in);
     };
     for (int k = 0; k < 3; k++) fdm_mul_dev(f, op, (double2 *)d_out, (const double2 *)d_in);
