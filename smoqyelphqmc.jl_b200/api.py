@@ -693,8 +693,9 @@ def make_measurements(measurements, fdm, greens, *, mu=0.0, bosonic_action=None,
       "local"        the density part of make_local_measurements! (:120-146): density_up / density_dn / density / double_occ per orbital
       "correlations" one array per entry of `correlations`: ("greens", (a, b)), ("density", (a, b)), ("spin_z", (a, b)),
                      ("pair", (bond', bond'')), ("bond", (bond', bond'')), ("current", (bond', bond'', t', t'')) -- the calls of
-                     make_correlation_measurements! (:161-394); the caller divides by the number of calls, as the container's
-                     processing does."""
+                     make_correlation_measurements! (:161-394) -- and ("composite", (label, type, id_pairs, coefficients)), the linear
+                     combinations of make_composite_correlation_measurements! (:398-913); the caller divides by the number of calls, as
+                     the container's processing does."""
     iters = greens.update_greens_estimator(preconditioner=preconditioner, tol=tol, maxiter=maxiter)
     norb, dims = greens._geom(norb, dims)
     G = measurements.setdefault("global", {})
@@ -711,23 +712,34 @@ def make_measurements(measurements, fdm, greens, *, mu=0.0, bosonic_action=None,
         Lm["density_up"][a] += n; Lm["density_dn"][a] += n; Lm["density"][a] += 2 * n
         Lm["double_occ"][a] += greens.measure_double_occ_orbital(a, norb, dims)
     Cm = measurements.setdefault("correlations", {})
-    for name, args in correlations:
-        key = (name,) + tuple(repr(a) if isinstance(a, np.ndarray) else a for a in args[:2])
+
+    def one(name, args):
         if name == "greens":
-            val = greens.measure_GD0(tuple(args), norb=norb, dims=dims)
-        elif name == "density":
-            val = greens.measure_density_correlation(args[0], args[1], norb=norb, dims=dims)
-        elif name == "spin_z":
-            val = greens.measure_spin_correlation(args[0], args[1], norb=norb, dims=dims)
-        elif name == "pair":
-            val = greens.measure_pair_correlation(args[0], args[1], norb=norb, dims=dims)
-        elif name == "bond":
-            val = greens.measure_bond_correlation(args[0], args[1], norb=norb, dims=dims)
-        elif name == "current":
-            val = greens.measure_current_correlation(args[0], args[1], args[2], args[3], norb=norb, dims=dims)
-        else:
-            raise ValueError("unknown correlation " + str(name))
-        Cm[key] = Cm.get(key, 0.0) + val
+            return greens.measure_GD0(tuple(args), norb=norb, dims=dims)
+        if name == "density":
+            return greens.measure_density_correlation(args[0], args[1], norb=norb, dims=dims)
+        if name == "spin_z":
+            return greens.measure_spin_correlation(args[0], args[1], norb=norb, dims=dims)
+        if name == "pair":
+            return greens.measure_pair_correlation(args[0], args[1], norb=norb, dims=dims)
+        if name == "bond":
+            return greens.measure_bond_correlation(args[0], args[1], norb=norb, dims=dims)
+        if name == "current":
+            return greens.measure_current_correlation(args[0], args[1], args[2], args[3], norb=norb, dims=dims)
+        raise ValueError("unknown correlation " + str(name))
+
+    for name, args in correlations:
+        if name == "composite":
+            # make_composite_correlation_measurements! (make_measurements.jl:398-913): a named linear combination
+            # sum_k coefficient_k x correlation(id_pair_k) of one correlation type -- args = (label, type, id_pairs, coefficients)
+            label, ctype, pairs, coefs = args
+            if len(pairs) != len(coefs):
+                raise ValueError("composite correlation: one coefficient per id pair")
+            val = sum(c * one(ctype, pr) for pr, c in zip(pairs, coefs))
+            Cm[("composite", label)] = Cm.get(("composite", label), 0.0) + val
+            continue
+        key = (name,) + tuple(repr(a) if isinstance(a, np.ndarray) else a for a in args[:2])
+        Cm[key] = Cm.get(key, 0.0) + one(name, args)
     return iters
 
 

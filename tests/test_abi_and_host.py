@@ -236,7 +236,7 @@ def test_make_measurements_accumulates_like_the_reference_container():
 
     g = Stub()
     meas = {}
-    corr = [("greens", (0, 1)), ("density", (1, 1))]
+    corr = [("greens", (0, 1)), ("density", (1, 1)), ("composite", ("tr_greens", "greens", [(0, 0), (1, 1)], [1.0, -2.0]))]
     for k in range(3):
         it = api.make_measurements(meas, None, g, mu=0.3, bosonic_action=lambda: 2.0, correlations=corr)
         assert it == 7.5 and g.calls[2 * k] == "update" and g.calls[2 * k + 1] == "measure"
@@ -247,5 +247,6 @@ def test_make_measurements_accumulates_like_the_reference_container():
     assert np.allclose(L["density"], [3 * 0.8, 3 * 1.0]) and np.allclose(L["double_occ"], [0.3, 0.45]) and L["density_up"].shape == (2,)
     C = meas["correlations"]
     assert np.allclose(C[("greens", 0, 1)], 30.0) and np.allclose(C[("density", 1, 1)], 3.0)
+    assert np.allclose(C[("composite", "tr_greens")], 3 * (1.0 * 0.0 - 2.0 * 11.0))        # sum_k coefficient_k x G_(a_k, b_k)
     with pytest.raises(ValueError):
         api.make_measurements(meas, None, g, correlations=[("nonsense", (0, 0))])
