@@ -155,6 +155,12 @@ int sq_elph_create(sq_elph **out, sq_fdm *f, double dtau, int64_t Nph, const dou
  * FermionPathIntegral -- and be supplied here by the first call that does (hmc_update!, the global moves, update_chemical_potential!).
  * Only sq_elph_refresh_fdm / sq_elph_get_Vt need them; sample / action / force work on the operator state set by sq_fdm_update. */
 int sq_elph_set_bare(sq_elph *e, const double *V0, const double *t0);
+/* DispersionParameters of ElectronPhononParameters: disp_phonon (2 x Ndisp, 1-based) = dispersion_to_phonon, Omega / Omega4 per coupling.
+ * Enters bosonic_action (hmc_update! :136,238 and the global moves) and the kick through eval_derivative_dispersive_action!
+ * (src/EFAPFFHMCUpdater.jl:193).  Arithmetic un-vendored (SmoQyDQMC): restated from the published Hamiltonian, DESIGN.md section 2. */
+int sq_elph_set_dispersion(sq_elph *e, int64_t Ndisp, const int64_t *disp_phonon, const double *Omega, const double *Omega4);
+/* F (Nph x Ltau) = anharmonic + dispersive derivative of the bosonic action (the terms :190-193 add to the fermionic force; tests) */
+int sq_elph_potential_derivative(sq_elph *e, double *F);
 int sq_elph_destroy(sq_elph *e);
 int sq_elph_set_x(sq_elph *e, const double *x);          /* (Nph x Ltau) */
 int sq_elph_get_x(sq_elph *e, double *x);

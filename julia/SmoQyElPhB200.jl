@@ -170,8 +170,6 @@ function B200ElPh(elph::ElectronPhononParameters{T,E}, f::FermionDetMatrix{T,E})
     T <: Real || error("libsmoqyelph_b200 supports real hoppings / couplings only (T = $T)")
     ph = elph.phonon_parameters; hol = elph.holstein_parameters_up; ssh = elph.ssh_parameters_up
     disp = elph.dispersion_parameters
-    disp.Ndispersion == 0 || error("libsmoqyelph_b200: dispersive phonon couplings (Ndispersion = $(disp.Ndispersion)) are not implemented " *
-                                   "(bosonic action and eval_derivative_dispersive_action!, src/EFAPFFHMCUpdater.jl:193); use the CPU path for this model")
     (all(iszero, imag.(ssh.α)) && all(iszero, imag.(ssh.α2)) && all(iszero, imag.(ssh.α3)) && all(iszero, imag.(ssh.α4))) ||
         error("libsmoqyelph_b200: complex SSH couplings are not implemented")
     (elph.holstein_parameters_up === elph.holstein_parameters_dn || elph.holstein_parameters_up.α == elph.holstein_parameters_dn.α) ||
@@ -189,6 +187,10 @@ function B200ElPh(elph::ElectronPhononParameters{T,E}, f::FermionDetMatrix{T,E})
         real.(ssh.α3), real.(ssh.α4), C_NULL, C_NULL))
     e = B200ElPh(h[], false)
     finalizer(x -> ccall((:sq_elph_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), e)
+    if disp.Ndispersion > 0      # dispersive couplings: bosonic action + eval_derivative_dispersive_action! on the device (src/EFAPFFHMCUpdater.jl:193)
+        check(ccall((:sq_elph_set_dispersion, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{E}, Ptr{E}),
+                    e.h, disp.Ndispersion, Matrix{Int64}(disp.dispersion_to_phonon), Vector{E}(disp.Ω), Vector{E}(disp.Ω4)))
+    end
     _ELPH_OF_FDM[f.h] = WeakRef(e)
     return e
 end

@@ -82,6 +82,7 @@ def lib(omp=False):
         "ref_efa_init_momentum": (c_dbl, [c_vp, c_vp, c_vp, c_vp]), "ref_efa_kinetic": (c_dbl, [c_vp, c_vp, c_vp]),
         "ref_efa_evolve": (None, [c_vp, c_vp, c_vp, c_vp, c_dbl]),
         "ref_bosonic_action": (c_dbl, [c_vp]), "ref_anharmonic_derivative": (None, [c_vp, c_vp]),
+        "ref_dispersive_derivative": (None, [c_vp, c_vp]), "ref_elph_set_dispersion": (None, [c_vp, c_i64, c_vp, c_vp, c_vp]),
         "ref_hmc_update": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_i64, c_vp, c_vp]),
         "ref_greens_update": (c_dbl, [c_vp, c_vp, c_vp, c_vp, c_i64, c_dbl, c_i64]),
         "ref_measure_n": (None, [c_vp, c_vp, c_i64, c_i64, c_vp]),
@@ -256,6 +257,9 @@ class RefElPh:
                                         m.Nhol, _ptr(k[3]), _ptr(k[4]), _ptr(k[5]), _ptr(k[6]), _ptr(k[7]), _ptr(k[8]), _ptr(k[9]),
                                         m.Nssh, _ptr(k[10]), _ptr(k[11]), _ptr(k[12]), _ptr(k[13]), _ptr(k[14]), _ptr(k[15]),
                                         _ptr(k[16]), _ptr(k[17]))
+        if getattr(m, "Ndisp", 0):
+            dp, do, do4 = i64(m.disp_phonon.T), f64(m.disp_Omega), f64(m.disp_Omega4)
+            self.L.ref_elph_set_dispersion(self.h, m.Ndisp, _ptr(dp), _ptr(do), _ptr(do4))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -300,6 +304,13 @@ class RefElPh:
         return F
 
     def bosonic_action(self): return self.L.ref_bosonic_action(self.h)
+
+    def potential_derivative(self):
+        """Anharmonic + dispersive parts of dS_b/dx (the terms the leapfrog kick adds to the fermionic force, EFAPFFHMCUpdater.jl:190-193)."""
+        F = np.zeros((self.model.Nph, self.model.Ltau), order="F")
+        self.L.ref_anharmonic_derivative(_ptr(F), self.h)
+        self.L.ref_dispersive_derivative(_ptr(F), self.h)
+        return F
 
 
 class RefPFF:

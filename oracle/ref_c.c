@@ -643,6 +643,7 @@ typedef struct ref_elph {
     i64 Nssh; i64 *ssh_ph; i64 *ssh_hop; double *sa, *sa2, *sa3, *sa4;
     double *V0, *t0;              /* bare on-site energy minus mu (N), bare hopping (Nh, original order) */
     double *V, *t;                /* (N x L), (Nh x L) scratch = FermionPathIntegral.V / .t */
+    i64 Ndisp; i64 *disp_ph; double *disp_Om, *disp_Om4;   /* DispersionParameters: phonon pairs (2 x Ndisp), Ω, Ω4 per coupling */
 } ref_elph;
 
 static double *dupd(const double *a, i64 n) { double *r = (double *)calloc(n + 1, sizeof(double)); if (n) memcpy(r, a, sizeof(double) * n); return r; }
@@ -670,7 +671,8 @@ void ref_elph_destroy(ref_elph *e) {
     if (!e) return;
     free(e->x); free(e->Om); free(e->Om4); free(e->M); free(e->hol_ph); free(e->hol_site); free(e->ha); free(e->ha2);
     free(e->ha3); free(e->ha4); free(e->hol_sym); free(e->ssh_ph); free(e->ssh_hop); free(e->sa); free(e->sa2);
-    free(e->sa3); free(e->sa4); free(e->V0); free(e->t0); free(e->V); free(e->t); free(e);
+    free(e->sa3); free(e->sa4); free(e->V0); free(e->t0); free(e->V); free(e->t);
+    free(e->disp_ph); free(e->disp_Om); free(e->disp_Om4); free(e);
 }
 double *ref_elph_x(ref_elph *e) { return e->x; }
 double *ref_elph_V(ref_elph *e) { return e->V; }
@@ -991,7 +993,19 @@ void ref_efa_evolve(const ref_efa *a, const ref_elph *e, double *x, double *p, d
     for (i64 k = 0; k < L * Nph; k++) if (isfinite(e->M[k % Nph])) { x[k] = creal(xs[k]); p[k] = creal(ps[k]); }
     free(xs); free(ps);
 }
-/* bosonic_action(elph, holstein_correction=false) [unvendored]; dispersive couplings not modelled */
+/* DispersionParameters [unvendored: SmoQyDQMC; restated from the published Hamiltonian, arXiv:2311.09395 eq. for U_disp]:
+ *   U_disp = sum_d M''_d [ Ω_d^2 (X_p' - X_p)^2 / 2 + Ω4_d^2 (X_p' - X_p)^4 / 24 ],  M'' = M_p M_p' / (M_p + M_p') (reduced mass; one
+ *   infinite mass => the other one).  Phonon indices 0-based here. */
+void ref_elph_set_dispersion(ref_elph *e, i64 Ndisp, const i64 *disp_ph, const double *Om, const double *Om4) {
+    free(e->disp_ph); free(e->disp_Om); free(e->disp_Om4);
+    e->Ndisp = Ndisp; e->disp_ph = dupi(disp_ph, 2 * Ndisp); e->disp_Om = dupd(Om, Ndisp); e->disp_Om4 = dupd(Om4, Ndisp);
+}
+static double reduced_mass(double a, double b) {
+    if (!isfinite(a)) return b;
+    if (!isfinite(b)) return a;
+    return a * b / (a + b);
+}
+/* bosonic_action(elph, holstein_correction=false) [unvendored]: on-site harmonic + quartic, kinetic, dispersive */
 double ref_bosonic_action(const ref_elph *e) {
     i64 L = e->L, Nph = e->Nph; double S = 0;
     for (i64 l = 0; l < L; l++) for (i64 p = 0; p < Nph; p++) {
@@ -1000,7 +1014,27 @@ double ref_bosonic_action(const ref_elph *e) {
         S += e->dtau * e->M[p] * e->Om[p] * e->Om[p] * x * x / 2 + e->dtau * e->M[p] * e->Om4[p] * e->Om4[p] * x * x * x * x / 24
            + e->M[p] * d * d / (2 * e->dtau);
     }
+    for (i64 l = 0; l < L; l++) for (i64 c = 0; c < e->Ndisp; c++) {
+        i64 p = e->disp_ph[2 * c], pp = e->disp_ph[2 * c + 1];
+        double m = reduced_mass(e->M[p], e->M[pp]);
+        if (!isfinite(m)) continue;
+        double D = e->x[pp + l * Nph] - e->x[p + l * Nph];
+        S += e->dtau * m * e->disp_Om[c] * e->disp_Om[c] * D * D / 2 + e->dtau * m * e->disp_Om4[c] * e->disp_Om4[c] * D * D * D * D / 24;
+    }
     return S;
+}
+/* eval_derivative_dispersive_action! [unvendored] (src/EFAPFFHMCUpdater.jl:193): -= on the first phonon of the pair, += on the second */
+void ref_dispersive_derivative(double *F, const ref_elph *e) {
+    i64 L = e->L, Nph = e->Nph;
+    for (i64 l = 0; l < L; l++) for (i64 c = 0; c < e->Ndisp; c++) {
+        i64 p = e->disp_ph[2 * c], pp = e->disp_ph[2 * c + 1];
+        double m = reduced_mass(e->M[p], e->M[pp]);
+        if (!isfinite(m)) continue;
+        double D = e->x[pp + l * Nph] - e->x[p + l * Nph];
+        double g = e->dtau * m * (e->disp_Om[c] * e->disp_Om[c] * D + e->disp_Om4[c] * e->disp_Om4[c] * D * D * D / 6);
+        if (isfinite(e->M[pp])) F[pp + l * Nph] += g;
+        if (isfinite(e->M[p])) F[p + l * Nph] -= g;
+    }
 }
 /* eval_derivative_anharmonic_action! [unvendored] */
 void ref_anharmonic_derivative(double *F, const ref_elph *e) {
@@ -1045,6 +1079,7 @@ int ref_hmc_update(ref_elph *e, ref_fdm *f, ref_pff *q, ref_kpm *P, ref_efa *a, 
         if (P) rp += N;
         iters_avg += (double)iters / (double)(Nt + 1);
         ref_anharmonic_derivative(dS, e);                                         /* :190 */
+        ref_dispersive_derivative(dS, e);                                         /* :193 */
         for (i64 k = 0; k < nx; k++) p[k] -= dt * dS[k];                           /* :196 */
         ref_efa_evolve(a, e, e->x, p, t == Nt ? dt / 2 : dt);                      /* :200-205 */
         ref_elph_refresh(e, f);

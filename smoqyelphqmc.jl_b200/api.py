@@ -287,6 +287,9 @@ class ElectronPhononParameters:
                                     m.Nssh, ptr(k[10]), ptr(k[11]), ptr(k[12]), ptr(k[13]), ptr(k[14]), ptr(k[15]),
                                     ptr(k[16]), ptr(k[17])))
         self.h = h
+        if getattr(m, "Ndisp", 0):
+            dp, do, do4 = _i64(m.disp_phonon.T), _f64(m.disp_Omega), _f64(m.disp_Omega4)
+            check(self.L.sq_elph_set_dispersion(self.h, m.Ndisp, ptr(dp), ptr(do), ptr(do4)))
 
     def close(self):
         if getattr(self, "h", None):
@@ -319,6 +322,12 @@ class ElectronPhononParameters:
         t = np.zeros((m.Nh, m.Ltau), order="F")
         check(self.L.sq_elph_get_Vt(self.h, ptr(V), ptr(t)))
         return V, t
+
+    def potential_derivative(self):
+        """Anharmonic + dispersive parts of dS_b/dx (what the leapfrog kick adds to the fermionic force)."""
+        F = np.zeros((self.model.Nph, self.model.Ltau), order="F")
+        check(self.L.sq_elph_potential_derivative(self.h, ptr(F)))
+        return F
 
     def bosonic_action(self):
         s = C.c_double(0)

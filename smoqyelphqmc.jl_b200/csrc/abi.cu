@@ -432,6 +432,26 @@ int sq_elph_set_bare(sq_elph *e, const double *V0, const double *t0) {
     elph_set_bare(e, V0, t0);
     SQ_CATCH
 }
+int sq_elph_set_dispersion(sq_elph *e, int64_t Ndisp, const int64_t *disp_phonon, const double *Omega, const double *Omega4) {
+    SQ_TRY
+    SQ_REQUIRE(e, "NULL handle");
+    SQ_CUDA(cudaSetDevice(e->f->device));
+    elph_set_dispersion(e, Ndisp, disp_phonon, Omega, Omega4);
+    SQ_CATCH
+}
+int sq_elph_potential_derivative(sq_elph *e, double *F) {
+    SQ_TRY
+    SQ_REQUIRE(e && F, "NULL argument");
+    sq_fdm *f = e->f;
+    SQ_CUDA(cudaSetDevice(f->device));
+    const size_t nx = (size_t)f->L * e->Nph;
+    DevBuf<double> pm, z;
+    pm.alloc(nx); z.alloc(nx);                                  // p = 0, dS = 0:  p <- -1 * (anharmonic + dispersive)
+    elph_add_potential_derivative(e, pm.p, z.p, -1.0);
+    pm.download(F, nx, f->stream);
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
+    SQ_CATCH
+}
 int sq_elph_destroy(sq_elph *e) {
     SQ_TRY
     if (e) { fdm_sync_if_alive(e->f); delete e; }

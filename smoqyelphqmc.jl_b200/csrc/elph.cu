@@ -121,6 +121,48 @@ __global__ void k_bosonic_action(const double *__restrict__ x, const double *__r
     block_sum<1>(v, red);
     if (threadIdx.x == 0) part[blockIdx.x] = v[0];
 }
+// dispersive part of the bosonic action [unvendored, SmoQyDQMC DispersionParameters]:
+//   sum_{l, d} dtau M''_d [ Omega_d^2 D^2 / 2 + Omega4_d^2 D^4 / 24 ],  D = x[p'_d, l] - x[p_d, l];  k2 = M'' Omega^2, k4 = M'' Omega4^2
+__global__ void k_dispersive_action(const double *__restrict__ x, const int *__restrict__ dp, const int *__restrict__ dpp,
+                                    const double *__restrict__ k2, const double *__restrict__ k4, int L, int Nph, int Ndisp, double dtau,
+                                    double *__restrict__ part) {
+    __shared__ double red[32];
+    double acc = 0;
+    size_t tot = (size_t)L * Ndisp;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < tot; k += (size_t)gridDim.x * blockDim.x) {
+        int l = (int)(k / Ndisp), c = (int)(k - (size_t)l * Ndisp);
+        double D = x[(size_t)l * Nph + dpp[c]] - x[(size_t)l * Nph + dp[c]], D2 = D * D;
+        acc += dtau * k2[c] * D2 / 2 + dtau * k4[c] * D2 * D2 / 24;
+    }
+    double v[1] = {acc};
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = v[0];
+}
+// p <- p - dt (dS/dx + anharmonic + dispersive derivative);  EFAPFFHMCUpdater.jl:190-196.  The dispersive term is gathered per phonon
+// from its signed coupling list (fixed order, no floating-point atomics): eval_derivative_dispersive_action! [unvendored].
+__global__ void k_kick(double *__restrict__ pm, const double *__restrict__ dS, const double *__restrict__ x, const double *__restrict__ Om4,
+                       const double *__restrict__ M, const int *__restrict__ fin, int Nph, double dtau, double dt, size_t n, int Ndisp,
+                       const int *__restrict__ dp, const int *__restrict__ dpp, const double *__restrict__ k2, const double *__restrict__ k4,
+                       const int *__restrict__ dptr, const int *__restrict__ dcpl) {
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        int p = (int)(k % Nph);
+        size_t base = k - p;
+        double f = dS[k];
+        if (fin[p]) {
+            double xv = x[k];
+            f += dtau * M[p] * Om4[p] * Om4[p] * xv * xv * xv / 6;
+            if (Ndisp) {
+                for (int q = dptr[p]; q < dptr[p + 1]; q++) {
+                    int sc = dcpl[q], c = (sc > 0 ? sc : -sc) - 1;
+                    double D = x[base + dpp[c]] - x[base + dp[c]];
+                    double g = dtau * (k2[c] * D + k4[c] * D * D * D / 6);
+                    f += sc > 0 ? g : -g;
+                }
+            }
+        }
+        pm[k] -= dt * f;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------
 static ElphDev elph_dev(const sq_elph *e) {
@@ -172,6 +214,44 @@ void elph_set_bare(sq_elph *e, const double *V0, const double *t0) {
         for (int h = f->clo[c]; h < f->chi[c]; h++)
             if (t0[f->h_perm[h]] != t0[f->h_perm[f->clo[c]]]) { e->t0_coluni = false; break; }
     e->bare_set = true;
+}
+
+// DispersionParameters: disp_ph (2 x Ndisp) 1-based phonon pairs, Omega / Omega4 per coupling.  The reduced mass M'' = M M' / (M + M')
+// (one infinite mass: the other one; both infinite: the coupling carries no dynamics and is dropped) is folded into k2, k4.
+void elph_set_dispersion(sq_elph *e, i64 Ndisp, const i64 *disp_ph, const double *Om, const double *Om4) {
+    sq_fdm *f = e->f;
+    SQ_REQUIRE(Ndisp >= 0 && (Ndisp == 0 || (disp_ph && Om && Om4)), "bad dispersion tables");
+    const i64 Nph = e->Nph;
+    std::vector<int> dp, dpp;
+    std::vector<double> k2, k4;
+    for (i64 c = 0; c < Ndisp; c++) {
+        const i64 p = disp_ph[2 * c] - 1, pp = disp_ph[2 * c + 1] - 1;
+        SQ_REQUIRE(p >= 0 && p < Nph && pp >= 0 && pp < Nph && p != pp, "dispersive coupling map out of range");
+        const double a = e->h_M[p], b = e->h_M[pp];
+        const double m = !std::isfinite(a) ? b : (!std::isfinite(b) ? a : a * b / (a + b));
+        if (!std::isfinite(m)) continue;
+        dp.push_back((int)p); dpp.push_back((int)pp);
+        k2.push_back(m * Om[c] * Om[c]); k4.push_back(m * Om4[c] * Om4[c]);
+    }
+    e->Ndisp = (i64)dp.size();
+    std::vector<int> cnt(Nph + 1, 0);
+    for (size_t c = 0; c < dp.size(); c++) { cnt[dp[c] + 1]++; cnt[dpp[c] + 1]++; }
+    for (i64 p = 0; p < Nph; p++) cnt[p + 1] += cnt[p];
+    std::vector<int> items(2 * dp.size() + 1), fill(cnt.begin(), cnt.end() - 1);
+    for (size_t c = 0; c < dp.size(); c++) { items[fill[dp[c]]++] = -(int)(c + 1); items[fill[dpp[c]]++] = (int)(c + 1); }
+    cudaStream_t s = f->stream;
+    up(e->disp_p, dp, s); up(e->disp_pp, dpp, s); up(e->disp_k2, k2, s); up(e->disp_k4, k4, s);
+    up(e->ph_disp_ptr, cnt, s); up(e->ph_disp_cpl, items, s);
+}
+
+void elph_add_potential_derivative(sq_elph *e, double *pm, const double *dS, double dt) {
+    sq_fdm *f = e->f;
+    const size_t nx = (size_t)f->L * e->Nph;
+    const int g = std::min(SQ_MAXPART, f->num_sms * 4);
+    k_kick<<<g, 256, 0, f->stream>>>(pm, dS, e->x.p, e->Om4.p, e->M.p, e->fin.p, (int)e->Nph, e->dtau, dt, nx, (int)e->Ndisp, e->disp_p.p,
+                                     e->disp_pp.p, e->disp_k2.p, e->disp_k4.p, e->ph_disp_ptr.p, e->ph_disp_cpl.p);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
 }
 
 void elph_create_impl(sq_elph **out, sq_fdm *f, double dtau, i64 Nph, const double *Om, const double *Om4, const double *M, i64 Nhol,
@@ -292,5 +372,12 @@ double elph_bosonic_action(sq_elph *e) {
     k_bosonic_action<<<nb, 256, 0, f->stream>>>(e->x.p, e->Om.p, e->Om4.p, e->M.p, e->fin.p, (int)f->L, (int)e->Nph, e->dtau, f->part.p);
     SQ_LAUNCH_CHECK();
     f->launches++;
+    if (e->Ndisp > 0) {
+        k_dispersive_action<<<nb, 256, 0, f->stream>>>(e->x.p, e->disp_p.p, e->disp_pp.p, e->disp_k2.p, e->disp_k4.p, (int)f->L, (int)e->Nph,
+                                                      (int)e->Ndisp, e->dtau, f->part.p + nb);
+        SQ_LAUNCH_CHECK();
+        f->launches++;
+        return reduce_partials_host(f, f->part.p, nb) + reduce_partials_host(f, f->part.p + nb, nb);
+    }
     return reduce_partials_host(f, f->part.p, nb);
 }

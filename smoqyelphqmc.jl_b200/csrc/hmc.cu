@@ -77,17 +77,6 @@ __global__ void k_efa_momentum(double2 *__restrict__ zt, const double *__restric
     block_sum<1>(t, red);
     if (threadIdx.x == 0) part[blockIdx.x] = t[0];
 }
-// p <- p - dt (dS/dx + anharmonic);   EFAPFFHMCUpdater.jl:190-196
-__global__ void k_kick(double *__restrict__ pm, const double *__restrict__ dS, const double *__restrict__ x, const double *__restrict__ Om4,
-                       const double *__restrict__ M, const int *__restrict__ fin, int Nph, double dtau, double dt, size_t n) {
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
-        int p = (int)(k % Nph);
-        double f = dS[k];
-        if (fin[p]) { double xv = x[k]; f += dtau * M[p] * Om4[p] * Om4[p] * xv * xv * xv / 6; }
-        pm[k] -= dt * f;
-    }
-}
-
 static inline unsigned nblk(size_t n) { return (unsigned)((n + 255) / 256); }
 static int red_grid(const sq_fdm *f) { return std::min(SQ_MAXPART, f->num_sms * 4); }
 
@@ -234,9 +223,7 @@ int hmc_update_impl(sq_hmc *h, sq_kpm *kpm, double tol_action, double tol_force,
             pff_force_dev(q, kpm, kpm != nullptr, nullptr, kpm ? r_lan + (size_t)solve * N : nullptr, tol_force, maxiter, &it, &eps);   // :171
             solve++;
             iters_avg += (double)it / (double)(Nt + 1);
-            k_kick<<<red_grid(f), 256, 0, f->stream>>>(h->pm.p, q->F.p, e->x.p, e->Om4.p, e->M.p, e->fin.p, (int)Nph, e->dtau, dt, nx);   // :190-196
-            SQ_LAUNCH_CHECK();
-            f->launches++;
+            elph_add_potential_derivative(e, h->pm.p, q->F.p, dt);                          // :190-196 (anharmonic + dispersive + kick)
             hmc_evolve_dev(h, e->x.p, h->pm.p, t == Nt ? dt / 2 : dt);                      // :200-203
             elph_refresh_fdm(e);                                                            // :204-205
         }

@@ -191,6 +191,11 @@ struct sq_elph {
     DevBuf<int> bond_ptr, bond_cpl;          // CSR: checkerboard bond -> SSH couplings
     // force gather lists: phonon -> Holstein couplings, phonon -> signed SSH couplings (+-(c+1))
     DevBuf<int> ph_hol_ptr, ph_hol_cpl, ph_ssh_ptr, ph_ssh_cpl;
+    // dispersive phonon couplings (DispersionParameters): pair (p, p'), reduced mass x Omega^2 and x Omega4^2 per coupling, and the gather
+    // list phonon -> signed couplings (+-(c+1): + for the second phonon of the pair) of the derivative
+    i64 Ndisp = 0;
+    DevBuf<int> disp_p, disp_pp, ph_disp_ptr, ph_disp_cpl;
+    DevBuf<double> disp_k2, disp_k4;
     DevBuf<double> V0, t0;                   // bare on-site energy (N), bare hopping (Nh, ORIGINAL order)
     DevBuf<double> V, t;                     // materialised only by sq_elph_get_Vt: [l][i], [l][h] original order
     bool any_phsym = false;
@@ -273,6 +278,8 @@ void kpm_update(sq_kpm *k, const double *h_lanczos_start, const double *d_lanczo
 void kpm_set_bounds(sq_kpm *k, double emin, double emax);
 void elph_refresh_fdm(sq_elph *e);
 void elph_set_bare(sq_elph *e, const double *V0, const double *t0);
+void elph_set_dispersion(sq_elph *e, i64 Ndisp, const i64 *disp_ph, const double *Om, const double *Om4);
+void elph_add_potential_derivative(sq_elph *e, double *pm, const double *dS, double dt);   // p -= dt (dS + anharmonic + dispersive)
 double elph_bosonic_action(sq_elph *e);
 void elph_update_lambda(sq_elph *e, double *Lam);
 void elph_lambda_op(sq_elph *e, int which, double2 *out, const double2 *in, const double *Lam);

@@ -58,6 +58,8 @@ SIGNATURES = {
     "sq_kpm_fourier": [vp, vp, i32],
     "sq_elph_create": [pp, vp, f64, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp],
     "sq_elph_set_bare": [vp, vp, vp],
+    "sq_elph_set_dispersion": [vp, i64, vp, vp, vp],
+    "sq_elph_potential_derivative": [vp, vp],
     "sq_elph_destroy": [vp],
     "sq_elph_set_x": [vp, vp],
     "sq_elph_get_x": [vp, vp],

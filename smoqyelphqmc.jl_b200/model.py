@@ -39,6 +39,10 @@ class Model:
     ssh_phonon: np.ndarray = field(default_factory=lambda: np.zeros((2, 0), np.int64))
     ssh_hopping: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))
     ssh_alpha: np.ndarray = field(default_factory=lambda: np.zeros((4, 0)))
+    # dispersive phonon couplings (DispersionParameters): phonon pairs (2, Ndisp), frequencies per coupling
+    disp_phonon: np.ndarray = field(default_factory=lambda: np.zeros((2, 0), np.int64))
+    disp_Omega: np.ndarray = field(default_factory=lambda: np.zeros(0))
+    disp_Omega4: np.ndarray = field(default_factory=lambda: np.zeros(0))
     # checkerboard decomposition (filled by finalize)
     perm: np.ndarray | None = None          # checkerboard index -> original hopping index
     nt_chk: np.ndarray | None = None        # (2, Nh) permuted neighbour table
@@ -73,6 +77,10 @@ class Model:
     @property
     def Nssh(self) -> int:
         return self.ssh_hopping.shape[0]
+
+    @property
+    def Ndisp(self) -> int:
+        return self.disp_Omega.shape[0]
 
     def finalize(self, bond_colors=None) -> "Model":
         """Checkerboard decomposition: any colouring in which bonds of one colour share no site."""
@@ -251,6 +259,18 @@ def holstein_ssh_chain(n, beta, dtau=0.05, name=None):
               ssh_phonon=np.stack([i, (i + 1) % n]), ssh_hopping=i.copy(),
               ssh_alpha=np.stack([np.full(n, 0.4), np.full(n, 0.1), np.full(n, 0.03), np.full(n, 0.01)]), lattice_dims=(n,))
     return m.finalize(None)
+
+
+def with_dispersion(m: Model, Omega_d=0.5, Omega4_d=0.0) -> Model:
+    """Adds nearest-neighbour dispersive phonon couplings (SmoQyDQMC PhononDispersion: a spring between the phonons of the two ends
+    of every bond that carries a phonon on each site) to a Holstein-type model: one coupling per bond of the original neighbour table."""
+    ph_of_site = {int(s): int(p) for p, s in zip(m.hol_phonon, m.hol_site)}
+    pairs = [(ph_of_site[int(i)], ph_of_site[int(j)]) for i, j in m.neighbor_table.T if int(i) in ph_of_site and int(j) in ph_of_site]
+    m.disp_phonon = np.ascontiguousarray(np.array(pairs, np.int64).T.reshape(2, -1))
+    m.disp_Omega = np.full(len(pairs), float(Omega_d))
+    m.disp_Omega4 = np.full(len(pairs), float(Omega4_d))
+    m.name += "_disp"
+    return m
 
 
 def config(name: str) -> Model:

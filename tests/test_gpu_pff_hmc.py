@@ -31,6 +31,8 @@ MODELS = {
     "sq16": lambda: mdl.holstein_square(16, 16, 0.5),
     "sq32": lambda: mdl.holstein_square(32, 32, 0.3),
     "hc8": lambda: mdl.holstein_honeycomb(8, 0.4),
+    # dispersive phonon couplings (nearest-neighbour springs, quadratic + quartic) on top of a Holstein model with anharmonic on-site terms
+    "disp": lambda: mdl.with_dispersion(mdl.holstein_square(4, 4, 0.5, ph_sym=False), 0.8, 0.4),
 }
 REGISTER_PATH = ("sq16", "sq32", "hc8")
 
@@ -75,6 +77,10 @@ def test_refresh_and_lambda(name, sym):
     np.testing.assert_allclose(s, rf.sinh, rtol=1e-13, atol=1e-15)
     assert np.array_equal(ge.x, x)
     assert abs(ge.bosonic_action() - re.bosonic_action()) < 1e-12 * abs(re.bosonic_action())
+    Pr_, Pg_ = re.potential_derivative(), ge.potential_derivative()           # anharmonic + dispersive derivative of the kick
+    assert np.abs(Pg_ - Pr_).max() <= 1e-13 * max(1.0, np.abs(Pr_).max())
+    if name == "disp":
+        assert m.Ndisp == 32 and np.abs(Pr_).max() > 0
     Lam = re.Lambda()
     v = rand_cvec(rng, m)
     for which in ("mul", "ldiv", "mulT", "ldivT"):
@@ -160,7 +166,7 @@ def test_efa_pieces(name):
 
 
 @pytest.mark.parametrize("precond", [False, True])
-@pytest.mark.parametrize("name,sym", [("cfg1t", True), ("mixed", True), ("mixed", False), ("cfg3s", True), ("sq16", True), ("hc8", True)])
+@pytest.mark.parametrize("name,sym", [("cfg1t", True), ("mixed", True), ("mixed", False), ("cfg3s", True), ("sq16", True), ("hc8", True), ("disp", True)])
 def test_hmc_update_matches_oracle(name, sym, precond):
     """One full hmc_update! with the same random stream on both sides: same trajectory, energies, decision."""
     from smoqyelph_b200 import api

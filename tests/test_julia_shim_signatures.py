@@ -102,8 +102,9 @@ def test_reference_positional_signatures_are_kept():
     assert "function sample_pseudofermion_fields!(p::PFFCalculator{E}, elph, f::FermionDetMatrix, rng" in src
     assert re.search(r"function calculate_fermionic_action!\(p::PFFCalculator\{E\}, elph, f, preconditioner, rng::AbstractRNG, tol::E = ", src)
     assert re.search(r"function calculate_derivative_fermionic_action!\(∂Sf∂x::AbstractMatrix\{E\}, p::PFFCalculator\{E\}, elph, f, preconditioner, rng::AbstractRNG,", src)
-    # loud failures instead of silent wrong physics (round-1 ADVICE): dispersive couplings, complex couplings, missing correlation driver
-    assert "dispersive phonon couplings" in src and "Ndispersion == 0 ||" in src
+    # no silent wrong physics (round-1 ADVICE): dispersive couplings are passed to the device, complex couplings and a missing correlation
+    # driver are errors
+    assert "sq_elph_set_dispersion" in src and "complex SSH couplings are not implemented" in src
     assert "no correlation driver is" in src
     assert "α3[u] * xv^3" in src              # the reference's x^2 typo is not propagated
 

@@ -314,3 +314,28 @@ def test_scalar_measurements_free_fermions():
     assert abs(n_exact - n_ed) < 1e-10
     d = orc.measure("double_occ", R, GR)
     assert abs(d.real - n_exact.real**2) < 0.05          # non-interacting: <n_up n_dn> = n^2 per spin
+
+
+def test_dispersive_couplings_action_and_derivative():
+    """Dispersive phonon couplings [unvendored SmoQyDQMC arithmetic, restated]: the derivative the kick uses is the gradient of the
+    dispersive part of the bosonic action (central differences), the term vanishes for equal displacements, and a frozen partner
+    (M = inf) gives the reduced mass of the free one."""
+    m = mdl.with_dispersion(mdl.holstein_square(4, 4, 0.5), 0.7, 0.3)
+    m0 = mdl.holstein_square(4, 4, 0.5)
+    e, e0 = orc.RefElPh(m), orc.RefElPh(m0)
+    rng = np.random.default_rng(0)
+    x = m.random_fields(rng)
+
+    def extra(xx):
+        e.set_x(xx); e0.set_x(xx)
+        return e.bosonic_action() - e0.bosonic_action()
+    e.set_x(x); e0.set_x(x)
+    G = e.potential_derivative() - e0.potential_derivative()
+    h = 1e-5
+    for k in [(0, 0), (3, 2), (15, 9), (7, 5)]:
+        xp, xm = x.copy(), x.copy()
+        xp[k] += h; xm[k] -= h
+        fd = (extra(xp) - extra(xm)) / (2 * h)
+        assert abs(G[k] - fd) < 1e-6 * max(1.0, abs(fd)), (k, G[k], fd)
+    assert abs(extra(np.full_like(x, 0.37))) < 1e-12
+    assert extra(x) > 0
