@@ -500,7 +500,9 @@ void fdm_mul_dev(sq_fdm *f, int op, double2 *out, const double2 *in, double *pAp
 }
 
 // choose (slab, threads) by timing the fused kernel on the device (done once per handle)
-static void fdm_autotune(sq_fdm *f) {
+// timing = false: only decide between the fused kernels (path 0) and the global-memory passes (path 1) and set a valid default
+// configuration -- what creation needs; the timed search runs lazily at the first product (fdm_select_tuning)
+static void fdm_autotune(sq_fdm *f, bool timing = true) {
     size_t lim = f->smem_optin;
     int Smax = 0;
     for (int S = 1; S <= f->L; S++) {
@@ -516,6 +518,7 @@ static void fdm_autotune(sq_fdm *f) {
         f->use_v2 = (ev && atoi(ev) == 0) ? 0 : (fdm_v2_supported(f, 2, f->slab, f->threads) ? 1 : 0);
         return;
     }
+    if (!timing) { f->slab = std::min(Smax, 2); f->threads = 256; f->use_v2 = 0; f->use_v3 = 0; return; }
     std::vector<int> Ss;
     for (int S = 1; S <= Smax; S++) {
         int nsl = (int)((f->L + S - 1) / S);
@@ -725,8 +728,7 @@ void fdm_create_impl(sq_fdm **out, int sym, i64 L, i64 N, i64 Nh, const i64 *nt,
         std::vector<double2> cs1((size_t)L * Nh + 1, make_double2(1.0, 0.0));
         f->cs.upload(cs1.data(), (size_t)L * Nh, f->stream);
         SQ_CUDA(cudaStreamSynchronize(f->stream));
-        fdm_autotune(f);              // decides path 0 / 1; the per-mode tuning itself is refined lazily
-        if (f->path == 0) { f->tuned[0][0] = 1; f->tuned[0][1] = f->slab; f->tuned[0][2] = f->threads; f->tuned[0][3] = f->use_v2; f->tuned[0][4] = 0; f->tuned[0][5] = 3; }
+        fdm_autotune(f, false);       // decides path 0 / 1; the timed search of (slab, threads, kernel) runs lazily at the first product
         f->launches = 0;
         SQ_CUDA(cudaStreamSynchronize(f->stream));
     } catch (...) {
