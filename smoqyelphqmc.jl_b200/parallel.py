@@ -46,6 +46,28 @@ def halo_plan(Ltau: int, world: int, rank: int):
     }
 
 
+def rhs_owner(j: int, world: int) -> int:
+    """Rank that solves measurement system j of a sharded chain (greens.cu: column j on rank j mod world)."""
+    return int(j) % int(world)
+
+
+def frequency_share(schedule, Ltau: int, world: int, rank: int):
+    """This rank's share of the Chebyshev schedule in tau-slab mode: the scheduled Matsubara frequencies (order > 1, longest recurrence
+    first) that fall into the rank's index range -- a rank owns the frequencies with the same indices as its time slices (slab.cu,
+    kpm_ldiv_slab)."""
+    lo, hi = slab_range(Ltau, world, rank)
+    return [int(n) for n in schedule if lo <= int(n) < hi]
+
+
+def partial_dft(v_own, lo: int, Ltau: int, inverse: bool = False):
+    """The contribution of the rows [lo, lo + len(v_own)) to the length-Ltau DFT along axis 0 (all other rows zero): what every rank
+    computes before the all-to-all of the tau-FFT preconditioner.  Summed over the ranks it is the full transform (the DFT is linear)."""
+    v_own = np.asarray(v_own)
+    pad = np.zeros((Ltau,) + v_own.shape[1:], dtype=np.complex128)
+    pad[lo:lo + v_own.shape[0]] = v_own
+    return (np.fft.ifft(pad, axis=0) * Ltau) if inverse else np.fft.fft(pad, axis=0)
+
+
 def merge_chain_statistics(values, dist=None):
     """Mean and standard error over chains of per-chain means.  `values`: 1-D array of this rank's per-chain
     observables.  With torch.distributed initialised the chains of all ranks are gathered first."""

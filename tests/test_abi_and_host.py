@@ -119,6 +119,31 @@ prev = np.vstack([halo[None, :], v[lo:hi - 1]])
 sg = np.full(hi - lo, -1.0); sg[0] = plan["sign_from_prev"]
 mine += sg[:, None] * B[lo:hi] * prev
 assert np.allclose(mine, full[lo:hi])
+# the all-to-all of the tau-FFT preconditioner (slab.cu, kpm_ldiv_slab) emulated with gloo: every rank transforms its own slices into
+# partial sums for all frequencies, the pieces of rank q's frequencies travel to rank q and are added in rank order; a per-frequency
+# operation on the own frequencies; the same on the way back.  Result == the serial  ifft(f * fft(v))  on the rank's slices.
+Lt, Ns = 10, 4
+vv = rng.standard_normal((Lt, Ns)) + 1j * rng.standard_normal((Lt, Ns))
+fmul = 1.0 + np.arange(Lt)[:, None] * (0.5 + 0.1j)                               # stands in for the per-frequency Chebyshev stage
+want = np.fft.ifft(fmul * np.fft.fft(vv, axis=0), axis=0)
+lo, hi = parallel.slab_range(Lt, w, r)
+def exchange_sum(partial):
+    pieces = [None] * w
+    dist.all_gather_object(pieces, partial)                                      # (the library sends only the destination's rows)
+    acc = np.zeros((hi - lo, Ns), complex)
+    for q in range(w):                                                           # fixed rank order: deterministic sum
+        acc += pieces[q][lo:hi]
+    return acc
+freq = exchange_sum(parallel.partial_dft(vv[lo:hi], lo, Lt))                     # own frequencies, all slices summed
+freq = fmul[lo:hi] * freq
+back = exchange_sum(parallel.partial_dft(freq, lo, Lt, inverse=True)) / Lt       # own slices, all frequencies summed
+assert np.allclose(back, want[lo:hi], atol=1e-12)
+sched = [0, Lt - 1, 1, Lt - 2, 2]
+share = parallel.frequency_share(sched, Lt, w, r)
+allsh = [None] * w
+dist.all_gather_object(allsh, share)
+assert sorted(sum(allsh, [])) == sorted(sched) and all(lo <= n < hi for n in share)
+assert [parallel.rhs_owner(j, w) for j in range(5)] == [0, 1, 0, 1, 0][:5] if w == 2 else True
 dist.destroy_process_group()
 print("ok", r)
 '''
