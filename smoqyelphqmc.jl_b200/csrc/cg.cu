@@ -335,7 +335,7 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
             x = f->v3_x.p;
             r = f->v3_r.p;
             if (!getenv("SQ_NO_PERSISTENT_CG") && maxiter > 0) {
-                // one cooperative launch for the whole solve (fdm_v3.cu: k_cg_v3_persistent); k_cg_init left |r0|^2, |b|, tol in st
+                // one cooperative launch for the whole solve (fdm_v3.cu: k_cg_v3_resident1); k_cg_init left |r0|^2, |b|, tol in st
                 SQ_CUDA(cudaMemcpyAsync(f->h_cg, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
                 SQ_CUDA(cudaStreamSynchronize(s));
                 if (f->h_cg->done == 2) throw SqNumericalInstability("conjugate gradient: NaN encountered in the residual (numerical instability)");

@@ -1137,7 +1137,7 @@ static v3_resident1_t pick3_resident1_multi(int kind, int a, int b) {
     return nullptr;
 }
 
-// One-sum resident kernel (k_cg_v3_resident1).  Returns false if it cannot run (the caller falls back to the two-sum kernel).
+// One-sum resident kernel (k_cg_v3_resident1).  Returns false if it cannot run (the caller falls back to the launch loop in cg.cu).
 static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *state, i64 maxiter) {
     v3_resident1_t k = f->v3_kind == 1 ? pick3h_resident1(f->v3_lxl, f->v3_ry) : pick3_resident1(f->v3_lxl, f->v3_ry);
     if (!k || !f->v3_ok || !f->cs_coluni) return false;

@@ -12,13 +12,15 @@
 //
 //   * square lattice: lane = (group of 4 consecutive x, block of 2 rows), warp w owns 2 (32 / LXL) consecutive rows; x-even and
 //     y-even bonds are lane-local, x-odd bonds one shuffle per two sites, y-odd bonds shuffle the lane's two rows -- except across
-//     the W warps of the chain, where the boundary rows cross through a small double-buffered shared-memory window (one
-//     CTA barrier each, 2 per application instead of 6 with no other shared-memory traffic);
+//     the W warps of the chain, where the boundary rows cross through a small double-buffered shared-memory window (one CTA barrier);
 //   * honeycomb: lane = R1 x R2 block of cells, the intra-cell bond is lane-local, the two inter-cell bond types shuffle one
 //     boundary column / row (rows across warps through the same window);
 //   * scaled rotations a' = a + tanh b with prod_c cosh_c^2, the Chebyshev rescaling 2 / mag and the tau-mean diagonal folded
-//     into ONE per-site factor kept in registers: a B-bar application is 2C + 1 dependent-free DFMA per site, the recurrence
-//     T_{q+1} = 2 B' T_q - T_{q-1} and the accumulation 3 more;
+//     into ONE per-site factor kept in registers;
+//   * the recurrence runs in the frame rotated by the OUTER colour step K (B-bar = K A K  =>  K B-bar K^-1 = K^2 A, and K^2 is one
+//     step with the doubled angle): one outer step -- the expensive one, it crosses lanes and warps -- per application instead of
+//     two, i.e. 2C - 1 colour steps + the diagonal (one DFMA per site each) + 3 DFMA per site for T_{q+1} = 2 B' T_q - T_{q-1} and
+//     the accumulation; the result is rotated back once per chain;
 //   * W is chosen so that a lane holds 4 - 12 sites: T_{q-1}, T_q, the working copy, the accumulator and the diagonal fit in
 //     registers, and the four FP64 pipes of the SM all work on the one chain that matters.
 // Chains are scheduled longest first, one CTA per SM (CTA b runs chains b, b + G, ...: the long chains get an SM to themselves).
