@@ -419,9 +419,14 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
                                     : fdm_v2_launch_cg(f, q, pb[pc], pb[pc ^ 1], z, B, A, part_rr, G, part_rz, g, 1, (int)it, 0, part_pAp);
                     pc ^= 1;
                 }
-                k_cg_update_xr<<<G, TB, 0, s>>>(A, x, r, pb[pc], q, n, part_pAp, npart, 0, part_rr, B, ticket, (int)it);
-                g = kpm_ldiv_dev_dot(kpm, z, r, B, r, part_rz);
-                f->launches += 1;
+                if (!getenv("SQ_NO_FFT_FUSION")) {            // x / r update + convergence test inside the forward transform's load phase
+                    FftCgUpdate U = {x, r, pb[pc], q, A, B, part_pAp, npart, 0, part_rr, ticket, (int)it};
+                    g = kpm_ldiv_dev_fused(kpm, z, U, part_rz);
+                } else {
+                    k_cg_update_xr<<<G, TB, 0, s>>>(A, x, r, pb[pc], q, n, part_pAp, npart, 0, part_rr, B, ticket, (int)it);
+                    g = kpm_ldiv_dev_dot(kpm, z, r, B, r, part_rz);
+                    f->launches += 1;
+                }
             }
             SQ_LAUNCH_CHECK();
             SQ_CUDA(cudaMemcpyAsync(f->h_cg, B, sizeof(CgState), cudaMemcpyDeviceToHost, s));
@@ -436,6 +441,7 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
         if (f->h_cg->done) f->prec_iters_hint[tol < 1e-7 ? 0 : 1] = (int)std::min<i64>(*iters, 1 << 20);
         return;
     }
+    const bool fuse_fft = prec && !getenv("SQ_NO_FFT_FUSION");
     while (!finished) {
         // preconditioned solves take a few tens of iterations and consecutive solves of a trajectory take about the same number:
         // the first read-back is placed shortly before the point where the previous solve of this tolerance class converged, later ones
@@ -454,11 +460,20 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
                 k_cg_update_p<<<G, TB, 0, s>>>(sc, sn, p, r, n, part_rr, G, (int)it);
                 f->launches += 2;
             } else {
-                // x, r update with the convergence test (k_cg_check) done by the last block to finish
-                k_cg_update_xr<<<G, TB, 0, s>>>(sc, x, r, p, z, n, part_pAp, npart, 0, part_rr, sn, ticket, (int)it);
-                int g = kpm_ldiv_dev_dot(kpm, z, r, sn, r, part_rz);      // z = P^-1 r with the r.z partials fused in
+                int g;
+                if (fuse_fft) {
+                    // x / r update and convergence test inside the load phase of the forward transform (which reads r anyway); z holds
+                    // q = M^T M p on entry and P^-1 r on exit (the inverse transform writes it after the forward one has consumed it)
+                    FftCgUpdate U = {x, r, p, z, sc, sn, part_pAp, npart, 0, part_rr, ticket, (int)it};
+                    g = kpm_ldiv_dev_fused(kpm, z, U, part_rz);
+                    f->launches += 1;
+                } else {
+                    // x, r update with the convergence test (k_cg_check) done by the last block to finish
+                    k_cg_update_xr<<<G, TB, 0, s>>>(sc, x, r, p, z, n, part_pAp, npart, 0, part_rr, sn, ticket, (int)it);
+                    g = kpm_ldiv_dev_dot(kpm, z, r, sn, r, part_rz);      // z = P^-1 r with the r.z partials fused in
+                    f->launches += 2;
+                }
                 k_cg_update_p_prec<<<G, TB, 0, s>>>(sn, sc, p, z, n, part_rz, g);
-                f->launches += 2;
             }
             cur ^= 1;
         }

@@ -14,8 +14,6 @@
 
 #include <algorithm>
 
-void kpm_fft_cheb_batch(sq_kpm *k, double2 *out, const double2 *in, double2 *zt, int nrhs, size_t stride, const CgState *skip,
-                        const double2 *dot_with, double *dot_part, int *npart);
 
 // partials of conj(a).b (re, im) and |a|^2 per system: part[rhs][q][block]
 __global__ void kb_dot_partials(const double2 *__restrict__ a, const double2 *__restrict__ b, size_t n, double *__restrict__ part) {
@@ -201,6 +199,9 @@ void fdm_cg_batch_dev(sq_fdm *f, double2 *X, const double2 *B, int nrhs, bool ze
     int cur = 0;
     bool finished = maxiter <= 0;
     const int batch = 4;
+    // (fusing the x / r update into the forward transform saves 3 - 5 us per iteration for ONE system -- cg.cu -- but measured 2 % slower for a
+    //  batch, whose transform is bandwidth-bound: opt-in here)
+    const bool fuse_update = getenv("SQ_BATCH_FFT_FUSION") != nullptr;
     while (!finished) {
         i64 step = batch;
         if (it == 0) step = std::max<i64>(batch, std::min<i64>((i64)(0.85 * f->prec_iters_hint[tol < 1e-7 ? 0 : 1]), 256));
@@ -209,10 +210,16 @@ void fdm_cg_batch_dev(sq_fdm *f, double2 *X, const double2 *B, int nrhs, bool ze
             it++;
             CgState *sc = st + (size_t)cur * nrhs, *sn = st + (size_t)(cur ^ 1) * nrhs;
             const int np = mul_batch(f, q, p, nrhs, V, part_pAp, SQ_MAXPART, sc);
-            kb_update_xr<<<dim3(G, nrhs), TB, 0, s>>>(sc, sn, X, r, p, q, V, part_pAp, np, SQ_MAXPART, part_rr, f->bt_ticket.p, (int)it);
-            kpm_fft_cheb_batch(kpm, z, r, f->bt_zt.p, nrhs, V, sn, r, part_dot, &g);
+            if (fuse_update) {                                // x / r update + convergence test inside the forward transform's load phase
+                FftCgUpdate U = {X, r, p, q, sc, sn, part_pAp, np, SQ_MAXPART, part_rr, f->bt_ticket.p, (int)it};
+                kpm_fft_cheb_batch(kpm, z, r, f->bt_zt.p, nrhs, V, sn, r, part_dot, &g, &U);
+            } else {
+                kb_update_xr<<<dim3(G, nrhs), TB, 0, s>>>(sc, sn, X, r, p, q, V, part_pAp, np, SQ_MAXPART, part_rr, f->bt_ticket.p, (int)it);
+                kpm_fft_cheb_batch(kpm, z, r, f->bt_zt.p, nrhs, V, sn, r, part_dot, &g);
+                f->launches++;
+            }
             kb_update_p<<<dim3(G, nrhs), TB, 0, s>>>(sn, sc, p, z, V, part_dot, g);
-            f->launches += 2;
+            f->launches++;
             cur ^= 1;
         }
         SQ_LAUNCH_CHECK();

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 void fft_radices(i64 n, std::vector<int> &rad) {
     rad.clear();
@@ -130,15 +131,22 @@ __device__ __forceinline__ void stockham_pass_generic(const double2 *__restrict_
 __global__ void __launch_bounds__(256, 2) k_tau_fft(const FftPlan plan, double2 *__restrict__ out, const double2 *__restrict__ in, int N, int SB, int inverse,
                           int twist, const double2 *tw, const double2 *__restrict__ theta,
                           const double *__restrict__ scale1, const double2 *__restrict__ dot_with, double *__restrict__ dot_part,
-                          const CgState *__restrict__ skip, size_t bstride) {
+                          const CgState *__restrict__ skip, size_t bstride, const FftCgUpdate U) {
     extern __shared__ double2 sm[];
     __shared__ double red[2 * 32];
+    __shared__ double ush[1];
+    __shared__ int ulast;
     // batch of vectors (multi-RHS solves): blockIdx.y selects the vector, its partial sums and its solver state
     in += (size_t)blockIdx.y * bstride;
     out += (size_t)blockIdx.y * bstride;
     if (dot_with) { dot_with += (size_t)blockIdx.y * bstride; dot_part += (size_t)blockIdx.y * 2 * SQ_MAXPART; }
     if (skip) skip += blockIdx.y;
-    if (skip && skip->done) return;
+    if (U.x != nullptr) {                              // fused CG update: the state BEFORE the update decides; a finished system keeps its state
+        if (U.cur[blockIdx.y].done) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) U.nxt[blockIdx.y] = U.cur[blockIdx.y];
+            return;
+        }
+    } else if (skip && skip->done) return;
     const int L = plan.L;
     double2 *bufA = sm, *bufB = sm + (size_t)L * SB;
     double2 *stw = sm + (size_t)2 * L * SB;          // twiddles staged in shared memory: no global loads inside the passes
@@ -146,6 +154,23 @@ __global__ void __launch_bounds__(256, 2) k_tau_fft(const FftPlan plan, double2 
     const int ncol = min(SB, N - i0);
     const double rs = rsqrt((double)L);
     for (int k = threadIdx.x; k < L; k += blockDim.x) stw[k] = tw[k];
+    // fused CG update (forward transform of the preconditioner only): alpha from the p.Ap partials and the current state
+    const bool fuse = (U.x != nullptr);
+    double2 alpha = make_double2(0.0, 0.0);
+    double2 *ux = nullptr, *ur = nullptr;
+    const double2 *up = nullptr, *uq = nullptr;
+    double acc_rr = 0.0;
+    if (fuse) {
+        const size_t bo = (size_t)blockIdx.y * bstride;
+        ux = U.x + bo; ur = U.r + bo; up = U.p + bo; uq = U.q + bo;
+        if (threadIdx.x < 32) {
+            const double pAp = warp_sum_partials(U.pAp_part + (size_t)blockIdx.y * U.pap_stride, U.npart);
+            if (threadIdx.x == 0) ush[0] = pAp;
+        }
+        __syncthreads();
+        const CgState st = U.cur[blockIdx.y];
+        alpha = make_double2(st.rz_re / ush[0], st.rz_im / ush[0]);
+    }
     // tile load, 4 independent global loads in flight per thread
     const int tot = L * SB, T = blockDim.x;
     for (int w0 = threadIdx.x; w0 < tot; w0 += 4 * T) {
@@ -159,7 +184,17 @@ __global__ void __launch_bounds__(256, 2) k_tau_fft(const FftPlan plan, double2 
             if (w < tot) {
                 int l = w >> plan.sbshift, col = w & (SB - 1);
                 lq[q] = l;
-                if (col < ncol) v[q] = in[(size_t)l * N + i0 + col];
+                if (col < ncol) {
+                    const size_t g = (size_t)l * N + i0 + col;
+                    v[q] = fuse ? U.r[(size_t)blockIdx.y * bstride + g] : in[g];      // (fused: r is read through the pointer it is written through)
+                    if (fuse) {                               // x += alpha p ; r -= alpha q ; the transform continues on the new r
+                        const double2 rk = csub(v[q], cmul(alpha, uq[g]));
+                        ux[g] = cadd(ux[g], cmul(alpha, up[g]));
+                        ur[g] = rk;
+                        acc_rr += rk.x * rk.x + rk.y * rk.y;
+                        v[q] = rk;
+                    }
+                }
             }
         }
 #pragma unroll
@@ -174,6 +209,35 @@ __global__ void __launch_bounds__(256, 2) k_tau_fft(const FftPlan plan, double2 
         }
     }
     __syncthreads();
+    if (fuse) {
+        // |r|^2 partial of this CTA; the CTA that finishes last sums them in a fixed order and performs the convergence test
+        double a1[1] = {acc_rr};
+        block_sum<1>(a1, red);
+        double *rrp = U.rr_part + (size_t)blockIdx.y * SQ_MAXPART;
+        if (threadIdx.x == 0) {
+            rrp[blockIdx.x] = a1[0];
+            __threadfence();
+            ulast = (atomicAdd(U.ticket + blockIdx.y, 1u) == gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (ulast && threadIdx.x < 32) {
+            __threadfence();
+            const volatile double *vp = rrp;
+            double t = 0;
+            for (int k = threadIdx.x; k < (int)gridDim.x; k += 32) t += vp[k];
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (threadIdx.x == 0) {
+                CgState c = U.cur[blockIdx.y];
+                c.eps = sqrt(t) / c.normb;
+                c.iters = U.iter;
+                c.done = (c.eps < c.tol) ? 1 : 0;
+                if (!(c.eps == c.eps)) c.done = 2;
+                U.nxt[blockIdx.y] = c;
+                U.ticket[blockIdx.y] = 0;
+            }
+        }
+        __syncthreads();
+    }
     tw = stw;
     double2 *src = bufA, *dst = bufB;
     int Ns = 1;
@@ -219,16 +283,16 @@ __global__ void __launch_bounds__(256, 2) k_tau_fft(const FftPlan plan, double2 
 // Returns the number of CTAs (= number of dot partials when dot_with != NULL).
 int tau_fft_launch_batch(cudaStream_t stream, const std::vector<int> &radices, int L, int N, double2 *out, const double2 *in, bool inverse,
                          bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
-                         double *dot_part, const CgState *skip, size_t smem_limit, int nbatch, size_t bstride);
+                         double *dot_part, const CgState *skip, size_t smem_limit, int nbatch, size_t bstride, const FftCgUpdate *upd);
 int tau_fft_launch(cudaStream_t stream, const std::vector<int> &radices, int L, int N, double2 *out, const double2 *in, bool inverse,
                    bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
                    double *dot_part, const CgState *skip, size_t smem_limit) {
-    return tau_fft_launch_batch(stream, radices, L, N, out, in, inverse, twist, tw, theta, scale1, dot_with, dot_part, skip, smem_limit, 1, 0);
+    return tau_fft_launch_batch(stream, radices, L, N, out, in, inverse, twist, tw, theta, scale1, dot_with, dot_part, skip, smem_limit, 1, 0, nullptr);
 }
 // nbatch vectors, bstride elements apart (dot_with likewise; dot_part 2 SQ_MAXPART doubles apart; skip[] one state per vector)
 int tau_fft_launch_batch(cudaStream_t stream, const std::vector<int> &radices, int L, int N, double2 *out, const double2 *in, bool inverse,
                          bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
-                         double *dot_part, const CgState *skip, size_t smem_limit, int nbatch, size_t bstride) {
+                         double *dot_part, const CgState *skip, size_t smem_limit, int nbatch, size_t bstride, const FftCgUpdate *upd) {
     FftPlan plan;
     plan.L = L;
     plan.nrad = (int)radices.size();
@@ -260,8 +324,14 @@ int tau_fft_launch_batch(cudaStream_t stream, const std::vector<int> &radices, i
         int Ns = 1;
         for (int s = 0; s < plan.nrad; s++) { plan.tws[s] = L / (Ns * plan.rad[s]); Ns *= plan.rad[s]; }
     }
+    FftCgUpdate U;
+    memset(&U, 0, sizeof(U));
+    if (upd) {
+        if (inverse || grid > SQ_MAXPART) throw SqError("fused CG update: forward transform with at most SQ_MAXPART CTAs only");
+        U = *upd;
+    }
     k_tau_fft<<<dim3(grid, nbatch), threads, smem, stream>>>(plan, out, in, N, SB, inverse ? 1 : 0, twist ? 1 : 0, tw, theta, scale1, dot_with,
-                                                             dot_part, skip, bstride);
+                                                             dot_part, skip, bstride, U);
     SQ_LAUNCH_CHECK();
     return grid;
 }

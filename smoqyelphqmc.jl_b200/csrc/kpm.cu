@@ -670,11 +670,13 @@ void kpm_cheb_apply(sq_kpm *k, double2 *z, const int *d_sched, int nsched, int n
 // out_j = P^-1 in_j for nrhs vectors `stride` elements apart (active preconditioner): forward tau-FFT (order-1 frequencies folded in),
 // Chebyshev recurrences, inverse tau-FFT with the partials of conj(dot_with_j).out_j (2 SQ_MAXPART doubles per vector) if requested.
 // zt: frequency-space scratch of the same shape.  skip[j].done skips vector j.  *npart = partials per vector.
+// upd != NULL: the CG x / r update of this iteration rides in the forward transform's load phase (FftCgUpdate, sq_internal.h); `in` is
+// then upd->r and `skip` the state array the update WRITES (upd->nxt), which the later stages read.
 void kpm_fft_cheb_batch(sq_kpm *k, double2 *out, const double2 *in, double2 *zt, int nrhs, size_t stride, const CgState *skip,
-                        const double2 *dot_with, double *dot_part, int *npart) {
+                        const double2 *dot_with, double *dot_part, int *npart, const FftCgUpdate *upd) {
     sq_fdm *f = k->f;
     tau_fft_launch_batch(f->stream, k->radices, (int)f->L, (int)f->N, zt, in, false, true, k->tw.p, k->theta.p, k->d_scale1.p, nullptr, nullptr,
-                         skip, f->smem_optin, nrhs, stride);
+                         skip, f->smem_optin, nrhs, stride, upd);
     kpm_cheb_apply(k, zt, k->d_freq_sched.p, k->nsched, nrhs, stride, skip);
     const int g = tau_fft_launch_batch(f->stream, k->radices, (int)f->L, (int)f->N, out, zt, true, true, k->tw.p, k->theta.p, nullptr, dot_with,
                                        dot_part, skip, f->smem_optin, nrhs, stride);
@@ -691,7 +693,13 @@ int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *
         return 0;
     }
     int g = 0;
-    kpm_fft_cheb_batch(k, out, in, k->ztmp.p, 1, 0, skip, dot_with, dot_part, &g);
+    kpm_fft_cheb_batch(k, out, in, k->ztmp.p, 1, 0, skip, dot_with, dot_part, &g, nullptr);
+    return g;
+}
+// z = P^-1 r with the CG x / r update fused into the forward transform (active preconditioner only); returns the number of r.z partials
+int kpm_ldiv_dev_fused(sq_kpm *k, double2 *z, const FftCgUpdate &upd, double *dot_part) {
+    int g = 0;
+    kpm_fft_cheb_batch(k, z, upd.r, k->ztmp.p, 1, 0, upd.nxt, upd.r, dot_part, &g, &upd);
     return g;
 }
 void kpm_ldiv_dev(sq_kpm *k, double2 *out, const double2 *in, const CgState *skip) { kpm_ldiv_dev_dot(k, out, in, skip, nullptr, nullptr); }

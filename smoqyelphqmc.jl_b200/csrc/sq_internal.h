@@ -259,6 +259,21 @@ static inline uint64_t sq_mix_seed(uint64_t seed, uint64_t tag) {
     return z ^ (z >> 31);
 }
 
+// CG x / r update fused into the load phase of the forward tau-FFT of the preconditioner (fft.cu): the transform reads r anyway, so
+//   alpha = (r.z) / (p.Ap);  x += alpha p;  r -= alpha q;  |r|^2 partials;  last CTA: eps, convergence test -> nxt
+// ride along and one launch (and one pass over x, r, p, q) per iteration disappears.  All arrays are indexed by the batch (blockIdx.y).
+struct FftCgUpdate {
+    double2 *x, *r;             // updated in place (r is the transform's input)
+    const double2 *p, *q;
+    const CgState *cur;         // [batch]
+    CgState *nxt;               // [batch]
+    const double *pAp_part;     // [batch][pap_stride]
+    int npart, pap_stride;
+    double *rr_part;            // [batch][SQ_MAXPART]
+    unsigned *ticket;           // [batch]
+    int iter;
+};
+
 // ---- functions shared between translation units (all enqueue on f->stream) ------------------------
 void fdm_mul_dev(sq_fdm *f, int op, double2 *out, const double2 *in, double *pAp_partials = nullptr,
                  int *npart = nullptr, const CgState *skip_if_done = nullptr);
@@ -271,6 +286,10 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
                 i64 *iters, double *eps);
 void kpm_ldiv_dev(sq_kpm *k, double2 *out, const double2 *in, const CgState *skip_if_done = nullptr);
 int kpm_ldiv_dev_dot(sq_kpm *k, double2 *out, const double2 *in, const CgState *skip, const double2 *dot_with, double *dot_part);
+struct FftCgUpdate;
+int kpm_ldiv_dev_fused(sq_kpm *k, double2 *z, const FftCgUpdate &upd, double *dot_part);
+void kpm_fft_cheb_batch(sq_kpm *k, double2 *out, const double2 *in, double2 *zt, int nrhs, size_t stride, const CgState *skip,
+                        const double2 *dot_with, double *dot_part, int *npart, const FftCgUpdate *upd = nullptr);
 void kpm_fourier_dev(sq_kpm *k, double2 *v, bool forward);
 void kpm_cheb_apply(sq_kpm *k, double2 *z, const int *d_sched, int nsched, int nrhs, size_t rhs_stride, const CgState *skip);
 void kpm_lanczos(sq_kpm *k, const double *h_start, const double *d_start, double *emin, double *emax);
@@ -298,7 +317,7 @@ int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, d
 bool fdm_v3_supported(const sq_fdm *f, int S);
 int tau_fft_launch_batch(cudaStream_t stream, const std::vector<int> &radices, int L, int N, double2 *out, const double2 *in, bool inverse,
                          bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
-                         double *dot_part, const CgState *skip, size_t smem_limit, int nbatch, size_t bstride);
+                         double *dot_part, const CgState *skip, size_t smem_limit, int nbatch, size_t bstride, const FftCgUpdate *upd = nullptr);
 // multi-RHS preconditioned CG (cg_batch.cu): nrhs systems M^T M x_j = b_j, vectors V elements apart
 void fdm_cg_batch_dev(sq_fdm *f, double2 *X, const double2 *B, int nrhs, bool zero_start, sq_kpm *kpm, double tol, i64 maxiter, i64 *iters,
                       double *eps);
