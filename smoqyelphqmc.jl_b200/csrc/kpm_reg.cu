@@ -40,6 +40,7 @@ struct ChebRegParams {
     const double2 *csbar;           // (mean cosh, mean sinh) per bond; colour c = csbar[clo[c]]
     int clo[4];
     const double *Dbar;             // [i]
+    const int *site_bond;           // per-bond engines: internal bond index of site i in colour c at [c * N + i]
     double avg, imag_;              // (emax + emin) / 2, 2 / (emax - emin)
     const CgState *skip;
 };
@@ -69,6 +70,7 @@ struct RegSquare {
             g *= q.x * q.x;
         }
         t2o = 2.0 * t[3] / (1.0 + t[3] * t[3]);
+        g *= 1.0 + t[3] * t[3];                                   // K^2 = (1 + t^2)(1 + t' sigma)
     }
     // site of value k = 4 r + j
     __device__ __forceinline__ int site(int k) const { return 4 * xl + (k & 3) + LX * ((w * YH + yh) * RY + (k >> 2)); }
@@ -138,7 +140,13 @@ struct RegSquare {
         step<0>(v, xb); step<1>(v, xb); step<2>(v, xb);
         step<3>(v, xb, t2o);
     }
-    __device__ __forceinline__ void outer(double (&v)[NV], double *xb, double s) const { step<3>(v, xb, s); }
+    __device__ __forceinline__ void outer_in(double (&v)[NV], double *xb) const { step<3>(v, xb, t[3]); }          // u = K v
+    __device__ __forceinline__ void outer_out(double (&v)[NV], double *xb) const {                                   // v = K^-1 u
+        step<3>(v, xb, -t[3]);
+        const double back = 1.0 / (1.0 - t[3] * t[3]);
+#pragma unroll
+        for (int k = 0; k < NV; k++) v[k] *= back;
+    }
     static constexpr int XHALF = W * 2 * LX;
 };
 
@@ -170,6 +178,7 @@ struct RegHoney {
             g *= q.x * q.x;
         }
         t2o = 2.0 * t[2] / (1.0 + t[2] * t[2]);
+        g *= 1.0 + t[2] * t[2];
     }
     __device__ __forceinline__ int site(int k) const {
         const int u = k >> 1, a1 = u % R1, a2 = u / R1;
@@ -242,8 +251,192 @@ struct RegHoney {
         step<0>(v, xb); step<1>(v, xb);
         step<2>(v, xb, t2o);
     }
-    __device__ __forceinline__ void outer(double (&v)[NV], double *xb, double s) const { step<2>(v, xb, s); }
+    __device__ __forceinline__ void outer_in(double (&v)[NV], double *xb) const { step<2>(v, xb, t[2]); }
+    __device__ __forceinline__ void outer_out(double (&v)[NV], double *xb) const {
+        step<2>(v, xb, -t[2]);
+        const double back = 1.0 / (1.0 - t[2] * t[2]);
+#pragma unroll
+        for (int k = 0; k < NV; k++) v[k] *= back;
+    }
     static constexpr int XHALF = W * 2 * L1;
+};
+
+// ---- per-bond coefficients (SSH models, disordered hoppings): square lattice and chain ----------------------------------------
+// B-bar's bonds carry their own tau-mean (cosh, sinh) -- no common factor to fold, so a colour step is c a + s b (DMUL + DFMA per
+// site) with the coefficients of the lane's 8 sites x 4 colours kept in registers for the whole recurrence.  The frame rotation by
+// the outer colour works bond by bond: K = c + s sigma, K^2 = (c^2 + s^2) + 2 c s sigma, K^-1 = (c - s sigma) / (c^2 - s^2) (the
+// tau-means do not satisfy c^2 - s^2 = 1).
+template <int LXL_, int W_>
+struct RegSquarePB {
+    static constexpr int LXL = LXL_, W = W_, RY = 2, YH = 32 / LXL, LX = 4 * LXL, LY = RY * YH * W, N = LX * LY, NV = 4 * RY, NCOL = 4;
+    static constexpr int XCH = 2 * W * 2 * LX, XHALF = W * 2 * LX;
+    int xl, yh, w, lane_r, lane_l, lane_u, lane_d;
+    double2 cs[3][NV];          // (c, s) of the bond that touches value k in the inner colours 0, 1, 2
+    double2 k2[NV];             // outer colour squared: (c^2 + s^2, 2 c s); K itself is re-read for the two frame changes of a chain
+    const double2 *csbar;
+    const int *sb3;             // site -> bond of the outer colour
+
+    __device__ __forceinline__ int site(int k) const { return 4 * xl + (k & 3) + LX * ((w * YH + yh) * RY + (k >> 2)); }
+    __device__ __forceinline__ void init(const ChebRegParams &P, double &g) {
+        const int lane = threadIdx.x & 31;
+        w = threadIdx.x >> 5;
+        xl = lane % LXL;
+        yh = lane / LXL;
+        lane_r = lane - xl + (xl + 1) % LXL;
+        lane_l = lane - xl + (xl + LXL - 1) % LXL;
+        lane_u = xl + LXL * ((yh + 1) % YH);
+        lane_d = xl + LXL * ((yh + YH - 1) % YH);
+        g = 1.0;
+        csbar = P.csbar;
+        sb3 = P.site_bond + 3 * N;
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int k = 0; k < NV; k++) cs[c][k] = __ldg(P.csbar + __ldg(P.site_bond + c * N + site(k)));
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const double2 q = __ldg(csbar + __ldg(sb3 + site(k)));
+            k2[k] = make_double2(q.x * q.x + q.y * q.y, 2.0 * q.x * q.y);
+        }
+    }
+    // one colour step; the outer colour takes its coefficients from `co` (K, K^2 or K^-1)
+    template <int CL>
+    __device__ __forceinline__ void step(double (&v)[NV], double *xb, const double2 (&co)[NV]) const {
+        if (CL == 0) {
+#pragma unroll
+            for (int r = 0; r < RY; r++) {
+                const double a = v[4 * r], b = v[4 * r + 1], c = v[4 * r + 2], d = v[4 * r + 3];
+                v[4 * r] = fma(co[4 * r].y, b, co[4 * r].x * a); v[4 * r + 1] = fma(co[4 * r + 1].y, a, co[4 * r + 1].x * b);
+                v[4 * r + 2] = fma(co[4 * r + 2].y, d, co[4 * r + 2].x * c); v[4 * r + 3] = fma(co[4 * r + 3].y, c, co[4 * r + 3].x * d);
+            }
+        } else if (CL == 1) {
+#pragma unroll
+            for (int r = 0; r < RY; r++) {
+                const double fromR = __shfl_sync(0xffffffffu, v[4 * r], lane_r);
+                const double fromL = __shfl_sync(0xffffffffu, v[4 * r + 3], lane_l);
+                const double b = v[4 * r + 1], c = v[4 * r + 2];
+                v[4 * r + 1] = fma(co[4 * r + 1].y, c, co[4 * r + 1].x * b); v[4 * r + 2] = fma(co[4 * r + 2].y, b, co[4 * r + 2].x * c);
+                v[4 * r + 3] = fma(co[4 * r + 3].y, fromR, co[4 * r + 3].x * v[4 * r + 3]);
+                v[4 * r] = fma(co[4 * r].y, fromL, co[4 * r].x * v[4 * r]);
+            }
+        } else if (CL == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const double a = v[j], b = v[4 + j];
+                v[j] = fma(co[j].y, b, co[j].x * a); v[4 + j] = fma(co[4 + j].y, a, co[4 + j].x * b);
+            }
+        } else {
+            double up[4], dn[4];
+            if (W > 1) {
+                if (yh == 0) *reinterpret_cast<double4 *>(xb + (w * 2 + 0) * LX + 4 * xl) = make_double4(v[0], v[1], v[2], v[3]);
+                if (yh == YH - 1) *reinterpret_cast<double4 *>(xb + (w * 2 + 1) * LX + 4 * xl) = make_double4(v[4], v[5], v[6], v[7]);
+                __syncthreads();
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                up[j] = __shfl_sync(0xffffffffu, v[j], lane_u);
+                dn[j] = __shfl_sync(0xffffffffu, v[4 + j], lane_d);
+            }
+            if (W > 1) {
+                if (yh == YH - 1) {
+                    const double4 q = *reinterpret_cast<const double4 *>(xb + (((w + 1) % W) * 2 + 0) * LX + 4 * xl);
+                    up[0] = q.x; up[1] = q.y; up[2] = q.z; up[3] = q.w;
+                }
+                if (yh == 0) {
+                    const double4 q = *reinterpret_cast<const double4 *>(xb + (((w + W - 1) % W) * 2 + 1) * LX + 4 * xl);
+                    dn[0] = q.x; dn[1] = q.y; dn[2] = q.z; dn[3] = q.w;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                v[4 + j] = fma(co[4 + j].y, up[j], co[4 + j].x * v[4 + j]);
+                v[j] = fma(co[j].y, dn[j], co[j].x * v[j]);
+            }
+        }
+    }
+    __device__ __forceinline__ void apply(double (&v)[NV], const double (&dg)[NV], double *xb) const {
+        step<2>(v, xb, cs[2]); step<1>(v, xb, cs[1]); step<0>(v, xb, cs[0]);
+#pragma unroll
+        for (int k = 0; k < NV; k++) v[k] *= dg[k];
+        step<0>(v, xb, cs[0]); step<1>(v, xb, cs[1]); step<2>(v, xb, cs[2]);
+        step<3>(v, xb, k2);
+    }
+    __device__ __forceinline__ void outer_in(double (&v)[NV], double *xb) const {                                    // u = K v
+        double2 co[NV];
+#pragma unroll
+        for (int k = 0; k < NV; k++) co[k] = __ldg(csbar + __ldg(sb3 + site(k)));
+        step<3>(v, xb, co);
+    }
+    __device__ __forceinline__ void outer_out(double (&v)[NV], double *xb) const {                                   // v = K^-1 u
+        double2 co[NV];
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const double2 q = __ldg(csbar + __ldg(sb3 + site(k)));
+            const double inv = 1.0 / (q.x * q.x - q.y * q.y);
+            co[k] = make_double2(q.x * inv, -q.y * inv);
+        }
+        step<3>(v, xb, co);
+    }
+};
+
+// periodic chain of N = 64 W sites, colour 0 = even bonds (2m, 2m+1), colour 1 = odd bonds (2m+1, 2m+2): lane holds one even bond
+template <int W_>
+struct RegChainPB {
+    static constexpr int W = W_, N = 64 * W, NV = 2, NCOL = 2;
+    static constexpr int XCH = 2 * W * 2, XHALF = W * 2;
+    int lane, w;
+    double2 cs[2][NV], k2[NV];
+    double kinv[NV];
+    __device__ __forceinline__ int site(int k) const { return 2 * (32 * w + lane) + k; }
+    __device__ __forceinline__ void init(const ChebRegParams &P, double &g) {
+        lane = threadIdx.x & 31;
+        w = threadIdx.x >> 5;
+        g = 1.0;
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int k = 0; k < NV; k++) cs[c][k] = __ldg(P.csbar + __ldg(P.site_bond + c * N + site(k)));
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            const double c = cs[1][k].x, s_ = cs[1][k].y;
+            k2[k] = make_double2(c * c + s_ * s_, 2.0 * c * s_);
+            kinv[k] = 1.0 / (c * c - s_ * s_);
+        }
+    }
+    // odd bonds: value 1 pairs with value 0 of the next lane (next warp through the window), value 0 with value 1 of the previous
+    __device__ __forceinline__ void odd(double (&v)[NV], double *xb, const double2 (&co)[NV]) const {
+        if (W > 1) {
+            if (lane == 0) xb[w * 2 + 0] = v[0];
+            if (lane == 31) xb[w * 2 + 1] = v[1];
+            __syncthreads();
+        }
+        double nx = __shfl_sync(0xffffffffu, v[0], (lane + 1) & 31), pv = __shfl_sync(0xffffffffu, v[1], (lane + 31) & 31);
+        if (W > 1) {
+            if (lane == 31) nx = xb[((w + 1) % W) * 2 + 0];
+            if (lane == 0) pv = xb[((w + W - 1) % W) * 2 + 1];
+        }
+        const double a = v[0], b = v[1];
+        v[1] = fma(co[1].y, nx, co[1].x * b);
+        v[0] = fma(co[0].y, pv, co[0].x * a);
+    }
+    __device__ __forceinline__ void even(double (&v)[NV]) const {
+        const double a = v[0], b = v[1];
+        v[0] = fma(cs[0][0].y, b, cs[0][0].x * a);
+        v[1] = fma(cs[0][1].y, a, cs[0][1].x * b);
+    }
+    __device__ __forceinline__ void apply(double (&v)[NV], const double (&dg)[NV], double *xb) const {
+        even(v);
+        v[0] *= dg[0]; v[1] *= dg[1];
+        even(v);
+        odd(v, xb, k2);
+    }
+    __device__ __forceinline__ void outer_in(double (&v)[NV], double *xb) const { odd(v, xb, cs[1]); }
+    __device__ __forceinline__ void outer_out(double (&v)[NV], double *xb) const {
+        double2 ci[NV];
+#pragma unroll
+        for (int k = 0; k < NV; k++) ci[k] = make_double2(cs[1][k].x * kinv[k], -cs[1][k].y * kinv[k]);
+        odd(v, xb, ci);
+    }
 };
 
 // One CTA = one chain at a time (W warps).  The recurrence runs in the rotated frame u_q = K T_q (see apply()):
@@ -259,8 +452,7 @@ k_kpm_cheb_reg(const __grid_constant__ ChebRegParams P) {
     G E;
     double g;
     E.init(P, g);
-    const double to = E.t[G::NCOL - 1];                         // tanh of the outer colour
-    const double kappa = 2.0 * P.avg * P.imag_, dscale = 2.0 * P.imag_ * g * (1.0 + to * to), back = 1.0 / (1.0 - to * to);
+    const double kappa = 2.0 * P.avg * P.imag_, dscale = 2.0 * P.imag_ * g;       // g: whatever the engine folds into the diagonal
     double dg[NV];
     int off[NV];
 #pragma unroll
@@ -284,7 +476,7 @@ k_kpm_cheb_reg(const __grid_constant__ ChebRegParams P) {
 #pragma unroll
         for (int k = 0; k < NV; k++) ta[k] = zn[2 * off[k]];
         const double c0 = __ldg(&c[0].x), c1 = __ldg(&c[1].x);
-        E.outer(ta, XB(), to);                                  // u_0 = K T_0
+        E.outer_in(ta, XB());                                   // u_0 = K T_0
 #pragma unroll
         for (int k = 0; k < NV; k++) y[k] = ta[k];
         E.apply(y, dg, XB());
@@ -326,9 +518,9 @@ k_kpm_cheb_reg(const __grid_constant__ ChebRegParams P) {
 #pragma unroll
             for (int k = 0; k < NV; k++) acc[k] = fma(ca, fma(-kappa, tb[k], y[k]) - ta[k], acc[k]);
         }
-        E.outer(acc, XB(), -to);                                // back to the original frame
+        E.outer_out(acc, XB());                                 // back to the original frame
 #pragma unroll
-        for (int k = 0; k < NV; k++) zn[2 * off[k]] = back * acc[k];
+        for (int k = 0; k < NV; k++) zn[2 * off[k]] = acc[k];
     }
 #undef XB
 }
@@ -336,10 +528,42 @@ k_kpm_cheb_reg(const __grid_constant__ ChebRegParams P) {
 typedef void (*cheb_reg_t)(const ChebRegParams);
 struct ChebRegPick { cheb_reg_t k; int threads; };
 
-static ChebRegPick pick_cheb_reg(const sq_fdm *f) {
-    if (!f->v3_ok || !f->sym) return {nullptr, 0};
+// periodic chain in natural order with colour 0 = even bonds, colour 1 = odd bonds, N a multiple of 64 (one lane per even bond)
+static bool chain_geometry(const sq_fdm *f) {
+    if (!f->sym || f->C != 2 || f->Nh != f->N || f->N % 64 || f->N / 64 > 8) return false;
+    for (int c = 0; c < 2; c++) {
+        if (f->chi[c] - f->clo[c] != f->N / 2) return false;
+        for (int h = f->clo[c]; h < f->chi[c]; h++) {
+            int i = f->h_nt[h].x, j = f->h_nt[h].y;
+            if ((j + 1) % f->N == i) std::swap(i, j);
+            if ((i + 1) % f->N != j || (i & 1) != c) return false;
+        }
+    }
+    return true;
+}
+
+// perbond = false: colour-uniform coefficients (scaled rotations); true: every bond its own (cosh, sinh) means
+static ChebRegPick pick_cheb_reg(const sq_fdm *f, bool perbond) {
+    if (!f->sym) return {nullptr, 0};
+    if (perbond && chain_geometry(f)) {
+        switch ((int)(f->N / 64)) {
+            case 1: return {k_kpm_cheb_reg<RegChainPB<1>>, 32};
+            case 2: return {k_kpm_cheb_reg<RegChainPB<2>>, 64};
+            case 4: return {k_kpm_cheb_reg<RegChainPB<4>>, 128};
+            case 8: return {k_kpm_cheb_reg<RegChainPB<8>>, 256};
+        }
+        return {nullptr, 0};
+    }
+    if (!f->v3_ok) return {nullptr, 0};
     if (f->v3_kind == 0) {                                     // square: v3_lxl = Lx / 4, v3_ry = rows per lane of the matvec engine
         const int lxl = f->v3_lxl, w = f->v3_ry / 2;           // Ly = v3_ry (32 / lxl) = 2 (32 / lxl) W
+        if (perbond) {
+            if (lxl == 8 && w == 2) return {k_kpm_cheb_reg<RegSquarePB<8, 2>>, 64};
+            if (lxl == 8 && w == 4) return {k_kpm_cheb_reg<RegSquarePB<8, 4>>, 128};
+            if (lxl == 4 && w == 1) return {k_kpm_cheb_reg<RegSquarePB<4, 1>>, 32};  // 16 x 16 (cfg3)
+            if (lxl == 4 && w == 2) return {k_kpm_cheb_reg<RegSquarePB<4, 2>>, 64};
+            return {nullptr, 0};
+        }
         if (lxl == 8 && w == 2) return {k_kpm_cheb_reg<RegSquare<8, 2>>, 64};       // 32 x 16
         if (lxl == 8 && w == 4) return {k_kpm_cheb_reg<RegSquare<8, 4>>, 128};      // 32 x 32
         if (lxl == 8 && w == 8) return {k_kpm_cheb_reg<RegSquare<8, 8>>, 256};      // 32 x 64
@@ -348,29 +572,42 @@ static ChebRegPick pick_cheb_reg(const sq_fdm *f) {
         if (lxl == 4 && w == 4) return {k_kpm_cheb_reg<RegSquare<4, 4>>, 128};      // 16 x 64
         return {nullptr, 0};
     }
+    if (perbond) return {nullptr, 0};
     if (f->v3_lxl == 24 && f->v3_ry == 24) return {k_kpm_cheb_reg<RegHoney<8, 3, 2, 3>>, 96};
     if (f->v3_lxl == 16 && f->v3_ry == 16) return {k_kpm_cheb_reg<RegHoney<4, 4, 1, 2>>, 64};
     if (f->v3_lxl == 8 && f->v3_ry == 8) return {k_kpm_cheb_reg<RegHoney<4, 2, 1, 1>>, 32};
     return {nullptr, 0};
 }
 
-// Is the register Chebyshev kernel available for this preconditioner?  (symmetric propagator on a register-path lattice with
-// colour-uniform tau-independent hoppings; SQ_KPM_REG=0 forces the shared-memory kernel)
-bool kpm_reg_ok(const sq_kpm *k) {
+// which register kernel serves this preconditioner: 0 none (shared-memory kernels), 1 colour-uniform, 2 per-bond
+static int kpm_reg_mode(const sq_kpm *k) {
     const sq_fdm *f = k->f;
-    if (const char *e = getenv("SQ_KPM_REG")) if (atoi(e) == 0) return false;
-    return f->sym && f->v3_ok && f->cs_coluni && pick_cheb_reg(f).k != nullptr;
+    if (const char *e = getenv("SQ_KPM_REG")) if (atoi(e) == 0) return 0;
+    if (!f->sym) return 0;
+    if (f->v3_ok && f->cs_coluni && pick_cheb_reg(f, false).k) return 1;
+    if (pick_cheb_reg(f, true).k) return 2;
+    return 0;
 }
+// Is a register Chebyshev kernel available for this preconditioner?  (symmetric propagator; a register-path lattice with colour-uniform
+// tau-independent hoppings, or a square lattice / chain with arbitrary real hoppings; SQ_KPM_REG=0 forces the shared-memory kernels)
+bool kpm_reg_ok(const sq_kpm *k) { return kpm_reg_mode(k) != 0; }
 
 // z: nrhs frequency-major arrays [n][i] (rhs_stride elements apart); applies sum_q c_q T_q(B') to every scheduled frequency in place
 void kpm_cheb_reg_launch(sq_kpm *k, double2 *z, const int *d_sched, int nsched, int nrhs, size_t rhs_stride, const CgState *skip) {
     sq_fdm *f = k->f;
     if (nsched <= 0) return;
-    const ChebRegPick pk = pick_cheb_reg(f);
+    const int mode = kpm_reg_mode(k);
+    const ChebRegPick pk = pick_cheb_reg(f, mode == 2);
+    if (mode == 2 && !k->site_bond.p) {                          // (colour, site) -> internal bond index, built once
+        std::vector<int> sb((size_t)f->C * f->N, 0);
+        for (int c = 0; c < f->C; c++)
+            for (int h = f->clo[c]; h < f->chi[c]; h++) { sb[(size_t)c * f->N + f->h_nt[h].x] = h; sb[(size_t)c * f->N + f->h_nt[h].y] = h; }
+        k->site_bond.from_vector(sb, f->stream);
+    }
     ChebRegParams P;
     P.N = (int)f->N; P.L = (int)f->L; P.nsched = nsched; P.nrhs = nrhs; P.nchain = nsched * 2 * nrhs; P.rhs_stride = rhs_stride;
     P.z = z; P.sched = d_sched; P.order = k->d_order.p; P.coef_off = k->d_coef_off.p; P.coefs = k->d_coefs.p;
-    P.csbar = k->csbar.p; P.Dbar = k->Dbar.p;
+    P.csbar = k->csbar.p; P.Dbar = k->Dbar.p; P.site_bond = k->site_bond.p;
     for (int c = 0; c < 4; c++) P.clo[c] = c < f->C ? f->clo[c] : 0;
     P.avg = 0.5 * (k->bounds[1] + k->bounds[0]);
     P.imag_ = 2.0 / (k->bounds[1] - k->bounds[0]);

@@ -161,6 +161,7 @@ struct sq_kpm {
     i64 sched_slab_version = -1;
     int sched_slab_lo = -1, sched_slab_hi = -1;
     DevBuf<double2> slab_a, slab_b, slab_recv;
+    DevBuf<int> site_bond;                   // per-bond register Chebyshev kernel: (colour, site) -> internal bond index
     DevBuf<double2> ztmp;                    // [n][i] frequency-space scratch
     DevBuf<double> lan;                      // Lanczos alpha/beta read-back
     DevBuf<double> lan_start;                // N

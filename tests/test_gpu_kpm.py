@@ -107,6 +107,12 @@ REG_LATTICES = {
     "hc8": lambda: mdl.holstein_honeycomb(8, 1.0),
     "hc16": lambda: mdl.holstein_honeycomb(16, 0.6),
     "hc24": lambda: mdl.holstein_honeycomb(24, 0.5),         # cfg5's lattice: three warps per chain
+    # per-bond coefficients (SSH couplings: every bond its own tau-mean cosh / sinh): square lattices and chains
+    "bssh16": lambda: mdl.bssh_square(16, 16, 1.0),          # cfg3's lattice
+    "bssh32x16": lambda: mdl.bssh_square(32, 16, 0.5),
+    "bssh32": lambda: mdl.bssh_square(32, 32, 0.5),
+    "ossh64": lambda: mdl.ossh_chain(64, 2.0),               # cfg2's lattice: one warp per chain
+    "ossh256": lambda: mdl.ossh_chain(256, 1.0),             # four warps per chain
 }
 
 
