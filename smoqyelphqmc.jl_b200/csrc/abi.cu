@@ -187,7 +187,7 @@ int sq_fdm_time_mul(sq_fdm *f, int op, void *d_out, const void *d_in, int reps, 
     if (nbatch) {
         SQ_REQUIRE(nbatch >= 1 && nbatch <= 64, "batch size out of range");
         fdm_select_tuning(f);
-        SQ_REQUIRE(f->path == 0 && f->v3_ok && f->cs_coluni && fdm_v3_supported(f, f->v3_S), "register path not active");
+        SQ_REQUIRE(f->path == 0 && fdm_v3_supported(f, f->v3_S), "register path not active");
         if (batch_native) fdm_v3_prepare_native(f);
     }
     auto fdm_mul_dev = [&](sq_fdm *ff, int o, double2 *out, const double2 *in) {

@@ -32,6 +32,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
+
+void fdm_v3_prepare_native(sq_fdm *f);
 
 struct V3Params {
     int L, lb, le, S, C;
@@ -44,6 +47,7 @@ struct V3Params {
     const double *expVn;    // native order (NAT kernels)
     const double2 *ctn;     // (cosh, tanh) per colour, prepared with expVn (the in-kernel divisions were 18 % of the stall samples)
     long long *dbg;         // optional clock stamps of warp 1 of CTA 0 (profiling aid, NULL in production)
+    const double2 *csn;     // per-bond engines: (cosh, sinh) of slot q of lane `lane` of slice l = csn[(l * NCS + q) * 32 + lane]
     size_t bstride;         // batch of vectors (blockIdx.z): elements between consecutive vectors
     int bpart;              // ... doubles between their p.Ap partials
     // CG fusion, same meaning as K2Params (fdm_v2.cu)
@@ -105,6 +109,8 @@ struct V3Lane {
             cc[c] = q.x; ss[c] = q.y;
         }
     }
+
+    __device__ __forceinline__ void load_cs(const V3Params &, int) {}      // uniform coefficients: nothing per slice
 
     template <int CL, int SC>
     __device__ __forceinline__ void step(double (&v)[RY][4]) const {
@@ -211,6 +217,7 @@ struct V3Honey {
         }
     }
     __device__ __forceinline__ int pair_site(int u) const { return 2 * ((R1 * g1 + u % R1) + L1 * (R2 * g2 + u / R1)); }
+    __device__ __forceinline__ void load_cs(const V3Params &, int) {}
 
     template <int CL, int SC>
     __device__ __forceinline__ void step(double (&v)[NV]) const {
@@ -266,6 +273,154 @@ struct V3Honey {
             v[2 * u] *= e.x; v[2 * u + 1] *= e.y;
         }
         step<0, NAT>(v); step<1, NAT>(v); step<2, NAT>(v);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Per-bond engines: every bond of every slice has its own (cosh, sinh) -- SSH couplings, disordered hoppings.  A warp applies
+// the propagator of ONE slice for the whole kernel (both passes of M^T M, every iteration of the resident solver), so the
+// coefficients of that slice live in REGISTERS: slot q of a lane is one bond the lane takes part in; bonds that cross to a
+// neighbouring lane are held by both lanes (no coefficient shuffles).  The slots are filled from a slot-ordered copy of the
+// coefficient table (csn, built with the native-order copy of exp(-dtau V)): one coalesced 16-byte load per slot.  The update
+// is the reference expression a' = c a + s b (rot1<0>): bit-identical to fdm.cu / fdm_v2.cu in every order.
+// The slot enumeration below is mirrored on the host by v3pb_slot_bonds().
+// ---------------------------------------------------------------------------------------------------
+template <int LXL, int RY>
+struct V3LanePB {
+    static constexpr int YH = 32 / LXL, LX = 4 * LXL, LY = RY * YH, N = LX * LY;
+    static constexpr int NV = 4 * RY, NP = 2 * RY, NCOL = 4;
+    static constexpr int REGS_LIGHT = 0;
+    // slots: x-even 2 RY | x-odd 3 RY (inner, to the right lane, from the left lane) | y-even 2 RY | y-odd 4 up + 4 down + inner
+    static constexpr int Q0 = 0, Q1 = 2 * RY, Q2 = 5 * RY, Q3 = 7 * RY, NCS = 9 * RY + 4;
+    static_assert(YH > 1, "row blocks of at least two lanes");
+    int xl, part, yh;
+    int lane_r, lane_l, lane_u, lane_d;
+    int site0;
+    double2 cf[NCS];
+
+    template <int SC>
+    __device__ __forceinline__ void init(const V3Params &, int part_) {
+        const int lane = threadIdx.x & 31;
+        xl = lane % LXL;
+        part = part_;
+        yh = lane / LXL;
+        lane_r = lane - xl + (xl + 1) % LXL;
+        lane_l = lane - xl + (xl + LXL - 1) % LXL;
+        lane_u = xl + LXL * ((yh + 1) % YH);
+        lane_d = xl + LXL * ((yh + YH - 1) % YH);
+        site0 = LX * RY * yh + 4 * xl;
+    }
+    __device__ __forceinline__ void load_cs(const V3Params &P, int l) {
+        const double2 *g = P.csn + (size_t)l * NCS * 32 + (threadIdx.x & 31);
+#pragma unroll
+        for (int q = 0; q < NCS; q++) cf[q] = __ldg(g + 32 * q);
+    }
+    __device__ __forceinline__ int pair_site(int u) const { return site0 + LX * (u >> 1) + 2 * (u & 1); }
+
+    template <int CL>
+    __device__ __forceinline__ void step(double (&v)[RY][4]) const {
+        if (CL == 0) {
+#pragma unroll
+            for (int r = 0; r < RY; r++) {
+                rot1<0>(v[r][0], v[r][1], cf[Q0 + 2 * r].x, cf[Q0 + 2 * r].y);
+                rot1<0>(v[r][2], v[r][3], cf[Q0 + 2 * r + 1].x, cf[Q0 + 2 * r + 1].y);
+            }
+        } else if (CL == 1) {
+#pragma unroll
+            for (int r = 0; r < RY; r++) {
+                const double fromR = __shfl_sync(0xffffffffu, v[r][0], lane_r);
+                const double fromL = __shfl_sync(0xffffffffu, v[r][3], lane_l);
+                rot1<0>(v[r][1], v[r][2], cf[Q1 + 3 * r].x, cf[Q1 + 3 * r].y);
+                v[r][3] = rot_half<0>(v[r][3], fromR, cf[Q1 + 3 * r + 1].x, cf[Q1 + 3 * r + 1].y);
+                v[r][0] = rot_half<0>(v[r][0], fromL, cf[Q1 + 3 * r + 2].x, cf[Q1 + 3 * r + 2].y);
+            }
+        } else if (CL == 2) {
+#pragma unroll
+            for (int r = 0; r < RY; r += 2)
+#pragma unroll
+                for (int j = 0; j < 4; j++) rot1<0>(v[r][j], v[r + 1][j], cf[Q2 + 2 * r + j].x, cf[Q2 + 2 * r + j].y);
+        } else {
+            double up[4], dn[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                up[j] = __shfl_sync(0xffffffffu, v[0][j], lane_u);
+                dn[j] = __shfl_sync(0xffffffffu, v[RY - 1][j], lane_d);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                v[RY - 1][j] = rot_half<0>(v[RY - 1][j], up[j], cf[Q3 + j].x, cf[Q3 + j].y);
+                v[0][j] = rot_half<0>(v[0][j], dn[j], cf[Q3 + 4 + j].x, cf[Q3 + 4 + j].y);
+            }
+#pragma unroll
+            for (int r = 1; r + 1 < RY; r += 2)
+#pragma unroll
+                for (int j = 0; j < 4; j++) rot1<0>(v[r][j], v[r + 1][j], cf[Q3 + 8 + 2 * (r - 1) + j].x, cf[Q3 + 8 + 2 * (r - 1) + j].y);
+        }
+    }
+    template <int NAT, int SM>
+    __device__ __forceinline__ void apply_B_ev(double (&w)[NV], const double *ev0) const {
+        double (&v)[RY][4] = reinterpret_cast<double (&)[RY][4]>(w);
+        const double *ev = NAT ? ev0 : ev0 + site0;
+        step<3>(v); step<2>(v); step<1>(v); step<0>(v);
+#pragma unroll
+        for (int r = 0; r < RY; r++) {
+            const double2 *q01 = (const double2 *)(ev + (NAT ? 128 * r : LX * r)), *q23 = (const double2 *)(ev + (NAT ? 128 * r + 64 : LX * r + 2));
+            const double2 e01 = SM ? *q01 : __ldg(q01), e23 = SM ? *q23 : __ldg(q23);
+            v[r][0] *= e01.x; v[r][1] *= e01.y; v[r][2] *= e23.x; v[r][3] *= e23.y;
+        }
+        step<0>(v); step<1>(v); step<2>(v); step<3>(v);
+    }
+};
+
+// Chain, N = 64 R sites in natural order, colour 0 = bonds (2k, 2k+1), colour 1 = bonds (2k+1, 2k+2): a lane holds 2 R consecutive
+// sites; pair u = sites 2 R lane + 2u, + 1.  Slots: R even bonds | R - 1 inner odd bonds | to the right lane | from the left lane.
+template <int R>
+struct V3ChainPB {
+    static constexpr int N = 64 * R, NV = 2 * R, NP = R, NCOL = 2, NCS = 2 * R + 1;
+    static constexpr int REGS_LIGHT = 1;
+    int part, lane_r, lane_l, site0;
+    double2 cf[NCS];
+
+    template <int SC>
+    __device__ __forceinline__ void init(const V3Params &, int part_) {
+        const int lane = threadIdx.x & 31;
+        part = part_;
+        lane_r = (lane + 1) & 31;
+        lane_l = (lane + 31) & 31;
+        site0 = 2 * R * lane;
+    }
+    __device__ __forceinline__ void load_cs(const V3Params &P, int l) {
+        const double2 *g = P.csn + (size_t)l * NCS * 32 + (threadIdx.x & 31);
+#pragma unroll
+        for (int q = 0; q < NCS; q++) cf[q] = __ldg(g + 32 * q);
+    }
+    __device__ __forceinline__ int pair_site(int u) const { return site0 + 2 * u; }
+
+    template <int CL>
+    __device__ __forceinline__ void step(double (&v)[NV]) const {
+        if (CL == 0) {
+#pragma unroll
+            for (int u = 0; u < R; u++) rot1<0>(v[2 * u], v[2 * u + 1], cf[u].x, cf[u].y);
+        } else {
+            const double fromR = __shfl_sync(0xffffffffu, v[0], lane_r);
+            const double fromL = __shfl_sync(0xffffffffu, v[NV - 1], lane_l);
+#pragma unroll
+            for (int u = 0; u + 1 < R; u++) rot1<0>(v[2 * u + 1], v[2 * u + 2], cf[R + u].x, cf[R + u].y);
+            v[NV - 1] = rot_half<0>(v[NV - 1], fromR, cf[2 * R - 1].x, cf[2 * R - 1].y);
+            v[0] = rot_half<0>(v[0], fromL, cf[2 * R].x, cf[2 * R].y);
+        }
+    }
+    template <int NAT, int SM>
+    __device__ __forceinline__ void apply_B_ev(double (&v)[NV], const double *ev0) const {
+        const double *ev = NAT ? ev0 : ev0 + site0;
+        step<1>(v); step<0>(v);
+#pragma unroll
+        for (int u = 0; u < NP; u++) {
+            const double2 *q = (const double2 *)(ev + (NAT ? 64 * u : 2 * u));
+            const double2 e = SM ? *q : __ldg(q);
+            v[2 * u] *= e.x; v[2 * u + 1] *= e.y;
+        }
+        step<0>(v); step<1>(v);
     }
 };
 
@@ -344,6 +499,7 @@ k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const do
     lself = lself >= L ? lself - L : lself;
     const double sg = (lB == 0) ? 1.0 : -1.0;
     const int part = E.part;
+    if (active) E.load_cs(P, lB);                       // per-bond engines: this warp's slice of (cosh, sinh) into registers
     const bool publish = (MODE == 2) && (k < ns);
     double *evsm = wsm + (size_t)(P.S + 1) * N + (size_t)k * N;
     double2 *selfsm = reinterpret_cast<double2 *>(wsm) + (size_t)k * NP * 32;
@@ -491,6 +647,26 @@ static v3_kernel_t pick_mode_h(int mode) {
     }
     return nullptr;
 }
+template <class G>
+static v3_kernel_t pick_mode_pb(int mode) {    // per-bond engines (no bulk-copy staged variant: these lattices are L2-resident)
+    switch (mode) {
+        case 0: return k_fdm_v3<0, 0, 0, G>;
+        case 1: return k_fdm_v3<1, 0, 0, G>;
+        case 2: return k_fdm_v3<2, 0, 0, G>;
+        case 3: return k_fdm_v3<2, 1, 0, G>;
+        case 6: return k_fdm_v3<2, 0, 1, G>;
+        case 7: return k_fdm_v3<2, 1, 1, G>;
+    }
+    return nullptr;
+}
+// per-bond geometries: kind 0 square (lxl, ry), kind 2 chain (lxl = site pairs per lane)
+static v3_kernel_t pick3pb(int kind, int a, int b, int mode) {
+    if (kind == 0 && a == 4 && b == 2) return pick_mode_pb<V3LanePB<4, 2>>(mode);      // 16 x 16
+    if (kind == 2 && a == 1) return pick_mode_pb<V3ChainPB<1>>(mode);                  // N = 64
+    if (kind == 2 && a == 2) return pick_mode_pb<V3ChainPB<2>>(mode);                  // N = 128
+    if (kind == 2 && a == 4) return pick_mode_pb<V3ChainPB<4>>(mode);                  // N = 256
+    return nullptr;
+}
 // honeycomb geometries: (lxl, ry) hold (L1, L2) with kind = 1
 static v3_kernel_t pick3h(int L1, int L2, int mode) {
     if (L1 == 24 && L2 == 24) return pick_mode_h<8, 3, 6>(mode);
@@ -536,10 +712,32 @@ static bool fdm_v3_detect_honeycomb(sq_fdm *f) {
     return false;
 }
 
+// chain of N = 64 R sites in natural order: colour 0 = bonds (2k, 2k+1), colour 1 = bonds (2k+1, 2k+2 mod N)
+static bool fdm_v3_detect_chain(sq_fdm *f) {
+    if (!f->sym || f->C != 2 || f->Nh != f->N || f->N % 64) return false;
+    const int N = (int)f->N, R = N / 64;
+    if (!pick3pb(2, R, 0, 2)) return false;
+    for (int c = 0; c < 2; c++) {
+        if (f->chi[c] - f->clo[c] != N / 2) return false;
+        for (int h = f->clo[c]; h < f->chi[c]; h++) {
+            int a = f->h_nt[h].x, b = f->h_nt[h].y;
+            if ((a + 1) % N != b) std::swap(a, b);
+            if ((a + 1) % N != b || (a & 1) != c) return false;
+        }
+    }
+    f->v3_kind = 2; f->v3_lxl = R; f->v3_ry = 0; f->v3_pb_ok = 1;
+    for (int c = 0; c < 4; c++) f->v3_cls[c] = c;
+    for (int mode : {0, 1, 2, 3, 6, 7})
+        SQ_CUDA(cudaFuncSetAttribute(pick3pb(2, R, 0, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+    return true;
+}
+
 void fdm_v3_detect(sq_fdm *f) {
     f->v3_ok = 0;
+    f->v3_pb_ok = 0;
     f->v3_kind = 0;
     if (fdm_v3_detect_honeycomb(f)) return;
+    if (fdm_v3_detect_chain(f)) return;
     if (!f->sym || f->C != 4 || f->Nh != 2 * f->N) return;
     for (int LX : {32, 16}) {
         if (f->N % LX) continue;
@@ -575,12 +773,18 @@ void fdm_v3_detect(sq_fdm *f) {
         for (int c = 0; c < 4; c++) f->v3_cls[c] = cls[c];
         for (int mode : {0, 1, 2, 3, 6, 7, 10})
             SQ_CUDA(cudaFuncSetAttribute(pick3(LXL, RY, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        if (pick3pb(0, LXL, RY, 2)) {
+            f->v3_pb_ok = 1;
+            for (int mode : {0, 1, 2, 3, 6, 7})
+                SQ_CUDA(cudaFuncSetAttribute(pick3pb(0, LXL, RY, mode), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_optin));
+        }
         return;
     }
 }
 
 bool fdm_v3_supported(const sq_fdm *f, int S) {
-    if (!f->v3_ok || !f->cs_coluni) return false;
+    if (!(f->v3_ok && f->cs_coluni) && !f->v3_pb_ok) return false;
+    if (getenv("SQ_V3_NO_PERBOND") && fdm_v3_perbond(f)) return false;
     if (S < 1 || S > 7) return false;
     return (size_t)S * f->N * sizeof(double) <= f->smem_optin;
 }
@@ -611,7 +815,9 @@ int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, d
         P.pre = e ? atoi(e) : ((size_t)40 * f->N * f->L > ((size_t)100 << 20) ? 2 : 0);
     }
     for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = c < f->C ? f->clo[c] : 0; }
-    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p;
+    const bool pb = fdm_v3_perbond(f);
+    if (pb) fdm_v3_prepare_native(f);                   // slot-ordered coefficients (version-checked: a no-op between operator updates)
+    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p; P.csn = f->v3_csn.p;
     static long long *dbg = nullptr;
     if (!dbg && getenv("SQ_DEBUG_STAMPS")) {
         SQ_CUDA(cudaMallocManaged((void **)&dbg, 16 * sizeof(long long)));
@@ -628,11 +834,13 @@ int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, d
     size_t smem = (mode == 2) ? (size_t)S * f->N * sizeof(double) : 0;
     if (native) SQ_REQUIRE(mode == 2 && f->v3_expVn.p && f->v3_expv_version == f->coef_version, "native-order operator not prepared");
     int kmode = ((mode == 2 && g_fuse3) ? 3 : mode) + (native ? 4 : 0);
-    if (kmode == 6 && P.pre == 2 && (size_t)2 * (S + 1) * f->N * sizeof(double) <= f->smem_optin) {       // TMA-staged operands
+    if (kmode == 6 && !pb && P.pre == 2 && (size_t)2 * (S + 1) * f->N * sizeof(double) <= f->smem_optin) {       // TMA-staged operands
         kmode = 10;
         smem = (size_t)2 * (S + 1) * f->N * sizeof(double);
     }
-    v3_kernel_t k = f->v3_kind == 1 ? pick3h(f->v3_lxl, f->v3_ry, kmode) : pick3(f->v3_lxl, f->v3_ry, kmode);
+    v3_kernel_t k = pb ? pick3pb(f->v3_kind, f->v3_lxl, f->v3_ry, kmode)
+                       : (f->v3_kind == 1 ? pick3h(f->v3_lxl, f->v3_ry, kmode) : pick3(f->v3_lxl, f->v3_ry, kmode));
+    SQ_REQUIRE(k != nullptr, "register path: no kernel for this lattice / mode");
     k<<<dim3(grid, 2, nbatch), 32 * (S + 1), smem, f->stream>>>(P, out, in, part, skip);
     SQ_LAUNCH_CHECK();
     f->launches++;
@@ -895,6 +1103,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     lself = lself >= L ? lself - L : lself;
     const int lB = lself, lo = l0 + k - 1;               // owner: slice lo
     const double sg = (lB == 0) ? 1.0 : -1.0;
+    if (active) E.load_cs(P, lB);
     // shared memory (doubles): p [part][S+2][N] | w [part][S][N] | exp(-dtau V) [S+1][N] | r of the halo slices [part][2][N]
     double2 *Pb = reinterpret_cast<double2 *>(smem) + (size_t)part * (S + 2) * (N / 2);
     double2 *W = reinterpret_cast<double2 *>(smem) + (size_t)2 * (S + 2) * (N / 2) + (size_t)part * S * (N / 2);
@@ -1128,6 +1337,13 @@ static v3_resident1_t pick3h_resident1(int L1, int L2) {
     if (L1 == 8 && L2 == 8) return k_cg_v3_resident1<V3Honey<4, 2, 1>, 0>;
     return nullptr;
 }
+static v3_resident1_t pick3pb_resident1(int kind, int a, int b) {
+    if (kind == 0 && a == 4 && b == 2) return k_cg_v3_resident1<V3LanePB<4, 2>, 0>;
+    if (kind == 2 && a == 1) return k_cg_v3_resident1<V3ChainPB<1>, 0>;
+    if (kind == 2 && a == 2) return k_cg_v3_resident1<V3ChainPB<2>, 0>;
+    if (kind == 2 && a == 4) return k_cg_v3_resident1<V3ChainPB<4>, 0>;
+    return nullptr;
+}
 // tau-slab over several GPUs: the geometries of the named multi-GPU configurations
 static v3_resident1_t pick3_resident1_multi(int kind, int a, int b) {
     if (kind == 0 && a == 8 && b == 8) return k_cg_v3_resident1<V3Lane<8, 8>, 1>;          // 32 x 32 square
@@ -1139,8 +1355,11 @@ static v3_resident1_t pick3_resident1_multi(int kind, int a, int b) {
 
 // One-sum resident kernel (k_cg_v3_resident1).  Returns false if it cannot run (the caller falls back to the launch loop in cg.cu).
 static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *state, i64 maxiter) {
-    v3_resident1_t k = f->v3_kind == 1 ? pick3h_resident1(f->v3_lxl, f->v3_ry) : pick3_resident1(f->v3_lxl, f->v3_ry);
-    if (!k || !f->v3_ok || !f->cs_coluni) return false;
+    const bool pb = fdm_v3_perbond(f);
+    if (!fdm_v3_supported(f, 1)) return false;
+    v3_resident1_t k = pb ? pick3pb_resident1(f->v3_kind, f->v3_lxl, f->v3_ry)
+                          : (f->v3_kind == 1 ? pick3h_resident1(f->v3_lxl, f->v3_ry) : pick3_resident1(f->v3_lxl, f->v3_ry));
+    if (!k) return false;
     const int nsl = f->slab_hi - f->slab_lo;
     int S = (nsl + f->num_sms - 1) / f->num_sms;
     if (const char *e = getenv("SQ_V3_RESIDENT_SLAB")) S = atoi(e);
@@ -1153,7 +1372,7 @@ static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *stat
     memset(&P, 0, sizeof(P));
     P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = (int)f->C; P.nphase = 2;
     for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = c < f->C ? f->clo[c] : 0; }
-    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p;
+    P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p; P.csn = f->v3_csn.p;
     SQ_CUDA(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k, T, smem));
@@ -1287,6 +1506,10 @@ __device__ __forceinline__ size_t v3_native_index(int i, int lxl, int ry, int ki
         const int lane = c1 / R1 + G1 * (c2 / R2), u = (c2 % R2) * R1 + c1 % R1;
         return (size_t)(u * 32 + lane) * 2 + orb;
     }
+    if (kind == 2) {                                           // chain: lane holds 2 lxl consecutive sites
+        const int lane = i / (2 * lxl), u = (i % (2 * lxl)) / 2;
+        return (size_t)(u * 32 + lane) * 2 + (i & 1);
+    }
     const int LX = 4 * lxl, x = i % LX, y = i / LX;
     const int lane = x / 4 + lxl * (y / ry), r = y % ry, j = x % 4;
     return (size_t)((r * 2 + j / 2) * 32 + lane) * 2 + (j & 1);
@@ -1309,16 +1532,82 @@ __global__ void k_v3_from_native(double2 *__restrict__ dst, const double *__rest
 }
 struct V3Clo { int lo[4]; };
 __global__ void k_v3_expV_native(double *__restrict__ dst, const double *__restrict__ src, int L, int N, int lxl, int ry,
-                                 const double2 *__restrict__ cs, const V3Clo clo, double2 *__restrict__ ctn, int kind, int ncol) {
+                                 const double2 *__restrict__ cs, const V3Clo clo, double2 *__restrict__ ctn, int kind, int ncol, int scaled) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < (size_t)ncol) { const double2 q = __ldg(cs + clo.lo[idx]); ctn[idx] = make_double2(q.x, q.y / q.x); }
+    if (scaled && idx < (size_t)ncol) { const double2 q = __ldg(cs + clo.lo[idx]); ctn[idx] = make_double2(q.x, q.y / q.x); }
     if (idx >= (size_t)L * N) return;
     const int l = (int)(idx / N), i = (int)(idx % N);
     double g = 1.0;                                            // prod_c cosh_c^2 (each colour is applied twice in B)
+    if (scaled) {
 #pragma unroll
-    for (int c = 0; c < ncol; c++) { const double ch = __ldg(cs + clo.lo[c]).x; g *= ch * ch; }
-    dst[(size_t)l * N + v3_native_index(i, lxl, ry, kind)] = g * src[idx];
+        for (int c = 0; c < ncol; c++) { const double ch = __ldg(cs + clo.lo[c]).x; g *= ch * ch; }
+    }
+    dst[(size_t)l * N + v3_native_index(i, lxl, ry, kind)] = scaled ? g * src[idx] : src[idx];
 }
+// per-bond engines: csn[l][e] = cs[l][map[e]], e = slot * 32 + lane
+__global__ void k_v3_cs_native(double2 *__restrict__ dst, const double2 *__restrict__ cs, const int *__restrict__ map, int L, int Nh, int ne) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)L * ne) return;
+    const int l = (int)(idx / ne), e = (int)(idx % ne);
+    dst[idx] = __ldg(cs + (size_t)l * Nh + __ldg(map + e));
+}
+
+// Host mirror of the slot enumeration of the per-bond engines: the two sites of slot q of every lane (index q * 32 + lane).
+static std::vector<int2> v3pb_slot_sites(int kind, int a, int b) {
+    std::vector<int2> out;
+    if (kind == 2) {
+        const int R = a, N = 64 * R, NCS = 2 * R + 1;
+        out.resize((size_t)NCS * 32);
+        for (int lane = 0; lane < 32; lane++) {
+            const int s0 = 2 * R * lane;
+            int q = 0;
+            for (int u = 0; u < R; u++) out[(q++) * 32 + lane] = make_int2(s0 + 2 * u, s0 + 2 * u + 1);
+            for (int u = 0; u + 1 < R; u++) out[(q++) * 32 + lane] = make_int2(s0 + 2 * u + 1, s0 + 2 * u + 2);
+            out[(q++) * 32 + lane] = make_int2(s0 + 2 * R - 1, (s0 + 2 * R) % N);
+            out[(q++) * 32 + lane] = make_int2((s0 + N - 1) % N, s0);
+        }
+        return out;
+    }
+    const int LXL = a, RY = b, YH = 32 / LXL, LX = 4 * LXL, NCS = 9 * RY + 4;
+    out.resize((size_t)NCS * 32);
+    auto site = [&](int xl, int yh, int r, int j) { return LX * (RY * ((yh + YH) % YH) + r) + 4 * ((xl + LXL) % LXL) + j; };
+    for (int lane = 0; lane < 32; lane++) {
+        const int xl = lane % LXL, yh = lane / LXL;
+        int q = 0;
+        for (int r = 0; r < RY; r++) {
+            out[(q++) * 32 + lane] = make_int2(site(xl, yh, r, 0), site(xl, yh, r, 1));
+            out[(q++) * 32 + lane] = make_int2(site(xl, yh, r, 2), site(xl, yh, r, 3));
+        }
+        for (int r = 0; r < RY; r++) {
+            out[(q++) * 32 + lane] = make_int2(site(xl, yh, r, 1), site(xl, yh, r, 2));
+            out[(q++) * 32 + lane] = make_int2(site(xl, yh, r, 3), site(xl + 1, yh, r, 0));
+            out[(q++) * 32 + lane] = make_int2(site(xl - 1, yh, r, 3), site(xl, yh, r, 0));
+        }
+        for (int r = 0; r < RY; r += 2)
+            for (int j = 0; j < 4; j++) out[(q++) * 32 + lane] = make_int2(site(xl, yh, r, j), site(xl, yh, r + 1, j));
+        for (int j = 0; j < 4; j++) out[(q++) * 32 + lane] = make_int2(site(xl, yh, RY - 1, j), site(xl, yh + 1, 0, j));
+        for (int j = 0; j < 4; j++) out[(q++) * 32 + lane] = make_int2(site(xl, yh - 1, RY - 1, j), site(xl, yh, 0, j));
+        for (int r = 1; r + 1 < RY; r += 2)
+            for (int j = 0; j < 4; j++) out[(q++) * 32 + lane] = make_int2(site(xl, yh, r, j), site(xl, yh, r + 1, j));
+    }
+    return out;
+}
+static void v3pb_build_map(sq_fdm *f) {
+    const std::vector<int2> ss = v3pb_slot_sites(f->v3_kind, f->v3_lxl, f->v3_ry);
+    std::map<std::pair<int, int>, int> bond;
+    for (int h = 0; h < (int)f->Nh; h++) bond[std::make_pair(std::min(f->h_nt[h].x, f->h_nt[h].y), std::max(f->h_nt[h].x, f->h_nt[h].y))] = h;
+    std::vector<int> map(ss.size());
+    for (size_t e = 0; e < ss.size(); e++) {
+        auto it = bond.find(std::make_pair(std::min(ss[e].x, ss[e].y), std::max(ss[e].x, ss[e].y)));
+        SQ_REQUIRE(it != bond.end(), "register path: a slot of the per-bond engine has no bond in the neighbour table");
+        map[e] = it->second;
+    }
+    f->v3_ncs = (int)(ss.size() / 32);
+    f->v3_csmap.alloc(map.size());
+    f->v3_csmap.upload(map.data(), map.size(), f->stream);
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
+}
+
 
 void fdm_v3_to_native(sq_fdm *f, double2 *dst, const double2 *src) {
     const size_t n = (size_t)f->L * f->N;
@@ -1336,12 +1625,22 @@ void fdm_v3_from_native(sq_fdm *f, double2 *dst, const double2 *src) {
 void fdm_v3_prepare_native(sq_fdm *f) {
     const size_t n = (size_t)f->L * f->N;
     if (!f->v3_expVn.p) { f->v3_expVn.alloc(n); f->v3_ctn.alloc(4); f->v3_x.alloc(n); f->v3_r.alloc(n); f->v3_expv_version = -1; }
-    if (f->v3_expv_version == f->coef_version) return;
+    const int pb = fdm_v3_perbond(f) ? 1 : 0;
+    if (f->v3_expv_version == f->coef_version && f->v3_native_pb == pb) return;
     V3Clo clo;
     for (int c = 0; c < 4; c++) clo.lo[c] = c < f->C ? f->clo[c] : 0;
     k_v3_expV_native<<<(unsigned)((n + 255) / 256), 256, 0, f->stream>>>(f->v3_expVn.p, f->expV.p, (int)f->L, (int)f->N, f->v3_lxl, f->v3_ry,
-                                                                        f->cs.p, clo, f->v3_ctn.p, f->v3_kind, (int)f->C);
+                                                                        f->cs.p, clo, f->v3_ctn.p, f->v3_kind, (int)f->C, pb ? 0 : 1);
     SQ_LAUNCH_CHECK();
     f->launches++;
+    if (pb) {
+        if (!f->v3_csmap.p) v3pb_build_map(f);
+        const size_t ne = (size_t)f->v3_ncs * 32, tot = ne * f->L;
+        if (f->v3_csn.n < tot) f->v3_csn.alloc(tot);
+        k_v3_cs_native<<<(unsigned)((tot + 255) / 256), 256, 0, f->stream>>>(f->v3_csn.p, f->cs.p, f->v3_csmap.p, (int)f->L, (int)f->Nh, (int)ne);
+        SQ_LAUNCH_CHECK();
+        f->launches++;
+    }
     f->v3_expv_version = f->coef_version;
+    f->v3_native_pb = pb;
 }

@@ -75,7 +75,13 @@ struct sq_fdm {
     int cs_coluni = 0;                       // ... and are equal for all bonds of one colour (uniform hopping): fdm_v3.cu
     // register path (fdm_v3.cu): rectangular lattice, one warp per slice
     int v3_ok = 0, v3_lxl = 0, v3_ry = 0, v3_cls[4] = {0, 0, 0, 0};
-    int v3_kind = 0;                         // 0: square (v3_lxl = Lx / 4, v3_ry = rows per lane), 1: honeycomb (v3_lxl = L1, v3_ry = L2)
+    int v3_kind = 0;                         // 0: square (v3_lxl = Lx / 4, v3_ry = rows per lane), 1: honeycomb (v3_lxl = L1, v3_ry = L2),
+                                             // 2: chain (v3_lxl = site pairs per lane: N = 64 v3_lxl)
+    int v3_pb_ok = 0;                        // a per-bond engine exists: (cosh, sinh) of every bond and slice in registers (SSH couplings)
+    int v3_ncs = 0;                          // ... coefficient slots per lane and slice
+    DevBuf<int> v3_csmap;                    // ... bond index of slot (q, lane)
+    DevBuf<double2> v3_csn;                  // ... coefficients in slot order [l][q][lane], rebuilt with v3_expVn
+    int v3_native_pb = -1;                   // engine family the native-order copies were prepared for
     int v3_S = 3;                            // slices per CTA of the register path
     int use_v3 = 0;                          // stand-alone products (library-order vectors): chosen by timing
     int v3_cg = 0;                           // CG solves: register path whenever it applies (native order + resident kernel)
@@ -316,6 +322,9 @@ void fdm_select_tuning(sq_fdm *f);
 int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native = false,
                   int nbatch = 1, size_t bstride = 0, int bpart = 0);
 bool fdm_v3_supported(const sq_fdm *f, int S);
+// engine family of the register path: uniform engines (one cosh / tanh per colour) when the hoppings are colour-uniform and the lattice
+// has one, otherwise the per-bond engines
+inline bool fdm_v3_perbond(const sq_fdm *f) { return !(f->v3_ok && f->cs_coluni); }
 int tau_fft_launch_batch(cudaStream_t stream, const std::vector<int> &radices, int L, int N, double2 *out, const double2 *in, bool inverse,
                          bool twist, const double2 *tw, const double2 *theta, const double *scale1, const double2 *dot_with,
                          double *dot_part, const CgState *skip, size_t smem_limit, int nbatch, size_t bstride, const FftCgUpdate *upd = nullptr);

@@ -137,6 +137,11 @@ SQUARES = {
     "hc8": lambda: mdl.holstein_honeycomb(8, 1.0),
     "hc16": lambda: mdl.holstein_honeycomb(16, 0.6),
     "hc24": lambda: mdl.holstein_honeycomb(24, 0.5),
+    # per-bond engines (SSH couplings: every bond of every slice has its own cosh / sinh, held in registers)
+    "bssh16": lambda: mdl.bssh_square(16, 16, 2.0),         # cfg3's lattice
+    "ossh64": lambda: mdl.ossh_chain(64, 2.0),              # cfg2's lattice
+    "ossh128": lambda: mdl.ossh_chain(128, 1.5),
+    "ossh256": lambda: mdl.ossh_chain(256, 1.0),
 }
 
 
@@ -169,20 +174,28 @@ def test_register_path_products(name):
 
 
 def test_register_path_requires_uniform_colours_and_canonical_order():
-    """Disordered hoppings or a permuted colour order must fall back to the shared-memory kernels (and stay correct)."""
+    """Disordered hoppings on a lattice without a per-bond engine, or a permuted colour order, must fall back to the shared-memory
+    kernels (and stay correct); on 16 x 16 the disordered operator runs on the per-bond register engine, bit-identical."""
     from smoqyelph_b200 import api
-    m = mdl.holstein_square(16, 16, 0.5)
     rng = np.random.default_rng(3)
-    V, t = dr.build_Vt(m, m.random_fields(rng))
-    t = t * (1.0 + 0.1 * rng.standard_normal(t.shape[0]))[:, None]          # bond disorder: colours no longer uniform
-    ref = orc.RefFDM(m, sym=True)
-    ref.update(V, t)
-    fdm = api.FermionDetMatrix(m, sym=True)
-    fdm.update(V, t)
-    fdm.set_fast_path(2)
-    assert fdm.tuning["path"] != 3
+    for (lx, ly, want3) in ((32, 32, False), (16, 16, True)):
+        m = mdl.holstein_square(lx, ly, 0.5)
+        V, t = dr.build_Vt(m, m.random_fields(rng))
+        t = t * (1.0 + 0.1 * rng.standard_normal(t.shape[0]))[:, None]          # bond disorder: colours no longer uniform
+        ref = orc.RefFDM(m, sym=True)
+        ref.update(V, t)
+        fdm = api.FermionDetMatrix(m, sym=True)
+        fdm.update(V, t)
+        v = rand_cvec(rng, m)
+        fdm.set_fast_path(1)
+        base = fdm.mul_MtM(v)
+        fdm.set_fast_path(2)
+        assert (fdm.tuning["path"] == 3) == want3, (lx, ly, fdm.tuning)
+        got = fdm.mul_MtM(v)
+        assert relerr(got, ref.mul_MtM(v)) < RTOL
+        assert np.array_equal(got, base)
+    m = mdl.holstein_square(16, 16, 0.5)
     v = rand_cvec(rng, m)
-    assert relerr(fdm.mul_MtM(v), ref.mul_MtM(v)) < RTOL
     # y colours before x colours: a valid checkerboard, but not the order the register kernels are written for
     nt, col, _ = mdl._square_bonds(16, 16)
     m2 = mdl.holstein_square(16, 16, 0.5)
@@ -198,7 +211,7 @@ def test_register_path_requires_uniform_colours_and_canonical_order():
 
 
 @pytest.mark.parametrize("solver", ["resident", "launches", "launches_tma"])
-@pytest.mark.parametrize("name", ["h16x16", "h32x16", "h32x32", "hc8", "hc24"])
+@pytest.mark.parametrize("name", ["h16x16", "h32x16", "h32x32", "hc8", "hc24", "bssh16", "ossh64", "ossh256"])
 def test_register_path_cg(name, solver, monkeypatch):
     """CG on the register path in native order: the whole-solve resident kernel (one grid-wide sum per iteration) and the
     two-launches-per-iteration loop (its only fallback) against the oracle's CG."""
@@ -238,11 +251,11 @@ def test_register_path_cg(name, solver, monkeypatch):
     assert it00 == 0 and abs(eps00 - 1.0) < 1e-12
 
 
-@pytest.mark.parametrize("name", ["cfg3", "cfg4", "cfg5"])
+@pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4", "cfg5"])
 def test_cg_iteration_counts_at_named_sizes(name):
     """CG iteration counts within +-1 of the reference recurrence (src/IterativeSolvers/ConjugateGradient.jl:93-167) at the FULL size of
     the named configurations 3, 4, 5 and at the production tolerances 1e-5 / 1e-10, on tau-smooth synthetic fields.
-    cfg4 / cfg5 run the whole-solve resident register kernel the benchmark times; cfg3 the cooperative shared-memory kernel."""
+    All three run the whole-solve resident register kernel (cfg4 / cfg5: uniform engines, cfg3: per-bond engine)."""
     from smoqyelph_b200 import api
     m = mdl.config(name)
     rng = np.random.default_rng(11)
@@ -260,8 +273,7 @@ def test_cg_iteration_counts_at_named_sizes(name):
         assert epsg < tol and epsr < tol
         assert relerr(xg, xr) < 50 * tol                     # both inside the tolerance ball (cond(M^T M) ~ 10 on these fields)
     st = fdm.stats
-    if name in ("cfg4", "cfg5"):
-        assert st["cg_resident"] - st0["cg_resident"] == 2, st
+    assert st["cg_resident"] - st0["cg_resident"] == 2, st       # cfg3: per-bond register engine
     assert st["watchdog_aborts"] == 0
 
 

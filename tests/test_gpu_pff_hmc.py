@@ -31,10 +31,12 @@ MODELS = {
     "sq16": lambda: mdl.holstein_square(16, 16, 0.5),
     "sq32": lambda: mdl.holstein_square(32, 32, 0.3),
     "hc8": lambda: mdl.holstein_honeycomb(8, 0.4),
+    # ... with the per-bond register engines (SSH couplings; cfg2s above is the chain engine, cfg3r the 16 x 16 one of cfg3)
+    "cfg3r": lambda: mdl.bssh_square(16, 16, 0.5),
     # dispersive phonon couplings (nearest-neighbour springs, quadratic + quartic) on top of a Holstein model with anharmonic on-site terms
     "disp": lambda: mdl.with_dispersion(mdl.holstein_square(4, 4, 0.5, ph_sym=False), 0.8, 0.4),
 }
-REGISTER_PATH = ("sq16", "sq32", "hc8")
+REGISTER_PATH = ("sq16", "sq32", "hc8", "cfg2s", "cfg3r")
 
 
 def assert_register_path(name, sym, gf, st0):
