@@ -954,6 +954,7 @@ struct CgResident1 {
     unsigned int slot_stride;   // bytes
     size_t slot_array_bytes;
     double *halo;               // [cta][side][part][N] boundary slices of z
+    unsigned long long *flags;  // [cta] (128 bytes apart): last iteration whose boundary z of that CTA is visible device-wide
     int maxiter;
     // tau-slab mode over several GPUs (MULTI kernels): every rank runs this kernel on its slab; the grid-wide sums run over the
     // CTAs of ALL ranks and the boundary z of the first / last CTA travels to the neighbour rank.  Each rank owns a mailbox
@@ -972,12 +973,24 @@ __device__ __forceinline__ double v3_tag(double x, long long tag) { return __lon
 
 // Two warps share the work: warp `half` (0 or 1) publishes and polls the 16-byte half `half` of every slot -- (a, b) or (c, d).
 // All lanes hold the CTA's two partials of that half in t[]; returns the two grid totals (identical bits in every CTA).
+#ifdef SQ_V3_STAMPS
+__device__ long long g_sumdbg[8];       // profiling build: fence cycles, store -> all slots valid, poll rounds, sums (CTA nblk / 2, warp 0)
+#endif
+template <bool FENCE>
 __device__ __forceinline__ void v3_slot_sum2(double (&t)[2], int half, char *slots, unsigned int stride_bytes, long long tag, unsigned int nblk,
                                              unsigned int bid, bool &bad) {
     const int lane = threadIdx.x & 31;
+#ifdef SQ_V3_STAMPS
+    const bool sdbg = bid == nblk / 2 && half == 0 && lane == 0;
+    const long long ts0 = clock64();
+    long long ts1 = ts0, rounds = 0;
+#endif
     if (lane == 0) {
         char *mine = slots + (size_t)bid * stride_bytes + 16 * half;
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (FENCE) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#ifdef SQ_V3_STAMPS
+        ts1 = clock64();
+#endif
         asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(mine), "d"(v3_tag(t[0], tag)), "d"(v3_tag(t[1], tag)) : "memory");
     }
     double s[2] = {0.0, 0.0};
@@ -985,6 +998,9 @@ __device__ __forceinline__ void v3_slot_sum2(double (&t)[2], int half, char *slo
     for (unsigned int base = 0; base < nblk; base += 256) {
         long long val[8][2];
         while (true) {
+#ifdef SQ_V3_STAMPS
+            rounds++;
+#endif
 #pragma unroll
             for (int u = 0; u < 8; u++) {                         // all loads first, then the checks
                 const unsigned int q = base + lane + 32 * u;
@@ -994,6 +1010,10 @@ __device__ __forceinline__ void v3_slot_sum2(double (&t)[2], int half, char *slo
             bool ready = true;
 #pragma unroll
             for (int u = 0; u < 8; u++) ready = ready && ((val[u][0] & 3LL) == tag) && ((val[u][1] & 3LL) == tag);
+#ifdef SQ_V3_STAMPS
+            if (sdbg && rounds == 1) g_sumdbg[4] += clock64() - ts1;      // one poll round trip
+            if (sdbg && !ready) { int miss = 0; for (int u = 0; u < 8; u++) miss += ((val[u][0] & 3LL) != tag); g_sumdbg[5] += miss; }
+#endif
             if (ready) break;
             if (clock64() - t0 > 4000000000LL) { bad = true; break; }
         }
@@ -1005,6 +1025,9 @@ __device__ __forceinline__ void v3_slot_sum2(double (&t)[2], int half, char *slo
     }
     t[0] = warp_sum(s[0]);
     t[1] = warp_sum(s[1]);
+#ifdef SQ_V3_STAMPS
+    if (sdbg) { g_sumdbg[0] += ts1 - ts0; g_sumdbg[1] += clock64() - ts1; g_sumdbg[2] += rounds; g_sumdbg[3] += 1; }
+#endif
 }
 
 // Multi-GPU versions: publish into every rank's mailbox (system scope), poll the own one.
@@ -1099,6 +1122,12 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     const unsigned int nblk = gridDim.x, bid = blockIdx.x;
     const unsigned int gtot = MULTI ? C.gtot : nblk, gid = MULTI ? C.gid0 + bid : bid;
     const bool active = k <= ns, owner = active && k >= 1, publish = k < ns;
+    // Single GPU: the device-scope fence that publishes the boundary z (>= 1000 cycles on this part) is executed by a warp that is
+    // idle at that point -- the slice-less warp of part 1 -- in parallel with the (fence-free) grid-wide sum; it then raises this CTA's
+    // flag to the iteration number, and the neighbours wait for the flag before they fetch the boundary z.
+    constexpr bool FLAGS = !MULTI;
+    const bool fwarp = FLAGS && part == 1 && k == 0, bwarp = FLAGS && owner && (k == 1 || k == ns);
+    const int fcnt = 32 * (1 + (ns > 1 ? 4 : 2)), tcnt = (int)blockDim.x;
     int lself = l0 + k;
     lself = lself >= L ? lself - L : lself;
     const int lB = lself, lo = l0 + k - 1;               // owner: slice lo
@@ -1205,6 +1234,10 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
                     if (h0) h0[el(u)] = make_double2(z0, z1);
                     if (h1) h1[el(u)] = make_double2(z0, z1);
                 }
+            if (bwarp) {                                  // boundary z stored: hand it to the fencing warp
+                __threadfence_block();
+                asm volatile("bar.arrive 3, %0;" ::"r"(fcnt) : "memory");
+            }
         }
         R1_STAMP(4);
         // ---- the grid-wide sum of (a, b, c, d)
@@ -1213,7 +1246,20 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
             const double t = warp_sum(acc[c]);
             if (lane == 0) red[c * 8 + wid] = t;
         }
-        __syncthreads();
+        if (fwarp) {                                      // arrives without waiting, then: boundary z of both parts -> fence -> flag
+            __threadfence_block();
+            asm volatile("bar.arrive 4, %0;" ::"r"(tcnt) : "memory");       // (its own barrier id: this warp runs ahead of the others)
+            asm volatile("bar.sync 3, %0;" ::"r"(fcnt) : "memory");
+            if (lane == 0) {
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(C.flags + (size_t)bid * 16), "l"(itg) : "memory");
+            }
+            __syncwarp();
+        } else if (FLAGS) {
+            asm volatile("bar.sync 4, %0;" ::"r"(tcnt) : "memory");
+        } else {
+            __syncthreads();
+        }
         R1_STAMP(5);
         if (wid < 2) {                                    // warp 0: (a, b), warp 1: (c, d)
             const int nw = blockDim.x >> 5;
@@ -1222,7 +1268,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
             for (int c = 0; c < 2; c++) { t[c] = 0.0; for (int w = 0; w < nw; w++) t[c] += red[(2 * wid + c) * 8 + w]; }
             bool bad = false;
             if (MULTI) v3_slot_sum2_multi(t, wid, C.mail, C.world, C.rank, (size_t)(itg & 1) * C.slot_array_bytes, C.slot_stride, (long long)(itg & 3), gtot, gid, bad);
-            else v3_slot_sum2(t, wid, C.slots + (size_t)(it & 1) * C.slot_array_bytes, C.slot_stride, (long long)(it & 3), nblk, bid, bad);
+            else v3_slot_sum2<false>(t, wid, C.slots + (size_t)(it & 1) * C.slot_array_bytes, C.slot_stride, (long long)(it & 3), nblk, bid, bad);
             if (lane == 0) { sh[2 * wid] = t[0]; sh[2 * wid + 1] = t[1]; if (bad) sh[5] = 1.0; }
         }
         R1_STAMP(6);
@@ -1262,6 +1308,19 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
             if (MULTI) {
                 if (bid == nblk - 1) gu = inbox(C.rank, (int)(itg & 1), 1);
                 if (bid == 0) gl = inbox(C.rank, (int)(itg & 1), 0);
+            }
+            if (FLAGS) {                                  // the neighbours' boundary z of this iteration is visible once their flag says so
+                if (lane < 2) {
+                    const unsigned long long *fl = C.flags + (size_t)(lane ? right : left) * 16;
+                    unsigned long long got;
+                    const long long t0 = clock64();
+                    while (true) {
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(fl) : "memory");
+                        if (got >= itg) break;
+                        if (clock64() - t0 > 4000000000LL) { sh[5] = 1.0; break; }
+                    }
+                }
+                __syncwarp();
             }
 #pragma unroll
             for (int u = 0; u < N / 64; u++) { const double2 q = __ldcg(gl + lane + 32 * u); xr[2 * u] = q.x; xr[2 * u + 1] = q.y; }
@@ -1381,14 +1440,16 @@ static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *stat
     if (const char *e = getenv("SQ_V3_SLOT_STRIDE")) stride_bytes = (unsigned)atoi(e);
     stride_bytes = std::max(32u, stride_bytes / 32 * 32);
     const size_t arr = (size_t)grid * stride_bytes;
-    if (f->v3_slots.n < 3 * arr) f->v3_slots.alloc(3 * arr);
-    SQ_CUDA(cudaMemsetAsync(f->v3_slots.p, 0, 3 * arr, f->stream));
+    const size_t slot_bytes = 3 * arr + (size_t)grid * 128;
+    if (f->v3_slots.n < slot_bytes) f->v3_slots.alloc(slot_bytes);
+    SQ_CUDA(cudaMemsetAsync(f->v3_slots.p, 0, slot_bytes, f->stream));
     const size_t nh = (size_t)8 * grid * f->N;
     if (f->v3_halo.n < nh) f->v3_halo.alloc(nh);
     CgResident1 C;
     memset(&C, 0, sizeof(C));
     C.x = (double *)x; C.r = (const double *)r; C.state = state;
     C.slots = f->v3_slots.p; C.slot_array_bytes = arr; C.slots_check = f->v3_slots.p + 2 * arr; C.slot_stride = stride_bytes;
+    C.flags = reinterpret_cast<unsigned long long *>(f->v3_slots.p + 3 * arr);
     C.halo = f->v3_halo.p; C.maxiter = (int)std::min<i64>(maxiter, 2000000000);
 #ifdef SQ_V3_STAMPS
     static long long *dbg = nullptr;
@@ -1414,6 +1475,12 @@ static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *stat
                     w ? "first owner" : "halo warp, sums", dbg[16 * w + 10], tot);
             for (int q = 0; q < 10; q++) fprintf(stderr, "    %-36s %8.0f\n", names[q], dbg[16 * w + q] / n);
         }
+        long long sd[8];
+        cudaMemcpyFromSymbol(sd, g_sumdbg, sizeof(sd));
+        const double ns_ = (double)std::max<long long>(sd[3], 1);
+        fprintf(stderr, "grid-wide sum of that CTA (lane 0 of warp 0, per sum): fence %.0f, store -> total %.0f cycles, %.2f poll rounds, first round trip %.0f "
+                        "cycles, %.1f slots of this lane missing per failed round\n", sd[0] / ns_, sd[1] / ns_, sd[2] / ns_, sd[4] / ns_,
+                sd[2] > sd[3] ? (double)sd[5] / (double)(sd[2] - sd[3]) : 0.0);
     }
 #endif
     return true;
