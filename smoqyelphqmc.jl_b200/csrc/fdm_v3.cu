@@ -967,6 +967,7 @@ struct CgResident1 {
     unsigned long long it_base;
     char *mail[8];
     size_t off_check, off_inbox;
+    size_t off_flags;           // boundary-z flags in the mailbox: +0 from the left rank, +128 from the right rank, +256 + 128 cta: own CTAs
 };
 
 __device__ __forceinline__ double v3_tag(double x, long long tag) { return __longlong_as_double((__double_as_longlong(x) & ~3LL) | tag); }
@@ -1031,11 +1032,12 @@ __device__ __forceinline__ void v3_slot_sum2(double (&t)[2], int half, char *slo
 }
 
 // Multi-GPU versions: publish into every rank's mailbox (system scope), poll the own one.
+template <bool FENCE>
 __device__ __forceinline__ void v3_slot_sum2_multi(double (&t)[2], int half, char *const *mail, int world, int rank, size_t slot_off,
                                                    unsigned int stride_bytes, long long tag, unsigned int gtot, unsigned int gid, bool &bad) {
     const int lane = threadIdx.x & 31;
     if (lane == 0) {
-        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        if (FENCE) asm volatile("fence.acq_rel.sys;" ::: "memory");
         for (int q = 0; q < world; q++) {
             char *dst = mail[q] + slot_off + (size_t)gid * stride_bytes + 16 * half;
             asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(v3_tag(t[0], tag)), "d"(v3_tag(t[1], tag)) : "memory");
@@ -1125,7 +1127,11 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     // Single GPU: the device-scope fence that publishes the boundary z (>= 1000 cycles on this part) is executed by a warp that is
     // idle at that point -- the slice-less warp of part 1 -- in parallel with the (fence-free) grid-wide sum; it then raises this CTA's
     // flag to the iteration number, and the neighbours wait for the flag before they fetch the boundary z.
-    constexpr bool FLAGS = !MULTI;
+    // Several GPUs: the same with a system-scope fence; the first / last CTA of a slab also raises a flag in the neighbour rank's mailbox.
+    constexpr bool FLAGS = true;
+    auto flag_of = [&](unsigned int cta) -> unsigned long long * {
+        return MULTI ? reinterpret_cast<unsigned long long *>(C.mail[C.rank] + C.off_flags + 256 + (size_t)cta * 128) : C.flags + (size_t)cta * 16;
+    };
     const bool fwarp = FLAGS && part == 1 && k == 0, bwarp = FLAGS && owner && (k == 1 || k == ns);
     const int fcnt = 32 * (1 + (ns > 1 ? 4 : 2)), tcnt = (int)blockDim.x;
     int lself = l0 + k;
@@ -1251,8 +1257,15 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
             asm volatile("bar.arrive 4, %0;" ::"r"(tcnt) : "memory");       // (its own barrier id: this warp runs ahead of the others)
             asm volatile("bar.sync 3, %0;" ::"r"(fcnt) : "memory");
             if (lane == 0) {
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(C.flags + (size_t)bid * 16), "l"(itg) : "memory");
+                if (MULTI) {
+                    asm volatile("fence.acq_rel.sys;" ::: "memory");
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(flag_of(bid)), "l"(itg) : "memory");
+                    if (bid == 0) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(C.mail[rank_l] + C.off_flags + 128), "l"(itg) : "memory");
+                    if (bid == nblk - 1) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(C.mail[rank_r] + C.off_flags), "l"(itg) : "memory");
+                } else {
+                    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(flag_of(bid)), "l"(itg) : "memory");
+                }
             }
             __syncwarp();
         } else if (FLAGS) {
@@ -1267,7 +1280,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
 #pragma unroll
             for (int c = 0; c < 2; c++) { t[c] = 0.0; for (int w = 0; w < nw; w++) t[c] += red[(2 * wid + c) * 8 + w]; }
             bool bad = false;
-            if (MULTI) v3_slot_sum2_multi(t, wid, C.mail, C.world, C.rank, (size_t)(itg & 1) * C.slot_array_bytes, C.slot_stride, (long long)(itg & 3), gtot, gid, bad);
+            if (MULTI) v3_slot_sum2_multi<false>(t, wid, C.mail, C.world, C.rank, (size_t)(itg & 1) * C.slot_array_bytes, C.slot_stride, (long long)(itg & 3), gtot, gid, bad);
             else v3_slot_sum2<false>(t, wid, C.slots + (size_t)(it & 1) * C.slot_array_bytes, C.slot_stride, (long long)(it & 3), nblk, bid, bad);
             if (lane == 0) { sh[2 * wid] = t[0]; sh[2 * wid + 1] = t[1]; if (bad) sh[5] = 1.0; }
         }
@@ -1311,13 +1324,16 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
             }
             if (FLAGS) {                                  // the neighbours' boundary z of this iteration is visible once their flag says so
                 if (lane < 2) {
-                    const unsigned long long *fl = C.flags + (size_t)(lane ? right : left) * 16;
+                    const unsigned long long *fl = flag_of(lane ? right : left);
+                    if (MULTI && lane == 0 && bid == 0) fl = reinterpret_cast<const unsigned long long *>(C.mail[C.rank] + C.off_flags);
+                    if (MULTI && lane == 1 && bid == nblk - 1) fl = reinterpret_cast<const unsigned long long *>(C.mail[C.rank] + C.off_flags + 128);
                     unsigned long long got;
                     const long long t0 = clock64();
                     while (true) {
-                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(fl) : "memory");
+                        if (MULTI) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(fl) : "memory");
+                        else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(fl) : "memory");
                         if (got >= itg) break;
-                        if (clock64() - t0 > 4000000000LL) { sh[5] = 1.0; break; }
+                        if (clock64() - t0 > (MULTI ? 8000000000LL : 4000000000LL)) { sh[5] = 1.0; break; }
                     }
                 }
                 __syncwarp();
@@ -1491,7 +1507,8 @@ static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *stat
 static const size_t V3_MAIL_STRIDE = 64, V3_MAIL_MAXCTA = 148 * 8;
 static size_t v3_mail_off_check() { return 2 * V3_MAIL_MAXCTA * V3_MAIL_STRIDE; }
 static size_t v3_mail_off_inbox() { return 3 * V3_MAIL_MAXCTA * V3_MAIL_STRIDE; }
-size_t fdm_v3_mailbox_bytes(const sq_fdm *f) { return v3_mail_off_inbox() + (size_t)8 * f->N * sizeof(double); }
+static size_t v3_mail_off_flags(const sq_fdm *f) { return v3_mail_off_inbox() + (size_t)8 * f->N * sizeof(double); }
+size_t fdm_v3_mailbox_bytes(const sq_fdm *f) { return v3_mail_off_flags(f) + 256 + (size_t)148 * 128; }
 
 // Can this slab configuration run the multi-GPU resident kernel?  Fills S and the CTA counts of all ranks.
 static bool v3_multi_plan(const sq_fdm *f, int *S_out, std::vector<int> *ctas) {
@@ -1547,7 +1564,7 @@ bool fdm_v3_cg_resident1_multi(sq_fdm *f, double2 *x, double2 *r, CgState *state
     C.world = f->world; C.rank = f->rank; C.gtot = 0; C.gid0 = 0;
     for (int q = 0; q < f->world; q++) { if (q < f->rank) C.gid0 += ctas[q]; C.gtot += ctas[q]; C.mail[q] = (char *)f->mail_ptr[q]; }
     C.it_base = f->v3_it_base;
-    C.off_check = v3_mail_off_check(); C.off_inbox = v3_mail_off_inbox();
+    C.off_check = v3_mail_off_check(); C.off_inbox = v3_mail_off_inbox(); C.off_flags = v3_mail_off_flags(f);
     void *args[] = {(void *)&P, (void *)&C};
     SQ_CUDA(cudaLaunchCooperativeKernel((const void *)k, dim3(grid), dim3(T), args, smem, f->stream));
     f->launches++;
