@@ -1157,6 +1157,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     double eps = C.state->eps;
     int it = 0, done = 0;
     double v[G::NV], xr[G::NV], rr_[G::NV];
+    double rr_lane = 0.0;        // this lane's share of |r|^2 of the stored residual: accumulated by the update, summed with the next iteration's dots
     if (threadIdx.x == 0) sh[5] = 0.0;
 #ifdef SQ_V3_STAMPS
     // per-phase cycle counts of one owner warp (k = 1) and the halo warp (k = 0) of a CTA in the middle of the grid (profiling build only)
@@ -1177,6 +1178,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
                 const double2 a = gx[el(u)], b = gr[el(u)];
                 xr[2 * u] = a.x; xr[2 * u + 1] = a.y;
                 rr_[2 * u] = b.x; rr_[2 * u + 1] = b.y;
+                rr_lane += b.x * b.x; rr_lane += b.y * b.y;
                 Pb[(size_t)k * (N / 2) + el(u)] = b;
             }
     }
@@ -1236,10 +1238,10 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
                     const double r0 = rr_[2 * u], r1 = rr_[2 * u + 1];
                     acc[1] += r0 * z0; acc[1] += r1 * z1;
                     acc[2] += z0 * z0; acc[2] += z1 * z1;
-                    acc[3] += r0 * r0; acc[3] += r1 * r1;
                     if (h0) h0[el(u)] = make_double2(z0, z1);
                     if (h1) h1[el(u)] = make_double2(z0, z1);
                 }
+            acc[3] = rr_lane;                             // same elements, same order as a fresh accumulation: same bits
             if (bwarp) {                                  // boundary z stored: hand it to the fencing warp
                 __threadfence_block();
                 asm volatile("bar.arrive 3, %0;" ::"r"(fcnt) : "memory");
@@ -1307,6 +1309,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
                     chk += r0 * r0; chk += r1 * r1;
                     Pb[(size_t)k * (N / 2) + el(u)] = make_double2(fma(beta, pv.x, r0), fma(beta, pv.y, r1));
                 }
+            rr_lane = chk;
         }
         // Warp 0 of each part owns no slice.  Right after the sum it fetches the neighbours' boundary z (published before the sum, so
         // visible now) into registers -- its xr / rr_ registers, which only owners use: N / 64 double2 per lane = NV doubles -- so that
