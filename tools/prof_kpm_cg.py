@@ -11,6 +11,7 @@ fdm = api.FermionDetMatrix(m, sym=True)
 elph = api.ElectronPhononParameters(m, fdm)
 elph.x = bench.bench_state(m)[0] if m.name == "cfg4" else bench.cdw_start(m, 0) if (m.Nhol and len(m.lattice_dims) == 2 and m.N == m.lattice_dims[0] * m.lattice_dims[1]) else m.random_fields(np.random.default_rng(0), smooth=True)
 elph.update_fdm()
+fdm.set_fast_path(2 + 256 * 3)          # no timing-based tuning under a profiler: register path where it applies, else the fast shared-memory kernel
 P = api.KPMPreconditioner(fdm)
 n = m.N * m.Ltau
 b = torch.randn(n, 2, dtype=torch.float64, device="cuda"); x = torch.zeros_like(b)
