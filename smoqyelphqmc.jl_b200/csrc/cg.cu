@@ -27,6 +27,13 @@ __device__ __forceinline__ void reduce_partials(const double *part, int n, int n
 }
 
 // partials of conj(a).b (re, im) and |a|^2
+int g_sq_pdl = 0;
+// scope guard: the launches inside take the programmatic-dependent-launch attribute (common.cuh)
+struct PdlScope {
+    explicit PdlScope(bool on) { g_sq_pdl = on ? 1 : 0; }
+    ~PdlScope() { g_sq_pdl = 0; }
+};
+
 __global__ void k_dot_partials(const double2 *__restrict__ a, const double2 *__restrict__ b, size_t n, double *__restrict__ part,
                                const CgState *__restrict__ skip) {
     __shared__ double red[3 * 32];
@@ -181,6 +188,7 @@ __global__ void k_cg_check(const CgState *__restrict__ cur, CgState *__restrict_
 // `st` is the state written by k_cg_check; the old r.z is read from `old` (the other ping-pong slot).
 __global__ void k_cg_update_p_prec(CgState *__restrict__ st, const CgState *__restrict__ old, double2 *__restrict__ p,
                                    const double2 *__restrict__ z, size_t n, const double *__restrict__ rz_part, int npart) {
+    sq_pdl_prologue();
     __shared__ double sh[3];
     if (st->done) return;
     reduce_partials(rz_part, npart, 2, sh);
@@ -409,6 +417,7 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
             i64 step = batch;
             if (it == 0 && !getenv("SQ_CG_BATCH")) step = std::max<i64>(batch, std::min<i64>((i64)(0.85 * f->prec_iters_hint[tol < 1e-7 ? 0 : 1]), 256));
             const i64 upto = std::min<i64>(maxiter, it + step);
+            PdlScope pdl(!getenv("SQ_NO_PDL"));
             for (; it < upto;) {
                 it++;
                 int npart = 0;
@@ -449,6 +458,9 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
         i64 step = batch;
         if (prec && it == 0 && !getenv("SQ_CG_BATCH")) step = std::max<i64>(batch, std::min<i64>((i64)(0.85 * f->prec_iters_hint[tol < 1e-7 ? 0 : 1]), 256));
         i64 upto = std::min<i64>(maxiter, it + step);
+        // (only while the iteration is launch-bound: at cfg4 the early-resident CTAs of the next kernel cost 3 %, at cfg1 / cfg5 the hidden
+        // launch latency is worth 8 - 10 %)
+        PdlScope pdl(prec && n <= 200000 && !getenv("SQ_NO_PDL"));
         for (; it < upto; ) {
             it++;
             const CgState *sc = st + cur;
@@ -473,7 +485,7 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
                     g = kpm_ldiv_dev_dot(kpm, z, r, sn, r, part_rz);      // z = P^-1 r with the r.z partials fused in
                     f->launches += 2;
                 }
-                k_cg_update_p_prec<<<G, TB, 0, s>>>(sn, sc, p, z, n, part_rz, g);
+                SQ_CUDA(sq_launch(k_cg_update_p_prec, dim3(G), dim3(TB), 0, s, sn, (const CgState *)sc, p, (const double2 *)z, n, (const double *)part_rz, g));
             }
             cur ^= 1;
         }

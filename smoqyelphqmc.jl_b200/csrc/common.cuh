@@ -1,6 +1,7 @@
 // common.cuh -- error handling, device buffers and small device helpers shared by all kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstring>
 
 #include <cstdint>
 #include <cstdio>
@@ -39,6 +40,28 @@ void sq_set_last_error(const std::string &m);
 #define SQ_LAUNCH_CHECK() SQ_CUDA(cudaGetLastError())
 
 // RAII device buffer
+// Programmatic dependent launch (PDL) for the launch-bound preconditioned CG iteration: a kernel launched with the attribute may become
+// resident while its predecessor in the stream still runs; it must not touch global memory before sq_pdl_prologue(), which (i) lets ITS
+// successor start launching and (ii) waits until the predecessor grid has completed and its writes are visible.  Without the attribute
+// both instructions are no-ops.  g_sq_pdl is set by the solver loop around the launches that take part.
+extern int g_sq_pdl;
+__device__ __forceinline__ void sq_pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KA, typename... A>
+inline cudaError_t sq_launch(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at;
+    memset(&at, 0, sizeof(at));
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at; cfg.numAttrs = g_sq_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KA(args)...);
+}
+
 template <class T>
 struct DevBuf {
     T *p = nullptr;

@@ -308,6 +308,7 @@ k_fdm_fused_v2(const __grid_constant__ K2Params P, double2 *__restrict__ out, co
                double *__restrict__ pAp_part, const CgState *__restrict__ skip) {
     extern __shared__ double2 smem[];
     __shared__ double red[32];
+    sq_pdl_prologue();
     if (skip && skip->done) {
         // converged earlier in this batch: keep the ping-ponged solver state consistent, do nothing else
         if (MODE == 2 && P.cg_d != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *P.cg_nxt = *skip;
@@ -519,7 +520,7 @@ void fdm_v2_launch(sq_fdm *f, int mode, int S, int T, double2 *out, const double
     size_t smem = slices * f->N * sizeof(double2);
     int grid = (f->slab_hi - f->slab_lo + S - 1) / S;
     v2_kernel_t k = pick(mode, (int)f->C, KMAX, f->cs_uniform);
-    k<<<grid, T, smem, f->stream>>>(P, out, in, part, skip);
+    SQ_CUDA(sq_launch(k, dim3(grid), dim3(T), smem, f->stream, P, out, in, part, skip));
     SQ_LAUNCH_CHECK();
     f->launches++;
 }

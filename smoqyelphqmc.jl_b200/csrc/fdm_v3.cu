@@ -440,6 +440,7 @@ k_fdm_v3(const __grid_constant__ V3Params P, double2 *__restrict__ out, const do
     extern __shared__ __align__(128) double wsm[];      // [S][NP][32] double2 (this CTA's part); TMA: [S + 1] of those + [S + 1][N] diagonal factors
     __shared__ __align__(8) unsigned long long mbar[8];
     __shared__ double red[32];
+    sq_pdl_prologue();
     if (!FUSE && gridDim.z > 1) {                       // multi-RHS batch: one vector, one set of partials and one solver state per blockIdx.z
         in += (size_t)blockIdx.z * P.bstride;
         out += (size_t)blockIdx.z * P.bstride;
@@ -841,7 +842,7 @@ int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, d
     v3_kernel_t k = pb ? pick3pb(f->v3_kind, f->v3_lxl, f->v3_ry, kmode)
                        : (f->v3_kind == 1 ? pick3h(f->v3_lxl, f->v3_ry, kmode) : pick3(f->v3_lxl, f->v3_ry, kmode));
     SQ_REQUIRE(k != nullptr, "register path: no kernel for this lattice / mode");
-    k<<<dim3(grid, 2, nbatch), 32 * (S + 1), smem, f->stream>>>(P, out, in, part, skip);
+    SQ_CUDA(sq_launch(k, dim3(grid, 2, nbatch), dim3(32 * (S + 1)), smem, f->stream, P, out, (const double2 *)in, part, skip));
     SQ_LAUNCH_CHECK();
     f->launches++;
     return 2 * grid;

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(256, 2) k_tau_fft(const FftPlan plan, double2 
     __shared__ double red[2 * 32];
     __shared__ double ush[1];
     __shared__ int ulast;
+    sq_pdl_prologue();
     // batch of vectors (multi-RHS solves): blockIdx.y selects the vector, its partial sums and its solver state
     in += (size_t)blockIdx.y * bstride;
     out += (size_t)blockIdx.y * bstride;
@@ -330,8 +331,8 @@ int tau_fft_launch_batch(cudaStream_t stream, const std::vector<int> &radices, i
         if (inverse || grid > SQ_MAXPART) throw SqError("fused CG update: forward transform with at most SQ_MAXPART CTAs only");
         U = *upd;
     }
-    k_tau_fft<<<dim3(grid, nbatch), threads, smem, stream>>>(plan, out, in, N, SB, inverse ? 1 : 0, twist ? 1 : 0, tw, theta, scale1, dot_with,
-                                                             dot_part, skip, bstride, U);
+    SQ_CUDA(sq_launch(k_tau_fft, dim3(grid, nbatch), dim3(threads), smem, stream, plan, out, in, N, SB, inverse ? 1 : 0, twist ? 1 : 0, tw, theta, scale1,
+                      dot_with, dot_part, skip, bstride, U));
     SQ_LAUNCH_CHECK();
     return grid;
 }

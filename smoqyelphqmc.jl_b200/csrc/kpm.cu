@@ -115,6 +115,7 @@ k_kpm_cheb(const __grid_constant__ BbarParams P, double2 *__restrict__ z, const 
            const int *__restrict__ coef_off, const double2 *__restrict__ coefs, int L, double avg, double imag_,
            const CgState *__restrict__ skip) {
     extern __shared__ double2 sm[];
+    sq_pdl_prologue();
     if (skip && skip->done) return;
     const int N = P.N;
     double2 *T0 = sm, *T1 = sm + N, *Y = sm + 2 * (size_t)N, *ACC = sm + 3 * (size_t)N;
@@ -260,6 +261,7 @@ k_kpm_cheb_fast(const __grid_constant__ BbarFast P, double2 *__restrict__ z, con
                 const int *__restrict__ coef_off, const double2 *__restrict__ coefs, int L, double avg, double imag_,
                 const CgState *__restrict__ skip) {
     extern __shared__ double Yr[];
+    sq_pdl_prologue();
     if (skip && skip->done) return;
     ChebEngine<CMAX> E;
     E.init(P);
@@ -647,8 +649,8 @@ void kpm_cheb_apply(sq_kpm *k, double2 *z, const int *d_sched, int nsched, int n
             size_t smem = f->N * sizeof(double2);
             const int T = kpm_fast_threads(k);
             smem = f->N * sizeof(double);
-#define SQ_CHEB(CM, MT) k_kpm_cheb_fast<CM, MT><<<2 * nsched, T, smem, f->stream>>>(Q, zt, d_sched, k->d_order.p, k->d_coef_off.p, \
-                                                                                           k->d_coefs.p, (int)f->L, avg, 1.0 / mag, sk)
+#define SQ_CHEB(CM, MT) SQ_CUDA(sq_launch(k_kpm_cheb_fast<CM, MT>, dim3(2 * nsched), dim3(T), smem, f->stream, Q, zt, (const int *)d_sched, \
+                                          (const int *)k->d_order.p, (const int *)k->d_coef_off.p, (const double2 *)k->d_coefs.p, (int)f->L, avg, 1.0 / mag, sk))
             if (f->C <= 4) { if (T <= 512) SQ_CHEB(4, 512); else SQ_CHEB(4, 1024); }
             else { if (T <= 512) SQ_CHEB(8, 512); else SQ_CHEB(8, 1024); }
 #undef SQ_CHEB
@@ -658,9 +660,8 @@ void kpm_cheb_apply(sq_kpm *k, double2 *z, const int *d_sched, int nsched, int n
             f->stats[SQ_STAT_KPM_SMEM]++;
             BbarParams P = bbar_params(k);
             double avg = 0.5 * (k->bounds[1] + k->bounds[0]), mag = 0.5 * (k->bounds[1] - k->bounds[0]);
-            k_kpm_cheb<<<nsched, kpm_threads(k), 4 * f->N * sizeof(double2), f->stream>>>(P, zt, d_sched, k->d_order.p,
-                                                                                            k->d_coef_off.p, k->d_coefs.p, (int)f->L, avg,
-                                                                                            1.0 / mag, sk);
+            SQ_CUDA(sq_launch(k_kpm_cheb, dim3(nsched), dim3(kpm_threads(k)), 4 * f->N * sizeof(double2), f->stream, P, zt, (const int *)d_sched,
+                              (const int *)k->d_order.p, (const int *)k->d_coef_off.p, (const double2 *)k->d_coefs.p, (int)f->L, avg, 1.0 / mag, sk));
             SQ_LAUNCH_CHECK();
             f->launches++;
         }

@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(32 * G::W, 1)
 k_kpm_cheb_reg(const __grid_constant__ ChebRegParams P) {
     constexpr int NV = G::NV;
     __shared__ __align__(32) double xch[G::XCH > 0 ? G::XCH : 1];
+    sq_pdl_prologue();
     if (P.skip && P.nrhs == 1 && P.skip->done) return;
     G E;
     double g;
@@ -621,7 +622,7 @@ void kpm_cheb_reg_launch(sq_kpm *k, double2 *z, const int *d_sched, int nsched, 
         if (const char *e = getenv("SQ_KPM_REG_OCC")) occ = std::max(1, atoi(e));
         grid = std::min(P.nchain, f->num_sms * std::max(1, std::min(occ, 4)));
     }
-    pk.k<<<grid, pk.threads, 0, f->stream>>>(P);
+    SQ_CUDA(sq_launch(pk.k, dim3(grid), dim3(pk.threads), 0, f->stream, P));
     SQ_LAUNCH_CHECK();
     f->launches++;
     f->stats[SQ_STAT_KPM_REG]++;
