@@ -128,6 +128,7 @@ def test_cg_matches_oracle(name, sym):
 # ---- register path (fdm_v3.cu) and the resident CG solver -----------------------------------------------------
 SQUARES = {
     "h16x16": lambda: mdl.holstein_square(16, 16, 2.0),
+    "h16x16odd": lambda: mdl.holstein_square(16, 16, 0.35),    # Ltau = 7: the last CTA of the resident solver owns ONE slice (ragged slab)
     "h32x16": lambda: mdl.holstein_square(32, 16, 1.0),
     "h16x32": lambda: mdl.holstein_square(16, 32, 1.0),
     "h32x32": lambda: mdl.holstein_square(32, 32, 1.5),
@@ -211,7 +212,7 @@ def test_register_path_requires_uniform_colours_and_canonical_order():
 
 
 @pytest.mark.parametrize("solver", ["resident", "launches", "launches_tma"])
-@pytest.mark.parametrize("name", ["h16x16", "h32x16", "h32x32", "hc8", "hc24", "bssh16", "ossh64", "ossh256"])
+@pytest.mark.parametrize("name", ["h16x16", "h16x16odd", "h32x16", "h32x32", "hc8", "hc24", "bssh16", "ossh64", "ossh256"])
 def test_register_path_cg(name, solver, monkeypatch):
     """CG on the register path in native order: the whole-solve resident kernel (one grid-wide sum per iteration) and the
     two-launches-per-iteration loop (its only fallback) against the oracle's CG."""
