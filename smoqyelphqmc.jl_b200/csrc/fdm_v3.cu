@@ -26,8 +26,10 @@
 //
 // Requirements (checked by fdm_v3_detect / fdm_v3_supported, otherwise the shared-memory kernels run): symmetric
 // propagator, natural site order i = x + Lx y, colour c is bond class c (x-even, x-odd, y-even, y-odd) -- or the honeycomb
-// lattice of the V3Honey engine below -- and the
-// (cosh, sinh) of all bonds of one colour are equal and tau-independent (any Holstein-type model with uniform hopping).
+// lattice of the V3Honey engine below, or a chain (V3ChainPB).  Two engine families: the UNIFORM engines (V3Lane, V3Honey) need the
+// (cosh, sinh) of all bonds of one colour equal and tau-independent (any Holstein-type model with uniform hopping) and keep one
+// tanh per colour; the PER-BOND engines (V3LanePB: 16 x 16, V3ChainPB: 64 / 128 / 256 sites) keep the (cosh, sinh) of every bond
+// of the warp's slice in registers (SSH couplings, disordered hoppings): fdm_v3_perbond() picks the family per operator update.
 #include "sq_internal.h"
 
 #include <algorithm>
