@@ -306,6 +306,25 @@ void fdm_cg_dev(sq_fdm *f, double2 *x, const double2 *b, bool zero_start, sq_kpm
     fdm_select_tuning(f);
     const bool v3 = f->path == 0 && f->v3_cg && fdm_v3_supported(f, f->v3_S);
     const bool fused = !prec && f->path == 0 && (v3 || (f->use_v2 && fdm_v2_supported(f, 2, f->slab, f->threads))) && !getenv("SQ_NO_CG_FUSION");
+    if (!prec && !v3 && f->path == 0 && f->v3g_ok && !getenv("SQ_NO_PERSISTENT_CG") && !getenv("SQ_NO_RESIDENT_CG") && !getenv("SQ_NO_CG_FUSION") &&
+        !getenv("SQ_V3_NO_GRAPH")) {
+        // small lattices (N <= 64): the whole solve in the resident register kernel with the graph engine (fdm_v3.cu)
+        SQ_CUDA(cudaMemcpyAsync(f->h_cg, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+        SQ_CUDA(cudaStreamSynchronize(s));
+        if (f->h_cg->done == 2) throw SqNumericalInstability("conjugate gradient: NaN encountered in the residual (numerical instability)");
+        if (f->h_cg->done) { *iters = 0; *eps = f->h_cg->eps; return; }
+        if (fdm_v3g_cg(f, x, r, zero_start, st, maxiter)) {
+            SQ_CUDA(cudaMemcpyAsync(f->h_cg, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+            SQ_CUDA(cudaStreamSynchronize(s));
+            f->stats[SQ_STAT_CG_RESIDENT]++;
+            if (f->h_cg->done == 3) { f->stats[SQ_STAT_WATCHDOG]++; throw SqError("conjugate gradient: a grid-wide sum of the resident kernel timed out (watchdog)"); }
+            if (f->h_cg->done == 2) throw SqNumericalInstability("conjugate gradient: NaN encountered in the residual (numerical instability)");
+            *iters = f->h_cg->done ? f->h_cg->iters : maxiter;
+            *eps = f->h_cg->eps;
+            f->stats[SQ_STAT_CG_ITERS] += *iters;
+            return;
+        }
+    }
     if (fused && !v3 && !getenv("SQ_NO_PERSISTENT_CG") && maxiter > 0) {
         // One cooperative launch for the whole solve (fdm_v2.cu: k_cg_persistent).  The state prepared by k_cg_init holds
         // |r0|^2, |b| and tol; an already converged system (eps0 < tol) is caught first.

@@ -49,6 +49,7 @@ struct V3Params {
     const double *expVn;    // native order (NAT kernels)
     const double2 *ctn;     // (cosh, tanh) per colour, prepared with expVn (the in-kernel divisions were 18 % of the stall samples)
     long long *dbg;         // optional clock stamps of warp 1 of CTA 0 (profiling aid, NULL in production)
+    const int *gpart;       // graph engine: partner of value a of lane `lane` in colour c = gpart[(c * 2 + a) * 32 + lane]: lane | value << 5
     const double2 *csn;     // per-bond engines: (cosh, sinh) of slot q of lane `lane` of slice l = csn[(l * NCS + q) * 32 + lane]
     size_t bstride;         // batch of vectors (blockIdx.z): elements between consecutive vectors
     int bpart;              // ... doubles between their p.Ap partials
@@ -426,6 +427,51 @@ struct V3ChainPB {
     }
 };
 
+// Graph engine (resident CG only): ANY lattice with N <= 64 sites and C <= 4 colours -- the 18-site honeycomb of BASELINE config 1,
+// short chains, 4 x 4 ... 8 x 8 squares.  The slice is padded to 64 sites, lane = sites 2 lane, 2 lane + 1 (native order = natural site
+// order, real and imaginary planes); every bond goes through shuffles: per colour a lane fetches both values of the partner lane of each
+// of its two sites and picks one.  Per-bond, per-slice (cosh, sinh) in registers as in the per-bond engines (slot q = 2 c + a); a site
+// without a bond in a colour -- and every padding site -- carries (1, 0) and is its own partner, so that it passes through unchanged.
+struct V3Graph {
+    static constexpr int N = 64, NV = 2, NP = 1, NCOL = 4, NCS = 8, REGS_LIGHT = 1;
+    int part, C;
+    int pl[4][2];
+    double2 cf[NCS];
+
+    template <int SC>
+    __device__ __forceinline__ void init(const V3Params &P, int part_) {
+        const int lane = threadIdx.x & 31;
+        part = part_;
+        C = P.C;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int a = 0; a < 2; a++) pl[c][a] = __ldg(P.gpart + (c * 2 + a) * 32 + lane);
+    }
+    __device__ __forceinline__ void load_cs(const V3Params &P, int l) {
+        const double2 *g = P.csn + (size_t)l * NCS * 32 + (threadIdx.x & 31);
+#pragma unroll
+        for (int q = 0; q < NCS; q++) cf[q] = __ldg(g + 32 * q);
+    }
+    template <int CL>
+    __device__ __forceinline__ void step(double (&v)[NV]) const {
+        if (CL >= C) return;                               // (warp-uniform)
+        const int w0 = pl[CL][0], w1 = pl[CL][1];
+        const double a0 = __shfl_sync(0xffffffffu, v[0], w0 & 31), a1 = __shfl_sync(0xffffffffu, v[1], w0 & 31);
+        const double b0 = __shfl_sync(0xffffffffu, v[0], w1 & 31), b1 = __shfl_sync(0xffffffffu, v[1], w1 & 31);
+        v[0] = rot_half<0>(v[0], (w0 & 32) ? a1 : a0, cf[2 * CL].x, cf[2 * CL].y);
+        v[1] = rot_half<0>(v[1], (w1 & 32) ? b1 : b0, cf[2 * CL + 1].x, cf[2 * CL + 1].y);
+    }
+    // v <- B v, B = Gamma D Gamma^T: colours C-1 ... 0, D, 0 ... C-1.  ev: the slice's diagonal factors (+ 2 lane)
+    template <int NAT, int SM>
+    __device__ __forceinline__ void apply_B_ev(double (&v)[NV], const double *ev) const {
+        step<3>(v); step<2>(v); step<1>(v); step<0>(v);
+        const double2 e = *reinterpret_cast<const double2 *>(ev);
+        v[0] *= e.x; v[1] *= e.y;
+        step<0>(v); step<1>(v); step<2>(v); step<3>(v);
+    }
+};
+
 // NAT = 1: all vectors (in, out, cg_d, cg_pnew) are in the NATIVE order of this kernel -- slice l, part q, then
 // [r][j/2][lane][j%2] doubles -- so that every load / store is one fully coalesced 16-byte access per lane.  The CG solver
 // keeps its vectors in this order for the whole solve (cg.cu); the order is converted once on entry and once on exit.
@@ -739,6 +785,7 @@ void fdm_v3_detect(sq_fdm *f) {
     f->v3_ok = 0;
     f->v3_pb_ok = 0;
     f->v3_kind = 0;
+    f->v3g_ok = (f->sym && f->N <= 64 && f->C >= 1 && f->C <= 4 && f->Nh >= 1) ? 1 : 0;      // graph engine of the resident CG
     if (fdm_v3_detect_honeycomb(f)) return;
     if (fdm_v3_detect_chain(f)) return;
     if (!f->sym || f->C != 4 || f->Nh != 2 * f->N) return;
@@ -1435,25 +1482,33 @@ static v3_resident1_t pick3_resident1_multi(int kind, int a, int b) {
 }
 
 // One-sum resident kernel (k_cg_v3_resident1).  Returns false if it cannot run (the caller falls back to the launch loop in cg.cu).
-static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *state, i64 maxiter) {
+// graph: the V3Graph kernel on the padded 64-site slices prepared by fdm_v3g_cg (its own native copies of the operator)
+static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *state, i64 maxiter, bool graph = false) {
     const bool pb = fdm_v3_perbond(f);
-    if (!fdm_v3_supported(f, 1)) return false;
-    v3_resident1_t k = pb ? pick3pb_resident1(f->v3_kind, f->v3_lxl, f->v3_ry)
-                          : (f->v3_kind == 1 ? pick3h_resident1(f->v3_lxl, f->v3_ry) : pick3_resident1(f->v3_lxl, f->v3_ry));
+    v3_resident1_t k;
+    if (graph) {
+        k = k_cg_v3_resident1<V3Graph, 0>;
+    } else {
+        if (!fdm_v3_supported(f, 1)) return false;
+        k = pb ? pick3pb_resident1(f->v3_kind, f->v3_lxl, f->v3_ry)
+               : (f->v3_kind == 1 ? pick3h_resident1(f->v3_lxl, f->v3_ry) : pick3_resident1(f->v3_lxl, f->v3_ry));
+    }
     if (!k) return false;
+    const size_t Nslice = graph ? (size_t)V3Graph::N : (size_t)f->N;      // sites of a slice as the kernel sees it
     const int nsl = f->slab_hi - f->slab_lo;
     int S = (nsl + f->num_sms - 1) / f->num_sms;
     if (const char *e = getenv("SQ_V3_RESIDENT_SLAB")) S = atoi(e);
     S = std::max(S, 2);
     if (S > 3 || nsl < S) return false;
     const int grid = (nsl + S - 1) / S, T = 64 * (S + 1);
-    const size_t smem = (size_t)(5 * S + 9) * f->N * sizeof(double);
+    const size_t smem = (size_t)(5 * S + 9) * Nslice * sizeof(double);
     if (smem > f->smem_optin || grid > f->num_sms || grid < 2) return false;
     V3Params P;
     memset(&P, 0, sizeof(P));
     P.L = (int)f->L; P.lb = f->slab_lo; P.le = f->slab_hi; P.S = S; P.C = (int)f->C; P.nphase = 2;
     for (int c = 0; c < 4; c++) { P.cls[c] = f->v3_cls[c]; P.clo[c] = c < f->C ? f->clo[c] : 0; }
     P.cs = f->cs.p; P.expV = f->expV.p; P.expVn = f->v3_expVn.p; P.ctn = f->v3_ctn.p; P.csn = f->v3_csn.p;
+    if (graph) { P.expVn = f->v3g_expVn.p; P.csn = f->v3g_csn.p; P.gpart = f->v3g_part.p; }
     SQ_CUDA(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k, T, smem));
@@ -1465,7 +1520,7 @@ static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *stat
     const size_t slot_bytes = 3 * arr + (size_t)grid * 128;
     if (f->v3_slots.n < slot_bytes) f->v3_slots.alloc(slot_bytes);
     SQ_CUDA(cudaMemsetAsync(f->v3_slots.p, 0, slot_bytes, f->stream));
-    const size_t nh = (size_t)8 * grid * f->N;
+    const size_t nh = (size_t)8 * grid * Nslice;
     if (f->v3_halo.n < nh) f->v3_halo.alloc(nh);
     CgResident1 C;
     memset(&C, 0, sizeof(C));
@@ -1505,6 +1560,81 @@ static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *stat
                 sd[2] > sd[3] ? (double)sd[5] / (double)(sd[2] - sd[3]) : 0.0);
     }
 #endif
+    return true;
+}
+
+// ---- graph engine: small lattices ------------------------------------------------------------------------
+__global__ void k_v3g_to_native(double *__restrict__ dst, const double2 *__restrict__ src, int L, int N) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)L * 64) return;
+    const int l = (int)(idx / 64), i = (int)(idx % 64);
+    const double2 v = i < N ? src[(size_t)l * N + i] : make_double2(0.0, 0.0);      // padding sites stay zero for the whole solve
+    dst[((size_t)l * 2) * 64 + i] = v.x;
+    dst[((size_t)l * 2 + 1) * 64 + i] = v.y;
+}
+__global__ void k_v3g_from_native(double2 *__restrict__ dst, const double *__restrict__ src, int L, int N) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)L * N) return;
+    const int l = (int)(idx / N), i = (int)(idx % N);
+    dst[idx] = make_double2(src[((size_t)l * 2) * 64 + i], src[((size_t)l * 2 + 1) * 64 + i]);
+}
+// operator in the engine's layout: exp(-dtau V) padded with zeros, (cosh, sinh) per slot with (1, 0) where a site has no bond
+__global__ void k_v3g_operator(double *__restrict__ ev, double2 *__restrict__ csn, const double *__restrict__ expV, const double2 *__restrict__ cs,
+                               const int *__restrict__ map, int L, int N, int Nh) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)L * 256) return;
+    const int l = (int)(idx / 256), e = (int)(idx % 256);
+    if (e < 64) ev[(size_t)l * 64 + e] = e < N ? expV[(size_t)l * N + e] : 0.0;
+    const int h = map[e];
+    csn[idx] = h >= 0 ? cs[(size_t)l * Nh + h] : make_double2(1.0, 0.0);
+}
+
+static void v3g_build_tables(sq_fdm *f) {
+    std::vector<int> part(256), map(256, -1);
+    for (int c = 0; c < 4; c++)
+        for (int a = 0; a < 2; a++)
+            for (int lane = 0; lane < 32; lane++) part[(c * 2 + a) * 32 + lane] = lane | (a << 5);      // its own partner: passes through
+    for (int c = 0; c < (int)f->C; c++)
+        for (int h = f->clo[c]; h < f->chi[c]; h++) {
+            const int i = f->h_nt[h].x, j = f->h_nt[h].y;
+            part[(c * 2 + (i & 1)) * 32 + i / 2] = (j / 2) | ((j & 1) << 5);
+            part[(c * 2 + (j & 1)) * 32 + j / 2] = (i / 2) | ((i & 1) << 5);
+            map[(c * 2 + (i & 1)) * 32 + i / 2] = h;
+            map[(c * 2 + (j & 1)) * 32 + j / 2] = h;
+        }
+    f->v3g_part.alloc(256);
+    f->v3g_csmap.alloc(256);
+    f->v3g_part.upload(part.data(), 256, f->stream);
+    f->v3g_csmap.upload(map.data(), 256, f->stream);
+    SQ_CUDA(cudaStreamSynchronize(f->stream));
+}
+
+bool fdm_v3g_cg(sq_fdm *f, double2 *x, const double2 *r, bool zero_start, CgState *state, i64 maxiter) {
+    if (!f->v3g_ok || f->slab_lo != 0 || f->slab_hi != (int)f->L) return false;
+    const int L = (int)f->L;
+    const int S = std::max(2, (L + f->num_sms - 1) / f->num_sms);
+    if (S > 3 || L < S || (L + S - 1) / S < 2 || (L + S - 1) / S > f->num_sms) return false;      // (the launch below would refuse: nothing converted yet)
+    const size_t nn = (size_t)L * 2 * 64;
+    if (!f->v3g_part.p) v3g_build_tables(f);
+    if (!f->v3g_x.p) { f->v3g_x.alloc(nn); f->v3g_r.alloc(nn); f->v3g_expVn.alloc((size_t)L * 64); f->v3g_csn.alloc((size_t)L * 256); f->v3g_version = -1; }
+    cudaStream_t s = f->stream;
+    if (f->v3g_version != f->coef_version) {
+        k_v3g_operator<<<(unsigned)(((size_t)L * 256 + 255) / 256), 256, 0, s>>>(f->v3g_expVn.p, f->v3g_csn.p, f->expV.p, f->cs.p, f->v3g_csmap.p, L, (int)f->N,
+                                                                                 (int)f->Nh);
+        SQ_LAUNCH_CHECK();
+        f->launches++;
+        f->v3g_version = f->coef_version;
+    }
+    const unsigned gb = (unsigned)(((size_t)L * 64 + 255) / 256);
+    k_v3g_to_native<<<gb, 256, 0, s>>>(f->v3g_r.p, r, L, (int)f->N);
+    if (zero_start) SQ_CUDA(cudaMemsetAsync(f->v3g_x.p, 0, nn * sizeof(double), s));
+    else k_v3g_to_native<<<gb, 256, 0, s>>>(f->v3g_x.p, x, L, (int)f->N);
+    SQ_LAUNCH_CHECK();
+    f->launches += zero_start ? 1 : 2;
+    if (!fdm_v3_cg_resident1(f, (double2 *)f->v3g_x.p, (double2 *)f->v3g_r.p, state, maxiter, true)) return false;
+    k_v3g_from_native<<<(unsigned)(((size_t)L * f->N + 255) / 256), 256, 0, s>>>(x, f->v3g_x.p, L, (int)f->N);
+    SQ_LAUNCH_CHECK();
+    f->launches++;
     return true;
 }
 

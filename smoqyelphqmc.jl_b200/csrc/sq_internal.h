@@ -82,6 +82,13 @@ struct sq_fdm {
     DevBuf<int> v3_csmap;                    // ... bond index of slot (q, lane)
     DevBuf<double2> v3_csn;                  // ... coefficients in slot order [l][q][lane], rebuilt with v3_expVn
     int v3_native_pb = -1;                   // engine family the native-order copies were prepared for
+    // graph engine of the resident CG (fdm_v3.cu: V3Graph): ANY lattice with N <= 64 sites and <= 4 colours, padded to 64 sites
+    int v3g_ok = 0;
+    DevBuf<int> v3g_part, v3g_csmap;         // partner lane / value of (colour, value, lane); bond of coefficient slot (q, lane) or -1
+    DevBuf<double> v3g_expVn;                // [l][64]
+    DevBuf<double2> v3g_csn;                 // [l][8][32]
+    DevBuf<double> v3g_x, v3g_r;             // [l][part][64]
+    i64 v3g_version = -1;
     int v3_S = 3;                            // slices per CTA of the register path
     int use_v3 = 0;                          // stand-alone products (library-order vectors): chosen by timing
     int v3_cg = 0;                           // CG solves: register path whenever it applies (native order + resident kernel)
@@ -322,6 +329,9 @@ void fdm_select_tuning(sq_fdm *f);
 int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native = false,
                   int nbatch = 1, size_t bstride = 0, int bpart = 0);
 bool fdm_v3_supported(const sq_fdm *f, int S);
+// small lattices (graph engine): whole unpreconditioned solve in the resident kernel; x (in / out) and r (in) in library order.
+// Returns false when the problem does not qualify (the caller continues with its other solvers; x and r are untouched).
+bool fdm_v3g_cg(sq_fdm *f, double2 *x, const double2 *r, bool zero_start, CgState *state, i64 maxiter);
 // engine family of the register path: uniform engines (one cosh / tanh per colour) when the hoppings are colour-uniform and the lattice
 // has one, otherwise the per-bond engines
 inline bool fdm_v3_perbond(const sq_fdm *f) { return !(f->v3_ok && f->cs_coluni); }

@@ -36,7 +36,8 @@ MODELS = {
     # dispersive phonon couplings (nearest-neighbour springs, quadratic + quartic) on top of a Holstein model with anharmonic on-site terms
     "disp": lambda: mdl.with_dispersion(mdl.holstein_square(4, 4, 0.5, ph_sym=False), 0.8, 0.4),
 }
-REGISTER_PATH = ("sq16", "sq32", "hc8", "cfg2s", "cfg3r")
+# ... and the graph engine (any lattice with N <= 64): the small models above
+REGISTER_PATH = ("sq16", "sq32", "hc8", "cfg2s", "cfg3r", "cfg1t", "cfg1", "cfg3s", "mixed", "nosym", "disp")
 
 
 def assert_register_path(name, sym, gf, st0):
