@@ -27,7 +27,7 @@ __device__ __forceinline__ void reduce_partials(const double *part, int n, int n
 }
 
 // partials of conj(a).b (re, im) and |a|^2
-int g_sq_pdl = 0;
+thread_local int g_sq_pdl = 0;
 // scope guard: the launches inside take the programmatic-dependent-launch attribute (common.cuh)
 struct PdlScope {
     explicit PdlScope(bool on) { g_sq_pdl = on ? 1 : 0; }

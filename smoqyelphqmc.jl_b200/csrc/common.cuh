@@ -44,7 +44,7 @@ void sq_set_last_error(const std::string &m);
 // resident while its predecessor in the stream still runs; it must not touch global memory before sq_pdl_prologue(), which (i) lets ITS
 // successor start launching and (ii) waits until the predecessor grid has completed and its writes are visible.  Without the attribute
 // both instructions are no-ops.  g_sq_pdl is set by the solver loop around the launches that take part.
-extern int g_sq_pdl;
+extern thread_local int g_sq_pdl;
 __device__ __forceinline__ void sq_pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
