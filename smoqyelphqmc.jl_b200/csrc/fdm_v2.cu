@@ -485,7 +485,7 @@ struct CgFuseArgs {
     const double2 *d; double2 *pnew; const CgState *cur; CgState *nxt;
     const double *rr_part, *beta_part; int nrr, nbeta, beta_complex, iter, check;
 };
-static const CgFuseArgs *g_fuse = nullptr;          // set by fdm_v2_launch_cg around the launch (single host thread per handle)
+static thread_local const CgFuseArgs *g_fuse = nullptr;     // set by fdm_v2_launch_cg around the launch (per host thread: handles may be driven from different threads)
 
 void fdm_v2_launch(sq_fdm *f, int mode, int S, int T, double2 *out, const double2 *in, double *part, const CgState *skip) {
     K2Params P;

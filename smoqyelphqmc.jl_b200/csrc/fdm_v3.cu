@@ -843,7 +843,7 @@ struct CgFuse3 {
     const double2 *d; double2 *pnew; const CgState *cur; CgState *nxt;
     const double *rr_part, *beta_part; int nrr, nbeta, beta_complex, iter, check;
 };
-static const CgFuse3 *g_fuse3 = nullptr;
+static thread_local const CgFuse3 *g_fuse3 = nullptr;
 
 // returns the number of CTAs (= p.Ap partials for mode 2)
 int fdm_v3_launch(sq_fdm *f, int mode, int S, double2 *out, const double2 *in, double *part, const CgState *skip, bool native, int nbatch,
