@@ -1179,10 +1179,18 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     // flag to the iteration number, and the neighbours wait for the flag before they fetch the boundary z.
     // Several GPUs: the same with a system-scope fence; the first / last CTA of a slab also raises a flag in the neighbour rank's mailbox.
     constexpr bool FLAGS = true;
+    // Small slices (N <= 128, one GPU): no fence and no flag at all.  The boundary z carries the iteration tag in the two low mantissa bits of
+    // every double (as the partial sums do) -- the owner rounds its boundary z to the tagged value BEFORE using it, so both sides compute
+    // with the same bits -- and the slice-less warps poll the neighbours' boundary slices WHILE the grid-wide sum is in flight (the sum is run
+    // by two owner warps instead): on these lattices the iteration is a chain of L2 round trips, and this takes two of them off the chain.
+    // (Measured: 64-site chain 2.77 -> 2.40 us, 8 x 8 honeycomb 3.53 -> 3.08 us per iteration; 16 x 16 lattices 4.1 -> 4.7 us: not used there.)
+    constexpr bool TAGH = !MULTI && G::N <= 128;
     auto flag_of = [&](unsigned int cta) -> unsigned long long * {
         return MULTI ? reinterpret_cast<unsigned long long *>(C.mail[C.rank] + C.off_flags + 256 + (size_t)cta * 128) : C.flags + (size_t)cta * 16;
     };
-    const bool fwarp = FLAGS && part == 1 && k == 0, bwarp = FLAGS && owner && (k == 1 || k == ns);
+    const bool fwarp = FLAGS && !TAGH && part == 1 && k == 0, bwarp = FLAGS && owner && (k == 1 || k == ns);
+    const bool sumw = TAGH ? (k == 1) : (wid < 2);       // the two warps that run the grid-wide sum: half 0 = (a, b), half 1 = (c, d)
+    const int sumh = TAGH ? part : wid;
     const int fcnt = 32 * (1 + (ns > 1 ? 4 : 2)), tcnt = (int)blockDim.x;
     int lself = l0 + k;
     lself = lself >= L ? lself - L : lself;
@@ -1283,16 +1291,22 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
 #pragma unroll
             for (int u = 0; u < NP; u++) {
                     const double2 w = W[(size_t)(k - 1) * (N / 2) + el(u)];
-                    const double z0 = fma(sg, v[2 * u], w.x), z1 = fma(sg, v[2 * u + 1], w.y);
+                    double z0 = fma(sg, v[2 * u], w.x), z1 = fma(sg, v[2 * u + 1], w.y);
+                    if (TAGH && bwarp) { z0 = v3_tag(z0, (long long)(itg & 3)); z1 = v3_tag(z1, (long long)(itg & 3)); }
                     v[2 * u] = z0; v[2 * u + 1] = z1;
                     const double r0 = rr_[2 * u], r1 = rr_[2 * u + 1];
                     acc[1] += r0 * z0; acc[1] += r1 * z1;
                     acc[2] += z0 * z0; acc[2] += z1 * z1;
-                    if (h0) h0[el(u)] = make_double2(z0, z1);
-                    if (h1) h1[el(u)] = make_double2(z0, z1);
+                    if (TAGH) {                           // self-validating words: strong stores, no fence
+                        if (h0) asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(h0 + el(u)), "d"(z0), "d"(z1) : "memory");
+                        if (h1) asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(h1 + el(u)), "d"(z0), "d"(z1) : "memory");
+                    } else {
+                        if (h0) h0[el(u)] = make_double2(z0, z1);
+                        if (h1) h1[el(u)] = make_double2(z0, z1);
+                    }
                 }
             acc[3] = rr_lane;                             // same elements, same order as a fresh accumulation: same bits
-            if (bwarp) {                                  // boundary z stored: hand it to the fencing warp
+            if (bwarp && !TAGH) {                         // boundary z stored: hand it to the fencing warp
                 __threadfence_block();
                 asm volatile("bar.arrive 3, %0;" ::"r"(fcnt) : "memory");
             }
@@ -1326,15 +1340,38 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
             __syncthreads();
         }
         R1_STAMP(5);
-        if (wid < 2) {                                    // warp 0: (a, b), warp 1: (c, d)
+        if (sumw) {                                       // half 0: (a, b), half 1: (c, d)
             const int nw = blockDim.x >> 5;
             double t[2];
 #pragma unroll
-            for (int c = 0; c < 2; c++) { t[c] = 0.0; for (int w = 0; w < nw; w++) t[c] += red[(2 * wid + c) * 8 + w]; }
+            for (int c = 0; c < 2; c++) { t[c] = 0.0; for (int w = 0; w < nw; w++) t[c] += red[(2 * sumh + c) * 8 + w]; }
             bool bad = false;
-            if (MULTI) v3_slot_sum2_multi<false>(t, wid, C.mail, C.world, C.rank, (size_t)(itg & 1) * C.slot_array_bytes, C.slot_stride, (long long)(itg & 3), gtot, gid, bad);
-            else v3_slot_sum2<false>(t, wid, C.slots + (size_t)(it & 1) * C.slot_array_bytes, C.slot_stride, (long long)(it & 3), nblk, bid, bad);
-            if (lane == 0) { sh[2 * wid] = t[0]; sh[2 * wid + 1] = t[1]; if (bad) sh[5] = 1.0; }
+            if (MULTI) v3_slot_sum2_multi<false>(t, sumh, C.mail, C.world, C.rank, (size_t)(itg & 1) * C.slot_array_bytes, C.slot_stride, (long long)(itg & 3), gtot, gid, bad);
+            else v3_slot_sum2<false>(t, sumh, C.slots + (size_t)(it & 1) * C.slot_array_bytes, C.slot_stride, (long long)(it & 3), nblk, bid, bad);
+            if (lane == 0) { sh[2 * sumh] = t[0]; sh[2 * sumh + 1] = t[1]; if (bad) sh[5] = 1.0; }
+        } else if (TAGH && k == 0) {
+            // meanwhile: the neighbours' boundary z of this iteration, valid word by word once its tag matches
+            const double2 *gu = hslice((int)(itg & 1), right, 0), *gl = hslice((int)(itg & 1), left, 1);
+            const long long tg = (long long)(itg & 3), t0 = clock64();
+            constexpr int NH = N / 64;                    // double2 per lane and boundary slice
+            long long q[2 * NH][2];
+            while (true) {                                // all loads in flight, then the checks: one L2 round trip per attempt
+#pragma unroll
+                for (int u = 0; u < NH; u++) {
+                    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(q[u][0]), "=l"(q[u][1]) : "l"(gl + lane + 32 * u) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(q[NH + u][0]), "=l"(q[NH + u][1]) : "l"(gu + lane + 32 * u) : "memory");
+                }
+                bool ready = true;
+#pragma unroll
+                for (int u = 0; u < 2 * NH; u++) ready = ready && (q[u][0] & 3LL) == tg && (q[u][1] & 3LL) == tg;
+                if (ready) break;
+                if (clock64() - t0 > 4000000000LL) { sh[5] = 1.0; break; }
+            }
+#pragma unroll
+            for (int u = 0; u < NH; u++) {
+                xr[2 * u] = __longlong_as_double(q[u][0]); xr[2 * u + 1] = __longlong_as_double(q[u][1]);
+                rr_[2 * u] = __longlong_as_double(q[NH + u][0]); rr_[2 * u + 1] = __longlong_as_double(q[NH + u][1]);
+            }
         }
         R1_STAMP(6);
         __syncthreads();
@@ -1369,7 +1406,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
         // the whole rebuild before the barrier 8.11 us, staging through shared memory with bulk async copies 7.73 us, this 7.45 us,
         // round 1 7.95 us per iteration at cfg4.)
         static_assert(G::NV == N / 32, "one warp holds one slice-part");
-        if (k == 0) {
+        if (k == 0 && !TAGH) {
             const double2 *gu = hslice((int)(itg & 1), right, 0), *gl = hslice((int)(itg & 1), left, 1);
             if (MULTI) {
                 if (bid == nblk - 1) gu = inbox(C.rank, (int)(itg & 1), 1);
@@ -1522,6 +1559,7 @@ static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *stat
     SQ_CUDA(cudaMemsetAsync(f->v3_slots.p, 0, slot_bytes, f->stream));
     const size_t nh = (size_t)8 * grid * Nslice;
     if (f->v3_halo.n < nh) f->v3_halo.alloc(nh);
+    if (Nslice <= 128) SQ_CUDA(cudaMemsetAsync(f->v3_halo.p, 0, nh * sizeof(double), f->stream));      // tagged boundary slices: no stale tags of an earlier solve
     CgResident1 C;
     memset(&C, 0, sizeof(C));
     C.x = (double *)x; C.r = (const double *)r; C.state = state;
