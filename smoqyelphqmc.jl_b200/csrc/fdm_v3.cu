@@ -1179,12 +1179,14 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     // flag to the iteration number, and the neighbours wait for the flag before they fetch the boundary z.
     // Several GPUs: the same with a system-scope fence; the first / last CTA of a slab also raises a flag in the neighbour rank's mailbox.
     constexpr bool FLAGS = true;
-    // Small slices (N <= 128, one GPU): no fence and no flag at all.  The boundary z carries the iteration tag in the two low mantissa bits of
+    // Small slices (N <= 256, one GPU): no fence and no flag at all.  The boundary z carries the iteration tag in the two low mantissa bits of
     // every double (as the partial sums do) -- the owner rounds its boundary z to the tagged value BEFORE using it, so both sides compute
     // with the same bits -- and the slice-less warps poll the neighbours' boundary slices WHILE the grid-wide sum is in flight (the sum is run
     // by two owner warps instead): on these lattices the iteration is a chain of L2 round trips, and this takes two of them off the chain.
-    // (Measured: 64-site chain 2.77 -> 2.40 us, 8 x 8 honeycomb 3.53 -> 3.08 us per iteration; 16 x 16 lattices 4.1 -> 4.7 us: not used there.)
-    constexpr bool TAGH = !MULTI && G::N <= 128;
+    // (Measured: 64-site chain 2.77 -> 2.40 us, 8 x 8 honeycomb 3.53 -> 3.08 us, 16 x 16 square 4.08 -> 3.60 us per iteration with all polling
+    // loads in flight at once -- one load at a time made 16 x 16 SLOWER, 4.7 us; at 32 x 32 / 24 x 24 honeycomb it changes nothing, 7.12 / 7.47 us:
+    // there the slice-less warps have slack and the fence-on-idle-warp protocol stays.)
+    constexpr bool TAGH = !MULTI && G::N <= 256;
     auto flag_of = [&](unsigned int cta) -> unsigned long long * {
         return MULTI ? reinterpret_cast<unsigned long long *>(C.mail[C.rank] + C.off_flags + 256 + (size_t)cta * 128) : C.flags + (size_t)cta * 16;
     };
@@ -1559,7 +1561,7 @@ static bool fdm_v3_cg_resident1(sq_fdm *f, double2 *x, double2 *r, CgState *stat
     SQ_CUDA(cudaMemsetAsync(f->v3_slots.p, 0, slot_bytes, f->stream));
     const size_t nh = (size_t)8 * grid * Nslice;
     if (f->v3_halo.n < nh) f->v3_halo.alloc(nh);
-    if (Nslice <= 128) SQ_CUDA(cudaMemsetAsync(f->v3_halo.p, 0, nh * sizeof(double), f->stream));      // tagged boundary slices: no stale tags of an earlier solve
+    if (Nslice <= 256) SQ_CUDA(cudaMemsetAsync(f->v3_halo.p, 0, nh * sizeof(double), f->stream));      // tagged boundary slices: no stale tags of an earlier solve
     CgResident1 C;
     memset(&C, 0, sizeof(C));
     C.x = (double *)x; C.r = (const double *)r; C.state = state;
