@@ -1,5 +1,8 @@
+"""Resident-CG iteration time of the 64-site SSH chain against the number of CTAs (Ltau = 40 ... 320, S = 2 / 3 slices per CTA): the iteration
+is a chain of L2 round trips, independent of how many CTAs take part."""
 import os, sys
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch, time
 from smoqyelph_b200 import model as mdl, api
 for beta in (2.0, 4.0, 8.0, 16.0):
