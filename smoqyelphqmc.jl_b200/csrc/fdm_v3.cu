@@ -1186,7 +1186,9 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     // (Measured: 64-site chain 2.77 -> 2.40 us, 8 x 8 honeycomb 3.53 -> 3.08 us, 16 x 16 square 4.08 -> 3.60 us per iteration with all polling
     // loads in flight at once -- one load at a time made 16 x 16 SLOWER, 4.7 us; at 32 x 32 / 24 x 24 honeycomb it changes nothing, 7.12 / 7.47 us:
     // there the slice-less warps have slack and the fence-on-idle-warp protocol stays.)
-    constexpr bool TAGH = !MULTI && G::N <= 256;
+    // Several GPUs: always -- a system-scope fence waits for the NVLink stores of the boundary to be acknowledged and the flag then crosses
+    // the link once more: with tags the boundary is in the neighbour rank's inbox one link latency after the z phase, before the sum completes.
+    constexpr bool TAGH = MULTI || G::N <= 256;
     auto flag_of = [&](unsigned int cta) -> unsigned long long * {
         return MULTI ? reinterpret_cast<unsigned long long *>(C.mail[C.rank] + C.off_flags + 256 + (size_t)cta * 128) : C.flags + (size_t)cta * 16;
     };
@@ -1258,6 +1260,9 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
         it++;
         const unsigned long long itg = MULTI ? C.it_base + (unsigned long long)it : (unsigned long long)it;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        // tag of the boundary slices of this iteration: 1, 2 or 3 -- never 0, the state of a cleared buffer -- and different for the iterations
+        // it - 2 and it - 4 that used the same buffer before
+        const long long htag = 1 + (long long)(itg % 3ULL);
         if (active) {
 #pragma unroll
             for (int u = 0; u < NP; u++) {
@@ -1294,12 +1299,15 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
             for (int u = 0; u < NP; u++) {
                     const double2 w = W[(size_t)(k - 1) * (N / 2) + el(u)];
                     double z0 = fma(sg, v[2 * u], w.x), z1 = fma(sg, v[2 * u + 1], w.y);
-                    if (TAGH && bwarp) { z0 = v3_tag(z0, (long long)(itg & 3)); z1 = v3_tag(z1, (long long)(itg & 3)); }
+                    if (TAGH && bwarp) { z0 = v3_tag(z0, htag); z1 = v3_tag(z1, htag); }
                     v[2 * u] = z0; v[2 * u + 1] = z1;
                     const double r0 = rr_[2 * u], r1 = rr_[2 * u + 1];
                     acc[1] += r0 * z0; acc[1] += r1 * z1;
                     acc[2] += z0 * z0; acc[2] += z1 * z1;
-                    if (TAGH) {                           // self-validating words: strong stores, no fence
+                    if (TAGH && MULTI) {                  // self-validating words: strong stores, no fence
+                        if (h0) asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(h0 + el(u)), "d"(z0), "d"(z1) : "memory");
+                        if (h1) asm volatile("st.relaxed.sys.global.v2.f64 [%0], {%1, %2};" ::"l"(h1 + el(u)), "d"(z0), "d"(z1) : "memory");
+                    } else if (TAGH) {
                         if (h0) asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(h0 + el(u)), "d"(z0), "d"(z1) : "memory");
                         if (h1) asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(h1 + el(u)), "d"(z0), "d"(z1) : "memory");
                     } else {
@@ -1354,20 +1362,29 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
         } else if (TAGH && k == 0) {
             // meanwhile: the neighbours' boundary z of this iteration, valid word by word once its tag matches
             const double2 *gu = hslice((int)(itg & 1), right, 0), *gl = hslice((int)(itg & 1), left, 1);
-            const long long tg = (long long)(itg & 3), t0 = clock64();
+            if (MULTI) {                                  // the slab's outer boundaries arrive in this rank's inbox
+                if (bid == nblk - 1) gu = inbox(C.rank, (int)(itg & 1), 1);
+                if (bid == 0) gl = inbox(C.rank, (int)(itg & 1), 0);
+            }
+            const long long tg = htag, t0 = clock64();
             constexpr int NH = N / 64;                    // double2 per lane and boundary slice
             long long q[2 * NH][2];
             while (true) {                                // all loads in flight, then the checks: one L2 round trip per attempt
 #pragma unroll
                 for (int u = 0; u < NH; u++) {
-                    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(q[u][0]), "=l"(q[u][1]) : "l"(gl + lane + 32 * u) : "memory");
-                    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(q[NH + u][0]), "=l"(q[NH + u][1]) : "l"(gu + lane + 32 * u) : "memory");
+                    if (MULTI) {
+                        asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(q[u][0]), "=l"(q[u][1]) : "l"(gl + lane + 32 * u) : "memory");
+                        asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(q[NH + u][0]), "=l"(q[NH + u][1]) : "l"(gu + lane + 32 * u) : "memory");
+                    } else {
+                        asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(q[u][0]), "=l"(q[u][1]) : "l"(gl + lane + 32 * u) : "memory");
+                        asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(q[NH + u][0]), "=l"(q[NH + u][1]) : "l"(gu + lane + 32 * u) : "memory");
+                    }
                 }
                 bool ready = true;
 #pragma unroll
                 for (int u = 0; u < 2 * NH; u++) ready = ready && (q[u][0] & 3LL) == tg && (q[u][1] & 3LL) == tg;
                 if (ready) break;
-                if (clock64() - t0 > 4000000000LL) { sh[5] = 1.0; break; }
+                if (clock64() - t0 > (MULTI ? 8000000000LL : 4000000000LL)) { sh[5] = 1.0; break; }
             }
 #pragma unroll
             for (int u = 0; u < NH; u++) {
@@ -1709,6 +1726,19 @@ bool fdm_v3_multi_possible(const sq_fdm *f) {
     int S;
     std::vector<int> c;
     return v3_multi_plan(f, &S, &c);
+}
+
+// Tagged boundary slices: clear this rank's boundary buffer and halo inbox so that no tag of an earlier solve validates.  Must be
+// enqueued BEFORE the collective that precedes the solve on this rank's stream (the peers start their kernels -- and write into this
+// inbox -- only after that collective, which needs this rank's part of it).
+void fdm_v3_multi_reset_boundaries(sq_fdm *f) {
+    int S;
+    std::vector<int> ctas;
+    if (!v3_multi_plan(f, &S, &ctas)) return;
+    const size_t nh = (size_t)8 * ctas[f->rank] * f->N;
+    if (f->v3_halo.n < nh) f->v3_halo.alloc(nh);
+    SQ_CUDA(cudaMemsetAsync(f->v3_halo.p, 0, f->v3_halo.n * sizeof(double), f->stream));
+    SQ_CUDA(cudaMemsetAsync((char *)f->mail_ptr[f->rank] + v3_mail_off_inbox(), 0, (size_t)8 * f->N * sizeof(double), f->stream));
 }
 
 // x (in/out), r (in): native order, own slab + the two halo slices of r valid.  state: normb / tol / eps0 set by the caller (global

@@ -291,6 +291,7 @@ __global__ void k_slab_roll(double *scal, double tol, int iter) {
 
 bool fdm_v3_multi_possible(const sq_fdm *f);
 bool fdm_v3_cg_resident1_multi(sq_fdm *f, double2 *x, double2 *r, CgState *state, i64 maxiter);
+void fdm_v3_multi_reset_boundaries(sq_fdm *f);
 void fdm_v3_prepare_native(sq_fdm *f);
 void fdm_v3_to_native(sq_fdm *f, double2 *dst, const double2 *src);
 void fdm_v3_from_native(sq_fdm *f, double2 *dst, const double2 *src);
@@ -328,6 +329,7 @@ static bool cg_slab_resident(sq_fdm *f, double2 *x, const double2 *b, bool zero_
     const double normb = std::sqrt(h[0]), eps0 = std::sqrt(h[1]) / normb;
     if (!(eps0 == eps0)) throw SqNumericalInstability("conjugate gradient (tau-slab): NaN encountered in the residual");
     if (eps0 < tol) { *iters = 0; *eps = eps0; return true; }
+    fdm_v3_multi_reset_boundaries(f);                          // (before the exchange below: see there)
     fdm_halo_exchange(f, r);                                   // p0 = r0 of the neighbours' boundary slices
     fdm_v3_prepare_native(f);
     fdm_v3_to_native(f, f->v3_r.p, r);
