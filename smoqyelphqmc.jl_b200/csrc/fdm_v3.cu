@@ -921,8 +921,9 @@ int fdm_v3_launch_cg(sq_fdm *f, double2 *z, const double2 *p_old, double2 *p_new
 // Grid-wide deterministic sum without atomics or a separate barrier: every CTA publishes (value, epoch) in its own 16-byte
 // slot (fence + relaxed store of the epoch), warp 0 of every CTA polls all slots for the epoch with relaxed loads that
 // bypass L1 and adds the values in a fixed order -- the same order in every CTA, so all CTAs get the same bits.  The
-// fence orders every earlier write of the CTA (cumulative through the preceding __syncthreads), so passing the sum also
-// publishes the boundary-r halo slices.  No L1 invalidation: shared data is only ever read with L2 loads.
+// fence orders every earlier write of the CTA (cumulative through the preceding __syncthreads).  This (value, epoch) form serves the
+// exact check at the end of a solve; the per-iteration sums use the fence-free tagged form below (v3_slot_sum2).  No L1 invalidation:
+// shared data is only ever read with L2 loads.
 struct V3Slot { double v; unsigned long long e; };
 // warp-level: `t` is this CTA's partial (same value in all lanes); publishes it and returns the grid total (all lanes).
 // One warp polls with up to 8 slots per lane in flight per round.  (Measured alternatives: every thread of the CTA polling
@@ -990,7 +991,9 @@ __device__ __forceinline__ double v3_grid_sum(double acc, double *red, double *s
 // sum, once per solve -- so the returned eps is exact and the solver never stops early.
 // Halo: with alpha and beta known to everybody, a CTA can update its copies of the neighbours' boundary r and p itself
 // if it knows their boundary z: r_h -= alpha z_h, p_h = r_h + beta p_h (the same fma's the owner executes: same bits).
-// So the boundary slices of z are stored before the sum -- its fence publishes them -- and read after it.
+// The boundary slices of z are stored before the sum and read after it (one GPU, slices above 256 sites: published by a device-scope
+// fence that an otherwise idle warp executes in parallel with the sum, then a per-CTA flag) or while it is in flight (several GPUs and
+// small slices: every word of the boundary carries a validity tag, no fence at all) -- see FLAGS / TAGH in the kernel.
 // The four partials travel as two 16-byte stores per CTA; the two low mantissa bits of every double carry the iteration
 // count mod 4 as validity tag (slot arrays alternate with the parity of the iteration), so one polling load returns two
 // values and their tag together.
@@ -1017,7 +1020,6 @@ struct CgResident1 {
     unsigned long long it_base;
     char *mail[8];
     size_t off_check, off_inbox;
-    size_t off_flags;           // boundary-z flags in the mailbox: +0 from the left rank, +128 from the right rank, +256 + 128 cta: own CTAs
 };
 
 __device__ __forceinline__ double v3_tag(double x, long long tag) { return __longlong_as_double((__double_as_longlong(x) & ~3LL) | tag); }
@@ -1177,7 +1179,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     // Single GPU: the device-scope fence that publishes the boundary z (>= 1000 cycles on this part) is executed by a warp that is
     // idle at that point -- the slice-less warp of part 1 -- in parallel with the (fence-free) grid-wide sum; it then raises this CTA's
     // flag to the iteration number, and the neighbours wait for the flag before they fetch the boundary z.
-    // Several GPUs: the same with a system-scope fence; the first / last CTA of a slab also raises a flag in the neighbour rank's mailbox.
+    // (One GPU, slices above 256 sites only: see TAGH below for everything else.)
     constexpr bool FLAGS = true;
     // Small slices (N <= 256, one GPU): no fence and no flag at all.  The boundary z carries the iteration tag in the two low mantissa bits of
     // every double (as the partial sums do) -- the owner rounds its boundary z to the tagged value BEFORE using it, so both sides compute
@@ -1189,9 +1191,7 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
     // Several GPUs: always -- a system-scope fence waits for the NVLink stores of the boundary to be acknowledged and the flag then crosses
     // the link once more: with tags the boundary is in the neighbour rank's inbox one link latency after the z phase, before the sum completes.
     constexpr bool TAGH = MULTI || G::N <= 256;
-    auto flag_of = [&](unsigned int cta) -> unsigned long long * {
-        return MULTI ? reinterpret_cast<unsigned long long *>(C.mail[C.rank] + C.off_flags + 256 + (size_t)cta * 128) : C.flags + (size_t)cta * 16;
-    };
+    auto flag_of = [&](unsigned int cta) -> unsigned long long * { return C.flags + (size_t)cta * 16; };
     const bool fwarp = FLAGS && !TAGH && part == 1 && k == 0, bwarp = FLAGS && owner && (k == 1 || k == ns);
     const bool sumw = TAGH ? (k == 1) : (wid < 2);       // the two warps that run the grid-wide sum: half 0 = (a, b), half 1 = (c, d)
     const int sumh = TAGH ? part : wid;
@@ -1333,15 +1333,8 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
             asm volatile("bar.arrive 4, %0;" ::"r"(tcnt) : "memory");       // (its own barrier id: this warp runs ahead of the others)
             asm volatile("bar.sync 3, %0;" ::"r"(fcnt) : "memory");
             if (lane == 0) {
-                if (MULTI) {
-                    asm volatile("fence.acq_rel.sys;" ::: "memory");
-                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(flag_of(bid)), "l"(itg) : "memory");
-                    if (bid == 0) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(C.mail[rank_l] + C.off_flags + 128), "l"(itg) : "memory");
-                    if (bid == nblk - 1) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(C.mail[rank_r] + C.off_flags), "l"(itg) : "memory");
-                } else {
-                    asm volatile("fence.acq_rel.gpu;" ::: "memory");
-                    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(flag_of(bid)), "l"(itg) : "memory");
-                }
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(flag_of(bid)), "l"(itg) : "memory");
             }
             __syncwarp();
         } else if (FLAGS) {
@@ -1427,22 +1420,15 @@ k_cg_v3_resident1(const __grid_constant__ V3Params P, const CgResident1 C) {
         static_assert(G::NV == N / 32, "one warp holds one slice-part");
         if (k == 0 && !TAGH) {
             const double2 *gu = hslice((int)(itg & 1), right, 0), *gl = hslice((int)(itg & 1), left, 1);
-            if (MULTI) {
-                if (bid == nblk - 1) gu = inbox(C.rank, (int)(itg & 1), 1);
-                if (bid == 0) gl = inbox(C.rank, (int)(itg & 1), 0);
-            }
             if (FLAGS) {                                  // the neighbours' boundary z of this iteration is visible once their flag says so
                 if (lane < 2) {
                     const unsigned long long *fl = flag_of(lane ? right : left);
-                    if (MULTI && lane == 0 && bid == 0) fl = reinterpret_cast<const unsigned long long *>(C.mail[C.rank] + C.off_flags);
-                    if (MULTI && lane == 1 && bid == nblk - 1) fl = reinterpret_cast<const unsigned long long *>(C.mail[C.rank] + C.off_flags + 128);
                     unsigned long long got;
                     const long long t0 = clock64();
                     while (true) {
-                        if (MULTI) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(fl) : "memory");
-                        else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(fl) : "memory");
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(got) : "l"(fl) : "memory");
                         if (got >= itg) break;
-                        if (clock64() - t0 > (MULTI ? 8000000000LL : 4000000000LL)) { sh[5] = 1.0; break; }
+                        if (clock64() - t0 > 4000000000LL) { sh[5] = 1.0; break; }
                     }
                 }
                 __syncwarp();
@@ -1700,8 +1686,7 @@ bool fdm_v3g_cg(sq_fdm *f, double2 *x, const double2 *r, bool zero_start, CgStat
 static const size_t V3_MAIL_STRIDE = 64, V3_MAIL_MAXCTA = 148 * 8;
 static size_t v3_mail_off_check() { return 2 * V3_MAIL_MAXCTA * V3_MAIL_STRIDE; }
 static size_t v3_mail_off_inbox() { return 3 * V3_MAIL_MAXCTA * V3_MAIL_STRIDE; }
-static size_t v3_mail_off_flags(const sq_fdm *f) { return v3_mail_off_inbox() + (size_t)8 * f->N * sizeof(double); }
-size_t fdm_v3_mailbox_bytes(const sq_fdm *f) { return v3_mail_off_flags(f) + 256 + (size_t)148 * 128; }
+size_t fdm_v3_mailbox_bytes(const sq_fdm *f) { return v3_mail_off_inbox() + (size_t)8 * f->N * sizeof(double); }
 
 // Can this slab configuration run the multi-GPU resident kernel?  Fills S and the CTA counts of all ranks.
 static bool v3_multi_plan(const sq_fdm *f, int *S_out, std::vector<int> *ctas) {
@@ -1770,7 +1755,7 @@ bool fdm_v3_cg_resident1_multi(sq_fdm *f, double2 *x, double2 *r, CgState *state
     C.world = f->world; C.rank = f->rank; C.gtot = 0; C.gid0 = 0;
     for (int q = 0; q < f->world; q++) { if (q < f->rank) C.gid0 += ctas[q]; C.gtot += ctas[q]; C.mail[q] = (char *)f->mail_ptr[q]; }
     C.it_base = f->v3_it_base;
-    C.off_check = v3_mail_off_check(); C.off_inbox = v3_mail_off_inbox(); C.off_flags = v3_mail_off_flags(f);
+    C.off_check = v3_mail_off_check(); C.off_inbox = v3_mail_off_inbox();
     void *args[] = {(void *)&P, (void *)&C};
     SQ_CUDA(cudaLaunchCooperativeKernel((const void *)k, dim3(grid), dim3(T), args, smem, f->stream));
     f->launches++;
